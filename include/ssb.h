@@ -1,0 +1,226 @@
+/* ssb.h — C-ABI of the B200-native backend for the two numeric hot paths of
+ * hridaybavle/semantic_slam.
+ *
+ * Plain C: opaque handles, plain pointers and sizes, int status codes (0/positive = ok, negative =
+ * error, text via ssb_last_error()).  No torch / Eigen / g2o / PCL types cross this boundary.
+ * Every entry point cites the reference interface (file:line under /root/reference) it replaces.
+ * Matrices are row-major.  SE3 values are 3x4 [R|t] (12 doubles), i.e. the top three rows of the
+ * Eigen::Isometry3d the reference passes.  A handle is not thread-safe (the reference drives these
+ * calls from a single thread, src/semantic_graph_SLAM_node.cpp:14-20); distinct handles are
+ * independent.
+ */
+#ifndef SSB_H
+#define SSB_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_OK 0
+#define SSB_ERR_INVALID (-1)  /* bad handle / id / argument            */
+#define SSB_ERR_CUDA (-2)     /* CUDA runtime error (see ssb_last_error) */
+#define SSB_ERR_NUMERIC (-3)  /* non-finite data reached the solver    */
+#define SSB_ERR_COMM (-4)     /* NCCL / multi-GPU set-up error         */
+
+/* ------------------------------------------------------------------------------------------- */
+/* Path (1): ps_graph_slam::GraphSLAM  (include/ps_graph_slam/graph_slam.hpp:27-150,           */
+/*           src/ps_graph_slam/graph_slam.cpp:40-239) — replaces g2o::SparseOptimizer "lm_var". */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct ssb_graph ssb_graph;
+
+typedef struct ssb_graph_opts {
+  int device;           /* CUDA device ordinal, -1 = current device                               */
+  int verbose;          /* graph_slam.cpp:41 verbose_                                             */
+  int max_pcg_iters;    /* cap on PCG iterations per damped solve (default 20000)                 */
+  double pcg_tol;       /* stop when sqrt(r'M^-1 r) <= pcg_tol * sqrt(r0'M^-1 r0) (default 1e-10)  */
+  int preconditioner;   /* 0 = block-Jacobi on the Schur complement; 1 = + rigid-body coarse level */
+  int coarse_group;     /* poses per coarse aggregate when preconditioner == 1 (default 32)        */
+  int reserved[4];
+} ssb_graph_opts;
+
+typedef struct ssb_lm_stats {
+  int iterations;        /* outer LM iterations performed (SparseOptimizer::optimize return)      */
+  int terminated;        /* 1 if the algorithm returned Terminate (10 failed trials or rho == 0)   */
+  int total_trials;      /* damped solves performed                                               */
+  int total_pcg_iters;   /* PCG iterations summed over all solves                                 */
+  double chi2_initial;   /* graph->chi2() before (graph_slam.cpp:202)                             */
+  double chi2_final;     /* graph->chi2() after  (graph_slam.cpp:212)                             */
+  double lambda_final;
+  double ms_prepare;     /* host CSR build + H2D upload                                           */
+  double ms_device;      /* CUDA-event time of the whole LM loop on the device                    */
+  double ms_total;       /* wall clock of the call                                                */
+  long long kernel_launches; /* kernels launched by this call                                     */
+} ssb_lm_stats;
+
+/* fills `o` with the defaults */
+void ssb_graph_default_opts(ssb_graph_opts* o);
+
+/* GraphSLAM::GraphSLAM(bool verbose)  graph_slam.cpp:40-97  (solver "lm_var", ParameterSE3Offset id 0
+ * = identity).  opts may be NULL.  Returns NULL on failure. */
+ssb_graph* ssb_graph_create(const ssb_graph_opts* opts);
+/* GraphSLAM::~GraphSLAM  graph_slam.cpp:102 */
+void ssb_graph_destroy(ssb_graph* g);
+
+/* GraphSLAM::add_se3_node  graph_slam.cpp:104-115.  Vertex id = number of vertices so far; the first
+ * vertex ever added is fixed (:109-111).  Returns the vertex id (>= 0) or an error. */
+int ssb_graph_add_se3_node(ssb_graph* g, const double T34[12]);
+/* GraphSLAM::add_point_xyz_node  graph_slam.cpp:127-134 */
+int ssb_graph_add_point_xyz_node(ssb_graph* g, const double xyz[3]);
+/* GraphSLAM::add_se3_edge  graph_slam.cpp:136-148 (g2o::EdgeSE3, measurement = relative pose,
+ * information 6x6).  Returns the edge id. */
+int ssb_graph_add_se3_edge(ssb_graph* g, int v1, int v2, const double Z34[12], const double info[36]);
+/* GraphSLAM::add_se3_point_xyz_edge  graph_slam.cpp:150-166 (g2o::EdgeSE3PointXYZ, parameter id 0,
+ * no robust kernel — the reference passes an uninitialised pointer). */
+int ssb_graph_add_se3_point_xyz_edge(ssb_graph* g, int v_se3, int v_xyz, const double xyz[3], const double info[9]);
+/* GraphSLAM::add_point_xyz_point_xyz_edge  graph_slam.cpp:168-180 (g2o::EdgePointXYZ; never called by
+ * the reference).  Accepted and stored; ssb_graph_optimize reports SSB_ERR_INVALID while such an edge
+ * exists (not supported by the Schur back-end in this round). */
+int ssb_graph_add_point_xyz_point_xyz_edge(ssb_graph* g, int v1, int v2, const double xyz[3], const double info[9]);
+
+int ssb_graph_num_vertices(const ssb_graph* g); /* graph->vertices().size() */
+int ssb_graph_num_edges(const ssb_graph* g);    /* graph->edges().size()    */
+
+/* VertexSE3::estimate() / VertexPointXYZ::estimate()  (semantic_graph_slam.cpp:94-95, data_association.h:378) */
+int ssb_graph_get_se3(ssb_graph* g, int vid, double T34[12]);
+int ssb_graph_get_point_xyz(ssb_graph* g, int vid, double xyz[3]);
+int ssb_graph_set_se3(ssb_graph* g, int vid, const double T34[12]);
+int ssb_graph_set_point_xyz(ssb_graph* g, int vid, const double xyz[3]);
+/* OptimizableGraph::Vertex::setFixed */
+int ssb_graph_set_fixed(ssb_graph* g, int vid, int fixed);
+/* OptimizableGraph::Vertex::hessianIndex(): position among the non-fixed vertices in id order, -1 if
+ * fixed (semantic_graph_slam.cpp:188-190).  Valid after an optimize call. */
+int ssb_graph_hessian_index(ssb_graph* g, int vid);
+/* bulk read-back: all SE3 estimates (12 doubles each, id order) and all XYZ estimates (3 each) */
+int ssb_graph_get_all(ssb_graph* g, double* se3_out, double* xyz_out);
+
+/* SparseOptimizer::chi2() at the current estimates (graph_slam.cpp:202,212) */
+int ssb_graph_chi2(ssb_graph* g, double* chi2_out);
+
+/* GraphSLAM::optimize  graph_slam.cpp:182-219:  returns 0 and does nothing when the graph has fewer
+ * than 10 edges (:184-186); otherwise initializeOptimization + optimize(max_iterations) (the reference
+ * passes 1024, :205) and returns 1.  Negative = error.  stats may be NULL. */
+int ssb_graph_optimize(ssb_graph* g, int max_iterations, ssb_lm_stats* stats);
+/* Splits of ssb_graph_optimize used by the benchmark and by incremental callers:
+ *   ssb_graph_prepare           : initializeOptimization analogue (graph_slam.cpp:199) — hessian indices, CSR
+ *                                 edge tables, H2D upload of whatever changed on the host.
+ *   ssb_graph_optimize_resident : the LM loop on the state already resident on the device (no upload, no
+ *                                 read-back of the estimates); requires ssb_graph_prepare.
+ *   ssb_graph_invalidate        : force the next prepare/optimize to rebuild and re-upload the edge tables.
+ *   ssb_graph_set_all           : bulk counterpart of ssb_graph_get_all. */
+int ssb_graph_prepare(ssb_graph* g);
+int ssb_graph_optimize_resident(ssb_graph* g, int max_iterations, ssb_lm_stats* stats);
+int ssb_graph_invalidate(ssb_graph* g);
+int ssb_graph_set_all(ssb_graph* g, const double* se3_in, const double* xyz_in);
+/* per-iteration records of the last optimize: 6 doubles each
+ * (chi2 before, chi2 after, lambda after, rho of last trial, trials, pcg iterations). Returns count. */
+int ssb_graph_get_history(ssb_graph* g, double* out6n, int cap);
+
+/* GraphSLAM::computeLandmarkMarginals  graph_slam.cpp:221-234 <- getAndSetLandmarkCov
+ * semantic_graph_slam.cpp:181-205: for each listed XYZ vertex the 3x3 block (H^-1)[v,v] of the last
+ * built (undamped) system.  out9n: n row-major 3x3 blocks.  Returns 1 on success, 0 if unavailable. */
+int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* out9n);
+
+/* GraphSLAM::save  graph_slam.cpp:236-239 (g2o text format: VERTEX_SE3:QUAT, VERTEX_TRACKXYZ,
+ * EDGE_SE3:QUAT, EDGE_SE3_TRACKXYZ, PARAMS_SE3OFFSET, FIX) and its inverse. */
+int ssb_graph_save_g2o(ssb_graph* g, const char* path);
+int ssb_graph_load_g2o(ssb_graph* g, const char* path);
+
+/* test hook: device linearisation of edge `eid` at the current estimates.  err[D], Ji[D*di], Jj[D*dj]
+ * row-major with (D,di,dj) = (6,6,6) for SE3 edges and (3,6,3) for SE3-XYZ edges. */
+int ssb_graph_edge_linearize(ssb_graph* g, int eid, double* err, double* Ji, double* Jj);
+/* test hook: solve (H + lambda I) x = b once at the current linearisation with the Schur/PCG device
+ * path; x is returned in hessian-index order (6 per SE3, 3 per XYZ vertex).  Returns PCG iterations. */
+int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len);
+
+/* multi-GPU (one process per GPU): attach an NCCL communicator built from `unique_id` (128 bytes from
+ * ssb_comm_unique_id on rank 0, broadcast by the host).  The graph is then sharded by contiguous
+ * keyframe range inside ssb_graph_optimize.  world == 1 detaches. */
+int ssb_comm_unique_id(unsigned char id_out[128]);
+int ssb_graph_attach_comm(ssb_graph* g, int rank, int world, const unsigned char unique_id[128]);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Path (2): planar_segmentation RANSAC plane fit on bbox-cropped depth clouds                  */
+/*   plane_segmentation::segmentPointCloudData  src/planar_segmentation/plane_segmentation.cpp:24-82 */
+/*   plane_segmentation::compute2DConvexHull -> pcl::SACSegmentation::segment  :631-647          */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct ssb_cloud_layout {     /* sensor_msgs::PointCloud2 fields used at :44-61 */
+  int width, height;                  /* 640 x 480 (:35)                               */
+  int point_step, row_step;           /* bytes                                         */
+  int off_x, off_y, off_z, off_rgb;   /* fields[0..3].offset                           */
+} ssb_cloud_layout;
+
+typedef struct ssb_bbox {             /* msg/ObjectInfo.msg:3-6 */
+  int tl_x, tl_y, width, height;
+} ssb_bbox;
+
+typedef struct ssb_ransac_opts {
+  double threshold;      /* seg.setDistanceThreshold(0.01)  :645                                */
+  int refine;            /* seg.setOptimizeCoefficients(true) :641                              */
+  int mode;              /* 0 = fixed-K (score every hypothesis), 1 = PCL adaptive-k replay      */
+  int max_iterations;    /* PCL default 50 (mode 1)                                             */
+  double probability;    /* PCL default 0.99 (mode 1)                                           */
+  int device;            /* CUDA device ordinal, -1 = current                                   */
+  int reserved[3];
+} ssb_ransac_opts;
+
+typedef struct ssb_plane_result {
+  int status;            /* 0 ok, 1 "spurious" bbox (:34-38), 2 no valid model                  */
+  int n_points;          /* width*height of the crop                                            */
+  int best_hyp;          /* winning hypothesis (first best, PCL keeps strictly-better only)     */
+  int best_count;        /* its inlier count                                                    */
+  int iterations;        /* hypotheses consumed                                                 */
+  int refined_count;     /* inliers of the refined model (selectWithinDistance)                 */
+  float coef[4];         /* winning 3-point model (a,b,c,d)                                     */
+  float refined[4];      /* after optimizeModelCoefficients                                     */
+} ssb_plane_result;
+
+typedef struct ssb_ransac ssb_ransac;   /* persistent device buffers + stream */
+
+void ssb_ransac_default_opts(ssb_ransac_opts* o);
+ssb_ransac* ssb_ransac_create(int device);
+void ssb_ransac_destroy(ssb_ransac* r);
+
+/* Crops every bbox out of the PointCloud2 byte buffer (K6), scores `n_hyp` 3-point plane hypotheses
+ * per crop given as index triples into the row-major crop (K7), refines the winner by PCA over its
+ * inliers and re-selects inliers (K8).
+ *   msg      : host pointer to PointCloud2.data (height*row_step bytes)
+ *   triples  : host int32 [n_boxes][n_hyp][3]
+ *   results  : host [n_boxes]
+ *   counts   : host int32 [n_boxes][n_hyp] inlier count per hypothesis (-1 = not evaluated), may be NULL
+ *   mask     : host uint8, concatenation over non-spurious boxes of the refined inlier mask, may be NULL
+ * Returns SSB_OK or an error. */
+int ssb_ransac_plane_batch(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout, const ssb_bbox* boxes,
+                           int n_boxes, const int* triples, int n_hyp, const ssb_ransac_opts* opts,
+                           ssb_plane_result* results, int* counts, unsigned char* mask);
+
+/* Device-resident variant used for the `value` leg of the benchmark: cloud and triples are uploaded
+ * once with ssb_ransac_upload, then ssb_ransac_run_resident re-runs crop + score + refine on the device
+ * without host traffic (results stay on the device until ssb_ransac_fetch). */
+int ssb_ransac_upload(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout, const ssb_bbox* boxes,
+                      int n_boxes, const int* triples, int n_hyp, const ssb_ransac_opts* opts);
+int ssb_ransac_run_resident(ssb_ransac* r);
+int ssb_ransac_fetch(ssb_ransac* r, ssb_plane_result* results, int* counts, unsigned char* mask);
+/* CUDA stream the handle launches on (for event timing by the caller), as an opaque pointer */
+void* ssb_ransac_stream(ssb_ransac* r);
+/* number of kernels launched so far on this handle */
+long long ssb_ransac_launch_count(ssb_ransac* r);
+
+/* plane_segmentation::segmentPointCloudData alone (K6): out = n x 4 floats (x,y,z,rgb), row-major
+ * organised crop.  Returns n = width*height, or -1 for a spurious box. */
+int ssb_crop_bbox(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout, const ssb_bbox* box, float* out);
+
+/* ------------------------------------------------------------------------------------------- */
+const char* ssb_last_error(void);
+/* "sm_100a" build tag, CUDA runtime version */
+const char* ssb_build_info(void);
+/* CUDA stream of a graph handle (opaque cudaStream_t) for caller-side event timing */
+void* ssb_graph_stream(ssb_graph* g);
+/* device-resident benchmark helpers: snapshot the current estimates on the device / restore them,
+ * so repeated optimize() calls start from the same state without host traffic */
+int ssb_graph_snapshot(ssb_graph* g);
+int ssb_graph_restore(ssb_graph* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSB_H */

@@ -1,0 +1,298 @@
+"""ORACLE — test infrastructure only (ctypes bindings of oracle/liboracle.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this package; the
+product package (semantic_slam_b200) never does.  See oracle/oracle_graph.cpp and
+oracle/oracle_ransac.cpp for the reference file:line each function follows.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_fp = C.POINTER(C.c_float)
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_graph.cpp", "oracle_ransac.cpp")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.orc_graph_create.restype = C.c_void_p
+        L.orc_graph_destroy.argtypes = [C.c_void_p]
+        L.orc_graph_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.orc_graph_add_se3_node.argtypes = [C.c_void_p, _dp]
+        L.orc_graph_add_point_xyz_node.argtypes = [C.c_void_p, _dp]
+        L.orc_graph_add_se3_edge.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
+        L.orc_graph_add_se3_point_xyz_edge.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
+        L.orc_graph_add_point_xyz_point_xyz_edge.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
+        L.orc_graph_num_vertices.argtypes = [C.c_void_p]
+        L.orc_graph_num_edges.argtypes = [C.c_void_p]
+        L.orc_graph_get_se3.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.orc_graph_set_se3.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.orc_graph_get_point_xyz.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.orc_graph_set_point_xyz.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.orc_graph_set_fixed.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_graph_get_all.argtypes = [C.c_void_p, _dp, _dp]
+        L.orc_graph_chi2.argtypes = [C.c_void_p]
+        L.orc_graph_chi2.restype = C.c_double
+        L.orc_graph_optimize.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, C.c_int]
+        L.orc_graph_last_stats.argtypes = [C.c_void_p, _dp]
+        L.orc_graph_edge_linearize.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+        L.orc_graph_dense_system.argtypes = [C.c_void_p, _dp, _dp, _ip]
+        L.orc_graph_sparse_system.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, _ip]
+        L.orc_graph_sparse_system.restype = C.c_longlong
+        L.orc_graph_num_scalar.argtypes = [C.c_void_p]
+        L.orc_graph_solve_once.argtypes = [C.c_void_p, C.c_double, _dp]
+        L.orc_graph_landmark_marginals.argtypes = [C.c_void_p, _ip, C.c_int, _dp, C.c_int]
+        L.orc_to_vector_mqt.argtypes = [_dp, _dp]
+        L.orc_from_vector_mqt.argtypes = [_dp, _dp]
+        L.orc_se3_oplus.argtypes = [_dp, _dp, _dp]
+        L.orc_ransac_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, _ip, C.c_int,
+                                       C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+        L.orc_ransac_batch.restype = C.c_int
+        L.orc_crop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _fp]
+        L.orc_crop.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+class OracleGraphSLAM:
+    """Same call surface as ps_graph_slam::GraphSLAM (graph_slam.hpp:27-150), CPU oracle behind it."""
+
+    def __init__(self, verbose: bool = False, threads: int = 1):
+        self._L = lib()
+        self._h = C.c_void_p(self._L.orc_graph_create())
+        self._L.orc_graph_set_threads(self._h, threads)
+        self.verbose_ = verbose
+        self.history = None
+        self.iterations = 0
+        self.terminated = False
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_graph_destroy(self._h)
+            self._h = None
+
+    def add_se3_node(self, pose34):
+        a, p = _d(pose34)
+        return self._L.orc_graph_add_se3_node(self._h, p)
+
+    def add_point_xyz_node(self, xyz):
+        a, p = _d(xyz)
+        return self._L.orc_graph_add_point_xyz_node(self._h, p)
+
+    def add_se3_edge(self, v1, v2, relative_pose34, information):
+        a, p = _d(relative_pose34)
+        b, q = _d(information)
+        r = self._L.orc_graph_add_se3_edge(self._h, v1, v2, p, q)
+        if r < 0:
+            raise ValueError("bad vertex ids")
+        return r
+
+    def add_se3_point_xyz_edge(self, v_se3, v_xyz, xyz, information):
+        a, p = _d(xyz)
+        b, q = _d(information)
+        r = self._L.orc_graph_add_se3_point_xyz_edge(self._h, v_se3, v_xyz, p, q)
+        if r < 0:
+            raise ValueError("bad vertex ids")
+        return r
+
+    def add_point_xyz_point_xyz_edge(self, v1, v2, xyz, information):
+        a, p = _d(xyz)
+        b, q = _d(information)
+        r = self._L.orc_graph_add_point_xyz_point_xyz_edge(self._h, v1, v2, p, q)
+        if r < 0:
+            raise ValueError("bad vertex ids")
+        return r
+
+    def num_vertices(self):
+        return self._L.orc_graph_num_vertices(self._h)
+
+    def num_edges(self):
+        return self._L.orc_graph_num_edges(self._h)
+
+    def optimize(self, max_iterations: int = 1024) -> bool:
+        it = C.c_int(0)
+        term = C.c_int(0)
+        hist = np.zeros((max(max_iterations, 1), 5))
+        r = self._L.orc_graph_optimize(self._h, max_iterations, C.byref(it), C.byref(term),
+                                       hist.ctypes.data_as(_dp), hist.shape[0])
+        self.iterations = it.value
+        self.terminated = bool(term.value)
+        self.history = hist[: max(it.value, 0)]
+        return bool(r)
+
+    def chi2(self) -> float:
+        return self._L.orc_graph_chi2(self._h)
+
+    def get_se3(self, vid):
+        out = np.zeros((3, 4))
+        if self._L.orc_graph_get_se3(self._h, vid, out.ctypes.data_as(_dp)) != 0:
+            raise ValueError("not an SE3 vertex")
+        return out
+
+    def get_point_xyz(self, vid):
+        out = np.zeros(3)
+        if self._L.orc_graph_get_point_xyz(self._h, vid, out.ctypes.data_as(_dp)) != 0:
+            raise ValueError("not an XYZ vertex")
+        return out
+
+    def set_se3(self, vid, T):
+        a, p = _d(T)
+        self._L.orc_graph_set_se3(self._h, vid, p)
+
+    def set_point_xyz(self, vid, x):
+        a, p = _d(x)
+        self._L.orc_graph_set_point_xyz(self._h, vid, p)
+
+    def get_all(self, n_se3, n_xyz):
+        a = np.zeros((n_se3, 3, 4))
+        b = np.zeros((max(n_xyz, 1), 3))
+        self._L.orc_graph_get_all(self._h, a.ctypes.data_as(_dp), b.ctypes.data_as(_dp))
+        return a, b[:n_xyz]
+
+    def last_stats(self):
+        out = np.zeros(5)
+        self._L.orc_graph_last_stats(self._h, out.ctypes.data_as(_dp))
+        return dict(analyze_ms=out[0], factor_ms=out[1], linearize_ms=out[2], nnzL=int(out[3]), n=int(out[4]))
+
+    def computeLandmarkMarginals(self, vids, relinearize=False):
+        vids = np.ascontiguousarray(vids, dtype=np.int32)
+        out = np.zeros((vids.size, 3, 3))
+        r = self._L.orc_graph_landmark_marginals(self._h, vids.ctypes.data_as(_ip), vids.size,
+                                                 out.ctypes.data_as(_dp), int(relinearize))
+        if r != 1:
+            raise RuntimeError("marginals failed")
+        return out
+
+    # ---- test hooks ----
+    def edge_linearize(self, eid, D, di, dj):
+        err = np.zeros(6)
+        Ji = np.zeros(36)
+        Jj = np.zeros(36)
+        self._L.orc_graph_edge_linearize(self._h, eid, err.ctypes.data_as(_dp), Ji.ctypes.data_as(_dp),
+                                         Jj.ctypes.data_as(_dp))
+        return err[:D].copy(), Ji[: D * di].reshape(D, di).copy(), Jj[: D * dj].reshape(D, dj).copy()
+
+    def dense_system(self):
+        nv = self.num_vertices()
+        off = np.zeros(nv, dtype=np.int32)
+        n = self._L.orc_graph_dense_system(self._h, None, None, off.ctypes.data_as(_ip))
+        H = np.zeros((n, n))
+        b = np.zeros(n)
+        self._L.orc_graph_dense_system(self._h, H.ctypes.data_as(_dp), b.ctypes.data_as(_dp), off.ctypes.data_as(_ip))
+        return H, b, off
+
+    def sparse_system(self):
+        """(H as scipy.sparse CSR full symmetric, b, scalar offset per vertex)"""
+        import scipy.sparse as sp
+        nv = self.num_vertices()
+        off = np.zeros(nv, dtype=np.int32)
+        nnz = self._L.orc_graph_sparse_system(self._h, None, None, None, None, off.ctypes.data_as(_ip))
+        n = self._L.orc_graph_num_scalar(self._h)
+        r = np.zeros(nnz, dtype=np.int32)
+        c = np.zeros(nnz, dtype=np.int32)
+        v = np.zeros(nnz)
+        b = np.zeros(n)
+        self._L.orc_graph_sparse_system(self._h, r.ctypes.data_as(_ip), c.ctypes.data_as(_ip), v.ctypes.data_as(_dp),
+                                        b.ctypes.data_as(_dp), off.ctypes.data_as(_ip))
+        U = sp.coo_matrix((v, (r, c)), shape=(n, n)).tocsr()
+        U.eliminate_zeros()
+        Hfull = U + sp.triu(U, k=1).T
+        return Hfull.tocsr(), b, off
+
+    def solve_once(self, lam):
+        n = self._L.orc_graph_dense_system(self._h, None, None, None)
+        x = np.zeros(n)
+        ok = self._L.orc_graph_solve_once(self._h, float(lam), x.ctypes.data_as(_dp))
+        return bool(ok), x
+
+
+def to_vector_mqt(T):
+    a, p = _d(T)
+    v = np.zeros(6)
+    lib().orc_to_vector_mqt(p, v.ctypes.data_as(_dp))
+    return v
+
+
+def from_vector_mqt(v):
+    a, p = _d(v)
+    T = np.zeros((3, 4))
+    lib().orc_from_vector_mqt(p, T.ctypes.data_as(_dp))
+    return T
+
+
+def se3_oplus(T, v):
+    a, p = _d(T)
+    b, q = _d(v)
+    out = np.zeros((3, 4))
+    lib().orc_se3_oplus(p, q, out.ctypes.data_as(_dp))
+    return out
+
+
+PLANE_RESULT_DTYPE = np.dtype([("status", "i4"), ("n_points", "i4"), ("best_hyp", "i4"), ("best_count", "i4"),
+                               ("iterations", "i4"), ("refined_count", "i4"), ("coef", "f4", 4), ("refined", "f4", 4)])
+
+
+def crop(msg, width, height, point_step, row_step, offsets, box):
+    """plane_segmentation::segmentPointCloudData restated. Returns (h, w, 4) float32 or None if spurious."""
+    msg = np.ascontiguousarray(msg, dtype=np.uint8)
+    off = np.ascontiguousarray(offsets, dtype=np.int32)
+    bx = np.ascontiguousarray(box, dtype=np.int32)
+    n = lib().orc_crop(msg.ctypes.data, width, height, point_step, row_step, off.ctypes.data_as(_ip),
+                       bx.ctypes.data_as(_ip), None)
+    if n < 0:
+        return None
+    out = np.zeros((int(bx[3]), int(bx[2]), 4), dtype=np.float32)
+    lib().orc_crop(msg.ctypes.data, width, height, point_step, row_step, off.ctypes.data_as(_ip),
+                   bx.ctypes.data_as(_ip), out.ctypes.data_as(_fp))
+    return out
+
+
+def ransac_plane_batch(msg, width, height, point_step, row_step, offsets, boxes, triples, threshold=0.01,
+                       refine=True, mode=0, max_iterations=50, probability=0.99, want_counts=True, want_mask=True):
+    """pcl::SACSegmentation(SACMODEL_PLANE, SAC_RANSAC) over every bbox crop, restated on the CPU.
+    Returns (results[nb] structured array, counts[nb,K] or None, mask (concatenated uint8) or None)."""
+    msg = np.ascontiguousarray(msg, dtype=np.uint8)
+    off = np.ascontiguousarray(offsets, dtype=np.int32)
+    boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 4)
+    triples = np.ascontiguousarray(triples, dtype=np.int32)
+    nb = boxes.shape[0]
+    K = triples.shape[1] if nb else 0
+    res = np.zeros(nb, dtype=PLANE_RESULT_DTYPE)
+    counts = np.zeros((nb, K), dtype=np.int32) if want_counts else None
+    valid = (boxes[:, 2] >= 0) & (boxes[:, 3] >= 0) & (boxes[:, 0] >= 0) & (boxes[:, 1] >= 0) & \
+            (boxes[:, 0] + boxes[:, 2] <= width) & (boxes[:, 1] + boxes[:, 3] <= height)
+    total = int((boxes[valid, 2].astype(np.int64) * boxes[valid, 3]).sum())
+    mask = np.zeros(max(total, 1), dtype=np.uint8) if want_mask else None
+    r = lib().orc_ransac_batch(msg.ctypes.data, width, height, point_step, row_step, off.ctypes.data_as(_ip),
+                               boxes.ctypes.data_as(_ip), nb, triples.ctypes.data_as(_ip), K, float(threshold),
+                               int(refine), int(mode), int(max_iterations), float(probability), res.ctypes.data,
+                               counts.ctypes.data if counts is not None else None,
+                               mask.ctypes.data if mask is not None else None)
+    if r != 0:
+        raise RuntimeError("oracle ransac failed")
+    return res, counts, (mask[:total] if mask is not None else None)

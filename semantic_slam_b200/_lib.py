@@ -1,0 +1,137 @@
+"""ctypes loader of semantic_slam_b200/libssb.so (the C-ABI of include/ssb.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libssb.so")
+_LIB = None
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+class SsbError(RuntimeError):
+    pass
+
+
+class GraphOpts(C.Structure):
+    _fields_ = [("device", C.c_int), ("verbose", C.c_int), ("max_pcg_iters", C.c_int), ("pcg_tol", C.c_double),
+                ("preconditioner", C.c_int), ("coarse_group", C.c_int), ("reserved", C.c_int * 4)]
+
+
+class LmStats(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("terminated", C.c_int), ("total_trials", C.c_int),
+                ("total_pcg_iters", C.c_int), ("chi2_initial", C.c_double), ("chi2_final", C.c_double),
+                ("lambda_final", C.c_double), ("ms_prepare", C.c_double), ("ms_device", C.c_double),
+                ("ms_total", C.c_double), ("kernel_launches", C.c_longlong)]
+
+
+class CloudLayoutC(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("point_step", C.c_int), ("row_step", C.c_int),
+                ("off_x", C.c_int), ("off_y", C.c_int), ("off_z", C.c_int), ("off_rgb", C.c_int)]
+
+
+class RansacOpts(C.Structure):
+    _fields_ = [("threshold", C.c_double), ("refine", C.c_int), ("mode", C.c_int), ("max_iterations", C.c_int),
+                ("probability", C.c_double), ("device", C.c_int), ("reserved", C.c_int * 3)]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libssb.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-s"]
+    subprocess.check_call(cmd)
+    return _SO
+
+
+# every symbol include/ssb.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "ssb_graph_default_opts", "ssb_graph_create", "ssb_graph_destroy", "ssb_graph_add_se3_node",
+    "ssb_graph_add_point_xyz_node", "ssb_graph_add_se3_edge", "ssb_graph_add_se3_point_xyz_edge",
+    "ssb_graph_add_point_xyz_point_xyz_edge", "ssb_graph_num_vertices", "ssb_graph_num_edges", "ssb_graph_get_se3",
+    "ssb_graph_get_point_xyz", "ssb_graph_set_se3", "ssb_graph_set_point_xyz", "ssb_graph_set_fixed",
+    "ssb_graph_hessian_index", "ssb_graph_get_all", "ssb_graph_set_all", "ssb_graph_invalidate", "ssb_graph_chi2",
+    "ssb_graph_prepare", "ssb_graph_optimize", "ssb_graph_optimize_resident", "ssb_graph_get_history",
+    "ssb_graph_landmark_marginals", "ssb_graph_save_g2o", "ssb_graph_load_g2o", "ssb_graph_edge_linearize",
+    "ssb_graph_solve_once", "ssb_comm_unique_id", "ssb_graph_attach_comm", "ssb_ransac_default_opts",
+    "ssb_ransac_create", "ssb_ransac_destroy", "ssb_ransac_plane_batch", "ssb_ransac_upload",
+    "ssb_ransac_run_resident", "ssb_ransac_fetch", "ssb_ransac_stream", "ssb_ransac_launch_count", "ssb_crop_bbox",
+    "ssb_last_error", "ssb_build_info", "ssb_graph_stream", "ssb_graph_snapshot", "ssb_graph_restore",
+]
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_SO):
+        raise SsbError(f"{_SO} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+                       "g.build()'); there is no CPU fallback")
+    L = C.CDLL(_SO)
+    vp = C.c_void_p
+    L.ssb_last_error.restype = C.c_char_p
+    L.ssb_build_info.restype = C.c_char_p
+    L.ssb_graph_default_opts.argtypes = [C.POINTER(GraphOpts)]
+    L.ssb_graph_create.argtypes = [C.POINTER(GraphOpts)]
+    L.ssb_graph_create.restype = vp
+    L.ssb_graph_destroy.argtypes = [vp]
+    L.ssb_graph_add_se3_node.argtypes = [vp, dp]
+    L.ssb_graph_add_point_xyz_node.argtypes = [vp, dp]
+    L.ssb_graph_add_se3_edge.argtypes = [vp, C.c_int, C.c_int, dp, dp]
+    L.ssb_graph_add_se3_point_xyz_edge.argtypes = [vp, C.c_int, C.c_int, dp, dp]
+    L.ssb_graph_add_point_xyz_point_xyz_edge.argtypes = [vp, C.c_int, C.c_int, dp, dp]
+    L.ssb_graph_num_vertices.argtypes = [vp]
+    L.ssb_graph_num_edges.argtypes = [vp]
+    L.ssb_graph_get_se3.argtypes = [vp, C.c_int, dp]
+    L.ssb_graph_get_point_xyz.argtypes = [vp, C.c_int, dp]
+    L.ssb_graph_set_se3.argtypes = [vp, C.c_int, dp]
+    L.ssb_graph_set_point_xyz.argtypes = [vp, C.c_int, dp]
+    L.ssb_graph_set_fixed.argtypes = [vp, C.c_int, C.c_int]
+    L.ssb_graph_hessian_index.argtypes = [vp, C.c_int]
+    L.ssb_graph_get_all.argtypes = [vp, dp, dp]
+    L.ssb_graph_set_all.argtypes = [vp, dp, dp]
+    L.ssb_graph_invalidate.argtypes = [vp]
+    L.ssb_graph_chi2.argtypes = [vp, dp]
+    L.ssb_graph_prepare.argtypes = [vp]
+    L.ssb_graph_optimize.argtypes = [vp, C.c_int, C.POINTER(LmStats)]
+    L.ssb_graph_optimize_resident.argtypes = [vp, C.c_int, C.POINTER(LmStats)]
+    L.ssb_graph_get_history.argtypes = [vp, dp, C.c_int]
+    L.ssb_graph_landmark_marginals.argtypes = [vp, ip, C.c_int, dp]
+    L.ssb_graph_save_g2o.argtypes = [vp, C.c_char_p]
+    L.ssb_graph_load_g2o.argtypes = [vp, C.c_char_p]
+    L.ssb_graph_edge_linearize.argtypes = [vp, C.c_int, dp, dp, dp]
+    L.ssb_graph_solve_once.argtypes = [vp, C.c_double, dp, C.c_int]
+    L.ssb_graph_stream.argtypes = [vp]
+    L.ssb_graph_stream.restype = vp
+    L.ssb_graph_snapshot.argtypes = [vp]
+    L.ssb_graph_restore.argtypes = [vp]
+    L.ssb_comm_unique_id.argtypes = [C.c_char_p]
+    L.ssb_graph_attach_comm.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.ssb_ransac_default_opts.argtypes = [C.POINTER(RansacOpts)]
+    L.ssb_ransac_create.argtypes = [C.c_int]
+    L.ssb_ransac_create.restype = vp
+    L.ssb_ransac_destroy.argtypes = [vp]
+    L.ssb_ransac_plane_batch.argtypes = [vp, vp, C.POINTER(CloudLayoutC), vp, C.c_int, vp, C.c_int,
+                                         C.POINTER(RansacOpts), vp, vp, vp]
+    L.ssb_ransac_upload.argtypes = [vp, vp, C.POINTER(CloudLayoutC), vp, C.c_int, vp, C.c_int, C.POINTER(RansacOpts)]
+    L.ssb_ransac_run_resident.argtypes = [vp]
+    L.ssb_ransac_fetch.argtypes = [vp, vp, vp, vp]
+    L.ssb_ransac_stream.argtypes = [vp]
+    L.ssb_ransac_stream.restype = vp
+    L.ssb_ransac_launch_count.argtypes = [vp]
+    L.ssb_ransac_launch_count.restype = C.c_longlong
+    L.ssb_crop_bbox.argtypes = [vp, vp, C.POINTER(CloudLayoutC), vp, vp]
+    _LIB = L
+    return L
+
+
+def last_error() -> str:
+    return lib().ssb_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str):
+    if rc < 0:
+        raise SsbError(f"{what} failed ({rc}): {last_error()}")
+    return rc

@@ -1,0 +1,1035 @@
+// ssb_graph.cu — host side of the graph hot path behind the C-ABI of include/ssb.h:
+// graph container mirroring ps_graph_slam::GraphSLAM (graph_slam.cpp:40-239), CSR edge-table
+// construction, and the Levenberg-Marquardt driver that restates g2o's
+// OptimizationAlgorithmLevenberg::solve on top of the sm_100a kernels in
+// ssb_graph_kernels.cuh (fused linearise / Schur / block-Jacobi PCG / update / chi2).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/ssb.h"
+#include "ssb_graph_kernels.cuh"
+
+namespace ssb {
+
+thread_local std::string g_last_error;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap && p) return SSB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max<size_t>(n, 1);
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+      return SSB_ERR_CUDA;
+    }
+    cap = want;
+    return SSB_OK;
+  }
+  ~DBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+static inline double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+enum { VK_SE3 = 0, VK_XYZ = 1 };
+enum { EK_PP = 0, EK_PL = 1, EK_LL = 2 };
+
+struct HostVertex {
+  int kind;
+  int idx;  // index into poses / landmarks
+  bool fixed;
+  int hidx;
+};
+struct HostEdgeRef {
+  int kind;
+  int idx;
+};
+struct LLEdge {
+  int a, b;
+  double z[3];
+  double info[9];
+};
+
+}  // namespace ssb
+
+using namespace ssb;
+
+struct ssb_graph {
+  ssb_graph_opts opts;
+  // host graph (authoritative for structure; estimates mirrored, see est_on_device)
+  std::vector<HostVertex> V;
+  std::vector<HostEdgeRef> E;
+  std::vector<Pose> poses;      // estimates, pose index order
+  std::vector<double> lms;      // 4 per landmark
+  std::vector<int> pose_vid, lm_vid;
+  std::vector<PPEdge> pp;       // creation order
+  std::vector<PLEdge> pl;       // creation order (host); device copy is L-order
+  std::vector<int> pl_full_info_sym;  // unused
+  std::vector<LLEdge> ll;
+  std::vector<int> plL_of_edge;  // creation index -> L-order position
+  bool structure_dirty = true;
+  bool host_est_dirty = true;    // host estimates changed since last upload
+  bool device_est_newer = false; // device estimates not yet copied back
+  bool have_system = false;      // a linearised system (H, b) is resident
+  bool have_snapshot = false;
+  int device = 0;
+  int num_sms = 0;
+  int pcg_grid = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // device buffers
+  DBuf<Pose> d_pose, d_pose_bak, d_pose_snap;
+  DBuf<double> d_lm, d_lm_bak, d_lm_snap;
+  DBuf<unsigned char> d_pose_fixed, d_lm_fixed;
+  DBuf<PLEdge> d_pl;
+  DBuf<PPEdge> d_pp;
+  DBuf<int> d_lm_rowptr, d_pose_pl_rowptr, d_pose_pl_idx, d_pose_pp_rowptr, d_pose_pp_idx, d_plP_lm;
+  DBuf<double> d_Hpp, d_bp, d_Hoff, d_Hll, d_bl, d_HplL, d_HplP, d_HllInv, d_Dinv, d_g;
+  DBuf<double> d_x, d_r, d_z, d_p0, d_p1, d_q, d_v, d_dl, d_part, d_scalars, d_tmp;
+  DBuf<int> d_iscalars;
+  double* h_scalars = nullptr;  // pinned: 8 doubles
+  int* h_iscalars = nullptr;    // pinned: 4 ints
+  DevGraph G;
+  std::vector<double> history;  // 6 per iteration
+  long long launches = 0;
+  int comm_rank = 0, comm_world = 1;
+};
+
+static int check_vertex(const ssb_graph* g, int id, int kind) {
+  return g && id >= 0 && id < (int)g->V.size() && g->V[id].kind == kind;
+}
+
+static void pose_from_34(const double* T, Pose& P) {
+  double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+  R_to_quat(R, P.q);
+  P.t[0] = T[3];
+  P.t[1] = T[7];
+  P.t[2] = T[11];
+  P.pad = 0.0;
+}
+static void pose_to_34(const Pose& P, double* T) {
+  double R[9];
+  quat_to_R(P.q, R);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) T[4 * r + c] = R[3 * r + c];
+    T[4 * r + 3] = P.t[r];
+  }
+}
+
+extern "C" {
+
+const char* ssb_last_error(void) { return g_last_error.c_str(); }
+#define SSB_STR2(x) #x
+#define SSB_STR(x) SSB_STR2(x)
+const char* ssb_build_info(void) {
+  return "semantic_slam_b200 libssb: sm_100a, CUDA " SSB_STR(__CUDACC_VER_MAJOR__) "." SSB_STR(__CUDACC_VER_MINOR__);
+}
+
+void ssb_graph_default_opts(ssb_graph_opts* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->device = -1;
+  o->verbose = 0;
+  o->max_pcg_iters = 20000;
+  o->pcg_tol = 1e-10;
+  o->preconditioner = 0;
+  o->coarse_group = 32;
+}
+
+ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
+  ssb_graph* g = new ssb_graph();
+  if (opts)
+    g->opts = *opts;
+  else
+    ssb_graph_default_opts(&g->opts);
+  if (g->opts.max_pcg_iters <= 0) g->opts.max_pcg_iters = 20000;
+  if (!(g->opts.pcg_tol > 0)) g->opts.pcg_tol = 1e-10;
+  int dev = g->opts.device;
+  cudaError_t e;
+  if (dev < 0) {
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+      set_error("no CUDA device: %s (the CUDA back-end has no CPU fallback)", cudaGetErrorString(e));
+      delete g;
+      return nullptr;
+    }
+  }
+  e = cudaSetDevice(dev);
+  if (e != cudaSuccess) {
+    set_error("cudaSetDevice(%d) failed: %s (the CUDA back-end has no CPU fallback)", dev, cudaGetErrorString(e));
+    delete g;
+    return nullptr;
+  }
+  g->device = dev;
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties failed: %s", cudaGetErrorString(e));
+    delete g;
+    return nullptr;
+  }
+  g->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess ||
+      cudaMallocHost((void**)&g->h_scalars, 8 * sizeof(double)) != cudaSuccess ||
+      cudaMallocHost((void**)&g->h_iscalars, 4 * sizeof(int)) != cudaSuccess) {
+    set_error("CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete g;
+    return nullptr;
+  }
+  int nb = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg, 1024, 0);
+  if (e != cudaSuccess || nb < 1) {
+    set_error("k_pcg cannot be made resident (occupancy %d): %s", nb, cudaGetErrorString(e));
+    delete g;
+    return nullptr;
+  }
+  g->pcg_grid = g->num_sms;  // one persistent CTA per SM
+  return g;
+}
+
+void ssb_graph_destroy(ssb_graph* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->h_scalars) cudaFreeHost(g->h_scalars);
+  if (g->h_iscalars) cudaFreeHost(g->h_iscalars);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+}
+
+void* ssb_graph_stream(ssb_graph* g) { return g ? (void*)g->stream : nullptr; }
+
+static int sync_estimates_to_host(ssb_graph* g);
+
+int ssb_graph_add_se3_node(ssb_graph* g, const double T34[12]) {
+  if (!g || !T34) return SSB_ERR_INVALID;
+  if (sync_estimates_to_host(g) != SSB_OK) return SSB_ERR_CUDA;
+  HostVertex v;
+  v.kind = VK_SE3;
+  v.idx = (int)g->poses.size();
+  v.fixed = g->V.empty();  // graph_slam.cpp:109-111
+  v.hidx = -1;
+  Pose P;
+  pose_from_34(T34, P);
+  g->poses.push_back(P);
+  g->pose_vid.push_back((int)g->V.size());
+  g->V.push_back(v);
+  g->structure_dirty = true;
+  return (int)g->V.size() - 1;
+}
+
+int ssb_graph_add_point_xyz_node(ssb_graph* g, const double xyz[3]) {
+  if (!g || !xyz) return SSB_ERR_INVALID;
+  if (sync_estimates_to_host(g) != SSB_OK) return SSB_ERR_CUDA;
+  HostVertex v;
+  v.kind = VK_XYZ;
+  v.idx = (int)(g->lms.size() / 4);
+  v.fixed = false;
+  v.hidx = -1;
+  g->lms.push_back(xyz[0]);
+  g->lms.push_back(xyz[1]);
+  g->lms.push_back(xyz[2]);
+  g->lms.push_back(0.0);
+  g->lm_vid.push_back((int)g->V.size());
+  g->V.push_back(v);
+  g->structure_dirty = true;
+  return (int)g->V.size() - 1;
+}
+
+int ssb_graph_add_se3_edge(ssb_graph* g, int v1, int v2, const double Z34[12], const double info[36]) {
+  if (!g || !Z34 || !info || !check_vertex(g, v1, VK_SE3) || !check_vertex(g, v2, VK_SE3)) {
+    set_error("add_se3_edge: invalid vertex ids %d, %d", v1, v2);
+    return SSB_ERR_INVALID;
+  }
+  PPEdge e;
+  std::memset(&e, 0, sizeof(e));
+  e.i = g->V[v1].idx;
+  e.j = g->V[v2].idx;
+  Pose Z;
+  pose_from_34(Z34, Z);
+  for (int k = 0; k < 3; ++k) e.zt[k] = Z.t[k];
+  for (int k = 0; k < 4; ++k) e.zq[k] = Z.q[k];
+  int k = 0;
+  for (int r = 0; r < 6; ++r)
+    for (int c = r; c < 6; ++c) e.info[k++] = 0.5 * (info[6 * r + c] + info[6 * c + r]);
+  g->pp.push_back(e);
+  g->E.push_back({EK_PP, (int)g->pp.size() - 1});
+  g->structure_dirty = true;
+  return (int)g->E.size() - 1;
+}
+
+int ssb_graph_add_se3_point_xyz_edge(ssb_graph* g, int v_se3, int v_xyz, const double xyz[3], const double info[9]) {
+  if (!g || !xyz || !info || !check_vertex(g, v_se3, VK_SE3) || !check_vertex(g, v_xyz, VK_XYZ)) {
+    set_error("add_se3_point_xyz_edge: invalid vertex ids %d, %d", v_se3, v_xyz);
+    return SSB_ERR_INVALID;
+  }
+  PLEdge e;
+  e.p = g->V[v_se3].idx;
+  e.l = g->V[v_xyz].idx;
+  for (int k = 0; k < 3; ++k) e.z[k] = xyz[k];
+  e.info[0] = info[0];
+  e.info[1] = 0.5 * (info[1] + info[3]);
+  e.info[2] = 0.5 * (info[2] + info[6]);
+  e.info[3] = info[4];
+  e.info[4] = 0.5 * (info[5] + info[7]);
+  e.info[5] = info[8];
+  g->pl.push_back(e);
+  g->E.push_back({EK_PL, (int)g->pl.size() - 1});
+  g->structure_dirty = true;
+  return (int)g->E.size() - 1;
+}
+
+int ssb_graph_add_point_xyz_point_xyz_edge(ssb_graph* g, int v1, int v2, const double xyz[3], const double info[9]) {
+  if (!g || !xyz || !info || !check_vertex(g, v1, VK_XYZ) || !check_vertex(g, v2, VK_XYZ)) {
+    set_error("add_point_xyz_point_xyz_edge: invalid vertex ids %d, %d", v1, v2);
+    return SSB_ERR_INVALID;
+  }
+  LLEdge e;
+  e.a = g->V[v1].idx;
+  e.b = g->V[v2].idx;
+  std::memcpy(e.z, xyz, sizeof(e.z));
+  std::memcpy(e.info, info, sizeof(e.info));
+  g->ll.push_back(e);
+  g->E.push_back({EK_LL, (int)g->ll.size() - 1});
+  g->structure_dirty = true;
+  return (int)g->E.size() - 1;
+}
+
+int ssb_graph_num_vertices(const ssb_graph* g) { return g ? (int)g->V.size() : SSB_ERR_INVALID; }
+int ssb_graph_num_edges(const ssb_graph* g) { return g ? (int)g->E.size() : SSB_ERR_INVALID; }
+
+}  // extern "C"
+
+// --------------------------------------------------------------------------------------------
+// device state management
+// --------------------------------------------------------------------------------------------
+static int sync_estimates_to_host(ssb_graph* g) {
+  if (!g->device_est_newer) return SSB_OK;
+  SSB_CUDA_CHECK(cudaSetDevice(g->device));
+  const size_t Np = g->poses.size(), Nl = g->lms.size() / 4;
+  if (Np) SSB_CUDA_CHECK(cudaMemcpyAsync(g->poses.data(), g->d_pose.p, Np * sizeof(Pose), cudaMemcpyDeviceToHost, g->stream));
+  if (Nl) SSB_CUDA_CHECK(cudaMemcpyAsync(g->lms.data(), g->d_lm.p, Nl * 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
+  g->device_est_newer = false;
+  return SSB_OK;
+}
+
+#define SSB_TRY(x)            \
+  do {                        \
+    int _r = (x);             \
+    if (_r != SSB_OK) return _r; \
+  } while (0)
+
+// Build CSR edge tables (initializeOptimization + buildStructure analogue) and upload everything.
+static int prepare(ssb_graph* g) {
+  SSB_CUDA_CHECK(cudaSetDevice(g->device));
+  if (!g->ll.empty()) {
+    set_error("landmark-landmark (EdgePointXYZ) edges are not supported by the Schur back-end in this round");
+    return SSB_ERR_INVALID;
+  }
+  const int Np = (int)g->poses.size(), Nl = (int)(g->lms.size() / 4);
+  const int El = (int)g->pl.size(), Epp = (int)g->pp.size();
+  if (g->structure_dirty) {
+    SSB_TRY(sync_estimates_to_host(g));
+    // hessian indices (buildIndexMapping: id order, fixed = -1)
+    int h = 0;
+    for (auto& v : g->V) v.hidx = v.fixed ? -1 : h++;
+    std::vector<unsigned char> pfix(std::max(Np, 1), 0), lfix(std::max(Nl, 1), 0);
+    for (auto& v : g->V) {
+      if (v.kind == VK_SE3)
+        pfix[v.idx] = v.fixed;
+      else
+        lfix[v.idx] = v.fixed;
+    }
+    // L-order (stable counting sort by landmark)
+    std::vector<int> lm_rowptr(Nl + 1, 0);
+    for (auto& e : g->pl) lm_rowptr[e.l + 1]++;
+    for (int l = 0; l < Nl; ++l) lm_rowptr[l + 1] += lm_rowptr[l];
+    std::vector<int> fill(lm_rowptr.begin(), lm_rowptr.end() - 1);
+    std::vector<PLEdge> plL(std::max(El, 1));
+    g->plL_of_edge.assign(El, 0);
+    for (int k = 0; k < El; ++k) {
+      int pos = fill[g->pl[k].l]++;
+      plL[pos] = g->pl[k];
+      g->plL_of_edge[k] = pos;
+    }
+    // pose-major index over L-order positions
+    std::vector<int> ppl_rowptr(Np + 1, 0);
+    for (int k = 0; k < El; ++k) ppl_rowptr[plL[k].p + 1]++;
+    for (int i = 0; i < Np; ++i) ppl_rowptr[i + 1] += ppl_rowptr[i];
+    std::vector<int> fill2(ppl_rowptr.begin(), ppl_rowptr.end() - 1);
+    std::vector<int> ppl_idx(std::max(El, 1));
+    for (int k = 0; k < El; ++k) ppl_idx[fill2[plL[k].p]++] = k;
+    // pose-pose incidence
+    std::vector<int> ppp_rowptr(Np + 1, 0);
+    for (auto& e : g->pp) {
+      ppp_rowptr[e.i + 1]++;
+      ppp_rowptr[e.j + 1]++;
+    }
+    for (int i = 0; i < Np; ++i) ppp_rowptr[i + 1] += ppp_rowptr[i];
+    std::vector<int> fill3(ppp_rowptr.begin(), ppp_rowptr.end() - 1);
+    std::vector<int> ppp_idx(std::max(2 * Epp, 1));
+    for (int k = 0; k < Epp; ++k) {
+      ppp_idx[fill3[g->pp[k].i]++] = (k << 1) | 0;
+      ppp_idx[fill3[g->pp[k].j]++] = (k << 1) | 1;
+    }
+    // allocate + upload
+    SSB_TRY(g->d_pose.ensure(Np));
+    SSB_TRY(g->d_pose_bak.ensure(Np));
+    SSB_TRY(g->d_lm.ensure((size_t)4 * Nl));
+    SSB_TRY(g->d_lm_bak.ensure((size_t)4 * Nl));
+    SSB_TRY(g->d_pose_fixed.ensure(Np));
+    SSB_TRY(g->d_lm_fixed.ensure(Nl));
+    SSB_TRY(g->d_pl.ensure(El));
+    SSB_TRY(g->d_pp.ensure(Epp));
+    SSB_TRY(g->d_lm_rowptr.ensure(Nl + 1));
+    SSB_TRY(g->d_pose_pl_rowptr.ensure(Np + 1));
+    SSB_TRY(g->d_pose_pl_idx.ensure(El));
+    SSB_TRY(g->d_pose_pp_rowptr.ensure(Np + 1));
+    SSB_TRY(g->d_pose_pp_idx.ensure((size_t)2 * Epp));
+    SSB_TRY(g->d_plP_lm.ensure(El));
+    SSB_TRY(g->d_Hpp.ensure((size_t)36 * Np));
+    SSB_TRY(g->d_bp.ensure((size_t)6 * Np));
+    SSB_TRY(g->d_Hoff.ensure((size_t)36 * Epp));
+    SSB_TRY(g->d_Hll.ensure((size_t)6 * Nl));
+    SSB_TRY(g->d_bl.ensure((size_t)3 * Nl));
+    SSB_TRY(g->d_HplL.ensure((size_t)18 * El));
+    SSB_TRY(g->d_HplP.ensure((size_t)18 * El));
+    SSB_TRY(g->d_HllInv.ensure((size_t)6 * Nl));
+    SSB_TRY(g->d_Dinv.ensure((size_t)36 * Np));
+    SSB_TRY(g->d_g.ensure((size_t)6 * Np));
+    SSB_TRY(g->d_x.ensure((size_t)6 * Np));
+    SSB_TRY(g->d_r.ensure((size_t)6 * Np));
+    SSB_TRY(g->d_z.ensure((size_t)6 * Np));
+    SSB_TRY(g->d_p0.ensure((size_t)6 * Np));
+    SSB_TRY(g->d_p1.ensure((size_t)6 * Np));
+    SSB_TRY(g->d_q.ensure((size_t)6 * Np));
+    SSB_TRY(g->d_v.ensure((size_t)3 * Nl));
+    SSB_TRY(g->d_dl.ensure((size_t)3 * Nl));
+    const size_t nb_bs = (size_t)(Np + Nl + 127) / 128 + 1;
+    SSB_TRY(g->d_part.ensure(std::max<size_t>(3 * PART_STRIDE, nb_bs) + 4096));
+    SSB_TRY(g->d_scalars.ensure(8));
+    SSB_TRY(g->d_iscalars.ensure(4));
+    SSB_TRY(g->d_tmp.ensure(128));
+    cudaStream_t s = g->stream;
+    SSB_CUDA_CHECK(cudaMemsetAsync(g->d_scalars.p, 0, 8 * sizeof(double), s));
+    SSB_CUDA_CHECK(cudaMemsetAsync(g->d_iscalars.p, 0, 4 * sizeof(int), s));
+    if (Np) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_fixed.p, pfix.data(), Np, cudaMemcpyHostToDevice, s));
+    if (Nl) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_fixed.p, lfix.data(), Nl, cudaMemcpyHostToDevice, s));
+    if (El) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pl.p, plL.data(), (size_t)El * sizeof(PLEdge), cudaMemcpyHostToDevice, s));
+    if (Epp) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pp.p, g->pp.data(), (size_t)Epp * sizeof(PPEdge), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_rowptr.p, lm_rowptr.data(), (Nl + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pl_rowptr.p, ppl_rowptr.data(), (Np + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (El) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pl_idx.p, ppl_idx.data(), (size_t)El * sizeof(int), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pp_rowptr.p, ppp_rowptr.data(), (Np + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (Epp) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pp_idx.p, ppp_idx.data(), (size_t)2 * Epp * sizeof(int), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaStreamSynchronize(s));  // host vectors above go out of scope
+    g->structure_dirty = false;
+    g->host_est_dirty = true;
+    g->have_system = false;
+    g->have_snapshot = false;
+    DevGraph& G = g->G;
+    G.Np = Np;
+    G.Nl = Nl;
+    G.El = El;
+    G.Epp = Epp;
+    G.pose = g->d_pose.p;
+    G.lm = g->d_lm.p;
+    G.pose_fixed = g->d_pose_fixed.p;
+    G.lm_fixed = g->d_lm_fixed.p;
+    G.pl = g->d_pl.p;
+    G.pp = g->d_pp.p;
+    G.lm_rowptr = g->d_lm_rowptr.p;
+    G.pose_pl_rowptr = g->d_pose_pl_rowptr.p;
+    G.pose_pl_idx = g->d_pose_pl_idx.p;
+    G.pose_pp_rowptr = g->d_pose_pp_rowptr.p;
+    G.pose_pp_idx = g->d_pose_pp_idx.p;
+    G.Hpp = g->d_Hpp.p;
+    G.bp = g->d_bp.p;
+    G.Hoff = g->d_Hoff.p;
+    G.Hll = g->d_Hll.p;
+    G.bl = g->d_bl.p;
+    G.HplL = g->d_HplL.p;
+    G.HplP = g->d_HplP.p;
+    G.plP_lm = g->d_plP_lm.p;
+    G.HllInv = g->d_HllInv.p;
+    G.Dinv = g->d_Dinv.p;
+    G.g = g->d_g.p;
+    G.x = g->d_x.p;
+    G.r = g->d_r.p;
+    G.z = g->d_z.p;
+    G.p0 = g->d_p0.p;
+    G.p1 = g->d_p1.p;
+    G.q = g->d_q.p;
+    G.v = g->d_v.p;
+    G.dl = g->d_dl.p;
+    G.part = g->d_part.p;
+    G.scalars = g->d_scalars.p;
+    G.iscalars = g->d_iscalars.p;
+  }
+  if (g->host_est_dirty) {
+    cudaStream_t s = g->stream;
+    if (Np) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose.p, g->poses.data(), (size_t)Np * sizeof(Pose), cudaMemcpyHostToDevice, s));
+    if (Nl) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm.p, g->lms.data(), (size_t)4 * Nl * sizeof(double), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+    g->host_est_dirty = false;
+    g->device_est_newer = false;
+    g->have_system = false;
+  }
+  return SSB_OK;
+}
+
+// ---- kernel launch helpers -----------------------------------------------------------------
+static int launch_chi2(ssb_graph* g) {
+  DevGraph& G = g->G;
+  const int nt = (G.El + CHI2_PL_TILE - 1) / CHI2_PL_TILE + (G.Epp + CHI2_PP_TILE - 1) / CHI2_PP_TILE;
+  const int grid = std::max(1, std::min(nt, 4 * g->num_sms));
+  k_chi2<<<grid, CHI2_THREADS, 0, g->stream>>>(G, G.part + 3 * PART_STRIDE, G.scalars + 0, G.iscalars + 2);
+  g->launches++;
+  SSB_CUDA_CHECK(cudaGetLastError());
+  return SSB_OK;
+}
+static int launch_linearize(ssb_graph* g) {
+  DevGraph& G = g->G;
+  if (G.Nl) {
+    k_lin_landmarks<<<(G.Nl + 127) / 128, 128, 0, g->stream>>>(G);
+    g->launches++;
+  }
+  if (G.Np) {
+    k_lin_poses<<<(G.Np + 63) / 64, 64, 0, g->stream>>>(G);
+    g->launches++;
+  }
+  SSB_CUDA_CHECK(cudaGetLastError());
+  g->have_system = true;
+  return SSB_OK;
+}
+static int launch_solve(ssb_graph* g, double lambda, int apply) {
+  DevGraph& G = g->G;
+  cudaStream_t s = g->stream;
+  if (G.Nl) {
+    k_prep_landmarks<<<(G.Nl + 127) / 128, 128, 0, s>>>(G, lambda);
+    g->launches++;
+  }
+  k_prep_poses<<<(G.Np + 63) / 64, 64, 0, s>>>(G, lambda);
+  g->launches++;
+  double tol2 = g->opts.pcg_tol * g->opts.pcg_tol;
+  int maxit = g->opts.max_pcg_iters;
+  void* args[] = {(void*)&G, (void*)&lambda, (void*)&tol2, (void*)&maxit};
+  SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(g->pcg_grid), dim3(1024), args, 0, s));
+  g->launches++;
+  if (apply) {
+    k_backsub_update<<<(G.Np + G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
+    g->launches++;
+  }
+  SSB_CUDA_CHECK(cudaGetLastError());
+  return SSB_OK;
+}
+static int read_scalars(ssb_graph* g) {
+  SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_scalars, g->d_scalars.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_iscalars, g->d_iscalars.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
+  return SSB_OK;
+}
+
+// The LM loop of SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve on device state.
+static int lm_loop(ssb_graph* g, int max_iterations, ssb_lm_stats* st) {
+  DevGraph& G = g->G;
+  cudaStream_t s = g->stream;
+  g->history.clear();
+  SSB_CUDA_CHECK(cudaEventRecord(g->ev0, s));
+  SSB_TRY(launch_chi2(g));
+  SSB_TRY(read_scalars(g));
+  double currentChi = g->h_scalars[0];
+  st->chi2_initial = currentChi;
+  double lambda = 0.0, ni = 2.0;
+  bool ok = true;
+  int it = 0;
+  for (it = 0; it < max_iterations && ok; ++it) {
+    SSB_TRY(launch_linearize(g));
+    if (it == 0) {
+      // computeLambdaInit: tau * max diag, tau = 1e-5
+      SSB_CUDA_CHECK(cudaMemsetAsync(G.scalars + 2, 0, sizeof(double), s));
+      k_maxdiag<<<(G.Np + G.Nl + 255) / 256, 256, 0, s>>>(G);
+      g->launches++;
+      SSB_TRY(read_scalars(g));
+      lambda = 1e-5 * g->h_scalars[2];
+      ni = 2.0;
+    }
+    double rho = 0.0;
+    int qmax = 0, pcg_its = 0;
+    const double chi_before = currentChi;
+    do {
+      SSB_TRY(launch_solve(g, lambda, 1));  // push() + setLambda + solve + update
+      SSB_TRY(launch_chi2(g));              // computeActiveErrors + activeRobustChi2
+      SSB_TRY(read_scalars(g));
+      st->total_trials++;
+      pcg_its += g->h_iscalars[0];
+      double tempChi = g->h_scalars[0];
+      const bool ok2 = g->h_iscalars[1] == 0;
+      if (!ok2) tempChi = std::numeric_limits<double>::max();
+      rho = currentChi - tempChi;
+      double scale = g->h_scalars[1] + 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1.0 - std::pow(2 * rho - 1, 3);
+        alpha = std::min(alpha, 2.0 / 3.0);
+        double scaleFactor = std::max(1.0 / 3.0, alpha);
+        lambda *= scaleFactor;
+        ni = 2;
+        currentChi = tempChi;
+        // discardTop(): nothing to do
+      } else {
+        lambda *= ni;
+        ni *= 2;
+        // pop(): restore the backup
+        const int n = std::max(G.Np, G.Nl);
+        k_copy_state<<<(n + 255) / 256, 256, 0, s>>>(G.pose, g->d_pose_bak.p, G.Np, G.lm, g->d_lm_bak.p, G.Nl);
+        g->launches++;
+      }
+      qmax++;
+    } while (rho < 0 && qmax < 10);
+    st->total_pcg_iters += pcg_its;
+    g->history.push_back(chi_before);
+    g->history.push_back(currentChi);
+    g->history.push_back(lambda);
+    g->history.push_back(rho);
+    g->history.push_back((double)qmax);
+    g->history.push_back((double)pcg_its);
+    if (qmax == 10 || rho == 0) {
+      st->terminated = 1;
+      ok = false;
+    }
+  }
+  SSB_CUDA_CHECK(cudaEventRecord(g->ev1, s));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+  float ms = 0;
+  SSB_CUDA_CHECK(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
+  st->ms_device = ms;
+  st->iterations = it;
+  st->chi2_final = currentChi;
+  st->lambda_final = lambda;
+  g->device_est_newer = true;
+  return SSB_OK;
+}
+
+extern "C" {
+
+int ssb_graph_prepare(ssb_graph* g) {
+  if (!g) return SSB_ERR_INVALID;
+  return prepare(g);
+}
+
+int ssb_graph_optimize(ssb_graph* g, int max_iterations, ssb_lm_stats* stats) {
+  if (!g) return SSB_ERR_INVALID;
+  ssb_lm_stats st;
+  std::memset(&st, 0, sizeof(st));
+  if (g->E.size() < 10) {  // graph_slam.cpp:184-186
+    if (stats) *stats = st;
+    return 0;
+  }
+  const double t0 = wall_ms();
+  const long long l0 = g->launches;
+  SSB_TRY(prepare(g));
+  st.ms_prepare = wall_ms() - t0;
+  int r = lm_loop(g, max_iterations, &st);
+  if (r != SSB_OK) return r;
+  SSB_TRY(sync_estimates_to_host(g));
+  st.ms_total = wall_ms() - t0;
+  st.kernel_launches = g->launches - l0;
+  if (stats) *stats = st;
+  return 1;
+}
+
+// device-resident variant: requires ssb_graph_prepare; neither uploads nor downloads estimates
+int ssb_graph_optimize_resident(ssb_graph* g, int max_iterations, ssb_lm_stats* stats) {
+  if (!g) return SSB_ERR_INVALID;
+  if (g->structure_dirty) {
+    set_error("optimize_resident: call ssb_graph_prepare first");
+    return SSB_ERR_INVALID;
+  }
+  ssb_lm_stats st;
+  std::memset(&st, 0, sizeof(st));
+  if (g->E.size() < 10) {
+    if (stats) *stats = st;
+    return 0;
+  }
+  SSB_CUDA_CHECK(cudaSetDevice(g->device));
+  const double t0 = wall_ms();
+  const long long l0 = g->launches;
+  int r = lm_loop(g, max_iterations, &st);
+  if (r != SSB_OK) return r;
+  st.ms_total = wall_ms() - t0;
+  st.kernel_launches = g->launches - l0;
+  if (stats) *stats = st;
+  return 1;
+}
+
+int ssb_graph_get_history(ssb_graph* g, double* out6n, int cap) {
+  if (!g) return SSB_ERR_INVALID;
+  int n = (int)(g->history.size() / 6);
+  int m = std::min(n, cap);
+  if (out6n && m > 0) std::memcpy(out6n, g->history.data(), (size_t)m * 6 * sizeof(double));
+  return n;
+}
+
+int ssb_graph_chi2(ssb_graph* g, double* chi2_out) {
+  if (!g || !chi2_out) return SSB_ERR_INVALID;
+  SSB_TRY(prepare(g));
+  SSB_TRY(launch_chi2(g));
+  SSB_TRY(read_scalars(g));
+  *chi2_out = g->h_scalars[0];
+  return SSB_OK;
+}
+
+int ssb_graph_get_se3(ssb_graph* g, int vid, double T34[12]) {
+  if (!check_vertex(g, vid, VK_SE3) || !T34) return SSB_ERR_INVALID;
+  SSB_TRY(sync_estimates_to_host(g));
+  pose_to_34(g->poses[g->V[vid].idx], T34);
+  return SSB_OK;
+}
+int ssb_graph_get_point_xyz(ssb_graph* g, int vid, double xyz[3]) {
+  if (!check_vertex(g, vid, VK_XYZ) || !xyz) return SSB_ERR_INVALID;
+  SSB_TRY(sync_estimates_to_host(g));
+  std::memcpy(xyz, &g->lms[4 * (size_t)g->V[vid].idx], 3 * sizeof(double));
+  return SSB_OK;
+}
+int ssb_graph_set_se3(ssb_graph* g, int vid, const double T34[12]) {
+  if (!check_vertex(g, vid, VK_SE3) || !T34) return SSB_ERR_INVALID;
+  SSB_TRY(sync_estimates_to_host(g));
+  pose_from_34(T34, g->poses[g->V[vid].idx]);
+  g->host_est_dirty = true;
+  return SSB_OK;
+}
+int ssb_graph_set_point_xyz(ssb_graph* g, int vid, const double xyz[3]) {
+  if (!check_vertex(g, vid, VK_XYZ) || !xyz) return SSB_ERR_INVALID;
+  SSB_TRY(sync_estimates_to_host(g));
+  std::memcpy(&g->lms[4 * (size_t)g->V[vid].idx], xyz, 3 * sizeof(double));
+  g->host_est_dirty = true;
+  return SSB_OK;
+}
+int ssb_graph_set_fixed(ssb_graph* g, int vid, int fixed) {
+  if (!g || vid < 0 || vid >= (int)g->V.size()) return SSB_ERR_INVALID;
+  g->V[vid].fixed = fixed != 0;
+  g->structure_dirty = true;
+  return SSB_OK;
+}
+int ssb_graph_hessian_index(ssb_graph* g, int vid) {
+  if (!g || vid < 0 || vid >= (int)g->V.size()) return SSB_ERR_INVALID;
+  int h = 0;
+  for (int k = 0; k < vid; ++k)
+    if (!g->V[k].fixed) ++h;
+  return g->V[vid].fixed ? -1 : h;
+}
+int ssb_graph_get_all(ssb_graph* g, double* se3_out, double* xyz_out) {
+  if (!g) return SSB_ERR_INVALID;
+  SSB_TRY(sync_estimates_to_host(g));
+  if (se3_out)
+    for (size_t i = 0; i < g->poses.size(); ++i) pose_to_34(g->poses[i], se3_out + 12 * i);
+  if (xyz_out)
+    for (size_t l = 0; l < g->lms.size() / 4; ++l) std::memcpy(xyz_out + 3 * l, &g->lms[4 * l], 3 * sizeof(double));
+  return SSB_OK;
+}
+// bulk setter (id order within each kind), counterpart of ssb_graph_get_all
+int ssb_graph_set_all(ssb_graph* g, const double* se3_in, const double* xyz_in) {
+  if (!g) return SSB_ERR_INVALID;
+  SSB_TRY(sync_estimates_to_host(g));
+  if (se3_in)
+    for (size_t i = 0; i < g->poses.size(); ++i) pose_from_34(se3_in + 12 * i, g->poses[i]);
+  if (xyz_in)
+    for (size_t l = 0; l < g->lms.size() / 4; ++l) std::memcpy(&g->lms[4 * l], xyz_in + 3 * l, 3 * sizeof(double));
+  g->host_est_dirty = true;
+  return SSB_OK;
+}
+// force the next optimize() to rebuild and re-upload the edge tables (what the reference's
+// initializeOptimization does on every call, graph_slam.cpp:199)
+int ssb_graph_invalidate(ssb_graph* g) {
+  if (!g) return SSB_ERR_INVALID;
+  SSB_TRY(sync_estimates_to_host(g));
+  g->structure_dirty = true;
+  return SSB_OK;
+}
+
+int ssb_graph_snapshot(ssb_graph* g) {
+  if (!g) return SSB_ERR_INVALID;
+  SSB_TRY(prepare(g));
+  SSB_TRY(g->d_pose_snap.ensure(g->G.Np));
+  SSB_TRY(g->d_lm_snap.ensure((size_t)4 * g->G.Nl));
+  const int n = std::max(g->G.Np, g->G.Nl);
+  k_copy_state<<<(n + 255) / 256, 256, 0, g->stream>>>(g->d_pose_snap.p, g->G.pose, g->G.Np, g->d_lm_snap.p, g->G.lm, g->G.Nl);
+  g->launches++;
+  SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
+  g->have_snapshot = true;
+  return SSB_OK;
+}
+int ssb_graph_restore(ssb_graph* g) {
+  if (!g || !g->have_snapshot || g->structure_dirty) {
+    set_error("restore: no snapshot for the current structure");
+    return SSB_ERR_INVALID;
+  }
+  SSB_CUDA_CHECK(cudaSetDevice(g->device));
+  const int n = std::max(g->G.Np, g->G.Nl);
+  k_copy_state<<<(n + 255) / 256, 256, 0, g->stream>>>(g->G.pose, g->d_pose_snap.p, g->G.Np, g->G.lm, g->d_lm_snap.p, g->G.Nl);
+  g->launches++;
+  SSB_CUDA_CHECK(cudaGetLastError());
+  g->device_est_newer = true;
+  g->host_est_dirty = false;
+  g->have_system = false;
+  return SSB_OK;
+}
+
+int ssb_graph_edge_linearize(ssb_graph* g, int eid, double* err, double* Ji, double* Jj) {
+  if (!g || eid < 0 || eid >= (int)g->E.size() || !err || !Ji || !Jj) return SSB_ERR_INVALID;
+  SSB_TRY(prepare(g));
+  HostEdgeRef r = g->E[eid];
+  if (r.kind == EK_LL) return SSB_ERR_INVALID;
+  int idx = r.kind == EK_PP ? r.idx : g->plL_of_edge[r.idx];
+  k_edge_linearize<<<1, 32, 0, g->stream>>>(g->G, r.kind == EK_PP ? 0 : 1, idx, g->d_tmp.p);
+  g->launches++;
+  double out[78];
+  SSB_CUDA_CHECK(cudaMemcpyAsync(out, g->d_tmp.p, sizeof(out), cudaMemcpyDeviceToHost, g->stream));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
+  if (r.kind == EK_PP) {
+    std::memcpy(err, out, 6 * sizeof(double));
+    std::memcpy(Ji, out + 6, 36 * sizeof(double));
+    std::memcpy(Jj, out + 42, 36 * sizeof(double));
+  } else {
+    std::memcpy(err, out, 3 * sizeof(double));
+    std::memcpy(Ji, out + 6, 18 * sizeof(double));
+    std::memcpy(Jj, out + 42, 9 * sizeof(double));
+  }
+  return SSB_OK;
+}
+
+int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len) {
+  if (!g || !x) return SSB_ERR_INVALID;
+  SSB_TRY(prepare(g));
+  SSB_TRY(launch_linearize(g));
+  SSB_TRY(launch_solve(g, lambda, 0));
+  // dl without applying: reuse the back-substitution on a scratch copy of the state
+  {
+    const int n = std::max(g->G.Np, g->G.Nl);
+    SSB_TRY(g->d_pose_snap.ensure(g->G.Np));
+    SSB_TRY(g->d_lm_snap.ensure((size_t)4 * g->G.Nl));
+    g->have_snapshot = false;
+    k_copy_state<<<(n + 255) / 256, 256, 0, g->stream>>>(g->d_pose_snap.p, g->G.pose, g->G.Np, g->d_lm_snap.p, g->G.lm, g->G.Nl);
+    k_backsub_update<<<(g->G.Np + g->G.Nl + 127) / 128, 128, 0, g->stream>>>(g->G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
+    k_copy_state<<<(n + 255) / 256, 256, 0, g->stream>>>(g->G.pose, g->d_pose_snap.p, g->G.Np, g->G.lm, g->d_lm_snap.p, g->G.Nl);
+    g->launches += 3;
+  }
+  std::vector<double> dp((size_t)6 * g->G.Np + 1), dl((size_t)3 * g->G.Nl + 1);
+  SSB_CUDA_CHECK(cudaMemcpyAsync(dp.data(), g->G.x, (size_t)6 * g->G.Np * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  if (g->G.Nl)
+    SSB_CUDA_CHECK(cudaMemcpyAsync(dl.data(), g->G.dl, (size_t)3 * g->G.Nl * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  SSB_TRY(read_scalars(g));
+  int need = 0;
+  for (auto& v : g->V)
+    if (!v.fixed) need += v.kind == VK_SE3 ? 6 : 3;
+  if (x_len < need) {
+    set_error("solve_once: x_len %d < %d", x_len, need);
+    return SSB_ERR_INVALID;
+  }
+  int o = 0;
+  for (auto& v : g->V) {
+    if (v.fixed) continue;
+    if (v.kind == VK_SE3) {
+      std::memcpy(x + o, &dp[6 * (size_t)v.idx], 6 * sizeof(double));
+      o += 6;
+    } else {
+      std::memcpy(x + o, &dl[3 * (size_t)v.idx], 3 * sizeof(double));
+      o += 3;
+    }
+  }
+  if (g->h_iscalars[1] != 0) {
+    set_error("PCG breakdown (status %d)", g->h_iscalars[1]);
+    return SSB_ERR_NUMERIC;
+  }
+  return g->h_iscalars[0];
+}
+
+int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* out9n) {
+  (void)vids;
+  (void)n;
+  (void)out9n;
+  if (!g) return SSB_ERR_INVALID;
+  set_error("landmark marginals: not implemented yet");
+  return 0;
+}
+
+// ---- g2o text format (graph_slam.cpp:236-239 -> OptimizableGraph::save) ---------------------
+int ssb_graph_save_g2o(ssb_graph* g, const char* path) {
+  if (!g || !path) return SSB_ERR_INVALID;
+  SSB_TRY(sync_estimates_to_host(g));
+  FILE* f = std::fopen(path, "w");
+  if (!f) {
+    set_error("cannot open %s for writing", path);
+    return SSB_ERR_INVALID;
+  }
+  std::fprintf(f, "PARAMS_SE3OFFSET 0 0 0 0 0 0 0 1\n");
+  for (size_t id = 0; id < g->V.size(); ++id) {
+    const HostVertex& v = g->V[id];
+    if (v.kind == VK_SE3) {
+      const Pose& P = g->poses[v.idx];
+      std::fprintf(f, "VERTEX_SE3:QUAT %zu %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", id, P.t[0], P.t[1], P.t[2], P.q[0],
+                   P.q[1], P.q[2], P.q[3]);
+    } else {
+      const double* p = &g->lms[4 * (size_t)v.idx];
+      std::fprintf(f, "VERTEX_TRACKXYZ %zu %.17g %.17g %.17g\n", id, p[0], p[1], p[2]);
+    }
+    if (v.fixed) std::fprintf(f, "FIX %zu\n", id);
+  }
+  for (auto& r : g->E) {
+    if (r.kind == EK_PP) {
+      const PPEdge& e = g->pp[r.idx];
+      std::fprintf(f, "EDGE_SE3:QUAT %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g", g->pose_vid[e.i], g->pose_vid[e.j],
+                   e.zt[0], e.zt[1], e.zt[2], e.zq[0], e.zq[1], e.zq[2], e.zq[3]);
+      for (int k = 0; k < 21; ++k) std::fprintf(f, " %.17g", e.info[k]);
+      std::fprintf(f, "\n");
+    } else if (r.kind == EK_PL) {
+      const PLEdge& e = g->pl[r.idx];
+      std::fprintf(f, "EDGE_SE3_TRACKXYZ %d %d 0 %.17g %.17g %.17g", g->pose_vid[e.p], g->lm_vid[e.l], e.z[0], e.z[1], e.z[2]);
+      for (int k = 0; k < 6; ++k) std::fprintf(f, " %.17g", e.info[k]);
+      std::fprintf(f, "\n");
+    } else {
+      const LLEdge& e = g->ll[r.idx];
+      std::fprintf(f, "EDGE_POINT_XYZ %d %d %.17g %.17g %.17g", g->lm_vid[e.a], g->lm_vid[e.b], e.z[0], e.z[1], e.z[2]);
+      const int ut[6] = {0, 1, 2, 4, 5, 8};
+      for (int k = 0; k < 6; ++k) std::fprintf(f, " %.17g", e.info[ut[k]]);
+      std::fprintf(f, "\n");
+    }
+  }
+  std::fclose(f);
+  return SSB_OK;
+}
+
+int ssb_graph_load_g2o(ssb_graph* g, const char* path) {
+  if (!g || !path) return SSB_ERR_INVALID;
+  if (!g->V.empty()) {
+    set_error("load_g2o: graph must be empty");
+    return SSB_ERR_INVALID;
+  }
+  std::ifstream in(path);
+  if (!in) {
+    set_error("cannot open %s", path);
+    return SSB_ERR_INVALID;
+  }
+  std::string line;
+  std::vector<int> fixes;
+  while (std::getline(in, line)) {
+    std::istringstream ss(line);
+    std::string tag;
+    if (!(ss >> tag)) continue;
+    if (tag == "VERTEX_SE3:QUAT") {
+      int id;
+      double t[3], q[4];
+      ss >> id >> t[0] >> t[1] >> t[2] >> q[0] >> q[1] >> q[2] >> q[3];
+      double R[9], T[12];
+      double qq[4] = {q[0], q[1], q[2], q[3]};
+      quat_normalize(qq);
+      quat_to_R(qq, R);
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) T[4 * r + c] = R[3 * r + c];
+        T[4 * r + 3] = t[r];
+      }
+      int got = ssb_graph_add_se3_node(g, T);
+      if (got != id) {
+        set_error("load_g2o: vertex ids must be consecutive (got %d, expected %d)", id, got);
+        return SSB_ERR_INVALID;
+      }
+    } else if (tag == "VERTEX_TRACKXYZ") {
+      int id;
+      double p[3];
+      ss >> id >> p[0] >> p[1] >> p[2];
+      int got = ssb_graph_add_point_xyz_node(g, p);
+      if (got != id) {
+        set_error("load_g2o: vertex ids must be consecutive (got %d, expected %d)", id, got);
+        return SSB_ERR_INVALID;
+      }
+    } else if (tag == "FIX") {
+      int id;
+      while (ss >> id) fixes.push_back(id);
+    } else if (tag == "EDGE_SE3:QUAT") {
+      int a, b;
+      double t[3], q[4], u[21];
+      ss >> a >> b >> t[0] >> t[1] >> t[2] >> q[0] >> q[1] >> q[2] >> q[3];
+      for (int k = 0; k < 21; ++k) ss >> u[k];
+      double R[9], T[12], info[36];
+      quat_normalize(q);
+      quat_to_R(q, R);
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) T[4 * r + c] = R[3 * r + c];
+        T[4 * r + 3] = t[r];
+      }
+      expand_sym6(u, info);
+      if (ssb_graph_add_se3_edge(g, a, b, T, info) < 0) return SSB_ERR_INVALID;
+    } else if (tag == "EDGE_SE3_TRACKXYZ") {
+      int a, b, pid;
+      double z[3], u[6], info[9];
+      ss >> a >> b >> pid >> z[0] >> z[1] >> z[2];
+      for (int k = 0; k < 6; ++k) ss >> u[k];
+      expand_sym3(u, info);
+      if (ssb_graph_add_se3_point_xyz_edge(g, a, b, z, info) < 0) return SSB_ERR_INVALID;
+    } else if (tag == "EDGE_POINT_XYZ") {
+      int a, b;
+      double z[3], u[6], info[9];
+      ss >> a >> b >> z[0] >> z[1] >> z[2];
+      for (int k = 0; k < 6; ++k) ss >> u[k];
+      expand_sym3(u, info);
+      if (ssb_graph_add_point_xyz_point_xyz_edge(g, a, b, z, info) < 0) return SSB_ERR_INVALID;
+    }
+  }
+  // g2o's reader applies FIX lines after loading; the first-vertex rule of add_se3_node stays
+  for (size_t id = 0; id < g->V.size(); ++id) g->V[id].fixed = false;
+  for (int id : fixes)
+    if (id >= 0 && id < (int)g->V.size()) g->V[id].fixed = true;
+  g->structure_dirty = true;
+  return SSB_OK;
+}
+
+int ssb_comm_unique_id(unsigned char id_out[128]) {
+  (void)id_out;
+  set_error("multi-GPU: not built in this round yet");
+  return SSB_ERR_COMM;
+}
+int ssb_graph_attach_comm(ssb_graph* g, int rank, int world, const unsigned char unique_id[128]) {
+  (void)unique_id;
+  if (!g) return SSB_ERR_INVALID;
+  if (world == 1) {
+    g->comm_rank = 0;
+    g->comm_world = 1;
+    return SSB_OK;
+  }
+  (void)rank;
+  set_error("multi-GPU: not built in this round yet");
+  return SSB_ERR_COMM;
+}
+
+}  // extern "C"

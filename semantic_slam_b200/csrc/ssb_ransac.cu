@@ -1,0 +1,690 @@
+// ssb_ransac.cu — planar_segmentation RANSAC plane fit on bbox-cropped depth clouds, sm_100a.
+//   K6 k_crop    : plane_segmentation::segmentPointCloudData (plane_segmentation.cpp:24-82)
+//   K7 k_hyp     : SampleConsensusModelPlane::computeModelCoefficients (3-point plane)
+//      k_count   : countWithinDistance for every (crop, hypothesis): float4 point tiles staged in
+//                  shared memory by 1-D TMA bulk copies, hypotheses held in registers (one lane =
+//                  HPT hypotheses), integer counts folded with one atomicAdd per (block, hypothesis)
+//   K8 k_finish  : RandomSampleConsensus::computeModel winner selection (first best / adaptive-k
+//                  replay), optimizeModelCoefficients (PCA of the inliers, fp64) and
+//                  selectWithinDistance (plane_segmentation.cpp:639-647 -> pcl::SACSegmentation)
+// Float evaluation order is Eigen's SSE3 4-vector dot: ((a*x + b*y) + (c*z + d)) with separate
+// IEEE roundings (no FMA contraction: __fmul_rn/__fadd_rn), so inlier counts are integer-exact
+// against the CPU oracle.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../../include/ssb.h"
+#include "ssb_common.cuh"
+
+namespace ssb {
+
+template <class T>
+struct RBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap && p) return SSB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max<size_t>(n, 1);
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+      return SSB_ERR_CUDA;
+    }
+    cap = want;
+    return SSB_OK;
+  }
+  ~RBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+struct BoxInfo {      // per bbox, device side
+  int tl_x, tl_y, w, h;
+  int n;              // w*h, or -1 if spurious
+  int pt_off;         // offset (in points) of the crop in the concatenated crop buffer
+  int tile_off;       // first tile index of this box
+  int pad;
+};
+
+__device__ __forceinline__ float plane_dist(float a, float b, float c, float d, float x, float y, float z) {
+  const float s0 = __fadd_rn(__fmul_rn(a, x), __fmul_rn(b, y));
+  const float s1 = __fadd_rn(__fmul_rn(c, z), d);
+  return fabsf(__fadd_rn(s0, s1));
+}
+
+// ---- K6 -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_crop(const unsigned char* __restrict__ msg, ssb_cloud_layout L,
+                                              const BoxInfo* __restrict__ boxes, float4* __restrict__ crop) {
+  const BoxInfo B = boxes[blockIdx.y];
+  if (B.n <= 0) return;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < B.n; idx += gridDim.x * blockDim.x) {
+    const int pv = idx / B.w, pu = idx - pv * B.w;
+    const size_t pos = (size_t)(B.tl_y + pv) * L.row_step + (size_t)(B.tl_x + pu) * L.point_step;
+    float4 o;
+    // 4-byte fields; PointCloud2 offsets are 4-byte aligned in every driver the reference consumes
+    o.x = *reinterpret_cast<const float*>(msg + pos + L.off_x);
+    o.y = *reinterpret_cast<const float*>(msg + pos + L.off_y);
+    o.z = *reinterpret_cast<const float*>(msg + pos + L.off_z);
+    o.w = *reinterpret_cast<const float*>(msg + pos + L.off_rgb);
+    crop[(size_t)B.pt_off + idx] = o;
+  }
+}
+
+// ---- K7a ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hyp(const float4* __restrict__ crop, const BoxInfo* __restrict__ boxes,
+                                             const int* __restrict__ triples, int K, float4* __restrict__ hyp,
+                                             int* __restrict__ valid) {
+  const int b = blockIdx.y;
+  const BoxInfo B = boxes[b];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const size_t o = (size_t)b * K + k;
+  const float qnan = __int_as_float(0x7fc00000);
+  if (B.n <= 0) {
+    hyp[o] = make_float4(qnan, qnan, qnan, qnan);
+    valid[o] = 0;
+    return;
+  }
+  const int* t = triples + 3 * o;
+  int i0 = t[0], i1 = t[1], i2 = t[2];
+  if ((unsigned)i0 >= (unsigned)B.n || (unsigned)i1 >= (unsigned)B.n || (unsigned)i2 >= (unsigned)B.n) {
+    hyp[o] = make_float4(qnan, qnan, qnan, qnan);
+    valid[o] = 0;
+    return;
+  }
+  const float4 p0 = crop[(size_t)B.pt_off + i0], p1 = crop[(size_t)B.pt_off + i1], p2 = crop[(size_t)B.pt_off + i2];
+  const float ax = __fsub_rn(p1.x, p0.x), ay = __fsub_rn(p1.y, p0.y), az = __fsub_rn(p1.z, p0.z);
+  const float bx = __fsub_rn(p2.x, p0.x), by = __fsub_rn(p2.y, p0.y), bz = __fsub_rn(p2.z, p0.z);
+  const float rx = __fdiv_rn(ax, bx), ry = __fdiv_rn(ay, by), rz = __fdiv_rn(az, bz);
+  if ((rx == ry) && (rz == ry)) {  // collinear sample
+    hyp[o] = make_float4(qnan, qnan, qnan, qnan);
+    valid[o] = 0;
+    return;
+  }
+  float c0 = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
+  float c1 = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
+  float c2 = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+  float c3 = 0.f;
+  const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)), __fadd_rn(__fmul_rn(c2, c2), __fmul_rn(c3, c3)));
+  const float n = __fsqrt_rn(n2);
+  c0 = __fdiv_rn(c0, n);
+  c1 = __fdiv_rn(c1, n);
+  c2 = __fdiv_rn(c2, n);
+  c3 = __fdiv_rn(c3, n);
+  const float dot = __fadd_rn(__fadd_rn(__fmul_rn(c0, p0.x), __fmul_rn(c1, p0.y)), __fadd_rn(__fmul_rn(c2, p0.z), __fmul_rn(c3, 1.0f)));
+  hyp[o] = make_float4(c0, c1, c2, __fmul_rn(-1.f, dot));
+  valid[o] = 1;
+}
+
+// ---- K7b: the point x hypothesis sweep --------------------------------------------------------
+constexpr int CNT_THREADS = 256;
+constexpr int CNT_HPT = 4;                       // hypotheses per thread
+constexpr int CNT_HYP_PER_BLOCK = CNT_THREADS * CNT_HPT;
+constexpr int CNT_TILE = 512;                    // points per tile (8 KB of float4)
+
+struct TileRef {
+  int box;
+  int first;  // first point of the tile inside the crop
+};
+
+__global__ void __launch_bounds__(CNT_THREADS, 4)
+    k_count(const float4* __restrict__ crop, const BoxInfo* __restrict__ boxes, const TileRef* __restrict__ tiles,
+            const float4* __restrict__ hyp, int K, float thr, int* __restrict__ counts) {
+  __shared__ __align__(128) float4 pts[CNT_TILE];
+  __shared__ __align__(8) uint64_t bar;
+  const TileRef T = tiles[blockIdx.x];
+  const BoxInfo B = boxes[T.box];
+  const int n = min(CNT_TILE, B.n - T.first);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)n * 16u);
+    tma_load_1d(pts, crop + (size_t)B.pt_off + T.first, (uint32_t)n * 16u, &bar);
+  }
+  // hypotheses of this thread (block-column blockIdx.y covers CNT_HYP_PER_BLOCK hypotheses)
+  float ha[CNT_HPT], hb[CNT_HPT], hc[CNT_HPT], hd[CNT_HPT];
+  int cnt[CNT_HPT];
+  const int hbase = blockIdx.y * CNT_HYP_PER_BLOCK;
+#pragma unroll
+  for (int j = 0; j < CNT_HPT; ++j) {
+    const int k = hbase + j * CNT_THREADS + tid;
+    float4 h = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+    if (k < K) h = hyp[(size_t)T.box * K + k];
+    ha[j] = h.x;
+    hb[j] = h.y;
+    hc[j] = h.z;
+    hd[j] = h.w;
+    cnt[j] = 0;
+  }
+  mbar_wait(&bar, 0);
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    const float4 P = pts[i];  // warp-wide broadcast
+#pragma unroll
+    for (int j = 0; j < CNT_HPT; ++j) cnt[j] += (plane_dist(ha[j], hb[j], hc[j], hd[j], P.x, P.y, P.z) < thr) ? 1 : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < CNT_HPT; ++j) {
+    const int k = hbase + j * CNT_THREADS + tid;
+    if (k < K && cnt[j]) atomicAdd(counts + (size_t)T.box * K + k, cnt[j]);
+  }
+}
+
+// ---- K8 --------------------------------------------------------------------------------------
+__device__ void compute_roots2(double b, double c, double* roots) {
+  roots[0] = 0;
+  double d = b * b - 4.0 * c;
+  if (d < 0.0) d = 0.0;
+  double sd = sqrt(d);
+  roots[2] = 0.5 * (b + sd);
+  roots[1] = 0.5 * (b - sd);
+}
+__device__ void compute_roots(const double* m, double* roots) {
+  double c0 = m[0] * m[4] * m[8] + 2.0 * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] - m[8] * m[1] * m[1];
+  double c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+  double c2 = m[0] + m[4] + m[8];
+  if (fabs(c0) < 2.220446049250313e-16) {
+    compute_roots2(c2, c1, roots);
+    return;
+  }
+  const double s_inv3 = 1.0 / 3.0;
+  const double s_sqrt3 = sqrt(3.0);
+  double c2_over_3 = c2 * s_inv3;
+  double a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.0) a_over_3 = 0.0;
+  double half_b = 0.5 * (c0 + c2_over_3 * (2.0 * c2_over_3 * c2_over_3 - c1));
+  double q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.0) q = 0.0;
+  double rho = sqrt(-a_over_3);
+  double theta = atan2(sqrt(-q), half_b) * s_inv3;
+  double cos_theta = cos(theta), sin_theta = sin(theta);
+  roots[0] = c2_over_3 + 2.0 * rho * cos_theta;
+  roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  double t;
+  if (roots[0] >= roots[1]) {
+    t = roots[0];
+    roots[0] = roots[1];
+    roots[1] = t;
+  }
+  if (roots[1] >= roots[2]) {
+    t = roots[1];
+    roots[1] = roots[2];
+    roots[2] = t;
+    if (roots[0] >= roots[1]) {
+      t = roots[0];
+      roots[0] = roots[1];
+      roots[1] = t;
+    }
+  }
+  if (roots[0] <= 0) compute_roots2(c2, c1, roots);
+}
+__device__ void eigen33_smallest(const double* mat, double* evec) {
+  double scale = 0;
+  for (int i = 0; i < 9; ++i) scale = fmax(scale, fabs(mat[i]));
+  if (scale <= 2.2250738585072014e-308) scale = 1.0;
+  double m[9];
+  for (int i = 0; i < 9; ++i) m[i] = mat[i] / scale;
+  double roots[3];
+  compute_roots(m, roots);
+  m[0] -= roots[0];
+  m[4] -= roots[0];
+  m[8] -= roots[0];
+  double v1[3] = {m[1] * m[5] - m[2] * m[4], m[2] * m[3] - m[0] * m[5], m[0] * m[4] - m[1] * m[3]};
+  double v2[3] = {m[1] * m[8] - m[2] * m[7], m[2] * m[6] - m[0] * m[8], m[0] * m[7] - m[1] * m[6]};
+  double v3[3] = {m[4] * m[8] - m[5] * m[7], m[5] * m[6] - m[3] * m[8], m[3] * m[7] - m[4] * m[6]};
+  double l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+  double l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+  double l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+  const double* v;
+  double l;
+  if (l1 >= l2 && l1 >= l3) {
+    v = v1;
+    l = l1;
+  } else if (l2 >= l1 && l2 >= l3) {
+    v = v2;
+    l = l2;
+  } else {
+    v = v3;
+    l = l3;
+  }
+  double s = sqrt(l);
+  for (int i = 0; i < 3; ++i) evec[i] = v[i] / s;
+}
+
+constexpr int FIN_THREADS = 256;
+
+__global__ void __launch_bounds__(FIN_THREADS)
+    k_finish(const float4* __restrict__ crop, const BoxInfo* __restrict__ boxes, const float4* __restrict__ hyp,
+             const int* __restrict__ valid, int* __restrict__ counts, int K, float thr, int refine, int mode,
+             int max_iterations, double probability, ssb_plane_result* __restrict__ results,
+             unsigned char* __restrict__ mask, const int* __restrict__ mask_off) {
+  __shared__ double shd[33];
+  __shared__ int s_best_cnt[FIN_THREADS], s_best_k[FIN_THREADS];
+  __shared__ float s_coef[4], s_ref[4];
+  __shared__ int s_iter, s_bestk, s_bestc, s_rc;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const BoxInfo B = boxes[b];
+  ssb_plane_result R;
+  memset(&R, 0, sizeof(R));
+  R.best_hyp = -1;
+  if (B.n < 0) {
+    R.status = 1;
+    if (tid == 0) results[b] = R;
+    for (int k = tid; k < K; k += FIN_THREADS) counts[(size_t)b * K + k] = -1;
+    return;
+  }
+  R.n_points = B.n;
+  if (B.n == 0)  // empty crop: nothing is evaluated
+    for (int k = tid; k < K; k += FIN_THREADS) counts[(size_t)b * K + k] = -1;
+  // invalid hypotheses count as 0 (fixed-K) — k_count already left them at 0 because their
+  // coefficients are NaN.
+  if (mode == 0) {
+    int bc = 0, bk = -1;
+    for (int k = tid; k < K; k += FIN_THREADS) {
+      const int c = counts[(size_t)b * K + k];
+      if (c > bc) {  // strictly better, ascending k => first best per thread
+        bc = c;
+        bk = k;
+      }
+    }
+    s_best_cnt[tid] = bc;
+    s_best_k[tid] = bk;
+    __syncthreads();
+    for (int o = FIN_THREADS / 2; o > 0; o >>= 1) {
+      if (tid < o) {
+        const int c2 = s_best_cnt[tid + o], k2 = s_best_k[tid + o];
+        const int c1 = s_best_cnt[tid], k1 = s_best_k[tid];
+        if (c2 > c1 || (c2 == c1 && k2 >= 0 && (k1 < 0 || k2 < k1))) {
+          s_best_cnt[tid] = c2;
+          s_best_k[tid] = k2;
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      s_bestc = s_best_cnt[0];
+      s_bestk = s_best_cnt[0] > 0 ? s_best_k[0] : -1;
+      s_iter = B.n > 0 ? K : 0;
+    }
+  } else if (tid == 0) {
+    // RandomSampleConsensus::computeModel replayed over the precomputed counts
+    double kk = 1.0;
+    const double log_probability = log(1.0 - probability);
+    const double one_over = B.n > 0 ? 1.0 / (double)B.n : 0.0;
+    int iterations = 0, skipped = 0, s = 0, best = 0, bestk = -1;
+    const int max_skip = max_iterations * 10;
+    while (iterations < kk && skipped < max_skip && s < K && B.n > 0) {
+      const int k = s++;
+      if (!valid[(size_t)b * K + k]) {
+        ++skipped;
+        continue;
+      }
+      const int c = counts[(size_t)b * K + k];
+      if (c > best) {
+        best = c;
+        bestk = k;
+        double w = (double)best * one_over;
+        double pno = 1.0 - pow(w, 3.0);
+        pno = fmax(2.220446049250313e-16, pno);
+        pno = fmin(1.0 - 2.220446049250313e-16, pno);
+        kk = log_probability / log(pno);
+      }
+      ++iterations;
+      if (iterations > max_iterations) break;
+    }
+    s_bestc = best;
+    s_bestk = bestk;
+    s_iter = iterations;
+    // hypotheses the adaptive loop never reached are reported as not evaluated
+    for (int k = s; k < K; ++k) counts[(size_t)b * K + k] = -1;
+    for (int k = 0; k < s; ++k)
+      if (!valid[(size_t)b * K + k]) counts[(size_t)b * K + k] = -1;
+  }
+  __syncthreads();
+  R.best_hyp = s_bestk;
+  R.best_count = s_bestc;
+  R.iterations = s_iter;
+  unsigned char* mk = mask ? mask + mask_off[b] : nullptr;
+  if (s_bestk < 0) {
+    R.status = 2;
+    if (tid == 0) results[b] = R;
+    if (mk)
+      for (int i = tid; i < B.n; i += FIN_THREADS) mk[i] = 0;
+    return;
+  }
+  if (tid == 0) {
+    const float4 h = hyp[(size_t)b * K + s_bestk];
+    s_coef[0] = h.x;
+    s_coef[1] = h.y;
+    s_coef[2] = h.z;
+    s_coef[3] = h.w;
+  }
+  __syncthreads();
+  const float a = s_coef[0], bb = s_coef[1], c = s_coef[2], d = s_coef[3];
+  const float4* P = crop + (size_t)B.pt_off;
+  if (refine) {
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double cnt = 0;
+    for (int i = tid; i < B.n; i += FIN_THREADS) {
+      const float4 p = P[i];
+      if (plane_dist(a, bb, c, d, p.x, p.y, p.z) < thr) {
+        const double x = p.x, y = p.y, z = p.z;
+        cnt += 1.0;
+        acc[0] += x * x;
+        acc[1] += x * y;
+        acc[2] += x * z;
+        acc[3] += y * y;
+        acc[4] += y * z;
+        acc[5] += z * z;
+        acc[6] += x;
+        acc[7] += y;
+        acc[8] += z;
+      }
+    }
+    cnt = block_sum(cnt, shd);
+    for (int k = 0; k < 9; ++k) acc[k] = block_sum(acc[k], shd);
+    if (tid == 0) {
+      if (cnt < 4.0) {
+        for (int k = 0; k < 4; ++k) s_ref[k] = s_coef[k];
+      } else {
+        for (int k = 0; k < 9; ++k) acc[k] /= cnt;
+        double cov[9];
+        cov[0] = acc[0] - acc[6] * acc[6];
+        cov[1] = acc[1] - acc[6] * acc[7];
+        cov[2] = acc[2] - acc[6] * acc[8];
+        cov[4] = acc[3] - acc[7] * acc[7];
+        cov[5] = acc[4] - acc[7] * acc[8];
+        cov[8] = acc[5] - acc[8] * acc[8];
+        cov[3] = cov[1];
+        cov[6] = cov[2];
+        cov[7] = cov[5];
+        double ev[3];
+        eigen33_smallest(cov, ev);
+        const float n0 = (float)ev[0], n1 = (float)ev[1], n2 = (float)ev[2];
+        const float cx = (float)acc[6], cy = (float)acc[7], cz = (float)acc[8];
+        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(n0, cx), __fmul_rn(n1, cy)), __fadd_rn(__fmul_rn(n2, cz), __fmul_rn(0.f, 1.0f)));
+        s_ref[0] = n0;
+        s_ref[1] = n1;
+        s_ref[2] = n2;
+        s_ref[3] = __fmul_rn(-1.f, dot);
+      }
+    }
+  } else if (tid == 0) {
+    for (int k = 0; k < 4; ++k) s_ref[k] = s_coef[k];
+  }
+  if (tid == 0) s_rc = 0;
+  __syncthreads();
+  const float ra = s_ref[0], rb = s_ref[1], rc_ = s_ref[2], rd = s_ref[3];
+  int local = 0;
+  for (int i = tid; i < B.n; i += FIN_THREADS) {
+    const float4 p = P[i];
+    const bool in = plane_dist(ra, rb, rc_, rd, p.x, p.y, p.z) < thr;
+    local += in;
+    if (mk) mk[i] = in ? 1 : 0;
+  }
+  local = __reduce_add_sync(0xffffffffu, local);
+  if ((tid & 31) == 0 && local) atomicAdd(&s_rc, local);
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 0; k < 4; ++k) {
+      R.coef[k] = s_coef[k];
+      R.refined[k] = s_ref[k];
+    }
+    R.refined_count = s_rc;
+    results[b] = R;
+  }
+}
+
+static float effective_threshold(double thr) {
+  float t = (float)thr;
+  if ((double)t < thr) t = std::nextafterf(t, std::numeric_limits<float>::infinity());
+  return t;
+}
+
+}  // namespace ssb
+
+using namespace ssb;
+
+struct ssb_ransac {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  RBuf<unsigned char> d_msg, d_mask;
+  RBuf<BoxInfo> d_boxes;
+  RBuf<TileRef> d_tiles;
+  RBuf<int> d_triples, d_valid, d_counts, d_mask_off;
+  RBuf<float4> d_crop, d_hyp;
+  RBuf<ssb_plane_result> d_results;
+  // current problem
+  ssb_cloud_layout layout;
+  ssb_ransac_opts opts;
+  std::vector<BoxInfo> boxes;
+  std::vector<int> mask_off;
+  int nb = 0, K = 0, n_tiles = 0;
+  long long total_pts = 0;
+  bool uploaded = false;
+  long long launches = 0;
+};
+
+static int plan(ssb_ransac* r, const ssb_cloud_layout* L, const ssb_bbox* bx, int nb) {
+  r->boxes.resize(nb);
+  r->mask_off.assign(nb + 1, 0);
+  std::vector<TileRef> tiles;
+  long long off = 0;
+  for (int b = 0; b < nb; ++b) {
+    BoxInfo& B = r->boxes[b];
+    B.tl_x = bx[b].tl_x;
+    B.tl_y = bx[b].tl_y;
+    B.w = bx[b].width;
+    B.h = bx[b].height;
+    B.pad = 0;
+    // plane_segmentation.cpp:34-35 (+ negative corner rejection)
+    const bool spurious = B.h < 0 || B.w < 0 || (B.tl_x + B.w) > L->width || (B.tl_y + B.h) > L->height || B.tl_x < 0 || B.tl_y < 0;
+    B.n = spurious ? -1 : B.w * B.h;
+    B.pt_off = (int)off;
+    B.tile_off = (int)tiles.size();
+    r->mask_off[b] = (int)off;
+    if (B.n > 0) {
+      for (int f = 0; f < B.n; f += CNT_TILE) tiles.push_back({b, f});
+      off += B.n;
+      off = (off + 3) & ~3LL;  // keep every crop 64 B aligned for the bulk copies
+    }
+  }
+  r->mask_off[nb] = (int)off;
+  r->total_pts = off;
+  r->n_tiles = (int)tiles.size();
+  SSB_CUDA_CHECK(cudaSetDevice(r->device));
+  int rc;
+  if ((rc = r->d_boxes.ensure(nb)) || (rc = r->d_tiles.ensure(tiles.size())) || (rc = r->d_crop.ensure((size_t)off + CNT_TILE)) ||
+      (rc = r->d_mask.ensure((size_t)off + 16)) || (rc = r->d_mask_off.ensure(nb + 1)) || (rc = r->d_results.ensure(nb)))
+    return rc;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(r->d_boxes.p, r->boxes.data(), nb * sizeof(BoxInfo), cudaMemcpyHostToDevice, r->stream));
+  if (!tiles.empty())
+    SSB_CUDA_CHECK(cudaMemcpyAsync(r->d_tiles.p, tiles.data(), tiles.size() * sizeof(TileRef), cudaMemcpyHostToDevice, r->stream));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(r->d_mask_off.p, r->mask_off.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(r->stream));  // `tiles` is a local
+  return SSB_OK;
+}
+
+static int run_device(ssb_ransac* r) {
+  const int nb = r->nb, K = r->K;
+  cudaStream_t s = r->stream;
+  const float thr = effective_threshold(r->opts.threshold);
+  if (nb == 0) return SSB_OK;
+  SSB_CUDA_CHECK(cudaMemsetAsync(r->d_counts.p, 0, (size_t)nb * std::max(K, 1) * sizeof(int), s));
+  {
+    dim3 grid(8, nb);
+    k_crop<<<grid, 256, 0, s>>>(r->d_msg.p, r->layout, r->d_boxes.p, r->d_crop.p);
+    r->launches++;
+  }
+  if (K > 0) {
+    dim3 grid((K + 255) / 256, nb);
+    k_hyp<<<grid, 256, 0, s>>>(r->d_crop.p, r->d_boxes.p, r->d_triples.p, K, r->d_hyp.p, r->d_valid.p);
+    r->launches++;
+    if (r->n_tiles > 0) {
+      dim3 g2(r->n_tiles, (K + CNT_HYP_PER_BLOCK - 1) / CNT_HYP_PER_BLOCK);
+      k_count<<<g2, CNT_THREADS, 0, s>>>(r->d_crop.p, r->d_boxes.p, r->d_tiles.p, r->d_hyp.p, K, thr, r->d_counts.p);
+      r->launches++;
+    }
+  }
+  k_finish<<<nb, FIN_THREADS, 0, s>>>(r->d_crop.p, r->d_boxes.p, r->d_hyp.p, r->d_valid.p, r->d_counts.p, K, thr, r->opts.refine,
+                                      r->opts.mode, r->opts.max_iterations, r->opts.probability, r->d_results.p, r->d_mask.p,
+                                      r->d_mask_off.p);
+  r->launches++;
+  SSB_CUDA_CHECK(cudaGetLastError());
+  return SSB_OK;
+}
+
+extern "C" {
+
+void ssb_ransac_default_opts(ssb_ransac_opts* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->threshold = 0.01;   // plane_segmentation.cpp:645
+  o->refine = 1;         // :641
+  o->mode = 0;
+  o->max_iterations = 50;
+  o->probability = 0.99;
+  o->device = -1;
+}
+
+ssb_ransac* ssb_ransac_create(int device) {
+  ssb_ransac* r = new ssb_ransac();
+  cudaError_t e;
+  if (device < 0) {
+    e = cudaGetDevice(&device);
+    if (e != cudaSuccess) {
+      set_error("no CUDA device: %s (the CUDA back-end has no CPU fallback)", cudaGetErrorString(e));
+      delete r;
+      return nullptr;
+    }
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess || cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaSetDevice(%d)/stream creation failed: %s (the CUDA back-end has no CPU fallback)", device,
+              cudaGetErrorString(cudaGetLastError()));
+    delete r;
+    return nullptr;
+  }
+  r->device = device;
+  ssb_ransac_default_opts(&r->opts);
+  return r;
+}
+
+void ssb_ransac_destroy(ssb_ransac* r) {
+  if (!r) return;
+  cudaSetDevice(r->device);
+  if (r->stream) {
+    cudaStreamSynchronize(r->stream);
+    cudaStreamDestroy(r->stream);
+  }
+  delete r;
+}
+
+void* ssb_ransac_stream(ssb_ransac* r) { return r ? (void*)r->stream : nullptr; }
+long long ssb_ransac_launch_count(ssb_ransac* r) { return r ? r->launches : 0; }
+
+int ssb_ransac_upload(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout, const ssb_bbox* boxes, int n_boxes,
+                      const int* triples, int n_hyp, const ssb_ransac_opts* opts) {
+  if (!r || !msg || !layout || (n_boxes > 0 && !boxes) || n_boxes < 0 || n_hyp < 0 || (n_hyp > 0 && n_boxes > 0 && !triples)) {
+    set_error("ssb_ransac_upload: invalid argument");
+    return SSB_ERR_INVALID;
+  }
+  if (layout->width <= 0 || layout->height <= 0 || layout->point_step < 16 || layout->row_step < layout->width * layout->point_step ||
+      (layout->off_x | layout->off_y | layout->off_z | layout->off_rgb) & 3 || (layout->point_step & 3) || (layout->row_step & 3)) {
+    set_error("ssb_ransac_upload: unsupported PointCloud2 layout");
+    return SSB_ERR_INVALID;
+  }
+  SSB_CUDA_CHECK(cudaSetDevice(r->device));
+  r->layout = *layout;
+  if (opts)
+    r->opts = *opts;
+  else
+    ssb_ransac_default_opts(&r->opts);
+  r->nb = n_boxes;
+  r->K = n_hyp;
+  int rc = plan(r, layout, boxes, n_boxes);
+  if (rc) return rc;
+  const size_t msg_bytes = (size_t)layout->height * layout->row_step;
+  const size_t nh = (size_t)n_boxes * std::max(n_hyp, 1);
+  if ((rc = r->d_msg.ensure(msg_bytes + 16)) || (rc = r->d_triples.ensure(3 * nh)) || (rc = r->d_valid.ensure(nh)) ||
+      (rc = r->d_counts.ensure(nh)) || (rc = r->d_hyp.ensure(nh)))
+    return rc;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(r->d_msg.p, msg, msg_bytes, cudaMemcpyHostToDevice, r->stream));
+  if (n_hyp > 0 && n_boxes > 0)
+    SSB_CUDA_CHECK(cudaMemcpyAsync(r->d_triples.p, triples, 3 * (size_t)n_boxes * n_hyp * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+  r->uploaded = true;
+  return SSB_OK;
+}
+
+int ssb_ransac_run_resident(ssb_ransac* r) {
+  if (!r || !r->uploaded) {
+    set_error("ssb_ransac_run_resident: nothing uploaded");
+    return SSB_ERR_INVALID;
+  }
+  SSB_CUDA_CHECK(cudaSetDevice(r->device));
+  return run_device(r);
+}
+
+int ssb_ransac_fetch(ssb_ransac* r, ssb_plane_result* results, int* counts, unsigned char* mask) {
+  if (!r || !r->uploaded) return SSB_ERR_INVALID;
+  SSB_CUDA_CHECK(cudaSetDevice(r->device));
+  const int nb = r->nb, K = r->K;
+  if (results && nb) SSB_CUDA_CHECK(cudaMemcpyAsync(results, r->d_results.p, nb * sizeof(ssb_plane_result), cudaMemcpyDeviceToHost, r->stream));
+  if (counts && nb && K) SSB_CUDA_CHECK(cudaMemcpyAsync(counts, r->d_counts.p, (size_t)nb * K * sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+  std::vector<unsigned char> tmp;
+  if (mask && r->total_pts) {
+    tmp.resize(r->total_pts);
+    SSB_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), r->d_mask.p, r->total_pts, cudaMemcpyDeviceToHost, r->stream));
+  }
+  SSB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  if (mask && r->total_pts) {
+    // compact the 4-point alignment padding away: caller layout is the plain concatenation
+    size_t o = 0;
+    for (int b = 0; b < nb; ++b) {
+      if (r->boxes[b].n > 0) {
+        std::memcpy(mask + o, tmp.data() + r->mask_off[b], r->boxes[b].n);
+        o += r->boxes[b].n;
+      }
+    }
+  }
+  return SSB_OK;
+}
+
+int ssb_ransac_plane_batch(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout, const ssb_bbox* boxes, int n_boxes,
+                           const int* triples, int n_hyp, const ssb_ransac_opts* opts, ssb_plane_result* results, int* counts,
+                           unsigned char* mask) {
+  int rc = ssb_ransac_upload(r, msg, layout, boxes, n_boxes, triples, n_hyp, opts);
+  if (rc) return rc;
+  rc = run_device(r);
+  if (rc) return rc;
+  return ssb_ransac_fetch(r, results, counts, mask);
+}
+
+int ssb_crop_bbox(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout, const ssb_bbox* box, float* out) {
+  if (!r || !msg || !layout || !box) return SSB_ERR_INVALID;
+  ssb_ransac_opts o;
+  ssb_ransac_default_opts(&o);
+  int rc = ssb_ransac_upload(r, msg, layout, box, 1, nullptr, 0, &o);
+  if (rc) return rc;
+  if (r->boxes[0].n < 0) return -1;
+  if (r->boxes[0].n == 0 || !out) return r->boxes[0].n;
+  dim3 grid(8, 1);
+  k_crop<<<grid, 256, 0, r->stream>>>(r->d_msg.p, r->layout, r->d_boxes.p, r->d_crop.p);
+  r->launches++;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(out, r->d_crop.p, (size_t)r->boxes[0].n * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  return r->boxes[0].n;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+"""Python mirror of the planar_segmentation RANSAC path over the C-ABI:
+``plane_segmentation::segmentPointCloudData`` (bbox crop, plane_segmentation.cpp:24-82) and the
+``pcl::SACSegmentation`` plane fit of ``compute2DConvexHull`` (plane_segmentation.cpp:631-647),
+batched over all bounding boxes of a frame."""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+PLANE_RESULT_DTYPE = np.dtype([("status", "i4"), ("n_points", "i4"), ("best_hyp", "i4"), ("best_count", "i4"),
+                               ("iterations", "i4"), ("refined_count", "i4"), ("coef", "f4", 4), ("refined", "f4", 4)])
+
+
+@dataclasses.dataclass
+class CloudLayout:
+    width: int = 640
+    height: int = 480
+    point_step: int = 32
+    row_step: int = 32 * 640
+    offsets: tuple = (0, 4, 8, 16)
+
+    def c(self):
+        return _lib.CloudLayoutC(self.width, self.height, self.point_step, self.row_step, *self.offsets)
+
+
+class PlaneSegmentation:
+    """plane_segmentation (the RANSAC part): persistent device buffers + stream."""
+
+    def __init__(self, device: int = -1, threshold: float = 0.01, refine: bool = True, mode: int = 0,
+                 max_iterations: int = 50, probability: float = 0.99):
+        self._L = _lib.lib()
+        h = self._L.ssb_ransac_create(device)
+        if not h:
+            raise _lib.SsbError("ssb_ransac_create failed: " + _lib.last_error())
+        self._h = C.c_void_p(h)
+        self.opts = _lib.RansacOpts()
+        self._L.ssb_ransac_default_opts(C.byref(self.opts))
+        self.opts.threshold = threshold
+        self.opts.refine = int(refine)
+        self.opts.mode = mode
+        self.opts.max_iterations = max_iterations
+        self.opts.probability = probability
+        self._shape = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.ssb_ransac_destroy(self._h)
+            self._h = None
+
+    def segmentPointCloudData(self, box, msg, layout: CloudLayout):
+        """bbox crop: returns (h, w, 4) float32 [x,y,z,rgb] or None for a 'spurious' box."""
+        msg = np.ascontiguousarray(msg, dtype=np.uint8)
+        bx = np.ascontiguousarray(box, dtype=np.int32)
+        lc = layout.c()
+        n = self._L.ssb_crop_bbox(self._h, msg.ctypes.data, C.byref(lc), bx.ctypes.data, None)
+        if n == -1:
+            return None
+        check(n, "ssb_crop_bbox")
+        out = np.zeros((int(bx[3]), int(bx[2]), 4), dtype=np.float32)
+        if n > 0:
+            check(self._L.ssb_crop_bbox(self._h, msg.ctypes.data, C.byref(lc), bx.ctypes.data, out.ctypes.data),
+                  "ssb_crop_bbox")
+        return out
+
+    def _alloc(self, boxes, K, layout, want_counts, want_mask):
+        nb = boxes.shape[0]
+        res = np.zeros(nb, dtype=PLANE_RESULT_DTYPE)
+        counts = np.zeros((nb, K), dtype=np.int32) if want_counts else None
+        valid = (boxes[:, 2] >= 0) & (boxes[:, 3] >= 0) & (boxes[:, 0] >= 0) & (boxes[:, 1] >= 0) & \
+                (boxes[:, 0] + boxes[:, 2] <= layout.width) & (boxes[:, 1] + boxes[:, 3] <= layout.height)
+        total = int((boxes[valid, 2].astype(np.int64) * boxes[valid, 3]).sum())
+        mask = np.zeros(max(total, 1), dtype=np.uint8) if want_mask else None
+        return res, counts, mask, total
+
+    def fit_planes(self, msg, layout: CloudLayout, boxes, triples, want_counts=True, want_mask=True):
+        """RANSAC plane fit of every bbox crop (host buffers in, host buffers out)."""
+        msg = np.ascontiguousarray(msg, dtype=np.uint8)
+        boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 4)
+        triples = np.ascontiguousarray(triples, dtype=np.int32)
+        nb = boxes.shape[0]
+        K = triples.shape[1] if triples.ndim == 3 else 0
+        res, counts, mask, total = self._alloc(boxes, K, layout, want_counts, want_mask)
+        lc = layout.c()
+        check(self._L.ssb_ransac_plane_batch(self._h, msg.ctypes.data, C.byref(lc), boxes.ctypes.data, nb,
+                                             triples.ctypes.data, K, C.byref(self.opts), res.ctypes.data,
+                                             counts.ctypes.data if counts is not None else None,
+                                             mask.ctypes.data if mask is not None else None), "ssb_ransac_plane_batch")
+        return res, counts, (mask[:total] if mask is not None else None)
+
+    # ---- device-resident variant (benchmark `value` leg) --------------------------------------
+    def upload(self, msg, layout: CloudLayout, boxes, triples):
+        msg = np.ascontiguousarray(msg, dtype=np.uint8)
+        boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 4)
+        triples = np.ascontiguousarray(triples, dtype=np.int32)
+        K = triples.shape[1] if triples.ndim == 3 else 0
+        lc = layout.c()
+        check(self._L.ssb_ransac_upload(self._h, msg.ctypes.data, C.byref(lc), boxes.ctypes.data, boxes.shape[0],
+                                        triples.ctypes.data, K, C.byref(self.opts)), "ssb_ransac_upload")
+        self._shape = (boxes.copy(), K, layout)
+
+    def run_resident(self):
+        check(self._L.ssb_ransac_run_resident(self._h), "ssb_ransac_run_resident")
+
+    def fetch(self, want_counts=True, want_mask=True):
+        boxes, K, layout = self._shape
+        res, counts, mask, total = self._alloc(boxes, K, layout, want_counts, want_mask)
+        check(self._L.ssb_ransac_fetch(self._h, res.ctypes.data, counts.ctypes.data if counts is not None else None,
+                                       mask.ctypes.data if mask is not None else None), "ssb_ransac_fetch")
+        return res, counts, (mask[:total] if mask is not None else None)
+
+    def stream(self):
+        return self._L.ssb_ransac_stream(self._h)
+
+    def launch_count(self):
+        return self._L.ssb_ransac_launch_count(self._h)

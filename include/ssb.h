@@ -50,6 +50,7 @@ typedef struct ssb_lm_stats {
   double ms_device;      /* CUDA-event time of the whole LM loop on the device                    */
   double ms_total;       /* wall clock of the call                                                */
   long long kernel_launches; /* kernels launched by this call                                     */
+  double ms_pcg;         /* CUDA-event time spent inside the PCG kernel (sum over trials)         */
 } ssb_lm_stats;
 
 /* fills `o` with the defaults */
@@ -202,6 +203,9 @@ int ssb_ransac_run_resident(ssb_ransac* r);
 int ssb_ransac_fetch(ssb_ransac* r, ssb_plane_result* results, int* counts, unsigned char* mask);
 /* CUDA stream the handle launches on (for event timing by the caller), as an opaque pointer */
 void* ssb_ransac_stream(ssb_ransac* r);
+/* CUDA-event timing of the last run: out[0] = whole device pipeline (crop..finish) in ms, out[1] = the
+ * point x hypothesis sweep kernel alone */
+int ssb_ransac_timing(ssb_ransac* r, double out[2]);
 /* number of kernels launched so far on this handle */
 long long ssb_ransac_launch_count(ssb_ransac* r);
 

@@ -26,7 +26,7 @@ class LmStats(C.Structure):
     _fields_ = [("iterations", C.c_int), ("terminated", C.c_int), ("total_trials", C.c_int),
                 ("total_pcg_iters", C.c_int), ("chi2_initial", C.c_double), ("chi2_final", C.c_double),
                 ("lambda_final", C.c_double), ("ms_prepare", C.c_double), ("ms_device", C.c_double),
-                ("ms_total", C.c_double), ("kernel_launches", C.c_longlong)]
+                ("ms_total", C.c_double), ("kernel_launches", C.c_longlong), ("ms_pcg", C.c_double)]
 
 
 class CloudLayoutC(C.Structure):
@@ -57,7 +57,7 @@ SYMBOLS = [
     "ssb_graph_landmark_marginals", "ssb_graph_save_g2o", "ssb_graph_load_g2o", "ssb_graph_edge_linearize",
     "ssb_graph_solve_once", "ssb_comm_unique_id", "ssb_graph_attach_comm", "ssb_ransac_default_opts",
     "ssb_ransac_create", "ssb_ransac_destroy", "ssb_ransac_plane_batch", "ssb_ransac_upload",
-    "ssb_ransac_run_resident", "ssb_ransac_fetch", "ssb_ransac_stream", "ssb_ransac_launch_count", "ssb_crop_bbox",
+    "ssb_ransac_run_resident", "ssb_ransac_fetch", "ssb_ransac_stream", "ssb_ransac_launch_count", "ssb_ransac_timing", "ssb_crop_bbox",
     "ssb_last_error", "ssb_build_info", "ssb_graph_stream", "ssb_graph_snapshot", "ssb_graph_restore",
 ]
 
@@ -122,6 +122,7 @@ def lib():
     L.ssb_ransac_stream.restype = vp
     L.ssb_ransac_launch_count.argtypes = [vp]
     L.ssb_ransac_launch_count.restype = C.c_longlong
+    L.ssb_ransac_timing.argtypes = [vp, dp]
     L.ssb_crop_bbox.argtypes = [vp, vp, C.POINTER(CloudLayoutC), vp, vp]
     _LIB = L
     return L

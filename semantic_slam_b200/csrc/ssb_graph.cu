@@ -103,6 +103,8 @@ struct ssb_graph {
   int pcg_grid = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool;  // pairs around every k_pcg launch of the current optimize
+  size_t ev_used = 0;
   // device buffers
   DBuf<Pose> d_pose, d_pose_bak, d_pose_snap;
   DBuf<double> d_lm, d_lm_bak, d_lm_snap;
@@ -218,6 +220,7 @@ void ssb_graph_destroy(ssb_graph* g) {
   if (!g) return;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
+  for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
   if (g->h_scalars) cudaFreeHost(g->h_scalars);
@@ -544,7 +547,17 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
   double tol2 = g->opts.pcg_tol * g->opts.pcg_tol;
   int maxit = g->opts.max_pcg_iters;
   void* args[] = {(void*)&G, (void*)&lambda, (void*)&tol2, (void*)&maxit};
+  if (g->ev_used + 2 > g->ev_pool.size()) {
+    for (int k = 0; k < 64; ++k) {
+      cudaEvent_t e;
+      SSB_CUDA_CHECK(cudaEventCreate(&e));
+      g->ev_pool.push_back(e);
+    }
+  }
+  SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used], s));
   SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(g->pcg_grid), dim3(1024), args, 0, s));
+  SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used + 1], s));
+  g->ev_used += 2;
   g->launches++;
   if (apply) {
     k_backsub_update<<<(G.Np + G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
@@ -565,6 +578,7 @@ static int lm_loop(ssb_graph* g, int max_iterations, ssb_lm_stats* st) {
   DevGraph& G = g->G;
   cudaStream_t s = g->stream;
   g->history.clear();
+  g->ev_used = 0;
   SSB_CUDA_CHECK(cudaEventRecord(g->ev0, s));
   SSB_TRY(launch_chi2(g));
   SSB_TRY(read_scalars(g));
@@ -634,6 +648,12 @@ static int lm_loop(ssb_graph* g, int max_iterations, ssb_lm_stats* st) {
   float ms = 0;
   SSB_CUDA_CHECK(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
   st->ms_device = ms;
+  st->ms_pcg = 0.0;
+  for (size_t k = 0; k + 1 < g->ev_used; k += 2) {
+    float t = 0;
+    SSB_CUDA_CHECK(cudaEventElapsedTime(&t, g->ev_pool[k], g->ev_pool[k + 1]));
+    st->ms_pcg += t;
+  }
   st->iterations = it;
   st->chi2_final = currentChi;
   st->lambda_final = lambda;

@@ -474,6 +474,7 @@ struct ssb_ransac {
   long long total_pts = 0;
   bool uploaded = false;
   long long launches = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // run begin/end, k_count begin/end
 };
 
 static int plan(ssb_ransac* r, const ssb_cloud_layout* L, const ssb_bbox* bx, int nb) {
@@ -521,6 +522,11 @@ static int run_device(ssb_ransac* r) {
   cudaStream_t s = r->stream;
   const float thr = effective_threshold(r->opts.threshold);
   if (nb == 0) return SSB_OK;
+  for (int k = 0; k < 4; ++k)
+    if (!r->ev[k]) SSB_CUDA_CHECK(cudaEventCreate(&r->ev[k]));
+  SSB_CUDA_CHECK(cudaEventRecord(r->ev[0], s));
+  SSB_CUDA_CHECK(cudaEventRecord(r->ev[2], s));
+  SSB_CUDA_CHECK(cudaEventRecord(r->ev[3], s));
   SSB_CUDA_CHECK(cudaMemsetAsync(r->d_counts.p, 0, (size_t)nb * std::max(K, 1) * sizeof(int), s));
   {
     dim3 grid(8, nb);
@@ -533,7 +539,9 @@ static int run_device(ssb_ransac* r) {
     r->launches++;
     if (r->n_tiles > 0) {
       dim3 g2(r->n_tiles, (K + CNT_HYP_PER_BLOCK - 1) / CNT_HYP_PER_BLOCK);
+      SSB_CUDA_CHECK(cudaEventRecord(r->ev[2], s));
       k_count<<<g2, CNT_THREADS, 0, s>>>(r->d_crop.p, r->d_boxes.p, r->d_tiles.p, r->d_hyp.p, K, thr, r->d_counts.p);
+      SSB_CUDA_CHECK(cudaEventRecord(r->ev[3], s));
       r->launches++;
     }
   }
@@ -541,11 +549,26 @@ static int run_device(ssb_ransac* r) {
                                       r->opts.mode, r->opts.max_iterations, r->opts.probability, r->d_results.p, r->d_mask.p,
                                       r->d_mask_off.p);
   r->launches++;
+  SSB_CUDA_CHECK(cudaEventRecord(r->ev[1], s));
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;
 }
 
 extern "C" {
+
+// CUDA-event timing of the last run: out[0] = whole device pipeline (crop..finish) ms, out[1] = k_count ms
+int ssb_ransac_timing(ssb_ransac* r, double out[2]) {
+  if (!r || !out || !r->ev[0]) return SSB_ERR_INVALID;
+  SSB_CUDA_CHECK(cudaSetDevice(r->device));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  float a = 0, b = 0;
+  SSB_CUDA_CHECK(cudaEventElapsedTime(&a, r->ev[0], r->ev[1]));
+  SSB_CUDA_CHECK(cudaEventElapsedTime(&b, r->ev[2], r->ev[3]));
+  out[0] = a;
+  out[1] = b;
+  return SSB_OK;
+}
+
 
 void ssb_ransac_default_opts(ssb_ransac_opts* o) {
   if (!o) return;
@@ -588,6 +611,8 @@ void ssb_ransac_destroy(ssb_ransac* r) {
     cudaStreamSynchronize(r->stream);
     cudaStreamDestroy(r->stream);
   }
+  for (int k = 0; k < 4; ++k)
+    if (r->ev[k]) cudaEventDestroy(r->ev[k]);
   delete r;
 }
 

@@ -112,6 +112,12 @@ class PlaneSegmentation:
                                        mask.ctypes.data if mask is not None else None), "ssb_ransac_fetch")
         return res, counts, (mask[:total] if mask is not None else None)
 
+    def timing(self):
+        """(ms of the whole device pipeline, ms of the point x hypothesis sweep) of the last run"""
+        out = np.zeros(2)
+        check(self._L.ssb_ransac_timing(self._h, out.ctypes.data_as(_lib.dp)), "ssb_ransac_timing")
+        return float(out[0]), float(out[1])
+
     def stream(self):
         return self._L.ssb_ransac_stream(self._h)
 

@@ -9,14 +9,14 @@ if which in ("all", "graph"):
     name = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     spec = synth.make_config_graph(name)
-    g = GraphSLAM()
+    g = GraphSLAM(preconditioner=int(os.environ.get('PRECOND', '0')), pcg_tol=float(os.environ.get('PCGTOL', '1e-10')))
     t = time.time(); synth.load_graph(g, spec); print("load", time.time() - t)
     g.snapshot()
     for rep in range(3):
         g.restore()
         t = time.time(); g.optimize_resident(iters); dt = time.time() - t
         print(f"rep {rep}: wall {dt*1e3:.1f} ms  device {g.stats['ms_device']:.1f} ms iters {g.iterations} trials {g.stats['total_trials']} "
-              f"pcg {g.stats['total_pcg_iters']} launches {g.stats['kernel_launches']} chi2 {g.stats['chi2_final']:.6f}")
+              f"pcg {g.stats['total_pcg_iters']} ms_pcg {g.stats['ms_pcg']:.1f} launches {g.stats['kernel_launches']} chi2 {g.stats['chi2_final']:.6f}")
     np.set_printoptions(linewidth=200, precision=6)
     print(g.history)
     print("us per pcg iter (upper bound):", g.stats['ms_device'] * 1e3 / max(1, g.stats['total_pcg_iters']))

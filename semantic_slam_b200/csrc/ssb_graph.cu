@@ -115,6 +115,12 @@ struct ssb_graph {
   DBuf<double> d_Hpp, d_bp, d_Hoff, d_Hll, d_bl, d_HplL, d_HplP, d_HllInv, d_Dinv, d_g;
   DBuf<double> d_x, d_r, d_z, d_p0, d_p1, d_q, d_v, d_dl, d_part, d_scalars, d_tmp;
   DBuf<int> d_iscalars;
+  // coarse level
+  DBuf<double> d_Bmat, d_Grun, d_panel;
+  DBuf<int> d_run_lm, d_run_group, d_run_e0, d_lm_run_rowptr, d_grp_run_rowptr, d_grp_runs;
+  DBuf<BarSlot> d_slots;
+  CoarseDev Cz;
+  size_t pcg_smem = 0;
   double* h_scalars = nullptr;  // pinned: 8 doubles
   int* h_iscalars = nullptr;    // pinned: 4 ints
   DevGraph G;
@@ -205,14 +211,16 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
     delete g;
     return nullptr;
   }
+  g->pcg_grid = std::min(g->num_sms, PCG_THREADS);  // one persistent CTA per SM
+  g->pcg_smem = (size_t)(PCG_THREADS + 14 * 6 * g->pcg_grid + GJ_SLICES * 36) * sizeof(double);
   int nb = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg, 1024, 0);
+  e = cudaFuncSetAttribute(k_pcg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_smem);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg, PCG_THREADS, g->pcg_smem);
   if (e != cudaSuccess || nb < 1) {
-    set_error("k_pcg cannot be made resident (occupancy %d): %s", nb, cudaGetErrorString(e));
+    set_error("k_pcg cannot be made resident (occupancy %d, %zu B smem): %s", nb, g->pcg_smem, cudaGetErrorString(e));
     delete g;
     return nullptr;
   }
-  g->pcg_grid = g->num_sms;  // one persistent CTA per SM
   return g;
 }
 
@@ -377,13 +385,49 @@ static int prepare(ssb_graph* g) {
     std::vector<int> lm_rowptr(Nl + 1, 0);
     for (auto& e : g->pl) lm_rowptr[e.l + 1]++;
     for (int l = 0; l < Nl; ++l) lm_rowptr[l + 1] += lm_rowptr[l];
-    std::vector<int> fill(lm_rowptr.begin(), lm_rowptr.end() - 1);
     std::vector<PLEdge> plL(std::max(El, 1));
     g->plL_of_edge.assign(El, 0);
-    for (int k = 0; k < El; ++k) {
-      int pos = fill[g->pl[k].l]++;
-      plL[pos] = g->pl[k];
-      g->plL_of_edge[k] = pos;
+    {
+      // L-order: by landmark, then by pose index, then by creation order
+      std::vector<int> ord(El);
+      for (int k = 0; k < El; ++k) ord[k] = k;
+      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+        const PLEdge &ea = g->pl[a], &eb = g->pl[b];
+        if (ea.l != eb.l) return ea.l < eb.l;
+        return ea.p < eb.p;
+      });
+      for (int pos = 0; pos < El; ++pos) {
+        plL[pos] = g->pl[ord[pos]];
+        g->plL_of_edge[ord[pos]] = pos;
+      }
+    }
+    // coarse aggregates: one per persistent CTA, contiguous pose ranges of C poses (multiple of 5)
+    const int nblk = g->pcg_grid;
+    int Cc = (Np + nblk - 1) / nblk;
+    Cc = std::max(5, ((Cc + 4) / 5) * 5);
+    std::vector<int> run_lm, run_group, run_e0, lm_run_rowptr(Nl + 1, 0);
+    for (int l = 0; l < Nl; ++l) {
+      lm_run_rowptr[l] = (int)run_lm.size();
+      int prev = -1;
+      for (int e = lm_rowptr[l]; e < lm_rowptr[l + 1]; ++e) {
+        const int grp = plL[e].p / Cc;
+        if (grp != prev) {
+          run_lm.push_back(l);
+          run_group.push_back(grp);
+          run_e0.push_back(e);
+          prev = grp;
+        }
+      }
+    }
+    lm_run_rowptr[Nl] = (int)run_lm.size();
+    run_e0.push_back(El);
+    const int n_runs = (int)run_lm.size();
+    std::vector<int> grp_run_rowptr(nblk + 1, 0), grp_runs(std::max(n_runs, 1));
+    for (int r = 0; r < n_runs; ++r) grp_run_rowptr[run_group[r] + 1]++;
+    for (int b = 0; b < nblk; ++b) grp_run_rowptr[b + 1] += grp_run_rowptr[b];
+    {
+      std::vector<int> f(grp_run_rowptr.begin(), grp_run_rowptr.end() - 1);
+      for (int r = 0; r < n_runs; ++r) grp_runs[f[run_group[r]]++] = r;
     }
     // pose-major index over L-order positions
     std::vector<int> ppl_rowptr(Np + 1, 0);
@@ -443,7 +487,42 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_scalars.ensure(8));
     SSB_TRY(g->d_iscalars.ensure(4));
     SSB_TRY(g->d_tmp.ensure(128));
+    const int ncoarse = 6 * nblk;
+    SSB_TRY(g->d_Bmat.ensure((size_t)36 * Np));
+    SSB_TRY(g->d_Grun.ensure((size_t)18 * n_runs));
+    SSB_TRY(g->d_panel.ensure((size_t)2 * (6 * ncoarse + 8)));
+    SSB_TRY(g->d_run_lm.ensure(n_runs));
+    SSB_TRY(g->d_run_group.ensure(n_runs));
+    SSB_TRY(g->d_run_e0.ensure(n_runs + 1));
+    SSB_TRY(g->d_lm_run_rowptr.ensure(Nl + 1));
+    SSB_TRY(g->d_grp_run_rowptr.ensure(nblk + 1));
+    SSB_TRY(g->d_grp_runs.ensure(n_runs));
+    SSB_TRY(g->d_slots.ensure((size_t)2 * nblk));
     cudaStream_t s = g->stream;
+    if (n_runs) {
+      SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_run_lm.p, run_lm.data(), n_runs * sizeof(int), cudaMemcpyHostToDevice, s));
+      SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_run_group.p, run_group.data(), n_runs * sizeof(int), cudaMemcpyHostToDevice, s));
+      SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_runs.p, grp_runs.data(), n_runs * sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_run_e0.p, run_e0.data(), (n_runs + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_run_rowptr.p, lm_run_rowptr.data(), (Nl + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_run_rowptr.p, grp_run_rowptr.data(), (nblk + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    {
+      CoarseDev& Cz = g->Cz;
+      Cz.enabled = g->opts.preconditioner == 1 ? 1 : 0;
+      Cz.C = Cc;
+      Cz.nc = ncoarse;
+      Cz.Bmat = g->d_Bmat.p;
+      Cz.Grun = g->d_Grun.p;
+      Cz.run_lm = g->d_run_lm.p;
+      Cz.run_group = g->d_run_group.p;
+      Cz.run_e0 = g->d_run_e0.p;
+      Cz.lm_run_rowptr = g->d_lm_run_rowptr.p;
+      Cz.grp_run_rowptr = g->d_grp_run_rowptr.p;
+      Cz.grp_runs = g->d_grp_runs.p;
+      Cz.n_runs = n_runs;
+      Cz.panel = g->d_panel.p;
+    }
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_scalars.p, 0, 8 * sizeof(double), s));
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_iscalars.p, 0, 4 * sizeof(int), s));
     if (Np) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_fixed.p, pfix.data(), Np, cudaMemcpyHostToDevice, s));
@@ -531,6 +610,14 @@ static int launch_linearize(ssb_graph* g) {
     k_lin_poses<<<(G.Np + 63) / 64, 64, 0, g->stream>>>(G);
     g->launches++;
   }
+  if (g->Cz.enabled) {
+    k_coarse_basis<<<g->pcg_grid, 256, 0, g->stream>>>(G, g->Cz);
+    g->launches++;
+    if (g->Cz.n_runs) {
+      k_coarse_runs<<<(g->Cz.n_runs + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
+      g->launches++;
+    }
+  }
   SSB_CUDA_CHECK(cudaGetLastError());
   g->have_system = true;
   return SSB_OK;
@@ -546,7 +633,9 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
   g->launches++;
   double tol2 = g->opts.pcg_tol * g->opts.pcg_tol;
   int maxit = g->opts.max_pcg_iters;
-  void* args[] = {(void*)&G, (void*)&lambda, (void*)&tol2, (void*)&maxit};
+  BarSlot* slots = g->d_slots.p;
+  SSB_CUDA_CHECK(cudaMemsetAsync(slots, 0, (size_t)2 * g->pcg_grid * sizeof(BarSlot), s));
+  void* args[] = {(void*)&G, (void*)&g->Cz, (void*)&slots, (void*)&lambda, (void*)&tol2, (void*)&maxit};
   if (g->ev_used + 2 > g->ev_pool.size()) {
     for (int k = 0; k < 64; ++k) {
       cudaEvent_t e;
@@ -555,7 +644,7 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
     }
   }
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used], s));
-  SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(g->pcg_grid), dim3(1024), args, 0, s));
+  SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(g->pcg_grid), dim3(PCG_THREADS), args, g->pcg_smem, s));
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used + 1], s));
   g->ev_used += 2;
   g->launches++;

@@ -258,71 +258,422 @@ __global__ void __launch_bounds__(64) k_prep_poses(DevGraph G, double lambda) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: persistent cooperative block-Jacobi PCG on the (implicit) Schur complement
-//   S x = g,  S = Hpp + lambda I - Hpl (Hll + lambda I)^-1 Hlp
-// 3 grid-wide syncs per iteration.  6 lanes per pose (one per row), 5 poses per warp; one warp per
-// landmark in the landmark sweep.  All reductions are fixed-order => bit-reproducible.
+// Coarse (rigid-body) level of the preconditioner.  Every persistent CTA owns a contiguous range of
+// C poses = one aggregate; its 6 coarse unknowns are a world-frame translation d and rotation w of
+// the aggregate about its centroid c, prolonged to pose i (right-multiplied MQT increment) by
+//   B_i = [ R_i'  -R_i' [t_i - c]x ;  0  1/2 R_i' ]      (zero for fixed poses)
+// A_c = P' S P (nc = 6 * #CTAs) is assembled and inverted inside k_pcg (block Gauss-Jordan, one
+// pivot aggregate per step, one grid barrier per step); each CTA keeps its 6 rows of A_c^-1 in smem.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double grid_total(const double* part, int nblk, double* sh) {
-  // every block sums the same partials in the same order
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (w == 0) {
-    double t = 0.0;
-    for (int k = lane; k < nblk; k += 32) t += __ldcg(part + k);
-    t = warp_sum(t);
-    if (lane == 0) sh[32] = t;
-  }
-  __syncthreads();
-  double r = sh[32];
-  __syncthreads();
-  return r;
+struct CoarseDev {
+  int enabled;
+  int C;    // poses per CTA (multiple of 5)
+  int nc;   // 6 * gridDim.x
+  double* Bmat;            // [Np][36]
+  double* Grun;            // [n_runs][18]  (3x6) = sum_e HplL_e B_p(e) over the run
+  const int* run_lm;       // [n_runs]
+  const int* run_group;    // [n_runs]
+  const int* run_e0;       // [n_runs+1] L-order edge range of each run
+  const int* lm_run_rowptr;   // [Nl+1] runs of each landmark (contiguous)
+  const int* grp_run_rowptr;  // [ngroups+1]
+  const int* grp_runs;        // runs sorted by group
+  int n_runs;
+  double* panel;           // [2][6*nc + 8] Gauss-Jordan pivot panels (double buffered)
+};
+
+struct BarSlot {  // one 64 B line per CTA and buffer
+  double v[7];
+  unsigned epoch;
+  unsigned pad;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(1024, 1) k_pcg(DevGraph G, double lambda, double tol2, int maxit) {
-  cg::grid_group grid = cg::this_grid();
+// Grid barrier fused with a fixed-order all-reduce of one double per CTA (+ optional all-gather of 6
+// doubles per CTA into `gather` (smem, 6 * gridDim.x)).  `part_sh` = gridDim.x doubles of smem, `sh` = 33.
+// Every thread of every CTA must call it; requires gridDim.x <= blockDim.x and co-resident CTAs.
+__device__ __forceinline__ double grid_bar_sum(BarSlot* slots, unsigned& epoch, double my_partial, const double* my6,
+                                               double* gather, double* part_sh, double* sh) {
+  ++epoch;
+  BarSlot* S = slots + (size_t)(epoch & 1u) * gridDim.x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    BarSlot* me = S + blockIdx.x;
+    me->v[0] = my_partial;
+    if (my6) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) me->v[1 + k] = my6[k];
+    }
+    __threadfence();
+    st_release_u32(&me->epoch, epoch);
+  }
+  if (threadIdx.x < gridDim.x) {
+    const BarSlot* o = S + threadIdx.x;
+    while (ld_acquire_u32(&o->epoch) != epoch) {
+    }
+    part_sh[threadIdx.x] = __ldcg(&o->v[0]);
+    if (gather) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) gather[6 * threadIdx.x + k] = __ldcg(&o->v[1 + k]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += 32) t += part_sh[k];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+// deterministic block reduction of 6 values per thread -> out6 (smem), valid after return
+__device__ __forceinline__ void block_sum6(const double* v, double* out6, double* scratch /* 6*32 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double r[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) r[k] = warp_sum(v[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) scratch[6 * w + k] = r[k];
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double t = lane < nw ? scratch[6 * lane + k] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) out6[k] = t;
+    }
+  }
+  __syncthreads();
+}
+
+// per LM iteration (poses changed): aggregate centroids and the prolongation blocks B_i
+__global__ void __launch_bounds__(256) k_coarse_basis(DevGraph G, CoarseDev Cz) {
   __shared__ double sh[33];
+  __shared__ double cen[3];
+  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np, p0 + Cz.C);
+  double s[3] = {0, 0, 0};
+  for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x)
+    for (int k = 0; k < 3; ++k) s[k] += G.pose[i].t[k];
+  for (int k = 0; k < 3; ++k) {
+    double t = block_sum(s[k], sh);
+    if (threadIdx.x == 0) cen[k] = p1 > p0 ? t / (double)(p1 - p0) : 0.0;
+  }
+  __syncthreads();
+  for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+    double* B = Cz.Bmat + 36 * (size_t)i;
+    if (G.pose_fixed[i]) {
+      for (int k = 0; k < 36; ++k) B[k] = 0.0;
+      continue;
+    }
+    const Pose X = G.pose[i];
+    double R[9];
+    quat_to_R(X.q, R);
+    const double d[3] = {X.t[0] - cen[0], X.t[1] - cen[1], X.t[2] - cen[2]};
+    const double Sx[9] = {0, -d[2], d[1], d[2], 0, -d[0], -d[1], d[0], 0};
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        const double rt = R[3 * c + r];  // R'
+        B[6 * r + c] = rt;
+        B[6 * r + 3 + c] = -(R[r] * Sx[c] + R[3 + r] * Sx[3 + c] + R[6 + r] * Sx[6 + c]);  // -(R' [d]x)
+        B[6 * (3 + r) + c] = 0.0;
+        B[6 * (3 + r) + 3 + c] = 0.5 * rt;
+      }
+  }
+}
+
+// per LM iteration: G_run = sum over the run of HplL_e (3x6) * B_p(e) (6x6)
+__global__ void __launch_bounds__(128) k_coarse_runs(DevGraph G, CoarseDev Cz) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Cz.n_runs) return;
+  double acc[18];
+  for (int k = 0; k < 18; ++k) acc[k] = 0.0;
+  for (int e = Cz.run_e0[r]; e < Cz.run_e0[r + 1]; ++e) {
+    const double* Hl = G.HplL + 18 * (size_t)e;
+    const double* B = Cz.Bmat + 36 * (size_t)G.pl[e].p;
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 6; ++c) {
+        double t = 0.0;
+        for (int k = 0; k < 6; ++k) t += Hl[6 * a + k] * B[6 * k + c];
+        acc[6 * a + c] += t;
+      }
+  }
+  for (int k = 0; k < 18; ++k) Cz.Grun[18 * (size_t)r + k] = acc[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: persistent cooperative PCG on the (implicit) Schur complement
+//   S x = g,  S = Hpp + lambda I - Hpl (Hll + lambda I)^-1 Hlp
+// preconditioned by block-Jacobi (6x6 diagonal blocks of S) plus, optionally, the rigid-body coarse
+// level above (additive two-level).  One CTA per SM, each owning a contiguous pose range; 6 lanes
+// per pose (one per row), 5 poses per warp; one warp per landmark in the landmark sweep.
+// 3 grid-wide barriers per iteration, each fused with the all-reduce it needs; all reductions are
+// fixed-order => bit-reproducible for a fixed grid.
+// ---------------------------------------------------------------------------------------------
+constexpr int PCG_THREADS = 1024;
+constexpr int GJ_SLICES = 28;  // 28 * 36 = 1008 threads take part in the aggregate reduction
+
+__global__ void __launch_bounds__(PCG_THREADS, 1)
+    k_pcg(DevGraph G, CoarseDev Cz, BarSlot* slots, double lambda, double tol2, int maxit) {
+  extern __shared__ __align__(16) double dsm[];
+  __shared__ double sh[33];
+  __shared__ double s6[8], zc6[8], red6[6 * 32];
+  __shared__ int s_flag;
+  const int nblk = gridDim.x;
+  const int nc = 6 * nblk;
+  // dynamic smem carve-up
+  double* part_sh = dsm;                 // [1024]
+  double* Arow = part_sh + PCG_THREADS;  // [6][nc]   rows of A_c, then of A_c^-1
+  double* panel_sh = Arow + 6 * nc;      // [6][nc]
+  double* rc = panel_sh + 6 * nc;        // [nc] restricted residual (kept by recurrence)
+  double* qc = rc + nc;                  // [nc] gathered restricted q
+  double* red = qc + nc;                 // [GJ_SLICES][36]
+  const bool coarse = Cz.enabled != 0;
+
   const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
-  const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int total_warps = gridDim.x * warps_per_block;
+  const int gw = blockIdx.x * warps_per_block + warp;
+  const int total_warps = nblk * warps_per_block;
   const int slot = lane / 6, comp = lane - 6 * slot;
   const bool lane_active = lane < 30;
   const int base_lane = 6 * slot;
-  const int nblk = gridDim.x;
-  double* partA = G.part;
-  double* partB = G.part + PART_STRIDE;
-  double* partC = G.part + 2 * PART_STRIDE;
+  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np, p0 + Cz.C);
+  unsigned epoch = 0;
   double* pold = G.p0;
   double* pnew = G.p1;
+  int status = 0;
 
-  // ---- init: x = 0, r = g, z = Dinv r, pold = 0
+  // =================== coarse prologue: assemble my 6 rows of A_c, invert by block Gauss-Jordan ==========
+  if (coarse) {
+    for (int k = threadIdx.x; k < 6 * nc; k += blockDim.x) Arow[k] = 0.0;
+    __syncthreads();
+    const int myg = blockIdx.x;
+    // (a) diagonal block: sum_i B_i' (Hpp_ii + lambda I) B_i + intra-aggregate pose-pose edges
+    {
+      const int ent = threadIdx.x % 36, sl = threadIdx.x / 36;
+      const int r = ent / 6, c = ent - 6 * r;
+      double acc = 0.0;
+      if (sl < GJ_SLICES) {
+        for (int i = p0 + sl; i < p1; i += GJ_SLICES) {
+          const double* B = Cz.Bmat + 36 * (size_t)i;
+          const double* H = G.Hpp + 36 * (size_t)i;
+          // (B' (H + lambda) B)[r][c]
+          double t = 0.0;
+          for (int a = 0; a < 6; ++a) {
+            double hb = lambda * B[6 * a + c];
+            for (int b = 0; b < 6; ++b) hb += H[6 * a + b] * B[6 * b + c];
+            t += B[6 * a + r] * hb;
+          }
+          acc += t;
+          // pose-pose edges where i is the `from` vertex and the other end is in the same aggregate:
+          // contributes B_i' Hoff B_j and its transpose to the diagonal block
+          for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
+            const int code = G.pose_pp_idx[kk];
+            if (code & 1) continue;
+            const int e = code >> 1;
+            const int j = G.pp[e].j;
+            if (j < p0 || j >= p1) continue;
+            const double* Bj = Cz.Bmat + 36 * (size_t)j;
+            const double* Ho = G.Hoff + 36 * (size_t)e;
+            double t1 = 0.0, t2 = 0.0;
+            for (int a = 0; a < 6; ++a) {
+              double hb1 = 0.0, hb2 = 0.0;
+              for (int b = 0; b < 6; ++b) {
+                hb1 += Ho[6 * a + b] * Bj[6 * b + c];  // (Hoff Bj)[a][c]
+                hb2 += Ho[6 * a + b] * Bj[6 * b + r];  // (Hoff Bj)[a][r]
+              }
+              t1 += B[6 * a + r] * hb1;  // (Bi' Hoff Bj)[r][c]
+              t2 += B[6 * a + c] * hb2;  // (Bi' Hoff Bj)[c][r]  -> transpose term
+            }
+            acc += t1 + t2;
+          }
+        }
+        red[36 * sl + ent] = acc;
+      }
+      __syncthreads();
+      if (threadIdx.x < 36) {
+        double t = 0.0;
+        for (int k = 0; k < GJ_SLICES; ++k) t += red[36 * k + threadIdx.x];
+        const int rr = threadIdx.x / 6, cc = threadIdx.x - 6 * rr;
+        if (p1 <= p0 && rr == cc) t = 1.0;  // empty aggregate: identity keeps A_c invertible
+        Arow[rr * nc + 6 * myg + cc] = t;
+      }
+      __syncthreads();
+    }
+    // (b) pose-pose edges crossing aggregates, (c) landmark terms: sequential over the list, 36 lanes each
+    if (threadIdx.x < 36) {
+      const int r = threadIdx.x / 6, c = threadIdx.x - 6 * r;
+      for (int i = p0; i < p1; ++i) {
+        const double* B = Cz.Bmat + 36 * (size_t)i;
+        for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
+          const int code = G.pose_pp_idx[kk];
+          const int e = code >> 1, role = code & 1;
+          const int j = role == 0 ? G.pp[e].j : G.pp[e].i;
+          if (j >= p0 && j < p1) continue;
+          const int gj = j / Cz.C;
+          const double* Bj = Cz.Bmat + 36 * (size_t)j;
+          const double* Ho = G.Hoff + 36 * (size_t)e;
+          double t = 0.0;
+          for (int a = 0; a < 6; ++a) {
+            double hb = 0.0;
+            for (int b = 0; b < 6; ++b) hb += (role == 0 ? Ho[6 * a + b] : Ho[6 * b + a]) * Bj[6 * b + c];
+            t += B[6 * a + r] * hb;
+          }
+          Arow[r * nc + 6 * gj + c] += t;
+        }
+      }
+      // landmark runs of my aggregate
+      for (int q = Cz.grp_run_rowptr[myg]; q < Cz.grp_run_rowptr[myg + 1]; ++q) {
+        const int ra = Cz.grp_runs[q];
+        const int l = Cz.run_lm[ra];
+        const double* Ga = Cz.Grun + 18 * (size_t)ra;  // 3x6
+        const double* Wu = G.HllInv + 6 * (size_t)l;
+        const double W[9] = {Wu[0], Wu[1], Wu[2], Wu[1], Wu[3], Wu[4], Wu[2], Wu[4], Wu[5]};
+        // u = (Ga' W)[r][:]  (1x3)
+        double u[3];
+        for (int v = 0; v < 3; ++v) u[v] = Ga[r] * W[v] + Ga[6 + r] * W[3 + v] + Ga[12 + r] * W[6 + v];
+        for (int rb = Cz.lm_run_rowptr[l]; rb < Cz.lm_run_rowptr[l + 1]; ++rb) {
+          const double* Gb = Cz.Grun + 18 * (size_t)rb;
+          const int gb = Cz.run_group[rb];
+          Arow[r * nc + 6 * gb + c] -= u[0] * Gb[c] + u[1] * Gb[6 + c] + u[2] * Gb[12 + c];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- block Gauss-Jordan: step k pivots on aggregate k ----
+    if (threadIdx.x == 0) s_flag = 0;
+    for (int k = 0; k < nblk; ++k) {
+      double* gp = Cz.panel + (size_t)(k & 1) * (6 * nc + 8);
+      if ((int)blockIdx.x == k) {
+        // pivot inverse (SPD 6x6) by thread 0, then scale my rows: panel = Pinv * Arow, panel[:,k] = Pinv
+        if (threadIdx.x == 0) {
+          double Pv[36];
+          for (int a = 0; a < 6; ++a)
+            for (int b = 0; b < 6; ++b) Pv[6 * a + b] = Arow[a * nc + 6 * k + b];
+          int bad = 0;
+          if (!inv_spd6(Pv)) {
+            bad = 1;
+            for (int a = 0; a < 36; ++a) Pv[a] = 0.0;
+            for (int a = 0; a < 6; ++a) Pv[7 * a] = 1.0;
+          }
+          for (int a = 0; a < 36; ++a) red[a] = Pv[a];
+          red[36] = (double)bad;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < nc; j += blockDim.x) {
+          double col[6], out[6];
+          for (int a = 0; a < 6; ++a) col[a] = Arow[a * nc + j];
+          const bool inpiv = (j >= 6 * k && j < 6 * k + 6);
+          for (int a = 0; a < 6; ++a) {
+            double t = 0.0;
+            if (inpiv)
+              t = red[6 * a + (j - 6 * k)];
+            else
+              for (int b = 0; b < 6; ++b) t += red[6 * a + b] * col[b];
+            out[a] = t;
+          }
+          for (int a = 0; a < 6; ++a) {
+            Arow[a * nc + j] = out[a];
+            gp[a * nc + j] = out[a];
+          }
+        }
+        if (threadIdx.x == 0) gp[6 * nc] = red[36];
+      }
+      grid_bar_sum(slots, epoch, 0.0, nullptr, nullptr, part_sh, sh);
+      if ((int)blockIdx.x != k) {
+        for (int j = threadIdx.x; j < 6 * nc; j += blockDim.x) panel_sh[j] = __ldcg(gp + j);
+        if (threadIdx.x == 0 && __ldcg(gp + 6 * nc) != 0.0) s_flag = 1;
+        // F = my pivot-column block (6x6)
+        if (threadIdx.x < 36) red[threadIdx.x] = Arow[(threadIdx.x / 6) * nc + 6 * k + (threadIdx.x % 6)];
+        __syncthreads();
+        for (int j = threadIdx.x; j < nc; j += blockDim.x) {
+          const bool inpiv = (j >= 6 * k && j < 6 * k + 6);
+          double pj[6];
+          for (int b = 0; b < 6; ++b) pj[b] = panel_sh[b * nc + j];
+          for (int a = 0; a < 6; ++a) {
+            double t = 0.0;
+            for (int b = 0; b < 6; ++b) t += red[6 * a + b] * pj[b];
+            Arow[a * nc + j] = inpiv ? -t : Arow[a * nc + j] - t;
+          }
+        }
+        __syncthreads();
+      } else if (threadIdx.x == 0 && red[36] != 0.0) {
+        s_flag = 1;
+      }
+    }
+    __syncthreads();
+    if (s_flag) status = 3;  // a pivot aggregate was not positive definite: coarse level unusable
+  }
+  const bool use_coarse = coarse && status == 0;
+  if (status == 3) status = 0;  // fall back to block-Jacobi only (every CTA sees the same flag)
+
+  // =================== init: x = 0, r = g, z = M^-1 r ======================================================
   double local = 0.0;
-  for (int pbase = gw * 5; pbase < G.Np; pbase += total_warps * 5) {
+  double l6[6] = {0, 0, 0, 0, 0, 0};
+  for (int pbase = p0 + warp * 5; pbase < p1; pbase += warps_per_block * 5) {
     const int i = pbase + slot;
-    const bool act = lane_active && i < G.Np;
-    double rc = act ? G.g[6 * (size_t)i + comp] : 0.0;
+    const bool act = lane_active && i < p1;
+    double rcomp = act ? G.g[6 * (size_t)i + comp] : 0.0;
+    if (act) {
+      G.x[6 * (size_t)i + comp] = 0.0;
+      G.r[6 * (size_t)i + comp] = rcomp;
+      pold[6 * (size_t)i + comp] = 0.0;
+      if (use_coarse) {
+        const double* B = Cz.Bmat + 36 * (size_t)i + 6 * comp;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) l6[k] += B[k] * rcomp;
+      }
+    }
+  }
+  if (use_coarse) {
+    block_sum6(l6, s6, red6);
+    grid_bar_sum(slots, epoch, 0.0, s6, rc, part_sh, sh);  // rc = P' r  (all aggregates)
+    // zc = Ainv_rows * rc
+    if (warp < 6) {
+      double t = 0.0;
+      for (int j = lane; j < nc; j += 32) t += Arow[warp * nc + j] * rc[j];
+      t = warp_sum(t);
+      if (lane == 0) zc6[warp] = t;
+    }
+    __syncthreads();
+  }
+  for (int pbase = p0 + warp * 5; pbase < p1; pbase += warps_per_block * 5) {
+    const int i = pbase + slot;
+    const bool act = lane_active && i < p1;
+    double rcomp = act ? G.r[6 * (size_t)i + comp] : 0.0;
     double zc = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      double rk = __shfl_sync(0xffffffffu, rc, base_lane + k);
+      double rk = __shfl_sync(0xffffffffu, rcomp, base_lane + k);
       if (act) zc += G.Dinv[36 * (size_t)i + 6 * comp + k] * rk;
     }
     if (act) {
-      G.x[6 * (size_t)i + comp] = 0.0;
-      G.r[6 * (size_t)i + comp] = rc;
+      if (use_coarse) {
+        const double* B = Cz.Bmat + 36 * (size_t)i + 6 * comp;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) zc += B[k] * zc6[k];
+      }
       G.z[6 * (size_t)i + comp] = zc;
-      pold[6 * (size_t)i + comp] = 0.0;
-      local += rc * zc;
+      local += rcomp * zc;
     }
   }
   double bs = block_sum(local, sh);
-  if (threadIdx.x == 0) partA[blockIdx.x] = bs;
-  grid.sync();
-  double rz = grid_total(partA, nblk, sh);
+  double rz = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh, sh);
   const double rz0 = rz;
   double beta = 0.0;
   int it = 0;
-  int status = 0;
   if (!(rz0 > 0.0)) {
     status = (rz0 == 0.0) ? 0 : 2;
     maxit = 0;
@@ -355,25 +706,25 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(DevGraph G, double lambda, doub
         G.v[3 * (size_t)l + 2] = Wi[2] * a0 + Wi[4] * a1 + Wi[5] * a2;
       }
     }
-    grid.sync();
-    // ---- phase 2: q = (Hpp + lambda) p + sum Hoff p_nbr - sum HplP v ; partial p.q
+    grid_bar_sum(slots, epoch, 0.0, nullptr, nullptr, part_sh, sh);
+    // ---- phase 2: q = (Hpp + lambda) p + sum Hoff p_nbr - sum HplP v ; partial p.q ; restricted q
     local = 0.0;
-    for (int pbase = gw * 5; pbase < G.Np; pbase += total_warps * 5) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) l6[k] = 0.0;
+    for (int pbase = p0 + warp * 5; pbase < p1; pbase += warps_per_block * 5) {
       const int i = pbase + slot;
-      const bool act = lane_active && i < G.Np;
+      const bool act = lane_active && i < p1;
       double pc = 0.0;
       if (act) {
         pc = __ldcg(G.z + 6 * (size_t)i + comp) + beta * __ldcg(pold + 6 * (size_t)i + comp);
         pnew[6 * (size_t)i + comp] = pc;
       }
-      double qc = lambda * pc;
+      double qv = lambda * pc;
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         double pk = __shfl_sync(0xffffffffu, pc, base_lane + k);
-        if (act) qc += G.Hpp[36 * (size_t)i + 6 * comp + k] * pk;
+        if (act) qv += G.Hpp[36 * (size_t)i + 6 * comp + k] * pk;
       }
-      // pose-pose neighbours (loop bounds are uniform inside a slot; slots may differ -> use ballot-free
-      // formulation: every lane iterates to the warp maximum and masks)
       int k0 = 0, k1 = 0;
       if (act) {
         k0 = G.pose_pp_rowptr[i];
@@ -398,57 +749,75 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(DevGraph G, double lambda, doub
           double ok = __shfl_sync(0xffffffffu, oc, base_lane + k);
           if (has) {
             const double* Ho = G.Hoff + 36 * (size_t)e;
-            qc += (role == 0 ? Ho[6 * comp + k] : Ho[6 * k + comp]) * ok;
+            qv += (role == 0 ? Ho[6 * comp + k] : Ho[6 * k + comp]) * ok;
           }
         }
       }
       if (act) {
-        const int p0 = G.pose_pl_rowptr[i], p1 = G.pose_pl_rowptr[i + 1];
-        for (int kk = p0; kk < p1; ++kk) {
+        const int q0 = G.pose_pl_rowptr[i], q1 = G.pose_pl_rowptr[i + 1];
+        for (int kk = q0; kk < q1; ++kk) {
           const double* Hp = G.HplP + 18 * (size_t)kk + 3 * comp;
           const double* vv = G.v + 3 * (size_t)G.plP_lm[kk];
-          qc -= Hp[0] * __ldcg(vv) + Hp[1] * __ldcg(vv + 1) + Hp[2] * __ldcg(vv + 2);
+          qv -= Hp[0] * __ldcg(vv) + Hp[1] * __ldcg(vv + 1) + Hp[2] * __ldcg(vv + 2);
         }
-        G.q[6 * (size_t)i + comp] = qc;
-        local += pc * qc;
+        G.q[6 * (size_t)i + comp] = qv;
+        local += pc * qv;
+        if (use_coarse) {
+          const double* B = Cz.Bmat + 36 * (size_t)i + 6 * comp;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) l6[k] += B[k] * qv;
+        }
       }
     }
     bs = block_sum(local, sh);
-    if (threadIdx.x == 0) partB[blockIdx.x] = bs;
-    grid.sync();
-    const double pq = grid_total(partB, nblk, sh);
+    if (use_coarse) block_sum6(l6, s6, red6);
+    const double pq = grid_bar_sum(slots, epoch, bs, use_coarse ? s6 : nullptr, use_coarse ? qc : nullptr, part_sh, sh);
     if (!(pq > 0.0) || !isfinite(pq)) {  // breakdown: S not positive definite / non-finite data
       status = 1;
       break;
     }
     const double alpha = rz / pq;
-    // ---- phase 3: x += alpha p ; r -= alpha q ; z = Dinv r ; partial r.z
+    // ---- phase 3: x += alpha p ; r -= alpha q ; z = M^-1 r ; partial r.z
+    if (use_coarse) {
+      for (int j = threadIdx.x; j < nc; j += blockDim.x) rc[j] -= alpha * qc[j];
+      __syncthreads();
+      if (warp < 6) {
+        double t = 0.0;
+        for (int j = lane; j < nc; j += 32) t += Arow[warp * nc + j] * rc[j];
+        t = warp_sum(t);
+        if (lane == 0) zc6[warp] = t;
+      }
+      __syncthreads();
+    }
     local = 0.0;
-    for (int pbase = gw * 5; pbase < G.Np; pbase += total_warps * 5) {
+    for (int pbase = p0 + warp * 5; pbase < p1; pbase += warps_per_block * 5) {
       const int i = pbase + slot;
-      const bool act = lane_active && i < G.Np;
-      double rc = 0.0;
+      const bool act = lane_active && i < p1;
+      double rcomp = 0.0;
       if (act) {
         const size_t o = 6 * (size_t)i + comp;
         G.x[o] += alpha * pnew[o];
-        rc = G.r[o] - alpha * G.q[o];
-        G.r[o] = rc;
+        rcomp = G.r[o] - alpha * G.q[o];
+        G.r[o] = rcomp;
       }
       double zc = 0.0;
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        double rk = __shfl_sync(0xffffffffu, rc, base_lane + k);
+        double rk = __shfl_sync(0xffffffffu, rcomp, base_lane + k);
         if (act) zc += G.Dinv[36 * (size_t)i + 6 * comp + k] * rk;
       }
       if (act) {
+        if (use_coarse) {
+          const double* B = Cz.Bmat + 36 * (size_t)i + 6 * comp;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) zc += B[k] * zc6[k];
+        }
         G.z[6 * (size_t)i + comp] = zc;
-        local += rc * zc;
+        local += rcomp * zc;
       }
     }
     bs = block_sum(local, sh);
-    if (threadIdx.x == 0) partC[blockIdx.x] = bs;
-    grid.sync();
-    const double rzn = grid_total(partC, nblk, sh);
+    const double rzn = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh, sh);
     beta = rzn / rz;
     rz = rzn;
     double* t = pold;

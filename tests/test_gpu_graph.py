@@ -73,10 +73,11 @@ def test_chi2_matches_oracle():
     assert abs(a - b) <= 1e-11 * abs(b)
 
 
+@pytest.mark.parametrize("precond", [0, 1])
 @pytest.mark.parametrize("lam", [10.0, 1e-2, 1e-6])
-def test_damped_solve_matches_sparse_cholesky(lam):
+def test_damped_solve_matches_sparse_cholesky(lam, precond):
     spec = synth.make_config_graph("cfg1")
-    g, o, ids = _pair(spec, pcg_tol=1e-13)
+    g, o, ids = _pair(spec, pcg_tol=1e-13, preconditioner=precond)
     ok, xo = o.solve_once(lam)
     assert ok
     its, xg = g.solve_once(lam, xo.size)
@@ -84,9 +85,10 @@ def test_damped_solve_matches_sparse_cholesky(lam):
     assert np.abs(xg - xo).max() <= 1e-8 * max(1.0, np.abs(xo).max()), (its, np.abs(xg - xo).max())
 
 
-def test_lm_trajectory_cfg1():
+@pytest.mark.parametrize("precond", [0, 1])
+def test_lm_trajectory_cfg1(precond):
     spec = synth.make_config_graph("cfg1")
-    g, o, ids = _pair(spec)
+    g, o, ids = _pair(spec, preconditioner=precond)
     assert g.optimize(8) and o.optimize(8)
     assert g.iterations == o.iterations == 8
     # per-iteration chi2 / lambda / trials agree
@@ -154,13 +156,29 @@ def test_incremental_growth():
     assert np.abs(X - Xo).max() <= 1e-5 * max(1.0, np.abs(Xo).max())
 
 
-def test_cfg2_full_size_properties():
+def test_coarse_level_reduces_pcg_iterations():
+    """the rigid-body coarse level must give the same solution in far fewer PCG iterations (cfg5-size graph)"""
+    spec = synth.make_graph(2000, 400, seed=77)
+    xs, its = [], []
+    for precond in (0, 1):
+        g = GraphSLAM(pcg_tol=1e-12, preconditioner=precond)
+        synth.load_graph(g, spec)
+        n = 6 * (spec.n_poses - 1) + 3 * spec.n_landmarks
+        k, x = g.solve_once(1e-3, n)
+        xs.append(x)
+        its.append(k)
+    assert np.abs(xs[0] - xs[1]).max() <= 1e-7 * max(1.0, np.abs(xs[0]).max())
+    assert its[1] * 2 < its[0], its
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_cfg2_full_size_properties(precond):
     """BASELINE.json configs[1] (10k KF / 2k landmarks / 60k edges): size-independent properties —
     chi2 is monotone over accepted iterations, repeatable bit-for-bit, and matches the committed
     oracle fixture for the first iterations."""
     import json, os
     spec = synth.make_config_graph("cfg2")
-    g = GraphSLAM()
+    g = GraphSLAM(preconditioner=precond)
     synth.load_graph(g, spec)
     g.snapshot()
     assert g.optimize_resident(6)

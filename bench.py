@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pcg-tol", type=float, default=1e-10)
-    ap.add_argument("--preconditioner", type=int, default=0)
+    ap.add_argument("--preconditioner", type=int, default=1)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -9,7 +9,7 @@ if which in ("all", "graph"):
     name = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     spec = synth.make_config_graph(name)
-    g = GraphSLAM(preconditioner=int(os.environ.get('PRECOND', '0')), pcg_tol=float(os.environ.get('PCGTOL', '1e-10')))
+    g = GraphSLAM(preconditioner=int(os.environ.get('PRECOND', '0')), pcg_tol=float(os.environ.get('PCGTOL', '1e-10')), force_generic=bool(int(os.environ.get('GENERIC', '0'))))
     t = time.time(); synth.load_graph(g, spec); print("load", time.time() - t)
     g.snapshot()
     for rep in range(3):
@@ -19,6 +19,13 @@ if which in ("all", "graph"):
               f"pcg {g.stats['total_pcg_iters']} ms_pcg {g.stats['ms_pcg']:.1f} launches {g.stats['kernel_launches']} chi2 {g.stats['chi2_final']:.6f}")
     np.set_printoptions(linewidth=200, precision=6)
     print(g.history)
+    import ctypes as C
+    tm = np.zeros(8)
+    if hasattr(g._L, "ssb_graph_debug_timers"):
+        g._L.ssb_graph_debug_timers.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        g._L.ssb_graph_debug_timers(g._h, tm.ctypes.data_as(C.POINTER(C.c_double)))
+        names = ["assemble", "gauss-jordan", "init", "phase1", "barriers", "phase2", "phase3", "-"]
+        print("k_pcg cycles (block 0, all launches since prepare), ms @1.9GHz:", {n: round(v / 1.9e6, 2) for n, v in zip(names, tm)})
     print("us per pcg iter (upper bound):", g.stats['ms_device'] * 1e3 / max(1, g.stats['total_pcg_iters']))
 if which in ("all", "ransac"):
     cl = synth.make_cloud()

@@ -120,7 +120,9 @@ struct ssb_graph {
   DBuf<int> d_run_lm, d_run_group, d_run_e0, d_lm_run_rowptr, d_grp_run_rowptr, d_grp_runs;
   DBuf<BarSlot> d_slots;
   CoarseDev Cz;
-  size_t pcg_smem = 0;
+  size_t pcg_smem = 0, pcgf_smem = 0;
+  bool fast_ok = false;   // the graph fits the on-chip resident PCG kernel
+  bool allow_fast = true;
   double* h_scalars = nullptr;  // pinned: 8 doubles
   int* h_iscalars = nullptr;    // pinned: 4 ints
   DevGraph G;
@@ -205,19 +207,29 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
   g->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess ||
-      cudaMallocHost((void**)&g->h_scalars, 8 * sizeof(double)) != cudaSuccess ||
+      cudaMallocHost((void**)&g->h_scalars, 32 * sizeof(double)) != cudaSuccess ||
       cudaMallocHost((void**)&g->h_iscalars, 4 * sizeof(int)) != cudaSuccess) {
     set_error("CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete g;
     return nullptr;
   }
   g->pcg_grid = std::min(g->num_sms, PCG_THREADS);  // one persistent CTA per SM
-  g->pcg_smem = (size_t)(PCG_THREADS + 14 * 6 * g->pcg_grid + GJ_SLICES * 36) * sizeof(double);
+  g->pcg_smem = (size_t)(PCG_THREADS + 14 * 6 * g->pcg_grid + (PCG_THREADS / 36) * 36) * sizeof(double);
+  g->pcgf_smem = (size_t)(PCGF_THREADS + 8 * 6 * g->pcg_grid + (PCGF_THREADS / 36) * 36 +
+                          std::max(PCGF_BIG, 6 * 6 * g->pcg_grid)) * sizeof(double);
+  g->allow_fast = g->opts.reserved[0] == 0;   // reserved[0] = 1 forces the generic (streaming) kernel
   int nb = 0;
   e = cudaFuncSetAttribute(k_pcg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_smem);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg, PCG_THREADS, g->pcg_smem);
   if (e != cudaSuccess || nb < 1) {
     set_error("k_pcg cannot be made resident (occupancy %d, %zu B smem): %s", nb, g->pcg_smem, cudaGetErrorString(e));
+    delete g;
+    return nullptr;
+  }
+  e = cudaFuncSetAttribute(k_pcg_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcgf_smem);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_fast, PCGF_THREADS, g->pcgf_smem);
+  if (e != cudaSuccess || nb < 1) {
+    set_error("k_pcg_fast cannot be made resident (occupancy %d, %zu B smem): %s", nb, g->pcgf_smem, cudaGetErrorString(e));
     delete g;
     return nullptr;
   }
@@ -484,10 +496,29 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_dl.ensure((size_t)3 * Nl));
     const size_t nb_bs = (size_t)(Np + Nl + 127) / 128 + 1;
     SSB_TRY(g->d_part.ensure(std::max<size_t>(3 * PART_STRIDE, nb_bs) + 4096));
-    SSB_TRY(g->d_scalars.ensure(8));
+    SSB_TRY(g->d_scalars.ensure(32));
     SSB_TRY(g->d_iscalars.ensure(4));
     SSB_TRY(g->d_tmp.ensure(128));
     const int ncoarse = 6 * nblk;
+    {
+      // does the graph fit the on-chip resident kernel?  (<= 80 poses per CTA, bounded incidence lists,
+      // one landmark per warp, <= 64 edges per landmark, bounded overflow per CTA)
+      bool ok = g->allow_fast && Cc <= 5 * (PCGF_THREADS / 32) && Nl <= nblk * (PCGF_THREADS / 32);
+      if (ok) {
+        std::vector<int> ov(nblk, 0);
+        for (int l = 0; l < Nl && ok; ++l) {
+          const int deg = lm_rowptr[l + 1] - lm_rowptr[l];
+          if (deg > 64) ok = false;
+          ov[l % nblk] += std::max(0, deg - 32);
+        }
+        for (int b = 0; b < nblk && ok; ++b) {
+          const int q0 = std::min(Np, b * Cc), q1 = std::min(Np, q0 + Cc);
+          if (ov[b] > PCGF_MAXOV || ppl_rowptr[q1] - ppl_rowptr[q0] > PCGF_MAXPL || ppp_rowptr[q1] - ppp_rowptr[q0] > PCGF_MAXPP)
+            ok = false;
+        }
+      }
+      g->fast_ok = ok;
+    }
     SSB_TRY(g->d_Bmat.ensure((size_t)36 * Np));
     SSB_TRY(g->d_Grun.ensure((size_t)18 * n_runs));
     SSB_TRY(g->d_panel.ensure((size_t)2 * (6 * ncoarse + 8)));
@@ -497,7 +528,7 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_lm_run_rowptr.ensure(Nl + 1));
     SSB_TRY(g->d_grp_run_rowptr.ensure(nblk + 1));
     SSB_TRY(g->d_grp_runs.ensure(n_runs));
-    SSB_TRY(g->d_slots.ensure((size_t)2 * nblk));
+    SSB_TRY(g->d_slots.ensure((size_t)2 * nblk + 1));
     cudaStream_t s = g->stream;
     if (n_runs) {
       SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_run_lm.p, run_lm.data(), n_runs * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -523,7 +554,7 @@ static int prepare(ssb_graph* g) {
       Cz.n_runs = n_runs;
       Cz.panel = g->d_panel.p;
     }
-    SSB_CUDA_CHECK(cudaMemsetAsync(g->d_scalars.p, 0, 8 * sizeof(double), s));
+    SSB_CUDA_CHECK(cudaMemsetAsync(g->d_scalars.p, 0, 32 * sizeof(double), s));
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_iscalars.p, 0, 4 * sizeof(int), s));
     if (Np) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_fixed.p, pfix.data(), Np, cudaMemcpyHostToDevice, s));
     if (Nl) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_fixed.p, lfix.data(), Nl, cudaMemcpyHostToDevice, s));
@@ -634,7 +665,7 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
   double tol2 = g->opts.pcg_tol * g->opts.pcg_tol;
   int maxit = g->opts.max_pcg_iters;
   BarSlot* slots = g->d_slots.p;
-  SSB_CUDA_CHECK(cudaMemsetAsync(slots, 0, (size_t)2 * g->pcg_grid * sizeof(BarSlot), s));
+  SSB_CUDA_CHECK(cudaMemsetAsync(slots, 0, ((size_t)2 * g->pcg_grid + 1) * sizeof(BarSlot), s));
   void* args[] = {(void*)&G, (void*)&g->Cz, (void*)&slots, (void*)&lambda, (void*)&tol2, (void*)&maxit};
   if (g->ev_used + 2 > g->ev_pool.size()) {
     for (int k = 0; k < 64; ++k) {
@@ -644,7 +675,10 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
     }
   }
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used], s));
-  SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(g->pcg_grid), dim3(PCG_THREADS), args, g->pcg_smem, s));
+  if (g->fast_ok)
+    SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg_fast, dim3(g->pcg_grid), dim3(PCGF_THREADS), args, g->pcgf_smem, s));
+  else
+    SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(g->pcg_grid), dim3(PCG_THREADS), args, g->pcg_smem, s));
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used + 1], s));
   g->ev_used += 2;
   g->launches++;
@@ -656,7 +690,7 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
   return SSB_OK;
 }
 static int read_scalars(ssb_graph* g) {
-  SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_scalars, g->d_scalars.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_scalars, g->d_scalars.p, 32 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
   SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_iscalars, g->d_iscalars.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
   SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
   return SSB_OK;
@@ -800,6 +834,14 @@ int ssb_graph_optimize_resident(ssb_graph* g, int max_iterations, ssb_lm_stats* 
   st.kernel_launches = g->launches - l0;
   if (stats) *stats = st;
   return 1;
+}
+
+// debug: cycle counters of k_pcg accumulated since prepare (only with -DSSB_PCG_TIMERS)
+int ssb_graph_debug_timers(ssb_graph* g, double out8[8]) {
+  if (!g || !out8) return SSB_ERR_INVALID;
+  SSB_TRY(read_scalars(g));
+  for (int k = 0; k < 8; ++k) out8[k] = g->h_scalars[8 + k];
+  return SSB_OK;
 }
 
 int ssb_graph_get_history(ssb_graph* g, double* out6n, int cap) {

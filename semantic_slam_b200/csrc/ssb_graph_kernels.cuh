@@ -281,7 +281,7 @@ struct CoarseDev {
   double* panel;           // [2][6*nc + 8] Gauss-Jordan pivot panels (double buffered)
 };
 
-struct BarSlot {  // one 64 B line per CTA and buffer
+struct BarSlot {  // one 64 B line per CTA and buffer; slot [2*gridDim.x] holds the arrival counter
   double v[7];
   unsigned epoch;
   unsigned pad;
@@ -292,17 +292,20 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // Grid barrier fused with a fixed-order all-reduce of one double per CTA (+ optional all-gather of 6
-// doubles per CTA into `gather` (smem, 6 * gridDim.x)).  `part_sh` = gridDim.x doubles of smem, `sh` = 33.
+// doubles per CTA into `gather` (smem, 6 * gridDim.x)).  Arrival = payload store + release-add on one
+// counter; one thread per CTA spins on the counter; then every CTA reads the gridDim.x payload slots
+// and every warp folds them in the same fixed order.  `part_sh` = gridDim.x doubles of smem.
 // Every thread of every CTA must call it; requires gridDim.x <= blockDim.x and co-resident CTAs.
 __device__ __forceinline__ double grid_bar_sum(BarSlot* slots, unsigned& epoch, double my_partial, const double* my6,
-                                               double* gather, double* part_sh, double* sh) {
+                                               double* gather, double* part_sh) {
   ++epoch;
   BarSlot* S = slots + (size_t)(epoch & 1u) * gridDim.x;
+  unsigned* counter = &slots[2 * (size_t)gridDim.x].epoch;
   __syncthreads();
   if (threadIdx.x == 0) {
     BarSlot* me = S + blockIdx.x;
@@ -311,13 +314,14 @@ __device__ __forceinline__ double grid_bar_sum(BarSlot* slots, unsigned& epoch, 
 #pragma unroll
       for (int k = 0; k < 6; ++k) me->v[1 + k] = my6[k];
     }
-    __threadfence();
-    st_release_u32(&me->epoch, epoch);
+    red_release_add_u32(counter, 1u);  // release: orders this CTA's earlier writes (bar.sync-cumulative)
+    const unsigned target = epoch * gridDim.x;
+    while (ld_acquire_u32(counter) < target) {
+    }
   }
+  __syncthreads();
   if (threadIdx.x < gridDim.x) {
     const BarSlot* o = S + threadIdx.x;
-    while (ld_acquire_u32(&o->epoch) != epoch) {
-    }
     part_sh[threadIdx.x] = __ldcg(&o->v[0]);
     if (gather) {
 #pragma unroll
@@ -325,14 +329,9 @@ __device__ __forceinline__ double grid_bar_sum(BarSlot* slots, unsigned& epoch, 
     }
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    double t = 0.0;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += 32) t += part_sh[k];
-    t = warp_sum(t);
-    if (threadIdx.x == 0) sh[32] = t;
-  }
-  __syncthreads();
-  return sh[32];
+  double t = 0.0;
+  for (int k = (threadIdx.x & 31); k < (int)gridDim.x; k += 32) t += part_sh[k];
+  return warp_sum(t);
 }
 
 // deterministic block reduction of 6 values per thread -> out6 (smem), valid after return
@@ -356,6 +355,40 @@ __device__ __forceinline__ void block_sum6(const double* v, double* out6, double
     }
   }
   __syncthreads();
+}
+
+// 6x6 SPD inverse by 6 lanes of one warp (lane j owns column j of [A | I]); all 32 lanes must call.
+// col[6] in: column j of A (lanes >= 6: ignored); out: column j of A^-1.  Returns false if a pivot is
+// not positive.
+__device__ __forceinline__ bool warp_inv6(double* col) {
+  const int lane = threadIdx.x & 31;
+  double inv[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) inv[i] = (i == lane) ? 1.0 : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double piv = __shfl_sync(0xffffffffu, col[k], k);
+    if (!(piv > 0.0) || !isfinite(piv)) ok = false;
+    const double ip = 1.0 / piv;
+    double ck[6];  // column k of A (multipliers a_ik)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ck[i] = __shfl_sync(0xffffffffu, col[i], k);
+    const double akj = col[k] * ip, bkj = inv[k] * ip;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (i == k) {
+        col[i] = akj;
+        inv[i] = bkj;
+      } else {
+        col[i] -= ck[i] * akj;
+        inv[i] -= ck[i] * bkj;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) col[i] = inv[i];
+  return __all_sync(0xffffffffu, ok || lane >= 6);
 }
 
 // per LM iteration (poses changed): aggregate centroids and the prolongation blocks B_i
@@ -413,6 +446,179 @@ __global__ void __launch_bounds__(128) k_coarse_runs(DevGraph G, CoarseDev Cz) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Coarse prologue shared by both PCG kernels: CTA g assembles rows [6g, 6g+6) of A_c = P' S P in
+// shared memory (Arow[6][nc]) and the grid inverts A_c in place by block Gauss-Jordan (pivot
+// aggregate k at step k: its owner publishes the scaled pivot panel, one barrier per step).
+// Returns true when A_c^-1 is usable (every pivot block was positive definite).
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__device__ bool coarse_prologue(const DevGraph& G, const CoarseDev& Cz, BarSlot* slots, unsigned& epoch, double lambda,
+                                double* Arow, double* panel_sh, double* red, double* part_sh, int p0, int p1) {
+  constexpr int SLICES = NT / 36;
+  __shared__ int s_flag;
+  __shared__ double piv_sh[40];
+  const int nblk = gridDim.x, nc = 6 * nblk, myg = blockIdx.x;
+  for (int k = threadIdx.x; k < 6 * nc; k += NT) Arow[k] = 0.0;
+  if (threadIdx.x == 0) s_flag = 0;
+  __syncthreads();
+  // (a) diagonal block: sum_i B_i' (Hpp_ii + lambda I) B_i + pose-pose edges inside the aggregate
+  {
+    const int ent = threadIdx.x % 36, sl = threadIdx.x / 36;
+    const int r = ent / 6, c = ent - 6 * r;
+    if (sl < SLICES) {
+      double acc = 0.0;
+      for (int i = p0 + sl; i < p1; i += SLICES) {
+        const double* B = Cz.Bmat + 36 * (size_t)i;
+        const double* H = G.Hpp + 36 * (size_t)i;
+        double t = 0.0;
+        for (int a = 0; a < 6; ++a) {
+          double hb = lambda * B[6 * a + c];
+          for (int b = 0; b < 6; ++b) hb += H[6 * a + b] * B[6 * b + c];
+          t += B[6 * a + r] * hb;
+        }
+        acc += t;
+        for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
+          const int code = G.pose_pp_idx[kk];
+          if (code & 1) continue;
+          const int e = code >> 1;
+          const int j = G.pp[e].j;
+          if (j < p0 || j >= p1) continue;
+          const double* Bj = Cz.Bmat + 36 * (size_t)j;
+          const double* Ho = G.Hoff + 36 * (size_t)e;
+          double t1 = 0.0, t2 = 0.0;
+          for (int a = 0; a < 6; ++a) {
+            double hb1 = 0.0, hb2 = 0.0;
+            for (int b = 0; b < 6; ++b) {
+              hb1 += Ho[6 * a + b] * Bj[6 * b + c];
+              hb2 += Ho[6 * a + b] * Bj[6 * b + r];
+            }
+            t1 += B[6 * a + r] * hb1;  // (Bi' Hoff Bj)[r][c]
+            t2 += B[6 * a + c] * hb2;  // its transpose
+          }
+          acc += t1 + t2;
+        }
+      }
+      red[36 * sl + ent] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 36) {
+      double t = 0.0;
+      for (int k = 0; k < SLICES; ++k) t += red[36 * k + threadIdx.x];
+      const int rr = threadIdx.x / 6, cc = threadIdx.x - 6 * rr;
+      if (p1 <= p0 && rr == cc) t = 1.0;  // empty aggregate: identity keeps A_c invertible
+      Arow[rr * nc + 6 * myg + cc] = t;
+    }
+    __syncthreads();
+  }
+  // (b) pose-pose edges leaving the aggregate, (c) landmark terms; fixed order, 36 lanes (one per entry)
+  if (threadIdx.x < 36) {
+    const int r = threadIdx.x / 6, c = threadIdx.x - 6 * r;
+    for (int i = p0; i < p1; ++i) {
+      const double* B = Cz.Bmat + 36 * (size_t)i;
+      for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
+        const int code = G.pose_pp_idx[kk];
+        const int e = code >> 1, role = code & 1;
+        const int j = role == 0 ? G.pp[e].j : G.pp[e].i;
+        if (j >= p0 && j < p1) continue;
+        const int gj = j / Cz.C;
+        const double* Bj = Cz.Bmat + 36 * (size_t)j;
+        const double* Ho = G.Hoff + 36 * (size_t)e;
+        double t = 0.0;
+        for (int a = 0; a < 6; ++a) {
+          double hb = 0.0;
+          for (int b = 0; b < 6; ++b) hb += (role == 0 ? Ho[6 * a + b] : Ho[6 * b + a]) * Bj[6 * b + c];
+          t += B[6 * a + r] * hb;
+        }
+        Arow[r * nc + 6 * gj + c] += t;
+      }
+    }
+    for (int q = Cz.grp_run_rowptr[myg]; q < Cz.grp_run_rowptr[myg + 1]; ++q) {
+      const int ra = Cz.grp_runs[q];
+      const int l = Cz.run_lm[ra];
+      const double* Ga = Cz.Grun + 18 * (size_t)ra;
+      const double* Wu = G.HllInv + 6 * (size_t)l;
+      const double W[9] = {Wu[0], Wu[1], Wu[2], Wu[1], Wu[3], Wu[4], Wu[2], Wu[4], Wu[5]};
+      double u[3];
+      for (int v = 0; v < 3; ++v) u[v] = Ga[r] * W[v] + Ga[6 + r] * W[3 + v] + Ga[12 + r] * W[6 + v];
+      for (int rb = Cz.lm_run_rowptr[l]; rb < Cz.lm_run_rowptr[l + 1]; ++rb) {
+        const double* Gb = Cz.Grun + 18 * (size_t)rb;
+        const int gb = Cz.run_group[rb];
+        Arow[r * nc + 6 * gb + c] -= u[0] * Gb[c] + u[1] * Gb[6 + c] + u[2] * Gb[12 + c];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- block Gauss-Jordan ----
+  for (int k = 0; k < nblk; ++k) {
+    double* gp = Cz.panel + (size_t)(k & 1) * (6 * nc + 8);
+    if ((int)blockIdx.x == k) {
+      if (threadIdx.x < 32) {  // pivot inverse by warp 0
+        double col[6];
+        const int lane = threadIdx.x;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) col[a] = lane < 6 ? Arow[a * nc + 6 * k + lane] : 0.0;
+        const bool ok = warp_inv6(col);
+        if (lane < 6) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) piv_sh[6 * a + lane] = ok ? col[a] : (a == lane ? 1.0 : 0.0);
+        }
+        if (lane == 0) piv_sh[36] = ok ? 0.0 : 1.0;
+      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < nc; j += NT) {
+        double colv[6], out[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) colv[a] = Arow[a * nc + j];
+        const bool inpiv = (j >= 6 * k && j < 6 * k + 6);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          double t = 0.0;
+          if (inpiv) {
+            t = piv_sh[6 * a + (j - 6 * k)];
+          } else {
+#pragma unroll
+            for (int b = 0; b < 6; ++b) t += piv_sh[6 * a + b] * colv[b];
+          }
+          out[a] = t;
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          Arow[a * nc + j] = out[a];
+          gp[a * nc + j] = out[a];
+        }
+      }
+      if (threadIdx.x == 0) {
+        gp[6 * nc] = piv_sh[36];
+        if (piv_sh[36] != 0.0) s_flag = 1;
+      }
+    }
+    grid_bar_sum(slots, epoch, 0.0, nullptr, nullptr, part_sh);
+    if ((int)blockIdx.x != k) {
+      for (int j = threadIdx.x; j < 6 * nc; j += NT) panel_sh[j] = __ldcg(gp + j);
+      if (threadIdx.x == 0 && __ldcg(gp + 6 * nc) != 0.0) s_flag = 1;
+      if (threadIdx.x < 36) piv_sh[threadIdx.x] = Arow[(threadIdx.x / 6) * nc + 6 * k + (threadIdx.x % 6)];  // F
+      __syncthreads();
+      for (int j = threadIdx.x; j < nc; j += NT) {
+        const bool inpiv = (j >= 6 * k && j < 6 * k + 6);
+        double pj[6];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) pj[b] = panel_sh[b * nc + j];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          double t = 0.0;
+#pragma unroll
+          for (int b = 0; b < 6; ++b) t += piv_sh[6 * a + b] * pj[b];
+          Arow[a * nc + j] = inpiv ? -t : Arow[a * nc + j] - t;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  return s_flag == 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3: persistent cooperative PCG on the (implicit) Schur complement
 //   S x = g,  S = Hpp + lambda I - Hpl (Hll + lambda I)^-1 Hlp
 // preconditioned by block-Jacobi (6x6 diagonal blocks of S) plus, optionally, the rigid-body coarse
@@ -420,32 +626,39 @@ __global__ void __launch_bounds__(128) k_coarse_runs(DevGraph G, CoarseDev Cz) {
 // per pose (one per row), 5 poses per warp; one warp per landmark in the landmark sweep.
 // 3 grid-wide barriers per iteration, each fused with the all-reduce it needs; all reductions are
 // fixed-order => bit-reproducible for a fixed grid.
+//
+// k_pcg      : generic (any size; operands streamed from L2/HBM every iteration)
+// k_pcg_fast : on-chip resident variant for graphs that fit (<= 80 poses and <= 16 landmarks of degree
+//              <= 32 per CTA): Hpp/Dinv/B rows and the landmark blocks live in registers, HplP / Hoff
+//              rows in shared memory for the whole solve; only p, z and v travel through L2.
 // ---------------------------------------------------------------------------------------------
 constexpr int PCG_THREADS = 1024;
-constexpr int GJ_SLICES = 28;  // 28 * 36 = 1008 threads take part in the aggregate reduction
+constexpr int PCGF_THREADS = 512;
+constexpr int PCGF_MAXPL = 448;   // pose-landmark entries cached per CTA (fast path)
+constexpr int PCGF_MAXPP = 160;   // pose-pose incidences cached per CTA (fast path)
+constexpr int PCGF_MAXOV = 64;    // landmark edges beyond the first 32 of a landmark, per CTA (fast path)
+constexpr int PCGF_BIG = 18 * PCGF_MAXPL + 36 * PCGF_MAXPP + 18 * PCGF_MAXOV + (PCGF_MAXPL + PCGF_MAXPP + 1) / 2;
 
 __global__ void __launch_bounds__(PCG_THREADS, 1)
     k_pcg(DevGraph G, CoarseDev Cz, BarSlot* slots, double lambda, double tol2, int maxit) {
   extern __shared__ __align__(16) double dsm[];
   __shared__ double sh[33];
   __shared__ double s6[8], zc6[8], red6[6 * 32];
-  __shared__ int s_flag;
   const int nblk = gridDim.x;
   const int nc = 6 * nblk;
-  // dynamic smem carve-up
   double* part_sh = dsm;                 // [1024]
   double* Arow = part_sh + PCG_THREADS;  // [6][nc]   rows of A_c, then of A_c^-1
   double* panel_sh = Arow + 6 * nc;      // [6][nc]
   double* rc = panel_sh + 6 * nc;        // [nc] restricted residual (kept by recurrence)
   double* qc = rc + nc;                  // [nc] gathered restricted q
-  double* red = qc + nc;                 // [GJ_SLICES][36]
+  double* red = qc + nc;                 // [28][36]
   const bool coarse = Cz.enabled != 0;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
-  const int gw = blockIdx.x * warps_per_block + warp;
   const int total_warps = nblk * warps_per_block;
+  const int gw = warp * nblk + blockIdx.x;  // landmark sweep: round-robin over CTAs
   const int slot = lane / 6, comp = lane - 6 * slot;
   const bool lane_active = lane < 30;
   const int base_lane = 6 * slot;
@@ -455,171 +668,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   double* pnew = G.p1;
   int status = 0;
 
-  // =================== coarse prologue: assemble my 6 rows of A_c, invert by block Gauss-Jordan ==========
-  if (coarse) {
-    for (int k = threadIdx.x; k < 6 * nc; k += blockDim.x) Arow[k] = 0.0;
-    __syncthreads();
-    const int myg = blockIdx.x;
-    // (a) diagonal block: sum_i B_i' (Hpp_ii + lambda I) B_i + intra-aggregate pose-pose edges
-    {
-      const int ent = threadIdx.x % 36, sl = threadIdx.x / 36;
-      const int r = ent / 6, c = ent - 6 * r;
-      double acc = 0.0;
-      if (sl < GJ_SLICES) {
-        for (int i = p0 + sl; i < p1; i += GJ_SLICES) {
-          const double* B = Cz.Bmat + 36 * (size_t)i;
-          const double* H = G.Hpp + 36 * (size_t)i;
-          // (B' (H + lambda) B)[r][c]
-          double t = 0.0;
-          for (int a = 0; a < 6; ++a) {
-            double hb = lambda * B[6 * a + c];
-            for (int b = 0; b < 6; ++b) hb += H[6 * a + b] * B[6 * b + c];
-            t += B[6 * a + r] * hb;
-          }
-          acc += t;
-          // pose-pose edges where i is the `from` vertex and the other end is in the same aggregate:
-          // contributes B_i' Hoff B_j and its transpose to the diagonal block
-          for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
-            const int code = G.pose_pp_idx[kk];
-            if (code & 1) continue;
-            const int e = code >> 1;
-            const int j = G.pp[e].j;
-            if (j < p0 || j >= p1) continue;
-            const double* Bj = Cz.Bmat + 36 * (size_t)j;
-            const double* Ho = G.Hoff + 36 * (size_t)e;
-            double t1 = 0.0, t2 = 0.0;
-            for (int a = 0; a < 6; ++a) {
-              double hb1 = 0.0, hb2 = 0.0;
-              for (int b = 0; b < 6; ++b) {
-                hb1 += Ho[6 * a + b] * Bj[6 * b + c];  // (Hoff Bj)[a][c]
-                hb2 += Ho[6 * a + b] * Bj[6 * b + r];  // (Hoff Bj)[a][r]
-              }
-              t1 += B[6 * a + r] * hb1;  // (Bi' Hoff Bj)[r][c]
-              t2 += B[6 * a + c] * hb2;  // (Bi' Hoff Bj)[c][r]  -> transpose term
-            }
-            acc += t1 + t2;
-          }
-        }
-        red[36 * sl + ent] = acc;
-      }
-      __syncthreads();
-      if (threadIdx.x < 36) {
-        double t = 0.0;
-        for (int k = 0; k < GJ_SLICES; ++k) t += red[36 * k + threadIdx.x];
-        const int rr = threadIdx.x / 6, cc = threadIdx.x - 6 * rr;
-        if (p1 <= p0 && rr == cc) t = 1.0;  // empty aggregate: identity keeps A_c invertible
-        Arow[rr * nc + 6 * myg + cc] = t;
-      }
-      __syncthreads();
-    }
-    // (b) pose-pose edges crossing aggregates, (c) landmark terms: sequential over the list, 36 lanes each
-    if (threadIdx.x < 36) {
-      const int r = threadIdx.x / 6, c = threadIdx.x - 6 * r;
-      for (int i = p0; i < p1; ++i) {
-        const double* B = Cz.Bmat + 36 * (size_t)i;
-        for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
-          const int code = G.pose_pp_idx[kk];
-          const int e = code >> 1, role = code & 1;
-          const int j = role == 0 ? G.pp[e].j : G.pp[e].i;
-          if (j >= p0 && j < p1) continue;
-          const int gj = j / Cz.C;
-          const double* Bj = Cz.Bmat + 36 * (size_t)j;
-          const double* Ho = G.Hoff + 36 * (size_t)e;
-          double t = 0.0;
-          for (int a = 0; a < 6; ++a) {
-            double hb = 0.0;
-            for (int b = 0; b < 6; ++b) hb += (role == 0 ? Ho[6 * a + b] : Ho[6 * b + a]) * Bj[6 * b + c];
-            t += B[6 * a + r] * hb;
-          }
-          Arow[r * nc + 6 * gj + c] += t;
-        }
-      }
-      // landmark runs of my aggregate
-      for (int q = Cz.grp_run_rowptr[myg]; q < Cz.grp_run_rowptr[myg + 1]; ++q) {
-        const int ra = Cz.grp_runs[q];
-        const int l = Cz.run_lm[ra];
-        const double* Ga = Cz.Grun + 18 * (size_t)ra;  // 3x6
-        const double* Wu = G.HllInv + 6 * (size_t)l;
-        const double W[9] = {Wu[0], Wu[1], Wu[2], Wu[1], Wu[3], Wu[4], Wu[2], Wu[4], Wu[5]};
-        // u = (Ga' W)[r][:]  (1x3)
-        double u[3];
-        for (int v = 0; v < 3; ++v) u[v] = Ga[r] * W[v] + Ga[6 + r] * W[3 + v] + Ga[12 + r] * W[6 + v];
-        for (int rb = Cz.lm_run_rowptr[l]; rb < Cz.lm_run_rowptr[l + 1]; ++rb) {
-          const double* Gb = Cz.Grun + 18 * (size_t)rb;
-          const int gb = Cz.run_group[rb];
-          Arow[r * nc + 6 * gb + c] -= u[0] * Gb[c] + u[1] * Gb[6 + c] + u[2] * Gb[12 + c];
-        }
-      }
-    }
-    __syncthreads();
-    // ---- block Gauss-Jordan: step k pivots on aggregate k ----
-    if (threadIdx.x == 0) s_flag = 0;
-    for (int k = 0; k < nblk; ++k) {
-      double* gp = Cz.panel + (size_t)(k & 1) * (6 * nc + 8);
-      if ((int)blockIdx.x == k) {
-        // pivot inverse (SPD 6x6) by thread 0, then scale my rows: panel = Pinv * Arow, panel[:,k] = Pinv
-        if (threadIdx.x == 0) {
-          double Pv[36];
-          for (int a = 0; a < 6; ++a)
-            for (int b = 0; b < 6; ++b) Pv[6 * a + b] = Arow[a * nc + 6 * k + b];
-          int bad = 0;
-          if (!inv_spd6(Pv)) {
-            bad = 1;
-            for (int a = 0; a < 36; ++a) Pv[a] = 0.0;
-            for (int a = 0; a < 6; ++a) Pv[7 * a] = 1.0;
-          }
-          for (int a = 0; a < 36; ++a) red[a] = Pv[a];
-          red[36] = (double)bad;
-        }
-        __syncthreads();
-        for (int j = threadIdx.x; j < nc; j += blockDim.x) {
-          double col[6], out[6];
-          for (int a = 0; a < 6; ++a) col[a] = Arow[a * nc + j];
-          const bool inpiv = (j >= 6 * k && j < 6 * k + 6);
-          for (int a = 0; a < 6; ++a) {
-            double t = 0.0;
-            if (inpiv)
-              t = red[6 * a + (j - 6 * k)];
-            else
-              for (int b = 0; b < 6; ++b) t += red[6 * a + b] * col[b];
-            out[a] = t;
-          }
-          for (int a = 0; a < 6; ++a) {
-            Arow[a * nc + j] = out[a];
-            gp[a * nc + j] = out[a];
-          }
-        }
-        if (threadIdx.x == 0) gp[6 * nc] = red[36];
-      }
-      grid_bar_sum(slots, epoch, 0.0, nullptr, nullptr, part_sh, sh);
-      if ((int)blockIdx.x != k) {
-        for (int j = threadIdx.x; j < 6 * nc; j += blockDim.x) panel_sh[j] = __ldcg(gp + j);
-        if (threadIdx.x == 0 && __ldcg(gp + 6 * nc) != 0.0) s_flag = 1;
-        // F = my pivot-column block (6x6)
-        if (threadIdx.x < 36) red[threadIdx.x] = Arow[(threadIdx.x / 6) * nc + 6 * k + (threadIdx.x % 6)];
-        __syncthreads();
-        for (int j = threadIdx.x; j < nc; j += blockDim.x) {
-          const bool inpiv = (j >= 6 * k && j < 6 * k + 6);
-          double pj[6];
-          for (int b = 0; b < 6; ++b) pj[b] = panel_sh[b * nc + j];
-          for (int a = 0; a < 6; ++a) {
-            double t = 0.0;
-            for (int b = 0; b < 6; ++b) t += red[6 * a + b] * pj[b];
-            Arow[a * nc + j] = inpiv ? -t : Arow[a * nc + j] - t;
-          }
-        }
-        __syncthreads();
-      } else if (threadIdx.x == 0 && red[36] != 0.0) {
-        s_flag = 1;
-      }
-    }
-    __syncthreads();
-    if (s_flag) status = 3;  // a pivot aggregate was not positive definite: coarse level unusable
-  }
-  const bool use_coarse = coarse && status == 0;
-  if (status == 3) status = 0;  // fall back to block-Jacobi only (every CTA sees the same flag)
+  bool use_coarse = false;
+  if (coarse) use_coarse = coarse_prologue<PCG_THREADS>(G, Cz, slots, epoch, lambda, Arow, panel_sh, red, part_sh, p0, p1);
 
-  // =================== init: x = 0, r = g, z = M^-1 r ======================================================
+  // ---- init: x = 0, r = g, z = M^-1 r
   double local = 0.0;
   double l6[6] = {0, 0, 0, 0, 0, 0};
   for (int pbase = p0 + warp * 5; pbase < p1; pbase += warps_per_block * 5) {
@@ -639,8 +691,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   }
   if (use_coarse) {
     block_sum6(l6, s6, red6);
-    grid_bar_sum(slots, epoch, 0.0, s6, rc, part_sh, sh);  // rc = P' r  (all aggregates)
-    // zc = Ainv_rows * rc
+    grid_bar_sum(slots, epoch, 0.0, s6, rc, part_sh);  // rc = P' r  (all aggregates)
     if (warp < 6) {
       double t = 0.0;
       for (int j = lane; j < nc; j += 32) t += Arow[warp * nc + j] * rc[j];
@@ -670,7 +721,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     }
   }
   double bs = block_sum(local, sh);
-  double rz = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh, sh);
+  double rz = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh);
   const double rz0 = rz;
   double beta = 0.0;
   int it = 0;
@@ -706,7 +757,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
         G.v[3 * (size_t)l + 2] = Wi[2] * a0 + Wi[4] * a1 + Wi[5] * a2;
       }
     }
-    grid_bar_sum(slots, epoch, 0.0, nullptr, nullptr, part_sh, sh);
+    grid_bar_sum(slots, epoch, 0.0, nullptr, nullptr, part_sh);
     // ---- phase 2: q = (Hpp + lambda) p + sum Hoff p_nbr - sum HplP v ; partial p.q ; restricted q
     local = 0.0;
 #pragma unroll
@@ -771,7 +822,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     }
     bs = block_sum(local, sh);
     if (use_coarse) block_sum6(l6, s6, red6);
-    const double pq = grid_bar_sum(slots, epoch, bs, use_coarse ? s6 : nullptr, use_coarse ? qc : nullptr, part_sh, sh);
+    const double pq = grid_bar_sum(slots, epoch, bs, use_coarse ? s6 : nullptr, use_coarse ? qc : nullptr, part_sh);
     if (!(pq > 0.0) || !isfinite(pq)) {  // breakdown: S not positive definite / non-finite data
       status = 1;
       break;
@@ -817,7 +868,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       }
     }
     bs = block_sum(local, sh);
-    const double rzn = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh, sh);
+    const double rzn = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh);
     beta = rzn / rz;
     rz = rzn;
     double* t = pold;
@@ -833,6 +884,307 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     G.iscalars[1] = status;
     G.scalars[3] = rz;
     G.scalars[4] = rz0;
+  }
+}
+
+// ------------------------------------- on-chip resident variant --------------------------------
+__global__ void __launch_bounds__(PCGF_THREADS, 1)
+    k_pcg_fast(DevGraph G, CoarseDev Cz, BarSlot* slots, double lambda, double tol2, int maxit) {
+  extern __shared__ __align__(16) double dsm[];
+  __shared__ double sh[33];
+  __shared__ double s6[8], zc6[8], red6[6 * 32];
+  const int nblk = gridDim.x;
+  const int nc = 6 * nblk;
+  double* part_sh = dsm;                  // [PCGF_THREADS]
+  double* Arow = part_sh + PCGF_THREADS;  // [6][nc]
+  double* rc = Arow + 6 * nc;             // [nc]
+  double* qc = rc + nc;                   // [nc]
+  double* red = qc + nc;                  // [14][36]
+  double* big = red + (PCGF_THREADS / 36) * 36;
+  // `big` is first the Gauss-Jordan panel [6][nc], afterwards the resident operands:
+  double* panel_sh = big;
+  double* plH = big;                                   // [PCGF_MAXPL][18]  HplP blocks of my poses (6x3)
+  double* ppH = plH + 18 * PCGF_MAXPL;                 // [PCGF_MAXPP][36]  Hoff blocks (as stored)
+  double* ovH = ppH + 36 * PCGF_MAXPP;                 // [PCGF_MAXOV][18]  HplL blocks of edges 32.. of a landmark
+  int* pl_lm = reinterpret_cast<int*>(ovH + 18 * PCGF_MAXOV);  // [PCGF_MAXPL]
+  int* pp_other = pl_lm + PCGF_MAXPL;                  // [PCGF_MAXPP] neighbour pose, role in bit 31
+  __shared__ int ovcnt[PCGF_THREADS / 32];
+  const bool coarse = Cz.enabled != 0;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int slot = lane / 6, comp = lane - 6 * slot;
+  const int base_lane = 6 * slot;
+  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np, p0 + Cz.C);
+  const int i = p0 + warp * 5 + slot;          // my pose (pose role)
+  const bool act = lane < 30 && i < p1;
+  const int l = warp * nblk + blockIdx.x;      // my landmark (landmark role), round-robin over CTAs
+  const bool lact = l < G.Nl;
+  unsigned epoch = 0;
+  double* pold = G.p0;
+  double* pnew = G.p1;
+  int status = 0;
+
+#ifdef SSB_PCG_TIMERS
+  long long tmr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+#define SSB_TICK(k)           \
+  do {                        \
+    long long _n = clock64(); \
+    tmr[k] += _n - tlast;     \
+    tlast = _n;               \
+  } while (0)
+#else
+#define SSB_TICK(k) \
+  do {              \
+  } while (0)
+#endif
+  bool use_coarse = false;
+  if (coarse) use_coarse = coarse_prologue<PCGF_THREADS>(G, Cz, slots, epoch, lambda, Arow, panel_sh, red, part_sh, p0, p1);
+
+  SSB_TICK(1);
+  // ---- load the resident operands ------------------------------------------------------------
+  double Hrow[6], Drow[6], Brow[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    Hrow[k] = act ? G.Hpp[36 * (size_t)i + 6 * comp + k] : 0.0;
+    Drow[k] = act ? G.Dinv[36 * (size_t)i + 6 * comp + k] : 0.0;
+    Brow[k] = (act && use_coarse) ? Cz.Bmat[36 * (size_t)i + 6 * comp + k] : 0.0;
+  }
+  Hrow[comp] += act ? lambda : 0.0;
+  const int plbase = G.pose_pl_rowptr[p0 < G.Np ? p0 : G.Np];
+  const int ppbase = G.pose_pp_rowptr[p0 < G.Np ? p0 : G.Np];
+  const int npl_blk = G.pose_pl_rowptr[p1 > p0 ? p1 : (p0 < G.Np ? p0 : G.Np)] - plbase;
+  const int npp_blk = G.pose_pp_rowptr[p1 > p0 ? p1 : (p0 < G.Np ? p0 : G.Np)] - ppbase;
+  for (int k = threadIdx.x; k < 18 * npl_blk; k += PCGF_THREADS) plH[k] = G.HplP[18 * (size_t)plbase + k];
+  for (int k = threadIdx.x; k < npl_blk; k += PCGF_THREADS) pl_lm[k] = G.plP_lm[plbase + k];
+  for (int k = threadIdx.x; k < npp_blk; k += PCGF_THREADS) {
+    const int code = G.pose_pp_idx[ppbase + k];
+    const int e = code >> 1, role = code & 1;
+    pp_other[k] = (role == 0 ? G.pp[e].j : G.pp[e].i) | (role << 31);
+    for (int m = 0; m < 36; ++m) ppH[36 * k + m] = G.Hoff[36 * (size_t)e + m];
+  }
+  const int mypl0 = act ? G.pose_pl_rowptr[i] - plbase : 0, mypl1 = act ? G.pose_pl_rowptr[i + 1] - plbase : 0;
+  const int mypp0 = act ? G.pose_pp_rowptr[i] - ppbase : 0, mypp1 = act ? G.pose_pp_rowptr[i + 1] - ppbase : 0;
+  // landmark role: lane e of the warp owns edge e of landmark l
+  double HL[18];
+  int lpose = 0;
+  bool eact = false;
+  double Wi[6] = {0, 0, 0, 0, 0, 0};
+  if (lact) {
+    const int e0 = G.lm_rowptr[l], e1 = G.lm_rowptr[l + 1];
+    eact = e0 + lane < e1;
+    if (eact) {
+      lpose = G.pl[e0 + lane].p;
+#pragma unroll
+      for (int k = 0; k < 18; ++k) HL[k] = G.HplL[18 * (size_t)(e0 + lane) + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Wi[k] = G.HllInv[6 * (size_t)l + k];
+  }
+  if (!eact) {
+#pragma unroll
+    for (int k = 0; k < 18; ++k) HL[k] = 0.0;
+  }
+  // edges 32..63 of a landmark: second edge of the lane, block kept in shared memory
+  int nov = 0;
+  if (lact) nov = max(0, G.lm_rowptr[l + 1] - G.lm_rowptr[l] - 32);
+  if (lane == 0) ovcnt[warp] = nov;
+  __syncthreads();
+  int ovbase = 0;
+  for (int w = 0; w < warp; ++w) ovbase += ovcnt[w];
+  const bool eact2 = lane < nov;
+  int lpose2 = 0;
+  if (eact2) {
+    const int e = G.lm_rowptr[l] + 32 + lane;
+    lpose2 = G.pl[e].p;
+    for (int k = 0; k < 18; ++k) ovH[18 * (ovbase + lane) + k] = G.HplL[18 * (size_t)e + k];
+  }
+  const double* HL2 = ovH + 18 * (ovbase + lane);
+  __syncthreads();
+
+  // ---- init: x = 0, r = g, z = M^-1 r ------------------------------------------------------------
+  double xc = 0.0;
+  double rcomp = act ? G.g[6 * (size_t)i + comp] : 0.0;
+  double pold_c = 0.0, zc = 0.0, pc = 0.0, qv = 0.0;
+  double l6[6];
+  if (use_coarse) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) l6[k] = Brow[k] * rcomp;
+    block_sum6(l6, s6, red6);
+    grid_bar_sum(slots, epoch, 0.0, s6, rc, part_sh);
+    if (warp < 6) {
+      double t = 0.0;
+      for (int j = lane; j < nc; j += 32) t += Arow[warp * nc + j] * rc[j];
+      t = warp_sum(t);
+      if (lane == 0) zc6[warp] = t;
+    }
+    __syncthreads();
+  }
+  {
+    zc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) zc += Drow[k] * __shfl_sync(0xffffffffu, rcomp, base_lane + k);
+    if (use_coarse) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) zc += Brow[k] * zc6[k];
+    }
+    if (act) {
+      G.z[6 * (size_t)i + comp] = zc;
+      pold[6 * (size_t)i + comp] = 0.0;
+    } else {
+      zc = 0.0;
+    }
+  }
+  double bs = block_sum(rcomp * zc, sh);
+  double rz = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh);
+  const double rz0 = rz;
+  double beta = 0.0;
+  int it = 0;
+  if (!(rz0 > 0.0)) {
+    status = (rz0 == 0.0) ? 0 : 2;
+    maxit = 0;
+  }
+  SSB_TICK(2);
+  for (it = 0; it < maxit; ++it) {
+    // ---- phase 1 (landmark role)
+    if (lact) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      if (eact) {
+        const double2* zz = reinterpret_cast<const double2*>(G.z + 6 * (size_t)lpose);
+        const double2* po = reinterpret_cast<const double2*>(pold + 6 * (size_t)lpose);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double2 zv = __ldcg(zz + c), pv = __ldcg(po + c);
+          const double pa = zv.x + beta * pv.x, pb = zv.y + beta * pv.y;
+          a0 += HL[2 * c] * pa + HL[2 * c + 1] * pb;
+          a1 += HL[6 + 2 * c] * pa + HL[6 + 2 * c + 1] * pb;
+          a2 += HL[12 + 2 * c] * pa + HL[12 + 2 * c + 1] * pb;
+        }
+      }
+      if (eact2) {
+        const double2* zz = reinterpret_cast<const double2*>(G.z + 6 * (size_t)lpose2);
+        const double2* po = reinterpret_cast<const double2*>(pold + 6 * (size_t)lpose2);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double2 zv = __ldcg(zz + c), pv = __ldcg(po + c);
+          const double pa = zv.x + beta * pv.x, pb = zv.y + beta * pv.y;
+          a0 += HL2[2 * c] * pa + HL2[2 * c + 1] * pb;
+          a1 += HL2[6 + 2 * c] * pa + HL2[6 + 2 * c + 1] * pb;
+          a2 += HL2[12 + 2 * c] * pa + HL2[12 + 2 * c + 1] * pb;
+        }
+      }
+      a0 = warp_sum(a0);
+      a1 = warp_sum(a1);
+      a2 = warp_sum(a2);
+      if (lane == 0) {
+        G.v[3 * (size_t)l + 0] = Wi[0] * a0 + Wi[1] * a1 + Wi[2] * a2;
+        G.v[3 * (size_t)l + 1] = Wi[1] * a0 + Wi[3] * a1 + Wi[4] * a2;
+        G.v[3 * (size_t)l + 2] = Wi[2] * a0 + Wi[4] * a1 + Wi[5] * a2;
+      }
+    }
+    // own p (pose role) does not depend on phase 1: compute and publish before the barrier
+    pc = zc + beta * pold_c;
+    if (act) pnew[6 * (size_t)i + comp] = pc;
+    SSB_TICK(3);
+    grid_bar_sum(slots, epoch, 0.0, nullptr, nullptr, part_sh);
+    SSB_TICK(4);
+    // ---- phase 2 (pose role)
+    qv = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) qv += Hrow[k] * __shfl_sync(0xffffffffu, pc, base_lane + k);
+    {
+      int nmax = mypp1 - mypp0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+      for (int s = 0; s < nmax; ++s) {
+        const bool has = mypp0 + s < mypp1;
+        double oc = 0.0;
+        int role = 0;
+        const double* Ho = ppH;
+        if (has) {
+          const int code = pp_other[mypp0 + s];
+          const int other = code & 0x7fffffff;
+          role = (code >> 31) & 1;
+          Ho = ppH + 36 * (mypp0 + s);
+          oc = __ldcg(pnew + 6 * (size_t)other + comp);  // published before the barrier
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const double ok = __shfl_sync(0xffffffffu, oc, base_lane + k);
+          if (has) qv += (role == 0 ? Ho[6 * comp + k] : Ho[6 * k + comp]) * ok;
+        }
+      }
+    }
+    for (int kk = mypl0; kk < mypl1; ++kk) {
+      const double* Hp = plH + 18 * kk + 3 * comp;
+      const double* vv = G.v + 3 * (size_t)pl_lm[kk];
+      qv -= Hp[0] * __ldcg(vv) + Hp[1] * __ldcg(vv + 1) + Hp[2] * __ldcg(vv + 2);
+    }
+    if (!act) qv = 0.0;
+    bs = block_sum(pc * qv, sh);
+    if (use_coarse) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) l6[k] = Brow[k] * qv;
+      block_sum6(l6, s6, red6);
+    }
+    SSB_TICK(5);
+    const double pq = grid_bar_sum(slots, epoch, bs, use_coarse ? s6 : nullptr, use_coarse ? qc : nullptr, part_sh);
+    if (!(pq > 0.0) || !isfinite(pq)) {
+      status = 1;
+      break;
+    }
+    const double alpha = rz / pq;
+    SSB_TICK(4);
+    // ---- phase 3
+    if (use_coarse) {
+      for (int j = threadIdx.x; j < nc; j += PCGF_THREADS) rc[j] -= alpha * qc[j];
+      __syncthreads();
+      if (warp < 6) {
+        double t = 0.0;
+        for (int j = lane; j < nc; j += 32) t += Arow[warp * nc + j] * rc[j];
+        t = warp_sum(t);
+        if (lane == 0) zc6[warp] = t;
+      }
+      __syncthreads();
+    }
+    xc += alpha * pc;
+    rcomp -= alpha * qv;
+    zc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) zc += Drow[k] * __shfl_sync(0xffffffffu, rcomp, base_lane + k);
+    if (use_coarse) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) zc += Brow[k] * zc6[k];
+    }
+    if (act)
+      G.z[6 * (size_t)i + comp] = zc;
+    else
+      zc = 0.0;
+    pold_c = pc;
+    bs = block_sum(rcomp * zc, sh);
+    SSB_TICK(6);
+    const double rzn = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh);
+    SSB_TICK(4);
+    beta = rzn / rz;
+    rz = rzn;
+    double* t = pold;
+    pold = pnew;
+    pnew = t;
+    if (!(rz > tol2 * rz0)) {
+      ++it;
+      break;
+    }
+  }
+  if (act) G.x[6 * (size_t)i + comp] = xc;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    G.iscalars[0] = it;
+    G.iscalars[1] = status;
+    G.scalars[3] = rz;
+    G.scalars[4] = rz0;
+#ifdef SSB_PCG_TIMERS
+    for (int k = 0; k < 8; ++k) G.scalars[8 + k] += (double)tmr[k];
+#endif
   }
 }
 

@@ -18,7 +18,7 @@ def _d(a):
 
 class GraphSLAM:
     def __init__(self, verbose: bool = False, device: int = -1, pcg_tol: float = 1e-10, max_pcg_iters: int = 20000,
-                 preconditioner: int = 0, coarse_group: int = 32):
+                 preconditioner: int = 0, coarse_group: int = 32, force_generic: bool = False):
         self._L = _lib.lib()
         o = _lib.GraphOpts()
         self._L.ssb_graph_default_opts(C.byref(o))
@@ -28,6 +28,7 @@ class GraphSLAM:
         o.max_pcg_iters = max_pcg_iters
         o.preconditioner = preconditioner
         o.coarse_group = coarse_group
+        o.reserved[0] = int(force_generic)   # 1 = always use the streaming PCG kernel (no on-chip residency)
         h = self._L.ssb_graph_create(C.byref(o))
         if not h:
             raise _lib.SsbError("ssb_graph_create failed: " + _lib.last_error())

@@ -73,11 +73,12 @@ def test_chi2_matches_oracle():
     assert abs(a - b) <= 1e-11 * abs(b)
 
 
+@pytest.mark.parametrize("generic", [False, True])
 @pytest.mark.parametrize("precond", [0, 1])
 @pytest.mark.parametrize("lam", [10.0, 1e-2, 1e-6])
-def test_damped_solve_matches_sparse_cholesky(lam, precond):
+def test_damped_solve_matches_sparse_cholesky(lam, precond, generic):
     spec = synth.make_config_graph("cfg1")
-    g, o, ids = _pair(spec, pcg_tol=1e-13, preconditioner=precond)
+    g, o, ids = _pair(spec, pcg_tol=1e-13, preconditioner=precond, force_generic=generic)
     ok, xo = o.solve_once(lam)
     assert ok
     its, xg = g.solve_once(lam, xo.size)
@@ -85,10 +86,11 @@ def test_damped_solve_matches_sparse_cholesky(lam, precond):
     assert np.abs(xg - xo).max() <= 1e-8 * max(1.0, np.abs(xo).max()), (its, np.abs(xg - xo).max())
 
 
+@pytest.mark.parametrize("generic", [False, True])
 @pytest.mark.parametrize("precond", [0, 1])
-def test_lm_trajectory_cfg1(precond):
+def test_lm_trajectory_cfg1(precond, generic):
     spec = synth.make_config_graph("cfg1")
-    g, o, ids = _pair(spec, preconditioner=precond)
+    g, o, ids = _pair(spec, preconditioner=precond, force_generic=generic)
     assert g.optimize(8) and o.optimize(8)
     assert g.iterations == o.iterations == 8
     # per-iteration chi2 / lambda / trials agree
@@ -160,15 +162,17 @@ def test_coarse_level_reduces_pcg_iterations():
     """the rigid-body coarse level must give the same solution in far fewer PCG iterations (cfg5-size graph)"""
     spec = synth.make_graph(2000, 400, seed=77)
     xs, its = [], []
-    for precond in (0, 1):
-        g = GraphSLAM(pcg_tol=1e-12, preconditioner=precond)
+    for precond, generic in ((0, False), (1, False), (1, True)):
+        g = GraphSLAM(pcg_tol=1e-12, preconditioner=precond, force_generic=generic)
         synth.load_graph(g, spec)
         n = 6 * (spec.n_poses - 1) + 3 * spec.n_landmarks
         k, x = g.solve_once(1e-3, n)
         xs.append(x)
         its.append(k)
     assert np.abs(xs[0] - xs[1]).max() <= 1e-7 * max(1.0, np.abs(xs[0]).max())
+    assert np.abs(xs[0] - xs[2]).max() <= 1e-7 * max(1.0, np.abs(xs[0]).max())
     assert its[1] * 2 < its[0], its
+    assert abs(its[1] - its[2]) <= 2, its       # resident and streaming kernels run the same algorithm
 
 
 @pytest.mark.parametrize("precond", [0, 1])

@@ -138,6 +138,9 @@ int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len);
  * keyframe range inside ssb_graph_optimize.  world == 1 detaches. */
 int ssb_comm_unique_id(unsigned char id_out[128]);
 int ssb_graph_attach_comm(ssb_graph* g, int rank, int world, const unsigned char unique_id[128]);
+/* contiguous keyframe range [out[0], out[1]) and landmark range [out[2], out[3]) owned by `rank`
+ * (host-only, no GPU needed) */
+int ssb_shard_ranges(int n_poses, int n_landmarks, int world, int rank, int out4[4]);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Path (2): planar_segmentation RANSAC plane fit on bbox-cropped depth clouds                  */

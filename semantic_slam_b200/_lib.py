@@ -55,7 +55,7 @@ SYMBOLS = [
     "ssb_graph_hessian_index", "ssb_graph_get_all", "ssb_graph_set_all", "ssb_graph_invalidate", "ssb_graph_chi2",
     "ssb_graph_prepare", "ssb_graph_optimize", "ssb_graph_optimize_resident", "ssb_graph_get_history",
     "ssb_graph_landmark_marginals", "ssb_graph_save_g2o", "ssb_graph_load_g2o", "ssb_graph_edge_linearize",
-    "ssb_graph_solve_once", "ssb_comm_unique_id", "ssb_graph_attach_comm", "ssb_ransac_default_opts",
+    "ssb_graph_solve_once", "ssb_comm_unique_id", "ssb_graph_attach_comm", "ssb_shard_ranges", "ssb_ransac_default_opts",
     "ssb_ransac_create", "ssb_ransac_destroy", "ssb_ransac_plane_batch", "ssb_ransac_upload",
     "ssb_ransac_run_resident", "ssb_ransac_fetch", "ssb_ransac_stream", "ssb_ransac_launch_count", "ssb_ransac_timing", "ssb_crop_bbox",
     "ssb_last_error", "ssb_build_info", "ssb_graph_stream", "ssb_graph_snapshot", "ssb_graph_restore",
@@ -109,6 +109,7 @@ def lib():
     L.ssb_graph_restore.argtypes = [vp]
     L.ssb_comm_unique_id.argtypes = [C.c_char_p]
     L.ssb_graph_attach_comm.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.ssb_shard_ranges.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip]
     L.ssb_ransac_default_opts.argtypes = [C.POINTER(RansacOpts)]
     L.ssb_ransac_create.argtypes = [C.c_int]
     L.ssb_ransac_create.restype = vp

@@ -15,8 +15,59 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "../../include/ssb.h"
 #include "ssb_graph_kernels.cuh"
+
+// ---- NCCL, resolved at run time (the library the process already loaded — torch's — else libnccl.so.2).
+// Minimal declarations of the stable C ABI; nothing links against libnccl at build time.
+extern "C" {
+typedef struct ncclComm* ssb_ncclComm_t;
+typedef struct {
+  char internal[128];
+} ssb_ncclUniqueId;
+}
+namespace ssb {
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(ssb_ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ssb_ncclComm_t*, int, ssb_ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ssb_ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ssb_ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ssb_ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclSum = 0;
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!api.handle) api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!api.handle) return api;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+  api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString;
+  return api;
+}
+#define SSB_NCCL_CHECK(expr)                                                                        \
+  do {                                                                                              \
+    int _r = (expr);                                                                                \
+    if (_r != 0) {                                                                                  \
+      ::ssb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, nccl_api().GetErrorString(_r)); \
+      return SSB_ERR_COMM;                                                                          \
+    }                                                                                               \
+  } while (0)
+}  // namespace ssb
 
 namespace ssb {
 
@@ -129,6 +180,9 @@ struct ssb_graph {
   std::vector<double> history;  // 6 per iteration
   long long launches = 0;
   int comm_rank = 0, comm_world = 1;
+  ssb_ncclComm_t comm = nullptr;
+  DBuf<double> d_mg;
+  double* h_mg = nullptr;  // pinned, 16 doubles
 };
 
 static int check_vertex(const ssb_graph* g, int id, int kind) {
@@ -208,7 +262,8 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
   if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess ||
       cudaMallocHost((void**)&g->h_scalars, 32 * sizeof(double)) != cudaSuccess ||
-      cudaMallocHost((void**)&g->h_iscalars, 4 * sizeof(int)) != cudaSuccess) {
+      cudaMallocHost((void**)&g->h_iscalars, 4 * sizeof(int)) != cudaSuccess ||
+      cudaMallocHost((void**)&g->h_mg, 16 * sizeof(double)) != cudaSuccess) {
     set_error("CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete g;
     return nullptr;
@@ -245,6 +300,8 @@ void ssb_graph_destroy(ssb_graph* g) {
   if (g->ev1) cudaEventDestroy(g->ev1);
   if (g->h_scalars) cudaFreeHost(g->h_scalars);
   if (g->h_iscalars) cudaFreeHost(g->h_iscalars);
+  if (g->h_mg) cudaFreeHost(g->h_mg);
+  if (g->comm && nccl_api().ok) nccl_api().CommDestroy(g->comm);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
@@ -486,13 +543,14 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_HllInv.ensure((size_t)6 * Nl));
     SSB_TRY(g->d_Dinv.ensure((size_t)36 * Np));
     SSB_TRY(g->d_g.ensure((size_t)6 * Np));
-    SSB_TRY(g->d_x.ensure((size_t)6 * Np));
+    SSB_TRY(g->d_x.ensure((size_t)6 * (Np + 64)));
     SSB_TRY(g->d_r.ensure((size_t)6 * Np));
     SSB_TRY(g->d_z.ensure((size_t)6 * Np));
-    SSB_TRY(g->d_p0.ensure((size_t)6 * Np));
+    SSB_TRY(g->d_p0.ensure((size_t)6 * (Np + 64)));
     SSB_TRY(g->d_p1.ensure((size_t)6 * Np));
     SSB_TRY(g->d_q.ensure((size_t)6 * Np));
-    SSB_TRY(g->d_v.ensure((size_t)3 * Nl));
+    SSB_TRY(g->d_v.ensure((size_t)3 * (Nl + 64)));
+    SSB_TRY(g->d_mg.ensure(16));
     SSB_TRY(g->d_dl.ensure((size_t)3 * Nl));
     const size_t nb_bs = (size_t)(Np + Nl + 127) / 128 + 1;
     SSB_TRY(g->d_part.ensure(std::max<size_t>(3 * PART_STRIDE, nb_bs) + 4096));
@@ -689,6 +747,73 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;
 }
+// PCG row-sharded over the ranks of the attached NCCL communicator (see the k_mg_* kernels).
+__global__ void k_mg_finish(const double* mg, int* iscalars, double* scalars) {
+  iscalars[0] = (int)mg[5];
+  iscalars[1] = (int)mg[6];
+  scalars[3] = 0.0;
+  scalars[4] = mg[3];
+}
+static void shard_ranges(int Np, int Nl, int world, int rank, int out[4]) {
+  const int cp = (Np + world - 1) / world, cl = (Nl + world - 1) / world;
+  out[0] = std::min(Np, rank * cp);
+  out[1] = std::min(Np, out[0] + cp);
+  out[2] = std::min(Nl, rank * cl);
+  out[3] = std::min(Nl, out[2] + cl);
+}
+static int launch_solve_mg(ssb_graph* g, double lambda) {
+  DevGraph& G = g->G;
+  NcclApi& N = nccl_api();
+  cudaStream_t s = g->stream;
+  const int world = g->comm_world, rank = g->comm_rank;
+  if (G.Nl) {
+    k_prep_landmarks<<<(G.Nl + 127) / 128, 128, 0, s>>>(G, lambda);
+    g->launches++;
+  }
+  k_prep_poses<<<(G.Np + 63) / 64, 64, 0, s>>>(G, lambda);
+  g->launches++;
+  int rr[4];
+  shard_ranges(G.Np, G.Nl, world, rank, rr);
+  MgRange R{rr[0], rr[1], rr[2], rr[3]};
+  const int cp = (G.Np + world - 1) / world, cl = (G.Nl + world - 1) / world;
+  double* mg = g->d_mg.p;
+  double* p = g->d_p0.p;
+  const double tol2 = g->opts.pcg_tol * g->opts.pcg_tol;
+  const int own_p = std::max(1, R.pe - R.ps), own_l = std::max(1, R.le - R.ls);
+  const int gridp = std::max(1, std::min(4 * g->num_sms, (((own_p + 4) / 5) + 7) / 8));
+  const int gridl = std::max(1, std::min(4 * g->num_sms, (own_l + 7) / 8));
+  SSB_CUDA_CHECK(cudaMemsetAsync(mg, 0, 16 * sizeof(double), s));
+  k_mg_init<<<gridp, 256, 0, s>>>(G, R, mg, p);
+  SSB_NCCL_CHECK(N.AllReduce(mg, mg, 1, kNcclFloat64, kNcclSum, g->comm, s));
+  k_mg_after_init<<<1, 1, 0, s>>>(mg);
+  SSB_NCCL_CHECK(N.AllGather(p + (size_t)6 * rank * cp, p, (size_t)6 * cp, kNcclFloat64, g->comm, s));
+  g->launches += 2;
+  const int maxit = g->opts.max_pcg_iters;
+  for (int it = 0; it < maxit; ++it) {
+    const int par = it & 1;
+    k_mg_p1<<<gridl, 256, 0, s>>>(G, R, mg, p);
+    if (G.Nl) SSB_NCCL_CHECK(N.AllGather(G.v + (size_t)3 * rank * cl, G.v, (size_t)3 * cl, kNcclFloat64, g->comm, s));
+    k_mg_p2<<<gridp, 256, 0, s>>>(G, R, lambda, mg, p);
+    SSB_NCCL_CHECK(N.AllReduce(mg + 2, mg + 2, 1, kNcclFloat64, kNcclSum, g->comm, s));
+    k_mg_p3<<<gridp, 256, 0, s>>>(G, R, mg, p, par);
+    SSB_NCCL_CHECK(N.AllReduce(mg + (par ^ 1), mg + (par ^ 1), 1, kNcclFloat64, kNcclSum, g->comm, s));
+    k_mg_p4<<<gridp, 256, 0, s>>>(G, R, mg, p, par, tol2);
+    SSB_NCCL_CHECK(N.AllGather(p + (size_t)6 * rank * cp, p, (size_t)6 * cp, kNcclFloat64, g->comm, s));
+    g->launches += 4;
+    if ((it & 15) == 15 || it == maxit - 1) {
+      SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_mg, mg, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+      if (g->h_mg[4] != 0.0) break;
+    }
+  }
+  SSB_NCCL_CHECK(N.AllGather(G.x + (size_t)6 * rank * cp, G.x, (size_t)6 * cp, kNcclFloat64, g->comm, s));
+  k_mg_finish<<<1, 1, 0, s>>>(mg, G.iscalars, G.scalars);
+  k_backsub_update<<<(G.Np + G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
+  g->launches += 2;
+  SSB_CUDA_CHECK(cudaGetLastError());
+  return SSB_OK;
+}
+
 static int read_scalars(ssb_graph* g) {
   SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_scalars, g->d_scalars.p, 32 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
   SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_iscalars, g->d_iscalars.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
@@ -725,7 +850,10 @@ static int lm_loop(ssb_graph* g, int max_iterations, ssb_lm_stats* st) {
     int qmax = 0, pcg_its = 0;
     const double chi_before = currentChi;
     do {
-      SSB_TRY(launch_solve(g, lambda, 1));  // push() + setLambda + solve + update
+      if (g->comm_world > 1)
+        SSB_TRY(launch_solve_mg(g, lambda));
+      else
+        SSB_TRY(launch_solve(g, lambda, 1));  // push() + setLambda + solve + update
       SSB_TRY(launch_chi2(g));              // computeActiveErrors + activeRobustChi2
       SSB_TRY(read_scalars(g));
       st->total_trials++;
@@ -1166,21 +1294,45 @@ int ssb_graph_load_g2o(ssb_graph* g, const char* path) {
 }
 
 int ssb_comm_unique_id(unsigned char id_out[128]) {
-  (void)id_out;
-  set_error("multi-GPU: not built in this round yet");
-  return SSB_ERR_COMM;
+  if (!id_out) return SSB_ERR_INVALID;
+  NcclApi& N = nccl_api();
+  if (!N.ok) {
+    set_error("multi-GPU: libnccl.so.2 could not be loaded");
+    return SSB_ERR_COMM;
+  }
+  ssb_ncclUniqueId id;
+  SSB_NCCL_CHECK(N.GetUniqueId(&id));
+  std::memcpy(id_out, id.internal, 128);
+  return SSB_OK;
 }
 int ssb_graph_attach_comm(ssb_graph* g, int rank, int world, const unsigned char unique_id[128]) {
-  (void)unique_id;
-  if (!g) return SSB_ERR_INVALID;
-  if (world == 1) {
-    g->comm_rank = 0;
-    g->comm_world = 1;
-    return SSB_OK;
+  if (!g || world < 1 || rank < 0 || rank >= world) return SSB_ERR_INVALID;
+  NcclApi& N = nccl_api();
+  if (g->comm && N.ok) {
+    N.CommDestroy(g->comm);
+    g->comm = nullptr;
   }
-  (void)rank;
-  set_error("multi-GPU: not built in this round yet");
-  return SSB_ERR_COMM;
+  g->comm_rank = 0;
+  g->comm_world = 1;
+  if (world == 1) return SSB_OK;
+  if (!unique_id) return SSB_ERR_INVALID;
+  if (!N.ok) {
+    set_error("multi-GPU: libnccl.so.2 could not be loaded");
+    return SSB_ERR_COMM;
+  }
+  SSB_CUDA_CHECK(cudaSetDevice(g->device));
+  ssb_ncclUniqueId id;
+  std::memcpy(id.internal, unique_id, 128);
+  SSB_NCCL_CHECK(N.CommInitRank(&g->comm, world, id, rank));
+  g->comm_rank = rank;
+  g->comm_world = world;
+  return SSB_OK;
+}
+// contiguous keyframe / landmark ranges owned by `rank` (host-only helper, no GPU needed)
+int ssb_shard_ranges(int n_poses, int n_landmarks, int world, int rank, int out4[4]) {
+  if (world < 1 || rank < 0 || rank >= world || !out4 || n_poses < 0 || n_landmarks < 0) return SSB_ERR_INVALID;
+  shard_ranges(n_poses, n_landmarks, world, rank, out4);
+  return SSB_OK;
 }
 
 }  // extern "C"

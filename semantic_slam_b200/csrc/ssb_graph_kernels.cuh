@@ -1189,6 +1189,242 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Multi-GPU PCG phases (one process per GPU).  The Schur PCG is row-sharded by contiguous keyframe
+// range [ps, pe) and landmark range [ls, le); the vectors p, v (and finally x) are replicated with
+// NCCL all-gathers, the two dot products with NCCL all-reduces (host side: ssb_graph.cu).  Everything
+// else in the LM iteration (linearisation, update, chi2) is computed redundantly and deterministically
+// on every rank, so all ranks hold bit-identical estimates.  Block-Jacobi preconditioner.
+// mg scalars: [0],[1] rz ping-pong  [2] pq  [3] rz0  [4] done  [5] iterations  [6] status  [8..] scratch
+// ---------------------------------------------------------------------------------------------
+struct MgRange {
+  int ps, pe, ls, le;
+};
+
+__global__ void __launch_bounds__(256) k_mg_init(DevGraph G, MgRange R, double* mg, double* p) {
+  __shared__ double sh[33];
+  __shared__ int is_last;
+  const int lane = threadIdx.x & 31;
+  const int slot = lane / 6, comp = lane - 6 * slot, base_lane = 6 * slot;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
+  double local = 0.0;
+  for (int pbase = R.ps + gw * 5; pbase < R.pe; pbase += tw * 5) {
+    const int i = pbase + slot;
+    const bool act = lane < 30 && i < R.pe;
+    const double rc = act ? G.g[6 * (size_t)i + comp] : 0.0;
+    double zc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double rk = __shfl_sync(0xffffffffu, rc, base_lane + k);
+      if (act) zc += G.Dinv[36 * (size_t)i + 6 * comp + k] * rk;
+    }
+    if (act) {
+      G.x[6 * (size_t)i + comp] = 0.0;
+      G.r[6 * (size_t)i + comp] = rc;
+      G.z[6 * (size_t)i + comp] = zc;
+      p[6 * (size_t)i + comp] = zc;
+      local += rc * zc;
+    }
+  }
+  const double bs = block_sum(local, sh);
+  if (threadIdx.x == 0) {
+    G.part[blockIdx.x] = bs;
+    __threadfence();
+    is_last = (atomicAdd(G.iscalars + 3, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double s = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) s += __ldcg(G.part + k);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) {
+      mg[0] = s;  // local partial of rz0, all-reduced by the host
+      mg[4] = 0.0;
+      mg[5] = 0.0;
+      mg[6] = 0.0;
+      G.iscalars[3] = 0;
+    }
+  }
+}
+__global__ void k_mg_after_init(double* mg) {
+  mg[3] = mg[0];
+  if (!(mg[0] > 0.0)) {
+    mg[4] = 1.0;
+    if (mg[0] != 0.0) mg[6] = 2.0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_mg_p1(DevGraph G, MgRange R, const double* mg, const double* p) {
+  if (mg[4] != 0.0) return;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
+  for (int l = R.ls + gw; l < R.le; l += tw) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    const int e1 = G.lm_rowptr[l + 1];
+    for (int e = G.lm_rowptr[l] + lane; e < e1; e += 32) {
+      const double* Hl = G.HplL + 18 * (size_t)e;
+      const double* pp = p + 6 * (size_t)G.pl[e].p;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double pc = pp[c];
+        a0 += Hl[c] * pc;
+        a1 += Hl[6 + c] * pc;
+        a2 += Hl[12 + c] * pc;
+      }
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    if (lane == 0) {
+      const double* Wi = G.HllInv + 6 * (size_t)l;
+      G.v[3 * (size_t)l + 0] = Wi[0] * a0 + Wi[1] * a1 + Wi[2] * a2;
+      G.v[3 * (size_t)l + 1] = Wi[1] * a0 + Wi[3] * a1 + Wi[4] * a2;
+      G.v[3 * (size_t)l + 2] = Wi[2] * a0 + Wi[4] * a1 + Wi[5] * a2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_mg_p2(DevGraph G, MgRange R, double lambda, double* mg, const double* p) {
+  __shared__ double sh[33];
+  __shared__ int is_last;
+  if (mg[4] != 0.0) return;
+  const int lane = threadIdx.x & 31;
+  const int slot = lane / 6, comp = lane - 6 * slot, base_lane = 6 * slot;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
+  double local = 0.0;
+  for (int pbase = R.ps + gw * 5; pbase < R.pe; pbase += tw * 5) {
+    const int i = pbase + slot;
+    const bool act = lane < 30 && i < R.pe;
+    const double pc = act ? p[6 * (size_t)i + comp] : 0.0;
+    double qv = lambda * pc;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double pk = __shfl_sync(0xffffffffu, pc, base_lane + k);
+      if (act) qv += G.Hpp[36 * (size_t)i + 6 * comp + k] * pk;
+    }
+    if (act) {
+      for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
+        const int code = G.pose_pp_idx[kk];
+        const int e = code >> 1, role = code & 1;
+        const int other = role == 0 ? G.pp[e].j : G.pp[e].i;
+        const double* Ho = G.Hoff + 36 * (size_t)e;
+        const double* po = p + 6 * (size_t)other;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) qv += (role == 0 ? Ho[6 * comp + k] : Ho[6 * k + comp]) * po[k];
+      }
+      for (int kk = G.pose_pl_rowptr[i]; kk < G.pose_pl_rowptr[i + 1]; ++kk) {
+        const double* Hp = G.HplP + 18 * (size_t)kk + 3 * comp;
+        const double* vv = G.v + 3 * (size_t)G.plP_lm[kk];
+        qv -= Hp[0] * vv[0] + Hp[1] * vv[1] + Hp[2] * vv[2];
+      }
+      G.q[6 * (size_t)i + comp] = qv;
+      local += pc * qv;
+    }
+  }
+  const double bs = block_sum(local, sh);
+  if (threadIdx.x == 0) {
+    G.part[blockIdx.x] = bs;
+    __threadfence();
+    is_last = (atomicAdd(G.iscalars + 3, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double s = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) s += __ldcg(G.part + k);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) {
+      mg[2] = s;
+      G.iscalars[3] = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_mg_p3(DevGraph G, MgRange R, double* mg, const double* p, int par) {
+  __shared__ double sh[33];
+  __shared__ int is_last;
+  if (mg[4] != 0.0) return;
+  const double pq = mg[2];
+  const bool bad = !(pq > 0.0) || !isfinite(pq);
+  const double alpha = bad ? 0.0 : mg[par] / pq;
+  const int lane = threadIdx.x & 31;
+  const int slot = lane / 6, comp = lane - 6 * slot, base_lane = 6 * slot;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
+  double local = 0.0;
+  for (int pbase = R.ps + gw * 5; pbase < R.pe; pbase += tw * 5) {
+    const int i = pbase + slot;
+    const bool act = lane < 30 && i < R.pe;
+    double rc = 0.0;
+    if (act) {
+      const size_t o = 6 * (size_t)i + comp;
+      G.x[o] += alpha * p[o];
+      rc = G.r[o] - alpha * G.q[o];
+      G.r[o] = rc;
+    }
+    double zc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double rk = __shfl_sync(0xffffffffu, rc, base_lane + k);
+      if (act) zc += G.Dinv[36 * (size_t)i + 6 * comp + k] * rk;
+    }
+    if (act) {
+      G.z[6 * (size_t)i + comp] = zc;
+      local += rc * zc;
+    }
+  }
+  const double bs = block_sum(local, sh);
+  if (threadIdx.x == 0) {
+    G.part[blockIdx.x] = bs;
+    __threadfence();
+    is_last = (atomicAdd(G.iscalars + 3, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double s = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) s += __ldcg(G.part + k);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) {
+      mg[par ^ 1] = s;  // local partial of the new rz, all-reduced by the host
+      G.iscalars[3] = 0;
+      if (bad) mg[7] = 1.0;  // breakdown seen by this rank (identical on all ranks)
+    }
+  }
+}
+
+// beta = rz_new / rz_old ; p = z + beta p (owned rows) ; convergence / breakdown flags
+__global__ void __launch_bounds__(256) k_mg_p4(DevGraph G, MgRange R, double* mg, double* p, int par, double tol2) {
+  if (mg[4] != 0.0) return;
+  const double rzo = mg[par], rzn = mg[par ^ 1];
+  const bool bad = mg[7] != 0.0;
+  const double beta = rzn / rzo;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = 6 * (R.pe - R.ps);
+  for (int k = t; k < n; k += gridDim.x * blockDim.x) {
+    const size_t o = 6 * (size_t)R.ps + k;
+    p[o] = G.z[o] + beta * p[o];
+  }
+  // the flags are written by the block that finishes last so that no block of this launch sees them early
+  __shared__ int is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = (atomicAdd(G.iscalars + 3, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    G.iscalars[3] = 0;
+    mg[5] += 1.0;
+    if (bad) {
+      mg[6] = 1.0;
+      mg[4] = 1.0;
+    } else if (!(rzn > tol2 * mg[3])) {
+      mg[4] = 1.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K4: back-substitution + state update (+ backup for LM reject) + computeScale partials
 //   dl = (Hll+lambda)^-1 (bl - sum_e HplL_e dp),  l += dl ;  X <- X * fromVectorMQT(dp)
 //   scale = sum_j d_j (lambda d_j + b_j)      (OptimizationAlgorithmLevenberg::computeScale)

@@ -711,7 +711,7 @@ static int launch_linearize(ssb_graph* g) {
   g->have_system = true;
   return SSB_OK;
 }
-static int launch_solve(ssb_graph* g, double lambda, int apply) {
+static int launch_prep(ssb_graph* g, double lambda) {
   DevGraph& G = g->G;
   cudaStream_t s = g->stream;
   if (G.Nl) {
@@ -720,6 +720,25 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
   }
   k_prep_poses<<<(G.Np + 63) / 64, 64, 0, s>>>(G, lambda);
   g->launches++;
+  SSB_CUDA_CHECK(cudaGetLastError());
+  return SSB_OK;
+}
+static int launch_pcg(ssb_graph* g, double lambda);
+static int launch_solve(ssb_graph* g, double lambda, int apply) {
+  DevGraph& G = g->G;
+  cudaStream_t s = g->stream;
+  SSB_TRY(launch_prep(g, lambda));
+  SSB_TRY(launch_pcg(g, lambda));
+  if (apply) {
+    k_backsub_update<<<(G.Np + G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
+    g->launches++;
+  }
+  SSB_CUDA_CHECK(cudaGetLastError());
+  return SSB_OK;
+}
+static int launch_pcg(ssb_graph* g, double lambda) {
+  DevGraph& G = g->G;
+  cudaStream_t s = g->stream;
   double tol2 = g->opts.pcg_tol * g->opts.pcg_tol;
   int maxit = g->opts.max_pcg_iters;
   BarSlot* slots = g->d_slots.p;
@@ -740,10 +759,6 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used + 1], s));
   g->ev_used += 2;
   g->launches++;
-  if (apply) {
-    k_backsub_update<<<(G.Np + G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
-    g->launches++;
-  }
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;
 }
@@ -1155,12 +1170,40 @@ int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len) {
 }
 
 int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* out9n) {
-  (void)vids;
-  (void)n;
-  (void)out9n;
-  if (!g) return SSB_ERR_INVALID;
-  set_error("landmark marginals: not implemented yet");
-  return 0;
+  if (!g || (n > 0 && (!vids || !out9n)) || n < 0) return SSB_ERR_INVALID;
+  for (int k = 0; k < n; ++k)
+    if (!check_vertex(g, vids[k], VK_XYZ) || g->V[vids[k]].fixed) {
+      set_error("landmark_marginals: vertex %d is not a free XYZ vertex", vids[k]);
+      return SSB_ERR_INVALID;
+    }
+  if (g->E.size() < 10) return 0;  // nothing was ever optimised (graph_slam.cpp:184-186)
+  if (g->comm_world > 1) {
+    set_error("landmark_marginals: not available on a sharded graph in this round");
+    return 0;
+  }
+  SSB_TRY(prepare(g));
+  if (!g->have_system) SSB_TRY(launch_linearize(g));  // else: the system built by the last optimize (g2o semantics)
+  SSB_TRY(launch_prep(g, 0.0));
+  SSB_TRY(g->d_tmp.ensure((size_t)std::max(128, 9 * n)));
+  const size_t ev_keep = g->ev_used;
+  for (int k = 0; k < n; ++k) {
+    const int l = g->V[vids[k]].idx;
+    for (int c = 0; c < 3; ++c) {
+      k_marg_rhs<<<1, 256, 0, g->stream>>>(g->G, l, c);
+      g->ev_used = ev_keep;  // do not grow the timing-event pool
+      SSB_TRY(launch_pcg(g, 0.0));
+      k_marg_out<<<1, 64, 0, g->stream>>>(g->G, l, c, g->d_tmp.p + 9 * (size_t)k);
+      g->launches += 2;
+    }
+  }
+  g->ev_used = ev_keep;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(out9n, g->d_tmp.p, (size_t)9 * n * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  SSB_TRY(read_scalars(g));
+  if (g->h_iscalars[1] != 0) {
+    set_error("landmark_marginals: PCG breakdown");
+    return 0;
+  }
+  return 1;
 }
 
 // ---- g2o text format (graph_slam.cpp:236-239 -> OptimizableGraph::save) ---------------------

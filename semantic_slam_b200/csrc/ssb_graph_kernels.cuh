@@ -1572,6 +1572,43 @@ __global__ void __launch_bounds__(CHI2_THREADS) k_chi2(DevGraph G, double* part,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K5: landmark marginals  (H^-1)[l,l] = W + W Hlp S^-1 Hpl W  with W = Hll_l^-1, S the undamped Schur
+// complement (GraphSLAM::computeLandmarkMarginals, graph_slam.cpp:221-234).  One PCG solve per column.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_marg_rhs(DevGraph G, int l, int c) {
+  const int n = 6 * G.Np;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) G.g[k] = 0.0;
+  __syncthreads();
+  const double* Wu = G.HllInv + 6 * (size_t)l;
+  const double W[9] = {Wu[0], Wu[1], Wu[2], Wu[1], Wu[3], Wu[4], Wu[2], Wu[4], Wu[5]};
+  const double w[3] = {W[c], W[3 + c], W[6 + c]};  // W e_c
+  for (int e = G.lm_rowptr[l] + threadIdx.x; e < G.lm_rowptr[l + 1]; e += blockDim.x) {
+    const double* Hl = G.HplL + 18 * (size_t)e;  // 3x6 = Hpl_e'
+    const int p = G.pl[e].p;
+    for (int k = 0; k < 6; ++k) atomicAdd(G.g + 6 * (size_t)p + k, Hl[k] * w[0] + Hl[6 + k] * w[1] + Hl[12 + k] * w[2]);
+  }
+}
+__global__ void k_marg_out(DevGraph G, int l, int c, double* out9) {
+  __shared__ double sh[33];
+  double a[3] = {0, 0, 0};
+  for (int e = G.lm_rowptr[l] + threadIdx.x; e < G.lm_rowptr[l + 1]; e += blockDim.x) {
+    const double* Hl = G.HplL + 18 * (size_t)e;
+    const double* x = G.x + 6 * (size_t)G.pl[e].p;
+    for (int k = 0; k < 6; ++k) {
+      a[0] += Hl[k] * x[k];
+      a[1] += Hl[6 + k] * x[k];
+      a[2] += Hl[12 + k] * x[k];
+    }
+  }
+  for (int k = 0; k < 3; ++k) a[k] = block_sum(a[k], sh);
+  if (threadIdx.x == 0) {
+    const double* Wu = G.HllInv + 6 * (size_t)l;
+    const double W[9] = {Wu[0], Wu[1], Wu[2], Wu[1], Wu[3], Wu[4], Wu[2], Wu[4], Wu[5]};
+    for (int r = 0; r < 3; ++r) out9[3 * r + c] = W[3 * r + c] + W[3 * r] * a[0] + W[3 * r + 1] * a[1] + W[3 * r + 2] * a[2];
+  }
+}
+
 // restore estimates (LM reject / benchmark restore)
 __global__ void k_copy_state(Pose* dst_pose, const Pose* src_pose, int Np, double* dst_lm, const double* src_lm, int Nl) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;

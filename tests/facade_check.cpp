@@ -1,0 +1,39 @@
+// Compile-and-run check of the C++ facade (POD twin; Eigen is absent from this image).
+// Built by tests/test_facade.py with g++ against include/ssb.h and libssb.so.
+#include <cmath>
+#include <cstdio>
+#include "ps_graph_slam/graph_slam.hpp"
+#include "planar_segmentation/plane_segmentation_b200.h"
+
+int main(int argc, char** argv) {
+  const bool run = argc > 1;  // without arguments: construct nothing (no GPU needed), just prove it links
+  if (!run) {
+    std::printf("facade linked: %s\n", ssb_build_info());
+    return 0;
+  }
+  ps_graph_slam::GraphSLAM gs(false);
+  if (!gs.graph) return 2;
+  using namespace ssb_host;
+  std::vector<g2o::VertexSE3*> kf;
+  for (int k = 0; k < 12; ++k) {
+    Isometry3d T = Isometry3d::Identity();
+    T.m[3] = 0.5 * k + (k ? 0.03 : 0.0);
+    kf.push_back(gs.add_se3_node(T));
+    if (k) {
+      Isometry3d Z = Isometry3d::Identity();
+      Z.m[3] = 0.5;
+      gs.add_se3_edge(kf[k - 1], kf[k], Z, MatrixXd::Identity(6));
+    }
+  }
+  Vector3d p{{2.0, 1.0, 0.5}};
+  g2o::VertexPointXYZ* lm = gs.add_point_xyz_node(p);
+  for (int k = 0; k < 12; ++k) {
+    Vector3d z{{2.0 - 0.5 * k, 1.0, 0.5}};
+    gs.add_se3_point_xyz_edge(kf[k], lm, z, MatrixXd::Identity(3));
+  }
+  if (!gs.optimize()) return 3;
+  Isometry3d last = kf.back()->estimate();
+  std::printf("last keyframe x = %.6f (expect 5.5), hessianIndex(first)=%d id(last)=%d\n", last.m[3], kf[0]->hessianIndex(),
+              kf.back()->id());
+  return std::fabs(last.m[3] - 5.5) < 1e-6 ? 0 : 4;
+}

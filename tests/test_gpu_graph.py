@@ -105,6 +105,35 @@ def test_lm_trajectory_cfg1(precond, generic):
     assert np.abs(X - Xo).max() <= 1e-5 * max(1.0, np.abs(Xo).max())
 
 
+def test_landmark_marginals_match_oracle():
+    """GraphSLAM::computeLandmarkMarginals (graph_slam.cpp:221-234): 3x3 blocks of H^-1 of the last built system"""
+    spec = synth.make_config_graph("cfg1")
+    g, o, ids = _pair(spec, preconditioner=1, pcg_tol=1e-12)
+    assert g.optimize(3) and o.optimize(3)
+    lms = [int(ids[v]) for v in range(spec.vkind.size) if spec.vkind[v] == 1][:5]
+    Mg = g.computeLandmarkMarginals(lms)
+    Mo = o.computeLandmarkMarginals(lms, relinearize=False)
+    assert Mg is not None
+    assert np.abs(Mg - Mo).max() <= 1e-6 * np.abs(Mo).max()
+    assert g.hessian_index(lms[0]) == lms[0] - 1       # first vertex fixed -> index shifts by one
+
+
+def test_g2o_save_load_roundtrip(tmp_path):
+    spec = synth.make_config_graph("cfg1")
+    g, o, ids = _pair(spec)
+    path = str(tmp_path / "graph.g2o")
+    g.save(path)
+    txt = open(path).read()
+    assert txt.startswith("PARAMS_SE3OFFSET 0") and "VERTEX_SE3:QUAT 0 " in txt and "FIX 0" in txt
+    assert txt.count("EDGE_SE3_TRACKXYZ") == int((spec.ekind == 1).sum())
+    g2 = GraphSLAM()
+    g2.load(path)
+    assert g2.num_vertices() == g.num_vertices() and g2.num_edges() == g.num_edges()
+    assert abs(g2.chi2() - g.chi2()) <= 1e-9 * g.chi2()
+    assert g2.optimize(4) and g.optimize(4)
+    assert abs(g2.stats["chi2_final"] - g.stats["chi2_final"]) <= 1e-9 * g.stats["chi2_final"]
+
+
 def test_optimize_skips_small_graphs():
     g = GraphSLAM()
     T0 = synth.T_make(np.eye(3), np.zeros(3))

@@ -221,7 +221,7 @@ void ssb_graph_default_opts(ssb_graph_opts* o) {
   o->device = -1;
   o->verbose = 0;
   o->max_pcg_iters = 20000;
-  o->pcg_tol = 1e-10;
+  o->pcg_tol = 1e-8;
   o->preconditioner = 0;
   o->coarse_group = 32;
 }
@@ -233,7 +233,7 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
   else
     ssb_graph_default_opts(&g->opts);
   if (g->opts.max_pcg_iters <= 0) g->opts.max_pcg_iters = 20000;
-  if (!(g->opts.pcg_tol > 0)) g->opts.pcg_tol = 1e-10;
+  if (!(g->opts.pcg_tol > 0)) g->opts.pcg_tol = 1e-8;
   int dev = g->opts.device;
   cudaError_t e;
   if (dev < 0) {

@@ -292,14 +292,28 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // Grid barrier fused with a fixed-order all-reduce of one double per CTA (+ optional all-gather of 6
 // doubles per CTA into `gather` (smem, 6 * gridDim.x)).  Arrival = payload store + release-add on one
-// counter; one thread per CTA spins on the counter; then every CTA reads the gridDim.x payload slots
-// and every warp folds them in the same fixed order.  `part_sh` = gridDim.x doubles of smem.
+// counter; ONE thread per CTA spins on the counter (many pollers per CTA were measured 2x slower: the
+// L2 polling traffic delays the CTAs that are still working); then every CTA reads the gridDim.x payload
+// slots and every warp folds them in the same fixed order.  Slots are double buffered on the epoch parity.
 // Every thread of every CTA must call it; requires gridDim.x <= blockDim.x and co-resident CTAs.
 __device__ __forceinline__ double grid_bar_sum(BarSlot* slots, unsigned& epoch, double my_partial, const double* my6,
                                                double* gather, double* part_sh) {
@@ -332,6 +346,29 @@ __device__ __forceinline__ double grid_bar_sum(BarSlot* slots, unsigned& epoch, 
   double t = 0.0;
   for (int k = (threadIdx.x & 31); k < (int)gridDim.x; k += 32) t += part_sh[k];
   return warp_sum(t);
+}
+
+// deterministic block reduction of 7 values (v0 and v6[0..5]) with a single __syncthreads: every warp
+// publishes its 7 warp sums, then every warp folds the per-warp values in the same fixed order.
+// Result: returned value = sum of v0; out6[0..5] (smem) = sums of v6 (valid after the next __syncthreads).
+__device__ __forceinline__ double block_sum7(double v0, const double* v6, double* out6, double* scratch /* 7*32 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double r[7];
+  r[0] = warp_sum(v0);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) r[1 + k] = warp_sum(v6[k]);
+  __syncthreads();  // scratch may still be read from the previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) scratch[7 * w + k] = r[k];
+  }
+  __syncthreads();
+  // lane k < 7 of every warp folds value k over the warps in order; lane 0's result is broadcast
+  double t = 0.0;
+  if (lane < 7)
+    for (int ww = 0; ww < nw; ++ww) t += scratch[7 * ww + lane];
+  if (w == 0 && lane >= 1 && lane < 7) out6[lane - 1] = t;
+  return __shfl_sync(0xffffffffu, t, 0);
 }
 
 // deterministic block reduction of 6 values per thread -> out6 (smem), valid after return
@@ -892,7 +929,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     k_pcg_fast(DevGraph G, CoarseDev Cz, BarSlot* slots, double lambda, double tol2, int maxit) {
   extern __shared__ __align__(16) double dsm[];
   __shared__ double sh[33];
-  __shared__ double s6[8], zc6[8], red6[6 * 32];
+  __shared__ double s6[8], zc6[8], red6[7 * 32];
   const int nblk = gridDim.x;
   const int nc = 6 * nblk;
   double* part_sh = dsm;                  // [PCGF_THREADS]
@@ -1089,25 +1126,60 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     SSB_TICK(3);
     grid_bar_sum(slots, epoch, 0.0, nullptr, nullptr, part_sh);
     SSB_TICK(4);
-    // ---- phase 2 (pose role)
+    // ---- phase 2 (pose role): all L2 loads of the phase are issued up front (one round trip)
+    double nb0 = 0.0, nb1 = 0.0;   // own component of the first two pose-pose neighbours' p
+    int role0 = 0, role1 = 0;
+    const bool has0 = mypp0 < mypp1, has1 = mypp0 + 1 < mypp1;
+    if (has0) {
+      const int code = pp_other[mypp0];
+      role0 = (code >> 31) & 1;
+      nb0 = __ldcg(pnew + 6 * (size_t)(code & 0x7fffffff) + comp);
+    }
+    if (has1) {
+      const int code = pp_other[mypp0 + 1];
+      role1 = (code >> 31) & 1;
+      nb1 = __ldcg(pnew + 6 * (size_t)(code & 0x7fffffff) + comp);
+    }
+    double vx[6], vy[6], vz[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int kk = mypl0 + u;
+      if (kk < mypl1) {
+        const double* vv = G.v + 3 * (size_t)pl_lm[kk];
+        vx[u] = __ldcg(vv);
+        vy[u] = __ldcg(vv + 1);
+        vz[u] = __ldcg(vv + 2);
+      } else {
+        vx[u] = vy[u] = vz[u] = 0.0;
+      }
+    }
     qv = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) qv += Hrow[k] * __shfl_sync(0xffffffffu, pc, base_lane + k);
     {
-      int nmax = mypp1 - mypp0;
+      const double* Ho0 = ppH + 36 * mypp0;
+      const double* Ho1 = Ho0 + 36;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double o0 = __shfl_sync(0xffffffffu, nb0, base_lane + k);
+        const double o1 = __shfl_sync(0xffffffffu, nb1, base_lane + k);
+        if (has0) qv += (role0 == 0 ? Ho0[6 * comp + k] : Ho0[6 * k + comp]) * o0;
+        if (has1) qv += (role1 == 0 ? Ho1[6 * comp + k] : Ho1[6 * k + comp]) * o1;
+      }
+      // further neighbours (loop closures): generic loop
+      int nmax = mypp1 - mypp0 - 2;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
       for (int s = 0; s < nmax; ++s) {
-        const bool has = mypp0 + s < mypp1;
+        const bool has = mypp0 + 2 + s < mypp1;
         double oc = 0.0;
         int role = 0;
         const double* Ho = ppH;
         if (has) {
-          const int code = pp_other[mypp0 + s];
-          const int other = code & 0x7fffffff;
+          const int code = pp_other[mypp0 + 2 + s];
           role = (code >> 31) & 1;
-          Ho = ppH + 36 * (mypp0 + s);
-          oc = __ldcg(pnew + 6 * (size_t)other + comp);  // published before the barrier
+          Ho = ppH + 36 * (mypp0 + 2 + s);
+          oc = __ldcg(pnew + 6 * (size_t)(code & 0x7fffffff) + comp);
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
@@ -1116,17 +1188,45 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
         }
       }
     }
-    for (int kk = mypl0; kk < mypl1; ++kk) {
-      const double* Hp = plH + 18 * kk + 3 * comp;
-      const double* vv = G.v + 3 * (size_t)pl_lm[kk];
-      qv -= Hp[0] * __ldcg(vv) + Hp[1] * __ldcg(vv + 1) + Hp[2] * __ldcg(vv + 2);
+    SSB_TICK(7);
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int kk = mypl0 + u;
+      if (kk < mypl1) {
+        const double* Hp = plH + 18 * kk + 3 * comp;
+        qv -= Hp[0] * vx[u] + Hp[1] * vy[u] + Hp[2] * vz[u];
+      }
+    }
+    for (int kb = mypl0 + 6; kb < mypl1; kb += 6) {
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int kk = kb + u;
+        if (kk < mypl1) {
+          const double* vv = G.v + 3 * (size_t)pl_lm[kk];
+          vx[u] = __ldcg(vv);
+          vy[u] = __ldcg(vv + 1);
+          vz[u] = __ldcg(vv + 2);
+        } else {
+          vx[u] = vy[u] = vz[u] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int kk = kb + u;
+        if (kk < mypl1) {
+          const double* Hp = plH + 18 * kk + 3 * comp;
+          qv -= Hp[0] * vx[u] + Hp[1] * vy[u] + Hp[2] * vz[u];
+        }
+      }
     }
     if (!act) qv = 0.0;
-    bs = block_sum(pc * qv, sh);
+    SSB_TICK(0);
     if (use_coarse) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) l6[k] = Brow[k] * qv;
-      block_sum6(l6, s6, red6);
+      bs = block_sum7(pc * qv, l6, s6, red6);
+    } else {
+      bs = block_sum(pc * qv, sh);
     }
     SSB_TICK(5);
     const double pq = grid_bar_sum(slots, epoch, bs, use_coarse ? s6 : nullptr, use_coarse ? qc : nullptr, part_sh);

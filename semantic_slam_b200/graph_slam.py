@@ -17,7 +17,7 @@ def _d(a):
 
 
 class GraphSLAM:
-    def __init__(self, verbose: bool = False, device: int = -1, pcg_tol: float = 1e-10, max_pcg_iters: int = 20000,
+    def __init__(self, verbose: bool = False, device: int = -1, pcg_tol: float = 1e-8, max_pcg_iters: int = 20000,
                  preconditioner: int = 0, coarse_group: int = 32, force_generic: bool = False):
         self._L = _lib.lib()
         o = _lib.GraphOpts()

@@ -33,7 +33,8 @@ typedef struct ssb_graph_opts {
   int verbose;          /* graph_slam.cpp:41 verbose_                                             */
   int max_pcg_iters;    /* cap on PCG iterations per damped solve (default 20000)                 */
   double pcg_tol;       /* stop when sqrt(r'M^-1 r) <= pcg_tol * sqrt(r0'M^-1 r0) (default 1e-8)   */
-  int preconditioner;   /* 0 = block-Jacobi on the Schur complement; 1 = + rigid-body coarse level */
+  int preconditioner;   /* 0 = block-Jacobi on the Schur complement; 1 = + rigid-body coarse level (one
+                           aggregate per CTA); 2 = + a middle level of 5-pose aggregates (3-level additive) */
   int coarse_group;     /* poses per coarse aggregate when preconditioner == 1 (default 32)        */
   int reserved[4];
 } ssb_graph_opts;

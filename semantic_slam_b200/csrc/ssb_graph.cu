@@ -167,7 +167,7 @@ struct ssb_graph {
   DBuf<double> d_x, d_r, d_z, d_p0, d_p1, d_q, d_v, d_dl, d_part, d_scalars, d_tmp;
   DBuf<int> d_iscalars;
   // coarse level
-  DBuf<double> d_Bmat, d_Grun, d_panel;
+  DBuf<double> d_Bmat, d_Grun, d_panel, d_B1mat, d_D1inv;
   DBuf<int> d_run_lm, d_run_group, d_run_e0, d_lm_run_rowptr, d_grp_run_rowptr, d_grp_runs;
   DBuf<BarSlot> d_slots;
   CoarseDev Cz;
@@ -578,6 +578,8 @@ static int prepare(ssb_graph* g) {
       g->fast_ok = ok;
     }
     SSB_TRY(g->d_Bmat.ensure((size_t)36 * Np));
+    SSB_TRY(g->d_B1mat.ensure((size_t)36 * Np));
+    SSB_TRY(g->d_D1inv.ensure((size_t)36 * ((Np + 4) / 5 + 1)));
     SSB_TRY(g->d_Grun.ensure((size_t)18 * n_runs));
     SSB_TRY(g->d_panel.ensure((size_t)2 * (6 * ncoarse + 8)));
     SSB_TRY(g->d_run_lm.ensure(n_runs));
@@ -598,7 +600,10 @@ static int prepare(ssb_graph* g) {
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_run_rowptr.p, grp_run_rowptr.data(), (nblk + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     {
       CoarseDev& Cz = g->Cz;
-      Cz.enabled = g->opts.preconditioner == 1 ? 1 : 0;
+      Cz.enabled = g->opts.preconditioner >= 1 ? 1 : 0;
+      Cz.sub_enabled = g->opts.preconditioner >= 2 ? 1 : 0;
+      Cz.B1mat = g->d_B1mat.p;
+      Cz.D1inv = g->d_D1inv.p;
       Cz.C = Cc;
       Cz.nc = ncoarse;
       Cz.Bmat = g->d_Bmat.p;
@@ -699,6 +704,10 @@ static int launch_linearize(ssb_graph* g) {
     k_lin_poses<<<(G.Np + 63) / 64, 64, 0, g->stream>>>(G);
     g->launches++;
   }
+  if (g->Cz.sub_enabled && G.Np) {
+    k_sub_basis<<<((G.Np + 4) / 5 + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
+    g->launches++;
+  }
   if (g->Cz.enabled) {
     k_coarse_basis<<<g->pcg_grid, 256, 0, g->stream>>>(G, g->Cz);
     g->launches++;
@@ -720,6 +729,10 @@ static int launch_prep(ssb_graph* g, double lambda) {
   }
   k_prep_poses<<<(G.Np + 63) / 64, 64, 0, s>>>(G, lambda);
   g->launches++;
+  if (g->Cz.sub_enabled && g->comm_world == 1) {
+    k_sub_assemble<<<((G.Np + 4) / 5 + 63) / 64, 64, 0, s>>>(G, g->Cz, lambda);
+    g->launches++;
+  }
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;
 }

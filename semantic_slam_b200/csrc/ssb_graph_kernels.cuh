@@ -279,6 +279,10 @@ struct CoarseDev {
   const int* grp_runs;        // runs sorted by group
   int n_runs;
   double* panel;           // [2][6*nc + 8] Gauss-Jordan pivot panels (double buffered)
+  // middle level: aggregates of 5 consecutive poses (= the 5 poses one warp owns)
+  int sub_enabled;
+  double* B1mat;           // [Np][36] prolongation blocks about the 5-pose centroid
+  double* D1inv;           // [ceil(Np/5)][36] inverse of P1' S P1 diagonal blocks (zero = level off for the aggregate)
 };
 
 struct BarSlot {  // one 64 B line per CTA and buffer; slot [2*gridDim.x] holds the arrival counter
@@ -482,6 +486,128 @@ __global__ void __launch_bounds__(128) k_coarse_runs(DevGraph G, CoarseDev Cz) {
   for (int k = 0; k < 18; ++k) Cz.Grun[18 * (size_t)r + k] = acc[k];
 }
 
+// ---- middle level (5-pose aggregates) -----------------------------------------------------------
+__global__ void __launch_bounds__(128) k_sub_basis(DevGraph G, CoarseDev Cz) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = 5 * a, i1 = min(G.Np, i0 + 5);
+  if (i0 >= G.Np) return;
+  double cen[3] = {0, 0, 0};
+  for (int i = i0; i < i1; ++i)
+    for (int k = 0; k < 3; ++k) cen[k] += G.pose[i].t[k];
+  for (int k = 0; k < 3; ++k) cen[k] /= (double)(i1 - i0);
+  for (int i = i0; i < i1; ++i) {
+    double* B = Cz.B1mat + 36 * (size_t)i;
+    if (G.pose_fixed[i]) {
+      for (int k = 0; k < 36; ++k) B[k] = 0.0;
+      continue;
+    }
+    const Pose X = G.pose[i];
+    double R[9];
+    quat_to_R(X.q, R);
+    const double d[3] = {X.t[0] - cen[0], X.t[1] - cen[1], X.t[2] - cen[2]};
+    const double Sx[9] = {0, -d[2], d[1], d[2], 0, -d[0], -d[1], d[0], 0};
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        const double rt = R[3 * c + r];
+        B[6 * r + c] = rt;
+        B[6 * r + 3 + c] = -(R[r] * Sx[c] + R[3 + r] * Sx[3 + c] + R[6 + r] * Sx[6 + c]);
+        B[6 * (3 + r) + c] = 0.0;
+        B[6 * (3 + r) + 3 + c] = 0.5 * rt;
+      }
+  }
+}
+
+// per damped trial: D1 = P1' S P1 restricted to the aggregate (6x6), inverted.  One thread per aggregate.
+__global__ void __launch_bounds__(64) k_sub_assemble(DevGraph G, CoarseDev Cz, double lambda) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = 5 * a, i1 = min(G.Np, i0 + 5);
+  if (i0 >= G.Np) return;
+  double D[36];
+  for (int k = 0; k < 36; ++k) D[k] = 0.0;
+  bool any = false;
+  for (int i = i0; i < i1; ++i) {
+    if (G.pose_fixed[i]) continue;
+    any = true;
+    const double* B = Cz.B1mat + 36 * (size_t)i;
+    const double* H = G.Hpp + 36 * (size_t)i;
+    double HB[36];
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c) {
+        double t = lambda * B[6 * r + c];
+        for (int k = 0; k < 6; ++k) t += H[6 * r + k] * B[6 * k + c];
+        HB[6 * r + c] = t;
+      }
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c) {
+        double t = 0.0;
+        for (int k = 0; k < 6; ++k) t += B[6 * k + r] * HB[6 * k + c];
+        D[6 * r + c] += t;
+      }
+    for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
+      const int code = G.pose_pp_idx[kk];
+      if (code & 1) continue;
+      const int e = code >> 1, j = G.pp[e].j;
+      if (j < i0 || j >= i1) continue;
+      const double* Bj = Cz.B1mat + 36 * (size_t)j;
+      const double* Ho = G.Hoff + 36 * (size_t)e;
+      for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) HB[6 * r + c] = 0.0;
+      for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) {
+          double t = 0.0;
+          for (int k = 0; k < 6; ++k) t += Ho[6 * r + k] * Bj[6 * k + c];
+          HB[6 * r + c] = t;
+        }
+      for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) {
+          double t = 0.0;
+          for (int k = 0; k < 6; ++k) t += B[6 * k + r] * HB[6 * k + c];
+          D[6 * r + c] += t;
+          D[6 * c + r] += t;
+        }
+    }
+  }
+  // landmark terms: entries of my poses are contiguous in P-order
+  const int q0 = G.pose_pl_rowptr[i0], q1 = min(G.pose_pl_rowptr[i1], q0 + 64);
+  for (int qa = q0; qa < q1; ++qa) {
+    const int l = G.plP_lm[qa];
+    bool leader = true;
+    for (int qb = q0; qb < qa; ++qb)
+      if (G.plP_lm[qb] == l) {
+        leader = false;
+        break;
+      }
+    if (!leader) continue;
+    double Gm[18];  // 6x3
+    for (int k = 0; k < 18; ++k) Gm[k] = 0.0;
+    int ip = i0;
+    for (int qb = qa; qb < q1; ++qb) {
+      if (G.plP_lm[qb] != l) continue;
+      while (qb >= G.pose_pl_rowptr[ip + 1]) ++ip;
+      // entries qa.. may belong to later poses; ip only moves forward because qb is increasing
+      const double* B = Cz.B1mat + 36 * (size_t)ip;
+      const double* Hp = G.HplP + 18 * (size_t)qb;  // 6x3
+      for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 3; ++c) {
+          double t = 0.0;
+          for (int k = 0; k < 6; ++k) t += B[6 * k + r] * Hp[3 * k + c];
+          Gm[3 * r + c] += t;
+        }
+    }
+    const double* Wu = G.HllInv + 6 * (size_t)l;
+    const double W[9] = {Wu[0], Wu[1], Wu[2], Wu[1], Wu[3], Wu[4], Wu[2], Wu[4], Wu[5]};
+    double GW[18];
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 3; ++c) GW[3 * r + c] = Gm[3 * r] * W[c] + Gm[3 * r + 1] * W[3 + c] + Gm[3 * r + 2] * W[6 + c];
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c) D[6 * r + c] -= GW[3 * r] * Gm[3 * c] + GW[3 * r + 1] * Gm[3 * c + 1] + GW[3 * r + 2] * Gm[3 * c + 2];
+  }
+  // the first entries belong to pose i0: make sure the pose walk above started right
+  if (!any || !inv_spd6(D))
+    for (int k = 0; k < 36; ++k) D[k] = 0.0;
+  for (int k = 0; k < 36; ++k) Cz.D1inv[36 * (size_t)a + k] = D[k];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Coarse prologue shared by both PCG kernels: CTA g assembles rows [6g, 6g+6) of A_c = P' S P in
 // shared memory (Arow[6][nc]) and the grid inverts A_c in place by block Gauss-Jordan (pivot
@@ -674,7 +800,29 @@ constexpr int PCGF_THREADS = 512;
 constexpr int PCGF_MAXPL = 448;   // pose-landmark entries cached per CTA (fast path)
 constexpr int PCGF_MAXPP = 160;   // pose-pose incidences cached per CTA (fast path)
 constexpr int PCGF_MAXOV = 64;    // landmark edges beyond the first 32 of a landmark, per CTA (fast path)
-constexpr int PCGF_BIG = 18 * PCGF_MAXPL + 36 * PCGF_MAXPP + 18 * PCGF_MAXOV + (PCGF_MAXPL + PCGF_MAXPP + 1) / 2;
+constexpr int PCGF_BIG = 18 * PCGF_MAXPL + 36 * PCGF_MAXPP + 18 * PCGF_MAXOV + (PCGF_MAXPL + PCGF_MAXPP + 2) / 2 + 80 * 36 + 16 * 36;
+
+// middle level applied to the residual of one warp's 5 poses: returns this lane's component of
+// P1 D1^-1 P1' r.  All 32 lanes must call (warp-uniform aggregate index `agg`).
+__device__ __forceinline__ double sub_level_apply(const CoarseDev& Cz, int i, int agg, int comp, bool act, double rcomp) {
+  const int lane = threadIdx.x & 31;
+  double b1[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) b1[k] = act ? Cz.B1mat[36 * (size_t)i + 6 * comp + k] : 0.0;
+  double r1[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) r1[k] = warp_sum(b1[k] * rcomp);
+  double z1 = 0.0;
+  if (lane < 6) {
+    const double* D = Cz.D1inv + 36 * (size_t)agg + 6 * lane;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) z1 += D[j] * r1[j];
+  }
+  double add = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) add += b1[k] * __shfl_sync(0xffffffffu, z1, k);
+  return add;
+}
 
 __global__ void __launch_bounds__(PCG_THREADS, 1)
     k_pcg(DevGraph G, CoarseDev Cz, BarSlot* slots, double lambda, double tol2, int maxit) {
@@ -705,6 +853,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   double* pnew = G.p1;
   int status = 0;
 
+  const bool use_sub = Cz.sub_enabled != 0;
   bool use_coarse = false;
   if (coarse) use_coarse = coarse_prologue<PCG_THREADS>(G, Cz, slots, epoch, lambda, Arow, panel_sh, red, part_sh, p0, p1);
 
@@ -747,6 +896,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       double rk = __shfl_sync(0xffffffffu, rcomp, base_lane + k);
       if (act) zc += G.Dinv[36 * (size_t)i + 6 * comp + k] * rk;
     }
+    if (use_sub) zc += sub_level_apply(Cz, i, pbase / 5, comp, act, rcomp);
     if (act) {
       if (use_coarse) {
         const double* B = Cz.Bmat + 36 * (size_t)i + 6 * comp;
@@ -894,6 +1044,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
         double rk = __shfl_sync(0xffffffffu, rcomp, base_lane + k);
         if (act) zc += G.Dinv[36 * (size_t)i + 6 * comp + k] * rk;
       }
+      if (use_sub) zc += sub_level_apply(Cz, i, pbase / 5, comp, act, rcomp);
       if (act) {
         if (use_coarse) {
           const double* B = Cz.Bmat + 36 * (size_t)i + 6 * comp;
@@ -924,6 +1075,20 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   }
 }
 
+#define SSB_SUB_APPLY_FAST(RCOMP, ZC)                                                              \
+  if (use_sub) {                                                                                   \
+    double _r1[6];                                                                                 \
+    _Pragma("unroll") for (int k = 0; k < 6; ++k) _r1[k] = warp_sum(act ? b1row[k] * (RCOMP) : 0.0); \
+    double _z1 = 0.0;                                                                              \
+    if (lane < 6) {                                                                                \
+      _Pragma("unroll") for (int j = 0; j < 6; ++j) _z1 += d1_sh[36 * warp + 6 * lane + j] * _r1[j]; \
+    }                                                                                              \
+    _Pragma("unroll") for (int k = 0; k < 6; ++k) {                                                 \
+      const double _zk = __shfl_sync(0xffffffffu, _z1, k);                                         \
+      if (act) (ZC) += b1row[k] * _zk;                                                             \
+    }                                                                                              \
+  }
+
 // ------------------------------------- on-chip resident variant --------------------------------
 __global__ void __launch_bounds__(PCGF_THREADS, 1)
     k_pcg_fast(DevGraph G, CoarseDev Cz, BarSlot* slots, double lambda, double tol2, int maxit) {
@@ -946,6 +1111,9 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   int* pl_lm = reinterpret_cast<int*>(ovH + 18 * PCGF_MAXOV);  // [PCGF_MAXPL]
   int* pp_other = pl_lm + PCGF_MAXPL;                  // [PCGF_MAXPP] neighbour pose, role in bit 31
   __shared__ int ovcnt[PCGF_THREADS / 32];
+  double* b1_sh = reinterpret_cast<double*>(pp_other + PCGF_MAXPP + (PCGF_MAXPP & 1));  // [80][36] middle-level prolongation rows
+  double* d1_sh = b1_sh + 80 * 36;                                               // [16][36] D1^-1 of my warps' aggregates
+  const bool use_sub = Cz.sub_enabled != 0;
   const bool coarse = Cz.enabled != 0;
 
   const int lane = threadIdx.x & 31;
@@ -1001,6 +1169,14 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     pp_other[k] = (role == 0 ? G.pp[e].j : G.pp[e].i) | (role << 31);
     for (int m = 0; m < 36; ++m) ppH[36 * k + m] = G.Hoff[36 * (size_t)e + m];
   }
+  if (use_sub) {
+    for (int k = threadIdx.x; k < 36 * (p1 - p0); k += PCGF_THREADS) b1_sh[k] = Cz.B1mat[36 * (size_t)p0 + k];
+    for (int k = threadIdx.x; k < 36 * (PCGF_THREADS / 32); k += PCGF_THREADS) {
+      const int agg = p0 / 5 + k / 36;
+      d1_sh[k] = (5 * agg < G.Np) ? Cz.D1inv[36 * (size_t)agg + (k % 36)] : 0.0;
+    }
+  }
+  const double* b1row = b1_sh + 36 * (warp * 5 + slot) + 6 * comp;
   const int mypl0 = act ? G.pose_pl_rowptr[i] - plbase : 0, mypl1 = act ? G.pose_pl_rowptr[i + 1] - plbase : 0;
   const int mypp0 = act ? G.pose_pp_rowptr[i] - ppbase : 0, mypp1 = act ? G.pose_pp_rowptr[i + 1] - ppbase : 0;
   // landmark role: lane e of the warp owns edge e of landmark l
@@ -1062,6 +1238,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     zc = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) zc += Drow[k] * __shfl_sync(0xffffffffu, rcomp, base_lane + k);
+    SSB_SUB_APPLY_FAST(rcomp, zc)
     if (use_coarse) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) zc += Brow[k] * zc6[k];
@@ -1253,6 +1430,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     zc = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) zc += Drow[k] * __shfl_sync(0xffffffffu, rcomp, base_lane + k);
+    SSB_SUB_APPLY_FAST(rcomp, zc)
     if (use_coarse) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) zc += Brow[k] * zc6[k];

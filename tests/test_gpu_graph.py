@@ -74,7 +74,7 @@ def test_chi2_matches_oracle():
 
 
 @pytest.mark.parametrize("generic", [False, True])
-@pytest.mark.parametrize("precond", [0, 1])
+@pytest.mark.parametrize("precond", [0, 1, 2])
 @pytest.mark.parametrize("lam", [10.0, 1e-2, 1e-6])
 def test_damped_solve_matches_sparse_cholesky(lam, precond, generic):
     spec = synth.make_config_graph("cfg1")
@@ -87,7 +87,7 @@ def test_damped_solve_matches_sparse_cholesky(lam, precond, generic):
 
 
 @pytest.mark.parametrize("generic", [False, True])
-@pytest.mark.parametrize("precond", [0, 1])
+@pytest.mark.parametrize("precond", [0, 1, 2])
 def test_lm_trajectory_cfg1(precond, generic):
     spec = synth.make_config_graph("cfg1")
     g, o, ids = _pair(spec, preconditioner=precond, force_generic=generic)
@@ -191,7 +191,7 @@ def test_coarse_level_reduces_pcg_iterations():
     """the rigid-body coarse level must give the same solution in far fewer PCG iterations (cfg5-size graph)"""
     spec = synth.make_graph(2000, 400, seed=77)
     xs, its = [], []
-    for precond, generic in ((0, False), (1, False), (1, True)):
+    for precond, generic in ((0, False), (1, False), (1, True), (2, False), (2, True)):
         g = GraphSLAM(pcg_tol=1e-12, preconditioner=precond, force_generic=generic)
         synth.load_graph(g, spec)
         n = 6 * (spec.n_poses - 1) + 3 * spec.n_landmarks
@@ -200,11 +200,15 @@ def test_coarse_level_reduces_pcg_iterations():
         its.append(k)
     assert np.abs(xs[0] - xs[1]).max() <= 1e-7 * max(1.0, np.abs(xs[0]).max())
     assert np.abs(xs[0] - xs[2]).max() <= 1e-7 * max(1.0, np.abs(xs[0]).max())
+    assert np.abs(xs[0] - xs[3]).max() <= 1e-7 * max(1.0, np.abs(xs[0]).max())
+    assert np.abs(xs[0] - xs[4]).max() <= 1e-7 * max(1.0, np.abs(xs[0]).max())
     assert its[1] * 2 < its[0], its
     assert abs(its[1] - its[2]) <= 2, its       # resident and streaming kernels run the same algorithm
+    assert abs(its[3] - its[4]) <= 2, its
+    assert its[3] < its[1], its                 # the middle level must pay for itself
 
 
-@pytest.mark.parametrize("precond", [0, 1])
+@pytest.mark.parametrize("precond", [0, 2])
 def test_cfg2_full_size_properties(precond):
     """BASELINE.json configs[1] (10k KF / 2k landmarks / 60k edges): size-independent properties —
     chi2 is monotone over accepted iterations, repeatable bit-for-bit, and matches the committed

@@ -242,6 +242,12 @@ def main():
     final_chi2 = g.stats["chi2_final"]
 
     # ---------------- end-to-end leg (host buffers through the C-ABI) -----------------------------
+    # inputs live in page-locked host memory (as a driver handing frames to the backend would keep them)
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy()
+    msg_h, boxes_h, triples_h = pin(cl.msg), pin(cl.boxes), pin(cl.triples)
+    P0, X0 = pin(P0), pin(X0)
     e2e_steps = max(2, min(steps, 5))
     t_e2e = 0.0
     t_e2e_r = 0.0
@@ -255,7 +261,7 @@ def main():
         P1, X1 = g.get_all(spec.n_poses, spec.n_landmarks)
         dt = time.perf_counter() - t0
         t0 = time.perf_counter()
-        res, counts, mask = seg.fit_planes(cl.msg, lay, cl.boxes, cl.triples)
+        res, counts, mask = seg.fit_planes(msg_h, lay, boxes_h, triples_h)
         dtr = time.perf_counter() - t0
         if s >= 1:
             t_e2e += dt

@@ -9,7 +9,7 @@ if which in ("all", "graph"):
     name = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     spec = synth.make_config_graph(name)
-    g = GraphSLAM(preconditioner=int(os.environ.get('PRECOND', '0')), pcg_tol=float(os.environ.get('PCGTOL', '1e-10')), force_generic=bool(int(os.environ.get('GENERIC', '0'))))
+    g = GraphSLAM(preconditioner=int(os.environ.get('PRECOND', '0')), pcg_tol=float(os.environ.get('PCGTOL', '1e-10')), force_generic=bool(int(os.environ.get('GENERIC', '0'))), coarse_refresh=int(os.environ.get('REFRESH', '1')))
     t = time.time(); synth.load_graph(g, spec); print("load", time.time() - t)
     g.snapshot()
     for rep in range(3):

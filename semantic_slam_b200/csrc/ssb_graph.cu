@@ -167,7 +167,9 @@ struct ssb_graph {
   DBuf<double> d_x, d_r, d_z, d_p0, d_p1, d_q, d_v, d_dl, d_part, d_scalars, d_tmp;
   DBuf<int> d_iscalars;
   // coarse level
-  DBuf<double> d_Bmat, d_Grun, d_panel, d_B1mat, d_D1inv;
+  DBuf<double> d_Bmat, d_Grun, d_panel, d_B1mat, d_D1inv, d_ainv;
+  bool ainv_valid = false;   // d_ainv holds the rows of a previously inverted coarse matrix
+  int solves_since_refresh = 0;
   DBuf<int> d_run_lm, d_run_group, d_run_e0, d_lm_run_rowptr, d_grp_run_rowptr, d_grp_runs;
   DBuf<BarSlot> d_slots;
   CoarseDev Cz;
@@ -589,6 +591,8 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_grp_run_rowptr.ensure(nblk + 1));
     SSB_TRY(g->d_grp_runs.ensure(n_runs));
     SSB_TRY(g->d_slots.ensure((size_t)2 * nblk + 1));
+    SSB_TRY(g->d_ainv.ensure((size_t)nblk * 6 * ncoarse));
+    g->ainv_valid = false;
     cudaStream_t s = g->stream;
     if (n_runs) {
       SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_run_lm.p, run_lm.data(), n_runs * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -616,6 +620,8 @@ static int prepare(ssb_graph* g) {
       Cz.grp_runs = g->d_grp_runs.p;
       Cz.n_runs = n_runs;
       Cz.panel = g->d_panel.p;
+      Cz.reuse_inverse = 0;
+      Cz.ainv_store = g->d_ainv.p;
     }
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_scalars.p, 0, 32 * sizeof(double), s));
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_iscalars.p, 0, 4 * sizeof(int), s));
@@ -754,6 +760,17 @@ static int launch_pcg(ssb_graph* g, double lambda) {
   cudaStream_t s = g->stream;
   double tol2 = g->opts.pcg_tol * g->opts.pcg_tol;
   int maxit = g->opts.max_pcg_iters;
+  // coarse inverse refresh policy: opts.reserved[1] = n > 0 re-inverts A_c only every n-th solve and
+  // reuses the stored (stale but SPD) inverse in between — the PCG solution is unaffected, only its
+  // iteration count can change.  Default 1 = always fresh.
+  {
+    const int every = std::max(1, g->opts.reserved[1]);
+    const bool reuse = g->Cz.enabled && g->ainv_valid && every > 1 && (g->solves_since_refresh % every) != 0;
+    g->Cz.reuse_inverse = reuse ? 1 : 0;
+    if (!reuse) g->solves_since_refresh = 0;
+    g->solves_since_refresh++;
+    if (g->Cz.enabled) g->ainv_valid = true;
+  }
   BarSlot* slots = g->d_slots.p;
   SSB_CUDA_CHECK(cudaMemsetAsync(slots, 0, ((size_t)2 * g->pcg_grid + 1) * sizeof(BarSlot), s));
   void* args[] = {(void*)&G, (void*)&g->Cz, (void*)&slots, (void*)&lambda, (void*)&tol2, (void*)&maxit};

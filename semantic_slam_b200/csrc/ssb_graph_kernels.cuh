@@ -281,6 +281,8 @@ struct CoarseDev {
   double* panel;           // [2][6*nc + 8] Gauss-Jordan pivot panels (double buffered)
   // middle level: aggregates of 5 consecutive poses (= the 5 poses one warp owns)
   int sub_enabled;
+  int reuse_inverse;       // 1: skip assembly + Gauss-Jordan, reload the rows of A_c^-1 stored by an earlier solve
+  double* ainv_store;      // [gridDim.x][6*nc] rows of A_c^-1 kept between solves
   double* B1mat;           // [Np][36] prolongation blocks about the 5-pose centroid
   double* D1inv;           // [ceil(Np/5)][36] inverse of P1' S P1 diagonal blocks (zero = level off for the aggregate)
 };
@@ -855,7 +857,17 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
 
   const bool use_sub = Cz.sub_enabled != 0;
   bool use_coarse = false;
-  if (coarse) use_coarse = coarse_prologue<PCG_THREADS>(G, Cz, slots, epoch, lambda, Arow, panel_sh, red, part_sh, p0, p1);
+  if (coarse) {
+    if (Cz.reuse_inverse) {
+      for (int k = threadIdx.x; k < 6 * nc; k += PCG_THREADS) Arow[k] = Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k];
+      use_coarse = true;
+      __syncthreads();
+    } else {
+      use_coarse = coarse_prologue<PCG_THREADS>(G, Cz, slots, epoch, lambda, Arow, panel_sh, red, part_sh, p0, p1);
+      if (use_coarse)
+        for (int k = threadIdx.x; k < 6 * nc; k += PCG_THREADS) Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k] = Arow[k];
+    }
+  }
 
   // ---- init: x = 0, r = g, z = M^-1 r
   double local = 0.0;
@@ -1145,7 +1157,17 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   } while (0)
 #endif
   bool use_coarse = false;
-  if (coarse) use_coarse = coarse_prologue<PCGF_THREADS>(G, Cz, slots, epoch, lambda, Arow, panel_sh, red, part_sh, p0, p1);
+  if (coarse) {
+    if (Cz.reuse_inverse) {
+      for (int k = threadIdx.x; k < 6 * nc; k += PCGF_THREADS) Arow[k] = Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k];
+      use_coarse = true;
+      __syncthreads();
+    } else {
+      use_coarse = coarse_prologue<PCGF_THREADS>(G, Cz, slots, epoch, lambda, Arow, panel_sh, red, part_sh, p0, p1);
+      if (use_coarse)
+        for (int k = threadIdx.x; k < 6 * nc; k += PCGF_THREADS) Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k] = Arow[k];
+    }
+  }
 
   SSB_TICK(1);
   // ---- load the resident operands ------------------------------------------------------------

@@ -12,6 +12,7 @@
 // against the CPU oracle.
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -123,8 +124,10 @@ __global__ void __launch_bounds__(256) k_hyp(const float4* __restrict__ crop, co
 }
 
 // ---- K7b: the point x hypothesis sweep --------------------------------------------------------
-constexpr int CNT_THREADS = 256;
-constexpr int CNT_HPT = 4;                       // hypotheses per thread
+// Packed fp32x2 arithmetic (Blackwell FMUL2 / FADD2): one instruction evaluates two hypotheses against
+// the broadcast point with the same per-lane IEEE roundings as the scalar form, so counts stay bit-exact.
+constexpr int CNT_THREADS = 128;
+constexpr int CNT_HPT = 8;                       // hypotheses per thread (4 packed pairs)
 constexpr int CNT_HYP_PER_BLOCK = CNT_THREADS * CNT_HPT;
 constexpr int CNT_TILE = 512;                    // points per tile (8 KB of float4)
 
@@ -133,7 +136,30 @@ struct TileRef {
   int first;  // first point of the tile inside the crop
 };
 
-__global__ void __launch_bounds__(CNT_THREADS, 4)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// NOTE: ptxas 12.9 contracts `mul.rn.f32x2` + `add.rn.f32x2` into FFMA2 (unlike the scalar .rn forms),
+// which changes the rounding and breaks integer-exact counts.  The `.ftz` qualifier on the multiply only
+// makes the pair non-contractable (verified in SASS: FMUL2.FTZ + FADD2).  Flushing a subnormal *product*
+// cannot change |n.p + d| < thr: a term below 1.2e-38 never moves a sum that is compared with ~1e-2.
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+__global__ void __launch_bounds__(CNT_THREADS, 8)
     k_count(const float4* __restrict__ crop, const BoxInfo* __restrict__ boxes, const TileRef* __restrict__ tiles,
             const float4* __restrict__ hyp, int K, float thr, int* __restrict__ counts) {
   __shared__ __align__(128) float4 pts[CNT_TILE];
@@ -151,27 +177,38 @@ __global__ void __launch_bounds__(CNT_THREADS, 4)
     mbar_expect_tx(&bar, (uint32_t)n * 16u);
     tma_load_1d(pts, crop + (size_t)B.pt_off + T.first, (uint32_t)n * 16u, &bar);
   }
-  // hypotheses of this thread (block-column blockIdx.y covers CNT_HYP_PER_BLOCK hypotheses)
-  float ha[CNT_HPT], hb[CNT_HPT], hc[CNT_HPT], hd[CNT_HPT];
+  // hypotheses of this thread, packed in pairs (block-column blockIdx.y covers CNT_HYP_PER_BLOCK hypotheses)
+  uint64_t ha[CNT_HPT / 2], hb[CNT_HPT / 2], hc[CNT_HPT / 2], hd[CNT_HPT / 2];
   int cnt[CNT_HPT];
   const int hbase = blockIdx.y * CNT_HYP_PER_BLOCK;
+  const float qnan = __int_as_float(0x7fc00000);
 #pragma unroll
-  for (int j = 0; j < CNT_HPT; ++j) {
-    const int k = hbase + j * CNT_THREADS + tid;
-    float4 h = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
-    if (k < K) h = hyp[(size_t)T.box * K + k];
-    ha[j] = h.x;
-    hb[j] = h.y;
-    hc[j] = h.z;
-    hd[j] = h.w;
-    cnt[j] = 0;
+  for (int j = 0; j < CNT_HPT / 2; ++j) {
+    const int k0 = hbase + (2 * j) * CNT_THREADS + tid, k1 = hbase + (2 * j + 1) * CNT_THREADS + tid;
+    float4 h0 = make_float4(qnan, 0.f, 0.f, 0.f), h1 = h0;
+    if (k0 < K) h0 = hyp[(size_t)T.box * K + k0];
+    if (k1 < K) h1 = hyp[(size_t)T.box * K + k1];
+    ha[j] = pack2(h0.x, h1.x);
+    hb[j] = pack2(h0.y, h1.y);
+    hc[j] = pack2(h0.z, h1.z);
+    hd[j] = pack2(h0.w, h1.w);
+    cnt[2 * j] = 0;
+    cnt[2 * j + 1] = 0;
   }
   mbar_wait(&bar, 0);
-#pragma unroll 4
+#pragma unroll 2
   for (int i = 0; i < n; ++i) {
     const float4 P = pts[i];  // warp-wide broadcast
+    const uint64_t x2 = pack2(P.x, P.x), y2 = pack2(P.y, P.y), z2 = pack2(P.z, P.z);
 #pragma unroll
-    for (int j = 0; j < CNT_HPT; ++j) cnt[j] += (plane_dist(ha[j], hb[j], hc[j], hd[j], P.x, P.y, P.z) < thr) ? 1 : 0;
+    for (int j = 0; j < CNT_HPT / 2; ++j) {
+      // ((a*x + b*y) + (c*z + d)) per lane, separate roundings
+      const uint64_t s = add2(add2(mul2(ha[j], x2), mul2(hb[j], y2)), add2(mul2(hc[j], z2), hd[j]));
+      float s0, s1;
+      unpack2(s, s0, s1);
+      cnt[2 * j] += (fabsf(s0) < thr) ? 1 : 0;
+      cnt[2 * j + 1] += (fabsf(s1) < thr) ? 1 : 0;
+    }
   }
 #pragma unroll
   for (int j = 0; j < CNT_HPT; ++j) {

@@ -18,7 +18,8 @@ def _d(a):
 
 class GraphSLAM:
     def __init__(self, verbose: bool = False, device: int = -1, pcg_tol: float = 1e-8, max_pcg_iters: int = 20000,
-                 preconditioner: int = 0, coarse_group: int = 32, force_generic: bool = False):
+                 preconditioner: int = 0, coarse_group: int = 32, force_generic: bool = False,
+                 coarse_refresh: int = 1):
         self._L = _lib.lib()
         o = _lib.GraphOpts()
         self._L.ssb_graph_default_opts(C.byref(o))
@@ -28,6 +29,7 @@ class GraphSLAM:
         o.max_pcg_iters = max_pcg_iters
         o.preconditioner = preconditioner
         o.coarse_group = coarse_group
+        o.reserved[1] = int(coarse_refresh)  # re-invert the coarse matrix only every n-th damped solve
         o.reserved[0] = int(force_generic)   # 1 = always use the streaming PCG kernel (no on-chip residency)
         h = self._L.ssb_graph_create(C.byref(o))
         if not h:

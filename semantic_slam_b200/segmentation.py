@@ -45,6 +45,8 @@ class PlaneSegmentation:
         self.opts.max_iterations = max_iterations
         self.opts.probability = probability
         self._shape = None
+        self._pinned = None
+        self._pin_cache = {}
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -66,14 +68,33 @@ class PlaneSegmentation:
                   "ssb_crop_bbox")
         return out
 
+    def _zeros(self, shape, dtype):
+        """result buffers: page-locked when torch is importable (D2H at PCIe speed), else plain numpy"""
+        if self._pinned is None:
+            try:
+                import torch
+                self._pinned = torch.cuda.is_available()
+            except Exception:
+                self._pinned = False
+        if self._pinned:
+            import torch
+            n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            key = (tuple(np.atleast_1d(shape)), np.dtype(dtype).str)
+            buf = self._pin_cache.get(key)
+            if buf is None:
+                buf = torch.zeros(max(n, 1), dtype=torch.uint8).pin_memory()
+                self._pin_cache[key] = buf
+            return buf.numpy()[:n].view(dtype).reshape(shape)
+        return np.zeros(shape, dtype=dtype)
+
     def _alloc(self, boxes, K, layout, want_counts, want_mask):
         nb = boxes.shape[0]
-        res = np.zeros(nb, dtype=PLANE_RESULT_DTYPE)
-        counts = np.zeros((nb, K), dtype=np.int32) if want_counts else None
+        res = self._zeros(nb, PLANE_RESULT_DTYPE)
+        counts = self._zeros((nb, K), np.int32) if want_counts else None
         valid = (boxes[:, 2] >= 0) & (boxes[:, 3] >= 0) & (boxes[:, 0] >= 0) & (boxes[:, 1] >= 0) & \
                 (boxes[:, 0] + boxes[:, 2] <= layout.width) & (boxes[:, 1] + boxes[:, 3] <= layout.height)
         total = int((boxes[valid, 2].astype(np.int64) * boxes[valid, 3]).sum())
-        mask = np.zeros(max(total, 1), dtype=np.uint8) if want_mask else None
+        mask = self._zeros(max(total, 1), np.uint8) if want_mask else None
         return res, counts, mask, total
 
     def fit_planes(self, msg, layout: CloudLayout, boxes, triples, want_counts=True, want_mask=True):

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <limits>
@@ -185,6 +186,9 @@ struct ssb_graph {
   ssb_ncclComm_t comm = nullptr;
   DBuf<double> d_mg;
   double* h_mg = nullptr;  // pinned, 16 doubles
+  cudaGraphExec_t mg_graph = nullptr;  // two captured PCG iterations (4 kernels + 4 NCCL collectives each)
+  bool mg_graph_failed = true;   // CUDA-graph replay of the NCCL iteration measured 2x SLOWER than plain stream
+                                 // launches on 2 GPUs (NCCL 2.28 in-graph collectives); opt in with SSB_MG_GRAPH=1
 };
 
 static int check_vertex(const ssb_graph* g, int id, int kind) {
@@ -274,7 +278,8 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
   g->pcg_smem = (size_t)(PCG_THREADS + 14 * 6 * g->pcg_grid + (PCG_THREADS / 36) * 36) * sizeof(double);
   g->pcgf_smem = (size_t)(PCGF_THREADS + 8 * 6 * g->pcg_grid + (PCGF_THREADS / 36) * 36 +
                           std::max(PCGF_BIG, 6 * 6 * g->pcg_grid)) * sizeof(double);
-  g->allow_fast = g->opts.reserved[0] == 0;   // reserved[0] = 1 forces the generic (streaming) kernel
+  g->allow_fast = g->opts.reserved[0] == 0;
+  if (const char* e = std::getenv("SSB_MG_GRAPH")) g->mg_graph_failed = !(e[0] == '1');   // reserved[0] = 1 forces the generic (streaming) kernel
   int nb = 0;
   e = cudaFuncSetAttribute(k_pcg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_smem);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg, PCG_THREADS, g->pcg_smem);
@@ -303,6 +308,7 @@ void ssb_graph_destroy(ssb_graph* g) {
   if (g->h_scalars) cudaFreeHost(g->h_scalars);
   if (g->h_iscalars) cudaFreeHost(g->h_iscalars);
   if (g->h_mg) cudaFreeHost(g->h_mg);
+  if (g->mg_graph) cudaGraphExecDestroy(g->mg_graph);
   if (g->comm && nccl_api().ok) nccl_api().CommDestroy(g->comm);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
@@ -636,6 +642,10 @@ static int prepare(ssb_graph* g) {
     if (Epp) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pp_idx.p, ppp_idx.data(), (size_t)2 * Epp * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaStreamSynchronize(s));  // host vectors above go out of scope
     g->structure_dirty = false;
+    if (g->mg_graph) {
+      cudaGraphExecDestroy(g->mg_graph);
+      g->mg_graph = nullptr;
+    }
     g->host_est_dirty = true;
     g->have_system = false;
     g->have_snapshot = false;
@@ -828,25 +838,53 @@ static int launch_solve_mg(ssb_graph* g, double lambda) {
   const int gridp = std::max(1, std::min(4 * g->num_sms, (((own_p + 4) / 5) + 7) / 8));
   const int gridl = std::max(1, std::min(4 * g->num_sms, (own_l + 7) / 8));
   SSB_CUDA_CHECK(cudaMemsetAsync(mg, 0, 16 * sizeof(double), s));
+  g->h_mg[8] = lambda;
+  g->h_mg[9] = tol2;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(mg + 8, g->h_mg + 8, 2 * sizeof(double), cudaMemcpyHostToDevice, s));
   k_mg_init<<<gridp, 256, 0, s>>>(G, R, mg, p);
   SSB_NCCL_CHECK(N.AllReduce(mg, mg, 1, kNcclFloat64, kNcclSum, g->comm, s));
   k_mg_after_init<<<1, 1, 0, s>>>(mg);
   SSB_NCCL_CHECK(N.AllGather(p + (size_t)6 * rank * cp, p, (size_t)6 * cp, kNcclFloat64, g->comm, s));
   g->launches += 2;
   const int maxit = g->opts.max_pcg_iters;
-  for (int it = 0; it < maxit; ++it) {
-    const int par = it & 1;
+  auto enqueue_iteration = [&](int par) -> int {
     k_mg_p1<<<gridl, 256, 0, s>>>(G, R, mg, p);
     if (G.Nl) SSB_NCCL_CHECK(N.AllGather(G.v + (size_t)3 * rank * cl, G.v, (size_t)3 * cl, kNcclFloat64, g->comm, s));
-    k_mg_p2<<<gridp, 256, 0, s>>>(G, R, lambda, mg, p);
+    k_mg_p2<<<gridp, 256, 0, s>>>(G, R, mg, p);
     SSB_NCCL_CHECK(N.AllReduce(mg + 2, mg + 2, 1, kNcclFloat64, kNcclSum, g->comm, s));
     k_mg_p3<<<gridp, 256, 0, s>>>(G, R, mg, p, par);
     SSB_NCCL_CHECK(N.AllReduce(mg + (par ^ 1), mg + (par ^ 1), 1, kNcclFloat64, kNcclSum, g->comm, s));
-    k_mg_p4<<<gridp, 256, 0, s>>>(G, R, mg, p, par, tol2);
+    k_mg_p4<<<gridp, 256, 0, s>>>(G, R, mg, p, par);
     SSB_NCCL_CHECK(N.AllGather(p + (size_t)6 * rank * cp, p, (size_t)6 * cp, kNcclFloat64, g->comm, s));
-    g->launches += 4;
-    if ((it & 15) == 15 || it == maxit - 1) {
-      SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_mg, mg, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    return SSB_OK;
+  };
+  // two iterations (both parities) are captured once into a CUDA graph and replayed: the iteration is
+  // launch-latency bound (8 tiny operations), so removing the per-operation host cost matters
+  if (!g->mg_graph && !g->mg_graph_failed) {
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const int r0 = enqueue_iteration(0), r1 = enqueue_iteration(1);
+      ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && r0 == SSB_OK && r1 == SSB_OK && graph;
+    }
+    if (ok) ok = cudaGraphInstantiate(&g->mg_graph, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      g->mg_graph = nullptr;
+      g->mg_graph_failed = true;  // fall back to plain stream launches
+    }
+  }
+  for (int it = 0; it < maxit; it += 2) {
+    if (g->mg_graph) {
+      SSB_CUDA_CHECK(cudaGraphLaunch(g->mg_graph, s));
+    } else {
+      SSB_TRY(enqueue_iteration(0));
+      SSB_TRY(enqueue_iteration(1));
+    }
+    g->launches += 8;
+    if ((it & 15) == 14 || it + 2 >= maxit) {
+      SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_mg, mg, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
       SSB_CUDA_CHECK(cudaStreamSynchronize(s));
       if (g->h_mg[4] != 0.0) break;
     }

@@ -1494,7 +1494,8 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
 // NCCL all-gathers, the two dot products with NCCL all-reduces (host side: ssb_graph.cu).  Everything
 // else in the LM iteration (linearisation, update, chi2) is computed redundantly and deterministically
 // on every rank, so all ranks hold bit-identical estimates.  Block-Jacobi preconditioner.
-// mg scalars: [0],[1] rz ping-pong  [2] pq  [3] rz0  [4] done  [5] iterations  [6] status  [8..] scratch
+// mg scalars: [0],[1] rz ping-pong  [2] pq  [3] rz0  [4] done  [5] iterations  [6] status  [7] breakdown
+//             [8] lambda  [9] tol^2
 // ---------------------------------------------------------------------------------------------
 struct MgRange {
   int ps, pe, ls, le;
@@ -1542,6 +1543,7 @@ __global__ void __launch_bounds__(256) k_mg_init(DevGraph G, MgRange R, double* 
       mg[4] = 0.0;
       mg[5] = 0.0;
       mg[6] = 0.0;
+      mg[7] = 0.0;
       G.iscalars[3] = 0;
     }
   }
@@ -1584,10 +1586,11 @@ __global__ void __launch_bounds__(256) k_mg_p1(DevGraph G, MgRange R, const doub
   }
 }
 
-__global__ void __launch_bounds__(256) k_mg_p2(DevGraph G, MgRange R, double lambda, double* mg, const double* p) {
+__global__ void __launch_bounds__(256) k_mg_p2(DevGraph G, MgRange R, double* mg, const double* p) {
   __shared__ double sh[33];
   __shared__ int is_last;
   if (mg[4] != 0.0) return;
+  const double lambda = mg[8];  // set by the host before the solve (keeps the captured graph reusable)
   const int lane = threadIdx.x & 31;
   const int slot = lane / 6, comp = lane - 6 * slot, base_lane = 6 * slot;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
@@ -1693,8 +1696,9 @@ __global__ void __launch_bounds__(256) k_mg_p3(DevGraph G, MgRange R, double* mg
 }
 
 // beta = rz_new / rz_old ; p = z + beta p (owned rows) ; convergence / breakdown flags
-__global__ void __launch_bounds__(256) k_mg_p4(DevGraph G, MgRange R, double* mg, double* p, int par, double tol2) {
+__global__ void __launch_bounds__(256) k_mg_p4(DevGraph G, MgRange R, double* mg, double* p, int par) {
   if (mg[4] != 0.0) return;
+  const double tol2 = mg[9];
   const double rzo = mg[par], rzn = mg[par ^ 1];
   const bool bad = mg[7] != 0.0;
   const double beta = rzn / rzo;

@@ -169,7 +169,7 @@ class GraphSLAM {
     ssb_graph_opts o;
     ssb_graph_default_opts(&o);
     o.verbose = verbose ? 1 : 0;
-    o.preconditioner = 1;
+    o.preconditioner = 2;
     graph = ssb_graph_create(&o);
     if (!graph) {
       std::cerr << std::endl << "error : failed to allocate solver!! " << ssb_last_error() << std::endl;

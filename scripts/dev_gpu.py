@@ -24,7 +24,7 @@ if which in ("all", "graph"):
     if hasattr(g._L, "ssb_graph_debug_timers"):
         g._L.ssb_graph_debug_timers.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         g._L.ssb_graph_debug_timers(g._h, tm.ctypes.data_as(C.POINTER(C.c_double)))
-        names = ["p2:pl-loop", "gauss-jordan", "init", "phase1", "barriers", "p2:reduce", "phase3", "p2:diag+pp"]
+        names = ["A:landmark", "B:pose", "C1:blockreduce", "C2:gatherpoll(t0)", "C2:sync", "C3:fold+dots", "D:update", "-"] if os.environ.get("FLOW", "1") == "1" else ["p2:pl-loop", "gauss-jordan", "init", "phase1", "barriers", "p2:reduce", "phase3", "p2:diag+pp"]
         print("k_pcg cycles (block 0, all launches since prepare), ms @1.9GHz:", {n: round(v / 1.9e6, 2) for n, v in zip(names, tm)})
     print("us per pcg iter (upper bound):", g.stats['ms_device'] * 1e3 / max(1, g.stats['total_pcg_iters']))
 if which in ("all", "ransac"):

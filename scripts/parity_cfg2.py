@@ -7,7 +7,7 @@ gold = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", 
 hist = np.array(json.load(open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "cfg2_oracle_history.json")))["history"])
 spec = synth.make_config_graph("cfg2")
 for tol in [float(x) for x in (sys.argv[1:] or ["1e-10", "1e-8", "1e-7", "1e-6"])]:
-    g = GraphSLAM(preconditioner=1, pcg_tol=tol)
+    g = GraphSLAM(preconditioner=int(os.environ.get("PRECOND", "2")), pcg_tol=tol, coarse_refresh=int(os.environ.get("REFRESH", "1")))
     synth.load_graph(g, spec)
     g.snapshot()
     g.optimize_resident(20); g.restore(); g.optimize_resident(20)

@@ -20,6 +20,7 @@
 
 #include "../../include/ssb.h"
 #include "ssb_graph_kernels.cuh"
+#include "ssb_pcg_flow.cuh"
 
 // ---- NCCL, resolved at run time (the library the process already loaded — torch's — else libnccl.so.2).
 // Minimal declarations of the stable C ABI; nothing links against libnccl at build time.
@@ -174,7 +175,12 @@ struct ssb_graph {
   DBuf<int> d_run_lm, d_run_group, d_run_e0, d_lm_run_rowptr, d_grp_run_rowptr, d_grp_runs;
   DBuf<BarSlot> d_slots;
   CoarseDev Cz;
-  size_t pcg_smem = 0, pcgf_smem = 0;
+  size_t pcg_smem = 0, pcgf_smem = 0, pcgw_smem = 0;
+  DBuf<int> d_ft_ulm_rowptr, d_ft_ulm, d_ft_pl_loc, d_ft_upp_rowptr, d_ft_upp, d_ft_pp_loc, d_ft_pp_src, d_ft_ext_rowptr, d_ft_ext;
+  FlowTabs FT;
+  DBuf<uint4> d_ucell, d_vcell, d_lines;   // tagged cells of the data-flow PCG kernel (ssb_pcg_flow.cuh)
+  unsigned flow_seq = 0;                   // launch counter -> tag base (seq << 16)
+  bool use_flow = true;                    // opts.reserved[2] = 1 selects the barrier-based k_pcg_fast instead
   bool fast_ok = false;   // the graph fits the on-chip resident PCG kernel
   bool allow_fast = true;
   double* h_scalars = nullptr;  // pinned: 8 doubles
@@ -279,12 +285,21 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
   g->pcgf_smem = (size_t)(PCGF_THREADS + 8 * 6 * g->pcg_grid + (PCGF_THREADS / 36) * 36 +
                           std::max(PCGF_BIG, 6 * 6 * g->pcg_grid)) * sizeof(double);
   g->allow_fast = g->opts.reserved[0] == 0;
+  g->use_flow = g->opts.reserved[2] == 0 && g->pcg_grid == 148;   // k_pcg_flow is instantiated for 148 CTAs (B200)
+  g->pcgw_smem = pcg_flow_smem_doubles(g->pcg_grid) * sizeof(double);
   if (const char* e = std::getenv("SSB_MG_GRAPH")) g->mg_graph_failed = !(e[0] == '1');   // reserved[0] = 1 forces the generic (streaming) kernel
   int nb = 0;
   e = cudaFuncSetAttribute(k_pcg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_smem);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg, PCG_THREADS, g->pcg_smem);
   if (e != cudaSuccess || nb < 1) {
     set_error("k_pcg cannot be made resident (occupancy %d, %zu B smem): %s", nb, g->pcg_smem, cudaGetErrorString(e));
+    delete g;
+    return nullptr;
+  }
+  e = cudaFuncSetAttribute(k_pcg_flow<148>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcgw_smem);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_flow<148>, PCGF_THREADS, g->pcgw_smem);
+  if (e != cudaSuccess || nb < 1) {
+    set_error("k_pcg_flow cannot be made resident (occupancy %d, %zu B smem): %s", nb, g->pcgw_smem, cudaGetErrorString(e));
     delete g;
     return nullptr;
   }
@@ -584,6 +599,74 @@ static int prepare(ssb_graph* g) {
         }
       }
       g->fast_ok = ok;
+      // gather tables of the data-flow kernel: per CTA the distinct landmarks / pose-pose edges / external
+      // neighbour poses its keyframe range touches, and per incidence the slot inside those lists
+      std::vector<int> ulm_rowptr(nblk + 1, 0), ulm, pl_loc(std::max(El, 1), 0), upp_rowptr(nblk + 1, 0), upp,
+          pp_loc(std::max(2 * Epp, 1), 0), pp_src(std::max(2 * Epp, 1), 0), ext_rowptr(nblk + 1, 0), ext;
+      if (ok) {
+        std::vector<int> lm_stamp(std::max(Nl, 1), -1), lm_slot(std::max(Nl, 1), 0), e_stamp(std::max(Epp, 1), -1),
+            e_slot(std::max(Epp, 1), 0);
+        for (int b = 0; b < nblk && ok; ++b) {
+          const int q0 = std::min(Np, b * Cc), q1 = std::min(Np, q0 + Cc);
+          const size_t u0 = ulm.size(), p0e = upp.size(), x0 = ext.size();
+          for (int kk = ppl_rowptr[q0]; kk < ppl_rowptr[q1]; ++kk) {
+            const int l = plL[ppl_idx[kk]].l;
+            if (lm_stamp[l] != b) {
+              lm_stamp[l] = b;
+              lm_slot[l] = (int)(ulm.size() - u0);
+              ulm.push_back(l);
+            }
+            pl_loc[kk] = lm_slot[l];
+          }
+          for (int i = q0; i < q1; ++i)
+            for (int kk = ppp_rowptr[i]; kk < ppp_rowptr[i + 1]; ++kk) {
+              const int code = ppp_idx[kk], e = code >> 1, role = code & 1;
+              if (e_stamp[e] != b) {
+                e_stamp[e] = b;
+                e_slot[e] = (int)(upp.size() - p0e);
+                upp.push_back(e);
+              }
+              pp_loc[kk] = e_slot[e];
+              const int o = role == 0 ? g->pp[e].j : g->pp[e].i;
+              int src;
+              if (o >= q0 && o < q1) {
+                src = o - q0;
+              } else {
+                size_t xi = x0;
+                while (xi < ext.size() && ext[xi] != o) ++xi;
+                if (xi == ext.size()) ext.push_back(o);
+                src = PCGW_POSES + (int)(xi - x0);
+              }
+              pp_src[kk] = src | (role ? (int)0x80000000u : 0);
+            }
+          ulm_rowptr[b + 1] = (int)ulm.size();
+          upp_rowptr[b + 1] = (int)upp.size();
+          ext_rowptr[b + 1] = (int)ext.size();
+          if ((int)(ulm.size() - u0) > PCGW_MAXU || (int)(upp.size() - p0e) > PCGW_MAXPPE || (int)(ext.size() - x0) > PCGW_MAXEXT)
+            ok = false;
+        }
+        g->fast_ok = ok;
+      }
+      if (ok) {
+        cudaStream_t s2 = g->stream;
+        auto up = [&](DBuf<int>& d, const std::vector<int>& h) -> int {
+          SSB_TRY(d.ensure(std::max<size_t>(h.size(), 1)));
+          if (!h.empty()) SSB_CUDA_CHECK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, s2));
+          return SSB_OK;
+        };
+        SSB_TRY(up(g->d_ft_ulm_rowptr, ulm_rowptr));
+        SSB_TRY(up(g->d_ft_ulm, ulm));
+        SSB_TRY(up(g->d_ft_pl_loc, pl_loc));
+        SSB_TRY(up(g->d_ft_upp_rowptr, upp_rowptr));
+        SSB_TRY(up(g->d_ft_upp, upp));
+        SSB_TRY(up(g->d_ft_pp_loc, pp_loc));
+        SSB_TRY(up(g->d_ft_pp_src, pp_src));
+        SSB_TRY(up(g->d_ft_ext_rowptr, ext_rowptr));
+        SSB_TRY(up(g->d_ft_ext, ext));
+        SSB_CUDA_CHECK(cudaStreamSynchronize(s2));
+        g->FT = FlowTabs{g->d_ft_ulm_rowptr.p, g->d_ft_ulm.p, g->d_ft_pl_loc.p, g->d_ft_upp_rowptr.p, g->d_ft_upp.p,
+                         g->d_ft_pp_loc.p, g->d_ft_pp_src.p, g->d_ft_ext_rowptr.p, g->d_ft_ext.p};
+      }
     }
     SSB_TRY(g->d_Bmat.ensure((size_t)36 * Np));
     SSB_TRY(g->d_B1mat.ensure((size_t)36 * Np));
@@ -598,6 +681,13 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_grp_runs.ensure(n_runs));
     SSB_TRY(g->d_slots.ensure((size_t)2 * nblk + 1));
     SSB_TRY(g->d_ainv.ensure((size_t)nblk * 6 * ncoarse));
+    SSB_TRY(g->d_ucell.ensure((size_t)6 * (Np + 64)));
+    SSB_TRY(g->d_vcell.ensure((size_t)3 * (Nl + 64)));
+    SSB_TRY(g->d_lines.ensure((size_t)2 * nblk * 8));
+    SSB_CUDA_CHECK(cudaMemsetAsync(g->d_ucell.p, 0, g->d_ucell.cap * sizeof(uint4), g->stream));
+    SSB_CUDA_CHECK(cudaMemsetAsync(g->d_vcell.p, 0, g->d_vcell.cap * sizeof(uint4), g->stream));
+    SSB_CUDA_CHECK(cudaMemsetAsync(g->d_lines.p, 0, g->d_lines.cap * sizeof(uint4), g->stream));
+    g->flow_seq = 0;
     g->ainv_valid = false;
     cudaStream_t s = g->stream;
     if (n_runs) {
@@ -792,7 +882,19 @@ static int launch_pcg(ssb_graph* g, double lambda) {
     }
   }
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used], s));
-  if (g->fast_ok)
+  if (g->fast_ok && g->use_flow) {
+    // tags = (seq << 16) + iteration: unique per launch, so the cell buffers are never cleared between solves
+    if (++g->flow_seq >= 0xFFFFu) {
+      SSB_CUDA_CHECK(cudaMemsetAsync(g->d_ucell.p, 0, g->d_ucell.cap * sizeof(uint4), s));
+      SSB_CUDA_CHECK(cudaMemsetAsync(g->d_vcell.p, 0, g->d_vcell.cap * sizeof(uint4), s));
+      SSB_CUDA_CHECK(cudaMemsetAsync(g->d_lines.p, 0, g->d_lines.cap * sizeof(uint4), s));
+      g->flow_seq = 1;
+    }
+    FlowBufs F{g->d_ucell.p, g->d_vcell.p, g->d_lines.p, g->flow_seq << 16};
+    int maxit_f = std::min(maxit, 60000);
+    void* fargs[] = {(void*)&G, (void*)&g->Cz, (void*)&slots, (void*)&F, (void*)&g->FT, (void*)&lambda, (void*)&tol2, (void*)&maxit_f};
+    SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg_flow<148>, dim3(g->pcg_grid), dim3(PCGF_THREADS), fargs, g->pcgw_smem, s));
+  } else if (g->fast_ok)
     SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg_fast, dim3(g->pcg_grid), dim3(PCGF_THREADS), args, g->pcgf_smem, s));
   else
     SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(g->pcg_grid), dim3(PCG_THREADS), args, g->pcg_smem, s));

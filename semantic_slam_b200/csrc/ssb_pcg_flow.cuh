@@ -1,0 +1,595 @@
+// ssb_pcg_flow.cuh — K3, data-flow variant of the on-chip resident Schur-complement PCG (sm_100a).
+//
+// Same mapping and operands as k_pcg_fast (one persistent CTA per SM owning a contiguous keyframe
+// range; 6 lanes per pose, 5 poses per warp; one warp per landmark), but the iteration is restructured
+// so that it needs ONE global reduction and NO grid-wide barrier:
+//
+//  * Chronopoulos-Gear recurrences (single-reduction preconditioned CG):
+//        w = S u,  gamma = r'u,  delta = w'u   (one fused all-reduce, + the 6 restricted values P'w per CTA)
+//        beta = gamma/gamma_old,  alpha = gamma / (delta - beta*gamma/alpha_old)
+//        p = u + beta p,  s = w + beta s,  x += alpha p,  r -= alpha s,  u = M^-1 r
+//    identical iterates to standard PCG in exact arithmetic.
+//  * Vectors that cross CTAs (u, and the landmark-space product v) travel as self-validating 16-byte
+//    cells {lo32, tag, hi32, tag} (each 8-byte half is written atomically, NCCL "LL" style): a consumer
+//    spins on exactly the cells it needs, so the u -> v -> w hand-offs cost one L2 hop each instead of a
+//    fence + counter barrier + re-read, and a CTA only ever waits for its own producers.
+//  * The all-reduce is a pull all-gather of one 128-byte line (8 cells) per CTA, folded by every CTA in
+//    the same fixed order => bit-reproducible for a fixed grid.  It is also the only write-after-read
+//    fence the cells need (a producer overwrites u / v only after it has seen every CTA's line of the
+//    iteration in which the old values were read).
+//  * The coarse level needs no restricted-residual vector: z_c = A_c^-1 P'r is carried by the recurrences
+//    t = A_c^-1 P'w (6 rows per CTA, dot with the gathered P'w),  y = t + beta y,  z_c -= alpha y.
+//
+// Tags are tagbase + iteration; tagbase is unique per launch (host counter << 16), so no buffer has to be
+// cleared between solves.
+#pragma once
+#include "ssb_graph_kernels.cuh"
+
+namespace ssb {
+
+struct FlowBufs {
+  uint4* ucell;   // [6 * Np]  u = M^-1 r
+  uint4* vcell;   // [3 * Nl]  v = W Hlp u
+  uint4* lines;   // [2][gridDim.x][8] per-CTA reduction lines, double buffered on the tag parity
+  unsigned tagbase;
+};
+
+__device__ __forceinline__ void st_cell(uint4* c, double v, unsigned tag) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(c), "r"(lo), "r"(tag), "r"(hi), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_cell(const uint4* c) {
+  uint4 u;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(c));
+  return u;
+}
+__device__ __forceinline__ bool cell_ok(const uint4& u, unsigned tag) { return u.y == tag && u.w == tag; }
+__device__ __forceinline__ double cell_val(const uint4& u) { return __hiloint2double((int)u.z, (int)u.x); }
+
+// Packed butterfly reductions: N values per lane are reduced across the warp with N-1 + (5 - log2 N)
+// exchanges instead of 5 N.  The sum of value j ends up in the lanes whose upper bits spell j.
+// Fixed exchange pattern => deterministic.
+// 8 values: result for value j in lanes 4j .. 4j+3
+__device__ __forceinline__ double warp_reduce8(const double* v) {
+  const int lane = threadIdx.x & 31;
+  double a[4], b[2], c;
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double send = up ? v[k] : v[k + 4];
+      const double keep = up ? v[k + 4] : v[k];
+      a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double send = up ? a[k] : a[k + 2];
+      const double keep = up ? a[k + 2] : a[k];
+      b[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+    const double send = up ? b[0] : b[1];
+    const double keep = up ? b[1] : b[0];
+    c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;
+}
+// 4 values: result for value j in lanes 8j .. 8j+7
+__device__ __forceinline__ double warp_reduce4(const double* v) {
+  const int lane = threadIdx.x & 31;
+  double a[2], b;
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double send = up ? v[k] : v[k + 2];
+      const double keep = up ? v[k + 2] : v[k];
+      a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+    const double send = up ? a[0] : a[1];
+    const double keep = up ? a[1] : a[0];
+    b = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  b += __shfl_xor_sync(0xffffffffu, b, 4);
+  b += __shfl_xor_sync(0xffffffffu, b, 2);
+  b += __shfl_xor_sync(0xffffffffu, b, 1);
+  return b;
+}
+
+// per-CTA gather tables built once per structure change on the host (ssb_graph.cu: prepare)
+struct FlowTabs {
+  const int* ulm_rowptr;  // [nblk+1] distinct landmarks referenced by the CTA's poses
+  const int* ulm;         //          their ids
+  const int* pl_loc;      // [El]     P-order entry -> index into the CTA's distinct-landmark list
+  const int* upp_rowptr;  // [nblk+1] distinct pose-pose edges incident to the CTA's poses
+  const int* upp;         //          their ids
+  const int* pp_loc;      // [2 Epp]  incidence -> index into the CTA's distinct-edge list
+  const int* pp_src;      // [2 Epp]  incidence -> slot of the neighbour's u in shared memory | role << 31
+  const int* ext_rowptr;  // [nblk+1] neighbour poses owned by other CTAs
+  const int* ext;
+};
+
+constexpr int PCGW_MAXU = 320;    // distinct landmarks per CTA
+constexpr int PCGW_MAXPPE = 96;   // distinct pose-pose edges per CTA
+constexpr int PCGW_MAXEXT = 16;   // external neighbour poses per CTA
+constexpr int PCGW_POSES = 5 * (PCGF_THREADS / 32);
+constexpr int PCGW_INTS = PCGF_MAXPL + PCGW_MAXU + 2 * PCGF_MAXPP + PCGW_MAXEXT + PCGF_MAXOV;
+constexpr int PCGW_BIG = 18 * PCGF_MAXPL + 36 * PCGW_MAXPPE + 18 * PCGF_MAXOV + 2 * PCGW_POSES * 36 + 3 * PCGW_MAXU +
+                         6 * (PCGW_POSES + PCGW_MAXEXT) + (PCGW_INTS + 1) / 2;
+// dynamic shared memory of k_pcg_flow in doubles for a grid of nblk CTAs
+__host__ __device__ constexpr size_t pcg_flow_smem_doubles(int nblk) {
+  return (size_t)PCGF_THREADS + (size_t)7 * 6 * nblk + (PCGF_THREADS / 36) * 36 +
+         (size_t)(PCGW_BIG > 6 * 6 * nblk ? PCGW_BIG : 6 * 6 * nblk);
+}
+
+// spin on one cell (the first attempt was already issued by the caller)
+__device__ __forceinline__ double cell_wait(const uint4* p, uint4 c, unsigned tag) {
+  while (!cell_ok(c, tag)) {
+    __nanosleep(20);
+    c = ld_cell(p);
+  }
+  return cell_val(c);
+}
+
+// NB = gridDim.x as a compile-time constant (148 = one CTA per B200 SM): every shared-memory array then has a
+// constant address and the reduction / coarse loops unroll.
+template <int NB>
+__global__ void __launch_bounds__(PCGF_THREADS, 1)
+    k_pcg_flow(DevGraph G, CoarseDev Cz, BarSlot* slots, FlowBufs F, FlowTabs T, double lambda, double tol2, int maxit) {
+  extern __shared__ __align__(16) double dsm[];
+  __shared__ double s6[8], zc6[8], red6[7 * 32];
+  __shared__ int ovcnt[PCGF_THREADS / 32];
+  constexpr int nblk = NB;
+  constexpr int nc = 6 * nblk;
+  double* part_sh = dsm;                  // [PCGF_THREADS]  (loop: gam = [0..255], del = [256..511])
+  double* Arow = part_sh + PCGF_THREADS;  // [6][nc]  my rows of A_c^-1
+  double* wc = Arow + 6 * nc;             // [nc]     gathered P'w (init: P'r)
+  double* red = wc + nc;                  // [14][36] prologue scratch (loop: per-warp partials)
+  double* big = red + (PCGF_THREADS / 36) * 36;
+  double* panel_sh = big;                              // Gauss-Jordan panel [6][nc], afterwards the resident operands:
+  double* plH = big;                                   // [PCGF_MAXPL][18]  HplP blocks of my poses (6x3)
+  double* ppH = plH + 18 * PCGF_MAXPL;                 // [PCGW_MAXPPE][36] Hoff blocks of the distinct edges
+  double* ovH = ppH + 36 * PCGW_MAXPPE;                // [PCGF_MAXOV][18]  HplL blocks of edges 32.. of a landmark
+  double* b1_sh = ovH + 18 * PCGF_MAXOV;               // [80][36] P1 rows
+  double* m1_sh = b1_sh + PCGW_POSES * 36;             // [80][36] P1 D1^-1 rows
+  double* v_sh = m1_sh + PCGW_POSES * 36;              // [PCGW_MAXU][3]  staged v of the landmarks my poses see
+  double* u_sh = v_sh + 3 * PCGW_MAXU;                 // [80 + PCGW_MAXEXT][6] u of my poses and of external neighbours
+  int* pl_loc = reinterpret_cast<int*>(u_sh + 6 * (PCGW_POSES + PCGW_MAXEXT));  // [PCGF_MAXPL]
+  int* ulm = pl_loc + PCGF_MAXPL;                      // [PCGW_MAXU]
+  int* pp_loc = ulm + PCGW_MAXU;                       // [PCGF_MAXPP]
+  int* pp_src = pp_loc + PCGF_MAXPP;                   // [PCGF_MAXPP]
+  int* ext = pp_src + PCGF_MAXPP;                      // [PCGW_MAXEXT]
+  int* ov_pose = ext + PCGW_MAXEXT;                    // [PCGF_MAXOV]
+  double* gam = part_sh;
+  double* del = part_sh + PCGF_THREADS / 2;
+  double* scratch8 = red;                  // [16][8]
+  double* dpart = red + 8 * (PCGF_THREADS / 32);  // [12]
+  const bool use_sub = Cz.sub_enabled != 0;
+  const bool coarse = Cz.enabled != 0;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int slot = lane / 6, comp = lane - 6 * slot;
+  const int base_lane = 6 * slot;
+  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np, p0 + Cz.C);
+  const int i = p0 + warp * 5 + slot;          // my pose (pose role)
+  const bool act = lane < 30 && i < p1;
+  const int l = warp * nblk + blockIdx.x;      // my landmark (landmark role), round-robin over CTAs
+  const bool lact = l < G.Nl;
+  unsigned epoch = 0;
+  int status = 0;
+
+  bool use_coarse = false;
+  if (coarse) {
+    if (Cz.reuse_inverse) {
+      for (int k = threadIdx.x; k < 6 * nc; k += PCGF_THREADS) Arow[k] = Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k];
+      use_coarse = true;
+      __syncthreads();
+    } else {
+      use_coarse = coarse_prologue<PCGF_THREADS>(G, Cz, slots, epoch, lambda, Arow, panel_sh, red, part_sh, p0, p1);
+      if (use_coarse)
+        for (int k = threadIdx.x; k < 6 * nc; k += PCGF_THREADS) Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k] = Arow[k];
+    }
+  }
+
+  // ---- load the resident operands ------------------------------------------------------------
+  double Hrow[6], Drow[6], Brow[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    Hrow[k] = act ? G.Hpp[36 * (size_t)i + 6 * comp + k] : 0.0;
+    Drow[k] = act ? G.Dinv[36 * (size_t)i + 6 * comp + k] : 0.0;
+    Brow[k] = (act && use_coarse) ? Cz.Bmat[36 * (size_t)i + 6 * comp + k] : 0.0;
+  }
+  Hrow[comp] += act ? lambda : 0.0;
+  const int plbase = G.pose_pl_rowptr[p0 < G.Np ? p0 : G.Np];
+  const int ppbase = G.pose_pp_rowptr[p0 < G.Np ? p0 : G.Np];
+  const int npl_blk = G.pose_pl_rowptr[p1 > p0 ? p1 : (p0 < G.Np ? p0 : G.Np)] - plbase;
+  const int npp_blk = G.pose_pp_rowptr[p1 > p0 ? p1 : (p0 < G.Np ? p0 : G.Np)] - ppbase;
+  const int ulm0 = T.ulm_rowptr[blockIdx.x], nuniq = T.ulm_rowptr[blockIdx.x + 1] - ulm0;
+  const int upp0 = T.upp_rowptr[blockIdx.x], nupp = T.upp_rowptr[blockIdx.x + 1] - upp0;
+  const int ext0 = T.ext_rowptr[blockIdx.x], next = T.ext_rowptr[blockIdx.x + 1] - ext0;
+  for (int k = threadIdx.x; k < 18 * npl_blk; k += PCGF_THREADS) plH[k] = G.HplP[18 * (size_t)plbase + k];
+  for (int k = threadIdx.x; k < npl_blk; k += PCGF_THREADS) pl_loc[k] = T.pl_loc[plbase + k];
+  for (int k = threadIdx.x; k < nuniq; k += PCGF_THREADS) ulm[k] = T.ulm[ulm0 + k];
+  for (int k = threadIdx.x; k < npp_blk; k += PCGF_THREADS) {
+    pp_loc[k] = T.pp_loc[ppbase + k];
+    pp_src[k] = T.pp_src[ppbase + k];
+  }
+  for (int k = threadIdx.x; k < 36 * nupp; k += PCGF_THREADS) ppH[k] = G.Hoff[36 * (size_t)T.upp[upp0 + k / 36] + (k % 36)];
+  for (int k = threadIdx.x; k < next; k += PCGF_THREADS) ext[k] = T.ext[ext0 + k];
+  if (use_sub) {
+    // P1 rows and M1 = P1 D1^-1 rows of my poses (zero D1^-1 = level off for that aggregate)
+    for (int k = threadIdx.x; k < 36 * (p1 - p0); k += PCGF_THREADS) {
+      const int ip = p0 + k / 36, rc_ = k % 36, row = rc_ / 6, j = rc_ - 6 * row;
+      const double* B1 = Cz.B1mat + 36 * (size_t)ip + 6 * row;
+      const double* D1 = Cz.D1inv + 36 * (size_t)(ip / 5);
+      b1_sh[k] = B1[j];
+      double t = 0.0;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) t += B1[m] * D1[6 * m + j];
+      m1_sh[k] = t;
+    }
+  }
+  const double* b1row = b1_sh + 36 * (warp * 5 + slot) + 6 * comp;
+  const double* m1row = m1_sh + 36 * (warp * 5 + slot) + 6 * comp;
+  const int mypl0 = act ? G.pose_pl_rowptr[i] - plbase : 0, mypl1 = act ? G.pose_pl_rowptr[i + 1] - plbase : 0;
+  const int mypp0 = act ? G.pose_pp_rowptr[i] - ppbase : 0, mypp1 = act ? G.pose_pp_rowptr[i + 1] - ppbase : 0;
+  // landmark role.  The (edge, column) pairs of landmark l are dealt to the lanes in cell order:
+  // item idx = 32 m + lane  ->  edge idx / 6, column idx % 6, so that one warp-wide load instruction reads
+  // runs of 6 consecutive cells (one pose's u) instead of 32 scattered ones.
+  double HLc[6][3];
+  int uoff[6];
+  double Wr[3] = {0, 0, 0};  // lane k < 3: row k of W_l = (Hll + lambda I)^-1
+  int deg = 0, le0 = 0;
+  if (lact) {
+    le0 = G.lm_rowptr[l];
+    deg = G.lm_rowptr[l + 1] - le0;
+    if (lane < 3) {
+      const double* Wu = G.HllInv + 6 * (size_t)l;
+      // upper triangle storage: 0:(0,0) 1:(0,1) 2:(0,2) 3:(1,1) 4:(1,2) 5:(2,2)
+      Wr[0] = lane == 0 ? Wu[0] : (lane == 1 ? Wu[1] : Wu[2]);
+      Wr[1] = lane == 0 ? Wu[1] : (lane == 1 ? Wu[3] : Wu[4]);
+      Wr[2] = lane == 0 ? Wu[2] : (lane == 1 ? Wu[4] : Wu[5]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 6; ++m) {
+    const int idx = 32 * m + lane, edge = idx / 6, k = idx - 6 * edge;
+    if (edge < min(deg, 32)) {
+      uoff[m] = 6 * G.pl[le0 + edge].p + k;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) HLc[m][r] = G.HplL[18 * (size_t)(le0 + edge) + 6 * r + k];
+    } else {
+      uoff[m] = -1;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) HLc[m][r] = 0.0;
+    }
+  }
+  // edges 32..63 of a landmark: blocks and pose ids kept in shared memory
+  const int nov = max(0, deg - 32);
+  if (lane == 0) ovcnt[warp] = nov;
+  __syncthreads();
+  int ovbase = 0;
+  for (int w = 0; w < warp; ++w) ovbase += ovcnt[w];
+  if (lane < nov) {
+    const int e = le0 + 32 + lane;
+    ov_pose[ovbase + lane] = G.pl[e].p;
+    for (int k = 0; k < 18; ++k) ovH[18 * (ovbase + lane) + k] = G.HplL[18 * (size_t)e + k];
+  }
+  __syncthreads();
+
+  // ---- init: x = 0, r = g, u = M^-1 r ------------------------------------------------------------
+  const unsigned tb = F.tagbase;
+  uint4* const my_ucell = F.ucell + 6 * (size_t)(act ? i : 0) + comp;
+  double* const my_ush = u_sh + 6 * (warp * 5 + slot) + comp;
+  double xc = 0.0;
+  double rcomp = act ? G.g[6 * (size_t)i + comp] : 0.0;
+  double uc = 0.0, pc = 0.0, sc = 0.0, cz = 0.0, cy = 0.0, wv = 0.0;
+  if (use_coarse) {
+    double l6[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) l6[k] = Brow[k] * rcomp;
+    block_sum6(l6, s6, red6);
+    grid_bar_sum(slots, epoch, 0.0, s6, wc, part_sh);  // wc = P'r (all aggregates)
+    if (warp < 6) {
+      double t = 0.0;
+      for (int j = lane; j < nc; j += 32) t += Arow[warp * nc + j] * wc[j];
+      t = warp_sum(t);
+      if (lane == 0) zc6[warp] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cz += Brow[k] * zc6[k];
+  }
+#define SSB_FLOW_PRECOND()                                                                              \
+  {                                                                                                     \
+    double _z = 0.0;                                                                                    \
+    _Pragma("unroll") for (int k = 0; k < 6; ++k) _z += Drow[k] * __shfl_sync(0xffffffffu, rcomp, base_lane + k); \
+    if (use_sub) {                                                                                      \
+      double _t[8];                                                                                     \
+      _Pragma("unroll") for (int k = 0; k < 6; ++k) _t[k] = act ? b1row[k] * rcomp : 0.0;                \
+      _t[6] = 0.0;                                                                                      \
+      _t[7] = 0.0;                                                                                      \
+      const double _r = warp_reduce8(_t); /* P1'r: value k in lanes 4k..4k+3 */                          \
+      _Pragma("unroll") for (int k = 0; k < 6; ++k) {                                                    \
+        const double _rk = __shfl_sync(0xffffffffu, _r, 4 * k);                                          \
+        if (act) _z += m1row[k] * _rk;                                                                   \
+      }                                                                                                 \
+    }                                                                                                   \
+    uc = act ? _z + cz : 0.0;                                                                           \
+  }
+  SSB_FLOW_PRECOND()
+  if (act) {
+    st_cell(my_ucell, uc, tb + 1u);
+    *my_ush = uc;
+  }
+
+  double gamma = 0.0, gamma0 = 0.0, inv_gamma_old = 1.0, inv_alpha = 1.0;
+  int it = 0;
+#ifdef SSB_PCG_TIMERS
+  long long tmr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+#define SSB_FTICK(k)          \
+  do {                        \
+    long long _n = clock64(); \
+    tmr[k] += _n - tlast;     \
+    tlast = _n;               \
+  } while (0)
+#else
+#define SSB_FTICK(k) \
+  do {               \
+  } while (0)
+#endif
+  const int nstage = 3 * nuniq + 6 * next;   // cells staged into shared memory per iteration
+  const int ngather = 8 * nblk;
+  for (it = 0;; ++it) {
+    const unsigned tg = tb + (unsigned)it + 1u;
+    // ---- A (landmark role): v = W_l sum_e HplL_e u_p(e) ------------------------------------------
+    if (lact) {
+      double a[4] = {0.0, 0.0, 0.0, 0.0};
+      uint4 c[6];
+#pragma unroll
+      for (int m = 0; m < 6; ++m)
+        if (uoff[m] >= 0) c[m] = ld_cell(F.ucell + uoff[m]);
+#pragma unroll
+      for (int m = 0; m < 6; ++m)
+        if (uoff[m] >= 0) {
+          const double uv = cell_wait(F.ucell + uoff[m], c[m], tg);
+          a[0] += HLc[m][0] * uv;
+          a[1] += HLc[m][1] * uv;
+          a[2] += HLc[m][2] * uv;
+        }
+      if (nov > 0) {  // warp-uniform: edges 32..63, same cell-order dealing, second batch of loads
+        const uint4* src[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+          const int idx = 32 * m + lane, edge = idx / 6;
+          src[m] = nullptr;
+          if (edge < nov) {
+            src[m] = F.ucell + 6 * (size_t)ov_pose[ovbase + edge] + (idx - 6 * edge);
+            c[m] = ld_cell(src[m]);
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+          const int idx = 32 * m + lane, edge = idx / 6;
+          if (edge < nov) {
+            const double uv = cell_wait(src[m], c[m], tg);
+            const double* H2 = ovH + 18 * (ovbase + edge) + (idx - 6 * edge);
+            a[0] += H2[0] * uv;
+            a[1] += H2[6] * uv;
+            a[2] += H2[12] * uv;
+          }
+        }
+      }
+      const double rsum = warp_reduce4(a);  // value j in lanes 8j..8j+7
+      const double a0 = __shfl_sync(0xffffffffu, rsum, 0);
+      const double a1 = __shfl_sync(0xffffffffu, rsum, 8);
+      const double a2 = __shfl_sync(0xffffffffu, rsum, 16);
+      if (lane < 3) st_cell(F.vcell + 3 * (size_t)l + lane, Wr[0] * a0 + Wr[1] * a1 + Wr[2] * a2, tg);
+    }
+    SSB_FTICK(0);
+    // ---- stage v of my poses' landmarks and u of external neighbours into shared memory --------------
+    {
+      uint4 c[3];
+      const uint4* src[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const int q = threadIdx.x + PCGF_THREADS * m;
+        src[m] = nullptr;
+        if (q < nstage) {
+          if (q < 3 * nuniq) {
+            const int lu = q / 3;
+            src[m] = F.vcell + 3 * (size_t)ulm[lu] + (q - 3 * lu);
+          } else {
+            const int qq = q - 3 * nuniq, xe = qq / 6;
+            src[m] = F.ucell + 6 * (size_t)ext[xe] + (qq - 6 * xe);
+          }
+          c[m] = ld_cell(src[m]);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const int q = threadIdx.x + PCGF_THREADS * m;
+        if (q < nstage) {
+          const double val = cell_wait(src[m], c[m], tg);
+          if (q < 3 * nuniq)
+            v_sh[q] = val;
+          else
+            u_sh[6 * PCGW_POSES + (q - 3 * nuniq)] = val;
+        }
+      }
+    }
+    SSB_FTICK(1);
+    __syncthreads();
+    // ---- B (pose role): w = (Hpp + lambda I) u + sum Hoff u_nbr - sum HplP v  (all operands on chip) ---
+    {
+      wv = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) wv += Hrow[k] * __shfl_sync(0xffffffffu, uc, base_lane + k);
+      for (int s = mypp0; s < mypp1; ++s) {
+        const int code = pp_src[s];
+        const double* us = u_sh + 6 * (code & 0x7fffffff);
+        const double* Ho = ppH + 36 * pp_loc[s];
+        if (code < 0) {  // role 1: my pose is vertex j of the edge -> Hoff'
+#pragma unroll
+          for (int k = 0; k < 6; ++k) wv += Ho[6 * k + comp] * us[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) wv += Ho[6 * comp + k] * us[k];
+        }
+      }
+      for (int kk = mypl0; kk < mypl1; ++kk) {
+        const double* vv = v_sh + 3 * pl_loc[kk];
+        const double* Hp = plH + 18 * kk + 3 * comp;
+        wv -= Hp[0] * vv[0] + Hp[1] * vv[1] + Hp[2] * vv[2];
+      }
+      if (!act) wv = 0.0;
+    }
+    // ---- C: one fused reduction: gamma = r'u, delta = w'u, P'w (6 per CTA) ---------------------------
+    {
+      double t8[8];
+      t8[0] = rcomp * uc;
+      t8[1] = wv * uc;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) t8[2 + k] = Brow[k] * wv;
+      const double rs = warp_reduce8(t8);
+      if ((lane & 3) == 0) scratch8[8 * warp + (lane >> 2)] = rs;
+    }
+    SSB_FTICK(2);
+    __syncthreads();
+    if (warp == 0 && lane < 8) {
+      double t = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < PCGF_THREADS / 32; ++ww) t += scratch8[8 * ww + lane];
+      st_cell(F.lines + ((size_t)(tg & 1u) * nblk + blockIdx.x) * 8 + lane, t, tg);
+    }
+    {
+      // pull all-gather of the nblk lines: thread q reads cell q (coalesced), value k of line q/8
+      const uint4* L = F.lines + (size_t)(tg & 1u) * nblk * 8;
+      uint4 c[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const int q = threadIdx.x + PCGF_THREADS * m;
+        if (q < ngather) c[m] = ld_cell(L + q);
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const int q = threadIdx.x + PCGF_THREADS * m;
+        if (q < ngather) {
+          const double val = cell_wait(L + q, c[m], tg);
+          const int ln = q >> 3, k = q & 7;
+          if (k == 0)
+            gam[ln] = val;
+          else if (k == 1)
+            del[ln] = val;
+          else
+            wc[6 * ln + k - 2] = val;
+        }
+      }
+      for (int q = threadIdx.x + 3 * PCGF_THREADS; q < ngather; q += PCGF_THREADS) {  // grids > 192 CTAs
+        const double val = cell_wait(L + q, ld_cell(L + q), tg);
+        const int ln = q >> 3, k = q & 7;
+        if (k == 0)
+          gam[ln] = val;
+        else if (k == 1)
+          del[ln] = val;
+        else
+          wc[6 * ln + k - 2] = val;
+      }
+    }
+    SSB_FTICK(3);
+    __syncthreads();
+    SSB_FTICK(4);
+    double delta;
+    {
+      double tg_ = 0.0, td_ = 0.0;
+      for (int k = lane; k < nblk; k += 32) {
+        tg_ += gam[k];
+        td_ += del[k];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        tg_ += __shfl_xor_sync(0xffffffffu, tg_, o);
+        td_ += __shfl_xor_sync(0xffffffffu, td_, o);
+      }
+      gamma = tg_;
+      delta = td_;
+    }
+    if (use_coarse) {
+      if (warp < 12) {  // two warps per row of A_c^-1
+        const int row = warp >> 1, j0 = (warp & 1) * (nc >> 1), j1 = j0 + (nc >> 1);
+        double t = 0.0;
+        for (int j = j0 + lane; j < j1; j += 32) t += Arow[row * nc + j] * wc[j];
+        t = warp_sum(t);
+        if (lane == 0) dpart[warp] = t;
+      }
+      __syncthreads();
+    }
+    SSB_FTICK(5);
+    // ---- scalars (identical in every thread of every CTA) -------------------------------------------
+    if (it == 0) {
+      gamma0 = gamma;
+      if (!(gamma0 > 0.0)) {
+        status = (gamma0 == 0.0) ? 0 : 2;
+        break;
+      }
+    }
+    if (!(gamma > tol2 * gamma0)) break;
+    if (it >= maxit) break;
+    // beta = gamma/gamma_old, alpha = gamma / (delta - beta*gamma/alpha_old) with one division on the
+    // critical path (1/gamma is independent of it)
+    const double inv_gamma = 1.0 / gamma;
+    const double beta = (it == 0) ? 0.0 : gamma * inv_gamma_old;
+    const double den = (it == 0) ? delta : delta - beta * gamma * inv_alpha;
+    if (!(den > 0.0) || !isfinite(den)) {
+      status = 1;
+      break;
+    }
+    const double alpha = gamma / den;
+    inv_alpha = den * inv_gamma;
+    inv_gamma_old = inv_gamma;
+    // ---- D: recurrences and u = M^-1 r ----------------------------------------------------------------
+    pc = uc + beta * pc;
+    sc = wv + beta * sc;
+    xc += alpha * pc;
+    rcomp -= alpha * sc;
+    if (use_coarse) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) t += Brow[k] * (dpart[2 * k] + dpart[2 * k + 1]);
+      cy = t + beta * cy;
+      cz -= alpha * cy;
+    }
+    SSB_FLOW_PRECOND()
+    if (act) {
+      st_cell(my_ucell, uc, tg + 1u);
+      *my_ush = uc;
+    }
+    SSB_FTICK(6);
+  }
+#undef SSB_FLOW_PRECOND
+  if (act) G.x[6 * (size_t)i + comp] = xc;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    G.iscalars[0] = it;
+    G.iscalars[1] = status;
+    G.scalars[3] = gamma;
+    G.scalars[4] = gamma0;
+#ifdef SSB_PCG_TIMERS
+    for (int k = 0; k < 8; ++k) G.scalars[8 + k] += (double)tmr[k];
+#endif
+  }
+}
+
+}  // namespace ssb

@@ -178,7 +178,7 @@ struct ssb_graph {
   size_t pcg_smem = 0, pcgf_smem = 0, pcgw_smem = 0;
   DBuf<int> d_ft_ulm_rowptr, d_ft_ulm, d_ft_pl_loc, d_ft_upp_rowptr, d_ft_upp, d_ft_pp_loc, d_ft_pp_src, d_ft_ext_rowptr, d_ft_ext;
   FlowTabs FT;
-  DBuf<uint4> d_ucell, d_vcell, d_lines;   // tagged cells of the data-flow PCG kernel (ssb_pcg_flow.cuh)
+  DBuf<uint4> d_ucell, d_vcell, d_lines, d_gj;   // tagged cells of the data-flow PCG kernel (ssb_pcg_flow.cuh)
   unsigned flow_seq = 0;                   // launch counter -> tag base (seq << 16)
   bool use_flow = true;                    // opts.reserved[2] = 1 selects the barrier-based k_pcg_fast instead
   bool fast_ok = false;   // the graph fits the on-chip resident PCG kernel
@@ -687,6 +687,10 @@ static int prepare(ssb_graph* g) {
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_ucell.p, 0, g->d_ucell.cap * sizeof(uint4), g->stream));
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_vcell.p, 0, g->d_vcell.cap * sizeof(uint4), g->stream));
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_lines.p, 0, g->d_lines.cap * sizeof(uint4), g->stream));
+    if (g->use_flow && g->opts.preconditioner >= 1) {
+      SSB_TRY(g->d_gj.ensure((size_t)nblk * (36 * (size_t)nblk + 8)));
+      SSB_CUDA_CHECK(cudaMemsetAsync(g->d_gj.p, 0, g->d_gj.cap * sizeof(uint4), g->stream));
+    }
     g->flow_seq = 0;
     g->ainv_valid = false;
     cudaStream_t s = g->stream;
@@ -888,9 +892,10 @@ static int launch_pcg(ssb_graph* g, double lambda) {
       SSB_CUDA_CHECK(cudaMemsetAsync(g->d_ucell.p, 0, g->d_ucell.cap * sizeof(uint4), s));
       SSB_CUDA_CHECK(cudaMemsetAsync(g->d_vcell.p, 0, g->d_vcell.cap * sizeof(uint4), s));
       SSB_CUDA_CHECK(cudaMemsetAsync(g->d_lines.p, 0, g->d_lines.cap * sizeof(uint4), s));
+      if (g->d_gj.p) SSB_CUDA_CHECK(cudaMemsetAsync(g->d_gj.p, 0, g->d_gj.cap * sizeof(uint4), s));
       g->flow_seq = 1;
     }
-    FlowBufs F{g->d_ucell.p, g->d_vcell.p, g->d_lines.p, g->flow_seq << 16};
+    FlowBufs F{g->d_ucell.p, g->d_vcell.p, g->d_lines.p, g->d_gj.p, g->flow_seq << 16};
     int maxit_f = std::min(maxit, 60000);
     void* fargs[] = {(void*)&G, (void*)&g->Cz, (void*)&slots, (void*)&F, (void*)&g->FT, (void*)&lambda, (void*)&tol2, (void*)&maxit_f};
     SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg_flow<148>, dim3(g->pcg_grid), dim3(PCGF_THREADS), fargs, g->pcgw_smem, s));

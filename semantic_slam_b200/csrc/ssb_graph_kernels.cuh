@@ -616,15 +616,13 @@ __global__ void __launch_bounds__(64) k_sub_assemble(DevGraph G, CoarseDev Cz, d
 // aggregate k at step k: its owner publishes the scaled pivot panel, one barrier per step).
 // Returns true when A_c^-1 is usable (every pivot block was positive definite).
 // ---------------------------------------------------------------------------------------------
+// assembly of my 6 rows of A_c = P' S P into Arow[6][nc] (shared memory)
 template <int NT>
-__device__ bool coarse_prologue(const DevGraph& G, const CoarseDev& Cz, BarSlot* slots, unsigned& epoch, double lambda,
-                                double* Arow, double* panel_sh, double* red, double* part_sh, int p0, int p1) {
+__device__ void coarse_assemble(const DevGraph& G, const CoarseDev& Cz, double lambda, double* Arow, double* red, int p0,
+                                int p1) {
   constexpr int SLICES = NT / 36;
-  __shared__ int s_flag;
-  __shared__ double piv_sh[40];
   const int nblk = gridDim.x, nc = 6 * nblk, myg = blockIdx.x;
   for (int k = threadIdx.x; k < 6 * nc; k += NT) Arow[k] = 0.0;
-  if (threadIdx.x == 0) s_flag = 0;
   __syncthreads();
   // (a) diagonal block: sum_i B_i' (Hpp_ii + lambda I) B_i + pose-pose edges inside the aggregate
   {
@@ -713,6 +711,16 @@ __device__ bool coarse_prologue(const DevGraph& G, const CoarseDev& Cz, BarSlot*
     }
   }
   __syncthreads();
+}
+
+template <int NT>
+__device__ bool coarse_prologue(const DevGraph& G, const CoarseDev& Cz, BarSlot* slots, unsigned& epoch, double lambda,
+                                double* Arow, double* panel_sh, double* red, double* part_sh, int p0, int p1) {
+  __shared__ int s_flag;
+  __shared__ double piv_sh[40];
+  const int nblk = gridDim.x, nc = 6 * nblk;
+  if (threadIdx.x == 0) s_flag = 0;
+  coarse_assemble<NT>(G, Cz, lambda, Arow, red, p0, p1);
   // ---- block Gauss-Jordan ----
   for (int k = 0; k < nblk; ++k) {
     double* gp = Cz.panel + (size_t)(k & 1) * (6 * nc + 8);

@@ -31,6 +31,7 @@ struct FlowBufs {
   uint4* ucell;   // [6 * Np]  u = M^-1 r
   uint4* vcell;   // [3 * Nl]  v = W Hlp u
   uint4* lines;   // [2][gridDim.x][8] per-CTA reduction lines, double buffered on the tag parity
+  uint4* gj;      // [gridDim.x][36 gridDim.x + 8] Gauss-Jordan pivot panels of the coarse inversion, one per step
   unsigned tagbase;
 };
 
@@ -46,6 +47,15 @@ __device__ __forceinline__ uint4 ld_cell(const uint4* c) {
 }
 __device__ __forceinline__ bool cell_ok(const uint4& u, unsigned tag) { return u.y == tag && u.w == tag; }
 __device__ __forceinline__ double cell_val(const uint4& u) { return __hiloint2double((int)u.z, (int)u.x); }
+
+// spin on one cell (the first attempt was already issued by the caller)
+__device__ __forceinline__ double cell_wait(const uint4* p, uint4 c, unsigned tag) {
+  while (!cell_ok(c, tag)) {
+    __nanosleep(20);
+    c = ld_cell(p);
+  }
+  return cell_val(c);
+}
 
 // Packed butterfly reductions: N values per lane are reduced across the warp with N-1 + (5 - log2 N)
 // exchanges instead of 5 N.  The sum of value j ends up in the lanes whose upper bits spell j.
@@ -133,13 +143,145 @@ __host__ __device__ constexpr size_t pcg_flow_smem_doubles(int nblk) {
          (size_t)(PCGW_BIG > 6 * 6 * nblk ? PCGW_BIG : 6 * 6 * nblk);
 }
 
-// spin on one cell (the first attempt was already issued by the caller)
-__device__ __forceinline__ double cell_wait(const uint4* p, uint4 c, unsigned tag) {
-  while (!cell_ok(c, tag)) {
-    __nanosleep(20);
-    c = ld_cell(p);
+
+// 1/x to full double precision without the IEEE division sequence: hardware seed (~20 bits) + 2 Newton steps
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+// 6x6 SPD inverse by 6 lanes of one warp (lane j owns column j of [A | I]); all 32 lanes must call.
+__device__ __forceinline__ bool warp_inv6_fast(double* col) {
+  const int lane = threadIdx.x & 31;
+  double inv[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) inv[i] = (i == lane) ? 1.0 : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double piv = __shfl_sync(0xffffffffu, col[k], k);
+    if (!(piv > 0.0) || !isfinite(piv)) ok = false;
+    const double ip = fast_rcp(piv);
+    double ck[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ck[i] = __shfl_sync(0xffffffffu, col[i], k);
+    const double akj = col[k] * ip, bkj = inv[k] * ip;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (i == k) {
+        col[i] = akj;
+        inv[i] = bkj;
+      } else {
+        col[i] -= ck[i] * akj;
+        inv[i] -= ck[i] * bkj;
+      }
+    }
   }
-  return cell_val(c);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) col[i] = inv[i];
+  return __all_sync(0xffffffffu, ok || lane >= 6);
+}
+
+// Block Gauss-Jordan inversion of A_c (my 6 rows in Arow[6][nc]) without grid barriers: the owner of pivot
+// aggregate k publishes its scaled panel as tagged cells into a per-step buffer, every other CTA applies the
+// panels in order as they arrive, so the critical path is panel k -> CTA k+1 -> panel k+1 (one L2 hop per
+// step).  CTAs whose block in pivot column k is zero skip the step without waiting.
+// Returns true when every pivot block was positive definite.
+template <int NT, int NB>
+__device__ bool coarse_gj_flow(uint4* gj, unsigned tag, double* Arow) {
+  constexpr int nc = 6 * NB;
+  constexpr int PER = (nc + NT - 1) / NT;
+  constexpr int PSTRIDE = 6 * nc + 8;
+  __shared__ int s_flag;
+  __shared__ double piv_sh[40];   // pivot inverse (pivot CTA) or F = my block in pivot column k
+  if (threadIdx.x == 0) s_flag = 0;
+  __syncthreads();
+  for (int k = 0; k < NB; ++k) {
+    uint4* P = gj + (size_t)k * PSTRIDE;
+    if ((int)blockIdx.x == k) {
+      if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double col[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) col[a] = lane < 6 ? Arow[a * nc + 6 * k + lane] : 0.0;
+        const bool ok = warp_inv6_fast(col);
+        if (lane < 6) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) piv_sh[6 * a + lane] = ok ? col[a] : (a == lane ? 1.0 : 0.0);
+        }
+        if (lane == 0) piv_sh[36] = ok ? 0.0 : 1.0;
+      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < nc; j += NT) {
+        double colv[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) colv[a] = Arow[a * nc + j];
+        const bool inpiv = (j >= 6 * k && j < 6 * k + 6);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          double t = 0.0;
+          if (inpiv) {
+            t = piv_sh[6 * a + (j - 6 * k)];
+          } else {
+#pragma unroll
+            for (int b = 0; b < 6; ++b) t += piv_sh[6 * a + b] * colv[b];
+          }
+          Arow[a * nc + j] = t;
+          st_cell(P + a * nc + j, t, tag);
+        }
+      }
+      if (threadIdx.x == 0) {
+        st_cell(P + 6 * nc, piv_sh[36], tag);
+        if (piv_sh[36] != 0.0) s_flag = 1;
+      }
+      __syncthreads();
+    } else {
+      // F = my block in pivot column k.  F == 0 (aggregates not coupled so far): the step leaves my rows
+      // unchanged, so the panel is neither awaited nor read.
+      double fv = 0.0;
+      if (threadIdx.x < 36) {
+        fv = Arow[(threadIdx.x / 6) * nc + 6 * k + (threadIdx.x % 6)];
+        piv_sh[threadIdx.x] = fv;
+      }
+      if (__syncthreads_or(fv != 0.0) == 0) continue;
+      double pj[PER][6];
+#pragma unroll
+      for (int m = 0; m < PER; ++m) {
+        const int j = threadIdx.x + NT * m;
+        if (j < nc) {
+          uint4 c[6];
+#pragma unroll
+          for (int b = 0; b < 6; ++b) c[b] = ld_cell(P + b * nc + j);
+#pragma unroll
+          for (int b = 0; b < 6; ++b) pj[m][b] = cell_wait(P + b * nc + j, c[b], tag);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < PER; ++m) {
+        const int j = threadIdx.x + NT * m;
+        if (j < nc) {
+          const bool inpiv = (j >= 6 * k && j < 6 * k + 6);
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+            double t = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) t += piv_sh[6 * a + b] * pj[m][b];
+            Arow[a * nc + j] = inpiv ? -t : Arow[a * nc + j] - t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // pivot failures must be seen by every CTA, including those that skipped the failing step
+  if (threadIdx.x < NB) {
+    const uint4* fc = gj + (size_t)threadIdx.x * PSTRIDE + 6 * nc;
+    if (cell_wait(fc, ld_cell(fc), tag) != 0.0) s_flag = 1;
+  }
+  __syncthreads();
+  return s_flag == 0;
 }
 
 // NB = gridDim.x as a compile-time constant (148 = one CTA per B200 SM): every shared-memory array then has a
@@ -190,6 +332,10 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   unsigned epoch = 0;
   int status = 0;
 
+#ifdef SSB_PCG_TIMERS
+  const long long t_start = clock64();
+  long long t_asm = t_start;
+#endif
   bool use_coarse = false;
   if (coarse) {
     if (Cz.reuse_inverse) {
@@ -197,7 +343,11 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       use_coarse = true;
       __syncthreads();
     } else {
-      use_coarse = coarse_prologue<PCGF_THREADS>(G, Cz, slots, epoch, lambda, Arow, panel_sh, red, part_sh, p0, p1);
+      coarse_assemble<PCGF_THREADS>(G, Cz, lambda, Arow, red, p0, p1);
+#ifdef SSB_PCG_TIMERS
+      t_asm = clock64();
+#endif
+      use_coarse = coarse_gj_flow<PCGF_THREADS, NB>(F.gj, F.tagbase + 1u, Arow);
       if (use_coarse)
         for (int k = threadIdx.x; k < 6 * nc; k += PCGF_THREADS) Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k] = Arow[k];
     }
@@ -340,6 +490,8 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
 #ifdef SSB_PCG_TIMERS
   long long tmr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
+  tmr[7] = tlast - t_asm;          // Gauss-Jordan + operand load + init
+  tmr[6] = -(t_asm - t_start);     // (negative) coarse assembly, folded into slot 6 for display
 #define SSB_FTICK(k)          \
   do {                        \
     long long _n = clock64(); \

@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pcg-tol", type=float, default=1e-8)
+    ap.add_argument("--pcg-tol", type=float, default=1e-6)
     ap.add_argument("--preconditioner", type=int, default=2)
     args = ap.parse_args()
 

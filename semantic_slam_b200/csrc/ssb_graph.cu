@@ -175,12 +175,14 @@ struct ssb_graph {
   DBuf<int> d_run_lm, d_run_group, d_run_e0, d_lm_run_rowptr, d_grp_run_rowptr, d_grp_runs;
   DBuf<BarSlot> d_slots;
   CoarseDev Cz;
-  size_t pcg_smem = 0, pcgf_smem = 0, pcgw_smem = 0;
+  size_t pcg_smem = 0, pcgw_smem = 0;
   DBuf<int> d_ft_ulm_rowptr, d_ft_ulm, d_ft_pl_loc, d_ft_upp_rowptr, d_ft_upp, d_ft_pp_loc, d_ft_pp_src, d_ft_ext_rowptr, d_ft_ext;
   FlowTabs FT;
-  DBuf<uint4> d_ucell, d_vcell, d_lines, d_gj;   // tagged cells of the data-flow PCG kernel (ssb_pcg_flow.cuh)
+  DBuf<uint4> d_ucell, d_lines, d_gj;
+  DBuf<unsigned long long> d_trace;
+  DBuf<double2> d_hlpark;   // tagged cells of the data-flow PCG kernel (ssb_pcg_flow.cuh)
   unsigned flow_seq = 0;                   // launch counter -> tag base (seq << 16)
-  bool use_flow = true;                    // opts.reserved[2] = 1 selects the barrier-based k_pcg_fast instead
+  bool use_flow = true;                    // the grid is 148 CTAs (B200): k_pcg_flow is instantiated for that size
   bool fast_ok = false;   // the graph fits the on-chip resident PCG kernel
   bool allow_fast = true;
   double* h_scalars = nullptr;  // pinned: 8 doubles
@@ -282,10 +284,8 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
   }
   g->pcg_grid = std::min(g->num_sms, PCG_THREADS);  // one persistent CTA per SM
   g->pcg_smem = (size_t)(PCG_THREADS + 14 * 6 * g->pcg_grid + (PCG_THREADS / 36) * 36) * sizeof(double);
-  g->pcgf_smem = (size_t)(PCGF_THREADS + 8 * 6 * g->pcg_grid + (PCGF_THREADS / 36) * 36 +
-                          std::max(PCGF_BIG, 6 * 6 * g->pcg_grid)) * sizeof(double);
   g->allow_fast = g->opts.reserved[0] == 0;
-  g->use_flow = g->opts.reserved[2] == 0 && g->pcg_grid == 148;   // k_pcg_flow is instantiated for 148 CTAs (B200)
+  g->use_flow = g->pcg_grid == 148;   // k_pcg_flow is instantiated for 148 CTAs (one per B200 SM)
   g->pcgw_smem = pcg_flow_smem_doubles(g->pcg_grid) * sizeof(double);
   if (const char* e = std::getenv("SSB_MG_GRAPH")) g->mg_graph_failed = !(e[0] == '1');   // reserved[0] = 1 forces the generic (streaming) kernel
   int nb = 0;
@@ -300,13 +300,6 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_flow<148>, PCGF_THREADS, g->pcgw_smem);
   if (e != cudaSuccess || nb < 1) {
     set_error("k_pcg_flow cannot be made resident (occupancy %d, %zu B smem): %s", nb, g->pcgw_smem, cudaGetErrorString(e));
-    delete g;
-    return nullptr;
-  }
-  e = cudaFuncSetAttribute(k_pcg_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcgf_smem);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_fast, PCGF_THREADS, g->pcgf_smem);
-  if (e != cudaSuccess || nb < 1) {
-    set_error("k_pcg_fast cannot be made resident (occupancy %d, %zu B smem): %s", nb, g->pcgf_smem, cudaGetErrorString(e));
     delete g;
     return nullptr;
   }
@@ -584,7 +577,7 @@ static int prepare(ssb_graph* g) {
     {
       // does the graph fit the on-chip resident kernel?  (<= 80 poses per CTA, bounded incidence lists,
       // one landmark per warp, <= 64 edges per landmark, bounded overflow per CTA)
-      bool ok = g->allow_fast && Cc <= 5 * (PCGF_THREADS / 32) && Nl <= nblk * (PCGF_THREADS / 32);
+      bool ok = g->allow_fast && g->use_flow && Cc <= 5 * (PCGF_THREADS / 32) && Nl <= nblk * (PCGF_THREADS / 32);
       if (ok) {
         std::vector<int> ov(nblk, 0);
         for (int l = 0; l < Nl && ok; ++l) {
@@ -681,11 +674,10 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_grp_runs.ensure(n_runs));
     SSB_TRY(g->d_slots.ensure((size_t)2 * nblk + 1));
     SSB_TRY(g->d_ainv.ensure((size_t)nblk * 6 * ncoarse));
-    SSB_TRY(g->d_ucell.ensure((size_t)6 * (Np + 64)));
-    SSB_TRY(g->d_vcell.ensure((size_t)3 * (Nl + 64)));
+    SSB_TRY(g->d_ucell.ensure((size_t)6 * (Np + 64) + (size_t)3 * (Nl + 64)));   // u cells, then v cells
     SSB_TRY(g->d_lines.ensure((size_t)2 * nblk * 8));
+    SSB_TRY(g->d_hlpark.ensure((size_t)nblk * (PCGF_THREADS / 32) * 9 * 32));
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_ucell.p, 0, g->d_ucell.cap * sizeof(uint4), g->stream));
-    SSB_CUDA_CHECK(cudaMemsetAsync(g->d_vcell.p, 0, g->d_vcell.cap * sizeof(uint4), g->stream));
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_lines.p, 0, g->d_lines.cap * sizeof(uint4), g->stream));
     if (g->use_flow && g->opts.preconditioner >= 1) {
       SSB_TRY(g->d_gj.ensure((size_t)nblk * (36 * (size_t)nblk + 8)));
@@ -886,22 +878,20 @@ static int launch_pcg(ssb_graph* g, double lambda) {
     }
   }
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used], s));
-  if (g->fast_ok && g->use_flow) {
+  if (g->fast_ok) {
     // tags = (seq << 16) + iteration: unique per launch, so the cell buffers are never cleared between solves
     if (++g->flow_seq >= 0xFFFFu) {
       SSB_CUDA_CHECK(cudaMemsetAsync(g->d_ucell.p, 0, g->d_ucell.cap * sizeof(uint4), s));
-      SSB_CUDA_CHECK(cudaMemsetAsync(g->d_vcell.p, 0, g->d_vcell.cap * sizeof(uint4), s));
       SSB_CUDA_CHECK(cudaMemsetAsync(g->d_lines.p, 0, g->d_lines.cap * sizeof(uint4), s));
       if (g->d_gj.p) SSB_CUDA_CHECK(cudaMemsetAsync(g->d_gj.p, 0, g->d_gj.cap * sizeof(uint4), s));
       g->flow_seq = 1;
     }
-    FlowBufs F{g->d_ucell.p, g->d_vcell.p, g->d_lines.p, g->d_gj.p, g->flow_seq << 16};
+    SSB_TRY(g->d_trace.ensure(8 * 256));
+    FlowBufs F{g->d_ucell.p, g->d_ucell.p + (size_t)6 * (G.Np + 64), g->d_lines.p, g->d_gj.p, g->flow_seq << 16, g->d_hlpark.p, g->d_trace.p};
     int maxit_f = std::min(maxit, 60000);
     void* fargs[] = {(void*)&G, (void*)&g->Cz, (void*)&slots, (void*)&F, (void*)&g->FT, (void*)&lambda, (void*)&tol2, (void*)&maxit_f};
     SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg_flow<148>, dim3(g->pcg_grid), dim3(PCGF_THREADS), fargs, g->pcgw_smem, s));
-  } else if (g->fast_ok)
-    SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg_fast, dim3(g->pcg_grid), dim3(PCGF_THREADS), args, g->pcgf_smem, s));
-  else
+  } else
     SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(g->pcg_grid), dim3(PCG_THREADS), args, g->pcg_smem, s));
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used + 1], s));
   g->ev_used += 2;
@@ -1152,6 +1142,13 @@ int ssb_graph_optimize_resident(ssb_graph* g, int max_iterations, ssb_lm_stats* 
   st.kernel_launches = g->launches - l0;
   if (stats) *stats = st;
   return 1;
+}
+
+// debug: globaltimer stamps of one k_pcg_flow iteration (only with -DSSB_FLOW_TRACE)
+int ssb_graph_debug_trace(ssb_graph* g, unsigned long long* out, int n) {
+  if (!g || !out || !g->d_trace.p) return SSB_ERR_INVALID;
+  SSB_CUDA_CHECK(cudaMemcpy(out, g->d_trace.p, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return SSB_OK;
 }
 
 // debug: cycle counters of k_pcg accumulated since prepare (only with -DSSB_PCG_TIMERS)

@@ -800,17 +800,17 @@ __device__ bool coarse_prologue(const DevGraph& G, const CoarseDev& Cz, BarSlot*
 // 3 grid-wide barriers per iteration, each fused with the all-reduce it needs; all reductions are
 // fixed-order => bit-reproducible for a fixed grid.
 //
-// k_pcg      : generic (any size; operands streamed from L2/HBM every iteration)
-// k_pcg_fast : on-chip resident variant for graphs that fit (<= 80 poses and <= 16 landmarks of degree
-//              <= 32 per CTA): Hpp/Dinv/B rows and the landmark blocks live in registers, HplP / Hoff
-//              rows in shared memory for the whole solve; only p, z and v travel through L2.
+// k_pcg      : generic (any size; operands streamed from L2/HBM every iteration; 3 grid barriers per iteration)
+// k_pcg_flow : (ssb_pcg_flow.cuh) on-chip resident data-flow variant for graphs that fit (<= 80 poses and
+//              <= 16 landmarks of degree <= 64 per CTA): Hpp/Dinv/B rows and the landmark blocks live in
+//              registers, HplP / Hoff rows in shared memory for the whole solve; single-reduction CG, tagged
+//              cells instead of grid barriers.
 // ---------------------------------------------------------------------------------------------
 constexpr int PCG_THREADS = 1024;
 constexpr int PCGF_THREADS = 512;
 constexpr int PCGF_MAXPL = 448;   // pose-landmark entries cached per CTA (fast path)
 constexpr int PCGF_MAXPP = 160;   // pose-pose incidences cached per CTA (fast path)
 constexpr int PCGF_MAXOV = 64;    // landmark edges beyond the first 32 of a landmark, per CTA (fast path)
-constexpr int PCGF_BIG = 18 * PCGF_MAXPL + 36 * PCGF_MAXPP + 18 * PCGF_MAXOV + (PCGF_MAXPL + PCGF_MAXPP + 2) / 2 + 80 * 36 + 16 * 36;
 
 // middle level applied to the residual of one warp's 5 poses: returns this lane's component of
 // P1 D1^-1 P1' r.  All 32 lanes must call (warp-uniform aggregate index `agg`).
@@ -1092,407 +1092,6 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     G.iscalars[1] = status;
     G.scalars[3] = rz;
     G.scalars[4] = rz0;
-  }
-}
-
-#define SSB_SUB_APPLY_FAST(RCOMP, ZC)                                                              \
-  if (use_sub) {                                                                                   \
-    double _r1[6];                                                                                 \
-    _Pragma("unroll") for (int k = 0; k < 6; ++k) _r1[k] = warp_sum(act ? b1row[k] * (RCOMP) : 0.0); \
-    double _z1 = 0.0;                                                                              \
-    if (lane < 6) {                                                                                \
-      _Pragma("unroll") for (int j = 0; j < 6; ++j) _z1 += d1_sh[36 * warp + 6 * lane + j] * _r1[j]; \
-    }                                                                                              \
-    _Pragma("unroll") for (int k = 0; k < 6; ++k) {                                                 \
-      const double _zk = __shfl_sync(0xffffffffu, _z1, k);                                         \
-      if (act) (ZC) += b1row[k] * _zk;                                                             \
-    }                                                                                              \
-  }
-
-// ------------------------------------- on-chip resident variant --------------------------------
-__global__ void __launch_bounds__(PCGF_THREADS, 1)
-    k_pcg_fast(DevGraph G, CoarseDev Cz, BarSlot* slots, double lambda, double tol2, int maxit) {
-  extern __shared__ __align__(16) double dsm[];
-  __shared__ double sh[33];
-  __shared__ double s6[8], zc6[8], red6[7 * 32];
-  const int nblk = gridDim.x;
-  const int nc = 6 * nblk;
-  double* part_sh = dsm;                  // [PCGF_THREADS]
-  double* Arow = part_sh + PCGF_THREADS;  // [6][nc]
-  double* rc = Arow + 6 * nc;             // [nc]
-  double* qc = rc + nc;                   // [nc]
-  double* red = qc + nc;                  // [14][36]
-  double* big = red + (PCGF_THREADS / 36) * 36;
-  // `big` is first the Gauss-Jordan panel [6][nc], afterwards the resident operands:
-  double* panel_sh = big;
-  double* plH = big;                                   // [PCGF_MAXPL][18]  HplP blocks of my poses (6x3)
-  double* ppH = plH + 18 * PCGF_MAXPL;                 // [PCGF_MAXPP][36]  Hoff blocks (as stored)
-  double* ovH = ppH + 36 * PCGF_MAXPP;                 // [PCGF_MAXOV][18]  HplL blocks of edges 32.. of a landmark
-  int* pl_lm = reinterpret_cast<int*>(ovH + 18 * PCGF_MAXOV);  // [PCGF_MAXPL]
-  int* pp_other = pl_lm + PCGF_MAXPL;                  // [PCGF_MAXPP] neighbour pose, role in bit 31
-  __shared__ int ovcnt[PCGF_THREADS / 32];
-  double* b1_sh = reinterpret_cast<double*>(pp_other + PCGF_MAXPP + (PCGF_MAXPP & 1));  // [80][36] middle-level prolongation rows
-  double* d1_sh = b1_sh + 80 * 36;                                               // [16][36] D1^-1 of my warps' aggregates
-  const bool use_sub = Cz.sub_enabled != 0;
-  const bool coarse = Cz.enabled != 0;
-
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int slot = lane / 6, comp = lane - 6 * slot;
-  const int base_lane = 6 * slot;
-  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np, p0 + Cz.C);
-  const int i = p0 + warp * 5 + slot;          // my pose (pose role)
-  const bool act = lane < 30 && i < p1;
-  const int l = warp * nblk + blockIdx.x;      // my landmark (landmark role), round-robin over CTAs
-  const bool lact = l < G.Nl;
-  unsigned epoch = 0;
-  double* pold = G.p0;
-  double* pnew = G.p1;
-  int status = 0;
-
-#ifdef SSB_PCG_TIMERS
-  long long tmr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long tlast = clock64();
-#define SSB_TICK(k)           \
-  do {                        \
-    long long _n = clock64(); \
-    tmr[k] += _n - tlast;     \
-    tlast = _n;               \
-  } while (0)
-#else
-#define SSB_TICK(k) \
-  do {              \
-  } while (0)
-#endif
-  bool use_coarse = false;
-  if (coarse) {
-    if (Cz.reuse_inverse) {
-      for (int k = threadIdx.x; k < 6 * nc; k += PCGF_THREADS) Arow[k] = Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k];
-      use_coarse = true;
-      __syncthreads();
-    } else {
-      use_coarse = coarse_prologue<PCGF_THREADS>(G, Cz, slots, epoch, lambda, Arow, panel_sh, red, part_sh, p0, p1);
-      if (use_coarse)
-        for (int k = threadIdx.x; k < 6 * nc; k += PCGF_THREADS) Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k] = Arow[k];
-    }
-  }
-
-  SSB_TICK(1);
-  // ---- load the resident operands ------------------------------------------------------------
-  double Hrow[6], Drow[6], Brow[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    Hrow[k] = act ? G.Hpp[36 * (size_t)i + 6 * comp + k] : 0.0;
-    Drow[k] = act ? G.Dinv[36 * (size_t)i + 6 * comp + k] : 0.0;
-    Brow[k] = (act && use_coarse) ? Cz.Bmat[36 * (size_t)i + 6 * comp + k] : 0.0;
-  }
-  Hrow[comp] += act ? lambda : 0.0;
-  const int plbase = G.pose_pl_rowptr[p0 < G.Np ? p0 : G.Np];
-  const int ppbase = G.pose_pp_rowptr[p0 < G.Np ? p0 : G.Np];
-  const int npl_blk = G.pose_pl_rowptr[p1 > p0 ? p1 : (p0 < G.Np ? p0 : G.Np)] - plbase;
-  const int npp_blk = G.pose_pp_rowptr[p1 > p0 ? p1 : (p0 < G.Np ? p0 : G.Np)] - ppbase;
-  for (int k = threadIdx.x; k < 18 * npl_blk; k += PCGF_THREADS) plH[k] = G.HplP[18 * (size_t)plbase + k];
-  for (int k = threadIdx.x; k < npl_blk; k += PCGF_THREADS) pl_lm[k] = G.plP_lm[plbase + k];
-  for (int k = threadIdx.x; k < npp_blk; k += PCGF_THREADS) {
-    const int code = G.pose_pp_idx[ppbase + k];
-    const int e = code >> 1, role = code & 1;
-    pp_other[k] = (role == 0 ? G.pp[e].j : G.pp[e].i) | (role << 31);
-    for (int m = 0; m < 36; ++m) ppH[36 * k + m] = G.Hoff[36 * (size_t)e + m];
-  }
-  if (use_sub) {
-    for (int k = threadIdx.x; k < 36 * (p1 - p0); k += PCGF_THREADS) b1_sh[k] = Cz.B1mat[36 * (size_t)p0 + k];
-    for (int k = threadIdx.x; k < 36 * (PCGF_THREADS / 32); k += PCGF_THREADS) {
-      const int agg = p0 / 5 + k / 36;
-      d1_sh[k] = (5 * agg < G.Np) ? Cz.D1inv[36 * (size_t)agg + (k % 36)] : 0.0;
-    }
-  }
-  const double* b1row = b1_sh + 36 * (warp * 5 + slot) + 6 * comp;
-  const int mypl0 = act ? G.pose_pl_rowptr[i] - plbase : 0, mypl1 = act ? G.pose_pl_rowptr[i + 1] - plbase : 0;
-  const int mypp0 = act ? G.pose_pp_rowptr[i] - ppbase : 0, mypp1 = act ? G.pose_pp_rowptr[i + 1] - ppbase : 0;
-  // landmark role: lane e of the warp owns edge e of landmark l
-  double HL[18];
-  int lpose = 0;
-  bool eact = false;
-  double Wi[6] = {0, 0, 0, 0, 0, 0};
-  if (lact) {
-    const int e0 = G.lm_rowptr[l], e1 = G.lm_rowptr[l + 1];
-    eact = e0 + lane < e1;
-    if (eact) {
-      lpose = G.pl[e0 + lane].p;
-#pragma unroll
-      for (int k = 0; k < 18; ++k) HL[k] = G.HplL[18 * (size_t)(e0 + lane) + k];
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) Wi[k] = G.HllInv[6 * (size_t)l + k];
-  }
-  if (!eact) {
-#pragma unroll
-    for (int k = 0; k < 18; ++k) HL[k] = 0.0;
-  }
-  // edges 32..63 of a landmark: second edge of the lane, block kept in shared memory
-  int nov = 0;
-  if (lact) nov = max(0, G.lm_rowptr[l + 1] - G.lm_rowptr[l] - 32);
-  if (lane == 0) ovcnt[warp] = nov;
-  __syncthreads();
-  int ovbase = 0;
-  for (int w = 0; w < warp; ++w) ovbase += ovcnt[w];
-  const bool eact2 = lane < nov;
-  int lpose2 = 0;
-  if (eact2) {
-    const int e = G.lm_rowptr[l] + 32 + lane;
-    lpose2 = G.pl[e].p;
-    for (int k = 0; k < 18; ++k) ovH[18 * (ovbase + lane) + k] = G.HplL[18 * (size_t)e + k];
-  }
-  const double* HL2 = ovH + 18 * (ovbase + lane);
-  __syncthreads();
-
-  // ---- init: x = 0, r = g, z = M^-1 r ------------------------------------------------------------
-  double xc = 0.0;
-  double rcomp = act ? G.g[6 * (size_t)i + comp] : 0.0;
-  double pold_c = 0.0, zc = 0.0, pc = 0.0, qv = 0.0;
-  double l6[6];
-  if (use_coarse) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) l6[k] = Brow[k] * rcomp;
-    block_sum6(l6, s6, red6);
-    grid_bar_sum(slots, epoch, 0.0, s6, rc, part_sh);
-    if (warp < 6) {
-      double t = 0.0;
-      for (int j = lane; j < nc; j += 32) t += Arow[warp * nc + j] * rc[j];
-      t = warp_sum(t);
-      if (lane == 0) zc6[warp] = t;
-    }
-    __syncthreads();
-  }
-  {
-    zc = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) zc += Drow[k] * __shfl_sync(0xffffffffu, rcomp, base_lane + k);
-    SSB_SUB_APPLY_FAST(rcomp, zc)
-    if (use_coarse) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) zc += Brow[k] * zc6[k];
-    }
-    if (act) {
-      G.z[6 * (size_t)i + comp] = zc;
-      pold[6 * (size_t)i + comp] = 0.0;
-    } else {
-      zc = 0.0;
-    }
-  }
-  double bs = block_sum(rcomp * zc, sh);
-  double rz = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh);
-  const double rz0 = rz;
-  double beta = 0.0;
-  int it = 0;
-  if (!(rz0 > 0.0)) {
-    status = (rz0 == 0.0) ? 0 : 2;
-    maxit = 0;
-  }
-  SSB_TICK(2);
-  for (it = 0; it < maxit; ++it) {
-    // ---- phase 1 (landmark role)
-    if (lact) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-      if (eact) {
-        const double2* zz = reinterpret_cast<const double2*>(G.z + 6 * (size_t)lpose);
-        const double2* po = reinterpret_cast<const double2*>(pold + 6 * (size_t)lpose);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const double2 zv = __ldcg(zz + c), pv = __ldcg(po + c);
-          const double pa = zv.x + beta * pv.x, pb = zv.y + beta * pv.y;
-          a0 += HL[2 * c] * pa + HL[2 * c + 1] * pb;
-          a1 += HL[6 + 2 * c] * pa + HL[6 + 2 * c + 1] * pb;
-          a2 += HL[12 + 2 * c] * pa + HL[12 + 2 * c + 1] * pb;
-        }
-      }
-      if (eact2) {
-        const double2* zz = reinterpret_cast<const double2*>(G.z + 6 * (size_t)lpose2);
-        const double2* po = reinterpret_cast<const double2*>(pold + 6 * (size_t)lpose2);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const double2 zv = __ldcg(zz + c), pv = __ldcg(po + c);
-          const double pa = zv.x + beta * pv.x, pb = zv.y + beta * pv.y;
-          a0 += HL2[2 * c] * pa + HL2[2 * c + 1] * pb;
-          a1 += HL2[6 + 2 * c] * pa + HL2[6 + 2 * c + 1] * pb;
-          a2 += HL2[12 + 2 * c] * pa + HL2[12 + 2 * c + 1] * pb;
-        }
-      }
-      a0 = warp_sum(a0);
-      a1 = warp_sum(a1);
-      a2 = warp_sum(a2);
-      if (lane == 0) {
-        G.v[3 * (size_t)l + 0] = Wi[0] * a0 + Wi[1] * a1 + Wi[2] * a2;
-        G.v[3 * (size_t)l + 1] = Wi[1] * a0 + Wi[3] * a1 + Wi[4] * a2;
-        G.v[3 * (size_t)l + 2] = Wi[2] * a0 + Wi[4] * a1 + Wi[5] * a2;
-      }
-    }
-    // own p (pose role) does not depend on phase 1: compute and publish before the barrier
-    pc = zc + beta * pold_c;
-    if (act) pnew[6 * (size_t)i + comp] = pc;
-    SSB_TICK(3);
-    grid_bar_sum(slots, epoch, 0.0, nullptr, nullptr, part_sh);
-    SSB_TICK(4);
-    // ---- phase 2 (pose role): all L2 loads of the phase are issued up front (one round trip)
-    double nb0 = 0.0, nb1 = 0.0;   // own component of the first two pose-pose neighbours' p
-    int role0 = 0, role1 = 0;
-    const bool has0 = mypp0 < mypp1, has1 = mypp0 + 1 < mypp1;
-    if (has0) {
-      const int code = pp_other[mypp0];
-      role0 = (code >> 31) & 1;
-      nb0 = __ldcg(pnew + 6 * (size_t)(code & 0x7fffffff) + comp);
-    }
-    if (has1) {
-      const int code = pp_other[mypp0 + 1];
-      role1 = (code >> 31) & 1;
-      nb1 = __ldcg(pnew + 6 * (size_t)(code & 0x7fffffff) + comp);
-    }
-    double vx[6], vy[6], vz[6];
-#pragma unroll
-    for (int u = 0; u < 6; ++u) {
-      const int kk = mypl0 + u;
-      if (kk < mypl1) {
-        const double* vv = G.v + 3 * (size_t)pl_lm[kk];
-        vx[u] = __ldcg(vv);
-        vy[u] = __ldcg(vv + 1);
-        vz[u] = __ldcg(vv + 2);
-      } else {
-        vx[u] = vy[u] = vz[u] = 0.0;
-      }
-    }
-    qv = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) qv += Hrow[k] * __shfl_sync(0xffffffffu, pc, base_lane + k);
-    {
-      const double* Ho0 = ppH + 36 * mypp0;
-      const double* Ho1 = Ho0 + 36;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double o0 = __shfl_sync(0xffffffffu, nb0, base_lane + k);
-        const double o1 = __shfl_sync(0xffffffffu, nb1, base_lane + k);
-        if (has0) qv += (role0 == 0 ? Ho0[6 * comp + k] : Ho0[6 * k + comp]) * o0;
-        if (has1) qv += (role1 == 0 ? Ho1[6 * comp + k] : Ho1[6 * k + comp]) * o1;
-      }
-      // further neighbours (loop closures): generic loop
-      int nmax = mypp1 - mypp0 - 2;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-      for (int s = 0; s < nmax; ++s) {
-        const bool has = mypp0 + 2 + s < mypp1;
-        double oc = 0.0;
-        int role = 0;
-        const double* Ho = ppH;
-        if (has) {
-          const int code = pp_other[mypp0 + 2 + s];
-          role = (code >> 31) & 1;
-          Ho = ppH + 36 * (mypp0 + 2 + s);
-          oc = __ldcg(pnew + 6 * (size_t)(code & 0x7fffffff) + comp);
-        }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          const double ok = __shfl_sync(0xffffffffu, oc, base_lane + k);
-          if (has) qv += (role == 0 ? Ho[6 * comp + k] : Ho[6 * k + comp]) * ok;
-        }
-      }
-    }
-    SSB_TICK(7);
-#pragma unroll
-    for (int u = 0; u < 6; ++u) {
-      const int kk = mypl0 + u;
-      if (kk < mypl1) {
-        const double* Hp = plH + 18 * kk + 3 * comp;
-        qv -= Hp[0] * vx[u] + Hp[1] * vy[u] + Hp[2] * vz[u];
-      }
-    }
-    for (int kb = mypl0 + 6; kb < mypl1; kb += 6) {
-#pragma unroll
-      for (int u = 0; u < 6; ++u) {
-        const int kk = kb + u;
-        if (kk < mypl1) {
-          const double* vv = G.v + 3 * (size_t)pl_lm[kk];
-          vx[u] = __ldcg(vv);
-          vy[u] = __ldcg(vv + 1);
-          vz[u] = __ldcg(vv + 2);
-        } else {
-          vx[u] = vy[u] = vz[u] = 0.0;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 6; ++u) {
-        const int kk = kb + u;
-        if (kk < mypl1) {
-          const double* Hp = plH + 18 * kk + 3 * comp;
-          qv -= Hp[0] * vx[u] + Hp[1] * vy[u] + Hp[2] * vz[u];
-        }
-      }
-    }
-    if (!act) qv = 0.0;
-    SSB_TICK(0);
-    if (use_coarse) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) l6[k] = Brow[k] * qv;
-      bs = block_sum7(pc * qv, l6, s6, red6);
-    } else {
-      bs = block_sum(pc * qv, sh);
-    }
-    SSB_TICK(5);
-    const double pq = grid_bar_sum(slots, epoch, bs, use_coarse ? s6 : nullptr, use_coarse ? qc : nullptr, part_sh);
-    if (!(pq > 0.0) || !isfinite(pq)) {
-      status = 1;
-      break;
-    }
-    const double alpha = rz / pq;
-    SSB_TICK(4);
-    // ---- phase 3
-    if (use_coarse) {
-      for (int j = threadIdx.x; j < nc; j += PCGF_THREADS) rc[j] -= alpha * qc[j];
-      __syncthreads();
-      if (warp < 6) {
-        double t = 0.0;
-        for (int j = lane; j < nc; j += 32) t += Arow[warp * nc + j] * rc[j];
-        t = warp_sum(t);
-        if (lane == 0) zc6[warp] = t;
-      }
-      __syncthreads();
-    }
-    xc += alpha * pc;
-    rcomp -= alpha * qv;
-    zc = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) zc += Drow[k] * __shfl_sync(0xffffffffu, rcomp, base_lane + k);
-    SSB_SUB_APPLY_FAST(rcomp, zc)
-    if (use_coarse) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) zc += Brow[k] * zc6[k];
-    }
-    if (act)
-      G.z[6 * (size_t)i + comp] = zc;
-    else
-      zc = 0.0;
-    pold_c = pc;
-    bs = block_sum(rcomp * zc, sh);
-    SSB_TICK(6);
-    const double rzn = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh);
-    SSB_TICK(4);
-    beta = rzn / rz;
-    rz = rzn;
-    double* t = pold;
-    pold = pnew;
-    pnew = t;
-    if (!(rz > tol2 * rz0)) {
-      ++it;
-      break;
-    }
-  }
-  if (act) G.x[6 * (size_t)i + comp] = xc;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    G.iscalars[0] = it;
-    G.iscalars[1] = status;
-    G.scalars[3] = rz;
-    G.scalars[4] = rz0;
-#ifdef SSB_PCG_TIMERS
-    for (int k = 0; k < 8; ++k) G.scalars[8 + k] += (double)tmr[k];
-#endif
   }
 }
 

@@ -1,8 +1,8 @@
-// ssb_pcg_flow.cuh — K3, data-flow variant of the on-chip resident Schur-complement PCG (sm_100a).
+// ssb_pcg_flow.cuh — K3, the on-chip resident Schur-complement PCG (sm_100a), data-flow synchronised.
 //
-// Same mapping and operands as k_pcg_fast (one persistent CTA per SM owning a contiguous keyframe
-// range; 6 lanes per pose, 5 poses per warp; one warp per landmark), but the iteration is restructured
-// so that it needs ONE global reduction and NO grid-wide barrier:
+// One persistent CTA per SM owns a contiguous keyframe range; 6 lanes per pose, 5 poses per warp; one warp
+// per landmark.  Hpp / Dinv / B rows and the landmark blocks live in registers, HplP / Hoff blocks in shared
+// memory for the whole solve.  The iteration needs ONE global reduction and NO grid-wide barrier:
 //
 //  * Chronopoulos-Gear recurrences (single-reduction preconditioned CG):
 //        w = S u,  gamma = r'u,  delta = w'u   (one fused all-reduce, + the 6 restricted values P'w per CTA)
@@ -33,6 +33,8 @@ struct FlowBufs {
   uint4* lines;   // [2][gridDim.x][8] per-CTA reduction lines, double buffered on the tag parity
   uint4* gj;      // [gridDim.x][36 gridDim.x + 8] Gauss-Jordan pivot panels of the coarse inversion, one per step
   unsigned tagbase;
+  double2* hlpark;  // [gridDim.x * warps][9][32] landmark-role blocks parked in L2 between iterations
+  unsigned long long* trace;  // debug (-DSSB_FLOW_TRACE): [gridDim.x][8] globaltimer stamps of one iteration
 };
 
 __device__ __forceinline__ void st_cell(uint4* c, double v, unsigned tag) {
@@ -47,6 +49,13 @@ __device__ __forceinline__ uint4 ld_cell(const uint4* c) {
 }
 __device__ __forceinline__ bool cell_ok(const uint4& u, unsigned tag) { return u.y == tag && u.w == tag; }
 __device__ __forceinline__ double cell_val(const uint4& u) { return __hiloint2double((int)u.z, (int)u.x); }
+
+// 6 consecutive doubles (16-byte aligned) from a shared-space byte address: 3 x LDS.128
+__device__ __forceinline__ void lds_row6(uint32_t addr, double* out) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(out[0]), "=d"(out[1]) : "r"(addr));
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(out[2]), "=d"(out[3]) : "r"(addr));
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+32];" : "=d"(out[4]), "=d"(out[5]) : "r"(addr));
+}
 
 // spin on one cell (the first attempt was already issued by the caller)
 __device__ __forceinline__ double cell_wait(const uint4* p, uint4 c, unsigned tag) {
@@ -134,7 +143,8 @@ constexpr int PCGW_MAXU = 320;    // distinct landmarks per CTA
 constexpr int PCGW_MAXPPE = 96;   // distinct pose-pose edges per CTA
 constexpr int PCGW_MAXEXT = 16;   // external neighbour poses per CTA
 constexpr int PCGW_POSES = 5 * (PCGF_THREADS / 32);
-constexpr int PCGW_INTS = PCGF_MAXPL + PCGW_MAXU + 2 * PCGF_MAXPP + PCGW_MAXEXT + PCGF_MAXOV;
+constexpr int PCGW_MAXSTAGE = 3 * PCGW_MAXU + 6 * PCGW_MAXEXT;   // cells staged into shared memory per iteration
+constexpr int PCGW_INTS = PCGF_MAXPL + PCGW_MAXSTAGE + 2 * PCGF_MAXPP + 6 * PCGF_MAXOV;
 constexpr int PCGW_BIG = 18 * PCGF_MAXPL + 36 * PCGW_MAXPPE + 18 * PCGF_MAXOV + 2 * PCGW_POSES * 36 + 3 * PCGW_MAXU +
                          6 * (PCGW_POSES + PCGW_MAXEXT) + (PCGW_INTS + 1) / 2;
 // dynamic shared memory of k_pcg_flow in doubles for a grid of nblk CTAs
@@ -302,17 +312,17 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   double* panel_sh = big;                              // Gauss-Jordan panel [6][nc], afterwards the resident operands:
   double* plH = big;                                   // [PCGF_MAXPL][18]  HplP blocks of my poses (6x3)
   double* ppH = plH + 18 * PCGF_MAXPL;                 // [PCGW_MAXPPE][36] Hoff blocks of the distinct edges
-  double* ovH = ppH + 36 * PCGW_MAXPPE;                // [PCGF_MAXOV][18]  HplL blocks of edges 32.. of a landmark
+  double* ovH = ppH + 36 * PCGW_MAXPPE;                // [6 PCGF_MAXOV][3] HplL columns of edges 32.. of a landmark, item order
   double* b1_sh = ovH + 18 * PCGF_MAXOV;               // [80][36] P1 rows
   double* m1_sh = b1_sh + PCGW_POSES * 36;             // [80][36] P1 D1^-1 rows
-  double* v_sh = m1_sh + PCGW_POSES * 36;              // [PCGW_MAXU][3]  staged v of the landmarks my poses see
-  double* u_sh = v_sh + 3 * PCGW_MAXU;                 // [80 + PCGW_MAXEXT][6] u of my poses and of external neighbours
-  int* pl_loc = reinterpret_cast<int*>(u_sh + 6 * (PCGW_POSES + PCGW_MAXEXT));  // [PCGF_MAXPL]
-  int* ulm = pl_loc + PCGF_MAXPL;                      // [PCGW_MAXU]
-  int* pp_loc = ulm + PCGW_MAXU;                       // [PCGF_MAXPP]
+  // u of my poses [80][6], then the staged cells of an iteration in one run: u of the external neighbours
+  // [next][6] followed by v of the landmarks my poses see [nuniq][3]
+  double* u_sh = m1_sh + PCGW_POSES * 36;
+  int* pl_loc = reinterpret_cast<int*>(u_sh + 6 * PCGW_POSES + PCGW_MAXSTAGE);  // [PCGF_MAXPL]
+  int* stage_src = pl_loc + PCGF_MAXPL;                // [PCGW_MAXSTAGE] cell index (u and v cells share one buffer)
+  int* pp_loc = stage_src + PCGW_MAXSTAGE;             // [PCGF_MAXPP]
   int* pp_src = pp_loc + PCGF_MAXPP;                   // [PCGF_MAXPP]
-  int* ext = pp_src + PCGF_MAXPP;                      // [PCGW_MAXEXT]
-  int* ov_pose = ext + PCGW_MAXEXT;                    // [PCGF_MAXOV]
+  int* ov_cell = pp_src + PCGF_MAXPP;                  // [6 PCGF_MAXOV] u cell of (edge, column) items 192.. of a landmark
   double* gam = part_sh;
   double* del = part_sh + PCGF_THREADS / 2;
   double* scratch8 = red;                  // [16][8]
@@ -371,13 +381,25 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   const int ext0 = T.ext_rowptr[blockIdx.x], next = T.ext_rowptr[blockIdx.x + 1] - ext0;
   for (int k = threadIdx.x; k < 18 * npl_blk; k += PCGF_THREADS) plH[k] = G.HplP[18 * (size_t)plbase + k];
   for (int k = threadIdx.x; k < npl_blk; k += PCGF_THREADS) pl_loc[k] = T.pl_loc[plbase + k];
-  for (int k = threadIdx.x; k < nuniq; k += PCGF_THREADS) ulm[k] = T.ulm[ulm0 + k];
+  const int nstage = 6 * next + 3 * nuniq;
+  const int voff = (int)(F.vcell - F.ucell);  // both live in one allocation
+  for (int q = threadIdx.x; q < nstage; q += PCGF_THREADS) {
+    if (q < 6 * next) {
+      const int xe = q / 6;
+      stage_src[q] = 6 * T.ext[ext0 + xe] + (q - 6 * xe);
+    } else {
+      const int qq = q - 6 * next, lu = qq / 3;
+      stage_src[q] = voff + 3 * T.ulm[ulm0 + lu] + (qq - 3 * lu);
+    }
+  }
+  double* const v_sh = u_sh + 6 * (PCGW_POSES + next);
   for (int k = threadIdx.x; k < npp_blk; k += PCGF_THREADS) {
     pp_loc[k] = T.pp_loc[ppbase + k];
     pp_src[k] = T.pp_src[ppbase + k];
   }
   for (int k = threadIdx.x; k < 36 * nupp; k += PCGF_THREADS) ppH[k] = G.Hoff[36 * (size_t)T.upp[upp0 + k / 36] + (k % 36)];
-  for (int k = threadIdx.x; k < next; k += PCGF_THREADS) ext[k] = T.ext[ext0 + k];
+  for (int k = threadIdx.x; k < 2 * 36 * PCGW_POSES; k += PCGF_THREADS) b1_sh[k] = 0.0;  // b1_sh and m1_sh (contiguous)
+  __syncthreads();
   if (use_sub) {
     // P1 rows and M1 = P1 D1^-1 rows of my poses (zero D1^-1 = level off for that aggregate)
     for (int k = threadIdx.x; k < 36 * (p1 - p0); k += PCGF_THREADS) {
@@ -391,14 +413,14 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       m1_sh[k] = t;
     }
   }
-  const double* b1row = b1_sh + 36 * (warp * 5 + slot) + 6 * comp;
-  const double* m1row = m1_sh + 36 * (warp * 5 + slot) + 6 * comp;
+  // shared-space byte address of my P1 row (lanes 30, 31 alias slot 0: their r is 0); the M1 row sits
+  // 36 * PCGW_POSES doubles further
+  const uint32_t b1addr = smem_u32(b1_sh + 36 * (warp * 5 + (lane < 30 ? slot : 0)) + 6 * (lane < 30 ? comp : 0));
   const int mypl0 = act ? G.pose_pl_rowptr[i] - plbase : 0, mypl1 = act ? G.pose_pl_rowptr[i + 1] - plbase : 0;
   const int mypp0 = act ? G.pose_pp_rowptr[i] - ppbase : 0, mypp1 = act ? G.pose_pp_rowptr[i + 1] - ppbase : 0;
   // landmark role.  The (edge, column) pairs of landmark l are dealt to the lanes in cell order:
   // item idx = 32 m + lane  ->  edge idx / 6, column idx % 6, so that one warp-wide load instruction reads
   // runs of 6 consecutive cells (one pose's u) instead of 32 scattered ones.
-  double HLc[6][3];
   int uoff[6];
   double Wr[3] = {0, 0, 0};  // lane k < 3: row k of W_l = (Hll + lambda I)^-1
   int deg = 0, le0 = 0;
@@ -413,18 +435,27 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       Wr[2] = lane == 0 ? Wu[2] : (lane == 1 ? Wu[4] : Wu[5]);
     }
   }
+  // The 18 block entries of a lane are only needed during phase A: they are parked in global memory (L2
+  // resident, [chunk][lane] so that the reload is coalesced) and re-read together with the u cells each
+  // iteration, which leaves the register file to the pose role during phases B..D.
+  double2* const park = F.hlpark + ((size_t)blockIdx.x * (PCGF_THREADS / 32) + warp) * 9 * 32 + lane;
+  {
+    double HLc[18];
 #pragma unroll
-  for (int m = 0; m < 6; ++m) {
-    const int idx = 32 * m + lane, edge = idx / 6, k = idx - 6 * edge;
-    if (edge < min(deg, 32)) {
-      uoff[m] = 6 * G.pl[le0 + edge].p + k;
+    for (int m = 0; m < 6; ++m) {
+      const int idx = 32 * m + lane, edge = idx / 6, k = idx - 6 * edge;
+      if (edge < min(deg, 32)) {
+        uoff[m] = 6 * G.pl[le0 + edge].p + k;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) HLc[m][r] = G.HplL[18 * (size_t)(le0 + edge) + 6 * r + k];
-    } else {
-      uoff[m] = -1;
+        for (int r = 0; r < 3; ++r) HLc[3 * m + r] = G.HplL[18 * (size_t)(le0 + edge) + 6 * r + k];
+      } else {
+        uoff[m] = -1;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) HLc[m][r] = 0.0;
+        for (int r = 0; r < 3; ++r) HLc[3 * m + r] = 0.0;
+      }
     }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) park[32 * c] = make_double2(HLc[2 * c], HLc[2 * c + 1]);
   }
   // edges 32..63 of a landmark: blocks and pose ids kept in shared memory
   const int nov = max(0, deg - 32);
@@ -432,10 +463,11 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   __syncthreads();
   int ovbase = 0;
   for (int w = 0; w < warp; ++w) ovbase += ovcnt[w];
-  if (lane < nov) {
-    const int e = le0 + 32 + lane;
-    ov_pose[ovbase + lane] = G.pl[e].p;
-    for (int k = 0; k < 18; ++k) ovH[18 * (ovbase + lane) + k] = G.HplL[18 * (size_t)e + k];
+  for (int idx = lane; idx < 6 * nov; idx += 32) {
+    const int edge = idx / 6, k = idx - 6 * edge, e = le0 + 32 + edge;
+    ov_cell[6 * ovbase + idx] = 6 * G.pl[e].p + k;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) ovH[3 * (6 * ovbase + idx) + r] = G.HplL[18 * (size_t)e + 6 * r + k];
   }
   __syncthreads();
 
@@ -467,15 +499,14 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     double _z = 0.0;                                                                                    \
     _Pragma("unroll") for (int k = 0; k < 6; ++k) _z += Drow[k] * __shfl_sync(0xffffffffu, rcomp, base_lane + k); \
     if (use_sub) {                                                                                      \
-      double _t[8];                                                                                     \
-      _Pragma("unroll") for (int k = 0; k < 6; ++k) _t[k] = act ? b1row[k] * rcomp : 0.0;                \
+      double _t[8], _b[6], _m[6];                                                                       \
+      lds_row6(b1addr, _b);                                                                             \
+      lds_row6(b1addr + 8u * 36u * PCGW_POSES, _m);                                                     \
+      _Pragma("unroll") for (int k = 0; k < 6; ++k) _t[k] = _b[k] * rcomp; /* r = 0 on inactive lanes */  \
       _t[6] = 0.0;                                                                                      \
       _t[7] = 0.0;                                                                                      \
       const double _r = warp_reduce8(_t); /* P1'r: value k in lanes 4k..4k+3 */                          \
-      _Pragma("unroll") for (int k = 0; k < 6; ++k) {                                                    \
-        const double _rk = __shfl_sync(0xffffffffu, _r, 4 * k);                                          \
-        if (act) _z += m1row[k] * _rk;                                                                   \
-      }                                                                                                 \
+      _Pragma("unroll") for (int k = 0; k < 6; ++k) _z += _m[k] * __shfl_sync(0xffffffffu, _r, 4 * k);    \
     }                                                                                                   \
     uc = act ? _z + cz : 0.0;                                                                           \
   }
@@ -498,15 +529,26 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     tmr[k] += _n - tlast;     \
     tlast = _n;               \
   } while (0)
+#elif defined(SSB_FLOW_TRACE)
+#define SSB_FTICK(k)                                                             \
+  do {                                                                           \
+    if (it == 40 && threadIdx.x == 0) {                                          \
+      unsigned long long _t;                                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                     \
+      F.trace[8 * blockIdx.x + (k)] = _t;                                        \
+    }                                                                            \
+  } while (0)
 #else
 #define SSB_FTICK(k) \
   do {               \
   } while (0)
 #endif
-  const int nstage = 3 * nuniq + 6 * next;   // cells staged into shared memory per iteration
   const int ngather = 8 * nblk;
   for (it = 0;; ++it) {
     const unsigned tg = tb + (unsigned)it + 1u;
+#ifdef SSB_FLOW_TRACE
+    SSB_FTICK(7);
+#endif
     // ---- A (landmark role): v = W_l sum_e HplL_e u_p(e) ------------------------------------------
     if (lact) {
       double a[4] = {0.0, 0.0, 0.0, 0.0};
@@ -514,36 +556,41 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
 #pragma unroll
       for (int m = 0; m < 6; ++m)
         if (uoff[m] >= 0) c[m] = ld_cell(F.ucell + uoff[m]);
+      double HLc[18];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        const double2 h = __ldcg(park + 32 * q);
+        HLc[2 * q] = h.x;
+        HLc[2 * q + 1] = h.y;
+      }
 #pragma unroll
       for (int m = 0; m < 6; ++m)
         if (uoff[m] >= 0) {
           const double uv = cell_wait(F.ucell + uoff[m], c[m], tg);
-          a[0] += HLc[m][0] * uv;
-          a[1] += HLc[m][1] * uv;
-          a[2] += HLc[m][2] * uv;
+          a[0] += HLc[3 * m] * uv;
+          a[1] += HLc[3 * m + 1] * uv;
+          a[2] += HLc[3 * m + 2] * uv;
         }
-      if (nov > 0) {  // warp-uniform: edges 32..63, same cell-order dealing, second batch of loads
-        const uint4* src[6];
+      if (nov > 0) {  // warp-uniform: edges 32..63, same item order, second batch of loads
+        int oc[6];
 #pragma unroll
         for (int m = 0; m < 6; ++m) {
-          const int idx = 32 * m + lane, edge = idx / 6;
-          src[m] = nullptr;
-          if (edge < nov) {
-            src[m] = F.ucell + 6 * (size_t)ov_pose[ovbase + edge] + (idx - 6 * edge);
-            c[m] = ld_cell(src[m]);
+          const int idx = 32 * m + lane;
+          oc[m] = -1;
+          if (idx < 6 * nov) {
+            oc[m] = ov_cell[6 * ovbase + idx];
+            c[m] = ld_cell(F.ucell + oc[m]);
           }
         }
 #pragma unroll
-        for (int m = 0; m < 6; ++m) {
-          const int idx = 32 * m + lane, edge = idx / 6;
-          if (edge < nov) {
-            const double uv = cell_wait(src[m], c[m], tg);
-            const double* H2 = ovH + 18 * (ovbase + edge) + (idx - 6 * edge);
+        for (int m = 0; m < 6; ++m)
+          if (oc[m] >= 0) {
+            const double uv = cell_wait(F.ucell + oc[m], c[m], tg);
+            const double* H2 = ovH + 3 * (6 * ovbase + 32 * m + lane);
             a[0] += H2[0] * uv;
-            a[1] += H2[6] * uv;
-            a[2] += H2[12] * uv;
+            a[1] += H2[1] * uv;
+            a[2] += H2[2] * uv;
           }
-        }
       }
       const double rsum = warp_reduce4(a);  // value j in lanes 8j..8j+7
       const double a0 = __shfl_sync(0xffffffffu, rsum, 0);
@@ -552,36 +599,22 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       if (lane < 3) st_cell(F.vcell + 3 * (size_t)l + lane, Wr[0] * a0 + Wr[1] * a1 + Wr[2] * a2, tg);
     }
     SSB_FTICK(0);
-    // ---- stage v of my poses' landmarks and u of external neighbours into shared memory --------------
+    // ---- stage u of external neighbours and v of my poses' landmarks into shared memory ----------------
     {
       uint4 c[3];
-      const uint4* src[3];
+      int sc_[3];
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
         const int q = threadIdx.x + PCGF_THREADS * m;
-        src[m] = nullptr;
+        sc_[m] = -1;
         if (q < nstage) {
-          if (q < 3 * nuniq) {
-            const int lu = q / 3;
-            src[m] = F.vcell + 3 * (size_t)ulm[lu] + (q - 3 * lu);
-          } else {
-            const int qq = q - 3 * nuniq, xe = qq / 6;
-            src[m] = F.ucell + 6 * (size_t)ext[xe] + (qq - 6 * xe);
-          }
-          c[m] = ld_cell(src[m]);
+          sc_[m] = stage_src[q];
+          c[m] = ld_cell(F.ucell + sc_[m]);
         }
       }
 #pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        const int q = threadIdx.x + PCGF_THREADS * m;
-        if (q < nstage) {
-          const double val = cell_wait(src[m], c[m], tg);
-          if (q < 3 * nuniq)
-            v_sh[q] = val;
-          else
-            u_sh[6 * PCGW_POSES + (q - 3 * nuniq)] = val;
-        }
-      }
+      for (int m = 0; m < 3; ++m)
+        if (sc_[m] >= 0) u_sh[6 * PCGW_POSES + threadIdx.x + PCGF_THREADS * m] = cell_wait(F.ucell + sc_[m], c[m], tg);
     }
     SSB_FTICK(1);
     __syncthreads();
@@ -702,14 +735,14 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     if (it >= maxit) break;
     // beta = gamma/gamma_old, alpha = gamma / (delta - beta*gamma/alpha_old) with one division on the
     // critical path (1/gamma is independent of it)
-    const double inv_gamma = 1.0 / gamma;
+    const double inv_gamma = fast_rcp(gamma);
     const double beta = (it == 0) ? 0.0 : gamma * inv_gamma_old;
     const double den = (it == 0) ? delta : delta - beta * gamma * inv_alpha;
     if (!(den > 0.0) || !isfinite(den)) {
       status = 1;
       break;
     }
-    const double alpha = gamma / den;
+    const double alpha = gamma * fast_rcp(den);
     inv_alpha = den * inv_gamma;
     inv_gamma_old = inv_gamma;
     // ---- D: recurrences and u = M^-1 r ----------------------------------------------------------------

@@ -57,10 +57,13 @@ __device__ __forceinline__ void lds_row6(uint32_t addr, double* out) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+32];" : "=d"(out[4]), "=d"(out[5]) : "r"(addr));
 }
 
+#ifndef SSB_POLL_NS
+#define SSB_POLL_NS 20   // back-off between polls of a cell that has not arrived (measured: see DESIGN.md)
+#endif
 // spin on one cell (the first attempt was already issued by the caller)
 __device__ __forceinline__ double cell_wait(const uint4* p, uint4 c, unsigned tag) {
   while (!cell_ok(c, tag)) {
-    __nanosleep(20);
+    __nanosleep(SSB_POLL_NS);
     c = ld_cell(p);
   }
   return cell_val(c);

@@ -79,6 +79,17 @@ int ssb_graph_add_se3_point_xyz_edge(ssb_graph* g, int v_se3, int v_xyz, const d
  * exists (not supported by the Schur back-end in this round). */
 int ssb_graph_add_point_xyz_point_xyz_edge(ssb_graph* g, int v1, int v2, const double xyz[3], const double info[9]);
 
+/* Plane landmarks: the API the reference keeps commented out — GraphSLAM::add_plane_node  graph_slam.hpp:44 /
+ * graph_slam.cpp:117-125 (g2o::VertexPlane, 3 DoF, estimate = 4 plane coefficients, normalised on entry like
+ * g2o::Plane3D) and GraphSLAM::add_se3_plane_edge  graph_slam.hpp:74-75 with the reference's own edge type
+ * g2o::EdgeSE3Plane  include/g2o/edge_se3_plane.hpp:8-48 (error = (X^-1 * plane).ominus(measurement) =
+ * (d azimuth, d elevation, d distance), information 3x3).  g2o differentiates this edge numerically; this
+ * back-end uses exact Jacobians.  Plane vertices are eliminated by the Schur step like point landmarks. */
+int ssb_graph_add_plane_node(ssb_graph* g, const double coeffs[4]);
+int ssb_graph_add_se3_plane_edge(ssb_graph* g, int v_se3, int v_plane, const double plane[4], const double info[9]);
+int ssb_graph_get_plane(ssb_graph* g, int vid, double coeffs[4]);
+int ssb_graph_set_plane(ssb_graph* g, int vid, const double coeffs[4]);
+
 int ssb_graph_num_vertices(const ssb_graph* g); /* graph->vertices().size() */
 int ssb_graph_num_edges(const ssb_graph* g);    /* graph->edges().size()    */
 
@@ -92,7 +103,8 @@ int ssb_graph_set_fixed(ssb_graph* g, int vid, int fixed);
 /* OptimizableGraph::Vertex::hessianIndex(): position among the non-fixed vertices in id order, -1 if
  * fixed (semantic_graph_slam.cpp:188-190).  Valid after an optimize call. */
 int ssb_graph_hessian_index(ssb_graph* g, int vid);
-/* bulk read-back: all SE3 estimates (12 doubles each, id order) and all XYZ estimates (3 each) */
+/* bulk read-back: all SE3 estimates (12 doubles each, id order) and all landmark estimates (3 each, id order;
+ * for a plane vertex its unit normal — use ssb_graph_get_plane for all 4 coefficients) */
 int ssb_graph_get_all(ssb_graph* g, double* se3_out, double* xyz_out);
 
 /* SparseOptimizer::chi2() at the current estimates (graph_slam.cpp:202,212) */
@@ -123,12 +135,12 @@ int ssb_graph_get_history(ssb_graph* g, double* out6n, int cap);
 int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* out9n);
 
 /* GraphSLAM::save  graph_slam.cpp:236-239 (g2o text format: VERTEX_SE3:QUAT, VERTEX_TRACKXYZ,
- * EDGE_SE3:QUAT, EDGE_SE3_TRACKXYZ, PARAMS_SE3OFFSET, FIX) and its inverse. */
+ * VERTEX_PLANE, EDGE_SE3:QUAT, EDGE_SE3_TRACKXYZ, EDGE_SE3_PLANE, PARAMS_SE3OFFSET, FIX) and its inverse. */
 int ssb_graph_save_g2o(ssb_graph* g, const char* path);
 int ssb_graph_load_g2o(ssb_graph* g, const char* path);
 
 /* test hook: device linearisation of edge `eid` at the current estimates.  err[D], Ji[D*di], Jj[D*dj]
- * row-major with (D,di,dj) = (6,6,6) for SE3 edges and (3,6,3) for SE3-XYZ edges. */
+ * row-major with (D,di,dj) = (6,6,6) for SE3 edges and (3,6,3) for SE3-XYZ and SE3-plane edges. */
 int ssb_graph_edge_linearize(ssb_graph* g, int eid, double* err, double* Ji, double* Jj);
 /* test hook: solve (H + lambda I) x = b once at the current linearisation with the Schur/PCG device
  * path; x is returned in hessian-index order (6 per SE3, 3 per XYZ vertex).  Returns PCG iterations. */

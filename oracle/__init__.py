@@ -42,6 +42,11 @@ def lib():
         L.orc_graph_add_se3_edge.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
         L.orc_graph_add_se3_point_xyz_edge.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
         L.orc_graph_add_point_xyz_point_xyz_edge.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
+        L.orc_graph_add_plane_node.argtypes = [C.c_void_p, _dp]
+        L.orc_graph_add_se3_plane_edge.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
+        L.orc_graph_get_plane.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.orc_graph_set_plane.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.orc_plane_oplus.argtypes = [_dp, _dp]
         L.orc_graph_num_vertices.argtypes = [C.c_void_p]
         L.orc_graph_num_edges.argtypes = [C.c_void_p]
         L.orc_graph_get_se3.argtypes = [C.c_void_p, C.c_int, _dp]
@@ -148,6 +153,29 @@ class OracleGraphSLAM:
     def chi2(self) -> float:
         return self._L.orc_graph_chi2(self._h)
 
+    # dormant plane API of the reference (graph_slam.hpp:44,74-75; include/g2o/edge_se3_plane.hpp)
+    def add_plane_node(self, plane_coeffs):
+        a, p = _d(plane_coeffs)
+        return self._L.orc_graph_add_plane_node(self._h, p)
+
+    def add_se3_plane_edge(self, v_se3, v_plane, plane_coeffs, information):
+        a, p = _d(plane_coeffs)
+        b, q = _d(information)
+        r = self._L.orc_graph_add_se3_plane_edge(self._h, v_se3, v_plane, p, q)
+        if r < 0:
+            raise ValueError("bad vertex ids")
+        return r
+
+    def get_plane(self, vid):
+        out = np.zeros(4)
+        if self._L.orc_graph_get_plane(self._h, vid, out.ctypes.data_as(_dp)) != 0:
+            raise ValueError("not a plane vertex")
+        return out
+
+    def set_plane(self, vid, c):
+        a, p = _d(c)
+        self._L.orc_graph_set_plane(self._h, vid, p)
+
     def get_se3(self, vid):
         out = np.zeros((3, 4))
         if self._L.orc_graph_get_se3(self._h, vid, out.ctypes.data_as(_dp)) != 0:
@@ -243,6 +271,14 @@ def from_vector_mqt(v):
     T = np.zeros((3, 4))
     lib().orc_from_vector_mqt(p, T.ctypes.data_as(_dp))
     return T
+
+
+def plane_oplus(c4, v3):
+    """g2o::Plane3D::oplus"""
+    c = np.array(c4, dtype=np.float64).copy()
+    v = np.ascontiguousarray(v3, dtype=np.float64)
+    lib().orc_plane_oplus(c.ctypes.data_as(_dp), v.ctypes.data_as(_dp))
+    return c
 
 
 def se3_oplus(T, v):

@@ -238,8 +238,8 @@ static inline void skew2(const double* t, double* S) {
 // ------------------------------------------------------------------------------------------
 // Graph containers
 // ------------------------------------------------------------------------------------------
-enum VKind { V_SE3 = 0, V_XYZ = 1 };
-enum EKind { E_SE3 = 0, E_SE3_XYZ = 1, E_XYZ_XYZ = 2 };
+enum VKind { V_SE3 = 0, V_XYZ = 1, V_PLANE = 2 };
+enum EKind { E_SE3 = 0, E_SE3_XYZ = 1, E_XYZ_XYZ = 2, E_SE3_PLANE = 3 };
 
 struct Vertex {
   int kind;
@@ -247,7 +247,7 @@ struct Vertex {
   int hidx;        // hessian (block) index, -1 if fixed
   int num_oplus;   // VertexSE3::_numOplusCalls
   Iso T;           // SE3 estimate
-  double p[3];     // XYZ estimate
+  double p[4];     // XYZ estimate, or the 4 normalised plane coefficients (V_PLANE)
   std::vector<Iso> stackT;
   std::vector<double> stackP;
   int dim() const { return kind == V_SE3 ? 6 : 3; }
@@ -257,7 +257,7 @@ struct Edge {
   int kind;
   int vi, vj;
   Iso Z, Zinv;       // E_SE3 measurement
-  double z[3];       // E_SE3_XYZ / E_XYZ_XYZ measurement
+  double z[4];       // E_SE3_XYZ / E_XYZ_XYZ measurement, or the measured plane (E_SE3_PLANE)
   double info[36];   // row-major DxD
   int D() const { return kind == E_SE3 ? 6 : 3; }
 };
@@ -381,6 +381,74 @@ static void edge_xyz_xyz_error(const Edge& e, const double* pi, const double* pj
   for (int i = 0; i < 3; ++i) err[i] = (pj[i] - pi[i]) - e.z[i];
 }
 
+// ---- g2o::Plane3D (types/slam3d_addons/plane3d.h) and EdgeSE3Plane
+// (/root/reference/include/g2o/edge_se3_plane.hpp:8-48, dormant in the reference) ----
+static inline void plane_normalize(double* c) {
+  const double n = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  for (int i = 0; i < 4; ++i) c[i] /= n;
+}
+// Plane3D::rotation(v) = AngleAxis(azimuth, Z) * AngleAxis(-elevation, Y)
+static inline void plane_rotation(const double* v, double* R) {
+  const double az = std::atan2(v[1], v[0]);
+  const double el = std::atan2(v[2], std::sqrt(v[0] * v[0] + v[1] * v[1]));
+  const double ca = std::cos(az), sa = std::sin(az), ce = std::cos(el), se = std::sin(el);
+  R[0] = ca * ce; R[1] = -sa; R[2] = -ca * se;
+  R[3] = sa * ce; R[4] = ca;  R[5] = -sa * se;
+  R[6] = se;      R[7] = 0.0; R[8] = ce;
+}
+// Plane3D::oplus
+static inline void plane_oplus(double* c, const double* v) {
+  const double s = std::sin(v[1]), co = std::cos(v[1]);
+  const double n[3] = {co * std::cos(v[0]), co * std::sin(v[0]), s};
+  double R[9], rn[3];
+  plane_rotation(c, R);
+  const double d = -c[3] + v[2];
+  mat3_vec(R, n, rn);
+  c[0] = rn[0]; c[1] = rn[1]; c[2] = rn[2];
+  c[3] = -d;
+  plane_normalize(c);
+}
+// EdgeSE3Plane::computeError: local = X^-1 * plane ; error = local.ominus(measurement)
+static void edge_se3_plane_error(const Edge& e, const Iso& X, const double* pl, double* err) {
+  Iso w2n = iso_inv(X);
+  double v2[4];
+  mat3_vec(w2n.R, pl, v2);
+  v2[3] = pl[3] - (w2n.t[0] * v2[0] + w2n.t[1] * v2[1] + w2n.t[2] * v2[2]);
+  plane_normalize(v2);  // Plane3D(v2)
+  double R[9], Rt[9], n[3];
+  plane_rotation(v2, R);
+  mat3_T(R, Rt);
+  mat3_vec(Rt, e.z, n);
+  err[0] = std::atan2(n[1], n[0]);
+  err[1] = std::atan2(n[2], std::sqrt(n[0] * n[0] + n[1] * n[1]));
+  err[2] = (-v2[3]) - (-e.z[3]);
+}
+// BaseBinaryEdge::linearizeOplus (numeric, central differences, delta = 1e-9) as g2o does for an edge
+// that does not override it
+static void edge_se3_plane_jac(const Edge& e, const Iso& X, const double* pl, double* Ji, double* Jj) {
+  const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+  for (int d = 0; d < 6; ++d) {
+    double add[6] = {0, 0, 0, 0, 0, 0}, e1[3], e2[3];
+    add[d] = delta;
+    edge_se3_plane_error(e, iso_mul(X, from_vector_mqt(add)), pl, e1);
+    add[d] = -delta;
+    edge_se3_plane_error(e, iso_mul(X, from_vector_mqt(add)), pl, e2);
+    for (int r = 0; r < 3; ++r) Ji[6 * r + d] = scalar * (e1[r] - e2[r]);
+  }
+  for (int d = 0; d < 3; ++d) {
+    double add[3] = {0, 0, 0}, e1[3], e2[3], q[4];
+    add[d] = delta;
+    std::memcpy(q, pl, sizeof(q));
+    plane_oplus(q, add);
+    edge_se3_plane_error(e, X, q, e1);
+    add[d] = -delta;
+    std::memcpy(q, pl, sizeof(q));
+    plane_oplus(q, add);
+    edge_se3_plane_error(e, X, q, e2);
+    for (int r = 0; r < 3; ++r) Jj[3 * r + d] = scalar * (e1[r] - e2[r]);
+  }
+}
+
 static void edge_error(const Graph& g, const Edge& e, double* err) {
   const Vertex& a = g.V[e.vi];
   const Vertex& b = g.V[e.vj];
@@ -388,6 +456,8 @@ static void edge_error(const Graph& g, const Edge& e, double* err) {
     edge_se3_error(e, a.T, b.T, err);
   else if (e.kind == E_SE3_XYZ)
     edge_se3_xyz_error(e, a.T, b.p, err);
+  else if (e.kind == E_SE3_PLANE)
+    edge_se3_plane_error(e, a.T, b.p, err);
   else
     edge_xyz_xyz_error(e, a.p, b.p, err);
 }
@@ -398,6 +468,8 @@ static void edge_jac(const Graph& g, const Edge& e, double* Ji, double* Jj) {
     edge_se3_jac(e, a.T, b.T, Ji, Jj);
   else if (e.kind == E_SE3_XYZ)
     edge_se3_xyz_jac(e, a.T, b.p, Ji, Jj);
+  else if (e.kind == E_SE3_PLANE)
+    edge_se3_plane_jac(e, a.T, b.p, Ji, Jj);
   else {
     std::memset(Ji, 0, 9 * sizeof(double));
     std::memset(Jj, 0, 9 * sizeof(double));
@@ -865,6 +937,8 @@ static void vertex_oplus(Vertex& v, const double* upd) {
       v.num_oplus = 0;
       approx_nearest_orthogonal(v.T.R);
     }
+  } else if (v.kind == V_PLANE) {
+    plane_oplus(v.p, upd);   // VertexPlane::oplusImpl
   } else {
     for (int i = 0; i < 3; ++i) v.p[i] += upd[i];
   }
@@ -875,9 +949,7 @@ static void graph_push(Graph& g) {
     if (v.kind == V_SE3)
       v.stackT.push_back(v.T);
     else {
-      v.stackP.push_back(v.p[0]);
-      v.stackP.push_back(v.p[1]);
-      v.stackP.push_back(v.p[2]);
+      for (int i = 0; i < 4; ++i) v.stackP.push_back(v.p[i]);
     }
   }
 }
@@ -889,10 +961,8 @@ static void graph_pop(Graph& g) {
       v.stackT.pop_back();
     } else {
       size_t n = v.stackP.size();
-      v.p[0] = v.stackP[n - 3];
-      v.p[1] = v.stackP[n - 2];
-      v.p[2] = v.stackP[n - 1];
-      v.stackP.resize(n - 3);
+      for (int i = 0; i < 4; ++i) v.p[i] = v.stackP[n - 4 + i];
+      v.stackP.resize(n - 4);
     }
   }
 }
@@ -902,7 +972,7 @@ static void graph_discard_top(Graph& g) {
     if (v.kind == V_SE3)
       v.stackT.pop_back();
     else
-      v.stackP.resize(v.stackP.size() - 3);
+      v.stackP.resize(v.stackP.size() - 4);
   }
 }
 
@@ -1033,7 +1103,7 @@ int orc_graph_add_se3_node(void* h, const double* T) {
   v.hidx = -1;
   v.num_oplus = 0;
   v.T = iso_from_3x4(T);
-  v.p[0] = v.p[1] = v.p[2] = 0;
+  v.p[0] = v.p[1] = v.p[2] = v.p[3] = 0;
   g.V.push_back(v);
   return (int)g.V.size() - 1;
 }
@@ -1048,6 +1118,7 @@ int orc_graph_add_point_xyz_node(void* h, const double* p) {
   v.p[0] = p[0];
   v.p[1] = p[1];
   v.p[2] = p[2];
+  v.p[3] = 0;
   g.V.push_back(v);
   return (int)g.V.size() - 1;
 }
@@ -1109,6 +1180,50 @@ int orc_graph_set_se3(void* h, int id, const double* T) {
   g.V[id].T = iso_from_3x4(T);
   return 0;
 }
+// commented-out API of the reference (graph_slam.hpp:44,74-75): VertexPlane / EdgeSE3Plane
+int orc_graph_add_plane_node(void* h, const double* c4) {
+  Graph& g = *(Graph*)h;
+  Vertex v;
+  v.kind = V_PLANE;
+  v.fixed = false;
+  v.hidx = -1;
+  v.num_oplus = 0;
+  v.T = iso_identity();
+  std::memcpy(v.p, c4, 4 * sizeof(double));
+  plane_normalize(v.p);  // Plane3D(const Vector4D&)
+  g.V.push_back(v);
+  return (int)g.V.size() - 1;
+}
+int orc_graph_add_se3_plane_edge(void* h, int vp, int vl, const double* plane4, const double* info9) {
+  Graph& g = *(Graph*)h;
+  if (!check_v(g, vp, V_SE3) || !check_v(g, vl, V_PLANE)) return -1;
+  Edge e;
+  e.kind = E_SE3_PLANE;
+  e.vi = vp;
+  e.vj = vl;
+  e.Z = e.Zinv = iso_identity();
+  std::memcpy(e.z, plane4, 4 * sizeof(double));
+  plane_normalize(e.z);  // setMeasurement(Plane3D(v))
+  std::memset(e.info, 0, sizeof(e.info));
+  std::memcpy(e.info, info9, 9 * sizeof(double));
+  g.E.push_back(e);
+  return (int)g.E.size() - 1;
+}
+int orc_graph_get_plane(void* h, int id, double* c4) {
+  Graph& g = *(Graph*)h;
+  if (!check_v(g, id, V_PLANE)) return -1;
+  std::memcpy(c4, g.V[id].p, 4 * sizeof(double));
+  return 0;
+}
+int orc_graph_set_plane(void* h, int id, const double* c4) {
+  Graph& g = *(Graph*)h;
+  if (!check_v(g, id, V_PLANE)) return -1;
+  std::memcpy(g.V[id].p, c4, 4 * sizeof(double));
+  plane_normalize(g.V[id].p);
+  return 0;
+}
+void orc_plane_oplus(double* c4, const double* v3) { plane_oplus(c4, v3); }
+
 int orc_graph_get_point_xyz(void* h, int id, double* p) {
   Graph& g = *(Graph*)h;
   if (!check_v(g, id, V_XYZ)) return -1;

@@ -50,7 +50,8 @@ def build(verbose: bool = False) -> str:
 SYMBOLS = [
     "ssb_graph_default_opts", "ssb_graph_create", "ssb_graph_destroy", "ssb_graph_add_se3_node",
     "ssb_graph_add_point_xyz_node", "ssb_graph_add_se3_edge", "ssb_graph_add_se3_point_xyz_edge",
-    "ssb_graph_add_point_xyz_point_xyz_edge", "ssb_graph_num_vertices", "ssb_graph_num_edges", "ssb_graph_get_se3",
+    "ssb_graph_add_point_xyz_point_xyz_edge", "ssb_graph_add_plane_node", "ssb_graph_add_se3_plane_edge",
+    "ssb_graph_get_plane", "ssb_graph_set_plane", "ssb_graph_num_vertices", "ssb_graph_num_edges", "ssb_graph_get_se3",
     "ssb_graph_get_point_xyz", "ssb_graph_set_se3", "ssb_graph_set_point_xyz", "ssb_graph_set_fixed",
     "ssb_graph_hessian_index", "ssb_graph_get_all", "ssb_graph_set_all", "ssb_graph_invalidate", "ssb_graph_chi2",
     "ssb_graph_prepare", "ssb_graph_optimize", "ssb_graph_optimize_resident", "ssb_graph_get_history",
@@ -82,6 +83,10 @@ def lib():
     L.ssb_graph_add_se3_edge.argtypes = [vp, C.c_int, C.c_int, dp, dp]
     L.ssb_graph_add_se3_point_xyz_edge.argtypes = [vp, C.c_int, C.c_int, dp, dp]
     L.ssb_graph_add_point_xyz_point_xyz_edge.argtypes = [vp, C.c_int, C.c_int, dp, dp]
+    L.ssb_graph_add_plane_node.argtypes = [vp, dp]
+    L.ssb_graph_add_se3_plane_edge.argtypes = [vp, C.c_int, C.c_int, dp, dp]
+    L.ssb_graph_get_plane.argtypes = [vp, C.c_int, dp]
+    L.ssb_graph_set_plane.argtypes = [vp, C.c_int, dp]
     L.ssb_graph_num_vertices.argtypes = [vp]
     L.ssb_graph_num_edges.argtypes = [vp]
     L.ssb_graph_get_se3.argtypes = [vp, C.c_int, dp]

@@ -110,7 +110,7 @@ static inline double wall_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-enum { VK_SE3 = 0, VK_XYZ = 1 };
+enum { VK_SE3 = 0, VK_XYZ = 1, VK_PLANE = 2 };
 enum { EK_PP = 0, EK_PL = 1, EK_LL = 2 };
 
 struct HostVertex {
@@ -139,7 +139,10 @@ struct ssb_graph {
   std::vector<HostVertex> V;
   std::vector<HostEdgeRef> E;
   std::vector<Pose> poses;      // estimates, pose index order
-  std::vector<double> lms;      // 4 per landmark
+  std::vector<double> lms;      // 4 per landmark vertex: xyz + pad, or the 4 normalised plane coefficients
+  std::vector<unsigned char> lm_kind;  // per landmark vertex: 0 = VertexPointXYZ, 1 = VertexPlane
+  std::vector<double> pl_zd;    // per pose-landmark edge (creation order): 4th coefficient of a measured plane
+  int n_plane_vertices = 0;
   std::vector<int> pose_vid, lm_vid;
   std::vector<PPEdge> pp;       // creation order
   std::vector<PLEdge> pl;       // creation order (host); device copy is L-order
@@ -161,7 +164,8 @@ struct ssb_graph {
   // device buffers
   DBuf<Pose> d_pose, d_pose_bak, d_pose_snap;
   DBuf<double> d_lm, d_lm_bak, d_lm_snap;
-  DBuf<unsigned char> d_pose_fixed, d_lm_fixed;
+  DBuf<unsigned char> d_pose_fixed, d_lm_fixed, d_lm_kind;
+  DBuf<double> d_pl_zd;
   DBuf<PLEdge> d_pl;
   DBuf<PPEdge> d_pp;
   DBuf<int> d_lm_rowptr, d_pose_pl_rowptr, d_pose_pl_idx, d_pose_pp_rowptr, d_pose_pp_idx, d_plP_lm;
@@ -355,6 +359,7 @@ int ssb_graph_add_point_xyz_node(ssb_graph* g, const double xyz[3]) {
   g->lms.push_back(xyz[1]);
   g->lms.push_back(xyz[2]);
   g->lms.push_back(0.0);
+  g->lm_kind.push_back(0);
   g->lm_vid.push_back((int)g->V.size());
   g->V.push_back(v);
   g->structure_dirty = true;
@@ -399,6 +404,7 @@ int ssb_graph_add_se3_point_xyz_edge(ssb_graph* g, int v_se3, int v_xyz, const d
   e.info[4] = 0.5 * (info[5] + info[7]);
   e.info[5] = info[8];
   g->pl.push_back(e);
+  g->pl_zd.push_back(0.0);
   g->E.push_back({EK_PL, (int)g->pl.size() - 1});
   g->structure_dirty = true;
   return (int)g->E.size() - 1;
@@ -416,6 +422,62 @@ int ssb_graph_add_point_xyz_point_xyz_edge(ssb_graph* g, int v1, int v2, const d
   std::memcpy(e.info, info, sizeof(e.info));
   g->ll.push_back(e);
   g->E.push_back({EK_LL, (int)g->ll.size() - 1});
+  g->structure_dirty = true;
+  return (int)g->E.size() - 1;
+}
+
+// VertexPlane / EdgeSE3Plane: the plane API the reference keeps commented out (graph_slam.hpp:44,74-75,
+// graph_slam.cpp:117-125) with its own edge type include/g2o/edge_se3_plane.hpp.  A plane vertex is a 3-DoF
+// landmark for the Schur back-end, exactly like a point landmark.
+int ssb_graph_add_plane_node(ssb_graph* g, const double coeffs[4]) {
+  if (!g || !coeffs) return SSB_ERR_INVALID;
+  if (sync_estimates_to_host(g) != SSB_OK) return SSB_ERR_CUDA;
+  double c[4] = {coeffs[0], coeffs[1], coeffs[2], coeffs[3]};
+  const double n = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  if (!(n > 0.0) || !std::isfinite(n)) {
+    set_error("add_plane_node: degenerate plane normal");
+    return SSB_ERR_INVALID;
+  }
+  plane_normalize(c);  // Plane3D(const Vector4D&)
+  HostVertex v;
+  v.kind = VK_PLANE;
+  v.idx = (int)(g->lms.size() / 4);
+  v.fixed = false;
+  v.hidx = -1;
+  for (int k = 0; k < 4; ++k) g->lms.push_back(c[k]);
+  g->lm_kind.push_back(1);
+  g->n_plane_vertices++;
+  g->lm_vid.push_back((int)g->V.size());
+  g->V.push_back(v);
+  g->structure_dirty = true;
+  return (int)g->V.size() - 1;
+}
+
+int ssb_graph_add_se3_plane_edge(ssb_graph* g, int v_se3, int v_plane, const double plane[4], const double info[9]) {
+  if (!g || !plane || !info || !check_vertex(g, v_se3, VK_SE3) || !check_vertex(g, v_plane, VK_PLANE)) {
+    set_error("add_se3_plane_edge: invalid vertex ids %d, %d", v_se3, v_plane);
+    return SSB_ERR_INVALID;
+  }
+  double c[4] = {plane[0], plane[1], plane[2], plane[3]};
+  const double n = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  if (!(n > 0.0) || !std::isfinite(n)) {
+    set_error("add_se3_plane_edge: degenerate plane normal");
+    return SSB_ERR_INVALID;
+  }
+  plane_normalize(c);  // setMeasurement(Plane3D(v))
+  PLEdge e;
+  e.p = g->V[v_se3].idx;
+  e.l = g->V[v_plane].idx;
+  for (int k = 0; k < 3; ++k) e.z[k] = c[k];
+  e.info[0] = info[0];
+  e.info[1] = 0.5 * (info[1] + info[3]);
+  e.info[2] = 0.5 * (info[2] + info[6]);
+  e.info[3] = info[4];
+  e.info[4] = 0.5 * (info[5] + info[7]);
+  e.info[5] = info[8];
+  g->pl.push_back(e);
+  g->pl_zd.push_back(c[3]);
+  g->E.push_back({EK_PL, (int)g->pl.size() - 1});
   g->structure_dirty = true;
   return (int)g->E.size() - 1;
 }
@@ -471,6 +533,7 @@ static int prepare(ssb_graph* g) {
     for (auto& e : g->pl) lm_rowptr[e.l + 1]++;
     for (int l = 0; l < Nl; ++l) lm_rowptr[l + 1] += lm_rowptr[l];
     std::vector<PLEdge> plL(std::max(El, 1));
+    std::vector<double> zdL(std::max(El, 1), 0.0);
     g->plL_of_edge.assign(El, 0);
     {
       // L-order: by landmark, then by pose index, then by creation order
@@ -483,6 +546,7 @@ static int prepare(ssb_graph* g) {
       });
       for (int pos = 0; pos < El; ++pos) {
         plL[pos] = g->pl[ord[pos]];
+        zdL[pos] = g->pl_zd[ord[pos]];
         g->plL_of_edge[ord[pos]] = pos;
       }
     }
@@ -541,6 +605,10 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_lm_bak.ensure((size_t)4 * Nl));
     SSB_TRY(g->d_pose_fixed.ensure(Np));
     SSB_TRY(g->d_lm_fixed.ensure(Nl));
+    if (g->n_plane_vertices) {
+      SSB_TRY(g->d_lm_kind.ensure(Nl));
+      SSB_TRY(g->d_pl_zd.ensure(El));
+    }
     SSB_TRY(g->d_pl.ensure(El));
     SSB_TRY(g->d_pp.ensure(Epp));
     SSB_TRY(g->d_lm_rowptr.ensure(Nl + 1));
@@ -719,6 +787,10 @@ static int prepare(ssb_graph* g) {
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_iscalars.p, 0, 4 * sizeof(int), s));
     if (Np) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_fixed.p, pfix.data(), Np, cudaMemcpyHostToDevice, s));
     if (Nl) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_fixed.p, lfix.data(), Nl, cudaMemcpyHostToDevice, s));
+    if (g->n_plane_vertices) {
+      SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_kind.p, g->lm_kind.data(), Nl, cudaMemcpyHostToDevice, s));
+      if (El) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pl_zd.p, zdL.data(), (size_t)El * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
     if (El) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pl.p, plL.data(), (size_t)El * sizeof(PLEdge), cudaMemcpyHostToDevice, s));
     if (Epp) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pp.p, g->pp.data(), (size_t)Epp * sizeof(PPEdge), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_rowptr.p, lm_rowptr.data(), (Nl + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -744,6 +816,8 @@ static int prepare(ssb_graph* g) {
     G.lm = g->d_lm.p;
     G.pose_fixed = g->d_pose_fixed.p;
     G.lm_fixed = g->d_lm_fixed.p;
+    G.lm_kind = g->n_plane_vertices ? g->d_lm_kind.p : nullptr;
+    G.pl_zd = g->n_plane_vertices ? g->d_pl_zd.p : nullptr;
     G.pl = g->d_pl.p;
     G.pp = g->d_pp.p;
     G.lm_rowptr = g->d_lm_rowptr.p;
@@ -1195,6 +1269,21 @@ int ssb_graph_set_se3(ssb_graph* g, int vid, const double T34[12]) {
   g->host_est_dirty = true;
   return SSB_OK;
 }
+int ssb_graph_get_plane(ssb_graph* g, int vid, double coeffs[4]) {
+  if (!check_vertex(g, vid, VK_PLANE) || !coeffs) return SSB_ERR_INVALID;
+  SSB_TRY(sync_estimates_to_host(g));
+  std::memcpy(coeffs, &g->lms[4 * (size_t)g->V[vid].idx], 4 * sizeof(double));
+  return SSB_OK;
+}
+int ssb_graph_set_plane(ssb_graph* g, int vid, const double coeffs[4]) {
+  if (!check_vertex(g, vid, VK_PLANE) || !coeffs) return SSB_ERR_INVALID;
+  SSB_TRY(sync_estimates_to_host(g));
+  double c[4] = {coeffs[0], coeffs[1], coeffs[2], coeffs[3]};
+  plane_normalize(c);
+  std::memcpy(&g->lms[4 * (size_t)g->V[vid].idx], c, 4 * sizeof(double));
+  g->host_est_dirty = true;
+  return SSB_OK;
+}
 int ssb_graph_set_point_xyz(ssb_graph* g, int vid, const double xyz[3]) {
   if (!check_vertex(g, vid, VK_XYZ) || !xyz) return SSB_ERR_INVALID;
   SSB_TRY(sync_estimates_to_host(g));
@@ -1344,7 +1433,7 @@ int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len) {
 int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* out9n) {
   if (!g || (n > 0 && (!vids || !out9n)) || n < 0) return SSB_ERR_INVALID;
   for (int k = 0; k < n; ++k)
-    if (!check_vertex(g, vids[k], VK_XYZ) || g->V[vids[k]].fixed) {
+    if (!(check_vertex(g, vids[k], VK_XYZ) || check_vertex(g, vids[k], VK_PLANE)) || g->V[vids[k]].fixed) {
       set_error("landmark_marginals: vertex %d is not a free XYZ vertex", vids[k]);
       return SSB_ERR_INVALID;
     }
@@ -1394,6 +1483,10 @@ int ssb_graph_save_g2o(ssb_graph* g, const char* path) {
       const Pose& P = g->poses[v.idx];
       std::fprintf(f, "VERTEX_SE3:QUAT %zu %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", id, P.t[0], P.t[1], P.t[2], P.q[0],
                    P.q[1], P.q[2], P.q[3]);
+    } else if (v.kind == VK_PLANE) {
+      // g2o VertexPlane::write: 4 coefficients followed by the display colour
+      const double* p = &g->lms[4 * (size_t)v.idx];
+      std::fprintf(f, "VERTEX_PLANE %zu %.17g %.17g %.17g %.17g 0 0 0\n", id, p[0], p[1], p[2], p[3]);
     } else {
       const double* p = &g->lms[4 * (size_t)v.idx];
       std::fprintf(f, "VERTEX_TRACKXYZ %zu %.17g %.17g %.17g\n", id, p[0], p[1], p[2]);
@@ -1406,6 +1499,13 @@ int ssb_graph_save_g2o(ssb_graph* g, const char* path) {
       std::fprintf(f, "EDGE_SE3:QUAT %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g", g->pose_vid[e.i], g->pose_vid[e.j],
                    e.zt[0], e.zt[1], e.zt[2], e.zq[0], e.zq[1], e.zq[2], e.zq[3]);
       for (int k = 0; k < 21; ++k) std::fprintf(f, " %.17g", e.info[k]);
+      std::fprintf(f, "\n");
+    } else if (r.kind == EK_PL && g->lm_kind[g->pl[r.idx].l]) {
+      // EdgeSE3Plane::write (include/g2o/edge_se3_plane.hpp:39-46): 4 coefficients + upper triangle
+      const PLEdge& e = g->pl[r.idx];
+      std::fprintf(f, "EDGE_SE3_PLANE %d %d %.17g %.17g %.17g %.17g", g->pose_vid[e.p], g->lm_vid[e.l], e.z[0], e.z[1], e.z[2],
+                   g->pl_zd[r.idx]);
+      for (int k = 0; k < 6; ++k) std::fprintf(f, " %.17g", e.info[k]);
       std::fprintf(f, "\n");
     } else if (r.kind == EK_PL) {
       const PLEdge& e = g->pl[r.idx];
@@ -1467,6 +1567,22 @@ int ssb_graph_load_g2o(ssb_graph* g, const char* path) {
         set_error("load_g2o: vertex ids must be consecutive (got %d, expected %d)", id, got);
         return SSB_ERR_INVALID;
       }
+    } else if (tag == "VERTEX_PLANE") {
+      int id;
+      double c[4];
+      ss >> id >> c[0] >> c[1] >> c[2] >> c[3];
+      int got = ssb_graph_add_plane_node(g, c);
+      if (got != id) {
+        set_error("load_g2o: vertex ids must be consecutive (got %d, expected %d)", id, got);
+        return SSB_ERR_INVALID;
+      }
+    } else if (tag == "EDGE_SE3_PLANE") {
+      int a, b;
+      double c[4], u[6], info[9];
+      ss >> a >> b >> c[0] >> c[1] >> c[2] >> c[3];
+      for (int k = 0; k < 6; ++k) ss >> u[k];
+      expand_sym3(u, info);
+      if (ssb_graph_add_se3_plane_edge(g, a, b, c, info) < 0) return SSB_ERR_INVALID;
     } else if (tag == "FIX") {
       int id;
       while (ss >> id) fixes.push_back(id);

@@ -23,6 +23,8 @@ struct DevGraph {
   double* lm;  // 4 doubles per landmark
   const unsigned char* pose_fixed;
   const unsigned char* lm_fixed;
+  const unsigned char* lm_kind;  // per landmark vertex: 0 = VertexPointXYZ, 1 = VertexPlane; null = all XYZ
+  const double* pl_zd;           // per pose-landmark edge (L-order): 4th coefficient of a measured plane; null = no planes
   const PLEdge* pl;
   const PPEdge* pp;
   const int* lm_rowptr;
@@ -43,6 +45,47 @@ struct DevGraph {
 };
 constexpr int PART_STRIDE = 1024;
 
+// Linearisation of one pose -> landmark edge at (X, landmark record lm4): error e(3), pose Jacobian Jp (3x6)
+// and the TRANSPOSED landmark Jacobian JlT (3x3), row-major.  EdgeSE3PointXYZ: Jp = [-I | 2[pc]x], Jl = R'
+// (so JlT = R); EdgeSE3Plane: exact dual-number Jacobians (ssb_math.cuh).
+__device__ __noinline__ void pl_plane_lin(const Pose& X, const double* pl4, const double* zn, double zd, double* err,
+                                          double* Jp, double* JlT) {
+  const double zm[4] = {zn[0], zn[1], zn[2], zd};
+  double Jl[9];
+  plane_linearize(X, pl4, zm, err, Jp, Jl);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) JlT[3 * r + c] = Jl[3 * c + r];
+}
+__device__ __forceinline__ bool pl_is_plane(const DevGraph& G, int l) { return G.lm_kind != nullptr && G.lm_kind[l] != 0; }
+__device__ __forceinline__ void pl_edge_lin(const DevGraph& G, const PLEdge& ed, int e_idx, const Pose& X, double* err,
+                                            double* Jp, double* JlT) {
+  const double* lm4 = G.lm + 4 * (size_t)ed.l;
+  if (pl_is_plane(G, ed.l)) {
+    const double pl4[4] = {lm4[0], lm4[1], lm4[2], lm4[3]};
+    pl_plane_lin(X, pl4, ed.z, G.pl_zd[e_idx], err, Jp, JlT);
+  } else {
+    const double p[3] = {lm4[0], lm4[1], lm4[2]};
+    PLLin L;
+    pl_linearize(X, p, ed.z, L);
+    for (int k = 0; k < 3; ++k) err[k] = L.e[k];
+    pl_jac_pose(L.pc, Jp);
+    for (int k = 0; k < 9; ++k) JlT[k] = L.R[k];
+  }
+}
+__device__ __forceinline__ void pl_edge_err(const DevGraph& G, const PLEdge& ed, int e_idx, const Pose& X, double* err) {
+  const double* lm4 = G.lm + 4 * (size_t)ed.l;
+  if (pl_is_plane(G, ed.l)) {
+    const double pl4[4] = {lm4[0], lm4[1], lm4[2], lm4[3]};
+    const double zm[4] = {ed.z[0], ed.z[1], ed.z[2], G.pl_zd[e_idx]};
+    plane_error(X, pl4, zm, err);
+  } else {
+    const double p[3] = {lm4[0], lm4[1], lm4[2]};
+    PLLin L;
+    pl_linearize(X, p, ed.z, L);
+    for (int k = 0; k < 3; ++k) err[k] = L.e[k];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1a: landmark-major linearisation.  One thread per landmark walks its L-order edges:
 //   Hll += R W R',  bl += -R W e,  HplL_e = R W Jp  (3x6)
@@ -52,31 +95,28 @@ __global__ void __launch_bounds__(128) k_lin_landmarks(DevGraph G) {
   int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= G.Nl) return;
   const bool lfixed = G.lm_fixed[l] != 0;
-  double p[3] = {G.lm[4 * l], G.lm[4 * l + 1], G.lm[4 * l + 2]};
   double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
   for (int e = G.lm_rowptr[l]; e < G.lm_rowptr[l + 1]; ++e) {
     const PLEdge ed = G.pl[e];
     const Pose X = G.pose[ed.p];
-    PLLin L;
-    pl_linearize(X, p, ed.z, L);
+    double err[3], Jp[18], R[9];  // R = Jl' (= the pose rotation for a point landmark)
+    pl_edge_lin(G, ed, e, X, err, Jp, R);
     double W[9];
     expand_sym3(ed.info, W);
-    // RW = R * W (3x3)
+    // RW = Jl' * W (3x3)
     double RW[9];
     for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) RW[3 * r + c] = L.R[3 * r] * W[c] + L.R[3 * r + 1] * W[3 + c] + L.R[3 * r + 2] * W[6 + c];
+      for (int c = 0; c < 3; ++c) RW[3 * r + c] = R[3 * r] * W[c] + R[3 * r + 1] * W[3 + c] + R[3 * r + 2] * W[6 + c];
     if (!lfixed) {
-      // Hll += RW * R'
+      // Hll += Jl' W Jl
       int k = 0;
       for (int r = 0; r < 3; ++r)
         for (int c = r; c < 3; ++c) {
-          H[k] += RW[3 * r] * L.R[3 * c] + RW[3 * r + 1] * L.R[3 * c + 1] + RW[3 * r + 2] * L.R[3 * c + 2];
+          H[k] += RW[3 * r] * R[3 * c] + RW[3 * r + 1] * R[3 * c + 1] + RW[3 * r + 2] * R[3 * c + 2];
           ++k;
         }
-      for (int r = 0; r < 3; ++r) b[r] -= RW[3 * r] * L.e[0] + RW[3 * r + 1] * L.e[1] + RW[3 * r + 2] * L.e[2];
+      for (int r = 0; r < 3; ++r) b[r] -= RW[3 * r] * err[0] + RW[3 * r + 1] * err[1] + RW[3 * r + 2] * err[2];
     }
-    double Jp[18];
-    pl_jac_pose(L.pc, Jp);
     double* out = G.HplL + 18 * (size_t)e;
     const bool zero = lfixed || G.pose_fixed[ed.p];
     for (int r = 0; r < 3; ++r)
@@ -108,12 +148,9 @@ __global__ void __launch_bounds__(64) k_lin_poses(DevGraph G) {
   for (int kk = G.pose_pl_rowptr[i]; kk < G.pose_pl_rowptr[i + 1]; ++kk) {
     const int e = G.pose_pl_idx[kk];
     const PLEdge ed = G.pl[e];
-    double p[3] = {G.lm[4 * ed.l], G.lm[4 * ed.l + 1], G.lm[4 * ed.l + 2]};
-    PLLin L;
-    pl_linearize(X, p, ed.z, L);
-    double W[9], Jp[18];
+    double W[9], Jp[18], err[3], JlT[9];
+    pl_edge_lin(G, ed, e, X, err, Jp, JlT);
     expand_sym3(ed.info, W);
-    pl_jac_pose(L.pc, Jp);
     // JtW = Jp' W (6x3)
     double JtW[18];
     for (int r = 0; r < 6; ++r)
@@ -121,15 +158,15 @@ __global__ void __launch_bounds__(64) k_lin_poses(DevGraph G) {
     if (!fixed) {
       for (int r = 0; r < 6; ++r) {
         for (int c = 0; c < 6; ++c) H[6 * r + c] += JtW[3 * r] * Jp[c] + JtW[3 * r + 1] * Jp[6 + c] + JtW[3 * r + 2] * Jp[12 + c];
-        b[r] -= JtW[3 * r] * L.e[0] + JtW[3 * r + 1] * L.e[1] + JtW[3 * r + 2] * L.e[2];
+        b[r] -= JtW[3 * r] * err[0] + JtW[3 * r + 1] * err[1] + JtW[3 * r + 2] * err[2];
       }
     }
-    // HplP = Jp' W R'  (6x3)
+    // HplP = Jp' W Jl  (6x3)
     const bool zero = fixed || G.lm_fixed[ed.l];
     double* out = G.HplP + 18 * (size_t)kk;
     for (int r = 0; r < 6; ++r)
       for (int c = 0; c < 3; ++c)
-        out[3 * r + c] = zero ? 0.0 : JtW[3 * r] * L.R[3 * c] + JtW[3 * r + 1] * L.R[3 * c + 1] + JtW[3 * r + 2] * L.R[3 * c + 2];
+        out[3 * r + c] = zero ? 0.0 : JtW[3 * r] * JlT[3 * c] + JtW[3 * r + 1] * JlT[3 * c + 1] + JtW[3 * r + 2] * JlT[3 * c + 2];
     G.plP_lm[kk] = ed.l;
   }
   // pose-pose edges
@@ -1362,10 +1399,18 @@ __global__ void __launch_bounds__(128) k_backsub_update(DevGraph G, double lambd
     double d[3] = {Wi[0] * a[0] + Wi[1] * a[1] + Wi[2] * a[2], Wi[1] * a[0] + Wi[3] * a[1] + Wi[4] * a[2],
                    Wi[2] * a[0] + Wi[4] * a[1] + Wi[5] * a[2]};
     if (G.lm_fixed[l]) d[0] = d[1] = d[2] = 0.0;
+    double cur[4];
+    for (int c = 0; c < 4; ++c) {
+      cur[c] = G.lm[4 * (size_t)l + c];
+      lm_bak[4 * (size_t)l + c] = cur[c];
+    }
+    if (pl_is_plane(G, l)) {
+      if (!G.lm_fixed[l]) plane_oplus(cur, d);  // VertexPlane::oplusImpl
+    } else {
+      for (int c = 0; c < 3; ++c) cur[c] += d[c];  // VertexPointXYZ::oplusImpl
+    }
+    for (int c = 0; c < 4; ++c) G.lm[4 * (size_t)l + c] = cur[c];
     for (int c = 0; c < 3; ++c) {
-      const double old = G.lm[4 * (size_t)l + c];
-      lm_bak[4 * (size_t)l + c] = old;
-      G.lm[4 * (size_t)l + c] = old + d[c];
       G.dl[3 * (size_t)l + c] = d[c];
       sc += d[c] * (lambda * d[c] + G.bl[3 * (size_t)l + c]);
     }
@@ -1438,10 +1483,9 @@ __global__ void __launch_bounds__(CHI2_THREADS) k_chi2(DevGraph G, double* part,
       if (tid < n) {
         const PLEdge* ed = reinterpret_cast<const PLEdge*>(tile) + tid;
         const Pose X = G.pose[ed->p];
-        double p[3] = {G.lm[4 * (size_t)ed->l], G.lm[4 * (size_t)ed->l + 1], G.lm[4 * (size_t)ed->l + 2]};
-        PLLin L;
-        pl_linearize(X, p, ed->z, L);
-        acc += quad3(ed->info, L.e);
+        double err[3];
+        pl_edge_err(G, *ed, e0 + tid, X, err);
+        acc += quad3(ed->info, err);
       }
     } else {
       const int e0 = (t - nPL) * CHI2_PP_TILE;
@@ -1541,13 +1585,10 @@ __global__ void k_edge_linearize(DevGraph G, int kind, int e, double* out /* err
     pp_linearize(G.pose[ed->i], G.pose[ed->j], ed->zt, ed->zq, err, Ji, Jj);
   } else {
     const PLEdge ed = G.pl[e];
-    double p[3] = {G.lm[4 * (size_t)ed.l], G.lm[4 * (size_t)ed.l + 1], G.lm[4 * (size_t)ed.l + 2]};
-    PLLin L;
-    pl_linearize(G.pose[ed.p], p, ed.z, L);
-    for (int k = 0; k < 3; ++k) err[k] = L.e[k];
-    pl_jac_pose(L.pc, Ji);
+    double JlT[9];
+    pl_edge_lin(G, ed, e, G.pose[ed.p], err, Ji, JlT);
     for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) Jj[3 * r + c] = L.R[3 * c + r];
+      for (int c = 0; c < 3; ++c) Jj[3 * r + c] = JlT[3 * c + r];
   }
 }
 

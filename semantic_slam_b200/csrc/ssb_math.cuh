@@ -185,6 +185,216 @@ SSB_HD void pl_jac_pose(const double* pc, double* J) {
   J[6 * 2 + 4] = 2 * pc[0];
 }
 
+// -------- EdgeSE3Plane / VertexPlane (dormant in the reference: include/g2o/edge_se3_plane.hpp:8-48,
+// graph_slam.hpp:44,74-75; upstream g2o types/slam3d_addons/plane3d.h) ------------------
+// A plane is 4 normalised coefficients (n, c3) with |n| = 1 and distance() = -c3; its minimal increment is
+// (d azimuth, d elevation, d distance) applied by Plane3D::oplus.  The edge error is
+//   e = (X^-1 * plane).ominus(measurement) = (azimuth(n'), elevation(n'), distance - distance_m),
+//   n' = rotation(n_local)^T n_m.
+// g2o differentiates this edge numerically (central differences, delta 1e-9); here the Jacobians are exact:
+// the error is evaluated on forward-mode dual numbers seeded with the 6 pose + 3 plane increments.
+template <int N>
+struct Dual {
+  double v;
+  double d[N];
+};
+template <int N>
+SSB_HD Dual<N> dconst(double v) {
+  Dual<N> r;
+  r.v = v;
+  for (int k = 0; k < N; ++k) r.d[k] = 0.0;
+  return r;
+}
+template <int N>
+SSB_HD Dual<N> operator+(const Dual<N>& a, const Dual<N>& b) {
+  Dual<N> r;
+  r.v = a.v + b.v;
+  for (int k = 0; k < N; ++k) r.d[k] = a.d[k] + b.d[k];
+  return r;
+}
+template <int N>
+SSB_HD Dual<N> operator+(const Dual<N>& a, double b) {
+  Dual<N> r = a;
+  r.v += b;
+  return r;
+}
+template <int N>
+SSB_HD Dual<N> operator-(const Dual<N>& a, const Dual<N>& b) {
+  Dual<N> r;
+  r.v = a.v - b.v;
+  for (int k = 0; k < N; ++k) r.d[k] = a.d[k] - b.d[k];
+  return r;
+}
+template <int N>
+SSB_HD Dual<N> operator-(const Dual<N>& a) {
+  Dual<N> r;
+  r.v = -a.v;
+  for (int k = 0; k < N; ++k) r.d[k] = -a.d[k];
+  return r;
+}
+template <int N>
+SSB_HD Dual<N> operator*(const Dual<N>& a, const Dual<N>& b) {
+  Dual<N> r;
+  r.v = a.v * b.v;
+  for (int k = 0; k < N; ++k) r.d[k] = a.d[k] * b.v + a.v * b.d[k];
+  return r;
+}
+template <int N>
+SSB_HD Dual<N> operator*(const Dual<N>& a, double b) {
+  Dual<N> r;
+  r.v = a.v * b;
+  for (int k = 0; k < N; ++k) r.d[k] = a.d[k] * b;
+  return r;
+}
+template <int N>
+SSB_HD Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) {
+  Dual<N> r;
+  const double ib = 1.0 / b.v;
+  r.v = a.v * ib;
+  for (int k = 0; k < N; ++k) r.d[k] = (a.d[k] - r.v * b.d[k]) * ib;
+  return r;
+}
+template <int N>
+SSB_HD Dual<N> dsqrt(const Dual<N>& a) {
+  Dual<N> r;
+  r.v = sqrt(a.v);
+  const double g = r.v > 0.0 ? 0.5 / r.v : 0.0;
+  for (int k = 0; k < N; ++k) r.d[k] = a.d[k] * g;
+  return r;
+}
+template <int N>
+SSB_HD Dual<N> dsin(const Dual<N>& a) {
+  Dual<N> r;
+  r.v = sin(a.v);
+  const double g = cos(a.v);
+  for (int k = 0; k < N; ++k) r.d[k] = a.d[k] * g;
+  return r;
+}
+template <int N>
+SSB_HD Dual<N> dcos(const Dual<N>& a) {
+  Dual<N> r;
+  r.v = cos(a.v);
+  const double g = -sin(a.v);
+  for (int k = 0; k < N; ++k) r.d[k] = a.d[k] * g;
+  return r;
+}
+template <int N>
+SSB_HD Dual<N> datan2(const Dual<N>& y, const Dual<N>& x) {
+  Dual<N> r;
+  r.v = atan2(y.v, x.v);
+  const double n2 = x.v * x.v + y.v * y.v;
+  const double gx = n2 > 0.0 ? -y.v / n2 : 0.0, gy = n2 > 0.0 ? x.v / n2 : 0.0;
+  for (int k = 0; k < N; ++k) r.d[k] = gy * y.d[k] + gx * x.d[k];
+  return r;
+}
+SSB_HD double dconst0(double v) { return v; }
+SSB_HD double dsqrt(double a) { return sqrt(a); }
+SSB_HD double dsin(double a) { return sin(a); }
+SSB_HD double dcos(double a) { return cos(a); }
+SSB_HD double datan2(double y, double x) { return atan2(y, x); }
+
+// Plane3D::rotation(v) = AngleAxis(azimuth(v), Z) * AngleAxis(-elevation(v), Y), row-major
+template <class T>
+SSB_HD void plane_rotation(const T* v, T* R, const T& zero) {
+  const T az = datan2(v[1], v[0]);
+  const T el = datan2(v[2], dsqrt(v[0] * v[0] + v[1] * v[1]));
+  const T ca = dcos(az), sa = dsin(az), ce = dcos(el), se = dsin(el);
+  R[0] = ca * ce;
+  R[1] = zero - sa;
+  R[2] = zero - ca * se;
+  R[3] = sa * ce;
+  R[4] = ca;
+  R[5] = zero - sa * se;
+  R[6] = se;
+  R[7] = zero;
+  R[8] = ce;
+}
+// EdgeSE3Plane::computeError on scalar type T (double or Dual): pose rotation R (world <- robot) and
+// translation t, plane coefficients pl (world), measurement zm (normalised, robot frame)
+template <class T>
+SSB_HD void plane_error_t(const T* R, const T* t, const T* pl, const double* zm, T* e, const T& zero) {
+  // local = X^-1 * plane : n_l = R^T n, c3_l = c3 + t . n ; Plane3D(v) normalises
+  T nl[3];
+  for (int r = 0; r < 3; ++r) nl[r] = R[r] * pl[0] + R[3 + r] * pl[1] + R[6 + r] * pl[2];
+  T c3 = pl[3] + t[0] * pl[0] + t[1] * pl[1] + t[2] * pl[2];
+  const T nn = dsqrt(nl[0] * nl[0] + nl[1] * nl[1] + nl[2] * nl[2]);
+  for (int r = 0; r < 3; ++r) nl[r] = nl[r] / nn;
+  c3 = c3 / nn;
+  // ominus: n' = rotation(n_l)^T n_m
+  T Rn[9];
+  plane_rotation(nl, Rn, zero);
+  T n[3];
+  for (int r = 0; r < 3; ++r) n[r] = Rn[r] * zm[0] + Rn[3 + r] * zm[1] + Rn[6 + r] * zm[2];
+  e[0] = datan2(n[1], n[0]);
+  e[1] = datan2(n[2], dsqrt(n[0] * n[0] + n[1] * n[1]));
+  e[2] = (zero - c3) + zm[3];
+}
+SSB_HD void plane_normalize(double* c) {
+  const double n = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  for (int k = 0; k < 4; ++k) c[k] /= n;
+}
+// Plane3D::oplus  (VertexPlane::oplusImpl)
+SSB_HD void plane_oplus(double* c, const double* v) {
+  const double s = sin(v[1]), co = cos(v[1]);
+  const double n[3] = {co * cos(v[0]), co * sin(v[0]), s};
+  double R[9];
+  plane_rotation(c, R, 0.0);
+  const double d = -c[3] + v[2];
+  const double r0 = R[0] * n[0] + R[1] * n[1] + R[2] * n[2];
+  const double r1 = R[3] * n[0] + R[4] * n[1] + R[5] * n[2];
+  const double r2 = R[6] * n[0] + R[7] * n[1] + R[8] * n[2];
+  c[0] = r0;
+  c[1] = r1;
+  c[2] = r2;
+  c[3] = -d;
+  plane_normalize(c);
+}
+SSB_HD void plane_error(const Pose& X, const double* pl, const double* zm, double* e) {
+  double R[9];
+  quat_to_R(X.q, R);
+  plane_error_t<double>(R, X.t, pl, zm, e, 0.0);
+}
+// error + exact Jacobians: Jp 3x6 wrt the pose increment (X <- X * fromVectorMQT(d): t' = t + R dt,
+// R' = R (I + 2 [dq]x) to first order), Jl 3x3 wrt the plane increment (n' = rotation(n) n(daz, del):
+// d n / d az = column 1, d n / d el = column 2 of rotation(n); c3' = c3 - dd).  Row-major.
+SSB_HD void plane_linearize(const Pose& X, const double* pl, const double* zm, double* e, double* Jp, double* Jl) {
+  typedef Dual<9> D;
+  double R0[9], Rp[9];
+  quat_to_R(X.q, R0);
+  plane_rotation(pl, Rp, 0.0);
+  const D zero = dconst<9>(0.0);
+  D R[9], t[3], p[4];
+  for (int i = 0; i < 3; ++i) {
+    t[i] = dconst<9>(X.t[i]);
+    for (int k = 0; k < 3; ++k) t[i].d[k] = R0[3 * i + k];
+    for (int j = 0; j < 3; ++j) R[3 * i + j] = dconst<9>(R0[3 * i + j]);
+  }
+  // d(R [e_k]x)/... : [e_0]x = (0 0 0; 0 0 -1; 0 1 0), [e_1]x = (0 0 1; 0 0 0; -1 0 0), [e_2]x = (0 -1 0; 1 0 0; 0 0 0)
+  for (int i = 0; i < 3; ++i) {
+    const double r0 = R0[3 * i], r1 = R0[3 * i + 1], r2 = R0[3 * i + 2];
+    R[3 * i + 1].d[3] = 2 * r2;   // k = x: column 1 += r2, column 2 -= r1
+    R[3 * i + 2].d[3] = -2 * r1;
+    R[3 * i + 0].d[4] = -2 * r2;  // k = y: column 0 -= r2, column 2 += r0
+    R[3 * i + 2].d[4] = 2 * r0;
+    R[3 * i + 0].d[5] = 2 * r1;   // k = z: column 0 += r1, column 1 -= r0
+    R[3 * i + 1].d[5] = -2 * r0;
+  }
+  for (int i = 0; i < 3; ++i) {
+    p[i] = dconst<9>(pl[i]);
+    p[i].d[6] = Rp[3 * i + 1];
+    p[i].d[7] = Rp[3 * i + 2];
+  }
+  p[3] = dconst<9>(pl[3]);
+  p[3].d[8] = -1.0;
+  D ed[3];
+  plane_error_t<D>(R, t, p, zm, ed, zero);
+  for (int r = 0; r < 3; ++r) {
+    e[r] = ed[r].v;
+    for (int c = 0; c < 6; ++c) Jp[6 * r + c] = ed[r].d[c];
+    for (int c = 0; c < 3; ++c) Jl[3 * r + c] = ed[r].d[6 + c];
+  }
+}
+
 // -------- EdgeSE3:  e = toVectorMQT(Z^-1 Xi^-1 Xj)  (g2o types/slam3d/edge_se3.cpp)
 // Ji, Jj 6x6 row-major (may be null when only the error is needed).
 SSB_HD void pp_linearize(const Pose& Xi, const Pose& Xj, const double* zt, const double* zq, double* e, double* Ji,

@@ -73,6 +73,30 @@ class GraphSLAM:
         return check(self._L.ssb_graph_add_point_xyz_point_xyz_edge(self._h, v1, v2, p, q),
                      "add_point_xyz_point_xyz_edge")
 
+    # plane landmarks: the API the reference keeps commented out (graph_slam.hpp:44,74-75) with its own edge type
+    # include/g2o/edge_se3_plane.hpp
+    def add_plane_node(self, plane_coeffs) -> int:
+        a, p = _d(plane_coeffs)
+        if a.size != 4:
+            raise ValueError("plane coefficients must be a 4-vector")
+        return check(self._L.ssb_graph_add_plane_node(self._h, p), "add_plane_node")
+
+    def add_se3_plane_edge(self, v_se3: int, v_plane: int, plane_coeffs, information_matrix) -> int:
+        a, p = _d(plane_coeffs)
+        b, q = _d(information_matrix)
+        if a.size != 4 or b.size != 9:
+            raise ValueError("plane must be a 4-vector and the information matrix 3x3")
+        return check(self._L.ssb_graph_add_se3_plane_edge(self._h, v_se3, v_plane, p, q), "add_se3_plane_edge")
+
+    def get_plane(self, vid: int):
+        out = np.zeros(4)
+        check(self._L.ssb_graph_get_plane(self._h, vid, out.ctypes.data_as(dp)), "get_plane")
+        return out
+
+    def set_plane(self, vid: int, coeffs):
+        a, p = _d(coeffs)
+        check(self._L.ssb_graph_set_plane(self._h, vid, p), "set_plane")
+
     def optimize(self, max_iterations: int = 1024) -> bool:
         """GraphSLAM::optimize: False when the graph has fewer than 10 edges (graph_slam.cpp:184-186)."""
         st = _lib.LmStats()

@@ -33,6 +33,7 @@
 namespace ssb_host {
 using Isometry3d = Eigen::Isometry3d;
 using Vector3d = Eigen::Vector3d;
+using Vector4d = Eigen::Vector4d;
 using MatrixXd = Eigen::MatrixXd;
 inline void to34(const Isometry3d& T, double* o) {
   for (int r = 0; r < 3; ++r)
@@ -58,6 +59,11 @@ struct Isometry3d {
 };
 struct Vector3d {
   double v[3];
+  double& operator()(int i) { return v[i]; }
+  double operator()(int i) const { return v[i]; }
+};
+struct Vector4d {
+  double v[4];
   double& operator()(int i) { return v[i]; }
   double operator()(int i) const { return v[i]; }
 };
@@ -131,9 +137,22 @@ class VertexPointXYZ : public VertexBase {
     return v;
   }
 };
+// g2o::VertexPlane stand-in (estimate() = the 4 normalised plane coefficients, g2o::Plane3D::toVector())
+class VertexPlane : public VertexBase {
+ public:
+  using VertexBase::VertexBase;
+  ssb_host::Vector4d estimate() const {
+    double c[4];
+    ssb_graph_get_plane(g_, id_, c);
+    ssb_host::Vector4d v;
+    for (int k = 0; k < 4; ++k) v(k) = c[k];
+    return v;
+  }
+};
 struct EdgeHandle {
   int id;
 };
+using EdgeSE3Plane = EdgeHandle;
 using EdgeSE3 = EdgeHandle;
 using EdgeSE3PointXYZ = EdgeHandle;
 using EdgePointXYZ = EdgeHandle;
@@ -217,6 +236,25 @@ class GraphSLAM {
     return edges_.back().get();
   }
   // graph_slam.cpp:168-180
+  // graph_slam.hpp:44 / graph_slam.cpp:117-125 (commented out in the reference): plane landmark
+  g2o::VertexPlane* add_plane_node(const ssb_host::Vector4d& plane_coeffs) {
+    double c[4] = {plane_coeffs(0), plane_coeffs(1), plane_coeffs(2), plane_coeffs(3)};
+    int id = ssb_graph_add_plane_node(graph, c);
+    if (id < 0) return nullptr;
+    planes_.emplace_back(new g2o::VertexPlane(graph, id));
+    return planes_.back().get();
+  }
+  // graph_slam.hpp:74-75 (commented out in the reference): g2o::EdgeSE3Plane (include/g2o/edge_se3_plane.hpp)
+  g2o::EdgeSE3Plane* add_se3_plane_edge(g2o::VertexSE3* v_se3, g2o::VertexPlane* v_plane,
+                                        const ssb_host::Vector4d& plane_coeffs,
+                                        const ssb_host::MatrixXd& information_matrix) {
+    double c[4] = {plane_coeffs(0), plane_coeffs(1), plane_coeffs(2), plane_coeffs(3)}, I[9];
+    ssb_host::toRowMajor(information_matrix, 3, I);
+    int id = ssb_graph_add_se3_plane_edge(graph, v_se3->id(), v_plane->id(), c, I);
+    if (id < 0) return nullptr;
+    edges_.emplace_back(new g2o::EdgeHandle{id});
+    return edges_.back().get();
+  }
   g2o::EdgePointXYZ* add_point_xyz_point_xyz_edge(g2o::VertexPointXYZ* v1_xyz, g2o::VertexPointXYZ* v2_xyz,
                                                   const ssb_host::Vector3d& xyz,
                                                   const ssb_host::MatrixXd& information_matrix) {
@@ -295,6 +333,7 @@ class GraphSLAM {
  private:
   std::vector<std::unique_ptr<g2o::VertexSE3>> se3_;
   std::vector<std::unique_ptr<g2o::VertexPointXYZ>> xyz_;
+  std::vector<std::unique_ptr<g2o::VertexPlane>> planes_;
   std::vector<std::unique_ptr<g2o::EdgeHandle>> edges_;
 };
 

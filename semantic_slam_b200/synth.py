@@ -281,3 +281,88 @@ def make_cloud(n_boxes: int = 64, n_hyp: int = 1024, seed: int = SEED_BASE + 3, 
         triples[b] = t
     return CloudSpec(msg.reshape(-1).view(np.uint8).copy(), width, height, point_step, row_step, (0, 4, 8, 16),
                      boxes, triples)
+
+
+# --------------------------------------------------------------------------------------------
+# Pose - plane graphs (the reference's dormant VertexPlane / EdgeSE3Plane path)
+# --------------------------------------------------------------------------------------------
+def plane_transform(T, c):
+    """g2o: Plane3D operator*(Isometry3D, Plane3D) — moves plane coefficients (n, c3) by T."""
+    n = T[:, :3] @ np.asarray(c[:3])
+    return np.array([n[0], n[1], n[2], c[3] - T[:, 3] @ n])
+
+
+@dataclasses.dataclass
+class PlaneGraphSpec:
+    vertices: list   # ("se3", T34) | ("xyz", p3) | ("plane", c4) in creation order
+    edges: list      # ("se3", vi, vj, Z34) | ("xyz", vi, vj, z3) | ("plane", vi, vj, c4)
+    info6: np.ndarray
+    info3: np.ndarray
+    info_plane: np.ndarray
+    gt_pose: np.ndarray
+    gt_planes: np.ndarray
+
+    @property
+    def n_poses(self):
+        return sum(1 for v in self.vertices if v[0] == "se3")
+
+
+def make_plane_graph(n_kf: int = 40, n_planes: int = 6, n_lm: int = 8, seed: int = SEED_BASE + 14,
+                     plane_sigma=(0.01, 0.01, 0.02)) -> PlaneGraphSpec:
+    """Keyframes on a lawn-mower path observing wall-like planes (and a few point landmarks): every keyframe
+    sees 3 planes; the measurement is the plane in the robot frame, perturbed through Plane3D::oplus."""
+    import oracle  # only for Plane3D::oplus when perturbing measurements (generator, not a back-end path)
+    rng = np.random.default_rng(seed)
+    base = make_graph(n_kf, max(n_lm, 1), obs_per_kf=2, seed=seed, name="plane_base")
+    gt = base.gt_pose
+    # planes: normals away from the z axis (azimuth/elevation chart is singular there), a few metres out
+    planes = []
+    for _ in range(n_planes):
+        az = rng.uniform(-np.pi, np.pi)
+        el = rng.uniform(-0.6, 0.6)
+        n = np.array([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)])
+        planes.append(np.array([n[0], n[1], n[2], -rng.uniform(2.0, 9.0)]))
+    planes = np.array(planes)
+    vertices, edges = [], []
+    vmap = {}
+    for v in range(base.vkind.size):
+        vmap[v] = len(vertices)
+        vertices.append(("se3", base.vpose[v]) if base.vkind[v] == 0 else ("xyz", base.vxyz[v]))
+    for e in range(base.ekind.size):
+        if base.ekind[e] == 0:
+            edges.append(("se3", vmap[int(base.evi[e])], vmap[int(base.evj[e])], base.eZ[e]))
+        else:
+            edges.append(("xyz", vmap[int(base.evi[e])], vmap[int(base.evj[e])], base.ez[e]))
+    pose_vids = [vmap[v] for v in range(base.vkind.size) if base.vkind[v] == 0]
+    plane_vid = {}
+    for k in range(n_kf):
+        seen = rng.choice(n_planes, size=min(3, n_planes), replace=False)
+        for j in seen:
+            local = plane_transform(T_inv(gt[k]), planes[j])
+            meas = oracle.plane_oplus(local, rng.normal(0, 1, 3) * np.array(plane_sigma))
+            if j not in plane_vid:
+                plane_vid[j] = len(vertices)
+                vertices.append(("plane", plane_transform(base.vpose[np.flatnonzero(base.vkind == 0)[k]], meas)))
+            edges.append(("plane", pose_vids[k], plane_vid[j], meas))
+    info_plane = np.diag([1 / 0.01, 1 / 0.01, 1 / 0.02])
+    return PlaneGraphSpec(vertices, edges, base.einfo6, base.einfo3, info_plane, gt, planes)
+
+
+def load_plane_graph(backend, spec: PlaneGraphSpec):
+    """Replay a PlaneGraphSpec through a GraphSLAM-like object; returns the vertex ids."""
+    ids = []
+    for v in spec.vertices:
+        if v[0] == "se3":
+            ids.append(backend.add_se3_node(v[1]))
+        elif v[0] == "xyz":
+            ids.append(backend.add_point_xyz_node(v[1]))
+        else:
+            ids.append(backend.add_plane_node(v[1]))
+    for e in spec.edges:
+        if e[0] == "se3":
+            backend.add_se3_edge(ids[e[1]], ids[e[2]], e[3], spec.info6)
+        elif e[0] == "xyz":
+            backend.add_se3_point_xyz_edge(ids[e[1]], ids[e[2]], e[3], spec.info3)
+        else:
+            backend.add_se3_plane_edge(ids[e[1]], ids[e[2]], e[3], spec.info_plane)
+    return ids

@@ -31,7 +31,14 @@ int main(int argc, char** argv) {
     Vector3d z{{2.0 - 0.5 * k, 1.0, 0.5}};
     gs.add_se3_point_xyz_edge(kf[k], lm, z, MatrixXd::Identity(3));
   }
+  // plane landmark (the reference's dormant VertexPlane / EdgeSE3Plane API): the floor z = 0 seen from every keyframe
+  Vector4d floor_w{{0.0, 0.0, 1.0, 0.0}};
+  g2o::VertexPlane* fl = gs.add_plane_node(floor_w);
+  if (!fl) return 5;
+  for (int k = 0; k < 12; ++k) gs.add_se3_plane_edge(kf[k], fl, floor_w, MatrixXd::Identity(3));
   if (!gs.optimize()) return 3;
+  Vector4d fe = fl->estimate();
+  if (std::fabs(fe(2) - 1.0) > 1e-6 || std::fabs(fe(3)) > 1e-6) return 6;
   Isometry3d last = kf.back()->estimate();
   std::printf("last keyframe x = %.6f (expect 5.5), hessianIndex(first)=%d id(last)=%d\n", last.m[3], kf[0]->hessianIndex(),
               kf.back()->id());

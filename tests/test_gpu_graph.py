@@ -253,3 +253,61 @@ def test_cfg2_parity_at_bench_tolerance():
     P, X = g.get_all(spec.n_poses, spec.n_landmarks)
     assert np.abs(P - gold["poses"]).max() <= 1e-5 * max(1.0, np.abs(gold["poses"]).max())
     assert np.abs(X - gold["landmarks"]).max() <= 1e-5 * max(1.0, np.abs(gold["landmarks"]).max())
+
+
+# ---- plane landmarks: VertexPlane / EdgeSE3Plane (dormant in the reference) -------------------
+def _plane_pair(**kw):
+    spec = synth.make_plane_graph()
+    g = GraphSLAM(**kw)
+    o = oracle.OracleGraphSLAM()
+    ids = synth.load_plane_graph(g, spec)
+    ids_o = synth.load_plane_graph(o, spec)
+    assert ids == ids_o
+    return spec, g, o, ids
+
+
+def test_plane_edge_linearization_matches_oracle():
+    """error bit-for-bit class agreement, exact (dual-number) Jacobians vs g2o's numeric ones (delta 1e-9)"""
+    spec, g, o, ids = _plane_pair()
+    n = 0
+    for eid, e in enumerate(spec.edges):
+        if e[0] != "plane":
+            continue
+        err, Ji, Jj = g.edge_linearize(eid, 3, 6, 3)
+        erro, Jio, Jjo = o.edge_linearize(eid, 3, 6, 3)
+        assert np.abs(err - erro).max() < 1e-12
+        assert np.abs(Ji - Jio).max() < 5e-6 * max(1.0, np.abs(Jio).max())
+        assert np.abs(Jj - Jjo).max() < 5e-6 * max(1.0, np.abs(Jjo).max())
+        n += 1
+    assert n > 50
+    assert abs(g.chi2() - o.chi2()) <= 1e-11 * o.chi2()
+
+
+@pytest.mark.parametrize("precond", [0, 2])
+def test_lm_trajectory_with_planes(precond):
+    spec, g, o, ids = _plane_pair(preconditioner=precond, pcg_tol=1e-10)
+    assert g.optimize(6) and o.optimize(6)
+    assert g.iterations == o.iterations == 6
+    assert np.array_equal(g.history[:, 4], o.history[:, 4])
+    # g2o (and the oracle) use numeric Jacobians for this edge: agreement is at the 1e-7 level, not 1e-12
+    assert np.allclose(g.history[:, 1], o.history[:, 1], rtol=1e-6)
+    for v, vert in enumerate(spec.vertices):
+        if vert[0] == "se3":
+            a, b = g.get_se3(ids[v]), o.get_se3(ids[v])
+        elif vert[0] == "xyz":
+            a, b = g.get_point_xyz(ids[v]), o.get_point_xyz(ids[v])
+        else:
+            a, b = g.get_plane(ids[v]), o.get_plane(ids[v])
+        assert np.abs(a - b).max() <= 1e-5 * max(1.0, np.abs(b).max()), (v, vert[0])
+
+
+def test_g2o_roundtrip_with_planes(tmp_path):
+    spec, g, o, ids = _plane_pair()
+    path = str(tmp_path / "planes.g2o")
+    g.save(path)
+    txt = open(path).read()
+    assert "VERTEX_PLANE" in txt and "EDGE_SE3_PLANE" in txt
+    g2 = GraphSLAM()
+    g2.load(path)
+    assert g2.num_vertices() == g.num_vertices() and g2.num_edges() == g.num_edges()
+    assert abs(g2.chi2() - g.chi2()) <= 1e-12 * max(1.0, g.chi2())

@@ -230,6 +230,61 @@ long long ssb_ransac_launch_count(ssb_ransac* r);
 int ssb_crop_bbox(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout, const ssb_bbox* box, float* out);
 
 /* ------------------------------------------------------------------------------------------- */
+/* Per-frame landmark association (host step between the two hot paths)                          */
+/*   data_association::find_matches / associate_lanmarks   include/ps_graph_slam/data_association.h:75-235 */
+/*   semantic_tools::transformNormalsToWorld / dist        include/tools.h:18-135,293-297        */
+/* Host code in the reference too (a few detections x a few hundred landmarks per frame); restated in   */
+/* single precision with the reference's evaluation order and quirks so that indices are bit-exact.     */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct ssb_assoc ssb_assoc;
+
+typedef struct ssb_assoc_opts {      /* ros params of data_association::init  :43-67 */
+  double maha_dist_thres;            /* 0.5  */
+  double eq_dist_thres;              /* 1.21 */
+  double land_noise_low;             /* 0.5  -> Q_ = land_noise_low * I3 */
+  double land_noise_high;            /* 0.9 (unused by the live code) */
+  int use_maha_dist;                 /* 1 */
+  int use_eq_dist;                   /* 0 (the shipped yamls set use_maha_dist 0 / use_eq_dist 1) */
+  int use_rtab_map_odom;             /* 0 */
+  int strict;                        /* 0 = reproduce the stale distance_min / nearest id of :100-107;
+                                        1 = reset them for every detection */
+} ssb_assoc_opts;
+
+typedef struct ssb_detection {       /* detected_object  include/planar_segmentation/detected_object.h:14-24 */
+  int type;                          /* std::string type, as an integer class id */
+  int plane_type;                    /* std::string plane_type ("horizontal"/"vertical"), as an integer id */
+  float pose[3];                     /* centroid in the camera frame */
+  float normal[4];                   /* normal_orientation */
+} ssb_detection;
+
+typedef struct ssb_landmark_obs {    /* landmark  include/ps_graph_slam/landmark.h:16-35 as returned per detection */
+  int is_new_landmark;               /* 1: caller adds a VertexPointXYZ at `pose` (semantic_graph_slam.cpp:160-166) */
+  int id;                            /* index into the mapped landmark list (-1: detection produced no landmark) */
+  int type, plane_type;
+  float pose[3];                     /* world frame */
+  float local_pose[3];               /* robot frame: the measurement of the SE3-XYZ edge (:171-174) */
+  float normal[4];                   /* world frame */
+  float covariance[9];               /* = Q_ */
+  double information[9];             /* covariance.inverse().cast<double>() (:170), row-major */
+} ssb_landmark_obs;
+
+void ssb_assoc_default_opts(ssb_assoc_opts* o);
+ssb_assoc* ssb_assoc_create(const ssb_assoc_opts* opts);   /* data_association::data_association + init */
+void ssb_assoc_destroy(ssb_assoc* a);
+/* data_association::find_matches: one ssb_landmark_obs per detection (out[n]); robot_pose = x y z roll pitch yaw
+ * (ros_utils.hpp:90-106 matrix2vector).  Returns n or an error. */
+int ssb_assoc_find_matches(ssb_assoc* a, const ssb_detection* dets, int n, const float robot_pose[6], float cam_angle,
+                           ssb_landmark_obs* out);
+/* landmarks_[id].node->estimate() as used by landmarkMeasurementModel (:375-389): the caller refreshes it
+ * from the graph after every optimize (assignLandmarkNode :391-393 binds the node in the reference) */
+int ssb_assoc_set_landmark_estimate(ssb_assoc* a, int id, const double xyz[3]);
+/* data_association::setLandmarkCovs  :395-397 */
+int ssb_assoc_set_landmark_cov(ssb_assoc* a, int id, const float cov[9]);
+/* data_association::getMappedLandmarks  :399 */
+int ssb_assoc_num_landmarks(const ssb_assoc* a);
+int ssb_assoc_get_landmark(const ssb_assoc* a, int id, ssb_landmark_obs* out);
+
+/* ------------------------------------------------------------------------------------------- */
 const char* ssb_last_error(void);
 /* "sm_100a" build tag, CUDA runtime version */
 const char* ssb_build_info(void);

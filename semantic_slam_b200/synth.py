@@ -292,6 +292,19 @@ def plane_transform(T, c):
     return np.array([n[0], n[1], n[2], c[3] - T[:, 3] @ n])
 
 
+def plane_perturb(c, v):
+    """measurement noise on a plane: rotate the unit normal by small azimuth / elevation angles about its own chart
+    (g2o Plane3D::oplus convention) and shift the distance; data generation only"""
+    c = np.asarray(c, dtype=np.float64)
+    n = c[:3] / np.linalg.norm(c[:3])
+    az, el = np.arctan2(n[1], n[0]), np.arctan2(n[2], np.hypot(n[0], n[1]))
+    Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1.0]])
+    Ry = np.array([[np.cos(el), 0, -np.sin(el)], [0, 1.0, 0], [np.sin(el), 0, np.cos(el)]])
+    d = np.array([np.cos(v[1]) * np.cos(v[0]), np.cos(v[1]) * np.sin(v[0]), np.sin(v[1])])
+    n2 = Rz @ Ry @ d
+    return np.array([n2[0], n2[1], n2[2], c[3] / np.linalg.norm(c[:3]) - v[2]])
+
+
 @dataclasses.dataclass
 class PlaneGraphSpec:
     vertices: list   # ("se3", T34) | ("xyz", p3) | ("plane", c4) in creation order
@@ -311,7 +324,6 @@ def make_plane_graph(n_kf: int = 40, n_planes: int = 6, n_lm: int = 8, seed: int
                      plane_sigma=(0.01, 0.01, 0.02)) -> PlaneGraphSpec:
     """Keyframes on a lawn-mower path observing wall-like planes (and a few point landmarks): every keyframe
     sees 3 planes; the measurement is the plane in the robot frame, perturbed through Plane3D::oplus."""
-    import oracle  # only for Plane3D::oplus when perturbing measurements (generator, not a back-end path)
     rng = np.random.default_rng(seed)
     base = make_graph(n_kf, max(n_lm, 1), obs_per_kf=2, seed=seed, name="plane_base")
     gt = base.gt_pose
@@ -339,7 +351,7 @@ def make_plane_graph(n_kf: int = 40, n_planes: int = 6, n_lm: int = 8, seed: int
         seen = rng.choice(n_planes, size=min(3, n_planes), replace=False)
         for j in seen:
             local = plane_transform(T_inv(gt[k]), planes[j])
-            meas = oracle.plane_oplus(local, rng.normal(0, 1, 3) * np.array(plane_sigma))
+            meas = plane_perturb(local, rng.normal(0, 1, 3) * np.array(plane_sigma))
             if j not in plane_vid:
                 plane_vid[j] = len(vertices)
                 vertices.append(("plane", plane_transform(base.vpose[np.flatnonzero(base.vkind == 0)[k]], meas)))
@@ -366,3 +378,58 @@ def load_plane_graph(backend, spec: PlaneGraphSpec):
         else:
             backend.add_se3_plane_edge(ids[e[1]], ids[e[2]], e[3], spec.info_plane)
     return ids
+
+
+# --------------------------------------------------------------------------------------------
+# Per-frame stream (BASELINE.json configs[4]: segment + associate + optimise per frame)
+# --------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class FrameStream:
+    odom: np.ndarray        # (n_kf,3,4) raw VIO odometry poses (chained noisy increments)
+    detections: list        # per keyframe: [(type, plane_type, pose_cam float32[3], normal float32[4])]
+    gt_pose: np.ndarray
+    gt_landmarks: np.ndarray
+    cam_angle: float
+    info6: np.ndarray
+
+
+def _world_from_cam_matrix(pose6, cam_angle):
+    """double-precision version of semantic_tools::transformNormalsToWorld (tools.h:18-102, including the sy*sp term
+    of :80-81) used only to synthesise camera-frame detections that land where the ground truth is."""
+    roll, pitch, yaw = pose6[3], pose6[4], pose6[5]
+    cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+    T = np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sp],
+                  [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                  [-sp, cp * sr, cp * cr]])
+    a = -1.5708
+    Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    Rx = np.array([[1.0, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    c = -cam_angle
+    Rc = np.array([[1.0, 0, 0], [0, np.cos(c), -np.sin(c)], [0, np.sin(c), np.cos(c)]])
+    return T @ Rz @ Rx @ Rc
+
+
+def make_frame_stream(n_kf: int = 60, n_lm: int = 12, seed: int = SEED_BASE + 5, view_radius: float = 5.0,
+                      max_det: int = 3, meas_sigma: float = 0.03, cam_angle: float = 0.1) -> FrameStream:
+    """Keyframes along a lawn-mower path; every keyframe detects up to `max_det` of the landmarks within
+    `view_radius` (so a landmark is seen from a run of consecutive keyframes), reported as camera-frame centroids."""
+    from .semantic_graph_slam import matrix2vector
+    rng = np.random.default_rng(seed)
+    base = make_graph(n_kf, n_lm, obs_per_kf=1, seed=seed, name="frames")
+    gt = base.gt_pose
+    odom = base.vpose[base.vkind == 0]
+    lm = base.gt_xyz
+    dets = []
+    for k in range(n_kf):
+        p6 = matrix2vector(gt[k]).astype(np.float64)
+        M = _world_from_cam_matrix(p6, cam_angle)
+        d = np.linalg.norm(lm[:, :2] - gt[k][:2, 3], axis=1)
+        near = np.argsort(d)[:max_det]
+        near = [int(j) for j in near if d[j] < view_radius]
+        frame = []
+        for j in near:
+            cam = np.linalg.solve(M, lm[j] - gt[k][:, 3]) + rng.normal(0, meas_sigma, 3)
+            ptype = int(j % 2)     # "horizontal" / "vertical"
+            frame.append((0, ptype, cam.astype(np.float32), np.array([0, 0, 1, 0], dtype=np.float32)))
+        dets.append(frame)
+    return FrameStream(odom, dets, gt, lm, cam_angle, base.einfo6)

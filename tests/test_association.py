@@ -1,0 +1,106 @@
+"""Landmark association: the product's host implementation (C-ABI ssb_assoc_*) against the
+independent float32 oracle restatement, bit for bit, plus hand-checkable frames.  No GPU needed: the step is host
+code in the reference as well (data_association.h:75-389, tools.h:18-135)."""
+import numpy as np
+import pytest
+
+from oracle.association import OracleDataAssociation, transform_normals_to_world, transform_cam_to_robot, dist
+from semantic_slam_b200 import DataAssociation
+
+KITTI = dict(use_maha_dist=False, use_eq_dist=True, eq_dist_thres=1.5, land_noise_low=0.1)   # config/yolo_detector_kitti.yaml:17-20
+
+
+def _frames(seed, n_frames=25, n_det=4):
+    rng = np.random.default_rng(seed)
+    anchors = rng.uniform(-4, 4, (6, 3)) + np.array([0, 0, 6.0])
+    for f in range(n_frames):
+        rp = np.array([0.3 * f, 0.05 * f, 0.02 * f, rng.normal(0, 0.02), rng.normal(0, 0.02), 0.05 * f], dtype=np.float32)
+        dets = []
+        for _ in range(n_det):
+            a = anchors[rng.integers(0, len(anchors))] + rng.normal(0, 0.15, 3)
+            dets.append((int(rng.integers(0, 2)), int(rng.integers(0, 2)), a.astype(np.float32),
+                         rng.normal(0, 1, 4).astype(np.float32)))
+        yield rp, dets
+
+
+def _same(A, O):
+    assert [(x.id, x.is_new_landmark) for x in A] == [(y.id, y.is_new_landmark) for y in O]
+    for x, y in zip(A, O):
+        assert np.array_equal(x.pose, y.pose) and np.array_equal(x.local_pose, y.local_pose)
+        assert np.array_equal(x.normal_orientation, y.normal_orientation)
+        assert np.array_equal(x.covariance, y.covariance) and np.array_equal(x.information, y.information)
+
+
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_euclidean_gate_bit_exact(seed, strict):
+    a, o = DataAssociation(strict=strict, **KITTI), OracleDataAssociation(strict=strict, **KITTI)
+    matched = 0
+    for rp, dets in _frames(seed):
+        A, O = a.find_matches(dets, rp, 0.17), o.find_matches(dets, rp, 0.17)
+        _same(A, O)
+        matched += sum(not x.is_new_landmark for x in A)
+        for lid in range(a.num_landmarks()):   # as after an optimize: refreshed node estimates
+            est = o.landmarks[lid].node_estimate + 0.01
+            a.setLandmarkEstimate(lid, est)
+            o.setLandmarkEstimate(lid, est)
+    assert a.num_landmarks() == o.num_landmarks() > 4 and matched > 10
+
+
+def test_mahalanobis_gate_bit_exact():
+    kw = dict(use_maha_dist=True, maha_dist_thres=3.0, land_noise_low=0.4)
+    a, o = DataAssociation(**kw), OracleDataAssociation(**kw)
+    rng = np.random.default_rng(7)
+    for rp, dets in _frames(11):
+        _same(a.find_matches(dets, rp, 0.0), o.find_matches(dets, rp, 0.0))
+        for lid in range(a.num_landmarks()):
+            B = rng.normal(0, 0.1, (3, 3))
+            cov = (B @ B.T + 0.05 * np.eye(3)).astype(np.float32)
+            a.setLandmarkCovs(lid, cov)
+            o.setLandmarkCovs(lid, cov)
+
+
+def test_axis_convention_of_the_camera_chain():
+    """cam (x right, y down, z forward) -> robot (x forward, y left, z up): rot_z(-90) rot_x(-90), tools.h:104-135"""
+    M = transform_cam_to_robot(0.0).astype(np.float64)
+    v = M @ np.array([1.0, 2.0, 3.0, 1.0])
+    assert np.allclose(v[:3], [3.0, -1.0, -2.0], atol=1e-4)
+    a = DataAssociation(**KITTI)
+    rp = np.array([10.0, -2.0, 0.5, 0, 0, np.pi / 2], dtype=np.float32)   # robot facing +y
+    l = a.find_matches([(0, 0, np.array([1.0, 2.0, 3.0], dtype=np.float32), np.array([0, 0, 1, 0], dtype=np.float32))], rp, 0.0)[0]
+    assert l.is_new_landmark and l.id == 0
+    assert np.allclose(l.local_pose, [3.0, -1.0, -2.0], atol=1e-4)
+    assert np.allclose(l.pose, [10.0 + 1.0, -2.0 + 3.0, 0.5 - 2.0], atol=1e-3)   # forward 3 m -> +y, left 1 m -> -x ... +x: -(-1)
+    assert np.allclose(np.diag(l.information), 1.0 / np.float32(0.1), rtol=1e-6)
+
+
+def test_quirk_h7_term_is_reproduced():
+    """T_robot_world(0,2) = cy*sp*cr + sy*sp (tools.h:80-81), not the textbook sy*sr"""
+    p = np.array([0, 0, 0, 0.3, 0.2, 0.4], dtype=np.float32)
+    M = transform_normals_to_world(p, 0.0).astype(np.float64)
+    cy, sy, sp, cr, sr = np.cos(0.4), np.sin(0.4), np.sin(0.2), np.cos(0.3), np.sin(0.3)
+    rz = np.array([[0, 1, 0], [-1, 0, 0], [0, 0, 1.0]])   # rot_z(-90), up to the 1.5708 rounding
+    rx = np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0.0]])   # rot_x(-90)
+    T02 = (M[:3, :3] @ np.linalg.inv(rz @ rx))[0, 2]
+    assert abs(T02 - (cy * sp * cr + sy * sp)) < 1e-4
+    assert abs(T02 - (cy * sp * cr + sy * sr)) > 1e-2
+
+
+def test_quirk_h4_stale_minimum_changes_the_outcome():
+    """distance_min is never reset between detections (data_association.h:100-107): a later detection that is far
+    from everything inherits the previous detection's match; strict mode maps a new landmark instead."""
+    det = lambda x: (0, 0, np.array([x, 0.0, 5.0], dtype=np.float32), np.array([0, 0, 1, 0], dtype=np.float32))
+    rp = np.zeros(6, dtype=np.float32)
+    out = {}
+    for strict in (False, True):
+        a = DataAssociation(strict=strict, **KITTI)
+        a.find_matches([det(0.0)], rp, 0.0)                    # landmark 0
+        res = a.find_matches([det(0.05), det(30.0)], rp, 0.0)  # near landmark 0, then far away
+        out[strict] = [(r.id, r.is_new_landmark) for r in res]
+    assert out[False] == [(0, False), (0, False)]
+    assert out[True] == [(0, False), (1, True)]
+
+
+def test_dist_is_single_precision():
+    d = dist(np.float32(0.1), np.float32(0.4), np.float32(0.2), np.float32(0.2), np.float32(-1.0), np.float32(3.0))
+    assert d.dtype == np.float32 and abs(float(d) - np.sqrt(0.09 + 16.0)) < 1e-6

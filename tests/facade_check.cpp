@@ -4,9 +4,28 @@
 #include <cstdio>
 #include "ps_graph_slam/graph_slam.hpp"
 #include "planar_segmentation/plane_segmentation_b200.h"
+#include "ps_graph_slam/data_association_b200.h"
 
 int main(int argc, char** argv) {
   const bool run = argc > 1;  // without arguments: construct nothing (no GPU needed), just prove it links
+  {
+    // association facade (host only): first frame maps, second frame matches
+    ssb_assoc_opts ao;
+    ssb_assoc_default_opts(&ao);
+    ao.use_maha_dist = 0;
+    ao.use_eq_dist = 1;
+    ao.eq_dist_thres = 1.5;
+    ssb_host::data_association da(false, &ao);
+    ssb_host::detected_object d;
+    d.pose[2] = 4.0f;
+    const float rp[6] = {0, 0, 0, 0, 0, 0};
+    auto first = da.find_matches({d}, rp, 0.0f);
+    if (first.size() != 1 || !first[0].is_new_landmark) return 7;
+    da.assignLandmarkNode(0, [&](double p[3]) { for (int k = 0; k < 3; ++k) p[k] = first[0].pose[k]; });
+    d.pose[0] = 0.1f;
+    auto second = da.find_matches({d}, rp, 0.0f);
+    if (second.size() != 1 || second[0].is_new_landmark || second[0].id != 0) return 8;
+  }
   if (!run) {
     std::printf("facade linked: %s\n", ssb_build_info());
     return 0;

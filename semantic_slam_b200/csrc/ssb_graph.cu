@@ -177,6 +177,8 @@ struct ssb_graph {
   bool ainv_valid = false;   // d_ainv holds the rows of a previously inverted coarse matrix
   int solves_since_refresh = 0;
   DBuf<int> d_run_lm, d_run_group, d_run_e0, d_lm_run_rowptr, d_grp_run_rowptr, d_grp_runs;
+  DBuf<int> d_run1_lm, d_run1_e0, d_agg_run_rowptr, d_agg_runs;
+  DBuf<double> d_Grun1;
   DBuf<BarSlot> d_slots;
   CoarseDev Cz;
   size_t pcg_smem = 0, pcgw_smem = 0;
@@ -578,6 +580,30 @@ static int prepare(ssb_graph* g) {
       std::vector<int> f(grp_run_rowptr.begin(), grp_run_rowptr.end() - 1);
       for (int r = 0; r < n_runs; ++r) grp_runs[f[run_group[r]]++] = r;
     }
+    // the same run structure for the middle level: (landmark, 5-pose aggregate) runs, grouped by aggregate
+    const int n_agg = (Np + 4) / 5;
+    std::vector<int> run1_lm, run1_agg, run1_e0, agg_run_rowptr(n_agg + 1, 0);
+    for (int l = 0; l < Nl; ++l) {
+      int prev = -1;
+      for (int e = lm_rowptr[l]; e < lm_rowptr[l + 1]; ++e) {
+        const int ag = plL[e].p / 5;
+        if (ag != prev) {
+          run1_lm.push_back(l);
+          run1_agg.push_back(ag);
+          run1_e0.push_back(e);
+          prev = ag;
+        }
+      }
+    }
+    run1_e0.push_back(El);
+    const int n_runs1 = (int)run1_lm.size();
+    std::vector<int> agg_runs(std::max(n_runs1, 1));
+    for (int r = 0; r < n_runs1; ++r) agg_run_rowptr[run1_agg[r] + 1]++;
+    for (int a = 0; a < n_agg; ++a) agg_run_rowptr[a + 1] += agg_run_rowptr[a];
+    {
+      std::vector<int> f(agg_run_rowptr.begin(), agg_run_rowptr.end() - 1);
+      for (int r = 0; r < n_runs1; ++r) agg_runs[f[run1_agg[r]]++] = r;
+    }
     // pose-major index over L-order positions
     std::vector<int> ppl_rowptr(Np + 1, 0);
     for (int k = 0; k < El; ++k) ppl_rowptr[plL[k].p + 1]++;
@@ -636,7 +662,7 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_v.ensure((size_t)3 * (Nl + 64)));
     SSB_TRY(g->d_mg.ensure(16));
     SSB_TRY(g->d_dl.ensure((size_t)3 * Nl));
-    const size_t nb_bs = (size_t)(Np + Nl + 127) / 128 + 1;
+    const size_t nb_bs = ((size_t)Np + (size_t)32 * Nl + 127) / 128 + 1;
     SSB_TRY(g->d_part.ensure(std::max<size_t>(3 * PART_STRIDE, nb_bs) + 4096));
     SSB_TRY(g->d_scalars.ensure(32));
     SSB_TRY(g->d_iscalars.ensure(4));
@@ -740,6 +766,11 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_lm_run_rowptr.ensure(Nl + 1));
     SSB_TRY(g->d_grp_run_rowptr.ensure(nblk + 1));
     SSB_TRY(g->d_grp_runs.ensure(n_runs));
+    SSB_TRY(g->d_run1_lm.ensure(n_runs1));
+    SSB_TRY(g->d_run1_e0.ensure(n_runs1 + 1));
+    SSB_TRY(g->d_agg_run_rowptr.ensure(n_agg + 1));
+    SSB_TRY(g->d_agg_runs.ensure(n_runs1));
+    SSB_TRY(g->d_Grun1.ensure((size_t)18 * n_runs1));
     SSB_TRY(g->d_slots.ensure((size_t)2 * nblk + 1));
     SSB_TRY(g->d_ainv.ensure((size_t)nblk * 6 * ncoarse));
     SSB_TRY(g->d_ucell.ensure((size_t)6 * (Np + 64) + (size_t)3 * (Nl + 64)));   // u cells, then v cells
@@ -760,6 +791,12 @@ static int prepare(ssb_graph* g) {
       SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_runs.p, grp_runs.data(), n_runs * sizeof(int), cudaMemcpyHostToDevice, s));
     }
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_run_e0.p, run_e0.data(), (n_runs + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (n_runs1) {
+      SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_run1_lm.p, run1_lm.data(), n_runs1 * sizeof(int), cudaMemcpyHostToDevice, s));
+      SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_agg_runs.p, agg_runs.data(), n_runs1 * sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_run1_e0.p, run1_e0.data(), (n_runs1 + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_agg_run_rowptr.p, agg_run_rowptr.data(), (n_agg + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_run_rowptr.p, lm_run_rowptr.data(), (Nl + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_run_rowptr.p, grp_run_rowptr.data(), (nblk + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     {
@@ -781,6 +818,12 @@ static int prepare(ssb_graph* g) {
       Cz.n_runs = n_runs;
       Cz.panel = g->d_panel.p;
       Cz.reuse_inverse = 0;
+      Cz.Grun1 = g->d_Grun1.p;
+      Cz.run1_lm = g->d_run1_lm.p;
+      Cz.run1_e0 = g->d_run1_e0.p;
+      Cz.agg_run_rowptr = g->d_agg_run_rowptr.p;
+      Cz.agg_runs = g->d_agg_runs.p;
+      Cz.n_runs1 = n_runs1;
       Cz.ainv_store = g->d_ainv.p;
     }
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_scalars.p, 0, 32 * sizeof(double), s));
@@ -873,7 +916,7 @@ static int launch_chi2(ssb_graph* g) {
 static int launch_linearize(ssb_graph* g) {
   DevGraph& G = g->G;
   if (G.Nl) {
-    k_lin_landmarks<<<(G.Nl + 127) / 128, 128, 0, g->stream>>>(G);
+    k_lin_landmarks<<<(32 * G.Nl + 127) / 128, 128, 0, g->stream>>>(G);
     g->launches++;
   }
   if (G.Np) {
@@ -883,6 +926,10 @@ static int launch_linearize(ssb_graph* g) {
   if (g->Cz.sub_enabled && G.Np) {
     k_sub_basis<<<((G.Np + 4) / 5 + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
     g->launches++;
+    if (g->Cz.n_runs1) {
+      k_sub_runs<<<(g->Cz.n_runs1 + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
+      g->launches++;
+    }
   }
   if (g->Cz.enabled) {
     k_coarse_basis<<<g->pcg_grid, 256, 0, g->stream>>>(G, g->Cz);
@@ -919,7 +966,7 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
   SSB_TRY(launch_prep(g, lambda));
   SSB_TRY(launch_pcg(g, lambda));
   if (apply) {
-    k_backsub_update<<<(G.Np + G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
+    k_backsub_update<<<(G.Np + 32 * G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
     g->launches++;
   }
   SSB_CUDA_CHECK(cudaGetLastError());
@@ -1062,7 +1109,7 @@ static int launch_solve_mg(ssb_graph* g, double lambda) {
   }
   SSB_NCCL_CHECK(N.AllGather(G.x + (size_t)6 * rank * cp, G.x, (size_t)6 * cp, kNcclFloat64, g->comm, s));
   k_mg_finish<<<1, 1, 0, s>>>(mg, G.iscalars, G.scalars);
-  k_backsub_update<<<(G.Np + G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
+  k_backsub_update<<<(G.Np + 32 * G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
   g->launches += 2;
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;
@@ -1396,7 +1443,7 @@ int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len) {
     SSB_TRY(g->d_lm_snap.ensure((size_t)4 * g->G.Nl));
     g->have_snapshot = false;
     k_copy_state<<<(n + 255) / 256, 256, 0, g->stream>>>(g->d_pose_snap.p, g->G.pose, g->G.Np, g->d_lm_snap.p, g->G.lm, g->G.Nl);
-    k_backsub_update<<<(g->G.Np + g->G.Nl + 127) / 128, 128, 0, g->stream>>>(g->G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
+    k_backsub_update<<<(g->G.Np + 32 * g->G.Nl + 127) / 128, 128, 0, g->stream>>>(g->G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
     k_copy_state<<<(n + 255) / 256, 256, 0, g->stream>>>(g->G.pose, g->d_pose_snap.p, g->G.Np, g->G.lm, g->d_lm_snap.p, g->G.Nl);
     g->launches += 3;
   }

@@ -92,11 +92,13 @@ __device__ __forceinline__ void pl_edge_err(const DevGraph& G, const PLEdge& ed,
 // (BlockSolver::buildSystem -> EdgeSE3PointXYZ::linearizeOplus + constructQuadraticForm)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_lin_landmarks(DevGraph G) {
-  int l = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per landmark, one lane per edge (stride 32); fixed-order butterfly sums => deterministic
+  const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (l >= G.Nl) return;
   const bool lfixed = G.lm_fixed[l] != 0;
   double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
-  for (int e = G.lm_rowptr[l]; e < G.lm_rowptr[l + 1]; ++e) {
+  for (int e = G.lm_rowptr[l] + lane; e < G.lm_rowptr[l + 1]; e += 32) {
     const PLEdge ed = G.pl[e];
     const Pose X = G.pose[ed.p];
     double err[3], Jp[18], R[9];  // R = Jl' (= the pose rotation for a point landmark)
@@ -123,12 +125,16 @@ __global__ void __launch_bounds__(128) k_lin_landmarks(DevGraph G) {
       for (int c = 0; c < 6; ++c)
         out[6 * r + c] = zero ? 0.0 : RW[3 * r] * Jp[c] + RW[3 * r + 1] * Jp[6 + c] + RW[3 * r + 2] * Jp[12 + c];
   }
+  for (int k = 0; k < 6; ++k) H[k] = warp_sum(H[k]);
+  for (int k = 0; k < 3; ++k) b[k] = warp_sum(b[k]);
   if (lfixed) {
     H[0] = H[3] = H[5] = 1.0;
     H[1] = H[2] = H[4] = 0.0;
   }
-  for (int k = 0; k < 6; ++k) G.Hll[6 * (size_t)l + k] = H[k];
-  for (int k = 0; k < 3; ++k) G.bl[3 * (size_t)l + k] = b[k];
+  if (lane == 0) {
+    for (int k = 0; k < 6; ++k) G.Hll[6 * (size_t)l + k] = H[k];
+    for (int k = 0; k < 3; ++k) G.bl[3 * (size_t)l + k] = b[k];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -322,6 +328,13 @@ struct CoarseDev {
   double* ainv_store;      // [gridDim.x][6*nc] rows of A_c^-1 kept between solves
   double* B1mat;           // [Np][36] prolongation blocks about the 5-pose centroid
   double* D1inv;           // [ceil(Np/5)][36] inverse of P1' S P1 diagonal blocks (zero = level off for the aggregate)
+  // (landmark, 5-pose aggregate) runs of the L-order edge table, built on the host like the per-CTA runs above
+  double* Grun1;           // [n_runs1][18] (3x6) = sum_e HplL_e B1_p(e) over the run
+  const int* run1_lm;      // [n_runs1]
+  const int* run1_e0;      // [n_runs1+1]
+  const int* agg_run_rowptr;  // [n_agg+1]
+  const int* agg_runs;        // runs sorted by aggregate (landmark order inside an aggregate)
+  int n_runs1;
 };
 
 struct BarSlot {  // one 64 B line per CTA and buffer; slot [2*gridDim.x] holds the arrival counter
@@ -556,6 +569,25 @@ __global__ void __launch_bounds__(128) k_sub_basis(DevGraph G, CoarseDev Cz) {
   }
 }
 
+// per LM iteration: Grun1 of every (landmark, 5-pose aggregate) run.  One thread per run.
+__global__ void __launch_bounds__(128) k_sub_runs(DevGraph G, CoarseDev Cz) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Cz.n_runs1) return;
+  double acc[18];
+  for (int k = 0; k < 18; ++k) acc[k] = 0.0;
+  for (int e = Cz.run1_e0[r]; e < Cz.run1_e0[r + 1]; ++e) {
+    const double* Hl = G.HplL + 18 * (size_t)e;
+    const double* B = Cz.B1mat + 36 * (size_t)G.pl[e].p;
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 6; ++c) {
+        double t = 0.0;
+        for (int k = 0; k < 6; ++k) t += Hl[6 * a + k] * B[6 * k + c];
+        acc[6 * a + c] += t;
+      }
+  }
+  for (int k = 0; k < 18; ++k) Cz.Grun1[18 * (size_t)r + k] = acc[k];
+}
+
 // per damped trial: D1 = P1' S P1 restricted to the aggregate (6x6), inverted.  One thread per aggregate.
 __global__ void __launch_bounds__(64) k_sub_assemble(DevGraph G, CoarseDev Cz, double lambda) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -606,42 +638,18 @@ __global__ void __launch_bounds__(64) k_sub_assemble(DevGraph G, CoarseDev Cz, d
         }
     }
   }
-  // landmark terms: entries of my poses are contiguous in P-order
-  const int q0 = G.pose_pl_rowptr[i0], q1 = min(G.pose_pl_rowptr[i1], q0 + 64);
-  for (int qa = q0; qa < q1; ++qa) {
-    const int l = G.plP_lm[qa];
-    bool leader = true;
-    for (int qb = q0; qb < qa; ++qb)
-      if (G.plP_lm[qb] == l) {
-        leader = false;
-        break;
-      }
-    if (!leader) continue;
-    double Gm[18];  // 6x3
-    for (int k = 0; k < 18; ++k) Gm[k] = 0.0;
-    int ip = i0;
-    for (int qb = qa; qb < q1; ++qb) {
-      if (G.plP_lm[qb] != l) continue;
-      while (qb >= G.pose_pl_rowptr[ip + 1]) ++ip;
-      // entries qa.. may belong to later poses; ip only moves forward because qb is increasing
-      const double* B = Cz.B1mat + 36 * (size_t)ip;
-      const double* Hp = G.HplP + 18 * (size_t)qb;  // 6x3
-      for (int r = 0; r < 6; ++r)
-        for (int c = 0; c < 3; ++c) {
-          double t = 0.0;
-          for (int k = 0; k < 6; ++k) t += B[6 * k + r] * Hp[3 * k + c];
-          Gm[3 * r + c] += t;
-        }
-    }
-    const double* Wu = G.HllInv + 6 * (size_t)l;
+  // landmark terms: D -= sum over my (landmark, aggregate) runs of G' W G with G = Grun1 (3x6)
+  for (int q = Cz.agg_run_rowptr[a]; q < Cz.agg_run_rowptr[a + 1]; ++q) {
+    const int r1 = Cz.agg_runs[q];
+    const double* Gr = Cz.Grun1 + 18 * (size_t)r1;
+    const double* Wu = G.HllInv + 6 * (size_t)Cz.run1_lm[r1];
     const double W[9] = {Wu[0], Wu[1], Wu[2], Wu[1], Wu[3], Wu[4], Wu[2], Wu[4], Wu[5]};
-    double GW[18];
+    double WG[18];  // W * G (3x6)
+    for (int u = 0; u < 3; ++u)
+      for (int c = 0; c < 6; ++c) WG[6 * u + c] = W[3 * u] * Gr[c] + W[3 * u + 1] * Gr[6 + c] + W[3 * u + 2] * Gr[12 + c];
     for (int r = 0; r < 6; ++r)
-      for (int c = 0; c < 3; ++c) GW[3 * r + c] = Gm[3 * r] * W[c] + Gm[3 * r + 1] * W[3 + c] + Gm[3 * r + 2] * W[6 + c];
-    for (int r = 0; r < 6; ++r)
-      for (int c = 0; c < 6; ++c) D[6 * r + c] -= GW[3 * r] * Gm[3 * c] + GW[3 * r + 1] * Gm[3 * c + 1] + GW[3 * r + 2] * Gm[3 * c + 2];
+      for (int c = 0; c < 6; ++c) D[6 * r + c] -= Gr[r] * WG[c] + Gr[6 + r] * WG[6 + c] + Gr[12 + r] * WG[12 + c];
   }
-  // the first entries belong to pose i0: make sure the pose walk above started right
   if (!any || !inv_spd6(D))
     for (int k = 0; k < 36; ++k) D[k] = 0.0;
   for (int k = 0; k < 36; ++k) Cz.D1inv[36 * (size_t)a + k] = D[k];
@@ -1381,12 +1389,13 @@ __global__ void __launch_bounds__(256) k_mg_p4(DevGraph G, MgRange R, double* mg
 __global__ void __launch_bounds__(128) k_backsub_update(DevGraph G, double lambda, Pose* pose_bak, double* lm_bak) {
   __shared__ double sh[33];
   __shared__ int is_last;
+  // threads [0, 32 Nl): one warp per landmark (lane per edge); threads [32 Nl, 32 Nl + Np): one thread per pose
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   double sc = 0.0;
-  if (t < G.Nl) {
-    const int l = t;
-    double a[3] = {G.bl[3 * (size_t)l], G.bl[3 * (size_t)l + 1], G.bl[3 * (size_t)l + 2]};
-    for (int e = G.lm_rowptr[l]; e < G.lm_rowptr[l + 1]; ++e) {
+  if (t < 32 * G.Nl) {
+    const int l = t >> 5, lane = t & 31;
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int e = G.lm_rowptr[l] + lane; e < G.lm_rowptr[l + 1]; e += 32) {
       const double* Hl = G.HplL + 18 * (size_t)e;
       const double* dp = G.x + 6 * (size_t)G.pl[e].p;
       for (int c = 0; c < 6; ++c) {
@@ -1395,27 +1404,30 @@ __global__ void __launch_bounds__(128) k_backsub_update(DevGraph G, double lambd
         a[2] -= Hl[12 + c] * dp[c];
       }
     }
-    const double* Wi = G.HllInv + 6 * (size_t)l;
-    double d[3] = {Wi[0] * a[0] + Wi[1] * a[1] + Wi[2] * a[2], Wi[1] * a[0] + Wi[3] * a[1] + Wi[4] * a[2],
-                   Wi[2] * a[0] + Wi[4] * a[1] + Wi[5] * a[2]};
-    if (G.lm_fixed[l]) d[0] = d[1] = d[2] = 0.0;
-    double cur[4];
-    for (int c = 0; c < 4; ++c) {
-      cur[c] = G.lm[4 * (size_t)l + c];
-      lm_bak[4 * (size_t)l + c] = cur[c];
+    for (int k = 0; k < 3; ++k) a[k] = warp_sum(a[k]) + G.bl[3 * (size_t)l + k];
+    if (lane == 0) {
+      const double* Wi = G.HllInv + 6 * (size_t)l;
+      double d[3] = {Wi[0] * a[0] + Wi[1] * a[1] + Wi[2] * a[2], Wi[1] * a[0] + Wi[3] * a[1] + Wi[4] * a[2],
+                     Wi[2] * a[0] + Wi[4] * a[1] + Wi[5] * a[2]};
+      if (G.lm_fixed[l]) d[0] = d[1] = d[2] = 0.0;
+      double cur[4];
+      for (int c = 0; c < 4; ++c) {
+        cur[c] = G.lm[4 * (size_t)l + c];
+        lm_bak[4 * (size_t)l + c] = cur[c];
+      }
+      if (pl_is_plane(G, l)) {
+        if (!G.lm_fixed[l]) plane_oplus(cur, d);  // VertexPlane::oplusImpl
+      } else {
+        for (int c = 0; c < 3; ++c) cur[c] += d[c];  // VertexPointXYZ::oplusImpl
+      }
+      for (int c = 0; c < 4; ++c) G.lm[4 * (size_t)l + c] = cur[c];
+      for (int c = 0; c < 3; ++c) {
+        G.dl[3 * (size_t)l + c] = d[c];
+        sc += d[c] * (lambda * d[c] + G.bl[3 * (size_t)l + c]);
+      }
     }
-    if (pl_is_plane(G, l)) {
-      if (!G.lm_fixed[l]) plane_oplus(cur, d);  // VertexPlane::oplusImpl
-    } else {
-      for (int c = 0; c < 3; ++c) cur[c] += d[c];  // VertexPointXYZ::oplusImpl
-    }
-    for (int c = 0; c < 4; ++c) G.lm[4 * (size_t)l + c] = cur[c];
-    for (int c = 0; c < 3; ++c) {
-      G.dl[3 * (size_t)l + c] = d[c];
-      sc += d[c] * (lambda * d[c] + G.bl[3 * (size_t)l + c]);
-    }
-  } else if (t < G.Nl + G.Np) {
-    const int i = t - G.Nl;
+  } else if (t < 32 * G.Nl + G.Np) {
+    const int i = t - 32 * G.Nl;
     Pose X = G.pose[i];
     pose_bak[i] = X;
     double d[6];

@@ -182,7 +182,7 @@ struct ssb_graph {
   DBuf<BarSlot> d_slots;
   CoarseDev Cz;
   size_t pcg_smem = 0, pcgw_smem = 0;
-  DBuf<int> d_ft_ulm_rowptr, d_ft_ulm, d_ft_pl_loc, d_ft_upp_rowptr, d_ft_upp, d_ft_pp_loc, d_ft_pp_src, d_ft_ext_rowptr, d_ft_ext;
+  DBuf<int> d_ft_ulm_rowptr, d_ft_ulm, d_ft_pl_loc, d_ft_upp_rowptr, d_ft_upp, d_ft_pp_loc, d_ft_pp_src, d_ft_ext_rowptr, d_ft_ext, d_ft_gj_order;
   FlowTabs FT;
   DBuf<uint4> d_ucell, d_lines, d_gj;
   DBuf<unsigned long long> d_trace;
@@ -509,6 +509,72 @@ static int sync_estimates_to_host(ssb_graph* g) {
     if (_r != SSB_OK) return _r; \
   } while (0)
 
+// Nested-dissection pivot order for the block Gauss-Jordan of the coarse matrix A_c (k_pcg_flow prologue).
+// Aggregates are adjacent when a pose-pose edge links them or they observe a common landmark.  With separators
+// eliminated last, rows of one subdomain have an exactly-zero block in the pivot column of another subdomain,
+// so they skip those steps, and independent subdomains are inverted concurrently: the critical path of the
+// data-flow elimination shrinks from N steps to the depth of the elimination tree.
+static void nd_order_rec(const std::vector<std::vector<int>>& adj, std::vector<int> nodes, std::vector<char>& in,
+                         std::vector<int>& order) {
+  if (nodes.size() <= 2) {
+    for (int v : nodes) order.push_back(v);
+    return;
+  }
+  for (int v : nodes) in[v] = 1;
+  auto bfs = [&](int src, std::vector<int>& level) {
+    // levels over the induced subgraph; returns the last node reached
+    for (int v : nodes) level[v] = -1;
+    std::vector<int> q{src};
+    level[src] = 0;
+    for (size_t h = 0; h < q.size(); ++h)
+      for (int w : adj[q[h]])
+        if (in[w] && level[w] < 0) {
+          level[w] = level[q[h]] + 1;
+          q.push_back(w);
+        }
+    return q;
+  };
+  std::vector<int> level(adj.size(), -1);
+  std::vector<int> reach = bfs(nodes[0], level);
+  if (reach.size() < nodes.size()) {
+    // disconnected: order every component on its own
+    std::vector<int> rest;
+    for (int v : nodes)
+      if (level[v] < 0) rest.push_back(v);
+    for (int v : nodes) in[v] = 0;
+    nd_order_rec(adj, reach, in, order);
+    nd_order_rec(adj, rest, in, order);
+    return;
+  }
+  reach = bfs(reach.back(), level);   // pseudo-peripheral start
+  reach = bfs(reach.back(), level);
+  const int depth = level[reach.back()];
+  for (int v : nodes) in[v] = 0;
+  if (depth < 2) {  // (nearly) complete graph: no useful separator
+    for (int v : nodes) order.push_back(v);
+    return;
+  }
+  // separator = the BFS level that splits the node count most evenly
+  std::vector<int> cnt(depth + 1, 0);
+  for (int v : nodes) cnt[level[v]]++;
+  int best = 1, acc = cnt[0];
+  long best_score = -1;
+  for (int L = 1; L < depth; ++L) {
+    const long a = acc, b = (long)nodes.size() - acc - cnt[L];
+    const long score = std::min(a, b) * 4 - cnt[L];
+    if (score > best_score) {
+      best_score = score;
+      best = L;
+    }
+    acc += cnt[L];
+  }
+  std::vector<int> A, B, S;
+  for (int v : nodes) (level[v] < best ? A : level[v] > best ? B : S).push_back(v);
+  nd_order_rec(adj, A, in, order);
+  nd_order_rec(adj, B, in, order);
+  for (int v : S) order.push_back(v);
+}
+
 // Build CSR edge tables (initializeOptimization + buildStructure analogue) and upload everything.
 static int prepare(ssb_graph* g) {
   SSB_CUDA_CHECK(cudaSetDevice(g->device));
@@ -750,9 +816,29 @@ static int prepare(ssb_graph* g) {
         SSB_TRY(up(g->d_ft_pp_src, pp_src));
         SSB_TRY(up(g->d_ft_ext_rowptr, ext_rowptr));
         SSB_TRY(up(g->d_ft_ext, ext));
+        // pivot order of the coarse Gauss-Jordan
+        std::vector<std::vector<int>> cadj(nblk);
+        auto link = [&](int a, int b) {
+          if (a == b || a < 0 || b < 0 || a >= nblk || b >= nblk) return;
+          cadj[a].push_back(b);
+          cadj[b].push_back(a);
+        };
+        for (auto& e : g->pp) link(e.i / Cc, e.j / Cc);
+        for (int l = 0; l < Nl; ++l)
+          for (int ra = lm_run_rowptr[l]; ra < lm_run_rowptr[l + 1]; ++ra)
+            for (int rb = ra + 1; rb < lm_run_rowptr[l + 1]; ++rb) link(run_group[ra], run_group[rb]);
+        for (auto& v : cadj) {
+          std::sort(v.begin(), v.end());
+          v.erase(std::unique(v.begin(), v.end()), v.end());
+        }
+        std::vector<int> all(nblk), gj_order;
+        for (int b = 0; b < nblk; ++b) all[b] = b;
+        std::vector<char> in(nblk, 0);
+        nd_order_rec(cadj, all, in, gj_order);
+        SSB_TRY(up(g->d_ft_gj_order, gj_order));
         SSB_CUDA_CHECK(cudaStreamSynchronize(s2));
         g->FT = FlowTabs{g->d_ft_ulm_rowptr.p, g->d_ft_ulm.p, g->d_ft_pl_loc.p, g->d_ft_upp_rowptr.p, g->d_ft_upp.p,
-                         g->d_ft_pp_loc.p, g->d_ft_pp_src.p, g->d_ft_ext_rowptr.p, g->d_ft_ext.p};
+                         g->d_ft_pp_loc.p, g->d_ft_pp_src.p, g->d_ft_ext_rowptr.p, g->d_ft_ext.p, g->d_ft_gj_order.p};
       }
     }
     SSB_TRY(g->d_Bmat.ensure((size_t)36 * Np));

@@ -140,6 +140,7 @@ struct FlowTabs {
   const int* pp_src;      // [2 Epp]  incidence -> slot of the neighbour's u in shared memory | role << 31
   const int* ext_rowptr;  // [nblk+1] neighbour poses owned by other CTAs
   const int* ext;
+  const int* gj_order;    // [nblk] pivot order of the coarse Gauss-Jordan (nested dissection, separators last)
 };
 
 constexpr int PCGW_MAXU = 320;    // distinct landmarks per CTA
@@ -203,15 +204,18 @@ __device__ __forceinline__ bool warp_inv6_fast(double* col) {
 // step).  CTAs whose block in pivot column k is zero skip the step without waiting.
 // Returns true when every pivot block was positive definite.
 template <int NT, int NB>
-__device__ bool coarse_gj_flow(uint4* gj, unsigned tag, double* Arow) {
+__device__ bool coarse_gj_flow(uint4* gj, unsigned tag, double* Arow, const int* order) {
   constexpr int nc = 6 * NB;
   constexpr int PER = (nc + NT - 1) / NT;
   constexpr int PSTRIDE = 6 * nc + 8;
   __shared__ int s_flag;
   __shared__ double piv_sh[40];   // pivot inverse (pivot CTA) or F = my block in pivot column k
+  __shared__ int order_sh[NB];
   if (threadIdx.x == 0) s_flag = 0;
+  for (int q = threadIdx.x; q < NB; q += NT) order_sh[q] = order[q];
   __syncthreads();
-  for (int k = 0; k < NB; ++k) {
+  for (int step = 0; step < NB; ++step) {
+    const int k = order_sh[step];   // pivot aggregate of this step (nested-dissection order)
     uint4* P = gj + (size_t)k * PSTRIDE;
     if ((int)blockIdx.x == k) {
       if (threadIdx.x < 32) {
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
 #ifdef SSB_PCG_TIMERS
       t_asm = clock64();
 #endif
-      use_coarse = coarse_gj_flow<PCGF_THREADS, NB>(F.gj, F.tagbase + 1u, Arow);
+      use_coarse = coarse_gj_flow<PCGF_THREADS, NB>(F.gj, F.tagbase + 1u, Arow, T.gj_order);
       if (use_coarse)
         for (int k = threadIdx.x; k < 6 * nc; k += PCGF_THREADS) Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k] = Arow[k];
     }

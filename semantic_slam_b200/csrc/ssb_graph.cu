@@ -596,6 +596,15 @@ static int prepare(ssb_graph* g) {
       else
         lfix[v.idx] = v.fixed;
     }
+    const bool prep_timing = std::getenv("SSB_PREP_TIMING") != nullptr;
+    double tp0 = wall_ms();
+    auto tick = [&](const char* what) {
+      if (prep_timing) {
+        const double t = wall_ms();
+        std::fprintf(stderr, "[ssb prepare] %-28s %.3f ms\n", what, t - tp0);
+        tp0 = t;
+      }
+    };
     // L-order (stable counting sort by landmark)
     std::vector<int> lm_rowptr(Nl + 1, 0);
     for (auto& e : g->pl) lm_rowptr[e.l + 1]++;
@@ -604,20 +613,24 @@ static int prepare(ssb_graph* g) {
     std::vector<double> zdL(std::max(El, 1), 0.0);
     g->plL_of_edge.assign(El, 0);
     {
-      // L-order: by landmark, then by pose index, then by creation order
-      std::vector<int> ord(El);
-      for (int k = 0; k < El; ++k) ord[k] = k;
-      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
-        const PLEdge &ea = g->pl[a], &eb = g->pl[b];
-        if (ea.l != eb.l) return ea.l < eb.l;
-        return ea.p < eb.p;
-      });
+      // L-order: by landmark, then by pose index, then by creation order — two stable counting-sort passes
+      // (least significant key first)
+      std::vector<int> ord(El), tmp(El);
+      {
+        std::vector<int> cntp(Np + 1, 0);
+        for (int k = 0; k < El; ++k) cntp[g->pl[k].p + 1]++;
+        for (int i = 0; i < Np; ++i) cntp[i + 1] += cntp[i];
+        for (int k = 0; k < El; ++k) tmp[cntp[g->pl[k].p]++] = k;
+        std::vector<int> cntl(lm_rowptr.begin(), lm_rowptr.end() - 1);
+        for (int q = 0; q < El; ++q) ord[cntl[g->pl[tmp[q]].l]++] = tmp[q];
+      }
       for (int pos = 0; pos < El; ++pos) {
         plL[pos] = g->pl[ord[pos]];
         zdL[pos] = g->pl_zd[ord[pos]];
         g->plL_of_edge[ord[pos]] = pos;
       }
     }
+    tick("hessian index + L-order sort");
     // coarse aggregates: one per persistent CTA, contiguous pose ranges of C poses (multiple of 5)
     const int nblk = g->pcg_grid;
     int Cc = (Np + nblk - 1) / nblk;
@@ -690,6 +703,7 @@ static int prepare(ssb_graph* g) {
       ppp_idx[fill3[g->pp[k].i]++] = (k << 1) | 0;
       ppp_idx[fill3[g->pp[k].j]++] = (k << 1) | 1;
     }
+    tick("run lists + CSR");
     // allocate + upload
     SSB_TRY(g->d_pose.ensure(Np));
     SSB_TRY(g->d_pose_bak.ensure(Np));
@@ -752,6 +766,7 @@ static int prepare(ssb_graph* g) {
         }
       }
       g->fast_ok = ok;
+      tick("buffer allocation");
       // gather tables of the data-flow kernel: per CTA the distinct landmarks / pose-pose edges / external
       // neighbour poses its keyframe range touches, and per incidence the slot inside those lists
       std::vector<int> ulm_rowptr(nblk + 1, 0), ulm, pl_loc(std::max(El, 1), 0), upp_rowptr(nblk + 1, 0), upp,
@@ -927,7 +942,9 @@ static int prepare(ssb_graph* g) {
     if (El) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pl_idx.p, ppl_idx.data(), (size_t)El * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pp_rowptr.p, ppp_rowptr.data(), (Np + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     if (Epp) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pp_idx.p, ppp_idx.data(), (size_t)2 * Epp * sizeof(int), cudaMemcpyHostToDevice, s));
+    tick("flow tables + ND order + enqueue uploads");
     SSB_CUDA_CHECK(cudaStreamSynchronize(s));  // host vectors above go out of scope
+    tick("upload sync");
     g->structure_dirty = false;
     if (g->mg_graph) {
       cudaGraphExecDestroy(g->mg_graph);

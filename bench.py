@@ -301,7 +301,7 @@ def main():
                 "d2h_bytes_per_step": gb["d2h"] + 96 * (e2e_trials + 2), "ms_per_step": 1e3 * t_e2e / e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"kernel": "k_pcg (persistent Schur-complement PCG)", "bound": "hbm", "achieved": achieved,
+        "roofline": {"kernel": "k_pcg_flow<148> (persistent data-flow Schur-complement PCG, coarse Gauss-Jordan included)", "bound": "hbm", "achieved": achieved,
                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                      "peak_source": peak_src,
                      "note": "algorithmic bytes = pcg iterations x B_cg (%d B, SURVEY 8d) / CUDA-event time of the "

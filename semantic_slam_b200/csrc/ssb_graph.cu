@@ -182,7 +182,8 @@ struct ssb_graph {
   DBuf<BarSlot> d_slots;
   CoarseDev Cz;
   size_t pcg_smem = 0, pcgw_smem = 0;
-  DBuf<int> d_ft_ulm_rowptr, d_ft_ulm, d_ft_pl_loc, d_ft_upp_rowptr, d_ft_upp, d_ft_pp_loc, d_ft_pp_src, d_ft_ext_rowptr, d_ft_ext, d_ft_gj_order;
+  DBuf<int> d_ft_ulm_rowptr, d_ft_ulm, d_ft_pl_loc, d_ft_upp_rowptr, d_ft_upp, d_ft_pp_loc, d_ft_pp_src, d_ft_ext_rowptr, d_ft_ext, d_ft_gj_order, d_ft_part_lm, d_ft_part_e0, d_ft_part_e1, d_ft_lm_partbase;
+  int flow_n_parts = 0;
   FlowTabs FT;
   DBuf<uint4> d_ucell, d_lines, d_gj;
   DBuf<unsigned long long> d_trace;
@@ -751,13 +752,26 @@ static int prepare(ssb_graph* g) {
     {
       // does the graph fit the on-chip resident kernel?  (<= 80 poses per CTA, bounded incidence lists,
       // one landmark per warp, <= 64 edges per landmark, bounded overflow per CTA)
-      bool ok = g->allow_fast && g->use_flow && Cc <= 5 * (PCGF_THREADS / 32) && Nl <= nblk * (PCGF_THREADS / 32);
+      // landmark "parts": a landmark's L-order edges are cut into runs of <= 64 edges, one warp each; the parts of
+      // a landmark publish W_l * (partial sum) separately and the consumers add them, so the landmark degree is
+      // unbounded
+      std::vector<int> part_lm, part_e0, part_e1, lm_partbase(Nl + 1, 0);
+      for (int l = 0; l < Nl; ++l) {
+        lm_partbase[l] = (int)part_lm.size();
+        for (int e = lm_rowptr[l]; e < lm_rowptr[l + 1]; e += 64) {
+          part_lm.push_back(l);
+          part_e0.push_back(e);
+          part_e1.push_back(std::min(e + 64, lm_rowptr[l + 1]));
+        }
+      }
+      lm_partbase[Nl] = (int)part_lm.size();
+      const int n_parts = (int)part_lm.size();
+      bool ok = g->allow_fast && g->use_flow && Cc <= 5 * (PCGF_THREADS / 32) && n_parts <= nblk * (PCGF_THREADS / 32);
       if (ok) {
         std::vector<int> ov(nblk, 0);
-        for (int l = 0; l < Nl && ok; ++l) {
-          const int deg = lm_rowptr[l + 1] - lm_rowptr[l];
-          if (deg > 64) ok = false;
-          ov[l % nblk] += std::max(0, deg - 32);
+        for (int q = 0; q < n_parts && ok; ++q) {
+          if (lm_partbase[part_lm[q] + 1] - lm_partbase[part_lm[q]] > 127) ok = false;   // part count rides in the top bits of an int
+          ov[q % nblk] += std::max(0, part_e1[q] - part_e0[q] - 32);
         }
         for (int b = 0; b < nblk && ok; ++b) {
           const int q0 = std::min(Np, b * Cc), q1 = std::min(Np, q0 + Cc);
@@ -831,6 +845,11 @@ static int prepare(ssb_graph* g) {
         SSB_TRY(up(g->d_ft_pp_src, pp_src));
         SSB_TRY(up(g->d_ft_ext_rowptr, ext_rowptr));
         SSB_TRY(up(g->d_ft_ext, ext));
+        SSB_TRY(up(g->d_ft_part_lm, part_lm));
+        SSB_TRY(up(g->d_ft_part_e0, part_e0));
+        SSB_TRY(up(g->d_ft_part_e1, part_e1));
+        SSB_TRY(up(g->d_ft_lm_partbase, lm_partbase));
+        g->flow_n_parts = n_parts;
         // pivot order of the coarse Gauss-Jordan
         std::vector<std::vector<int>> cadj(nblk);
         auto link = [&](int a, int b) {
@@ -853,7 +872,8 @@ static int prepare(ssb_graph* g) {
         SSB_TRY(up(g->d_ft_gj_order, gj_order));
         SSB_CUDA_CHECK(cudaStreamSynchronize(s2));
         g->FT = FlowTabs{g->d_ft_ulm_rowptr.p, g->d_ft_ulm.p, g->d_ft_pl_loc.p, g->d_ft_upp_rowptr.p, g->d_ft_upp.p,
-                         g->d_ft_pp_loc.p, g->d_ft_pp_src.p, g->d_ft_ext_rowptr.p, g->d_ft_ext.p, g->d_ft_gj_order.p};
+                         g->d_ft_pp_loc.p, g->d_ft_pp_src.p, g->d_ft_ext_rowptr.p, g->d_ft_ext.p, g->d_ft_gj_order.p,
+                         g->d_ft_part_lm.p, g->d_ft_part_e0.p, g->d_ft_part_e1.p, g->d_ft_lm_partbase.p, n_parts};
       }
     }
     SSB_TRY(g->d_Bmat.ensure((size_t)36 * Np));
@@ -874,7 +894,8 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_Grun1.ensure((size_t)18 * n_runs1));
     SSB_TRY(g->d_slots.ensure((size_t)2 * nblk + 1));
     SSB_TRY(g->d_ainv.ensure((size_t)nblk * 6 * ncoarse));
-    SSB_TRY(g->d_ucell.ensure((size_t)6 * (Np + 64) + (size_t)3 * (Nl + 64)));   // u cells, then v cells
+    // u cells, then v cells (one triple per landmark part; parts <= Nl + El / 64)
+    SSB_TRY(g->d_ucell.ensure((size_t)6 * (Np + 64) + (size_t)3 * ((size_t)Nl + El / 64 + 64)));
     SSB_TRY(g->d_lines.ensure((size_t)2 * nblk * 8));
     SSB_TRY(g->d_hlpark.ensure((size_t)nblk * (PCGF_THREADS / 32) * 9 * 32));
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_ucell.p, 0, g->d_ucell.cap * sizeof(uint4), g->stream));

@@ -141,6 +141,12 @@ struct FlowTabs {
   const int* ext_rowptr;  // [nblk+1] neighbour poses owned by other CTAs
   const int* ext;
   const int* gj_order;    // [nblk] pivot order of the coarse Gauss-Jordan (nested dissection, separators last)
+  // landmark parts: runs of <= 64 L-order edges of one landmark, one warp each (part q -> CTA q % nblk, warp q / nblk)
+  const int* part_lm;     // [n_parts] landmark of the part
+  const int* part_e0;     // [n_parts] first L-order edge
+  const int* part_e1;     // [n_parts] one past the last edge
+  const int* lm_partbase; // [Nl+1]    first part of every landmark (v cells: 3 per part, parts of a landmark adjacent)
+  int n_parts;
 };
 
 constexpr int PCGW_MAXU = 320;    // distinct landmarks per CTA
@@ -344,8 +350,9 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np, p0 + Cz.C);
   const int i = p0 + warp * 5 + slot;          // my pose (pose role)
   const bool act = lane < 30 && i < p1;
-  const int l = warp * nblk + blockIdx.x;      // my landmark (landmark role), round-robin over CTAs
-  const bool lact = l < G.Nl;
+  const int part = warp * nblk + blockIdx.x;   // my landmark part (landmark role), round-robin over CTAs
+  const bool lact = part < T.n_parts;
+  const int l = lact ? T.part_lm[part] : 0;    // its landmark
   unsigned epoch = 0;
   int status = 0;
 
@@ -395,8 +402,10 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       const int xe = q / 6;
       stage_src[q] = 6 * T.ext[ext0 + xe] + (q - 6 * xe);
     } else {
-      const int qq = q - 6 * next, lu = qq / 3;
-      stage_src[q] = voff + 3 * T.ulm[ulm0 + lu] + (qq - 3 * lu);
+      // v of a landmark = sum over its parts: first part's cell in the low 24 bits, part count in the top 8
+      const int qq = q - 6 * next, lu = qq / 3, lmid = T.ulm[ulm0 + lu];
+      const int pb = T.lm_partbase[lmid], np = T.lm_partbase[lmid + 1] - pb;
+      stage_src[q] = (voff + 3 * pb + (qq - 3 * lu)) | (np << 24);
     }
   }
   double* const v_sh = u_sh + 6 * (PCGW_POSES + next);
@@ -432,8 +441,8 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   double Wr[3] = {0, 0, 0};  // lane k < 3: row k of W_l = (Hll + lambda I)^-1
   int deg = 0, le0 = 0;
   if (lact) {
-    le0 = G.lm_rowptr[l];
-    deg = G.lm_rowptr[l + 1] - le0;
+    le0 = T.part_e0[part];
+    deg = T.part_e1[part] - le0;
     if (lane < 3) {
       const double* Wu = G.HllInv + 6 * (size_t)l;
       // upper triangle storage: 0:(0,0) 1:(0,1) 2:(0,2) 3:(1,1) 4:(1,2) 5:(2,2)
@@ -603,7 +612,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       const double a0 = __shfl_sync(0xffffffffu, rsum, 0);
       const double a1 = __shfl_sync(0xffffffffu, rsum, 8);
       const double a2 = __shfl_sync(0xffffffffu, rsum, 16);
-      if (lane < 3) st_cell(F.vcell + 3 * (size_t)l + lane, Wr[0] * a0 + Wr[1] * a1 + Wr[2] * a2, tg);
+      if (lane < 3) st_cell(F.vcell + 3 * (size_t)part + lane, Wr[0] * a0 + Wr[1] * a1 + Wr[2] * a2, tg);
     }
     SSB_FTICK(0);
     // ---- stage u of external neighbours and v of my poses' landmarks into shared memory ----------------
@@ -616,12 +625,17 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
         sc_[m] = -1;
         if (q < nstage) {
           sc_[m] = stage_src[q];
-          c[m] = ld_cell(F.ucell + sc_[m]);
+          c[m] = ld_cell(F.ucell + (sc_[m] & 0xffffff));
         }
       }
 #pragma unroll
       for (int m = 0; m < 3; ++m)
-        if (sc_[m] >= 0) u_sh[6 * PCGW_POSES + threadIdx.x + PCGF_THREADS * m] = cell_wait(F.ucell + sc_[m], c[m], tg);
+        if (sc_[m] >= 0) {
+          const int cell = sc_[m] & 0xffffff, np = sc_[m] >> 24;   // np = 0 for u cells, >= 1 for v cells
+          double val = cell_wait(F.ucell + cell, c[m], tg);
+          for (int j = 1; j < np; ++j) val += cell_wait(F.ucell + cell + 3 * j, ld_cell(F.ucell + cell + 3 * j), tg);
+          u_sh[6 * PCGW_POSES + threadIdx.x + PCGF_THREADS * m] = val;
+        }
     }
     SSB_FTICK(1);
     __syncthreads();

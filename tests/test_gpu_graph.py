@@ -311,3 +311,22 @@ def test_g2o_roundtrip_with_planes(tmp_path):
     g2.load(path)
     assert g2.num_vertices() == g.num_vertices() and g2.num_edges() == g.num_edges()
     assert abs(g2.chi2() - g.chi2()) <= 1e-12 * max(1.0, g.chi2())
+
+
+def test_high_degree_landmarks_are_split_into_parts():
+    """landmarks seen from more than 64 keyframes (long-lived landmarks of the per-frame loop) are cut into parts of
+    <= 64 edges whose partial products the consumers add: same answer as the oracle and as the streaming kernel"""
+    spec = synth.make_graph(150, 3, obs_per_kf=3, seed=91, obs_radius=1e9)   # every landmark is seen by all 150 KFs
+    deg = np.bincount(spec.evj[spec.ekind == 1])
+    assert deg.max() >= 150
+    res = {}
+    for generic in (False, True):
+        g, o, ids = _pair(spec, preconditioner=2, pcg_tol=1e-12, force_generic=generic)
+        assert g.optimize(6) and o.optimize(6)
+        P, X = g.get_all(spec.n_poses, spec.n_landmarks)
+        Po, Xo = o.get_all(spec.n_poses, spec.n_landmarks)
+        assert np.array_equal(g.history[:, 4], o.history[:, 4])
+        assert np.abs(P - Po).max() <= 1e-6 * max(1.0, np.abs(Po).max())
+        assert np.abs(X - Xo).max() <= 1e-6 * max(1.0, np.abs(Xo).max())
+        res[generic] = P
+    assert np.abs(res[False] - res[True]).max() <= 1e-9

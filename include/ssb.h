@@ -36,7 +36,8 @@ typedef struct ssb_graph_opts {
   int preconditioner;   /* 0 = block-Jacobi on the Schur complement; 1 = + rigid-body coarse level (one
                            aggregate per CTA); 2 = + a middle level of 5-pose aggregates (3-level additive) */
   int coarse_group;     /* poses per coarse aggregate when preconditioner == 1 (default 32)        */
-  int reserved[4];
+  int reserved[4];      /* [0] = 1: force the streaming PCG kernel; [1] = n: re-invert the coarse matrix every n-th solve;
+                           [3]: initial launch counter of the cell tags (test hook for the tag wrap-around) */
 } ssb_graph_opts;
 
 typedef struct ssb_lm_stats {

@@ -904,7 +904,7 @@ static int prepare(ssb_graph* g) {
       SSB_TRY(g->d_gj.ensure((size_t)nblk * (36 * (size_t)nblk + 8)));
       SSB_CUDA_CHECK(cudaMemsetAsync(g->d_gj.p, 0, g->d_gj.cap * sizeof(uint4), g->stream));
     }
-    g->flow_seq = 0;
+    g->flow_seq = (unsigned)std::max(0, g->opts.reserved[3]);   // test hook: start close to the tag wrap-around
     g->ainv_valid = false;
     cudaStream_t s = g->stream;
     if (n_runs) {

@@ -19,7 +19,7 @@ def _d(a):
 class GraphSLAM:
     def __init__(self, verbose: bool = False, device: int = -1, pcg_tol: float = 1e-8, max_pcg_iters: int = 20000,
                  preconditioner: int = 0, coarse_group: int = 32, force_generic: bool = False,
-                 coarse_refresh: int = 1):
+                 coarse_refresh: int = 1, tag_seq_start: int = 0):
         self._L = _lib.lib()
         o = _lib.GraphOpts()
         self._L.ssb_graph_default_opts(C.byref(o))
@@ -30,6 +30,7 @@ class GraphSLAM:
         o.preconditioner = preconditioner
         o.coarse_group = coarse_group
         o.reserved[1] = int(coarse_refresh)  # re-invert the coarse matrix only every n-th damped solve
+        o.reserved[3] = int(tag_seq_start)   # test hook: initial launch counter of the data-flow cell tags
         o.reserved[0] = int(force_generic)   # 1 = always use the streaming PCG kernel (no on-chip residency)
         h = self._L.ssb_graph_create(C.byref(o))
         if not h:

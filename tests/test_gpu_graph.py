@@ -330,3 +330,19 @@ def test_high_degree_landmarks_are_split_into_parts():
         assert np.abs(X - Xo).max() <= 1e-6 * max(1.0, np.abs(Xo).max())
         res[generic] = P
     assert np.abs(res[False] - res[True]).max() <= 1e-9
+
+
+def test_cell_tag_wraparound():
+    """the data-flow kernel tags its cells with (launch counter << 16 | iteration); when the counter wraps the cell
+    buffers are cleared and the tags restart — solves on both sides of the wrap must agree bit for bit"""
+    spec = synth.make_config_graph("cfg1")
+    ref = GraphSLAM(preconditioner=2)
+    synth.load_graph(ref, spec)
+    assert ref.optimize(8)
+    g = GraphSLAM(preconditioner=2, tag_seq_start=0xFFFF - 4)   # wraps after 4 damped solves
+    synth.load_graph(g, spec)
+    assert g.optimize(8)
+    assert np.array_equal(g.history, ref.history)
+    P, X = g.get_all(spec.n_poses, spec.n_landmarks)
+    Pr, Xr = ref.get_all(spec.n_poses, spec.n_landmarks)
+    assert np.array_equal(P, Pr) and np.array_equal(X, Xr)

@@ -182,7 +182,7 @@ struct ssb_graph {
   DBuf<BarSlot> d_slots;
   CoarseDev Cz;
   size_t pcg_smem = 0, pcgw_smem = 0;
-  DBuf<int> d_ft_ulm_rowptr, d_ft_ulm, d_ft_pl_loc, d_ft_upp_rowptr, d_ft_upp, d_ft_pp_loc, d_ft_pp_src, d_ft_ext_rowptr, d_ft_ext, d_ft_gj_order, d_ft_part_lm, d_ft_part_e0, d_ft_part_e1, d_ft_lm_partbase;
+  DBuf<int> d_ft_ulm_rowptr, d_ft_ulm, d_ft_pl_loc, d_ft_upp_rowptr, d_ft_upp, d_ft_pp_loc, d_ft_pp_src, d_ft_ext_rowptr, d_ft_ext, d_ft_gj_order, d_ft_gj_mask, d_ft_part_lm, d_ft_part_e0, d_ft_part_e1, d_ft_lm_partbase;
   int flow_n_parts = 0;
   FlowTabs FT;
   DBuf<uint4> d_ucell, d_lines, d_gj;
@@ -870,9 +870,28 @@ static int prepare(ssb_graph* g) {
         std::vector<char> in(nblk, 0);
         nd_order_rec(cadj, all, in, gj_order);
         SSB_TRY(up(g->d_ft_gj_order, gj_order));
+        // symbolic Gauss-Jordan: which column blocks of the pivot panel are structurally non-zero at every step
+        // (bit b of gj_mask[step] = block b); receivers neither load nor update the zero blocks
+        {
+          const int W = (nblk + 31) / 32;
+          std::vector<std::vector<unsigned>> pat(nblk, std::vector<unsigned>(W, 0u));
+          for (int b = 0; b < nblk; ++b) {
+            pat[b][b >> 5] |= 1u << (b & 31);
+            for (int c : cadj[b]) pat[b][c >> 5] |= 1u << (c & 31);
+          }
+          std::vector<int> gj_mask((size_t)nblk * W, 0);
+          for (int step = 0; step < nblk; ++step) {
+            const int k = gj_order[step];
+            for (int w = 0; w < W; ++w) gj_mask[(size_t)step * W + w] = (int)pat[k][w];
+            for (int r = 0; r < nblk; ++r)
+              if (r != k && ((pat[r][k >> 5] >> (k & 31)) & 1u))
+                for (int w = 0; w < W; ++w) pat[r][w] |= pat[k][w];
+          }
+          SSB_TRY(up(g->d_ft_gj_mask, gj_mask));
+        }
         SSB_CUDA_CHECK(cudaStreamSynchronize(s2));
         g->FT = FlowTabs{g->d_ft_ulm_rowptr.p, g->d_ft_ulm.p, g->d_ft_pl_loc.p, g->d_ft_upp_rowptr.p, g->d_ft_upp.p,
-                         g->d_ft_pp_loc.p, g->d_ft_pp_src.p, g->d_ft_ext_rowptr.p, g->d_ft_ext.p, g->d_ft_gj_order.p,
+                         g->d_ft_pp_loc.p, g->d_ft_pp_src.p, g->d_ft_ext_rowptr.p, g->d_ft_ext.p, g->d_ft_gj_order.p, (const unsigned*)g->d_ft_gj_mask.p,
                          g->d_ft_part_lm.p, g->d_ft_part_e0.p, g->d_ft_part_e1.p, g->d_ft_lm_partbase.p, n_parts};
       }
     }

@@ -141,6 +141,7 @@ struct FlowTabs {
   const int* ext_rowptr;  // [nblk+1] neighbour poses owned by other CTAs
   const int* ext;
   const int* gj_order;    // [nblk] pivot order of the coarse Gauss-Jordan (nested dissection, separators last)
+  const unsigned* gj_mask; // [nblk][ceil(nblk/32)] structurally non-zero column blocks of the pivot panel per step
   // landmark parts: runs of <= 64 L-order edges of one landmark, one warp each (part q -> CTA q % nblk, warp q / nblk)
   const int* part_lm;     // [n_parts] landmark of the part
   const int* part_e0;     // [n_parts] first L-order edge
@@ -210,18 +211,20 @@ __device__ __forceinline__ bool warp_inv6_fast(double* col) {
 // step).  CTAs whose block in pivot column k is zero skip the step without waiting.
 // Returns true when every pivot block was positive definite.
 template <int NT, int NB>
-__device__ bool coarse_gj_flow(uint4* gj, unsigned tag, double* Arow, const int* order) {
+__device__ bool coarse_gj_flow(uint4* gj, unsigned tag, double* Arow, const int* order, const unsigned* mask) {
   constexpr int nc = 6 * NB;
   constexpr int PER = (nc + NT - 1) / NT;
   constexpr int PSTRIDE = 6 * nc + 8;
   __shared__ int s_flag;
   __shared__ double piv_sh[40];   // pivot inverse (pivot CTA) or F = my block in pivot column k
   __shared__ int order_sh[NB];
+  constexpr int MW = (NB + 31) / 32;
   if (threadIdx.x == 0) s_flag = 0;
   for (int q = threadIdx.x; q < NB; q += NT) order_sh[q] = order[q];
   __syncthreads();
   for (int step = 0; step < NB; ++step) {
     const int k = order_sh[step];   // pivot aggregate of this step (nested-dissection order)
+    const unsigned* mk = mask + (size_t)step * MW;   // structurally non-zero column blocks of this panel
     uint4* P = gj + (size_t)k * PSTRIDE;
     if ((int)blockIdx.x == k) {
       if (threadIdx.x < 32) {
@@ -238,6 +241,8 @@ __device__ bool coarse_gj_flow(uint4* gj, unsigned tag, double* Arow, const int*
       }
       __syncthreads();
       for (int j = threadIdx.x; j < nc; j += NT) {
+        const int cb = j / 6;
+        if (!((__ldg(mk + (cb >> 5)) >> (cb & 31)) & 1u)) continue;   // structurally zero block: stays zero, not published
         double colv[6];
 #pragma unroll
         for (int a = 0; a < 6; ++a) colv[a] = Arow[a * nc + j];
@@ -271,9 +276,13 @@ __device__ bool coarse_gj_flow(uint4* gj, unsigned tag, double* Arow, const int*
       if (__syncthreads_or(fv != 0.0) == 0) continue;
       double pj[PER][6];
 #pragma unroll
+      bool nz[PER];
+#pragma unroll
       for (int m = 0; m < PER; ++m) {
         const int j = threadIdx.x + NT * m;
-        if (j < nc) {
+        const int cb = j / 6;
+        nz[m] = j < nc && ((__ldg(mk + (cb >> 5)) >> (cb & 31)) & 1u);
+        if (nz[m]) {
           uint4 c[6];
 #pragma unroll
           for (int b = 0; b < 6; ++b) c[b] = ld_cell(P + b * nc + j);
@@ -284,7 +293,7 @@ __device__ bool coarse_gj_flow(uint4* gj, unsigned tag, double* Arow, const int*
 #pragma unroll
       for (int m = 0; m < PER; ++m) {
         const int j = threadIdx.x + NT * m;
-        if (j < nc) {
+        if (nz[m]) {
           const bool inpiv = (j >= 6 * k && j < 6 * k + 6);
 #pragma unroll
           for (int a = 0; a < 6; ++a) {
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
 #ifdef SSB_PCG_TIMERS
       t_asm = clock64();
 #endif
-      use_coarse = coarse_gj_flow<PCGF_THREADS, NB>(F.gj, F.tagbase + 1u, Arow, T.gj_order);
+      use_coarse = coarse_gj_flow<PCGF_THREADS, NB>(F.gj, F.tagbase + 1u, Arow, T.gj_order, T.gj_mask);
       if (use_coarse)
         for (int k = threadIdx.x; k < 6 * nc; k += PCGF_THREADS) Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k] = Arow[k];
     }

@@ -69,6 +69,30 @@ __device__ __forceinline__ double cell_wait(const uint4* p, uint4 c, unsigned ta
   return cell_val(c);
 }
 
+// Batch wait: N cells base[off[m]] (off[m] < 0: not wanted) were all loaded once into c[].  Cells are consumed in
+// order; when cell m had to be spun on, the copies of the later cells are stale too, so they are re-issued TOGETHER
+// right after m arrived (one extra round trip for the rest of the batch instead of one per cell), and only then.
+template <int N>
+__device__ __forceinline__ void cells_wait(const uint4* base, const int (&off)[N], uint4 (&c)[N], unsigned tag,
+                                           double (&val)[N]) {
+#pragma unroll
+  for (int m = 0; m < N; ++m) {
+    val[m] = 0.0;
+    if (off[m] >= 0) {
+      if (!cell_ok(c[m], tag)) {
+        do {
+          __nanosleep(SSB_POLL_NS);
+          c[m] = ld_cell(base + off[m]);
+        } while (!cell_ok(c[m], tag));
+#pragma unroll
+        for (int q = m + 1; q < N; ++q)
+          if (off[q] >= 0 && !cell_ok(c[q], tag)) c[q] = ld_cell(base + off[q]);
+      }
+      val[m] = cell_val(c[m]);
+    }
+  }
+}
+
 // Packed butterfly reductions: N values per lane are reduced across the warp with N-1 + (5 - log2 N)
 // exchanges instead of 5 N.  The sum of value j ends up in the lanes whose upper bits spell j.
 // Fixed exchange pattern => deterministic.
@@ -284,10 +308,13 @@ __device__ bool coarse_gj_flow(uint4* gj, unsigned tag, double* Arow, const int*
         nz[m] = j < nc && ((__ldg(mk + (cb >> 5)) >> (cb & 31)) & 1u);
         if (nz[m]) {
           uint4 c[6];
+          int po[6];
 #pragma unroll
-          for (int b = 0; b < 6; ++b) c[b] = ld_cell(P + b * nc + j);
-#pragma unroll
-          for (int b = 0; b < 6; ++b) pj[m][b] = cell_wait(P + b * nc + j, c[b], tag);
+          for (int b = 0; b < 6; ++b) {
+            po[b] = b * nc + j;
+            c[b] = ld_cell(P + po[b]);
+          }
+          cells_wait<6>(P, po, c, tag, pj[m]);
         }
       }
 #pragma unroll
@@ -588,14 +615,14 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
         HLc[2 * q] = h.x;
         HLc[2 * q + 1] = h.y;
       }
+      double uv[6];
+      cells_wait<6>(F.ucell, uoff, c, tg, uv);
 #pragma unroll
-      for (int m = 0; m < 6; ++m)
-        if (uoff[m] >= 0) {
-          const double uv = cell_wait(F.ucell + uoff[m], c[m], tg);
-          a[0] += HLc[3 * m] * uv;
-          a[1] += HLc[3 * m + 1] * uv;
-          a[2] += HLc[3 * m + 2] * uv;
-        }
+      for (int m = 0; m < 6; ++m) {   // uv = 0 and HLc = 0 for unused items
+        a[0] += HLc[3 * m] * uv[m];
+        a[1] += HLc[3 * m + 1] * uv[m];
+        a[2] += HLc[3 * m + 2] * uv[m];
+      }
       if (nov > 0) {  // warp-uniform: edges 32..63, same item order, second batch of loads
         int oc[6];
 #pragma unroll
@@ -607,14 +634,14 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
             c[m] = ld_cell(F.ucell + oc[m]);
           }
         }
+        cells_wait<6>(F.ucell, oc, c, tg, uv);
 #pragma unroll
         for (int m = 0; m < 6; ++m)
           if (oc[m] >= 0) {
-            const double uv = cell_wait(F.ucell + oc[m], c[m], tg);
             const double* H2 = ovH + 3 * (6 * ovbase + 32 * m + lane);
-            a[0] += H2[0] * uv;
-            a[1] += H2[1] * uv;
-            a[2] += H2[2] * uv;
+            a[0] += H2[0] * uv[m];
+            a[1] += H2[1] * uv[m];
+            a[2] += H2[2] * uv[m];
           }
       }
       const double rsum = warp_reduce4(a);  // value j in lanes 8j..8j+7
@@ -637,12 +664,17 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
           c[m] = ld_cell(F.ucell + (sc_[m] & 0xffffff));
         }
       }
+      int so[3];
+      double sv[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) so[m] = sc_[m] >= 0 ? (sc_[m] & 0xffffff) : -1;
+      cells_wait<3>(F.ucell, so, c, tg, sv);
 #pragma unroll
       for (int m = 0; m < 3; ++m)
         if (sc_[m] >= 0) {
-          const int cell = sc_[m] & 0xffffff, np = sc_[m] >> 24;   // np = 0 for u cells, >= 1 for v cells
-          double val = cell_wait(F.ucell + cell, c[m], tg);
-          for (int j = 1; j < np; ++j) val += cell_wait(F.ucell + cell + 3 * j, ld_cell(F.ucell + cell + 3 * j), tg);
+          const int np = sc_[m] >> 24;   // 0 for u cells, >= 1 for v cells (parts of one landmark are adjacent)
+          double val = sv[m];
+          for (int j = 1; j < np; ++j) val += cell_wait(F.ucell + so[m] + 3 * j, ld_cell(F.ucell + so[m] + 3 * j), tg);
           u_sh[6 * PCGW_POSES + threadIdx.x + PCGF_THREADS * m] = val;
         }
     }
@@ -699,11 +731,16 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
         const int q = threadIdx.x + PCGF_THREADS * m;
         if (q < ngather) c[m] = ld_cell(L + q);
       }
+      int go[3];
+      double gv[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) go[m] = (threadIdx.x + PCGF_THREADS * m < ngather) ? threadIdx.x + PCGF_THREADS * m : -1;
+      cells_wait<3>(L, go, c, tg, gv);
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
         const int q = threadIdx.x + PCGF_THREADS * m;
         if (q < ngather) {
-          const double val = cell_wait(L + q, c[m], tg);
+          const double val = gv[m];
           const int ln = q >> 3, k = q & 7;
           if (k == 0)
             gam[ln] = val;

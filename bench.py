@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pcg-tol", type=float, default=1e-6)
-    ap.add_argument("--preconditioner", type=int, default=2)
+    ap.add_argument("--preconditioner", type=int, default=3)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -294,7 +294,7 @@ def main():
                                "lawn-mower trajectory, seed 20260927)" % (spec.n_landmarks, spec.n_edges, LM_ITERS),
                    "parallelism": "1 graph per GPU (independent replicas)" if world > 1 else "single GPU",
                    "l2": "flushed between timed steps (256 MiB write)", "pcg_tol": args.pcg_tol,
-                   "preconditioner": ["block-Jacobi", "block-Jacobi + per-CTA rigid-body coarse level", "block-Jacobi + 5-pose aggregates + per-CTA coarse level (3-level additive)"][args.preconditioner],
+                   "preconditioner": ["block-Jacobi", "block-Jacobi + per-CTA rigid-body coarse level", "block-Jacobi + 5-pose aggregates + per-CTA coarse level (3-level additive)", "block-Jacobi + 5-pose aggregates coupled exactly in two groups per CTA + per-CTA coarse level"][args.preconditioner],
                    "lm_iterations": lm_its // max(steps, 1), "trials_per_step": trials / max(steps, 1),
                    "pcg_iters_per_step": pcg_its / max(steps, 1), "chi2_final": final_chi2},
         "e2e": {"value": world * e2e_its / t_e2e, "unit": "LM iters/s", "h2d_bytes_per_step": gb["h2d"],

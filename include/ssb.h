@@ -34,7 +34,8 @@ typedef struct ssb_graph_opts {
   int max_pcg_iters;    /* cap on PCG iterations per damped solve (default 20000)                 */
   double pcg_tol;       /* stop when sqrt(r'M^-1 r) <= pcg_tol * sqrt(r0'M^-1 r0) (default 1e-8)   */
   int preconditioner;   /* 0 = block-Jacobi on the Schur complement; 1 = + rigid-body coarse level (one
-                           aggregate per CTA); 2 = + a middle level of 5-pose aggregates (3-level additive) */
+                           aggregate per CTA); 2 = + a middle level of 5-pose aggregates (3-level additive);
+                           3 = as 2 with the 5-pose aggregates of a CTA coupled exactly inside two groups (on-chip kernel) */
   int coarse_group;     /* poses per coarse aggregate when preconditioner == 1 (default 32)        */
   int reserved[4];      /* [0] = 1: force the streaming PCG kernel; [1] = n: re-invert the coarse matrix every n-th solve;
                            [3]: initial launch counter of the cell tags (test hook for the tag wrap-around) */

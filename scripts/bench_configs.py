@@ -9,7 +9,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "cfg4"):
     t = time.time()
     spec = synth.make_config_graph("cfg4")
-    g = GraphSLAM(preconditioner=2, pcg_tol=1e-6)
+    g = GraphSLAM(preconditioner=3, pcg_tol=1e-6)
     synth.load_graph(g, spec)
     g.snapshot()
     t_load = time.time() - t
@@ -26,7 +26,7 @@ if which in ("all", "cfg4"):
 if which in ("all", "cfg5"):
     n_kf = int(os.environ.get("CFG5_KF", "4000"))
     stream = synth.make_frame_stream(n_kf, max(12, n_kf // 10), seed=synth.SEED_BASE + 5, max_det=3)
-    g = GraphSLAM(preconditioner=2, pcg_tol=1e-6)
+    g = GraphSLAM(preconditioner=3, pcg_tol=1e-6)
     a = DataAssociation(use_maha_dist=False, use_eq_dist=True, eq_dist_thres=1.5, land_noise_low=0.1, strict=True)
     slam = SemanticGraphSLAM(g, a, stream.info6, cam_angle=stream.cam_angle, max_iterations=1024)
     t0 = time.time()

@@ -4,7 +4,7 @@ import numpy as np
 from semantic_slam_b200 import GraphSLAM, DataAssociation, SemanticGraphSLAM, synth
 n_kf = int(sys.argv[1]) if len(sys.argv) > 1 else 600
 stream = synth.make_frame_stream(n_kf, max(12, n_kf // 10), seed=synth.SEED_BASE + 5, max_det=3)
-g = GraphSLAM(preconditioner=int(os.environ.get("PRECOND", "2")), pcg_tol=1e-6)
+g = GraphSLAM(preconditioner=int(os.environ.get("PRECOND", "3")), pcg_tol=1e-6)
 a = DataAssociation(use_maha_dist=False, use_eq_dist=True, eq_dist_thres=1.5, land_noise_low=0.1, strict=True)
 slam = SemanticGraphSLAM(g, a, stream.info6, cam_angle=stream.cam_angle, max_iterations=1024)
 t0 = time.time()

@@ -177,8 +177,8 @@ struct ssb_graph {
   bool ainv_valid = false;   // d_ainv holds the rows of a previously inverted coarse matrix
   int solves_since_refresh = 0;
   DBuf<int> d_run_lm, d_run_group, d_run_e0, d_lm_run_rowptr, d_grp_run_rowptr, d_grp_runs;
-  DBuf<int> d_run1_lm, d_run1_e0, d_agg_run_rowptr, d_agg_runs;
-  DBuf<double> d_Grun1;
+  DBuf<int> d_run1_lm, d_run1_e0, d_agg_run_rowptr, d_agg_runs, d_grp_first_agg, d_grp_seg_rowptr, d_grp_seg_r0, d_grp_seg_m;
+  DBuf<double> d_Grun1, d_D1raw, d_GrpInv;
   DBuf<BarSlot> d_slots;
   CoarseDev Cz;
   size_t pcg_smem = 0, pcgw_smem = 0;
@@ -684,6 +684,43 @@ static int prepare(ssb_graph* g) {
       std::vector<int> f(agg_run_rowptr.begin(), agg_run_rowptr.end() - 1);
       for (int r = 0; r < n_runs1; ++r) agg_runs[f[run1_agg[r]]++] = r;
     }
+    // preconditioner 3: two groups of 5-pose aggregates per CTA, coupled exactly; landmark segments = >= 2 consecutive
+    // runs of one landmark whose aggregates fall into the same group (runs are ordered by landmark, then aggregate)
+    const int apc = Cc / 5;                     // aggregates per CTA
+    const int n_groups = 2 * nblk;
+    std::vector<int> grp_first_agg(n_groups + 1, 0);
+    for (int b = 0; b < nblk; ++b) {
+      const int ga0 = std::min(n_agg, b * apc), ga1 = std::min(n_agg, ga0 + apc);
+      grp_first_agg[2 * b] = ga0;
+      grp_first_agg[2 * b + 1] = ga0 + (ga1 - ga0 + 1) / 2;
+    }
+    grp_first_agg[n_groups] = std::min(n_agg, nblk * apc);
+    auto group_of = [&](int ag) {
+      const int b = std::min(nblk - 1, ag / apc);
+      return 2 * b + (ag >= grp_first_agg[2 * b + 1] ? 1 : 0);
+    };
+    std::vector<int> seg_grp, seg_r0, seg_m;
+    for (int r = 0; r < n_runs1;) {
+      int e = r + 1;
+      const int gr = group_of(run1_agg[r]);
+      while (e < n_runs1 && run1_lm[e] == run1_lm[r] && group_of(run1_agg[e]) == gr) ++e;
+      if (e - r >= 2) {
+        seg_grp.push_back(gr);
+        seg_r0.push_back(r);
+        seg_m.push_back(e - r);
+      }
+      r = e;
+    }
+    std::vector<int> grp_seg_rowptr(n_groups + 1, 0), grp_seg_r0(std::max<size_t>(seg_r0.size(), 1)), grp_seg_m(std::max<size_t>(seg_r0.size(), 1));
+    for (int gsg : seg_grp) grp_seg_rowptr[gsg + 1]++;
+    for (int q = 0; q < n_groups; ++q) grp_seg_rowptr[q + 1] += grp_seg_rowptr[q];
+    {
+      std::vector<int> f(grp_seg_rowptr.begin(), grp_seg_rowptr.end() - 1);
+      for (size_t q = 0; q < seg_grp.size(); ++q) {
+        grp_seg_r0[f[seg_grp[q]]] = seg_r0[q];
+        grp_seg_m[f[seg_grp[q]]++] = seg_m[q];
+      }
+    }
     // pose-major index over L-order positions
     std::vector<int> ppl_rowptr(Np + 1, 0);
     for (int k = 0; k < El; ++k) ppl_rowptr[plL[k].p + 1]++;
@@ -911,6 +948,12 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_agg_run_rowptr.ensure(n_agg + 1));
     SSB_TRY(g->d_agg_runs.ensure(n_runs1));
     SSB_TRY(g->d_Grun1.ensure((size_t)18 * n_runs1));
+    SSB_TRY(g->d_D1raw.ensure((size_t)36 * (n_agg + 1)));
+    SSB_TRY(g->d_GrpInv.ensure((size_t)n_groups * GRP_PACK));
+    SSB_TRY(g->d_grp_first_agg.ensure(n_groups + 1));
+    SSB_TRY(g->d_grp_seg_rowptr.ensure(n_groups + 1));
+    SSB_TRY(g->d_grp_seg_r0.ensure(grp_seg_r0.size()));
+    SSB_TRY(g->d_grp_seg_m.ensure(grp_seg_m.size()));
     SSB_TRY(g->d_slots.ensure((size_t)2 * nblk + 1));
     SSB_TRY(g->d_ainv.ensure((size_t)nblk * 6 * ncoarse));
     // u cells, then v cells (one triple per landmark part; parts <= Nl + El / 64)
@@ -938,6 +981,10 @@ static int prepare(ssb_graph* g) {
     }
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_run1_e0.p, run1_e0.data(), (n_runs1 + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_agg_run_rowptr.p, agg_run_rowptr.data(), (n_agg + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_first_agg.p, grp_first_agg.data(), (n_groups + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_seg_rowptr.p, grp_seg_rowptr.data(), (n_groups + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_seg_r0.p, grp_seg_r0.data(), grp_seg_r0.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_seg_m.p, grp_seg_m.data(), grp_seg_m.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_run_rowptr.p, lm_run_rowptr.data(), (Nl + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_run_rowptr.p, grp_run_rowptr.data(), (nblk + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     {
@@ -965,6 +1012,15 @@ static int prepare(ssb_graph* g) {
       Cz.agg_run_rowptr = g->d_agg_run_rowptr.p;
       Cz.agg_runs = g->d_agg_runs.p;
       Cz.n_runs1 = n_runs1;
+      // preconditioner 3 needs <= GRP_MAXA aggregates per group (<= 80 poses per CTA) and the on-chip kernel
+      Cz.grp_enabled = (g->opts.preconditioner >= 3 && (apc + 1) / 2 <= GRP_MAXA && g->comm_world == 1) ? 1 : 0;
+      Cz.D1raw = g->d_D1raw.p;
+      Cz.GrpInv = g->d_GrpInv.p;
+      Cz.grp_first_agg = g->d_grp_first_agg.p;
+      Cz.grp_seg_rowptr = g->d_grp_seg_rowptr.p;
+      Cz.grp_seg_r0 = g->d_grp_seg_r0.p;
+      Cz.grp_seg_m = g->d_grp_seg_m.p;
+      Cz.n_groups = n_groups;
       Cz.ainv_store = g->d_ainv.p;
     }
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_scalars.p, 0, 32 * sizeof(double), s));
@@ -1098,6 +1154,10 @@ static int launch_prep(ssb_graph* g, double lambda) {
   if (g->Cz.sub_enabled && g->comm_world == 1) {
     k_sub_assemble<<<((G.Np + 4) / 5 + 63) / 64, 64, 0, s>>>(G, g->Cz, lambda);
     g->launches++;
+    if (g->Cz.grp_enabled && g->fast_ok) {
+      k_grp_invert<<<g->Cz.n_groups, GRP_THREADS, 0, s>>>(G, g->Cz);
+      g->launches++;
+    }
   }
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;

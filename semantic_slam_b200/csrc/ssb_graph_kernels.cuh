@@ -335,7 +335,20 @@ struct CoarseDev {
   const int* agg_run_rowptr;  // [n_agg+1]
   const int* agg_runs;        // runs sorted by aggregate (landmark order inside an aggregate)
   int n_runs1;
+  // preconditioner 3: the 5-pose aggregates of one CTA are coupled exactly inside two groups of <= GRP_MAXA
+  // aggregates each (group matrix = P1' S P1 restricted to the group, <= 48x48, inverted per damped trial)
+  int grp_enabled;
+  double* D1raw;              // [n_agg][36] P1' S P1 diagonal blocks before inversion
+  double* GrpInv;             // [n_groups][GRP_PACK] packed lower triangle of the group inverse (zeros = level off)
+  const int* grp_first_agg;   // [n_groups+1] first aggregate of every group (groups 2b, 2b+1 belong to CTA b)
+  const int* grp_seg_rowptr;  // [n_groups+1] landmark segments: >= 2 consecutive runs of one landmark inside a group
+  const int* grp_seg_r0;      //              first run of the segment
+  const int* grp_seg_m;       //              number of runs
+  int n_groups;
 };
+constexpr int GRP_MAXA = 8;                          // aggregates per group
+constexpr int GRP_N = 6 * GRP_MAXA;                  // 48
+constexpr int GRP_PACK = GRP_N * (GRP_N + 1) / 2;    // 1176
 
 struct BarSlot {  // one 64 B line per CTA and buffer; slot [2*gridDim.x] holds the arrival counter
   double v[7];
@@ -650,9 +663,150 @@ __global__ void __launch_bounds__(64) k_sub_assemble(DevGraph G, CoarseDev Cz, d
     for (int r = 0; r < 6; ++r)
       for (int c = 0; c < 6; ++c) D[6 * r + c] -= Gr[r] * WG[c] + Gr[6 + r] * WG[6 + c] + Gr[12 + r] * WG[12 + c];
   }
+  if (Cz.grp_enabled)
+    for (int k = 0; k < 36; ++k) Cz.D1raw[36 * (size_t)a + k] = any ? D[k] : 0.0;
   if (!any || !inv_spd6(D))
     for (int k = 0; k < 36; ++k) D[k] = 0.0;
   for (int k = 0; k < 36; ++k) Cz.D1inv[36 * (size_t)a + k] = D[k];
+}
+
+// per damped trial (preconditioner 3): assemble P1' S P1 restricted to one group of 5-pose aggregates and invert it
+// in shared memory (Gauss-Jordan, SPD => no pivoting).  One CTA of 256 threads per group; every thread owns fixed
+// matrix entries, so the landmark terms and the elimination need no atomics and are deterministic.
+constexpr int GRP_THREADS = 256;
+__global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDev Cz) {
+  constexpr int LD = GRP_N + 1;
+  __shared__ double A[GRP_N * LD];
+  __shared__ double Gs[3 * GRP_N];   // runs of the current landmark scattered to their aggregates' columns (3 x n)
+  __shared__ double Ws[9];
+  __shared__ double colk[GRP_N], rowk[GRP_N];
+  __shared__ int s_fail;
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const int a0 = Cz.grp_first_agg[g], a1 = Cz.grp_first_agg[g + 1];
+  const int na = a1 - a0, n = 6 * na;
+  double* out = Cz.GrpInv + (size_t)g * GRP_PACK;
+  if (na <= 0 || na > GRP_MAXA) {
+    for (int k = tid; k < GRP_PACK; k += GRP_THREADS) out[k] = 0.0;
+    return;
+  }
+  for (int k = tid; k < GRP_N * LD; k += GRP_THREADS) A[k] = 0.0;
+  for (int k = tid; k < 3 * GRP_N; k += GRP_THREADS) Gs[k] = 0.0;
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (int idx = tid; idx < 36 * na; idx += GRP_THREADS) {
+    const int a = idx / 36, e = idx - 36 * a;
+    A[(6 * a + e / 6) * LD + 6 * a + e % 6] = Cz.D1raw[36 * (size_t)(a0 + a) + e];
+  }
+  __syncthreads();
+  // pose-pose edges between different aggregates of the group (a handful): B_i' Hoff B_j and its transpose
+  for (int i = 5 * a0 + tid; i < min(G.Np, 5 * a1); i += GRP_THREADS) {
+    const int ai = i / 5 - a0;
+    const double* B = Cz.B1mat + 36 * (size_t)i;
+    for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
+      const int code = G.pose_pp_idx[kk];
+      if (code & 1) continue;
+      const int e = code >> 1, j = G.pp[e].j;
+      const int aj = j / 5 - a0;
+      if (aj == ai || aj < 0 || aj >= na) continue;
+      const double* Bj = Cz.B1mat + 36 * (size_t)j;
+      const double* Ho = G.Hoff + 36 * (size_t)e;
+      double HB[36];
+      for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) {
+          double t = 0.0;
+          for (int k = 0; k < 6; ++k) t += Ho[6 * r + k] * Bj[6 * k + c];
+          HB[6 * r + c] = t;
+        }
+      for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) {
+          double t = 0.0;
+          for (int k = 0; k < 6; ++k) t += B[6 * k + r] * HB[6 * k + c];
+          atomicAdd(&A[(6 * ai + r) * LD + 6 * aj + c], t);
+          atomicAdd(&A[(6 * aj + c) * LD + 6 * ai + r], t);
+        }
+    }
+  }
+  __syncthreads();
+  // landmarks seen from several aggregates of the group: A -= Gs' W Gs on the blocks that couple different aggregates
+  for (int sgm = Cz.grp_seg_rowptr[g]; sgm < Cz.grp_seg_rowptr[g + 1]; ++sgm) {
+    const int r0 = Cz.grp_seg_r0[sgm], m = Cz.grp_seg_m[sgm];
+    if (tid < 18 * m) {
+      const int x = tid / 18, q = tid - 18 * x, u = q / 6, c = q - 6 * u;
+      const int ax = G.pl[Cz.run1_e0[r0 + x]].p / 5 - a0;
+      Gs[u * GRP_N + 6 * ax + c] = Cz.Grun1[18 * (size_t)(r0 + x) + q];
+    }
+    if (tid >= 224 && tid < 233) {
+      const double* Wu = G.HllInv + 6 * (size_t)Cz.run1_lm[r0];
+      const int q = tid - 224, r = q / 3, c = q - 3 * r;
+      const int ut[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+      Ws[3 * r + c] = Wu[ut[3 * r + c]];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += GRP_THREADS) {
+      const int i = idx / n, j = idx - n * i;
+      if (i / 6 == j / 6) continue;   // the diagonal blocks already hold their landmark terms (D1raw)
+      double t = 0.0;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const double wg = Ws[3 * u] * Gs[j] + Ws[3 * u + 1] * Gs[GRP_N + j] + Ws[3 * u + 2] * Gs[2 * GRP_N + j];
+        t += Gs[u * GRP_N + i] * wg;
+      }
+      A[i * LD + j] -= t;
+    }
+    __syncthreads();
+    if (tid < 18 * m) {   // clear the scattered entries again
+      const int x = tid / 18, q = tid - 18 * x, u = q / 6, c = q - 6 * u;
+      const int ax = G.pl[Cz.run1_e0[r0 + x]].p / 5 - a0;
+      Gs[u * GRP_N + 6 * ax + c] = 0.0;
+    }
+    // (the next iteration's writes to Gs / Ws are ordered after this one's reads by the barrier above)
+  }
+  __syncthreads();
+  // aggregates without a free pose have a zero block: decouple them with an identity
+  if (tid < na) {
+    bool zero = true;
+    for (int k = 0; k < 6; ++k)
+      if (A[(6 * tid + k) * LD + 6 * tid + k] != 0.0) zero = false;
+    if (zero)
+      for (int k = 0; k < 6; ++k) A[(6 * tid + k) * LD + 6 * tid + k] = 1.0;
+  }
+  __syncthreads();
+  // in-place Gauss-Jordan inverse, all entries updated in parallel from saved copies of pivot row and column
+  for (int k = 0; k < n; ++k) {
+    const double pk = A[k * LD + k];
+    if (!(pk > 0.0) || !isfinite(pk)) {   // uniform: every thread reads the same pivot
+      if (tid == 0) s_fail = 1;
+      break;
+    }
+    const double ip = 1.0 / pk;
+    if (tid < n) {
+      colk[tid] = A[tid * LD + k];
+      rowk[tid] = A[k * LD + tid];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += GRP_THREADS) {
+      const int i = idx / n, j = idx - n * i;
+      double v;
+      if (i == k)
+        v = (j == k) ? ip : rowk[j] * ip;
+      else if (j == k)
+        v = -colk[i] * ip;
+      else
+        v = A[i * LD + j] - colk[i] * rowk[j] * ip;
+      A[i * LD + j] = v;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const bool fail = s_fail != 0;
+  for (int idx = tid; idx < GRP_PACK; idx += GRP_THREADS) {
+    // idx -> (r, c) with c <= r
+    int r = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+    while (r * (r + 1) / 2 > idx) --r;
+    while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+    const int c = idx - r * (r + 1) / 2;
+    out[idx] = (fail || r >= n) ? 0.0 : 0.5 * (A[r * LD + c] + A[c * LD + r]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -452,6 +452,19 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   for (int k = threadIdx.x; k < 36 * nupp; k += PCGF_THREADS) ppH[k] = G.Hoff[36 * (size_t)T.upp[upp0 + k / 36] + (k % 36)];
   for (int k = threadIdx.x; k < 2 * 36 * PCGW_POSES; k += PCGF_THREADS) b1_sh[k] = 0.0;  // b1_sh and m1_sh (contiguous)
   __syncthreads();
+  // preconditioner 3: the m1 region holds instead the packed inverses of my two aggregate groups [2][GRP_PACK],
+  // the restricted residual of my aggregates r5 [96] and the group solutions z5 [96]
+  const bool use_grp = use_sub && Cz.grp_enabled != 0;
+  double* const GI = m1_sh;
+  double* const r5_sh = m1_sh + 2 * GRP_PACK;
+  double* const z5_sh = r5_sh + 6 * (PCGF_THREADS / 32);
+  int gn0 = 0, gn1 = 0;   // dimensions of my two groups
+  if (use_grp) {
+    const int ga0 = Cz.grp_first_agg[2 * blockIdx.x], gah = Cz.grp_first_agg[2 * blockIdx.x + 1],
+              ga1 = Cz.grp_first_agg[2 * blockIdx.x + 2];
+    gn0 = 6 * (gah - ga0);
+    gn1 = 6 * (ga1 - gah);
+  }
   if (use_sub) {
     // P1 rows and M1 = P1 D1^-1 rows of my poses (zero D1^-1 = level off for that aggregate)
     for (int k = threadIdx.x; k < 36 * (p1 - p0); k += PCGF_THREADS) {
@@ -459,11 +472,15 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       const double* B1 = Cz.B1mat + 36 * (size_t)ip + 6 * row;
       const double* D1 = Cz.D1inv + 36 * (size_t)(ip / 5);
       b1_sh[k] = B1[j];
-      double t = 0.0;
+      if (!use_grp) {
+        double t = 0.0;
 #pragma unroll
-      for (int m = 0; m < 6; ++m) t += B1[m] * D1[6 * m + j];
-      m1_sh[k] = t;
+        for (int m = 0; m < 6; ++m) t += B1[m] * D1[6 * m + j];
+        m1_sh[k] = t;
+      }
     }
+    if (use_grp)
+      for (int k = threadIdx.x; k < 2 * GRP_PACK; k += PCGF_THREADS) GI[k] = Cz.GrpInv[(size_t)2 * blockIdx.x * GRP_PACK + k];
   }
   // shared-space byte address of my P1 row (lanes 30, 31 alias slot 0: their r is 0); the M1 row sits
   // 36 * PCGW_POSES doubles further
@@ -551,14 +568,39 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     double _z = 0.0;                                                                                    \
     _Pragma("unroll") for (int k = 0; k < 6; ++k) _z += Drow[k] * __shfl_sync(0xffffffffu, rcomp, base_lane + k); \
     if (use_sub) {                                                                                      \
-      double _t[8], _b[6], _m[6];                                                                       \
+      double _t[8], _b[6];                                                                              \
       lds_row6(b1addr, _b);                                                                             \
-      lds_row6(b1addr + 8u * 36u * PCGW_POSES, _m);                                                     \
       _Pragma("unroll") for (int k = 0; k < 6; ++k) _t[k] = _b[k] * rcomp; /* r = 0 on inactive lanes */  \
       _t[6] = 0.0;                                                                                      \
       _t[7] = 0.0;                                                                                      \
       const double _r = warp_reduce8(_t); /* P1'r: value k in lanes 4k..4k+3 */                          \
-      _Pragma("unroll") for (int k = 0; k < 6; ++k) _z += _m[k] * __shfl_sync(0xffffffffu, _r, 4 * k);    \
+      if (use_grp) {                                                                                    \
+        /* exact solve inside each group of aggregates: z5 = Ginv r5 (packed symmetric, 4 threads per row) */ \
+        if ((lane & 3) == 0 && lane < 24) r5_sh[6 * warp + (lane >> 2)] = _r;                             \
+        __syncthreads();                                                                                \
+        {                                                                                               \
+          const int _row = threadIdx.x >> 2, _part = threadIdx.x & 3;                                   \
+          double _s = 0.0;                                                                              \
+          if (_row < gn0 + gn1) {                                                                       \
+            const int _h = _row >= gn0, _i = _row - (_h ? gn0 : 0), _nh = _h ? gn1 : gn0, _base = _h ? gn0 : 0; \
+            const double* _G = GI + _h * GRP_PACK;                                                       \
+            const int _chunk = (_nh + 3) >> 2, _j0 = _part * _chunk, _j1 = min(_nh, _j0 + _chunk);       \
+            for (int _j = _j0; _j < _j1; ++_j) {                                                         \
+              const int _hi = max(_i, _j), _lo = min(_i, _j);                                            \
+              _s += _G[((_hi * (_hi + 1)) >> 1) + _lo] * r5_sh[_base + _j];                               \
+            }                                                                                           \
+          }                                                                                             \
+          _s += __shfl_xor_sync(0xffffffffu, _s, 1);                                                     \
+          _s += __shfl_xor_sync(0xffffffffu, _s, 2);                                                     \
+          if (_part == 0 && _row < 6 * (PCGF_THREADS / 32)) z5_sh[_row] = _s;                            \
+        }                                                                                               \
+        __syncthreads();                                                                                \
+        _Pragma("unroll") for (int k = 0; k < 6; ++k) _z += _b[k] * z5_sh[6 * warp + k];                   \
+      } else {                                                                                          \
+        double _m[6];                                                                                   \
+        lds_row6(b1addr + 8u * 36u * PCGW_POSES, _m);                                                   \
+        _Pragma("unroll") for (int k = 0; k < 6; ++k) _z += _m[k] * __shfl_sync(0xffffffffu, _r, 4 * k);  \
+      }                                                                                                 \
     }                                                                                                   \
     uc = act ? _z + cz : 0.0;                                                                           \
   }

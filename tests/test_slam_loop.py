@@ -42,7 +42,7 @@ def test_loop_parity_gpu_vs_oracle(use_maha, strict):
     stream = synth.make_frame_stream(60, 12)
     kw = dict(use_maha_dist=True, maha_dist_thres=30.0, land_noise_low=0.1) if use_maha else dict(KITTI)
     kw["strict"] = strict
-    a = _drive(GraphSLAM(preconditioner=2, pcg_tol=1e-10), DataAssociation(**kw), stream, use_maha=use_maha)
+    a = _drive(GraphSLAM(preconditioner=3, pcg_tol=1e-10), DataAssociation(**kw), stream, use_maha=use_maha)
     b = _drive(oracle.OracleGraphSLAM(), OracleDataAssociation(**kw), stream, use_maha=use_maha)
     assert a.association_log == b.association_log, "association indices must be bit-exact"
     assert len(a.landmark_nodes_) == len(b.landmark_nodes_) >= 8

@@ -3,7 +3,7 @@ sys.path.insert(0, '/root/repo')
 import numpy as np
 from semantic_slam_b200 import GraphSLAM, synth
 spec = synth.make_config_graph("cfg2")
-g = GraphSLAM(preconditioner=2, pcg_tol=1e-6)
+g = GraphSLAM(preconditioner=3, pcg_tol=1e-6)
 synth.load_graph(g, spec)
 P0, X0 = g.get_all(spec.n_poses, spec.n_landmarks)
 for rep in range(4):

@@ -108,5 +108,9 @@ def run2(desc, ops_spec, tol=1e-6):
     while rz > tol * tol * rz0 and it < 5000:
         q = S @ p; a = rz / (p @ q); x += a * p; r -= a * q; z = M(r); rzn = r @ z; p = z + (rzn / rz) * p; rz = rzn; it += 1
     print(f"{desc:70s} iterations {it}", flush=True)
-for grp in (2, 3, 4, 5, 7):
-    run2(f"5-pose aggregates coupled exactly in groups of {grp} + CTA full", [("group", 5, grp), ("full", C, 0)])
+run2("groups7(5) + full(CTA)                 [preconditioner 3]", [("group", 5, 7), ("full", C, 0)])
+run2("groups7(5) + diag(CTA/2) + full(CTA)", [("group", 5, 7), ("diag", C // 2, 0), ("full", C, 0)])
+run2("groups7(5) + full(CTA/2)", [("group", 5, 7), ("full", C // 2, 0)])
+run2("groups7(5) + full(CTA/2) + full(CTA)", [("group", 5, 7), ("full", C // 2, 0), ("full", C, 0)])
+run2("groups14(5) + full(CTA)", [("group", 5, 14), ("full", C, 0)])
+run2("groups28(5) [2 CTAs] + full(CTA)", [("group", 5, 28), ("full", C, 0)])

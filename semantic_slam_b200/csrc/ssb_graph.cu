@@ -177,7 +177,8 @@ struct ssb_graph {
   bool ainv_valid = false;   // d_ainv holds the rows of a previously inverted coarse matrix
   int solves_since_refresh = 0;
   DBuf<int> d_run_lm, d_run_group, d_run_e0, d_lm_run_rowptr, d_grp_run_rowptr, d_grp_runs;
-  DBuf<int> d_run1_lm, d_run1_e0, d_agg_run_rowptr, d_agg_runs, d_grp_first_agg, d_grp_seg_rowptr, d_grp_seg_r0, d_grp_seg_m;
+  DBuf<int> d_run1_lm, d_run1_e0, d_agg_run_rowptr, d_agg_runs, d_grp_first_agg, d_grp_seg_rowptr, d_grp_seg_r0, d_grp_seg_m, d_grp_seg_off, d_run1_agg;
+  int grp_max_runs = 0;
   DBuf<double> d_Grun1, d_D1raw, d_GrpInv;
   DBuf<BarSlot> d_slots;
   CoarseDev Cz;
@@ -711,7 +712,8 @@ static int prepare(ssb_graph* g) {
       }
       r = e;
     }
-    std::vector<int> grp_seg_rowptr(n_groups + 1, 0), grp_seg_r0(std::max<size_t>(seg_r0.size(), 1)), grp_seg_m(std::max<size_t>(seg_r0.size(), 1));
+    std::vector<int> grp_seg_rowptr(n_groups + 1, 0), grp_seg_r0(std::max<size_t>(seg_r0.size(), 1)), grp_seg_m(std::max<size_t>(seg_r0.size(), 1)),
+        grp_seg_off(std::max<size_t>(seg_r0.size(), 1), 0);
     for (int gsg : seg_grp) grp_seg_rowptr[gsg + 1]++;
     for (int q = 0; q < n_groups; ++q) grp_seg_rowptr[q + 1] += grp_seg_rowptr[q];
     {
@@ -721,6 +723,17 @@ static int prepare(ssb_graph* g) {
         grp_seg_m[f[seg_grp[q]]++] = seg_m[q];
       }
     }
+    int grp_max_runs = 0, grp_max_seg = 0;
+    for (int q = 0; q < n_groups; ++q) {
+      int o = 0;
+      for (int sgi = grp_seg_rowptr[q]; sgi < grp_seg_rowptr[q + 1]; ++sgi) {
+        grp_seg_off[sgi] = o;
+        o += grp_seg_m[sgi];
+      }
+      grp_max_runs = std::max(grp_max_runs, o);
+      grp_max_seg = std::max(grp_max_seg, grp_seg_rowptr[q + 1] - grp_seg_rowptr[q]);
+    }
+    g->grp_max_runs = grp_max_runs;
     // pose-major index over L-order positions
     std::vector<int> ppl_rowptr(Np + 1, 0);
     for (int k = 0; k < El; ++k) ppl_rowptr[plL[k].p + 1]++;
@@ -954,6 +967,8 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_grp_seg_rowptr.ensure(n_groups + 1));
     SSB_TRY(g->d_grp_seg_r0.ensure(grp_seg_r0.size()));
     SSB_TRY(g->d_grp_seg_m.ensure(grp_seg_m.size()));
+    SSB_TRY(g->d_grp_seg_off.ensure(grp_seg_off.size()));
+    SSB_TRY(g->d_run1_agg.ensure(std::max(n_runs1, 1)));
     SSB_TRY(g->d_slots.ensure((size_t)2 * nblk + 1));
     SSB_TRY(g->d_ainv.ensure((size_t)nblk * 6 * ncoarse));
     // u cells, then v cells (one triple per landmark part; parts <= Nl + El / 64)
@@ -985,6 +1000,8 @@ static int prepare(ssb_graph* g) {
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_seg_rowptr.p, grp_seg_rowptr.data(), (n_groups + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_seg_r0.p, grp_seg_r0.data(), grp_seg_r0.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_seg_m.p, grp_seg_m.data(), grp_seg_m.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_seg_off.p, grp_seg_off.data(), grp_seg_off.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (n_runs1) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_run1_agg.p, run1_agg.data(), n_runs1 * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_run_rowptr.p, lm_run_rowptr.data(), (Nl + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_grp_run_rowptr.p, grp_run_rowptr.data(), (nblk + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     {
@@ -1013,7 +1030,12 @@ static int prepare(ssb_graph* g) {
       Cz.agg_runs = g->d_agg_runs.p;
       Cz.n_runs1 = n_runs1;
       // preconditioner 3 needs <= GRP_MAXA aggregates per group (<= 80 poses per CTA) and the on-chip kernel
-      Cz.grp_enabled = (g->opts.preconditioner >= 3 && (apc + 1) / 2 <= GRP_MAXA && g->comm_world == 1) ? 1 : 0;
+      // ... and every group's landmark segments staged in the shared memory of k_grp_invert
+      Cz.grp_enabled = (g->opts.preconditioner >= 3 && (apc + 1) / 2 <= GRP_MAXA && g->comm_world == 1 &&
+                        grp_max_seg <= GRP_MAXSEG && grp_max_runs <= GRP_MAXRUN && (size_t)grp_max_runs * 18 * sizeof(double) <= 96 * 1024)
+                           ? 1 : 0;
+      Cz.grp_seg_off = g->d_grp_seg_off.p;
+      Cz.run1_agg = g->d_run1_agg.p;
       Cz.D1raw = g->d_D1raw.p;
       Cz.GrpInv = g->d_GrpInv.p;
       Cz.grp_first_agg = g->d_grp_first_agg.p;
@@ -1126,7 +1148,7 @@ static int launch_linearize(ssb_graph* g) {
     k_sub_basis<<<((G.Np + 4) / 5 + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
     g->launches++;
     if (g->Cz.n_runs1) {
-      k_sub_runs<<<(g->Cz.n_runs1 + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
+      k_sub_runs<<<(18 * g->Cz.n_runs1 + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
       g->launches++;
     }
   }
@@ -1134,7 +1156,7 @@ static int launch_linearize(ssb_graph* g) {
     k_coarse_basis<<<g->pcg_grid, 256, 0, g->stream>>>(G, g->Cz);
     g->launches++;
     if (g->Cz.n_runs) {
-      k_coarse_runs<<<(g->Cz.n_runs + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
+      k_coarse_runs<<<(18 * g->Cz.n_runs + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
       g->launches++;
     }
   }
@@ -1152,10 +1174,13 @@ static int launch_prep(ssb_graph* g, double lambda) {
   k_prep_poses<<<(G.Np + 63) / 64, 64, 0, s>>>(G, lambda);
   g->launches++;
   if (g->Cz.sub_enabled && g->comm_world == 1) {
-    k_sub_assemble<<<((G.Np + 4) / 5 + 63) / 64, 64, 0, s>>>(G, g->Cz, lambda);
+    k_sub_assemble<<<((G.Np + 4) / 5 + SUBA_AGG - 1) / SUBA_AGG, 36 * SUBA_AGG, 0, s>>>(G, g->Cz, lambda);
     g->launches++;
     if (g->Cz.grp_enabled && g->fast_ok) {
-      k_grp_invert<<<g->Cz.n_groups, GRP_THREADS, 0, s>>>(G, g->Cz);
+      const size_t dsm = (size_t)std::max(g->grp_max_runs, 1) * 18 * sizeof(double);
+      if (dsm > 40 * 1024)
+        SSB_CUDA_CHECK(cudaFuncSetAttribute(k_grp_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      k_grp_invert<<<g->Cz.n_groups, GRP_THREADS, dsm, s>>>(G, g->Cz, g->grp_max_runs);
       g->launches++;
     }
   }

@@ -344,6 +344,8 @@ struct CoarseDev {
   const int* grp_seg_rowptr;  // [n_groups+1] landmark segments: >= 2 consecutive runs of one landmark inside a group
   const int* grp_seg_r0;      //              first run of the segment
   const int* grp_seg_m;       //              number of runs
+  const int* grp_seg_off;     //              offset of the segment's runs inside the group's flat run list
+  const int* run1_agg;        // [n_runs1] aggregate of every (landmark, aggregate) run
   int n_groups;
 };
 constexpr int GRP_MAXA = 8;                          // aggregates per group
@@ -534,21 +536,19 @@ __global__ void __launch_bounds__(256) k_coarse_basis(DevGraph G, CoarseDev Cz) 
 
 // per LM iteration: G_run = sum over the run of HplL_e (3x6) * B_p(e) (6x6)
 __global__ void __launch_bounds__(128) k_coarse_runs(DevGraph G, CoarseDev Cz) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  // one thread per (run, entry of the 3x6 product): Grun = sum_e HplL_e B_p(e)
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = t / 18, q = t - 18 * r;
   if (r >= Cz.n_runs) return;
-  double acc[18];
-  for (int k = 0; k < 18; ++k) acc[k] = 0.0;
+  const int a = q / 6, c = q - 6 * a;
+  double acc = 0.0;
   for (int e = Cz.run_e0[r]; e < Cz.run_e0[r + 1]; ++e) {
-    const double* Hl = G.HplL + 18 * (size_t)e;
-    const double* B = Cz.Bmat + 36 * (size_t)G.pl[e].p;
-    for (int a = 0; a < 3; ++a)
-      for (int c = 0; c < 6; ++c) {
-        double t = 0.0;
-        for (int k = 0; k < 6; ++k) t += Hl[6 * a + k] * B[6 * k + c];
-        acc[6 * a + c] += t;
-      }
+    const double* Hl = G.HplL + 18 * (size_t)e + 6 * a;
+    const double* B = Cz.Bmat + 36 * (size_t)G.pl[e].p + c;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc += Hl[k] * B[6 * k];
   }
-  for (int k = 0; k < 18; ++k) Cz.Grun[18 * (size_t)r + k] = acc[k];
+  Cz.Grun[18 * (size_t)r + q] = acc;
 }
 
 // ---- middle level (5-pose aggregates) -----------------------------------------------------------
@@ -584,101 +584,107 @@ __global__ void __launch_bounds__(128) k_sub_basis(DevGraph G, CoarseDev Cz) {
 
 // per LM iteration: Grun1 of every (landmark, 5-pose aggregate) run.  One thread per run.
 __global__ void __launch_bounds__(128) k_sub_runs(DevGraph G, CoarseDev Cz) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = t / 18, q = t - 18 * r;
   if (r >= Cz.n_runs1) return;
-  double acc[18];
-  for (int k = 0; k < 18; ++k) acc[k] = 0.0;
+  const int a = q / 6, c = q - 6 * a;
+  double acc = 0.0;
   for (int e = Cz.run1_e0[r]; e < Cz.run1_e0[r + 1]; ++e) {
-    const double* Hl = G.HplL + 18 * (size_t)e;
-    const double* B = Cz.B1mat + 36 * (size_t)G.pl[e].p;
-    for (int a = 0; a < 3; ++a)
-      for (int c = 0; c < 6; ++c) {
-        double t = 0.0;
-        for (int k = 0; k < 6; ++k) t += Hl[6 * a + k] * B[6 * k + c];
-        acc[6 * a + c] += t;
-      }
+    const double* Hl = G.HplL + 18 * (size_t)e + 6 * a;
+    const double* B = Cz.B1mat + 36 * (size_t)G.pl[e].p + c;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc += Hl[k] * B[6 * k];
   }
-  for (int k = 0; k < 18; ++k) Cz.Grun1[18 * (size_t)r + k] = acc[k];
+  Cz.Grun1[18 * (size_t)r + q] = acc;
 }
 
 // per damped trial: D1 = P1' S P1 restricted to the aggregate (6x6), inverted.  One thread per aggregate.
-__global__ void __launch_bounds__(64) k_sub_assemble(DevGraph G, CoarseDev Cz, double lambda) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int SUBA_AGG = 4;   // aggregates per block of k_sub_assemble (36 threads each)
+__global__ void __launch_bounds__(36 * SUBA_AGG) k_sub_assemble(DevGraph G, CoarseDev Cz, double lambda) {
+  // one thread per entry (r, c) of the aggregate's 6x6 matrix; the inverse is taken by one thread per aggregate
+  __shared__ double Dsh[SUBA_AGG][36];
+  __shared__ int anysh[SUBA_AGG];
+  const int slot = threadIdx.x / 36, ent = threadIdx.x - 36 * slot;
+  const int a = blockIdx.x * SUBA_AGG + slot;
+  const int r = ent / 6, c = ent - 6 * r;
   const int i0 = 5 * a, i1 = min(G.Np, i0 + 5);
-  if (i0 >= G.Np) return;
-  double D[36];
-  for (int k = 0; k < 36; ++k) D[k] = 0.0;
+  const bool live = i0 < G.Np;
+  double d = 0.0;
   bool any = false;
-  for (int i = i0; i < i1; ++i) {
-    if (G.pose_fixed[i]) continue;
-    any = true;
-    const double* B = Cz.B1mat + 36 * (size_t)i;
-    const double* H = G.Hpp + 36 * (size_t)i;
-    double HB[36];
-    for (int r = 0; r < 6; ++r)
-      for (int c = 0; c < 6; ++c) {
-        double t = lambda * B[6 * r + c];
-        for (int k = 0; k < 6; ++k) t += H[6 * r + k] * B[6 * k + c];
-        HB[6 * r + c] = t;
+  if (live) {
+    for (int i = i0; i < i1; ++i) {
+      if (G.pose_fixed[i]) continue;
+      any = true;
+      const double* B = Cz.B1mat + 36 * (size_t)i;
+      const double* H = G.Hpp + 36 * (size_t)i;
+      double t = 0.0;
+      for (int x = 0; x < 6; ++x) {
+        double hb = lambda * B[6 * x + c];
+        for (int y = 0; y < 6; ++y) hb += H[6 * x + y] * B[6 * y + c];
+        t += B[6 * x + r] * hb;
       }
-    for (int r = 0; r < 6; ++r)
-      for (int c = 0; c < 6; ++c) {
-        double t = 0.0;
-        for (int k = 0; k < 6; ++k) t += B[6 * k + r] * HB[6 * k + c];
-        D[6 * r + c] += t;
+      d += t;
+      for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
+        const int code = G.pose_pp_idx[kk];
+        if (code & 1) continue;
+        const int e = code >> 1, j = G.pp[e].j;
+        if (j < i0 || j >= i1) continue;
+        const double* Bj = Cz.B1mat + 36 * (size_t)j;
+        const double* Ho = G.Hoff + 36 * (size_t)e;
+        double t1 = 0.0, t2 = 0.0;   // (B_i' Ho B_j)[r][c] and [c][r]
+        for (int x = 0; x < 6; ++x) {
+          double h1 = 0.0, h2 = 0.0;
+          for (int y = 0; y < 6; ++y) {
+            h1 += Ho[6 * x + y] * Bj[6 * y + c];
+            h2 += Ho[6 * x + y] * Bj[6 * y + r];
+          }
+          t1 += B[6 * x + r] * h1;
+          t2 += B[6 * x + c] * h2;
+        }
+        d += t1 + t2;
       }
-    for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
-      const int code = G.pose_pp_idx[kk];
-      if (code & 1) continue;
-      const int e = code >> 1, j = G.pp[e].j;
-      if (j < i0 || j >= i1) continue;
-      const double* Bj = Cz.B1mat + 36 * (size_t)j;
-      const double* Ho = G.Hoff + 36 * (size_t)e;
-      for (int r = 0; r < 6; ++r)
-        for (int c = 0; c < 6; ++c) HB[6 * r + c] = 0.0;
-      for (int r = 0; r < 6; ++r)
-        for (int c = 0; c < 6; ++c) {
-          double t = 0.0;
-          for (int k = 0; k < 6; ++k) t += Ho[6 * r + k] * Bj[6 * k + c];
-          HB[6 * r + c] = t;
-        }
-      for (int r = 0; r < 6; ++r)
-        for (int c = 0; c < 6; ++c) {
-          double t = 0.0;
-          for (int k = 0; k < 6; ++k) t += B[6 * k + r] * HB[6 * k + c];
-          D[6 * r + c] += t;
-          D[6 * c + r] += t;
-        }
     }
+    // landmark terms: D -= sum over my (landmark, aggregate) runs of G' W G with G = Grun1 (3x6)
+    for (int q = Cz.agg_run_rowptr[a]; q < Cz.agg_run_rowptr[a + 1]; ++q) {
+      const int r1 = Cz.agg_runs[q];
+      const double* Gr = Cz.Grun1 + 18 * (size_t)r1;
+      const double* Wu = G.HllInv + 6 * (size_t)Cz.run1_lm[r1];
+      const double w0 = Wu[0] * Gr[c] + Wu[1] * Gr[6 + c] + Wu[2] * Gr[12 + c];
+      const double w1 = Wu[1] * Gr[c] + Wu[3] * Gr[6 + c] + Wu[4] * Gr[12 + c];
+      const double w2 = Wu[2] * Gr[c] + Wu[4] * Gr[6 + c] + Wu[5] * Gr[12 + c];
+      d -= Gr[r] * w0 + Gr[6 + r] * w1 + Gr[12 + r] * w2;
+    }
+    Dsh[slot][ent] = d;
+    if (ent == 0) anysh[slot] = any ? 1 : 0;
   }
-  // landmark terms: D -= sum over my (landmark, aggregate) runs of G' W G with G = Grun1 (3x6)
-  for (int q = Cz.agg_run_rowptr[a]; q < Cz.agg_run_rowptr[a + 1]; ++q) {
-    const int r1 = Cz.agg_runs[q];
-    const double* Gr = Cz.Grun1 + 18 * (size_t)r1;
-    const double* Wu = G.HllInv + 6 * (size_t)Cz.run1_lm[r1];
-    const double W[9] = {Wu[0], Wu[1], Wu[2], Wu[1], Wu[3], Wu[4], Wu[2], Wu[4], Wu[5]};
-    double WG[18];  // W * G (3x6)
-    for (int u = 0; u < 3; ++u)
-      for (int c = 0; c < 6; ++c) WG[6 * u + c] = W[3 * u] * Gr[c] + W[3 * u + 1] * Gr[6 + c] + W[3 * u + 2] * Gr[12 + c];
-    for (int r = 0; r < 6; ++r)
-      for (int c = 0; c < 6; ++c) D[6 * r + c] -= Gr[r] * WG[c] + Gr[6 + r] * WG[6 + c] + Gr[12 + r] * WG[12 + c];
+  __syncthreads();
+  if (!live) return;
+  any = anysh[slot] != 0;
+  if (Cz.grp_enabled) Cz.D1raw[36 * (size_t)a + ent] = any ? 0.5 * (Dsh[slot][ent] + Dsh[slot][6 * c + r]) : 0.0;
+  if (ent == 0) {
+    double D[36];
+    for (int k = 0; k < 36; ++k) D[k] = 0.5 * (Dsh[slot][k] + Dsh[slot][6 * (k % 6) + k / 6]);
+    if (!any || !inv_spd6(D))
+      for (int k = 0; k < 36; ++k) D[k] = 0.0;
+    for (int k = 0; k < 36; ++k) Cz.D1inv[36 * (size_t)a + k] = D[k];
   }
-  if (Cz.grp_enabled)
-    for (int k = 0; k < 36; ++k) Cz.D1raw[36 * (size_t)a + k] = any ? D[k] : 0.0;
-  if (!any || !inv_spd6(D))
-    for (int k = 0; k < 36; ++k) D[k] = 0.0;
-  for (int k = 0; k < 36; ++k) Cz.D1inv[36 * (size_t)a + k] = D[k];
 }
 
 // per damped trial (preconditioner 3): assemble P1' S P1 restricted to one group of 5-pose aggregates and invert it
 // in shared memory (Gauss-Jordan, SPD => no pivoting).  One CTA of 256 threads per group; every thread owns fixed
 // matrix entries, so the landmark terms and the elimination need no atomics and are deterministic.
 constexpr int GRP_THREADS = 256;
-__global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDev Cz) {
+constexpr int GRP_MAXSEG = 192;   // landmark segments per group held in shared memory
+constexpr int GRP_MAXRUN = 1024;  // runs of those segments
+__global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDev Cz, int max_runs) {
   constexpr int LD = GRP_N + 1;
+  extern __shared__ __align__(16) double gdyn[];   // [max_runs][18] Grun1 of every run of the group's segments
   __shared__ double A[GRP_N * LD];
-  __shared__ double Gs[3 * GRP_N];   // runs of the current landmark scattered to their aggregates' columns (3 x n)
-  __shared__ double Ws[9];
+  __shared__ double Wsh[GRP_MAXSEG * 6];
+  __shared__ short segoff[GRP_MAXSEG + 1];
+  __shared__ short segpos[GRP_MAXSEG * GRP_MAXA];   // per segment: aggregate -> staged run (or -1)
+  __shared__ int runidx[GRP_MAXRUN];                // staged run -> (landmark, aggregate) run
+  __shared__ short runseg[GRP_MAXRUN];              // staged run -> segment
   __shared__ double colk[GRP_N], rowk[GRP_N];
   __shared__ int s_fail;
   const int g = blockIdx.x, tid = threadIdx.x;
@@ -689,10 +695,32 @@ __global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDe
     for (int k = tid; k < GRP_PACK; k += GRP_THREADS) out[k] = 0.0;
     return;
   }
+  const int sg0 = Cz.grp_seg_rowptr[g], nseg = min(Cz.grp_seg_rowptr[g + 1] - sg0, GRP_MAXSEG);
   for (int k = tid; k < GRP_N * LD; k += GRP_THREADS) A[k] = 0.0;
-  for (int k = tid; k < 3 * GRP_N; k += GRP_THREADS) Gs[k] = 0.0;
   if (tid == 0) s_fail = 0;
+  // stage every landmark segment of the group: pass 1, one thread per segment (its W, the run list);
+  // pass 2, flat over all (run, entry) pairs — no dependent global loads inside serial loops
+  for (int sg = tid; sg < nseg; sg += GRP_THREADS) {
+    const int r0 = Cz.grp_seg_r0[sg0 + sg], o = Cz.grp_seg_off[sg0 + sg], m = Cz.grp_seg_m[sg0 + sg];
+    segoff[sg] = (short)o;
+    if (sg == nseg - 1) segoff[nseg] = (short)(o + m);
+    const double* Wu = G.HllInv + 6 * (size_t)Cz.run1_lm[r0];
+    for (int k = 0; k < 6; ++k) Wsh[6 * sg + k] = Wu[k];
+    for (int k = 0; k < GRP_MAXA; ++k) segpos[GRP_MAXA * sg + k] = -1;
+    for (int x = 0; x < m; ++x)
+      if (o + x < GRP_MAXRUN) {
+        runidx[o + x] = r0 + x;
+        runseg[o + x] = (short)sg;
+      }
+  }
+  if (nseg == 0 && tid == 0) segoff[0] = 0;
   __syncthreads();
+  const int nrun = min((int)segoff[nseg], min(max_runs, GRP_MAXRUN));
+  for (int idx = tid; idx < 18 * nrun; idx += GRP_THREADS) {
+    const int rr = idx / 18, q = idx - 18 * rr, rg = runidx[rr];
+    gdyn[idx] = Cz.Grun1[18 * (size_t)rg + q];
+    if (q == 0) segpos[GRP_MAXA * runseg[rr] + (Cz.run1_agg[rg] - a0)] = (short)rr;
+  }
   for (int idx = tid; idx < 36 * na; idx += GRP_THREADS) {
     const int a = idx / 36, e = idx - 36 * a;
     A[(6 * a + e / 6) * LD + 6 * a + e % 6] = Cz.D1raw[36 * (size_t)(a0 + a) + e];
@@ -727,39 +755,25 @@ __global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDe
     }
   }
   __syncthreads();
-  // landmarks seen from several aggregates of the group: A -= Gs' W Gs on the blocks that couple different aggregates
-  for (int sgm = Cz.grp_seg_rowptr[g]; sgm < Cz.grp_seg_rowptr[g + 1]; ++sgm) {
-    const int r0 = Cz.grp_seg_r0[sgm], m = Cz.grp_seg_m[sgm];
-    if (tid < 18 * m) {
-      const int x = tid / 18, q = tid - 18 * x, u = q / 6, c = q - 6 * u;
-      const int ax = G.pl[Cz.run1_e0[r0 + x]].p / 5 - a0;
-      Gs[u * GRP_N + 6 * ax + c] = Cz.Grun1[18 * (size_t)(r0 + x) + q];
+  // landmarks seen from several aggregates of the group: every thread owns fixed entries (i, j) in blocks that couple
+  // two different aggregates and walks the staged segments: A[i][j] -= sum_l (G_x' W_l G_y)[i%6][j%6]
+  for (int idx = tid; idx < n * n; idx += GRP_THREADS) {
+    const int i = idx / n, j = idx - n * i;
+    const int ai = i / 6, aj = j / 6, ri = i - 6 * ai, cj = j - 6 * aj;
+    if (ai == aj) continue;   // the diagonal blocks already hold their landmark terms (D1raw)
+    double t = 0.0;
+    for (int sg = 0; sg < nseg; ++sg) {
+      const int x = segpos[GRP_MAXA * sg + ai], y = segpos[GRP_MAXA * sg + aj];
+      if (x < 0 || y < 0) continue;
+      const double* Gx = gdyn + 18 * x;
+      const double* Gy = gdyn + 18 * y;
+      const double* Wu = Wsh + 6 * sg;
+      const double w0 = Wu[0] * Gy[cj] + Wu[1] * Gy[6 + cj] + Wu[2] * Gy[12 + cj];
+      const double w1 = Wu[1] * Gy[cj] + Wu[3] * Gy[6 + cj] + Wu[4] * Gy[12 + cj];
+      const double w2 = Wu[2] * Gy[cj] + Wu[4] * Gy[6 + cj] + Wu[5] * Gy[12 + cj];
+      t += Gx[ri] * w0 + Gx[6 + ri] * w1 + Gx[12 + ri] * w2;
     }
-    if (tid >= 224 && tid < 233) {
-      const double* Wu = G.HllInv + 6 * (size_t)Cz.run1_lm[r0];
-      const int q = tid - 224, r = q / 3, c = q - 3 * r;
-      const int ut[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
-      Ws[3 * r + c] = Wu[ut[3 * r + c]];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < n * n; idx += GRP_THREADS) {
-      const int i = idx / n, j = idx - n * i;
-      if (i / 6 == j / 6) continue;   // the diagonal blocks already hold their landmark terms (D1raw)
-      double t = 0.0;
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const double wg = Ws[3 * u] * Gs[j] + Ws[3 * u + 1] * Gs[GRP_N + j] + Ws[3 * u + 2] * Gs[2 * GRP_N + j];
-        t += Gs[u * GRP_N + i] * wg;
-      }
-      A[i * LD + j] -= t;
-    }
-    __syncthreads();
-    if (tid < 18 * m) {   // clear the scattered entries again
-      const int x = tid / 18, q = tid - 18 * x, u = q / 6, c = q - 6 * u;
-      const int ax = G.pl[Cz.run1_e0[r0 + x]].p / 5 - a0;
-      Gs[u * GRP_N + 6 * ax + c] = 0.0;
-    }
-    // (the next iteration's writes to Gs / Ws are ordered after this one's reads by the barrier above)
+    A[i * LD + j] -= t;
   }
   __syncthreads();
   // aggregates without a free pose have a zero block: decouple them with an identity
@@ -784,17 +798,17 @@ __global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDe
       rowk[tid] = A[k * LD + tid];
     }
     __syncthreads();
-    for (int idx = tid; idx < n * n; idx += GRP_THREADS) {
-      const int i = idx / n, j = idx - n * i;
-      double v;
-      if (i == k)
-        v = (j == k) ? ip : rowk[j] * ip;
-      else if (j == k)
-        v = -colk[i] * ip;
-      else
-        v = A[i * LD + j] - colk[i] * rowk[j] * ip;
-      A[i * LD + j] = v;
-    }
+    for (int i = tid >> 4; i < n; i += 16)
+      for (int j = tid & 15; j < n; j += 16) {
+        double v;
+        if (i == k)
+          v = (j == k) ? ip : rowk[j] * ip;
+        else if (j == k)
+          v = -colk[i] * ip;
+        else
+          v = A[i * LD + j] - colk[i] * rowk[j] * ip;
+        A[i * LD + j] = v;
+      }
     __syncthreads();
   }
   __syncthreads();

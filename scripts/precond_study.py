@@ -108,9 +108,14 @@ def run2(desc, ops_spec, tol=1e-6):
     while rz > tol * tol * rz0 and it < 5000:
         q = S @ p; a = rz / (p @ q); x += a * p; r -= a * q; z = M(r); rzn = r @ z; p = z + (rzn / rz) * p; rz = rzn; it += 1
     print(f"{desc:70s} iterations {it}", flush=True)
-run2("groups7(5) + full(CTA)                 [preconditioner 3]", [("group", 5, 7), ("full", C, 0)])
-run2("groups7(5) + diag(CTA/2) + full(CTA)", [("group", 5, 7), ("diag", C // 2, 0), ("full", C, 0)])
-run2("groups7(5) + full(CTA/2)", [("group", 5, 7), ("full", C // 2, 0)])
-run2("groups7(5) + full(CTA/2) + full(CTA)", [("group", 5, 7), ("full", C // 2, 0), ("full", C, 0)])
-run2("groups14(5) + full(CTA)", [("group", 5, 14), ("full", C, 0)])
-run2("groups28(5) [2 CTAs] + full(CTA)", [("group", 5, 28), ("full", C, 0)])
+def run3(desc, w, tol=1e-6):
+    P5, A5 = get(5); G5 = blockdiag_inv_groups(A5, 7)
+    Pc, Ac = get(C); lu = spla.splu(Ac.tocsc())
+    def M(r):
+        return w[0] * (Dinv @ r) + w[1] * (P5 @ (G5 @ (P5.T @ r))) + w[2] * (Pc @ lu.solve(Pc.T @ r))
+    x = np.zeros(n); r = g.copy(); z = M(r); p = z.copy(); rz = r @ z; rz0 = rz; it = 0
+    while rz > tol * tol * rz0 and it < 5000:
+        q = S @ p; a = rz / (p @ q); x += a * p; r -= a * q; z = M(r); rzn = r @ z; p = z + (rzn / rz) * p; rz = rzn; it += 1
+    print(f"{desc:50s} w={w} iterations {it}", flush=True)
+for w in [(1, 1, 1), (1, 1, 2), (0.5, 1, 2), (0.5, 1, 3)]:
+    run3("weighted additive", w)

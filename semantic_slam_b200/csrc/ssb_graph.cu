@@ -158,6 +158,8 @@ struct ssb_graph {
   int num_sms = 0;
   int pcg_grid = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // auxiliary stream for independent small kernels (forked from / joined to `stream`)
+  cudaEvent_t ev_fork = nullptr, ev_mid = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ev_pool;  // pairs around every k_pcg launch of the current optimize
   size_t ev_used = 0;
@@ -282,6 +284,10 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
   }
   g->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g->ev_mid, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess ||
       cudaMallocHost((void**)&g->h_scalars, 32 * sizeof(double)) != cudaSuccess ||
       cudaMallocHost((void**)&g->h_iscalars, 4 * sizeof(int)) != cudaSuccess ||
@@ -319,6 +325,11 @@ void ssb_graph_destroy(ssb_graph* g) {
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
+  if (g->stream2) cudaStreamSynchronize(g->stream2);
+  if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  if (g->ev_mid) cudaEventDestroy(g->ev_mid);
+  if (g->ev_join) cudaEventDestroy(g->ev_join);
+  if (g->stream2) cudaStreamDestroy(g->stream2);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
   if (g->h_scalars) cudaFreeHost(g->h_scalars);
@@ -1134,46 +1145,62 @@ static int launch_chi2(ssb_graph* g) {
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;
 }
+// The small per-iteration kernels under-fill the GPU (a few thousand threads each), so independent ones run
+// concurrently on an auxiliary stream forked from / joined to the handle's stream with events:
+//   s : lin_landmarks -> [E1] -> sub_basis -> sub_runs            s2: lin_poses -> (wait E1) coarse_basis -> coarse_runs
+//   s : prep_landmarks -> [E1] -> sub_assemble -> grp_invert       s2: (wait E1) prep_poses
 static int launch_linearize(ssb_graph* g) {
   DevGraph& G = g->G;
+  cudaStream_t s = g->stream, s2 = g->stream2;
+  SSB_CUDA_CHECK(cudaEventRecord(g->ev_fork, s));
+  SSB_CUDA_CHECK(cudaStreamWaitEvent(s2, g->ev_fork, 0));
   if (G.Nl) {
-    k_lin_landmarks<<<(32 * G.Nl + 127) / 128, 128, 0, g->stream>>>(G);
+    k_lin_landmarks<<<(32 * G.Nl + 127) / 128, 128, 0, s>>>(G);
     g->launches++;
   }
+  SSB_CUDA_CHECK(cudaEventRecord(g->ev_mid, s));
   if (G.Np) {
-    k_lin_poses<<<(G.Np + 63) / 64, 64, 0, g->stream>>>(G);
+    k_lin_poses<<<(G.Np + 63) / 64, 64, 0, s2>>>(G);
     g->launches++;
   }
   if (g->Cz.sub_enabled && G.Np) {
-    k_sub_basis<<<((G.Np + 4) / 5 + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
+    k_sub_basis<<<((G.Np + 4) / 5 + 127) / 128, 128, 0, s>>>(G, g->Cz);
     g->launches++;
     if (g->Cz.n_runs1) {
-      k_sub_runs<<<(18 * g->Cz.n_runs1 + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
+      k_sub_runs<<<(18 * g->Cz.n_runs1 + 127) / 128, 128, 0, s>>>(G, g->Cz);
       g->launches++;
     }
   }
   if (g->Cz.enabled) {
-    k_coarse_basis<<<g->pcg_grid, 256, 0, g->stream>>>(G, g->Cz);
+    SSB_CUDA_CHECK(cudaStreamWaitEvent(s2, g->ev_mid, 0));   // coarse_runs reads HplL written by lin_landmarks
+    k_coarse_basis<<<g->pcg_grid, 256, 0, s2>>>(G, g->Cz);
     g->launches++;
     if (g->Cz.n_runs) {
-      k_coarse_runs<<<(18 * g->Cz.n_runs + 127) / 128, 128, 0, g->stream>>>(G, g->Cz);
+      k_coarse_runs<<<(18 * g->Cz.n_runs + 127) / 128, 128, 0, s2>>>(G, g->Cz);
       g->launches++;
     }
   }
+  SSB_CUDA_CHECK(cudaEventRecord(g->ev_join, s2));
+  SSB_CUDA_CHECK(cudaStreamWaitEvent(s, g->ev_join, 0));
   SSB_CUDA_CHECK(cudaGetLastError());
   g->have_system = true;
   return SSB_OK;
 }
 static int launch_prep(ssb_graph* g, double lambda) {
   DevGraph& G = g->G;
-  cudaStream_t s = g->stream;
+  cudaStream_t s = g->stream, s2 = g->stream2;
   if (G.Nl) {
     k_prep_landmarks<<<(G.Nl + 127) / 128, 128, 0, s>>>(G, lambda);
     g->launches++;
   }
-  k_prep_poses<<<(G.Np + 63) / 64, 64, 0, s>>>(G, lambda);
+  const bool fork = g->Cz.sub_enabled && g->comm_world == 1;
+  if (fork) {
+    SSB_CUDA_CHECK(cudaEventRecord(g->ev_fork, s));
+    SSB_CUDA_CHECK(cudaStreamWaitEvent(s2, g->ev_fork, 0));
+  }
+  k_prep_poses<<<(G.Np + 63) / 64, 64, 0, fork ? s2 : s>>>(G, lambda);
   g->launches++;
-  if (g->Cz.sub_enabled && g->comm_world == 1) {
+  if (fork) {
     k_sub_assemble<<<((G.Np + 4) / 5 + SUBA_AGG - 1) / SUBA_AGG, 36 * SUBA_AGG, 0, s>>>(G, g->Cz, lambda);
     g->launches++;
     if (g->Cz.grp_enabled && g->fast_ok) {
@@ -1183,6 +1210,8 @@ static int launch_prep(ssb_graph* g, double lambda) {
       k_grp_invert<<<g->Cz.n_groups, GRP_THREADS, dsm, s>>>(G, g->Cz, g->grp_max_runs);
       g->launches++;
     }
+    SSB_CUDA_CHECK(cudaEventRecord(g->ev_join, s2));
+    SSB_CUDA_CHECK(cudaStreamWaitEvent(s, g->ev_join, 0));
   }
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;

@@ -311,7 +311,7 @@ def main():
                    "unit": "Mpts/s", "points_per_step": npts, "ms_per_step": 1e3 * t_rs / steps,
                    "e2e": {"value": world * e2e_steps * npts / t_e2e_r / 1e6, "unit": "Mpts/s",
                            "h2d_bytes_per_step": int(cl.msg.size + cl.triples.size * 4 + cl.boxes.size * 4),
-                           "d2h_bytes_per_step": int(64 * 48 + 64 * 1024 * 4 + npts)},
+                           "d2h_bytes_per_step": int(64 * 64 + 64 * 1024 * 4 + npts)},
                    "roofline": {"kernel": "k_count (point x hypothesis sweep)", "bound": "hbm",
                                 "achieved": steps * ransac_bytes / t_cnt / 1e9 if t_cnt > 0 else 0.0, "peak": hbm_peak,
                                 "unit": "GB/s", "frac": (steps * ransac_bytes / t_cnt / 1e9) / hbm_peak if t_cnt > 0 else 0.0,

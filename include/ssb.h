@@ -191,6 +191,9 @@ typedef struct ssb_plane_result {
   int refined_count;     /* inliers of the refined model (selectWithinDistance)                 */
   float coef[4];         /* winning 3-point model (a,b,c,d)                                     */
   float refined[4];      /* after optimizeModelCoefficients                                     */
+  float centroid[3];     /* centroid of the winning model's inliers (what optimizeModelCoefficients
+                            computes; zeros when refine is off or fewer than 4 inliers)             */
+  int reserved;
 } ssb_plane_result;
 
 typedef struct ssb_ransac ssb_ransac;   /* persistent device buffers + stream */
@@ -269,6 +272,31 @@ typedef struct ssb_landmark_obs {    /* landmark  include/ps_graph_slam/landmark
   float covariance[9];               /* = Q_ */
   double information[9];             /* covariance.inverse().cast<double>() (:170), row-major */
 } ssb_landmark_obs;
+
+typedef struct ssb_planar_region {   /* one pcl::PlanarRegion as consumed by multiPlaneSegmentation :160-255 */
+  float centroid[3];                 /* regions[i].getCentroid(), camera frame */
+  float model[4];                    /* regions[i].getCoefficients() */
+  int contour_points;                /* regions[i].getContour().size() (gate > 100, :169) */
+  float area;                        /* pcl::calculatePolygonArea(contour) (gate >= planar_area, :195) */
+} ssb_planar_region;
+
+typedef struct ssb_detected_object { /* detected_object  include/planar_segmentation/detected_object.h:14-24 */
+  int type;
+  int plane_type;                    /* 0 "horizontal", 1 "vertical" */
+  float prob;
+  float num_points;
+  float pose[3];                     /* camera frame */
+  float world_pose[3];
+  float normal_orientation[4];
+} ssb_detected_object;
+
+/* plane_segmentation::multiPlaneSegmentation's region post-processing (src/planar_segmentation/plane_segmentation.cpp:
+ * 117-132,160-255) + point_cloud_segmentation::segmentPlanarSurfaces (include/planar_segmentation/
+ * point_cloud_segmentation.h:26-103): gates, horizontal/vertical classification against gravity, normal sign
+ * conventions, camera -> world.  Host code (a handful of regions per frame).  Returns the number of objects written
+ * to out[] (<= n) or an error. */
+int ssb_segment_planar_surfaces(const ssb_planar_region* regions, int n, const float robot_pose[6], float cam_angle,
+                                int object_type, float prob, float planar_area, ssb_detected_object* out);
 
 void ssb_assoc_default_opts(ssb_assoc_opts* o);
 ssb_assoc* ssb_assoc_create(const ssb_assoc_opts* opts);   /* data_association::data_association + init */

@@ -290,7 +290,8 @@ def se3_oplus(T, v):
 
 
 PLANE_RESULT_DTYPE = np.dtype([("status", "i4"), ("n_points", "i4"), ("best_hyp", "i4"), ("best_count", "i4"),
-                               ("iterations", "i4"), ("refined_count", "i4"), ("coef", "f4", 4), ("refined", "f4", 4)])
+                               ("iterations", "i4"), ("refined_count", "i4"), ("coef", "f4", 4), ("refined", "f4", 4),
+                               ("centroid", "f4", 3), ("reserved", "i4")])
 
 
 def crop(msg, width, height, point_step, row_step, offsets, box):

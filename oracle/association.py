@@ -247,3 +247,34 @@ class OracleDataAssociation:
                 l.id = self.landmarks[nearest].id
                 out.append(l)
         return out
+
+
+def segment_planar_surfaces(regions, robot_pose, cam_angle, object_type=0, prob=1.0, planar_area=0.0):
+    """plane_segmentation.cpp:117-132,160-255 (gates, horizontal / vertical classification, normal signs) +
+    point_cloud_segmentation.h:26-103 (camera -> world), float32 like the reference"""
+    rp = np.asarray(robot_pose, dtype=f32)
+    M = transform_normals_to_world(rp, f32(cam_angle))
+    nh = [M[2, 0], M[2, 1], M[2, 2]]          # transformation_mat^T * (0,0,1,0)
+    out = []
+    for cen, model, cpts, area in regions:
+        cen = np.asarray(cen, dtype=f32)
+        model = np.asarray(model, dtype=f32)
+        if not cpts > 100:
+            continue
+        dot = f32(0)
+        for k in range(3):
+            dot = f32(dot + f32(nh[k] * model[k]))
+        if not f32(min(area, 3.0e38)) >= f32(planar_area):
+            continue
+        if all(float(f32(abs(model[k]) - abs(nh[k]))) < 0.3 for k in range(3)):
+            flag, flip = 0, bool(model[1] > 0)
+        elif float(dot) < 0.5:
+            flag, flip = 1, bool(model[0] > 0)
+        else:
+            continue
+        cam = np.array([cen[0], cen[1], cen[2], 1.0], dtype=f32)
+        w = mulv4(M, cam)
+        world = np.array([f32(w[k] + rp[k]) for k in range(3)], dtype=f32)
+        normal = (-model if flip else model).astype(f32)
+        out.append((int(object_type), flag, cam[:3].copy(), normal, world))
+    return out

@@ -39,6 +39,8 @@ struct PlaneResult {       // must match ssb_plane_result in include/ssb.h
   int refined_count;       // inliers of the refined model (== best_count when refine off)
   float coef[4];           // winning 3-point model
   float refined[4];        // after optimizeModelCoefficients (== coef when refine off or < 4 inliers)
+  float centroid[3];       // centroid of the winning model's inliers (zeros when not refined)
+  int reserved;
 };
 
 static inline float plane_dist(const float* c, float x, float y, float z) {
@@ -176,7 +178,8 @@ static void eigen33_smallest(const double* mat, double* evec) {
 }
 
 // SampleConsensusModelPlane::optimizeModelCoefficients over the inliers of `coef`
-static void refine_plane(const float* pts, int n, const float* coef, float thr_eff, float* out) {
+static void refine_plane(const float* pts, int n, const float* coef, float thr_eff, float* out, float* cen = nullptr) {
+  if (cen) cen[0] = cen[1] = cen[2] = 0.f;
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long cnt = 0;
   for (int i = 0; i < n; ++i) {
@@ -218,6 +221,11 @@ static void refine_plane(const float* pts, int n, const float* coef, float thr_e
   float cx = (float)acc[6], cy = (float)acc[7], cz = (float)acc[8];
   float dot = (out[0] * cx + out[1] * cy) + (out[2] * cz + 0.f * 1.0f);
   out[3] = -1.f * dot;
+  if (cen) {
+    cen[0] = cx;
+    cen[1] = cy;
+    cen[2] = cz;
+  }
 }
 
 // plane_segmentation::segmentPointCloudData :24-82.  Returns n = w*h, or -1 for a "spurious" box.
@@ -340,7 +348,7 @@ int orc_ransac_batch(const void* msg, int width, int height, int point_step, int
     }
     std::memcpy(R.coef, best_coef, sizeof(best_coef));
     if (refine)
-      refine_plane(pts.data(), n, best_coef, thr, R.refined);
+      refine_plane(pts.data(), n, best_coef, thr, R.refined, R.centroid);
     else
       std::memcpy(R.refined, best_coef, sizeof(best_coef));
     int rc = 0;

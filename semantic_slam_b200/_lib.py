@@ -59,7 +59,7 @@ SYMBOLS = [
     "ssb_graph_solve_once", "ssb_comm_unique_id", "ssb_graph_attach_comm", "ssb_shard_ranges", "ssb_ransac_default_opts",
     "ssb_ransac_create", "ssb_ransac_destroy", "ssb_ransac_plane_batch", "ssb_ransac_upload",
     "ssb_ransac_run_resident", "ssb_ransac_fetch", "ssb_ransac_stream", "ssb_ransac_launch_count", "ssb_ransac_timing", "ssb_crop_bbox",
-    "ssb_assoc_default_opts", "ssb_assoc_create", "ssb_assoc_destroy", "ssb_assoc_find_matches",
+    "ssb_segment_planar_surfaces", "ssb_assoc_default_opts", "ssb_assoc_create", "ssb_assoc_destroy", "ssb_assoc_find_matches",
     "ssb_assoc_set_landmark_estimate", "ssb_assoc_set_landmark_cov", "ssb_assoc_num_landmarks", "ssb_assoc_get_landmark",
     "ssb_last_error", "ssb_build_info", "ssb_graph_stream", "ssb_graph_snapshot", "ssb_graph_restore",
 ]

@@ -27,6 +27,49 @@ class LandmarkObsC(C.Structure):
                 ("covariance", C.c_float * 9), ("information", C.c_double * 9)]
 
 
+class PlanarRegionC(C.Structure):
+    _fields_ = [("centroid", C.c_float * 3), ("model", C.c_float * 4), ("contour_points", C.c_int), ("area", C.c_float)]
+
+
+class DetectedObjectC(C.Structure):
+    _fields_ = [("type", C.c_int), ("plane_type", C.c_int), ("prob", C.c_float), ("num_points", C.c_float),
+                ("pose", C.c_float * 3), ("world_pose", C.c_float * 3), ("normal_orientation", C.c_float * 4)]
+
+
+def segment_planar_surfaces(regions, robot_pose, cam_angle: float, object_type: int = 0, prob: float = 1.0,
+                            planar_area: float = 0.0):
+    """point_cloud_segmentation::segmentPlanarSurfaces over the post-processed regions of multiPlaneSegmentation
+    (point_cloud_segmentation.h:26-103, plane_segmentation.cpp:160-255).  regions: sequence of
+    (centroid3, model4, contour_points, area).  Returns detections in the form DataAssociation.find_matches takes,
+    plus the world pose: [(type, plane_type, pose_cam float32[3], normal float32[4], world_pose float32[3])]."""
+    L = _lib.lib()
+    L.ssb_segment_planar_surfaces.argtypes = [C.POINTER(PlanarRegionC), C.c_int, C.POINTER(C.c_float), C.c_float, C.c_int,
+                                              C.c_float, C.c_float, C.POINTER(DetectedObjectC)]
+    n = len(regions)
+    reg = (PlanarRegionC * max(n, 1))()
+    for k, (cen, model, cpts, area) in enumerate(regions):
+        for c in range(3):
+            reg[k].centroid[c] = float(np.float32(cen[c]))
+        for c in range(4):
+            reg[k].model[c] = float(np.float32(model[c]))
+        reg[k].contour_points = int(cpts)
+        reg[k].area = float(np.float32(min(area, 3.0e38)))
+    rp = np.ascontiguousarray(robot_pose, dtype=np.float32)
+    out = (DetectedObjectC * max(n, 1))()
+    m = check(L.ssb_segment_planar_surfaces(reg, n, rp.ctypes.data_as(C.POINTER(C.c_float)), C.c_float(float(np.float32(cam_angle))),
+                                            int(object_type), C.c_float(prob), C.c_float(planar_area), out),
+              "segment_planar_surfaces")
+    return [(o.type, o.plane_type, np.array(o.pose[:], dtype=np.float32), np.array(o.normal_orientation[:], dtype=np.float32),
+             np.array(o.world_pose[:], dtype=np.float32)) for o in out[:m]]
+
+
+def planar_regions_from_ransac(results):
+    """Regions for segment_planar_surfaces out of PlaneSegmentation.fit_planes results: inlier centroid and refined
+    model of every fitted crop; the RANSAC path has no contour, so the contour gate sees the inlier count and the
+    area gate is open."""
+    return [(r["centroid"], r["refined"], int(r["refined_count"]), np.inf) for r in results if int(r["status"]) == 0]
+
+
 @dataclasses.dataclass
 class Landmark:
     """``landmark`` (include/ps_graph_slam/landmark.h:16-35) as returned for one detection"""

@@ -241,6 +241,57 @@ int ssb_assoc_get_landmark(const ssb_assoc* a, int id, ssb_landmark_obs* out) {
   return SSB_OK;
 }
 
+// plane_segmentation::multiPlaneSegmentation's per-region post-processing (plane_segmentation.cpp:117-132,160-255:
+// gates, horizontal / vertical classification against gravity in the camera frame, normal sign conventions) followed
+// by point_cloud_segmentation::segmentPlanarSurfaces (point_cloud_segmentation.h:26-103: camera -> world, the
+// detected_object record).  The regions themselves come from a plane extractor (PCL's organised multi-plane
+// segmentation in the reference; ssb_ransac_plane_batch here).
+int ssb_segment_planar_surfaces(const ssb_planar_region* regions, int n, const float robot_pose[6], float cam_angle,
+                                int object_type, float prob, float planar_area, ssb_detected_object* out) {
+  if ((n > 0 && (!regions || !out)) || !robot_pose || n < 0) {
+    ssb::set_error("ssb_segment_planar_surfaces: invalid argument");
+    return SSB_ERR_INVALID;
+  }
+  const Mat4 M = transform_normals_to_world(robot_pose, cam_angle);
+  // normals_of_the_horizontal_plane_in_cam = transformation_mat^T * (0, 0, 1, 0)  (:126-132)
+  const float nh[3] = {M.m[8], M.m[9], M.m[10]};
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    const ssb_planar_region& R = regions[i];
+    if (!(R.contour_points > 100)) continue;                 // :169
+    float dot = 0;                                           // computeDotProduct :547-555
+    for (int k = 0; k < 3; ++k) dot = dot + nh[k] * R.model[k];
+    if (!(R.area >= planar_area)) continue;                  // :195
+    int flag;
+    bool flip;
+    if ((double)(std::fabs(R.model[0]) - std::fabs(nh[0])) < 0.3 && (double)(std::fabs(R.model[1]) - std::fabs(nh[1])) < 0.3 &&
+        (double)(std::fabs(R.model[2]) - std::fabs(nh[2])) < 0.3) {
+      flag = 0;                 // horizontal (:197-224); normals upwards
+      flip = R.model[1] > 0;
+    } else if ((double)dot < 0.5) {
+      flag = 1;                 // vertical (:226-250); normals to the left
+      flip = R.model[0] > 0;
+    } else {
+      continue;
+    }
+    ssb_detected_object& o = out[m++];
+    std::memset(&o, 0, sizeof(o));
+    const float cam[4] = {R.centroid[0], R.centroid[1], R.centroid[2], 1.0f};
+    float w[4];
+    mulv4(M, cam, w);           // point_cloud_segmentation.h:56-57
+    o.type = object_type;
+    o.plane_type = flag;        // 0 "horizontal", 1 "vertical" (:79-82)
+    o.prob = prob;
+    o.num_points = (float)R.contour_points;
+    for (int k = 0; k < 3; ++k) {
+      o.pose[k] = cam[k];
+      o.world_pose[k] = w[k] + robot_pose[k];   // :91-94
+    }
+    for (int k = 0; k < 4; ++k) o.normal_orientation[k] = flip ? -R.model[k] : R.model[k];
+  }
+  return m;
+}
+
 int ssb_assoc_find_matches(ssb_assoc* a, const ssb_detection* dets, int n, const float robot_pose[6], float cam_angle,
                            ssb_landmark_obs* out) {
   if (!a || (n > 0 && (!dets || !out)) || !robot_pose || n < 0) {

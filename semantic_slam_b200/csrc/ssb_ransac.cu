@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(FIN_THREADS)
              unsigned char* __restrict__ mask, const int* __restrict__ mask_off) {
   __shared__ double shd[33];
   __shared__ int s_best_cnt[FIN_THREADS], s_best_k[FIN_THREADS];
-  __shared__ float s_coef[4], s_ref[4];
+  __shared__ float s_coef[4], s_ref[4], s_cen[3];
   __shared__ int s_iter, s_bestk, s_bestc, s_rc;
   const int b = blockIdx.x, tid = threadIdx.x;
   const BoxInfo B = boxes[b];
@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(FIN_THREADS)
     cnt = block_sum(cnt, shd);
     for (int k = 0; k < 9; ++k) acc[k] = block_sum(acc[k], shd);
     if (tid == 0) {
+      s_cen[0] = s_cen[1] = s_cen[2] = 0.f;
       if (cnt < 4.0) {
         for (int k = 0; k < 4; ++k) s_ref[k] = s_coef[k];
       } else {
@@ -455,10 +456,14 @@ __global__ void __launch_bounds__(FIN_THREADS)
         s_ref[1] = n1;
         s_ref[2] = n2;
         s_ref[3] = __fmul_rn(-1.f, dot);
+        s_cen[0] = cx;
+        s_cen[1] = cy;
+        s_cen[2] = cz;
       }
     }
   } else if (tid == 0) {
     for (int k = 0; k < 4; ++k) s_ref[k] = s_coef[k];
+    s_cen[0] = s_cen[1] = s_cen[2] = 0.f;
   }
   if (tid == 0) s_rc = 0;
   __syncthreads();
@@ -478,6 +483,7 @@ __global__ void __launch_bounds__(FIN_THREADS)
       R.coef[k] = s_coef[k];
       R.refined[k] = s_ref[k];
     }
+    for (int k = 0; k < 3; ++k) R.centroid[k] = s_cen[k];
     R.refined_count = s_rc;
     results[b] = R;
   }

@@ -104,3 +104,44 @@ def test_quirk_h4_stale_minimum_changes_the_outcome():
 def test_dist_is_single_precision():
     d = dist(np.float32(0.1), np.float32(0.4), np.float32(0.2), np.float32(0.2), np.float32(-1.0), np.float32(3.0))
     assert d.dtype == np.float32 and abs(float(d) - np.sqrt(0.09 + 16.0)) < 1e-6
+
+
+def test_planar_surface_postprocessing_bit_exact():
+    """multiPlaneSegmentation's region post-processing + segmentPlanarSurfaces: product vs
+    the float32 oracle, bit for bit, incl. the gates, both classes, the rejected 'neither' case and the sign flips"""
+    from semantic_slam_b200.association import segment_planar_surfaces
+    from oracle.association import segment_planar_surfaces as oracle_sps
+    rng = np.random.default_rng(3)
+    n_h = n_v = n_skip = 0
+    for trial in range(40):
+        rp = np.array([rng.normal(), rng.normal(), 0.3, rng.normal(0, 0.03), rng.normal(0, 0.03), rng.uniform(-3, 3)], dtype=np.float32)
+        regions = []
+        for _ in range(6):
+            nrm = rng.normal(0, 1, 3)
+            nrm /= np.linalg.norm(nrm)
+            regions.append((rng.uniform(-2, 2, 3) + [0, 0, 4], np.r_[nrm, rng.uniform(-5, 5)], int(rng.integers(50, 400)),
+                            float(rng.uniform(0.0, 0.2))))
+        a = segment_planar_surfaces(regions, rp, 0.15, object_type=2, prob=0.7, planar_area=0.05)
+        o = oracle_sps(regions, rp, 0.15, object_type=2, prob=0.7, planar_area=0.05)
+        assert len(a) == len(o)
+        for x, y in zip(a, o):
+            assert x[0] == y[0] == 2 and x[1] == y[1]
+            assert np.array_equal(x[2], y[2]) and np.array_equal(x[3], y[3]) and np.array_equal(x[4], y[4])
+            n_h += x[1] == 0
+            n_v += x[1] == 1
+        n_skip += len(regions) - len(a)
+    assert n_h > 5 and n_v > 20 and n_skip > 20
+
+
+def test_planar_surface_classes_on_canonical_planes():
+    """camera looking forward (cam_angle 0, level robot): the floor (normal along camera -y... i.e. +-y) is horizontal with
+    an upward (negative camera y) normal, a wall facing the camera is vertical with a normal pointing to camera -x / left"""
+    from semantic_slam_b200.association import segment_planar_surfaces
+    rp = np.zeros(6, dtype=np.float32)
+    floor = ([0.0, 1.2, 3.0], [0.0, 1.0, 0.0, -1.2], 500, 1.0)      # camera y points down: floor 1.2 m below the camera
+    wall = ([0.5, 0.0, 4.0], [0.6, 0.0, 0.8, -3.5], 500, 1.0)
+    small = ([0.0, 0.0, 2.0], [0.0, 0.0, 1.0, -2.0], 60, 1.0)        # contour too small
+    out = segment_planar_surfaces([floor, wall, small], rp, 0.0, planar_area=0.1)
+    assert [o[1] for o in out] == [0, 1]
+    assert np.allclose(out[0][3], [0.0, -1.0, 0.0, 1.2]) and out[0][4][2] < -1.0     # flipped upwards; 1.2 m below the robot
+    assert np.allclose(out[1][3], [-0.6, 0.0, -0.8, 3.5])                             # flipped towards the left

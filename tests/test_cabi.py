@@ -31,7 +31,7 @@ def test_struct_layouts_match_python_mirrors():
     from semantic_slam_b200 import _lib
     from semantic_slam_b200.segmentation import PLANE_RESULT_DTYPE
     import oracle
-    assert PLANE_RESULT_DTYPE.itemsize == 56 and oracle.PLANE_RESULT_DTYPE == PLANE_RESULT_DTYPE
+    assert PLANE_RESULT_DTYPE.itemsize == 72 and oracle.PLANE_RESULT_DTYPE == PLANE_RESULT_DTYPE
     assert C.sizeof(_lib.CloudLayoutC) == 32 and C.sizeof(_lib.RansacOpts) == 48
     o = _lib.GraphOpts()
     _lib.lib().ssb_graph_default_opts(C.byref(o))

@@ -27,6 +27,8 @@ def _compare(res, counts, mask, ores, ocounts, omask):
     a, b = res["refined"][ok], ores["refined"][ok]
     s = np.sign((a[:, :3] * b[:, :3]).sum(1))[:, None]
     assert np.abs(a * s - b).max() <= 1e-5
+    # centroid of the winning model's inliers (same inlier set, fp64 accumulation in a different order)
+    assert np.abs(res["centroid"][ok] - ores["centroid"][ok]).max() <= 1e-5 * max(1.0, np.abs(ores["centroid"][ok]).max())
     assert np.abs(res["refined_count"][ok].astype(int) - ores["refined_count"][ok]).max() <= np.maximum(
         2, 0.001 * ores["refined_count"][ok]).max()
     if mask is not None:
@@ -106,3 +108,35 @@ def test_cfg3_full_size():
     seg.run_resident()
     r2, c2, m2 = seg.fetch()
     assert np.array_equal(c2, counts) and np.array_equal(m2, mask)
+
+
+def test_frame_pipeline_cloud_to_association():
+    """One frame end to end on the product path: PointCloud2 + boxes -> crop + RANSAC (GPU) -> planar-surface
+    post-processing (multiPlaneSegmentation's classification, segmentPlanarSurfaces) -> data association, against
+    the same chain over the oracle.  Classes and association indices must agree exactly, positions within 1e-5."""
+    from semantic_slam_b200 import DataAssociation
+    from semantic_slam_b200.association import segment_planar_surfaces, planar_regions_from_ransac
+    from oracle.association import OracleDataAssociation, segment_planar_surfaces as oracle_sps
+    cl = synth.make_cloud(n_boxes=12, n_hyp=256)
+    lay = CloudLayout(cl.width, cl.height, cl.point_step, cl.row_step, cl.offsets)
+    seg = PlaneSegmentation()
+    res, counts, mask = seg.fit_planes(cl.msg, lay, cl.boxes, cl.triples)
+    ores, ocounts, omask = oracle.ransac_plane_batch(cl.msg, cl.width, cl.height, cl.point_step, cl.row_step,
+                                                     cl.offsets, cl.boxes, cl.triples)
+    rp = np.array([1.0, -2.0, 0.4, 0.01, -0.02, 0.7], dtype=np.float32)
+    kw = dict(use_maha_dist=False, use_eq_dist=True, eq_dist_thres=1.5, land_noise_low=0.1, strict=True)
+    a, o = DataAssociation(**kw), OracleDataAssociation(**kw)
+    for frame in range(2):   # the second pass re-observes the landmarks mapped by the first
+        # the RANSAC normal's sign is arbitrary (smallest eigenvector): the reference's sign conventions remove it
+        dets = segment_planar_surfaces(planar_regions_from_ransac(res), rp, 0.1, planar_area=0.0)
+        odets = oracle_sps(planar_regions_from_ransac(ores), rp, 0.1, planar_area=0.0)
+        assert len(dets) == len(odets) >= 6
+        assert [d[1] for d in dets] == [d[1] for d in odets]
+        for d, e in zip(dets, odets):
+            assert np.abs(d[2] - e[2]).max() <= 1e-5 * max(1.0, np.abs(e[2]).max())
+            assert np.abs(np.abs(d[3]) - np.abs(e[3])).max() <= 2e-4     # refined normals: fp64 PCA, different summation order
+        A = a.find_matches([d[:4] for d in dets], rp, 0.1)
+        O = o.find_matches([d[:4] for d in odets], rp, 0.1)
+        assert [(x.id, x.is_new_landmark) for x in A] == [(y.id, y.is_new_landmark) for y in O]
+        if frame == 1:
+            assert not any(x.is_new_landmark for x in A)

@@ -1160,11 +1160,11 @@ static int launch_linearize(ssb_graph* g) {
   }
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_mid, s));
   if (G.Np) {
-    k_lin_poses<<<(G.Np + 63) / 64, 64, 0, s2>>>(G);
+    k_lin_poses<<<(G.Np + 31) / 32, 64, 0, s2>>>(G);
     g->launches++;
   }
   if (g->Cz.sub_enabled && G.Np) {
-    k_sub_basis<<<((G.Np + 4) / 5 + 127) / 128, 128, 0, s>>>(G, g->Cz);
+    k_sub_basis<<<(G.Np + 127) / 128, 128, 0, s>>>(G, g->Cz);
     g->launches++;
     if (g->Cz.n_runs1) {
       k_sub_runs<<<(18 * g->Cz.n_runs1 + 127) / 128, 128, 0, s>>>(G, g->Cz);
@@ -1176,7 +1176,7 @@ static int launch_linearize(ssb_graph* g) {
     k_coarse_basis<<<g->pcg_grid, 256, 0, s2>>>(G, g->Cz);
     g->launches++;
     if (g->Cz.n_runs) {
-      k_coarse_runs<<<(18 * g->Cz.n_runs + 127) / 128, 128, 0, s2>>>(G, g->Cz);
+      k_coarse_runs<<<(72 * g->Cz.n_runs + 127) / 128, 128, 0, s2>>>(G, g->Cz);
       g->launches++;
     }
   }
@@ -1201,7 +1201,7 @@ static int launch_prep(ssb_graph* g, double lambda) {
   k_prep_poses<<<(G.Np + 63) / 64, 64, 0, fork ? s2 : s>>>(G, lambda);
   g->launches++;
   if (fork) {
-    k_sub_assemble<<<((G.Np + 4) / 5 + SUBA_AGG - 1) / SUBA_AGG, 36 * SUBA_AGG, 0, s>>>(G, g->Cz, lambda);
+    k_sub_assemble<<<(G.Np + 4) / 5, SUBA_THREADS, 0, s>>>(G, g->Cz, lambda, (g->Cz.grp_enabled && g->fast_ok) ? 0 : 1);
     g->launches++;
     if (g->Cz.grp_enabled && g->fast_ok) {
       const size_t dsm = (size_t)std::max(g->grp_max_runs, 1) * 18 * sizeof(double);

@@ -143,14 +143,20 @@ __global__ void __launch_bounds__(128) k_lin_landmarks(DevGraph G) {
 // pose-pose edge writes the off-diagonal block Hoff_e = Ji' W Jj.  Deterministic (no atomics).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k_lin_poses(DevGraph G) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= G.Np) return;
-  const bool fixed = G.pose_fixed[i] != 0;
-  const Pose X = G.pose[i];
+  // 32 poses per block: warp 0 walks the pose-landmark edges of its poses, warp 1 their pose-pose edges (two
+  // independent dependent-load chains); warp 1 hands its partial block over through shared memory
+  __shared__ double acc_sh[32][43];
+  const int lane = threadIdx.x & 31, role_w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const bool live = i < G.Np;
+  const bool fixed = live && G.pose_fixed[i] != 0;
+  Pose X;
+  if (live) X = G.pose[i];
   double H[36], b[6];
   for (int k = 0; k < 36; ++k) H[k] = 0.0;
   for (int k = 0; k < 6; ++k) b[k] = 0.0;
   // pose-landmark edges
+  if (live && role_w == 0)
   for (int kk = G.pose_pl_rowptr[i]; kk < G.pose_pl_rowptr[i + 1]; ++kk) {
     const int e = G.pose_pl_idx[kk];
     const PLEdge ed = G.pl[e];
@@ -176,6 +182,7 @@ __global__ void __launch_bounds__(64) k_lin_poses(DevGraph G) {
     G.plP_lm[kk] = ed.l;
   }
   // pose-pose edges
+  if (live && role_w == 1)
   for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
     const int code = G.pose_pp_idx[kk];
     const int e = code >> 1, role = code & 1;
@@ -219,6 +226,14 @@ __global__ void __launch_bounds__(64) k_lin_poses(DevGraph G) {
         }
     }
   }
+  if (role_w == 1) {
+    for (int k = 0; k < 36; ++k) acc_sh[lane][k] = H[k];
+    for (int k = 0; k < 6; ++k) acc_sh[lane][36 + k] = b[k];
+  }
+  __syncthreads();
+  if (role_w == 1 || !live) return;
+  for (int k = 0; k < 36; ++k) H[k] += acc_sh[lane][k];
+  for (int k = 0; k < 6; ++k) b[k] += acc_sh[lane][36 + k];
   if (fixed) {
     for (int k = 0; k < 36; ++k) H[k] = 0.0;
     for (int k = 0; k < 6; ++k) {
@@ -401,7 +416,9 @@ __device__ __forceinline__ double grid_bar_sum(BarSlot* slots, unsigned& epoch, 
     }
     red_release_add_u32(counter, 1u);  // release: orders this CTA's earlier writes (bar.sync-cumulative)
     const unsigned target = epoch * gridDim.x;
+    unsigned spins = 0;   // watchdog: trap instead of hanging the GPU if a CTA never arrives
     while (ld_acquire_u32(counter) < target) {
+      if (++spins > (1u << 26)) __trap();
     }
   }
   __syncthreads();
@@ -536,50 +553,56 @@ __global__ void __launch_bounds__(256) k_coarse_basis(DevGraph G, CoarseDev Cz) 
 
 // per LM iteration: G_run = sum over the run of HplL_e (3x6) * B_p(e) (6x6)
 __global__ void __launch_bounds__(128) k_coarse_runs(DevGraph G, CoarseDev Cz) {
-  // one thread per (run, entry of the 3x6 product): Grun = sum_e HplL_e B_p(e)
+  // four lanes per (run, entry of the 3x6 product): Grun = sum_e HplL_e B_p(e); lane `part` takes every 4th edge of
+  // the run and the four partial sums are added by two butterfly steps (fixed order => deterministic)
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = t / 18, q = t - 18 * r;
-  if (r >= Cz.n_runs) return;
+  const int part = t & 3, rq = t >> 2;
+  const int r = rq / 18, q = rq - 18 * r;
+  const bool live = r < Cz.n_runs;
   const int a = q / 6, c = q - 6 * a;
   double acc = 0.0;
-  for (int e = Cz.run_e0[r]; e < Cz.run_e0[r + 1]; ++e) {
-    const double* Hl = G.HplL + 18 * (size_t)e + 6 * a;
-    const double* B = Cz.Bmat + 36 * (size_t)G.pl[e].p + c;
+  if (live) {
+    const int e1 = Cz.run_e0[r + 1];
+    for (int e = Cz.run_e0[r] + part; e < e1; e += 4) {
+      const double* Hl = G.HplL + 18 * (size_t)e + 6 * a;
+      const double* B = Cz.Bmat + 36 * (size_t)G.pl[e].p + c;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) acc += Hl[k] * B[6 * k];
+      for (int k = 0; k < 6; ++k) acc += Hl[k] * B[6 * k];
+    }
   }
-  Cz.Grun[18 * (size_t)r + q] = acc;
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (live && part == 0) Cz.Grun[18 * (size_t)r + q] = acc;
 }
 
 // ---- middle level (5-pose aggregates) -----------------------------------------------------------
 __global__ void __launch_bounds__(128) k_sub_basis(DevGraph G, CoarseDev Cz) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i0 = 5 * a, i1 = min(G.Np, i0 + 5);
-  if (i0 >= G.Np) return;
+  // one thread per pose; the aggregate centroid is recomputed by each of its (<= 5) threads in the same order
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G.Np) return;
+  const int i0 = 5 * (i / 5), i1 = min(G.Np, i0 + 5);
   double cen[3] = {0, 0, 0};
-  for (int i = i0; i < i1; ++i)
-    for (int k = 0; k < 3; ++k) cen[k] += G.pose[i].t[k];
+  for (int q = i0; q < i1; ++q)
+    for (int k = 0; k < 3; ++k) cen[k] += G.pose[q].t[k];
   for (int k = 0; k < 3; ++k) cen[k] /= (double)(i1 - i0);
-  for (int i = i0; i < i1; ++i) {
-    double* B = Cz.B1mat + 36 * (size_t)i;
-    if (G.pose_fixed[i]) {
-      for (int k = 0; k < 36; ++k) B[k] = 0.0;
-      continue;
-    }
-    const Pose X = G.pose[i];
-    double R[9];
-    quat_to_R(X.q, R);
-    const double d[3] = {X.t[0] - cen[0], X.t[1] - cen[1], X.t[2] - cen[2]};
-    const double Sx[9] = {0, -d[2], d[1], d[2], 0, -d[0], -d[1], d[0], 0};
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) {
-        const double rt = R[3 * c + r];
-        B[6 * r + c] = rt;
-        B[6 * r + 3 + c] = -(R[r] * Sx[c] + R[3 + r] * Sx[3 + c] + R[6 + r] * Sx[6 + c]);
-        B[6 * (3 + r) + c] = 0.0;
-        B[6 * (3 + r) + 3 + c] = 0.5 * rt;
-      }
+  double* B = Cz.B1mat + 36 * (size_t)i;
+  if (G.pose_fixed[i]) {
+    for (int k = 0; k < 36; ++k) B[k] = 0.0;
+    return;
   }
+  const Pose X = G.pose[i];
+  double R[9];
+  quat_to_R(X.q, R);
+  const double d[3] = {X.t[0] - cen[0], X.t[1] - cen[1], X.t[2] - cen[2]};
+  const double Sx[9] = {0, -d[2], d[1], d[2], 0, -d[0], -d[1], d[0], 0};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      const double rt = R[3 * c + r];
+      B[6 * r + c] = rt;
+      B[6 * r + 3 + c] = -(R[r] * Sx[c] + R[3 + r] * Sx[3 + c] + R[6 + r] * Sx[6 + c]);
+      B[6 * (3 + r) + c] = 0.0;
+      B[6 * (3 + r) + 3 + c] = 0.5 * rt;
+    }
 }
 
 // per LM iteration: Grun1 of every (landmark, 5-pose aggregate) run.  One thread per run.
@@ -598,33 +621,38 @@ __global__ void __launch_bounds__(128) k_sub_runs(DevGraph G, CoarseDev Cz) {
   Cz.Grun1[18 * (size_t)r + q] = acc;
 }
 
-// per damped trial: D1 = P1' S P1 restricted to the aggregate (6x6), inverted.  One thread per aggregate.
-constexpr int SUBA_AGG = 4;   // aggregates per block of k_sub_assemble (36 threads each)
-__global__ void __launch_bounds__(36 * SUBA_AGG) k_sub_assemble(DevGraph G, CoarseDev Cz, double lambda) {
-  // one thread per entry (r, c) of the aggregate's 6x6 matrix; the inverse is taken by one thread per aggregate
-  __shared__ double Dsh[SUBA_AGG][36];
-  __shared__ int anysh[SUBA_AGG];
-  const int slot = threadIdx.x / 36, ent = threadIdx.x - 36 * slot;
-  const int a = blockIdx.x * SUBA_AGG + slot;
+// per damped trial: D1 = P1' S P1 restricted to the aggregate (6x6).  One block per aggregate: slice s (36 threads,
+// one per entry) takes pose s of the aggregate and every 5th (landmark, aggregate) run, so the dependent-load chains
+// are 5x shorter than with one slice; the slices are added in a fixed order (deterministic).  The inverse (needed by
+// preconditioner 2 and by the streaming kernel only) is taken by one thread when need_inv != 0.
+constexpr int SUBA_THREADS = 192;   // 5 slices x 36 entries (+ 12 idle threads)
+__global__ void __launch_bounds__(SUBA_THREADS) k_sub_assemble(DevGraph G, CoarseDev Cz, double lambda, int need_inv) {
+  __shared__ double part[5][36];
+  __shared__ double Dsh[36];
+  __shared__ int anysh[5];
+  const int sl = threadIdx.x / 36, ent = threadIdx.x - 36 * sl;
+  const int a = blockIdx.x;
   const int r = ent / 6, c = ent - 6 * r;
   const int i0 = 5 * a, i1 = min(G.Np, i0 + 5);
-  const bool live = i0 < G.Np;
-  double d = 0.0;
-  bool any = false;
-  if (live) {
-    for (int i = i0; i < i1; ++i) {
-      if (G.pose_fixed[i]) continue;
+  if (sl < 5) {
+    double d = 0.0;
+    bool any = false;
+    const int i = i0 + sl;
+    if (i < i1 && !G.pose_fixed[i]) {
       any = true;
       const double* B = Cz.B1mat + 36 * (size_t)i;
       const double* H = G.Hpp + 36 * (size_t)i;
+      const int k0 = G.pose_pp_rowptr[i], k1 = G.pose_pp_rowptr[i + 1];
       double t = 0.0;
+#pragma unroll
       for (int x = 0; x < 6; ++x) {
         double hb = lambda * B[6 * x + c];
+#pragma unroll
         for (int y = 0; y < 6; ++y) hb += H[6 * x + y] * B[6 * y + c];
         t += B[6 * x + r] * hb;
       }
       d += t;
-      for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
+      for (int kk = k0; kk < k1; ++kk) {
         const int code = G.pose_pp_idx[kk];
         if (code & 1) continue;
         const int e = code >> 1, j = G.pp[e].j;
@@ -632,8 +660,10 @@ __global__ void __launch_bounds__(36 * SUBA_AGG) k_sub_assemble(DevGraph G, Coar
         const double* Bj = Cz.B1mat + 36 * (size_t)j;
         const double* Ho = G.Hoff + 36 * (size_t)e;
         double t1 = 0.0, t2 = 0.0;   // (B_i' Ho B_j)[r][c] and [c][r]
+#pragma unroll
         for (int x = 0; x < 6; ++x) {
           double h1 = 0.0, h2 = 0.0;
+#pragma unroll
           for (int y = 0; y < 6; ++y) {
             h1 += Ho[6 * x + y] * Bj[6 * y + c];
             h2 += Ho[6 * x + y] * Bj[6 * y + r];
@@ -645,7 +675,7 @@ __global__ void __launch_bounds__(36 * SUBA_AGG) k_sub_assemble(DevGraph G, Coar
       }
     }
     // landmark terms: D -= sum over my (landmark, aggregate) runs of G' W G with G = Grun1 (3x6)
-    for (int q = Cz.agg_run_rowptr[a]; q < Cz.agg_run_rowptr[a + 1]; ++q) {
+    for (int q = Cz.agg_run_rowptr[a] + sl; q < Cz.agg_run_rowptr[a + 1]; q += 5) {
       const int r1 = Cz.agg_runs[q];
       const double* Gr = Cz.Grun1 + 18 * (size_t)r1;
       const double* Wu = G.HllInv + 6 * (size_t)Cz.run1_lm[r1];
@@ -654,16 +684,17 @@ __global__ void __launch_bounds__(36 * SUBA_AGG) k_sub_assemble(DevGraph G, Coar
       const double w2 = Wu[2] * Gr[c] + Wu[4] * Gr[6 + c] + Wu[5] * Gr[12 + c];
       d -= Gr[r] * w0 + Gr[6 + r] * w1 + Gr[12 + r] * w2;
     }
-    Dsh[slot][ent] = d;
-    if (ent == 0) anysh[slot] = any ? 1 : 0;
+    part[sl][ent] = d;
+    if (ent == 0) anysh[sl] = any ? 1 : 0;
   }
   __syncthreads();
-  if (!live) return;
-  any = anysh[slot] != 0;
-  if (Cz.grp_enabled) Cz.D1raw[36 * (size_t)a + ent] = any ? 0.5 * (Dsh[slot][ent] + Dsh[slot][6 * c + r]) : 0.0;
-  if (ent == 0) {
+  if (threadIdx.x < 36) Dsh[ent] = (((part[0][ent] + part[1][ent]) + part[2][ent]) + part[3][ent]) + part[4][ent];
+  __syncthreads();
+  const bool any = (anysh[0] | anysh[1] | anysh[2] | anysh[3] | anysh[4]) != 0;
+  if (threadIdx.x < 36 && Cz.grp_enabled) Cz.D1raw[36 * (size_t)a + ent] = any ? 0.5 * (Dsh[ent] + Dsh[6 * c + r]) : 0.0;
+  if (threadIdx.x == 0 && need_inv) {
     double D[36];
-    for (int k = 0; k < 36; ++k) D[k] = 0.5 * (Dsh[slot][k] + Dsh[slot][6 * (k % 6) + k / 6]);
+    for (int k = 0; k < 36; ++k) D[k] = 0.5 * (Dsh[k] + Dsh[6 * (k % 6) + k / 6]);
     if (!any || !inv_spd6(D))
       for (int k = 0; k < 36; ++k) D[k] = 0.0;
     for (int k = 0; k < 36; ++k) Cz.D1inv[36 * (size_t)a + k] = D[k];
@@ -671,11 +702,21 @@ __global__ void __launch_bounds__(36 * SUBA_AGG) k_sub_assemble(DevGraph G, Coar
 }
 
 // per damped trial (preconditioner 3): assemble P1' S P1 restricted to one group of 5-pose aggregates and invert it
-// in shared memory (Gauss-Jordan, SPD => no pivoting).  One CTA of 256 threads per group; every thread owns fixed
-// matrix entries, so the landmark terms and the elimination need no atomics and are deterministic.
+// (Gauss-Jordan, SPD => no pivoting).  One CTA of 256 threads per group.  Assembly in shared memory with fixed entry
+// ownership (no atomics, deterministic); the elimination keeps the matrix in registers (thread (ti, tj) owns the
+// entries (ti + 16 a, tj + 16 b), a, b < 3), publishes the pivot row / column through double-buffered shared vectors
+// and needs one barrier per pivot.
 constexpr int GRP_THREADS = 256;
 constexpr int GRP_MAXSEG = 192;   // landmark segments per group held in shared memory
 constexpr int GRP_MAXRUN = 1024;  // runs of those segments
+constexpr int GRP_MAXPP = 64;     // pose-pose edges between different aggregates of one group
+__device__ __forceinline__ double grp_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
 __global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDev Cz, int max_runs) {
   constexpr int LD = GRP_N + 1;
   extern __shared__ __align__(16) double gdyn[];   // [max_runs][18] Grun1 of every run of the group's segments
@@ -683,10 +724,12 @@ __global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDe
   __shared__ double Wsh[GRP_MAXSEG * 6];
   __shared__ short segoff[GRP_MAXSEG + 1];
   __shared__ short segpos[GRP_MAXSEG * GRP_MAXA];   // per segment: aggregate -> staged run (or -1)
+  __shared__ unsigned char segmask[GRP_MAXSEG];     // per segment: bit a = aggregate a has a run
   __shared__ int runidx[GRP_MAXRUN];                // staged run -> (landmark, aggregate) run
   __shared__ short runseg[GRP_MAXRUN];              // staged run -> segment
-  __shared__ double colk[GRP_N], rowk[GRP_N];
-  __shared__ int s_fail;
+  __shared__ double rowk[2][GRP_N], colk[2][GRP_N];
+  __shared__ int ppcnt[5 * GRP_MAXA + 1];
+  __shared__ int pplist[3 * GRP_MAXPP];             // (edge, pose i, pose j)
   const int g = blockIdx.x, tid = threadIdx.x;
   const int a0 = Cz.grp_first_agg[g], a1 = Cz.grp_first_agg[g + 1];
   const int na = a1 - a0, n = 6 * na;
@@ -697,7 +740,6 @@ __global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDe
   }
   const int sg0 = Cz.grp_seg_rowptr[g], nseg = min(Cz.grp_seg_rowptr[g + 1] - sg0, GRP_MAXSEG);
   for (int k = tid; k < GRP_N * LD; k += GRP_THREADS) A[k] = 0.0;
-  if (tid == 0) s_fail = 0;
   // stage every landmark segment of the group: pass 1, one thread per segment (its W, the run list);
   // pass 2, flat over all (run, entry) pairs — no dependent global loads inside serial loops
   for (int sg = tid; sg < nseg; sg += GRP_THREADS) {
@@ -714,6 +756,19 @@ __global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDe
       }
   }
   if (nseg == 0 && tid == 0) segoff[0] = 0;
+  // pose-pose edges between different aggregates of the group: every pose counts its own (role 0) ...
+  const int np = min(G.Np, 5 * a1) - 5 * a0;
+  int my_n = 0;
+  if (tid < np) {
+    const int i = 5 * a0 + tid, ai = tid / 5;
+    for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
+      const int code = G.pose_pp_idx[kk];
+      if (code & 1) continue;
+      const int aj = G.pp[code >> 1].j / 5 - a0;
+      if (aj != ai && aj >= 0 && aj < na) ++my_n;
+    }
+    ppcnt[tid] = my_n;
+  }
   __syncthreads();
   const int nrun = min((int)segoff[nseg], min(max_runs, GRP_MAXRUN));
   for (int idx = tid; idx < 18 * nrun; idx += GRP_THREADS) {
@@ -725,55 +780,92 @@ __global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDe
     const int a = idx / 36, e = idx - 36 * a;
     A[(6 * a + e / 6) * LD + 6 * a + e % 6] = Cz.D1raw[36 * (size_t)(a0 + a) + e];
   }
-  __syncthreads();
-  // pose-pose edges between different aggregates of the group (a handful): B_i' Hoff B_j and its transpose
-  for (int i = 5 * a0 + tid; i < min(G.Np, 5 * a1); i += GRP_THREADS) {
-    const int ai = i / 5 - a0;
-    const double* B = Cz.B1mat + 36 * (size_t)i;
+  // ... and appends them to the list at a position fixed by the pose order (deterministic)
+  if (tid < np && my_n > 0) {   // (more than GRP_MAXPP such edges per group: the rest is left out of the preconditioner)
+    int o = 0;
+    for (int k = 0; k < tid; ++k) o += ppcnt[k];
+    const int i = 5 * a0 + tid, ai = tid / 5;
     for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
       const int code = G.pose_pp_idx[kk];
       if (code & 1) continue;
-      const int e = code >> 1, j = G.pp[e].j;
-      const int aj = j / 5 - a0;
+      const int e = code >> 1, j = G.pp[e].j, aj = j / 5 - a0;
       if (aj == ai || aj < 0 || aj >= na) continue;
-      const double* Bj = Cz.B1mat + 36 * (size_t)j;
-      const double* Ho = G.Hoff + 36 * (size_t)e;
-      double HB[36];
-      for (int r = 0; r < 6; ++r)
-        for (int c = 0; c < 6; ++c) {
-          double t = 0.0;
-          for (int k = 0; k < 6; ++k) t += Ho[6 * r + k] * Bj[6 * k + c];
-          HB[6 * r + c] = t;
-        }
-      for (int r = 0; r < 6; ++r)
-        for (int c = 0; c < 6; ++c) {
-          double t = 0.0;
-          for (int k = 0; k < 6; ++k) t += B[6 * k + r] * HB[6 * k + c];
-          atomicAdd(&A[(6 * ai + r) * LD + 6 * aj + c], t);
-          atomicAdd(&A[(6 * aj + c) * LD + 6 * ai + r], t);
-        }
+      if (o < GRP_MAXPP) {
+        pplist[3 * o] = e;
+        pplist[3 * o + 1] = i;
+        pplist[3 * o + 2] = j;
+      }
+      ++o;
     }
   }
+  if (tid == 0) {
+    int o = 0;
+    for (int k = 0; k < np; ++k) o += ppcnt[k];
+    ppcnt[5 * GRP_MAXA] = min(o, GRP_MAXPP);
+  }
   __syncthreads();
-  // landmarks seen from several aggregates of the group: every thread owns fixed entries (i, j) in blocks that couple
-  // two different aggregates and walks the staged segments: A[i][j] -= sum_l (G_x' W_l G_y)[i%6][j%6]
-  for (int idx = tid; idx < n * n; idx += GRP_THREADS) {
-    const int i = idx / n, j = idx - n * i;
-    const int ai = i / 6, aj = j / 6, ri = i - 6 * ai, cj = j - 6 * aj;
-    if (ai == aj) continue;   // the diagonal blocks already hold their landmark terms (D1raw)
-    double t = 0.0;
-    for (int sg = 0; sg < nseg; ++sg) {
-      const int x = segpos[GRP_MAXA * sg + ai], y = segpos[GRP_MAXA * sg + aj];
-      if (x < 0 || y < 0) continue;
-      const double* Gx = gdyn + 18 * x;
-      const double* Gy = gdyn + 18 * y;
-      const double* Wu = Wsh + 6 * sg;
-      const double w0 = Wu[0] * Gy[cj] + Wu[1] * Gy[6 + cj] + Wu[2] * Gy[12 + cj];
-      const double w1 = Wu[1] * Gy[cj] + Wu[3] * Gy[6 + cj] + Wu[4] * Gy[12 + cj];
-      const double w2 = Wu[2] * Gy[cj] + Wu[4] * Gy[6 + cj] + Wu[5] * Gy[12 + cj];
-      t += Gx[ri] * w0 + Gx[6 + ri] * w1 + Gx[12 + ri] * w2;
+  for (int sg = tid; sg < nseg; sg += GRP_THREADS) {
+    unsigned m = 0;
+    for (int k = 0; k < GRP_MAXA; ++k)
+      if (segpos[GRP_MAXA * sg + k] >= 0) m |= 1u << k;
+    segmask[sg] = (unsigned char)m;
+  }
+  // B_i' Hoff B_j and its transpose: 36 threads per list item; all items of one aggregate pair go to the same
+  // slice in list order, so the sums are deterministic and need no atomics
+  {
+    const int npp = ppcnt[5 * GRP_MAXA];
+    const int sl = tid / 36, ent = tid - 36 * sl, r = ent / 6, c = ent - 6 * r;
+    if (sl < 7)
+      for (int it = 0; it < npp; ++it) {
+        const int e = pplist[3 * it], i = pplist[3 * it + 1], j = pplist[3 * it + 2];
+        const int ai = i / 5 - a0, aj = j / 5 - a0;
+        const int lo = min(ai, aj), hi = max(ai, aj);
+        if ((lo * GRP_MAXA + hi) % 7 != sl) continue;
+        // thread (r, c) owns entry (r, c) of block (lo, hi): (B_i' Ho B_j)[r][c], transposed when the edge runs hi -> lo
+        const int rr = ai < aj ? r : c, cc = ai < aj ? c : r;
+        const double* B = Cz.B1mat + 36 * (size_t)i;
+        const double* Bj = Cz.B1mat + 36 * (size_t)j;
+        const double* Ho = G.Hoff + 36 * (size_t)e;
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double hb = 0.0;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) hb += Ho[6 * k + m] * Bj[6 * m + cc];
+          t += B[6 * k + rr] * hb;
+        }
+        A[(6 * lo + r) * LD + 6 * hi + c] += t;
+        A[(6 * hi + c) * LD + 6 * lo + r] += t;
+      }
+  }
+  __syncthreads();
+  // landmarks seen from several aggregates of the group: every thread owns fixed entries of the blocks (ai < aj)
+  // and walks the staged segments: A[i][j] -= sum_l (G_x' W_l G_y)[i%6][j%6], mirrored into (j, i)
+  {
+    const int npair = na * (na - 1) / 2;
+    for (int idx = tid; idx < 36 * npair; idx += GRP_THREADS) {
+      const int pr = idx / 36, ent = idx - 36 * pr, ri = ent / 6, cj = ent - 6 * ri;
+      int aj = 1, ai = pr;
+      while (ai >= aj) {
+        ai -= aj;
+        ++aj;
+      }
+      const unsigned need = (1u << ai) | (1u << aj);
+      double t = 0.0;
+      for (int sg = 0; sg < nseg; ++sg) {
+        if ((segmask[sg] & need) != need) continue;
+        const int x = segpos[GRP_MAXA * sg + ai], y = segpos[GRP_MAXA * sg + aj];
+        const double* Gx = gdyn + 18 * x;
+        const double* Gy = gdyn + 18 * y;
+        const double* Wu = Wsh + 6 * sg;
+        const double w0 = Wu[0] * Gy[cj] + Wu[1] * Gy[6 + cj] + Wu[2] * Gy[12 + cj];
+        const double w1 = Wu[1] * Gy[cj] + Wu[3] * Gy[6 + cj] + Wu[4] * Gy[12 + cj];
+        const double w2 = Wu[2] * Gy[cj] + Wu[4] * Gy[6 + cj] + Wu[5] * Gy[12 + cj];
+        t += Gx[ri] * w0 + Gx[6 + ri] * w1 + Gx[12 + ri] * w2;
+      }
+      A[(6 * ai + ri) * LD + 6 * aj + cj] -= t;
+      A[(6 * aj + cj) * LD + 6 * ai + ri] -= t;
     }
-    A[i * LD + j] -= t;
   }
   __syncthreads();
   // aggregates without a free pose have a zero block: decouple them with an identity
@@ -785,42 +877,62 @@ __global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDe
       for (int k = 0; k < 6; ++k) A[(6 * tid + k) * LD + 6 * tid + k] = 1.0;
   }
   __syncthreads();
-  // in-place Gauss-Jordan inverse, all entries updated in parallel from saved copies of pivot row and column
+  // in-place Gauss-Jordan inverse in registers
+  const int ti = tid >> 4, tj = tid & 15;
+  double v[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int i = ti + 16 * a, j = tj + 16 * b;
+      v[a][b] = (i < n && j < n) ? A[i * LD + j] : 0.0;
+    }
+  bool fail = false;
   for (int k = 0; k < n; ++k) {
-    const double pk = A[k * LD + k];
+    const int p = k & 1, ka = k >> 4, kr = k & 15;
+    if (ti == kr) {
+#pragma unroll
+      for (int b = 0; b < 3; ++b) rowk[p][tj + 16 * b] = ka == 0 ? v[0][b] : (ka == 1 ? v[1][b] : v[2][b]);
+    }
+    if (tj == kr) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) colk[p][ti + 16 * a] = ka == 0 ? v[a][0] : (ka == 1 ? v[a][1] : v[a][2]);
+    }
+    __syncthreads();
+    const double pk = rowk[p][k];
     if (!(pk > 0.0) || !isfinite(pk)) {   // uniform: every thread reads the same pivot
-      if (tid == 0) s_fail = 1;
+      fail = true;
       break;
     }
-    const double ip = 1.0 / pk;
-    if (tid < n) {
-      colk[tid] = A[tid * LD + k];
-      rowk[tid] = A[k * LD + tid];
-    }
-    __syncthreads();
-    for (int i = tid >> 4; i < n; i += 16)
-      for (int j = tid & 15; j < n; j += 16) {
-        double v;
-        if (i == k)
-          v = (j == k) ? ip : rowk[j] * ip;
-        else if (j == k)
-          v = -colk[i] * ip;
-        else
-          v = A[i * LD + j] - colk[i] * rowk[j] * ip;
-        A[i * LD + j] = v;
+    const double ip = grp_rcp(pk);
+    double ci[3], rj[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) ci[a] = colk[p][ti + 16 * a] * ip;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) rj[b] = rowk[p][tj + 16 * b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const bool ik = (ti + 16 * a) == k, jk = (tj + 16 * b) == k;
+        const double upd = v[a][b] - ci[a] * rj[b];
+        v[a][b] = ik ? (jk ? ip : rj[b] * ip) : (jk ? -ci[a] : upd);
       }
-    __syncthreads();
   }
   __syncthreads();
-  const bool fail = s_fail != 0;
-  for (int idx = tid; idx < GRP_PACK; idx += GRP_THREADS) {
-    // idx -> (r, c) with c <= r
-    int r = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-    while (r * (r + 1) / 2 > idx) --r;
-    while ((r + 1) * (r + 2) / 2 <= idx) ++r;
-    const int c = idx - r * (r + 1) / 2;
-    out[idx] = (fail || r >= n) ? 0.0 : 0.5 * (A[r * LD + c] + A[c * LD + r]);
-  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) A[(ti + 16 * a) * LD + tj + 16 * b] = v[a][b];
+  __syncthreads();
+  // packed lower triangle, symmetrised
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int r = ti + 16 * a, c = tj + 16 * b;
+      if (c <= r) out[r * (r + 1) / 2 + c] = (fail || r >= n) ? 0.0 : 0.5 * (A[r * LD + c] + A[c * LD + r]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

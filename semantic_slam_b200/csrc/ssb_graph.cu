@@ -89,10 +89,12 @@ struct DBuf {
   size_t cap = 0;
   int ensure(size_t n) {
     if (n <= cap && p) return SSB_OK;
+    // grow with slack: a graph that gains a keyframe per tick must not reallocate every buffer every tick
+    size_t want = std::max<size_t>(n, 1);
+    if (p) want = std::max(want, cap + cap / 2);
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
-    size_t want = std::max<size_t>(n, 1);
     cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
     if (e != cudaSuccess) {
       set_error("cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
@@ -103,6 +105,31 @@ struct DBuf {
   }
   ~DBuf() {
     if (p) cudaFree(p);
+  }
+};
+
+// page-locked host staging buffer (tables built in place, then uploaded by a truly asynchronous copy)
+template <class T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap && p) return SSB_OK;
+    size_t want = std::max<size_t>(n, 1);
+    if (p) want = std::max(want, cap + cap / 2);
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      set_error("cudaHostAlloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+      return SSB_ERR_CUDA;
+    }
+    cap = want;
+    return SSB_OK;
+  }
+  ~PinnedBuf() {
+    if (p) cudaFreeHost(p);
   }
 };
 
@@ -169,6 +196,8 @@ struct ssb_graph {
   DBuf<unsigned char> d_pose_fixed, d_lm_fixed, d_lm_kind;
   DBuf<double> d_pl_zd;
   DBuf<PLEdge> d_pl;
+  PinnedBuf<PLEdge> h_plL;   // L-ordered pose-landmark edges, built in place by prepare()
+  PinnedBuf<double> h_zdL;
   DBuf<PPEdge> d_pp;
   DBuf<int> d_lm_rowptr, d_pose_pl_rowptr, d_pose_pl_idx, d_pose_pp_rowptr, d_pose_pp_idx, d_plP_lm;
   DBuf<double> d_Hpp, d_bp, d_Hoff, d_Hll, d_bl, d_HplL, d_HplP, d_HllInv, d_Dinv, d_g;
@@ -622,33 +651,61 @@ static int prepare(ssb_graph* g) {
     std::vector<int> lm_rowptr(Nl + 1, 0);
     for (auto& e : g->pl) lm_rowptr[e.l + 1]++;
     for (int l = 0; l < Nl; ++l) lm_rowptr[l + 1] += lm_rowptr[l];
-    std::vector<PLEdge> plL(std::max(El, 1));
-    std::vector<double> zdL(std::max(El, 1), 0.0);
+    SSB_TRY(g->h_plL.ensure(std::max(El, 1)));
+    SSB_TRY(g->h_zdL.ensure(std::max(El, 1)));
+    SSB_TRY(g->d_pl.ensure(El));
+    if (g->n_plane_vertices) SSB_TRY(g->d_pl_zd.ensure(El));
+    PLEdge* plL = g->h_plL.p;
+    double* zdL = g->h_zdL.p;
     g->plL_of_edge.assign(El, 0);
     {
-      // L-order: by landmark, then by pose index, then by creation order — two stable counting-sort passes
-      // (least significant key first)
-      std::vector<int> ord(El), tmp(El);
+      // L-order: by landmark, then by pose index, then by creation order.  Edges normally arrive with non-decreasing
+      // pose index per landmark (keyframes are created in time order): one stable counting-sort pass by landmark
+      // is enough then; otherwise two passes (least significant key first)
+      std::vector<int> ord(El), tmp;
+      bool pose_sorted = true;
       {
+        std::vector<int> lastp(std::max(Nl, 1), -1);
+        for (int k = 0; k < El; ++k) {
+          const PLEdge& e = g->pl[k];
+          if (e.p < lastp[e.l]) {
+            pose_sorted = false;
+            break;
+          }
+          lastp[e.l] = e.p;
+        }
+      }
+      std::vector<int> cntl(lm_rowptr.begin(), lm_rowptr.end() - 1);
+      if (pose_sorted) {
+        for (int k = 0; k < El; ++k) ord[cntl[g->pl[k].l]++] = k;
+      } else {
+        tmp.resize(El);
         std::vector<int> cntp(Np + 1, 0);
         for (int k = 0; k < El; ++k) cntp[g->pl[k].p + 1]++;
         for (int i = 0; i < Np; ++i) cntp[i + 1] += cntp[i];
         for (int k = 0; k < El; ++k) tmp[cntp[g->pl[k].p]++] = k;
-        std::vector<int> cntl(lm_rowptr.begin(), lm_rowptr.end() - 1);
         for (int q = 0; q < El; ++q) ord[cntl[g->pl[tmp[q]].l]++] = tmp[q];
       }
+      const bool planes = g->n_plane_vertices != 0;
       for (int pos = 0; pos < El; ++pos) {
         plL[pos] = g->pl[ord[pos]];
-        zdL[pos] = g->pl_zd[ord[pos]];
+        if (planes) zdL[pos] = g->pl_zd[ord[pos]];
         g->plL_of_edge[ord[pos]] = pos;
       }
     }
+    // the big table goes out now (page-locked source: the copy overlaps the rest of the host work)
+    if (El) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pl.p, plL, (size_t)El * sizeof(PLEdge), cudaMemcpyHostToDevice, g->stream));
+    if (El && g->n_plane_vertices)
+      SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pl_zd.p, zdL, (size_t)El * sizeof(double), cudaMemcpyHostToDevice, g->stream));
     tick("hessian index + L-order sort");
     // coarse aggregates: one per persistent CTA, contiguous pose ranges of C poses (multiple of 5)
     const int nblk = g->pcg_grid;
     int Cc = (Np + nblk - 1) / nblk;
     Cc = std::max(5, ((Cc + 4) / 5) * 5);
     std::vector<int> run_lm, run_group, run_e0, lm_run_rowptr(Nl + 1, 0);
+    run_lm.reserve(El / 4 + 16);
+    run_group.reserve(El / 4 + 16);
+    run_e0.reserve(El / 4 + 17);
     for (int l = 0; l < Nl; ++l) {
       lm_run_rowptr[l] = (int)run_lm.size();
       int prev = -1;
@@ -675,6 +732,9 @@ static int prepare(ssb_graph* g) {
     // the same run structure for the middle level: (landmark, 5-pose aggregate) runs, grouped by aggregate
     const int n_agg = (Np + 4) / 5;
     std::vector<int> run1_lm, run1_agg, run1_e0, agg_run_rowptr(n_agg + 1, 0);
+    run1_lm.reserve(El / 2 + 16);
+    run1_agg.reserve(El / 2 + 16);
+    run1_e0.reserve(El / 2 + 17);
     for (int l = 0; l < Nl; ++l) {
       int prev = -1;
       for (int e = lm_rowptr[l]; e < lm_rowptr[l + 1]; ++e) {
@@ -849,6 +909,9 @@ static int prepare(ssb_graph* g) {
       if (ok) {
         std::vector<int> lm_stamp(std::max(Nl, 1), -1), lm_slot(std::max(Nl, 1), 0), e_stamp(std::max(Epp, 1), -1),
             e_slot(std::max(Epp, 1), 0);
+        ulm.reserve(El / 2 + 16);
+        upp.reserve(Epp + nblk + 16);
+        ext.reserve(4 * (size_t)nblk + 16);
         for (int b = 0; b < nblk && ok; ++b) {
           const int q0 = std::min(Np, b * Cc), q1 = std::min(Np, q0 + Cc);
           const size_t u0 = ulm.size(), p0e = upp.size(), x0 = ext.size();
@@ -1062,9 +1125,7 @@ static int prepare(ssb_graph* g) {
     if (Nl) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_fixed.p, lfix.data(), Nl, cudaMemcpyHostToDevice, s));
     if (g->n_plane_vertices) {
       SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_kind.p, g->lm_kind.data(), Nl, cudaMemcpyHostToDevice, s));
-      if (El) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pl_zd.p, zdL.data(), (size_t)El * sizeof(double), cudaMemcpyHostToDevice, s));
     }
-    if (El) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pl.p, plL.data(), (size_t)El * sizeof(PLEdge), cudaMemcpyHostToDevice, s));
     if (Epp) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pp.p, g->pp.data(), (size_t)Epp * sizeof(PPEdge), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_rowptr.p, lm_rowptr.data(), (Nl + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pl_rowptr.p, ppl_rowptr.data(), (Np + 1) * sizeof(int), cudaMemcpyHostToDevice, s));

@@ -352,3 +352,37 @@ def test_cell_tag_wraparound():
     P, X = g.get_all(spec.n_poses, spec.n_landmarks)
     Pr, Xr = ref.get_all(spec.n_poses, spec.n_landmarks)
     assert np.array_equal(P, Pr) and np.array_equal(X, Xr)
+
+
+def test_pose_pose_loop_closures_inside_groups():
+    """Pose-pose edges other than odometry (never built by the reference, but legal through the ABI): forward,
+    backward (later -> earlier keyframe) and duplicate edges that couple different 5-pose aggregates of one
+    preconditioner group.  The group matrices must stay symmetric positive definite and the solve must agree with
+    the plain block-Jacobi PCG and with the oracle."""
+    spec = synth.make_graph(3000, 600, seed=91)
+    pose_vid = np.flatnonzero(spec.vkind == 0)
+    rng = np.random.default_rng(5)
+    extra = []
+    for i in range(5, 2960, 37):
+        for a, b in ((i, i + 7), (i + 12, i + 3), (i, i + 7)):
+            Z = synth.T_mul(synth.T_inv(spec.gt_pose[a]), spec.gt_pose[b])
+            Z = synth.T_mul(Z, synth.T_make(synth.rotvec_to_R(rng.normal(0, 0.005, 3)), rng.normal(0, 0.01, 3)))
+            extra.append((int(pose_vid[a]), int(pose_vid[b]), Z))
+    def build(b):
+        synth.load_graph(b, spec)
+        for a, c, Z in extra:
+            b.add_se3_edge(a, c, Z, spec.einfo6)
+        return b
+    n = 6 * (spec.n_poses - 1) + 3 * spec.n_landmarks
+    k0, x0 = build(GraphSLAM(pcg_tol=1e-12, preconditioner=0)).solve_once(1e-3, n)
+    k3, x3 = build(GraphSLAM(pcg_tol=1e-12, preconditioner=3)).solve_once(1e-3, n)
+    assert np.abs(x0 - x3).max() <= 1e-7 * max(1.0, np.abs(x0).max())
+    assert 2 * k3 < k0, (k0, k3)
+    g = build(GraphSLAM(preconditioner=3))
+    o = build(oracle.OracleGraphSLAM())
+    assert g.optimize(5) and o.optimize(5)
+    P, X = g.get_all(spec.n_poses, spec.n_landmarks)
+    Po, Xo = o.get_all(spec.n_poses, spec.n_landmarks)
+    assert np.abs(P - Po).max() <= 1e-5 * max(1.0, np.abs(Po).max())
+    assert np.abs(X - Xo).max() <= 1e-5 * max(1.0, np.abs(Xo).max())
+    assert abs(g.stats["chi2_final"] - o.history[-1, 1]) <= 1e-8 * o.history[-1, 1]

@@ -416,9 +416,7 @@ __device__ __forceinline__ double grid_bar_sum(BarSlot* slots, unsigned& epoch, 
     }
     red_release_add_u32(counter, 1u);  // release: orders this CTA's earlier writes (bar.sync-cumulative)
     const unsigned target = epoch * gridDim.x;
-    unsigned spins = 0;   // watchdog: trap instead of hanging the GPU if a CTA never arrives
     while (ld_acquire_u32(counter) < target) {
-      if (++spins > (1u << 26)) __trap();
     }
   }
   __syncthreads();

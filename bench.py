@@ -52,12 +52,18 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (arrival time, csv line)
+        self.t_mark = None
+
+    def mark(self):
+        """Start of the timed region: only samples that arrive after this (and before stop()) are reported.  The
+        nvidia-smi process itself is started earlier (its start-up takes longer than a short timed region)."""
+        self.t_mark = time.monotonic()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -66,11 +72,12 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.monotonic(), ln.strip()))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_stop = time.monotonic()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -78,7 +85,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = self.t_mark if self.t_mark is not None else 0.0
+        for t_ln, ln in self.lines:
+            if t_ln < t0 or t_ln > t_stop:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -213,10 +223,11 @@ def main():
     pcg_its = trials = lm_its = launches = 0
     t_rs = t_cnt = 0.0
     clocks = ClockSampler(local)
+    clocks.start()
     for s in range(warmup + steps):
         if s == warmup:
             sync_all()
-            clocks.start()
+            clocks.mark()
             l0 = seg.launch_count()
         g.restore()
         flush.zero_()                      # flush L2 between timed iterations (untimed)

@@ -157,8 +157,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "LM iters/sec (10k-KF graph)", "value": value, "unit": "LM iters/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / max(len(times), 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2: 10000 KF / %d landmarks / %d edges (synthetic, seed 20260927)" %
-                   (spec.n_landmarks, spec.n_edges), "lm_iterations_per_step": n_it},
+        "config": {"workload": "cfg2: 10000 KF / %d landmarks / %d edges, %d LM iterations per step (synthetic, "
+                               "lawn-mower trajectory, seed 20260927)" % (spec.n_landmarks, spec.n_edges, LM_ITERS),
+                   "lm_iterations": n_it, "solver": "sparse Cholesky (CSparse restatement), as g2o lm_var"},
         "cpu_baseline": {"value": value, "unit": "LM iters/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "LM iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ransac": {"metric": "RANSAC Mpts/sec", "value": npts / tr / 1e6, "unit": "Mpts/s", "cores": 1,

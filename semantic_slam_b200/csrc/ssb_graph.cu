@@ -186,7 +186,10 @@ struct ssb_graph {
   int pcg_grid = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // auxiliary stream for independent small kernels (forked from / joined to `stream`)
-  cudaEvent_t ev_fork = nullptr, ev_mid = nullptr, ev_join = nullptr;
+  cudaStream_t stream3 = nullptr;   // the coarse-matrix inversion of a damped trial (k_coarse_invert)
+  cudaEvent_t ev_fork = nullptr, ev_mid = nullptr, ev_join = nullptr, ev_join3 = nullptr;
+  bool coarse_ready = false;        // k_coarse_invert ran for the system / lambda of the coming k_pcg_flow launches
+  size_t cinv_smem = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ev_pool;  // pairs around every k_pcg launch of the current optimize
   size_t ev_used = 0;
@@ -202,7 +205,7 @@ struct ssb_graph {
   DBuf<int> d_lm_rowptr, d_pose_pl_rowptr, d_pose_pl_idx, d_pose_pp_rowptr, d_pose_pp_idx, d_plP_lm;
   DBuf<double> d_Hpp, d_bp, d_Hoff, d_Hll, d_bl, d_HplL, d_HplP, d_HllInv, d_Dinv, d_g;
   DBuf<double> d_x, d_r, d_z, d_p0, d_p1, d_q, d_v, d_dl, d_part, d_scalars, d_tmp;
-  DBuf<int> d_iscalars;
+  DBuf<int> d_iscalars, d_ainv_ok;
   // coarse level
   DBuf<double> d_Bmat, d_Grun, d_panel, d_B1mat, d_D1inv, d_ainv;
   bool ainv_valid = false;   // d_ainv holds the rows of a previously inverted coarse matrix
@@ -317,6 +320,8 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
       cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&g->ev_mid, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g->stream3, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g->ev_join3, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess ||
       cudaMallocHost((void**)&g->h_scalars, 32 * sizeof(double)) != cudaSuccess ||
       cudaMallocHost((void**)&g->h_iscalars, 4 * sizeof(int)) != cudaSuccess ||
@@ -355,6 +360,9 @@ void ssb_graph_destroy(ssb_graph* g) {
   if (g->stream) cudaStreamSynchronize(g->stream);
   for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
   if (g->stream2) cudaStreamSynchronize(g->stream2);
+  if (g->stream3) cudaStreamSynchronize(g->stream3);
+  if (g->ev_join3) cudaEventDestroy(g->ev_join3);
+  if (g->stream3) cudaStreamDestroy(g->stream3);
   if (g->ev_fork) cudaEventDestroy(g->ev_fork);
   if (g->ev_mid) cudaEventDestroy(g->ev_mid);
   if (g->ev_join) cudaEventDestroy(g->ev_join);
@@ -868,6 +876,7 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_part.ensure(std::max<size_t>(3 * PART_STRIDE, nb_bs) + 4096));
     SSB_TRY(g->d_scalars.ensure(32));
     SSB_TRY(g->d_iscalars.ensure(4));
+    SSB_TRY(g->d_ainv_ok.ensure(1));
     SSB_TRY(g->d_tmp.ensure(128));
     const int ncoarse = 6 * nblk;
     {
@@ -1057,6 +1066,7 @@ static int prepare(ssb_graph* g) {
     }
     g->flow_seq = (unsigned)std::max(0, g->opts.reserved[3]);   // test hook: start close to the tag wrap-around
     g->ainv_valid = false;
+    g->coarse_ready = false;
     cudaStream_t s = g->stream;
     if (n_runs) {
       SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_run_lm.p, run_lm.data(), n_runs * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1118,6 +1128,7 @@ static int prepare(ssb_graph* g) {
       Cz.grp_seg_m = g->d_grp_seg_m.p;
       Cz.n_groups = n_groups;
       Cz.ainv_store = g->d_ainv.p;
+      Cz.ainv_ok = g->d_ainv_ok.p;
     }
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_scalars.p, 0, 32 * sizeof(double), s));
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_iscalars.p, 0, 4 * sizeof(int), s));
@@ -1247,7 +1258,11 @@ static int launch_linearize(ssb_graph* g) {
   g->have_system = true;
   return SSB_OK;
 }
-static int launch_prep(ssb_graph* g, double lambda) {
+// separate_coarse: invert the coarse matrix in k_coarse_invert (third stream) instead of inside k_pcg_flow.  Measured
+// on cfg2: the stand-alone kernel must leave registers for its neighbours (64 per thread) and takes 259 us against
+// 181 us in-kernel, which cancels the 57 us of overlap with k_sub_assemble -> k_grp_invert, so the LM loop keeps the
+// in-kernel inversion; the landmark marginals solve 3 systems per landmark with ONE matrix and reuse the stored rows.
+static int launch_prep(ssb_graph* g, double lambda, bool separate_coarse = false) {
   DevGraph& G = g->G;
   cudaStream_t s = g->stream, s2 = g->stream2;
   if (G.Nl) {
@@ -1255,9 +1270,26 @@ static int launch_prep(ssb_graph* g, double lambda) {
     g->launches++;
   }
   const bool fork = g->Cz.sub_enabled && g->comm_world == 1;
+  // the coarse matrix of this trial is assembled and inverted beside the other per-trial kernels (third stream)
+  const bool cinv = separate_coarse && fork && g->Cz.enabled && g->fast_ok && g->use_flow && g->opts.reserved[1] <= 1 && g->d_gj.p;
+  g->coarse_ready = false;
   if (fork) {
     SSB_CUDA_CHECK(cudaEventRecord(g->ev_fork, s));
     SSB_CUDA_CHECK(cudaStreamWaitEvent(s2, g->ev_fork, 0));
+  }
+  if (cinv) {
+    cudaStream_t s3 = g->stream3;
+    SSB_CUDA_CHECK(cudaStreamWaitEvent(s3, g->ev_fork, 0));
+    if (!g->cinv_smem) {
+      g->cinv_smem = ((size_t)6 * 6 * g->pcg_grid + (CINV_THREADS / 36) * 36) * sizeof(double);
+      SSB_CUDA_CHECK(cudaFuncSetAttribute(k_coarse_invert<148>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->cinv_smem));
+    }
+    // same tag family as the cells of the coming k_pcg_flow launch (flow_seq + 1): unique per launch
+    const unsigned tag = ((g->flow_seq + 1u) << 16) + 1u;
+    k_coarse_invert<148><<<g->pcg_grid, CINV_THREADS, g->cinv_smem, s3>>>(G, g->Cz, g->d_gj.p, tag, g->FT.gj_order, g->FT.gj_mask, lambda);
+    g->launches++;
+    SSB_CUDA_CHECK(cudaEventRecord(g->ev_join3, s3));
+    g->coarse_ready = true;
   }
   k_prep_poses<<<(G.Np + 63) / 64, 64, 0, fork ? s2 : s>>>(G, lambda);
   g->launches++;
@@ -1274,6 +1306,7 @@ static int launch_prep(ssb_graph* g, double lambda) {
     SSB_CUDA_CHECK(cudaEventRecord(g->ev_join, s2));
     SSB_CUDA_CHECK(cudaStreamWaitEvent(s, g->ev_join, 0));
   }
+  if (cinv) SSB_CUDA_CHECK(cudaStreamWaitEvent(s, g->ev_join3, 0));
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;
 }
@@ -1301,7 +1334,7 @@ static int launch_pcg(ssb_graph* g, double lambda) {
   {
     const int every = std::max(1, g->opts.reserved[1]);
     const bool reuse = g->Cz.enabled && g->ainv_valid && every > 1 && (g->solves_since_refresh % every) != 0;
-    g->Cz.reuse_inverse = reuse ? 1 : 0;
+    g->Cz.reuse_inverse = g->coarse_ready ? 2 : (reuse ? 1 : 0);
     if (!reuse) g->solves_since_refresh = 0;
     g->solves_since_refresh++;
     if (g->Cz.enabled) g->ainv_valid = true;
@@ -1809,7 +1842,7 @@ int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* o
   }
   SSB_TRY(prepare(g));
   if (!g->have_system) SSB_TRY(launch_linearize(g));  // else: the system built by the last optimize (g2o semantics)
-  SSB_TRY(launch_prep(g, 0.0));
+  SSB_TRY(launch_prep(g, 0.0, std::getenv("SSB_MARG_INKERNEL") == nullptr));   // env: A/B switch for measurements
   SSB_TRY(g->d_tmp.ensure((size_t)std::max(128, 9 * n)));
   const size_t ev_keep = g->ev_used;
   for (int k = 0; k < n; ++k) {

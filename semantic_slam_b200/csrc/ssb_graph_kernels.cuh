@@ -341,6 +341,7 @@ struct CoarseDev {
   int sub_enabled;
   int reuse_inverse;       // 1: skip assembly + Gauss-Jordan, reload the rows of A_c^-1 stored by an earlier solve
   double* ainv_store;      // [gridDim.x][6*nc] rows of A_c^-1 kept between solves
+  int* ainv_ok;            // [1] written by k_coarse_invert: every pivot block was positive definite
   double* B1mat;           // [Np][36] prolongation blocks about the 5-pose centroid
   double* D1inv;           // [ceil(Np/5)][36] inverse of P1' S P1 diagonal blocks (zero = level off for the aggregate)
   // (landmark, 5-pose aggregate) runs of the L-order edge table, built on the host like the per-CTA runs above

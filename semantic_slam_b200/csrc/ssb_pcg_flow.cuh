@@ -361,6 +361,33 @@ __device__ bool coarse_gj_flow(uint4* gj, unsigned tag, double* Arow, const int*
   return s_flag == 0;
 }
 
+// The coarse assembly + Gauss-Jordan as a kernel of its own (same device code as the prologue of k_pcg_flow): it
+// needs only the linearised system and (H_ll + lambda I)^-1, so the host runs it on a third stream next to
+// k_sub_assemble -> k_grp_invert and k_prep_poses; k_pcg_flow then starts from the stored rows
+// (Cz.reuse_inverse = 2).  Launched with NB CTAs that wait on each other's panels: like k_pcg_flow it relies on all
+// of them becoming resident, which holds because the kernels running beside it never wait on anything.
+#ifndef SSB_CINV_THREADS
+#define SSB_CINV_THREADS 512
+#endif
+#ifndef SSB_CINV_MINB
+#define SSB_CINV_MINB 2   // 512 threads x <= 64 registers: must leave room for the kernels it runs beside
+#endif
+constexpr int CINV_THREADS = SSB_CINV_THREADS;
+template <int NB>
+__global__ void __launch_bounds__(CINV_THREADS, SSB_CINV_MINB)
+    k_coarse_invert(DevGraph G, CoarseDev Cz, uint4* gj, unsigned tag, const int* order, const unsigned* mask, double lambda) {
+  extern __shared__ __align__(16) double dsm[];
+  constexpr int nc = 6 * NB;
+  double* Arow = dsm;             // [6][nc]
+  double* red = Arow + 6 * nc;    // [CINV_THREADS / 36][36]
+  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np, p0 + Cz.C);
+  coarse_assemble<CINV_THREADS>(G, Cz, lambda, Arow, red, p0, p1);
+  const bool ok = coarse_gj_flow<CINV_THREADS, NB>(gj, tag, Arow, order, mask);
+  if (ok)
+    for (int k = threadIdx.x; k < 6 * nc; k += CINV_THREADS) Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k] = Arow[k];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *Cz.ainv_ok = ok ? 1 : 0;
+}
+
 // NB = gridDim.x as a compile-time constant (148 = one CTA per B200 SM): every shared-memory array then has a
 // constant address and the reduction / coarse loops unroll.
 template <int NB>
@@ -417,8 +444,10 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   bool use_coarse = false;
   if (coarse) {
     if (Cz.reuse_inverse) {
-      for (int k = threadIdx.x; k < 6 * nc; k += PCGF_THREADS) Arow[k] = Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k];
-      use_coarse = true;
+      // 1: rows kept from an earlier solve (refresh policy); 2: rows written by k_coarse_invert for this solve
+      use_coarse = Cz.reuse_inverse == 1 || *Cz.ainv_ok != 0;   // uniform over the grid
+      if (use_coarse)
+        for (int k = threadIdx.x; k < 6 * nc; k += PCGF_THREADS) Arow[k] = Cz.ainv_store[(size_t)blockIdx.x * 6 * nc + k];
       __syncthreads();
     } else {
       coarse_assemble<PCGF_THREADS>(G, Cz, lambda, Arow, red, p0, p1);

@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(128) k_sub_basis(DevGraph G, CoarseDev Cz) {
     }
 }
 
-// per LM iteration: Grun1 of every (landmark, 5-pose aggregate) run.  One thread per run.
+// per LM iteration: Grun1 of every (landmark, 5-pose aggregate) run.  18 threads per run (one per entry of the 3x6 product).
 __global__ void __launch_bounds__(128) k_sub_runs(DevGraph G, CoarseDev Cz) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = t / 18, q = t - 18 * r;

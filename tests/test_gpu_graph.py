@@ -386,3 +386,35 @@ def test_pose_pose_loop_closures_inside_groups():
     assert np.abs(P - Po).max() <= 1e-5 * max(1.0, np.abs(Po).max())
     assert np.abs(X - Xo).max() <= 1e-5 * max(1.0, np.abs(Xo).max())
     assert abs(g.stats["chi2_final"] - o.history[-1, 1]) <= 1e-8 * o.history[-1, 1]
+
+
+def test_edges_added_out_of_order():
+    """prepare() sorts the pose-landmark edges by (landmark, pose, creation order); when the edges do not arrive
+    pose-ordered per landmark it needs the two-pass counting sort.  Shuffled insertion must give the oracle's
+    result for the same insertion order (the edge order only changes summation order)."""
+    spec = synth.make_graph(600, 120, seed=23)
+    perm = np.random.default_rng(3).permutation(spec.n_edges)
+    def build(b):
+        ids = np.zeros(spec.vkind.size, dtype=np.int64)
+        for v in range(spec.vkind.size):
+            ids[v] = b.add_se3_node(spec.vpose[v]) if spec.vkind[v] == 0 else b.add_point_xyz_node(spec.vxyz[v])
+        for e in perm:
+            if spec.ekind[e] == 0:
+                b.add_se3_edge(int(ids[spec.evi[e]]), int(ids[spec.evj[e]]), spec.eZ[e], spec.einfo6)
+            else:
+                b.add_se3_point_xyz_edge(int(ids[spec.evi[e]]), int(ids[spec.evj[e]]), spec.ez[e], spec.einfo3)
+        return b
+    g = build(GraphSLAM(preconditioner=3))
+    o = build(oracle.OracleGraphSLAM())
+    assert g.optimize(6) and o.optimize(6)
+    P, X = g.get_all(spec.n_poses, spec.n_landmarks)
+    Po, Xo = o.get_all(spec.n_poses, spec.n_landmarks)
+    assert np.abs(P - Po).max() <= 1e-5 * max(1.0, np.abs(Po).max())
+    assert np.abs(X - Xo).max() <= 1e-5 * max(1.0, np.abs(Xo).max())
+    assert abs(g.stats["chi2_final"] - o.history[-1, 1]) <= 1e-8 * o.history[-1, 1]
+    # and the same graph in creation order lands on the same optimum
+    g2 = GraphSLAM(preconditioner=3)
+    synth.load_graph(g2, spec)
+    assert g2.optimize(6)
+    P2, X2 = g2.get_all(spec.n_poses, spec.n_landmarks)
+    assert np.abs(P - P2).max() <= 1e-7 * max(1.0, np.abs(P2).max())

@@ -58,7 +58,9 @@ __device__ __forceinline__ void lds_row6(uint32_t addr, double* out) {
 }
 
 #ifndef SSB_POLL_NS
-#define SSB_POLL_NS 20   // back-off between polls of a cell that has not arrived (measured: see DESIGN.md)
+#define SSB_POLL_NS 0    // back-off between polls of a cell that has not arrived.  Measured on cfg2 with the coalesced
+                         // cell layout (A/B on one box, solve time per 20 LM iterations): 0 ns 33.1 ms, 8 and 20 ns
+                         // 34.2 ms, 40 ns 39.9 ms, 100 ns +20 % -> no back-off
 #endif
 // Debug watchdog (build with EXTRA=-DSSB_WATCHDOG): a cell that has not arrived after this many polls (>= 10 s)
 // means a producer died; trap instead of hanging (the launch then fails with a sticky error).  Off by default: the
@@ -72,7 +74,9 @@ __device__ __forceinline__ double cell_wait(const uint4* p, uint4 c, unsigned ta
   unsigned spins = 0;
 #endif
   while (!cell_ok(c, tag)) {
+#if SSB_POLL_NS > 0
     __nanosleep(SSB_POLL_NS);
+#endif
     c = ld_cell(p);
 #ifdef SSB_WATCHDOG
     if (++spins > SSB_SPIN_LIMIT) __trap();
@@ -96,7 +100,9 @@ __device__ __forceinline__ void cells_wait(const uint4* base, const int (&off)[N
         unsigned spins = 0;
 #endif
         do {
+#if SSB_POLL_NS > 0
           __nanosleep(SSB_POLL_NS);
+#endif
           c[m] = ld_cell(base + off[m]);
 #ifdef SSB_WATCHDOG
           if (++spins > SSB_SPIN_LIMIT) __trap();

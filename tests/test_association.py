@@ -145,3 +145,33 @@ def test_planar_surface_classes_on_canonical_planes():
     assert [o[1] for o in out] == [0, 1]
     assert np.allclose(out[0][3], [0.0, -1.0, 0.0, 1.2]) and out[0][4][2] < -1.0     # flipped upwards; 1.2 m below the robot
     assert np.allclose(out[1][3], [-0.6, 0.0, -0.8, 3.5])                             # flipped towards the left
+
+
+def test_edge_cases_empty_frames_and_type_partitions():
+    """Empty detection lists, the first non-empty frame (data_association.h:75-96: every detection is mapped as a new
+    landmark without association, even two identical ones), a repeat of that frame (every detection matches; of two
+    landmarks at the same place the first wins, `distance < distance_min`), a (type, plane_type) class without
+    landmarks, and a long frame: product == oracle, and the bookkeeping is the reference's."""
+    a, o = DataAssociation(strict=True, **KITTI), OracleDataAssociation(strict=True, **KITTI)
+    rp = np.zeros(6, dtype=np.float32)
+    assert a.find_matches([], rp, 0.0) == [] and o.find_matches([], rp, 0.0) == []
+    assert a.num_landmarks() == o.num_landmarks() == 0
+    p = np.array([0.5, 0.2, 4.0], dtype=np.float32)
+    n = np.array([0, 0, 1, -4.0], dtype=np.float32)
+    dets = [(0, 0, p, n), (0, 0, p, n), (1, 0, p, n), (0, 1, p, n)]
+    A, O = a.find_matches(dets, rp, 0.0), o.find_matches(dets, rp, 0.0)
+    _same(A, O)
+    assert [x.is_new_landmark for x in A] == [True] * 4 and [x.id for x in A] == [0, 1, 2, 3]
+    assert a.num_landmarks() == o.num_landmarks() == 4
+    assert a.find_matches([], rp, 0.0) == [] and o.find_matches([], rp, 0.0) == []
+    A, O = a.find_matches(dets + [(1, 1, p, n)], rp, 0.0), o.find_matches(dets + [(1, 1, p, n)], rp, 0.0)
+    _same(A, O)
+    assert [x.is_new_landmark for x in A] == [False, False, False, False, True]   # class (1, 1) had no landmark yet
+    assert [x.id for x in A] == [0, 0, 2, 3, 4]
+    assert a.num_landmarks() == o.num_landmarks() == 5
+    # a long frame: 300 detections around 30 anchors
+    rng = np.random.default_rng(4)
+    anchors = rng.uniform(-20, 20, (30, 3)).astype(np.float32) + np.array([0, 0, 30], dtype=np.float32)
+    big = [(int(k % 2), int((k // 2) % 2), (anchors[k % 30] + rng.normal(0, 0.05, 3)).astype(np.float32), n) for k in range(300)]
+    _same(a.find_matches(big, rp, 0.1), o.find_matches(big, rp, 0.1))
+    assert a.num_landmarks() == o.num_landmarks()

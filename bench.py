@@ -224,7 +224,8 @@ def main():
     pcg_its = trials = lm_its = launches = 0
     t_rs = t_cnt = 0.0
     clocks = ClockSampler(local)
-    clocks.start()
+    if rank == 0:                          # one sampler per job: rank 0 prints the line, its GPU is the one reported
+        clocks.start()
     for s in range(warmup + steps):
         if s == warmup:
             sync_all()

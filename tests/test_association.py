@@ -175,3 +175,30 @@ def test_edge_cases_empty_frames_and_type_partitions():
     big = [(int(k % 2), int((k // 2) % 2), (anchors[k % 30] + rng.normal(0, 0.05, 3)).astype(np.float32), n) for k in range(300)]
     _same(a.find_matches(big, rp, 0.1), o.find_matches(big, rp, 0.1))
     assert a.num_landmarks() == o.num_landmarks()
+
+
+@pytest.mark.parametrize("tag,kw", [("eq", KITTI), ("maha", dict(use_maha_dist=True, maha_dist_thres=3.0, land_noise_low=0.4))])
+def test_golden_association_stream(tag, kw):
+    """tests/golden/assoc_stream_oracle.npz (scripts/make_golden.py): ids, new-landmark flags and float32 world poses
+    over a 40-frame stream; the product's host code and the oracle must both reproduce the fixture bit for bit."""
+    import os
+    from semantic_slam_b200 import synth
+    from semantic_slam_b200.semantic_graph_slam import matrix2vector
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "assoc_stream_oracle.npz"))
+    stream = synth.make_frame_stream(40, 10)
+    for cls in (DataAssociation, OracleDataAssociation):
+        a = cls(**kw)
+        ids, new, pose = [], [], []
+        est = {}
+        for k in range(40):
+            rp = matrix2vector(stream.gt_pose[k]).astype(np.float32)
+            for l in a.find_matches(stream.detections[k], rp, stream.cam_angle):
+                ids.append(l.id); new.append(bool(l.is_new_landmark)); pose.append(np.asarray(l.pose, dtype=np.float32))
+                if l.is_new_landmark:
+                    est[l.id] = np.asarray(l.pose, dtype=np.float32).copy()
+            for lid in range(a.num_landmarks()):
+                est[lid] = (est[lid] + np.float32(0.002) * (lid % 3)).astype(np.float32)
+                a.setLandmarkEstimate(lid, est[lid])
+        assert np.array_equal(np.array(ids, dtype=np.int32), gold[tag + "_ids"]), cls.__name__
+        assert np.array_equal(np.array(new, dtype=bool), gold[tag + "_new"]), cls.__name__
+        assert np.array_equal(np.array(pose, dtype=np.float32), gold[tag + "_pose"]), cls.__name__

@@ -38,6 +38,7 @@ typedef struct ssb_graph_opts {
                            3 = as 2 with the 5-pose aggregates of a CTA coupled exactly inside two groups (on-chip kernel) */
   int coarse_group;     /* poses per coarse aggregate when preconditioner == 1 (default 32)        */
   int reserved[4];      /* [0] = 1: force the streaming PCG kernel; [1] = n: re-invert the coarse matrix every n-th solve;
+                           [2]: internal (CTAs per rank of a sharded graph, set by ssb_graph_attach_local);
                            [3]: initial launch counter of the cell tags (test hook for the tag wrap-around) */
 } ssb_graph_opts;
 
@@ -148,14 +149,25 @@ int ssb_graph_edge_linearize(ssb_graph* g, int eid, double* err, double* Ji, dou
  * path; x is returned in hessian-index order (6 per SE3, 3 per XYZ vertex).  Returns PCG iterations. */
 int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len);
 
-/* multi-GPU (one process per GPU): attach an NCCL communicator built from `unique_id` (128 bytes from
- * ssb_comm_unique_id on rank 0, broadcast by the host).  The graph is then sharded by contiguous
- * keyframe range inside ssb_graph_optimize.  world == 1 detaches. */
+/* One graph sharded over several GPUs by contiguous keyframe range (the reference re-optimises the
+ * whole graph every tick, semantic_graph_slam.cpp:81, graph_slam.cpp:199-205, so graph length is the scaling axis).
+ * Every rank replays the same add_* calls on its own handle; ssb_graph_prepare / optimize / chi2 / snapshot /
+ * restore are then collective (every rank must call them in the same order).  Inside optimize each rank linearises,
+ * solves and updates its own keyframe range; the kernels write boundary data straight into the neighbours' memory
+ * over NVLink (csrc/ssb_peer.cuh) — the communicator is only used to hand over the memory handles.
+ *   ssb_graph_attach_comm  : one process per GPU; `unique_id` = 128 bytes from ssb_comm_unique_id on rank 0,
+ *                            broadcast by the host (NCCL, resolved at run time).  world == 1 detaches.
+ *   ssb_graph_attach_local : the ranks are host threads of this process (one handle each, same or different
+ *                            devices), paired through `group_key`.  cta_per_rank = 74 or 37 lets 2 or 4 shards share
+ *                            ONE GPU ("virtual shards": the whole protocol on a single-GPU box); 0 = a GPU per rank.
+ *   ssb_shard_ranges       : own keyframe range [out[0], out[1]) of `rank` (host-only).
+ *   ssb_graph_shard_info   : the plan for the current graph (host-only): out[0..1] own keyframe range, out[2] local
+ *                            keyframes (own + ghosts), out[3] owned / out[4] touched landmarks, out[5] local edges. */
 int ssb_comm_unique_id(unsigned char id_out[128]);
 int ssb_graph_attach_comm(ssb_graph* g, int rank, int world, const unsigned char unique_id[128]);
-/* contiguous keyframe range [out[0], out[1]) and landmark range [out[2], out[3]) owned by `rank`
- * (host-only, no GPU needed) */
+int ssb_graph_attach_local(ssb_graph* g, int rank, int world, const char* group_key, int cta_per_rank);
 int ssb_shard_ranges(int n_poses, int n_landmarks, int world, int rank, int out4[4]);
+int ssb_graph_shard_info(ssb_graph* g, int world, int rank, int out6[6]);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Path (2): planar_segmentation RANSAC plane fit on bbox-cropped depth clouds                  */

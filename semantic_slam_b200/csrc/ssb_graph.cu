@@ -11,15 +11,20 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <condition_variable>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
 
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include "../../include/ssb.h"
 #include "ssb_graph_kernels.cuh"
+#include "ssb_peer.cuh"
 #include "ssb_pcg_flow.cuh"
 
 // ---- NCCL, resolved at run time (the library the process already loaded — torch's — else libnccl.so.2).
@@ -87,8 +92,19 @@ template <class T>
 struct DBuf {
   T* p = nullptr;
   size_t cap = 0;
+  bool view = false;   // non-owning window into the peer arena of a sharded graph (ssb_peer.cuh)
+  void set_view(void* q, size_t n) {
+    if (p && !view) cudaFree(p);
+    p = (T*)q;
+    cap = n;
+    view = true;
+  }
   int ensure(size_t n) {
     if (n <= cap && p) return SSB_OK;
+    if (view) {
+      set_error("internal: peer-arena view too small (%zu > %zu elements)", n, cap);
+      return SSB_ERR_INVALID;
+    }
     // grow with slack: a graph that gains a keyframe per tick must not reallocate every buffer every tick
     size_t want = std::max<size_t>(n, 1);
     if (p) want = std::max(want, cap + cap / 2);
@@ -104,7 +120,7 @@ struct DBuf {
     return SSB_OK;
   }
   ~DBuf() {
-    if (p) cudaFree(p);
+    if (p && !view) cudaFree(p);
   }
 };
 
@@ -156,6 +172,70 @@ struct LLEdge {
   double info[9];
 };
 
+// ---- sharded graphs: host-side bookkeeping (device side: ssb_peer.cuh) -------------------------------------------
+// Who owns what.  Computed from the full host graph, which every rank holds, so every rank derives the SAME plan for
+// ALL ranks without talking to anybody: a rank knows under which local index each of its keyframes / landmark parts
+// lives on every neighbour and can aim its pushes there.
+struct RankLocal {
+  int ps = 0, pe = 0;                 // own keyframes: global pose indices [ps, pe)
+  std::vector<int> l2g_pose;          // local pose -> global pose: own first (global order), then ghosts (global order)
+  std::vector<int> l2g_lm;            // local landmark -> global: owned first, then the other touched ones
+  int n_owned_lm = 0;
+  std::vector<int> partbase;          // [local landmarks + 1] first v-cell part of every local landmark
+  std::vector<int> g2l_pose, g2l_lm;  // global -> local (-1: not present on this rank)
+};
+struct ShardPlan {
+  int world = 1, nb = 0, Np = 0, Nl = 0;
+  std::vector<RankLocal> R;
+  std::vector<int> lm_deg;            // [Nl] observations per landmark
+  std::vector<int> lm_owner;          // [Nl] rank that eliminates the landmark (owner of its first observer)
+};
+// byte offsets inside a rank's peer arena (a function of that rank's local sizes => computable by everybody)
+struct ArenaLayout {
+  size_t flags, red, cells, lines, x, z, v, slots, pose_full, lm_full, total;
+  size_t n_cells, n_ucells, n_lines, n_x, n_v;
+};
+struct PeerBlob {                     // what the ranks tell each other when an arena was (re)allocated
+  int pid, device;
+  void* ptr;
+  unsigned long long bytes, serial;
+  cudaIpcMemHandle_t handle;
+};
+struct MrCtx {                        // member of the INNER (shard) handle
+  int world = 1, rank = 0, nb = 0;
+  int n_own = 0, n_owned_lm = 0;
+  std::vector<int> sortkey;           // local pose -> global pose index: the L-order is by GLOBAL keyframe index, so
+                                      // every rank (and the unsharded run) sums a landmark's edges in the same order
+  std::vector<unsigned char> lm_owned;
+  // peer arena
+  unsigned char* arena = nullptr;
+  size_t arena_cap = 0;
+  unsigned long long arena_serial = 0;
+  std::vector<unsigned char*> retired;        // replaced arenas, freed once every peer has unmapped them
+  unsigned char* peer_base[SSB_MAX_WORLD] = {};
+  PeerBlob peer_blob[SSB_MAX_WORLD] = {};
+  bool peer_mapped[SSB_MAX_WORLD] = {};
+  ArenaLayout lay[SSB_MAX_WORLD] = {};
+  PeerDev P{};
+  PeerGather PG{};
+  unsigned long long epoch = 0;               // k_peer_exchange calls so far (identical on every rank)
+  // push tables (absolute pointers into the peers' arenas)
+  DBuf<int> d_upush_rowptr, d_vpush_rowptr;
+  DBuf<uint4*> d_upush_cell, d_vpush_cell;
+  DBuf<double*> d_upush_x;
+  FlowPeer FP{};
+  // chi2 over the edges this rank owns (a shared edge is counted once)
+  DBuf<PLEdge> d_pl_own;
+  DBuf<PPEdge> d_pp_own;
+  DBuf<double> d_zd_own;
+  int n_pl_own = 0, n_pp_own = 0;
+  DBuf<int> d_err;
+  double* h_red = nullptr;                    // pinned: [world][PEER_RED_N]
+  int* h_err = nullptr;                       // pinned
+  DBuf<int> d_own_l2g;                        // [n_own] and [n_owned_lm]: targets of the final estimate gather
+  DBuf<int> d_ownlm_l2g;
+};
+
 }  // namespace ssb
 
 using namespace ssb;
@@ -196,7 +276,7 @@ struct ssb_graph {
   // device buffers
   DBuf<Pose> d_pose, d_pose_bak, d_pose_snap;
   DBuf<double> d_lm, d_lm_bak, d_lm_snap;
-  DBuf<unsigned char> d_pose_fixed, d_lm_fixed, d_lm_kind;
+  DBuf<unsigned char> d_pose_fixed, d_lm_fixed, d_lm_kind, d_lm_owned, d_blob_stage;
   DBuf<double> d_pl_zd;
   DBuf<PLEdge> d_pl;
   PinnedBuf<PLEdge> h_plL;   // L-ordered pose-landmark edges, built in place by prepare()
@@ -234,13 +314,27 @@ struct ssb_graph {
   long long launches = 0;
   int comm_rank = 0, comm_world = 1;
   ssb_ncclComm_t comm = nullptr;
-  DBuf<double> d_mg;
-  double* h_mg = nullptr;  // pinned, 16 doubles
-  cudaGraphExec_t mg_graph = nullptr;  // two captured PCG iterations (4 kernels + 4 NCCL collectives each)
-  bool mg_graph_failed = true;   // CUDA-graph replay of the NCCL iteration measured 2x SLOWER than plain stream
-                                 // launches on 2 GPUs (NCCL 2.28 in-graph collectives); opt in with SSB_MG_GRAPH=1
+  // ---- one graph sharded over several ranks (ssb_peer.cuh, "sharded graphs" below) ----
+  int local_group = 0;           // 1: the ranks are host threads of this process (ssb_graph_attach_local)
+  std::string local_key;
+  ssb_graph* shard = nullptr;    // outer handle: this rank's local subgraph (own + ghost keyframes), a handle of its own
+  MrCtx* mr = nullptr;           // inner (shard) handle: what it needs to know about the other ranks
+  ShardPlan* plan = nullptr;     // outer handle: who owns what, identical on every rank
+  std::vector<Pose> snap_poses;  // outer handle: host copy of the estimates at ssb_graph_snapshot
+  std::vector<double> snap_lms;
 };
 
+// k_pcg_flow is instantiated for the grids it is launched with: 148 CTAs (one per B200 SM); a sharded graph whose ranks
+// are host threads sharing one GPU ("virtual shards", ssb_graph_attach_local) runs 74 or 37 CTAs per rank
+static void* flow_kernel(int grid, bool mr) {
+  if (!mr) return grid == 148 ? (void*)k_pcg_flow<148, false> : nullptr;
+  switch (grid) {
+    case 148: return (void*)k_pcg_flow<148, true>;
+    case 74: return (void*)k_pcg_flow<74, true>;
+    case 37: return (void*)k_pcg_flow<37, true>;
+    default: return nullptr;
+  }
+}
 static int check_vertex(const ssb_graph* g, int id, int kind) {
   return g && id >= 0 && id < (int)g->V.size() && g->V[id].kind == kind;
 }
@@ -324,18 +418,18 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
       cudaEventCreateWithFlags(&g->ev_join3, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess ||
       cudaMallocHost((void**)&g->h_scalars, 32 * sizeof(double)) != cudaSuccess ||
-      cudaMallocHost((void**)&g->h_iscalars, 4 * sizeof(int)) != cudaSuccess ||
-      cudaMallocHost((void**)&g->h_mg, 16 * sizeof(double)) != cudaSuccess) {
+      cudaMallocHost((void**)&g->h_iscalars, 4 * sizeof(int)) != cudaSuccess) {
     set_error("CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete g;
     return nullptr;
   }
   g->pcg_grid = std::min(g->num_sms, PCG_THREADS);  // one persistent CTA per SM
+  const bool shard_handle = g->opts.reserved[2] > 0;   // internal: a shard of a larger graph, reserved[2] = CTAs of this rank
+  if (shard_handle) g->pcg_grid = std::min(g->pcg_grid, g->opts.reserved[2]);
   g->pcg_smem = (size_t)(PCG_THREADS + 14 * 6 * g->pcg_grid + (PCG_THREADS / 36) * 36) * sizeof(double);
   g->allow_fast = g->opts.reserved[0] == 0;
-  g->use_flow = g->pcg_grid == 148;   // k_pcg_flow is instantiated for 148 CTAs (one per B200 SM)
+  g->use_flow = flow_kernel(g->pcg_grid, shard_handle) != nullptr;
   g->pcgw_smem = pcg_flow_smem_doubles(g->pcg_grid) * sizeof(double);
-  if (const char* e = std::getenv("SSB_MG_GRAPH")) g->mg_graph_failed = !(e[0] == '1');   // reserved[0] = 1 forces the generic (streaming) kernel
   int nb = 0;
   e = cudaFuncSetAttribute(k_pcg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_smem);
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg, PCG_THREADS, g->pcg_smem);
@@ -344,8 +438,11 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
     delete g;
     return nullptr;
   }
-  e = cudaFuncSetAttribute(k_pcg_flow<148>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcgw_smem);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_flow<148>, PCGF_THREADS, g->pcgw_smem);
+  if (g->use_flow) {
+    void* fk = flow_kernel(g->pcg_grid, shard_handle);
+    e = cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcgw_smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fk, PCGF_THREADS, g->pcgw_smem);
+  }
   if (e != cudaSuccess || nb < 1) {
     set_error("k_pcg_flow cannot be made resident (occupancy %d, %zu B smem): %s", nb, g->pcgw_smem, cudaGetErrorString(e));
     delete g;
@@ -357,6 +454,25 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
 void ssb_graph_destroy(ssb_graph* g) {
   if (!g) return;
   cudaSetDevice(g->device);
+  if (g->shard) {
+    ssb_graph_destroy(g->shard);
+    g->shard = nullptr;
+  }
+  delete g->plan;
+  g->plan = nullptr;
+  if (g->mr) {
+    MrCtx* mr = g->mr;
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    // windows into the arena are not owned by their DBufs
+    for (int r = 0; r < SSB_MAX_WORLD; ++r)
+      if (mr->peer_mapped[r] && mr->peer_blob[r].pid != (int)getpid()) cudaIpcCloseMemHandle(mr->peer_base[r]);
+    for (unsigned char* q : mr->retired) cudaFree(q);
+    if (mr->arena) cudaFree(mr->arena);
+    if (mr->h_red) cudaFreeHost(mr->h_red);
+    if (mr->h_err) cudaFreeHost(mr->h_err);
+    delete mr;
+    g->mr = nullptr;
+  }
   if (g->stream) cudaStreamSynchronize(g->stream);
   for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
   if (g->stream2) cudaStreamSynchronize(g->stream2);
@@ -371,8 +487,6 @@ void ssb_graph_destroy(ssb_graph* g) {
   if (g->ev1) cudaEventDestroy(g->ev1);
   if (g->h_scalars) cudaFreeHost(g->h_scalars);
   if (g->h_iscalars) cudaFreeHost(g->h_iscalars);
-  if (g->h_mg) cudaFreeHost(g->h_mg);
-  if (g->mg_graph) cudaGraphExecDestroy(g->mg_graph);
   if (g->comm && nccl_api().ok) nccl_api().CommDestroy(g->comm);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
@@ -634,6 +748,10 @@ static int prepare(ssb_graph* g) {
   }
   const int Np = (int)g->poses.size(), Nl = (int)(g->lms.size() / 4);
   const int El = (int)g->pl.size(), Epp = (int)g->pp.size();
+  // a shard of a larger graph: own keyframes [0, n_own), then ghosts; owned landmarks [0, n_owned_lm), then ghosts
+  const MrCtx* mr = g->mr;
+  const int n_own = mr ? mr->n_own : Np;
+  const int n_owned_lm = mr ? mr->n_owned_lm : Nl;
   if (g->structure_dirty) {
     SSB_TRY(sync_estimates_to_host(g));
     // hessian indices (buildIndexMapping: id order, fixed = -1)
@@ -670,17 +788,23 @@ static int prepare(ssb_graph* g) {
       // L-order: by landmark, then by pose index, then by creation order.  Edges normally arrive with non-decreasing
       // pose index per landmark (keyframes are created in time order): one stable counting-sort pass by landmark
       // is enough then; otherwise two passes (least significant key first)
+      // (a shard sorts by the GLOBAL keyframe index of the pose, so that every rank sums a landmark's edges in the
+      // order of the unsharded run)
       std::vector<int> ord(El), tmp;
+      auto key = [&](int p) { return mr ? mr->sortkey[p] : p; };
+      int nkey = Np;
+      if (mr)
+        for (int i = 0; i < Np; ++i) nkey = std::max(nkey, mr->sortkey[i] + 1);
       bool pose_sorted = true;
       {
         std::vector<int> lastp(std::max(Nl, 1), -1);
         for (int k = 0; k < El; ++k) {
           const PLEdge& e = g->pl[k];
-          if (e.p < lastp[e.l]) {
+          if (key(e.p) < lastp[e.l]) {
             pose_sorted = false;
             break;
           }
-          lastp[e.l] = e.p;
+          lastp[e.l] = key(e.p);
         }
       }
       std::vector<int> cntl(lm_rowptr.begin(), lm_rowptr.end() - 1);
@@ -688,10 +812,10 @@ static int prepare(ssb_graph* g) {
         for (int k = 0; k < El; ++k) ord[cntl[g->pl[k].l]++] = k;
       } else {
         tmp.resize(El);
-        std::vector<int> cntp(Np + 1, 0);
-        for (int k = 0; k < El; ++k) cntp[g->pl[k].p + 1]++;
-        for (int i = 0; i < Np; ++i) cntp[i + 1] += cntp[i];
-        for (int k = 0; k < El; ++k) tmp[cntp[g->pl[k].p]++] = k;
+        std::vector<int> cntp(nkey + 1, 0);
+        for (int k = 0; k < El; ++k) cntp[key(g->pl[k].p) + 1]++;
+        for (int i = 0; i < nkey; ++i) cntp[i + 1] += cntp[i];
+        for (int k = 0; k < El; ++k) tmp[cntp[key(g->pl[k].p)]++] = k;
         for (int q = 0; q < El; ++q) ord[cntl[g->pl[tmp[q]].l]++] = tmp[q];
       }
       const bool planes = g->n_plane_vertices != 0;
@@ -708,7 +832,7 @@ static int prepare(ssb_graph* g) {
     tick("hessian index + L-order sort");
     // coarse aggregates: one per persistent CTA, contiguous pose ranges of C poses (multiple of 5)
     const int nblk = g->pcg_grid;
-    int Cc = (Np + nblk - 1) / nblk;
+    int Cc = (n_own + nblk - 1) / nblk;
     Cc = std::max(5, ((Cc + 4) / 5) * 5);
     std::vector<int> run_lm, run_group, run_e0, lm_run_rowptr(Nl + 1, 0);
     run_lm.reserve(El / 4 + 16);
@@ -718,6 +842,8 @@ static int prepare(ssb_graph* g) {
       lm_run_rowptr[l] = (int)run_lm.size();
       int prev = -1;
       for (int e = lm_rowptr[l]; e < lm_rowptr[l + 1]; ++e) {
+        // ghost keyframes carry no basis: their edges ride inside the previous run and contribute exact zeros
+        if (plL[e].p >= n_own) continue;
         const int grp = plL[e].p / Cc;
         if (grp != prev) {
           run_lm.push_back(l);
@@ -746,6 +872,7 @@ static int prepare(ssb_graph* g) {
     for (int l = 0; l < Nl; ++l) {
       int prev = -1;
       for (int e = lm_rowptr[l]; e < lm_rowptr[l + 1]; ++e) {
+        if (plL[e].p >= n_own) continue;
         const int ag = plL[e].p / 5;
         if (ag != prev) {
           run1_lm.push_back(l);
@@ -768,13 +895,14 @@ static int prepare(ssb_graph* g) {
     // runs of one landmark whose aggregates fall into the same group (runs are ordered by landmark, then aggregate)
     const int apc = Cc / 5;                     // aggregates per CTA
     const int n_groups = 2 * nblk;
+    const int n_agg_own = (n_own + 4) / 5;
     std::vector<int> grp_first_agg(n_groups + 1, 0);
     for (int b = 0; b < nblk; ++b) {
-      const int ga0 = std::min(n_agg, b * apc), ga1 = std::min(n_agg, ga0 + apc);
+      const int ga0 = std::min(n_agg_own, b * apc), ga1 = std::min(n_agg_own, ga0 + apc);
       grp_first_agg[2 * b] = ga0;
       grp_first_agg[2 * b + 1] = ga0 + (ga1 - ga0 + 1) / 2;
     }
-    grp_first_agg[n_groups] = std::min(n_agg, nblk * apc);
+    grp_first_agg[n_groups] = std::min(n_agg_own, nblk * apc);
     auto group_of = [&](int ag) {
       const int b = std::min(nblk - 1, ag / apc);
       return 2 * b + (ag >= grp_first_agg[2 * b + 1] ? 1 : 0);
@@ -870,7 +998,6 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_p1.ensure((size_t)6 * Np));
     SSB_TRY(g->d_q.ensure((size_t)6 * Np));
     SSB_TRY(g->d_v.ensure((size_t)3 * (Nl + 64)));
-    SSB_TRY(g->d_mg.ensure(16));
     SSB_TRY(g->d_dl.ensure((size_t)3 * Nl));
     const size_t nb_bs = ((size_t)Np + (size_t)32 * Nl + 127) / 128 + 1;
     SSB_TRY(g->d_part.ensure(std::max<size_t>(3 * PART_STRIDE, nb_bs) + 4096));
@@ -895,16 +1022,19 @@ static int prepare(ssb_graph* g) {
         }
       }
       lm_partbase[Nl] = (int)part_lm.size();
-      const int n_parts = (int)part_lm.size();
-      bool ok = g->allow_fast && g->use_flow && Cc <= 5 * (PCGF_THREADS / 32) && n_parts <= nblk * (PCGF_THREADS / 32);
+      // a shard computes the parts of the landmarks it owns (they come first); the parts of the others arrive as cells
+      const int n_parts_all = (int)part_lm.size();
+      const int n_parts = lm_partbase[n_owned_lm];
+      bool ok = g->allow_fast && g->use_flow && Cc <= 5 * (PCGF_THREADS / 32) && n_parts <= nblk * (PCGF_THREADS / 32) &&
+                6 * (size_t)(Np + 64) + 3 * (size_t)n_parts_all < (1u << 24);   // cell indices are staged in 24 bits
       if (ok) {
         std::vector<int> ov(nblk, 0);
-        for (int q = 0; q < n_parts && ok; ++q) {
+        for (int q = 0; q < n_parts_all && ok; ++q) {
           if (lm_partbase[part_lm[q] + 1] - lm_partbase[part_lm[q]] > 127) ok = false;   // part count rides in the top bits of an int
-          ov[q % nblk] += std::max(0, part_e1[q] - part_e0[q] - 32);
+          if (q < n_parts) ov[q % nblk] += std::max(0, part_e1[q] - part_e0[q] - 32);
         }
         for (int b = 0; b < nblk && ok; ++b) {
-          const int q0 = std::min(Np, b * Cc), q1 = std::min(Np, q0 + Cc);
+          const int q0 = std::min(n_own, b * Cc), q1 = std::min(n_own, q0 + Cc);
           if (ov[b] > PCGF_MAXOV || ppl_rowptr[q1] - ppl_rowptr[q0] > PCGF_MAXPL || ppp_rowptr[q1] - ppp_rowptr[q0] > PCGF_MAXPP)
             ok = false;
         }
@@ -922,7 +1052,7 @@ static int prepare(ssb_graph* g) {
         upp.reserve(Epp + nblk + 16);
         ext.reserve(4 * (size_t)nblk + 16);
         for (int b = 0; b < nblk && ok; ++b) {
-          const int q0 = std::min(Np, b * Cc), q1 = std::min(Np, q0 + Cc);
+          const int q0 = std::min(n_own, b * Cc), q1 = std::min(n_own, q0 + Cc);
           const size_t u0 = ulm.size(), p0e = upp.size(), x0 = ext.size();
           for (int kk = ppl_rowptr[q0]; kk < ppl_rowptr[q1]; ++kk) {
             const int l = plL[ppl_idx[kk]].l;
@@ -990,7 +1120,8 @@ static int prepare(ssb_graph* g) {
           cadj[a].push_back(b);
           cadj[b].push_back(a);
         };
-        for (auto& e : g->pp) link(e.i / Cc, e.j / Cc);
+        for (auto& e : g->pp)
+          if (e.i < n_own && e.j < n_own) link(e.i / Cc, e.j / Cc);
         for (int l = 0; l < Nl; ++l)
           for (int ra = lm_run_rowptr[l]; ra < lm_run_rowptr[l + 1]; ++ra)
             for (int rb = ra + 1; rb < lm_run_rowptr[l + 1]; ++rb) link(run_group[ra], run_group[rb]);
@@ -1029,6 +1160,7 @@ static int prepare(ssb_graph* g) {
       }
     }
     SSB_TRY(g->d_Bmat.ensure((size_t)36 * Np));
+    if (mr && Np) SSB_CUDA_CHECK(cudaMemsetAsync(g->d_Bmat.p, 0, (size_t)36 * Np * sizeof(double), g->stream));   // ghosts: B = 0
     SSB_TRY(g->d_B1mat.ensure((size_t)36 * Np));
     SSB_TRY(g->d_D1inv.ensure((size_t)36 * ((Np + 4) / 5 + 1)));
     SSB_TRY(g->d_Grun.ensure((size_t)18 * n_runs));
@@ -1058,6 +1190,7 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_ucell.ensure((size_t)6 * (Np + 64) + (size_t)3 * ((size_t)Nl + El / 64 + 64)));
     SSB_TRY(g->d_lines.ensure((size_t)2 * nblk * 8));
     SSB_TRY(g->d_hlpark.ensure((size_t)nblk * (PCGF_THREADS / 32) * 9 * 32));
+    SSB_TRY(g->d_trace.ensure(8 * 256));
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_ucell.p, 0, g->d_ucell.cap * sizeof(uint4), g->stream));
     SSB_CUDA_CHECK(cudaMemsetAsync(g->d_lines.p, 0, g->d_lines.cap * sizeof(uint4), g->stream));
     if (g->use_flow && g->opts.preconditioner >= 1) {
@@ -1147,10 +1280,6 @@ static int prepare(ssb_graph* g) {
     SSB_CUDA_CHECK(cudaStreamSynchronize(s));  // host vectors above go out of scope
     tick("upload sync");
     g->structure_dirty = false;
-    if (g->mg_graph) {
-      cudaGraphExecDestroy(g->mg_graph);
-      g->mg_graph = nullptr;
-    }
     g->host_est_dirty = true;
     g->have_system = false;
     g->have_snapshot = false;
@@ -1194,6 +1323,16 @@ static int prepare(ssb_graph* g) {
     G.part = g->d_part.p;
     G.scalars = g->d_scalars.p;
     G.iscalars = g->d_iscalars.p;
+    G.Np_own = n_own;
+    G.lm_owned = nullptr;
+    if (mr) {
+      SSB_TRY(g->d_lm_owned.ensure(std::max(Nl, 1)));
+      if (Nl) {
+        SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_owned.p, mr->lm_owned.data(), Nl, cudaMemcpyHostToDevice, g->stream));
+        SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
+      }
+      G.lm_owned = g->d_lm_owned.p;
+    }
   }
   if (g->host_est_dirty) {
     cudaStream_t s = g->stream;
@@ -1209,7 +1348,14 @@ static int prepare(ssb_graph* g) {
 
 // ---- kernel launch helpers -----------------------------------------------------------------
 static int launch_chi2(ssb_graph* g) {
-  DevGraph& G = g->G;
+  DevGraph G = g->G;
+  if (g->mr) {   // a shard sums the edges it owns; the partial sums are folded by read_scalars_sharded
+    G.pl = g->mr->d_pl_own.p;
+    G.El = g->mr->n_pl_own;
+    G.pp = g->mr->d_pp_own.p;
+    G.Epp = g->mr->n_pp_own;
+    if (G.pl_zd) G.pl_zd = g->mr->d_zd_own.p;
+  }
   const int nt = (G.El + CHI2_PL_TILE - 1) / CHI2_PL_TILE + (G.Epp + CHI2_PP_TILE - 1) / CHI2_PP_TILE;
   const int grid = std::max(1, std::min(nt, 4 * g->num_sms));
   k_chi2<<<grid, CHI2_THREADS, 0, g->stream>>>(G, G.part + 3 * PART_STRIDE, G.scalars + 0, G.iscalars + 2);
@@ -1271,7 +1417,8 @@ static int launch_prep(ssb_graph* g, double lambda, bool separate_coarse = false
   }
   const bool fork = g->Cz.sub_enabled && g->comm_world == 1;
   // the coarse matrix of this trial is assembled and inverted beside the other per-trial kernels (third stream)
-  const bool cinv = separate_coarse && fork && g->Cz.enabled && g->fast_ok && g->use_flow && g->opts.reserved[1] <= 1 && g->d_gj.p;
+  const bool cinv = separate_coarse && fork && g->Cz.enabled && g->fast_ok && g->use_flow && g->opts.reserved[1] <= 1 && g->d_gj.p &&
+                    g->pcg_grid == 148 && !g->mr;
   g->coarse_ready = false;
   if (fork) {
     SSB_CUDA_CHECK(cudaEventRecord(g->ev_fork, s));
@@ -1291,10 +1438,10 @@ static int launch_prep(ssb_graph* g, double lambda, bool separate_coarse = false
     SSB_CUDA_CHECK(cudaEventRecord(g->ev_join3, s3));
     g->coarse_ready = true;
   }
-  k_prep_poses<<<(G.Np + 63) / 64, 64, 0, fork ? s2 : s>>>(G, lambda);
+  k_prep_poses<<<(G.Np_own + 63) / 64, 64, 0, fork ? s2 : s>>>(G, lambda);
   g->launches++;
   if (fork) {
-    k_sub_assemble<<<(G.Np + 4) / 5, SUBA_THREADS, 0, s>>>(G, g->Cz, lambda, (g->Cz.grp_enabled && g->fast_ok) ? 0 : 1);
+    k_sub_assemble<<<(G.Np_own + 4) / 5, SUBA_THREADS, 0, s>>>(G, g->Cz, lambda, (g->Cz.grp_enabled && g->fast_ok) ? 0 : 1);
     g->launches++;
     if (g->Cz.grp_enabled && g->fast_ok) {
       const size_t dsm = (size_t)std::max(g->grp_max_runs, 1) * 18 * sizeof(double);
@@ -1311,11 +1458,14 @@ static int launch_prep(ssb_graph* g, double lambda, bool separate_coarse = false
   return SSB_OK;
 }
 static int launch_pcg(ssb_graph* g, double lambda);
+static int peer_exchange(ssb_graph* g, bool with_record);
 static int launch_solve(ssb_graph* g, double lambda, int apply) {
   DevGraph& G = g->G;
   cudaStream_t s = g->stream;
   SSB_TRY(launch_prep(g, lambda));
   SSB_TRY(launch_pcg(g, lambda));
+  // sharded: the solution of the ghost keyframes was pushed by their owners at the end of the PCG kernel
+  if (g->mr) SSB_TRY(peer_exchange(g, false));
   if (apply) {
     k_backsub_update<<<(G.Np + 32 * G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
     g->launches++;
@@ -1353,16 +1503,31 @@ static int launch_pcg(ssb_graph* g, double lambda) {
   if (g->fast_ok) {
     // tags = (seq << 16) + iteration: unique per launch, so the cell buffers are never cleared between solves
     if (++g->flow_seq >= 0xFFFFu) {
+      if (g->mr) SSB_TRY(peer_exchange(g, false));   // nobody may still be pushing cells of the old tag family
       SSB_CUDA_CHECK(cudaMemsetAsync(g->d_ucell.p, 0, g->d_ucell.cap * sizeof(uint4), s));
       SSB_CUDA_CHECK(cudaMemsetAsync(g->d_lines.p, 0, g->d_lines.cap * sizeof(uint4), s));
       if (g->d_gj.p) SSB_CUDA_CHECK(cudaMemsetAsync(g->d_gj.p, 0, g->d_gj.cap * sizeof(uint4), s));
+      if (g->mr) SSB_TRY(peer_exchange(g, false));   // ... nor start before everybody has cleared
       g->flow_seq = 1;
     }
-    SSB_TRY(g->d_trace.ensure(8 * 256));
     FlowBufs F{g->d_ucell.p, g->d_ucell.p + (size_t)6 * (G.Np + 64), g->d_lines.p, g->d_gj.p, g->flow_seq << 16, g->d_hlpark.p, g->d_trace.p};
     int maxit_f = std::min(maxit, 60000);
-    void* fargs[] = {(void*)&G, (void*)&g->Cz, (void*)&slots, (void*)&F, (void*)&g->FT, (void*)&lambda, (void*)&tol2, (void*)&maxit_f};
-    SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg_flow<148>, dim3(g->pcg_grid), dim3(PCGF_THREADS), fargs, g->pcgw_smem, s));
+    FlowPeer FP{};
+    if (g->mr) FP = g->mr->FP;
+    void* fargs[] = {(void*)&G, (void*)&g->Cz, (void*)&slots, (void*)&F, (void*)&g->FT, (void*)&lambda, (void*)&tol2, (void*)&maxit_f, (void*)&FP};
+    // shards sharing one GPU: two cooperative launches do not overlap, and the kernel needs co-residency with the
+    // OTHER ranks' grids, not cg::grid.sync — launch it as a plain kernel (all the grids together fit the SMs)
+    if (g->mr && g->pcg_grid < g->num_sms) {
+      SSB_CUDA_CHECK(cudaLaunchKernel(flow_kernel(g->pcg_grid, true), dim3(g->pcg_grid), dim3(PCGF_THREADS), fargs, g->pcgw_smem, s));
+      // ... and nothing may be queued BEHIND a kernel that waits for another rank of this process: streams share
+      // hardware queues (CUDA_DEVICE_MAX_CONNECTIONS), and a queue whose head depends on the waiting kernel would
+      // hold back the other rank's launches (false dependency => deadlock)
+      SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+    } else
+      SSB_CUDA_CHECK(cudaLaunchCooperativeKernel(flow_kernel(g->pcg_grid, g->mr != nullptr), dim3(g->pcg_grid), dim3(PCGF_THREADS), fargs, g->pcgw_smem, s));
+  } else if (g->mr) {
+    set_error("sharded graph: a shard does not fit the on-chip PCG kernel (<= %d keyframes per CTA); the streaming kernel is single-rank only", 5 * (PCGF_THREADS / 32));
+    return SSB_ERR_INVALID;
   } else
     SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(g->pcg_grid), dim3(PCG_THREADS), args, g->pcg_smem, s));
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used + 1], s));
@@ -1371,102 +1536,547 @@ static int launch_pcg(ssb_graph* g, double lambda) {
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;
 }
-// PCG row-sharded over the ranks of the attached NCCL communicator (see the k_mg_* kernels).
-__global__ void k_mg_finish(const double* mg, int* iscalars, double* scalars) {
-  iscalars[0] = (int)mg[5];
-  iscalars[1] = (int)mg[6];
-  scalars[3] = 0.0;
-  scalars[4] = mg[3];
+// ============================================================================================================
+// Sharded graphs: ONE graph over several ranks by contiguous keyframe range.
+//
+// Every rank holds the full host graph (the caller replays the same add_* calls everywhere) and derives the same
+// ShardPlan.  Rank r then builds its LOCAL SUBGRAPH as a handle of its own (g->shard):
+//   keyframes : its own range [ps, pe) first, then "ghosts" = keyframes of other ranks that observe a landmark one of
+//               ours observes, or are pose-pose neighbours of ours;
+//   landmarks : every landmark one of its keyframes observes ("touched"), with ALL edges of those landmarks;
+//               a landmark is eliminated ("owned") by the rank that owns its first observer.
+// All per-iteration kernels run unchanged on that subgraph: a touched landmark has all its edges here, so H_ll, b_l,
+// (H_ll + lambda I)^-1 and the back-substitution are computed redundantly and bit-identically by every rank that needs
+// them — nothing of the linearisation is exchanged.  Ghost keyframes have no basis (B = 0) in the aggregate levels,
+// which makes the preconditioner of rank r the one of S restricted to its own keyframes (block-Jacobi across ranks).
+// What crosses NVLink (written by the producer straight into the consumer's arena, ssb_peer.cuh):
+//   per PCG iteration : u of own keyframes that are ghosts elsewhere (6 cells each), v of owned landmark parts touched
+//                       elsewhere (3 cells each), 2 cells (r'u, w'u) per CTA to every other rank;
+//   per damped trial  : the solution x of those keyframes; one 64-byte record per rank (chi2, scale, ...);
+//   per optimize()    : the final estimates of own keyframes / owned landmarks to every rank (full replica).
+// ============================================================================================================
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static ArenaLayout arena_layout(int world, int nb, int NpL, int NlL, int ElL, int NpG, int NlG) {
+  ArenaLayout L{};
+  size_t o = 0;
+  L.flags = o;
+  o = align_up(o + (size_t)world * sizeof(unsigned long long), 256);
+  L.red = o;
+  o = align_up(o + (size_t)world * PEER_RED_N * sizeof(double), 256);
+  L.n_ucells = (size_t)6 * (NpL + 64);
+  L.n_cells = L.n_ucells + (size_t)3 * ((size_t)NlL + ElL / 64 + 64);
+  L.cells = o;
+  o = align_up(o + L.n_cells * sizeof(uint4), 256);
+  L.n_lines = (size_t)2 * world * nb * 8;
+  L.lines = o;
+  o = align_up(o + L.n_lines * sizeof(uint4), 256);
+  L.n_x = (size_t)6 * (NpL + 64);
+  L.x = o;
+  o = align_up(o + L.n_x * sizeof(double), 256);
+  L.z = o;
+  o = align_up(o + L.n_x * sizeof(double), 256);
+  L.n_v = (size_t)3 * (NlL + 64);
+  L.v = o;
+  o = align_up(o + L.n_v * sizeof(double), 256);
+  L.slots = o;
+  o = align_up(o + ((size_t)2 * world * nb + 1) * sizeof(BarSlot), 256);
+  L.pose_full = o;
+  o = align_up(o + (size_t)std::max(NpG, 1) * sizeof(Pose), 256);
+  L.lm_full = o;
+  o = align_up(o + (size_t)std::max(NlG, 1) * 4 * sizeof(double), 256);
+  L.total = o;
+  return L;
 }
-static void shard_ranges(int Np, int Nl, int world, int rank, int out[4]) {
-  const int cp = (Np + world - 1) / world, cl = (Nl + world - 1) / world;
-  out[0] = std::min(Np, rank * cp);
-  out[1] = std::min(Np, out[0] + cp);
-  out[2] = std::min(Nl, rank * cl);
-  out[3] = std::min(Nl, out[2] + cl);
+
+static void build_plan(const ssb_graph* g, int world, int nb, ShardPlan& P) {
+  const int Np = (int)g->poses.size(), Nl = (int)(g->lms.size() / 4);
+  P.world = world;
+  P.nb = nb;
+  P.Np = Np;
+  P.Nl = Nl;
+  P.R.assign(world, RankLocal());
+  const int per = std::max(1, (Np + world - 1) / world);
+  auto rank_of = [&](int p) { return std::min(world - 1, p / per); };
+  for (int r = 0; r < world; ++r) {
+    P.R[r].ps = std::min(Np, r * per);
+    P.R[r].pe = r == world - 1 ? Np : std::min(Np, (r + 1) * per);
+  }
+  P.lm_deg.assign(Nl, 0);
+  std::vector<int> first(Nl, Np);
+  for (auto& e : g->pl) {
+    P.lm_deg[e.l]++;
+    first[e.l] = std::min(first[e.l], e.p);
+  }
+  P.lm_owner.assign(Nl, 0);
+  for (int l = 0; l < Nl; ++l) P.lm_owner[l] = first[l] < Np ? rank_of(first[l]) : 0;
+  // touched[r][l]
+  std::vector<std::vector<unsigned char>> touched(world, std::vector<unsigned char>(std::max(Nl, 1), 0));
+  for (auto& e : g->pl) touched[rank_of(e.p)][e.l] = 1;
+  for (int l = 0; l < Nl; ++l) touched[P.lm_owner[l]][l] = 1;   // (a landmark without edges stays with rank 0)
+  for (int r = 0; r < world; ++r) {
+    RankLocal& R = P.R[r];
+    std::vector<unsigned char> need(std::max(Np, 1), 0);
+    for (auto& e : g->pl)
+      if (touched[r][e.l]) need[e.p] = 1;
+    for (auto& e : g->pp) {
+      const bool io = e.i >= R.ps && e.i < R.pe, jo = e.j >= R.ps && e.j < R.pe;
+      if (io || jo) need[e.i] = need[e.j] = 1;
+    }
+    R.l2g_pose.clear();
+    for (int p = R.ps; p < R.pe; ++p) R.l2g_pose.push_back(p);
+    for (int p = 0; p < Np; ++p)
+      if (need[p] && (p < R.ps || p >= R.pe)) R.l2g_pose.push_back(p);
+    R.g2l_pose.assign(std::max(Np, 1), -1);
+    for (size_t k = 0; k < R.l2g_pose.size(); ++k) R.g2l_pose[R.l2g_pose[k]] = (int)k;
+    R.l2g_lm.clear();
+    for (int l = 0; l < Nl; ++l)
+      if (touched[r][l] && P.lm_owner[l] == r) R.l2g_lm.push_back(l);
+    R.n_owned_lm = (int)R.l2g_lm.size();
+    for (int l = 0; l < Nl; ++l)
+      if (touched[r][l] && P.lm_owner[l] != r) R.l2g_lm.push_back(l);
+    R.g2l_lm.assign(std::max(Nl, 1), -1);
+    R.partbase.assign(R.l2g_lm.size() + 1, 0);
+    for (size_t k = 0; k < R.l2g_lm.size(); ++k) {
+      R.g2l_lm[R.l2g_lm[k]] = (int)k;
+      R.partbase[k + 1] = R.partbase[k] + (P.lm_deg[R.l2g_lm[k]] + 63) / 64;
+    }
+  }
 }
-static int launch_solve_mg(ssb_graph* g, double lambda) {
-  DevGraph& G = g->G;
-  NcclApi& N = nccl_api();
-  cudaStream_t s = g->stream;
+
+// ---- rank <-> rank exchange of small host blobs (arena handles): NCCL between processes, a registry between threads
+struct LocalGroup {
+  std::mutex m;
+  std::condition_variable cv;
+  int arrived = 0;
+  unsigned long long gen = 0;
+  PeerBlob in[SSB_MAX_WORLD], out[SSB_MAX_WORLD];
+};
+static std::mutex g_groups_mutex;
+static std::map<std::string, LocalGroup*> g_groups;
+static int exchange_blobs(ssb_graph* g, const PeerBlob& mine, PeerBlob* all) {
   const int world = g->comm_world, rank = g->comm_rank;
-  if (G.Nl) {
-    k_prep_landmarks<<<(G.Nl + 127) / 128, 128, 0, s>>>(G, lambda);
-    g->launches++;
-  }
-  k_prep_poses<<<(G.Np + 63) / 64, 64, 0, s>>>(G, lambda);
-  g->launches++;
-  int rr[4];
-  shard_ranges(G.Np, G.Nl, world, rank, rr);
-  MgRange R{rr[0], rr[1], rr[2], rr[3]};
-  const int cp = (G.Np + world - 1) / world, cl = (G.Nl + world - 1) / world;
-  double* mg = g->d_mg.p;
-  double* p = g->d_p0.p;
-  const double tol2 = g->opts.pcg_tol * g->opts.pcg_tol;
-  const int own_p = std::max(1, R.pe - R.ps), own_l = std::max(1, R.le - R.ls);
-  const int gridp = std::max(1, std::min(4 * g->num_sms, (((own_p + 4) / 5) + 7) / 8));
-  const int gridl = std::max(1, std::min(4 * g->num_sms, (own_l + 7) / 8));
-  SSB_CUDA_CHECK(cudaMemsetAsync(mg, 0, 16 * sizeof(double), s));
-  g->h_mg[8] = lambda;
-  g->h_mg[9] = tol2;
-  SSB_CUDA_CHECK(cudaMemcpyAsync(mg + 8, g->h_mg + 8, 2 * sizeof(double), cudaMemcpyHostToDevice, s));
-  k_mg_init<<<gridp, 256, 0, s>>>(G, R, mg, p);
-  SSB_NCCL_CHECK(N.AllReduce(mg, mg, 1, kNcclFloat64, kNcclSum, g->comm, s));
-  k_mg_after_init<<<1, 1, 0, s>>>(mg);
-  SSB_NCCL_CHECK(N.AllGather(p + (size_t)6 * rank * cp, p, (size_t)6 * cp, kNcclFloat64, g->comm, s));
-  g->launches += 2;
-  const int maxit = g->opts.max_pcg_iters;
-  auto enqueue_iteration = [&](int par) -> int {
-    k_mg_p1<<<gridl, 256, 0, s>>>(G, R, mg, p);
-    if (G.Nl) SSB_NCCL_CHECK(N.AllGather(G.v + (size_t)3 * rank * cl, G.v, (size_t)3 * cl, kNcclFloat64, g->comm, s));
-    k_mg_p2<<<gridp, 256, 0, s>>>(G, R, mg, p);
-    SSB_NCCL_CHECK(N.AllReduce(mg + 2, mg + 2, 1, kNcclFloat64, kNcclSum, g->comm, s));
-    k_mg_p3<<<gridp, 256, 0, s>>>(G, R, mg, p, par);
-    SSB_NCCL_CHECK(N.AllReduce(mg + (par ^ 1), mg + (par ^ 1), 1, kNcclFloat64, kNcclSum, g->comm, s));
-    k_mg_p4<<<gridp, 256, 0, s>>>(G, R, mg, p, par);
-    SSB_NCCL_CHECK(N.AllGather(p + (size_t)6 * rank * cp, p, (size_t)6 * cp, kNcclFloat64, g->comm, s));
+  if (g->local_group) {
+    LocalGroup* grp;
+    {
+      std::lock_guard<std::mutex> lk(g_groups_mutex);
+      LocalGroup*& slot = g_groups[g->local_key];
+      if (!slot) slot = new LocalGroup();
+      grp = slot;
+    }
+    std::unique_lock<std::mutex> lk(grp->m);
+    grp->in[rank] = mine;
+    const unsigned long long gen = grp->gen;
+    if (++grp->arrived == world) {
+      grp->arrived = 0;
+      for (int r = 0; r < world; ++r) grp->out[r] = grp->in[r];
+      grp->gen++;
+      grp->cv.notify_all();
+    } else if (!grp->cv.wait_for(lk, std::chrono::seconds(120), [&] { return grp->gen != gen; })) {
+      grp->arrived--;
+      set_error("sharded graph: the other ranks of group '%s' did not reach the same call within 120 s", g->local_key.c_str());
+      return SSB_ERR_COMM;
+    }
+    for (int r = 0; r < world; ++r) all[r] = grp->out[r];
     return SSB_OK;
-  };
-  // two iterations (both parities) are captured once into a CUDA graph and replayed: the iteration is
-  // launch-latency bound (8 tiny operations), so removing the per-operation host cost matters
-  if (!g->mg_graph && !g->mg_graph_failed) {
-    cudaGraph_t graph = nullptr;
-    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-    if (ok) {
-      const int r0 = enqueue_iteration(0), r1 = enqueue_iteration(1);
-      ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && r0 == SSB_OK && r1 == SSB_OK && graph;
-    }
-    if (ok) ok = cudaGraphInstantiate(&g->mg_graph, graph, 0) == cudaSuccess;
-    if (graph) cudaGraphDestroy(graph);
-    if (!ok) {
-      cudaGetLastError();
-      g->mg_graph = nullptr;
-      g->mg_graph_failed = true;  // fall back to plain stream launches
-    }
   }
-  for (int it = 0; it < maxit; it += 2) {
-    if (g->mg_graph) {
-      SSB_CUDA_CHECK(cudaGraphLaunch(g->mg_graph, s));
+  NcclApi& N = nccl_api();
+  if (!g->comm || !N.ok) {
+    set_error("sharded graph: no communicator attached");
+    return SSB_ERR_COMM;
+  }
+  MrCtx* mr = g->shard->mr;
+  DBuf<unsigned char>& stage = g->shard->d_blob_stage;
+  SSB_TRY(stage.ensure((size_t)(world + 1) * sizeof(PeerBlob)));
+  cudaStream_t s = g->shard->stream;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(stage.p + (size_t)world * sizeof(PeerBlob), &mine, sizeof(PeerBlob), cudaMemcpyHostToDevice, s));
+  SSB_NCCL_CHECK(N.AllGather(stage.p + (size_t)world * sizeof(PeerBlob), stage.p, sizeof(PeerBlob), /*ncclInt8*/ 0, g->comm, s));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(all, stage.p, (size_t)world * sizeof(PeerBlob), cudaMemcpyDeviceToHost, s));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+  (void)mr;
+  return SSB_OK;
+}
+
+// (re)allocate this rank's arena if needed, tell everybody, map everybody's
+static int map_arenas(ssb_graph* g, const ShardPlan& plan, const std::vector<int>& ElL) {
+  ssb_graph* in = g->shard;
+  MrCtx* mr = in->mr;
+  const int world = plan.world, rank = g->comm_rank;
+  for (int r = 0; r < world; ++r)
+    mr->lay[r] = arena_layout(world, plan.nb, (int)plan.R[r].l2g_pose.size(), (int)plan.R[r].l2g_lm.size(), ElL[r], plan.Np, plan.Nl);
+  const size_t need = mr->lay[rank].total;
+  // arenas replaced two exchanges ago are unmapped everywhere by now
+  if (mr->retired.size() > 1) {
+    cudaFree(mr->retired.front());
+    mr->retired.erase(mr->retired.begin());
+  }
+  if (need > mr->arena_cap || !mr->arena) {
+    if (mr->arena) mr->retired.push_back(mr->arena);
+    const size_t want = need + need / 2 + (1u << 20);
+    mr->arena = nullptr;
+    SSB_CUDA_CHECK(cudaMalloc((void**)&mr->arena, want));
+    mr->arena_cap = want;
+    mr->arena_serial++;
+  }
+  // flags / records / cells start from zero whenever the structure changed (epochs restart with them)
+  SSB_CUDA_CHECK(cudaMemsetAsync(mr->arena, 0, mr->lay[rank].total, in->stream));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(in->stream));
+  mr->epoch = 0;
+  PeerBlob mine{};
+  mine.pid = (int)getpid();
+  mine.device = in->device;
+  mine.ptr = mr->arena;
+  mine.bytes = mr->arena_cap;
+  mine.serial = mr->arena_serial;
+  if (!g->local_group) SSB_CUDA_CHECK(cudaIpcGetMemHandle(&mine.handle, mr->arena));
+  PeerBlob all[SSB_MAX_WORLD];
+  SSB_TRY(exchange_blobs(g, mine, all));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      mr->peer_base[r] = mr->arena;
+      continue;
+    }
+    const PeerBlob& b = all[r];
+    if (b.bytes < mr->lay[r].total) {
+      set_error("sharded graph: rank %d holds a different graph (arena %llu < %zu bytes)", r, b.bytes, mr->lay[r].total);
+      return SSB_ERR_COMM;
+    }
+    const bool same = mr->peer_mapped[r] && mr->peer_blob[r].pid == b.pid && mr->peer_blob[r].serial == b.serial && mr->peer_blob[r].ptr == b.ptr;
+    if (same) continue;
+    if (mr->peer_mapped[r] && mr->peer_blob[r].pid != (int)getpid()) cudaIpcCloseMemHandle(mr->peer_base[r]);
+    mr->peer_mapped[r] = false;
+    if (b.pid == (int)getpid()) {
+      if (b.device != in->device) {
+        int can = 0;
+        SSB_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, in->device, b.device));
+        if (!can) {
+          set_error("sharded graph: device %d cannot access device %d", in->device, b.device);
+          return SSB_ERR_COMM;
+        }
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) SSB_CUDA_CHECK(e);
+        cudaGetLastError();
+      }
+      mr->peer_base[r] = (unsigned char*)b.ptr;
     } else {
-      SSB_TRY(enqueue_iteration(0));
-      SSB_TRY(enqueue_iteration(1));
+      void* q = nullptr;
+      SSB_CUDA_CHECK(cudaIpcOpenMemHandle(&q, b.handle, cudaIpcMemLazyEnablePeerAccess));
+      mr->peer_base[r] = (unsigned char*)q;
     }
-    g->launches += 8;
-    if ((it & 15) == 14 || it + 2 >= maxit) {
-      SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_mg, mg, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
-      SSB_CUDA_CHECK(cudaStreamSynchronize(s));
-      if (g->h_mg[4] != 0.0) break;
-    }
+    mr->peer_blob[r] = b;
+    mr->peer_mapped[r] = true;
   }
-  SSB_NCCL_CHECK(N.AllGather(G.x + (size_t)6 * rank * cp, G.x, (size_t)6 * cp, kNcclFloat64, g->comm, s));
-  k_mg_finish<<<1, 1, 0, s>>>(mg, G.iscalars, G.scalars);
-  k_backsub_update<<<(G.Np + 32 * G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
-  g->launches += 2;
+  PeerDev& P = mr->P;
+  P.world = world;
+  P.rank = rank;
+  for (int r = 0; r < world; ++r) {
+    unsigned char* base = mr->peer_base[r];
+    P.flags[r] = (unsigned long long*)(base + mr->lay[r].flags);
+    P.red[r] = (double*)(base + mr->lay[r].red);
+    P.lines[r] = (uint4*)(base + mr->lay[r].lines);
+    P.slots[r] = base + mr->lay[r].slots;
+    mr->PG.pose_full[r] = base + mr->lay[r].pose_full;
+    mr->PG.lm_full[r] = (double*)(base + mr->lay[r].lm_full);
+    mr->FP.lines[r] = P.lines[r];
+  }
+  mr->PG.world = world;
+  mr->FP.world = world;
+  mr->FP.rank = rank;
+  return SSB_OK;
+}
+
+// barrier (+ small all-gather of the reduction results when with_record) across the ranks, on the handle's stream
+static int peer_exchange(ssb_graph* in, bool with_record) {
+  MrCtx* mr = in->mr;
+  ++mr->epoch;
+  k_peer_exchange<<<1, 32, 0, in->stream>>>(mr->P, with_record ? in->G.scalars : nullptr, in->G.iscalars, mr->epoch, mr->d_err.p);
+  in->launches++;
   SSB_CUDA_CHECK(cudaGetLastError());
+  if (in->pcg_grid < in->num_sms) SSB_CUDA_CHECK(cudaStreamSynchronize(in->stream));   // shards sharing one GPU: see launch_pcg
+  return SSB_OK;
+}
+// the sharded counterpart of read_scalars: exchange the per-rank records and fold them in rank order on the host
+// (identical bits on every rank => identical accept / reject decisions)
+static int read_scalars_sharded(ssb_graph* in) {
+  MrCtx* mr = in->mr;
+  SSB_TRY(peer_exchange(in, true));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(mr->h_red, mr->P.red[mr->rank], (size_t)mr->world * PEER_RED_N * sizeof(double), cudaMemcpyDeviceToHost, in->stream));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(mr->h_err, mr->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, in->stream));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(in->stream));
+  if (*mr->h_err) {
+    set_error("sharded graph: rank %d did not arrive at the exchange (timeout)", *mr->h_err - 1);
+    return SSB_ERR_COMM;
+  }
+  double chi = 0.0, scale = 0.0, md = 0.0;
+  int status = 0;
+  for (int r = 0; r < mr->world; ++r) {
+    const double* rec = mr->h_red + (size_t)r * PEER_RED_N;
+    chi += rec[PR_CHI2];
+    scale += rec[PR_SCALE];
+    md = std::max(md, rec[PR_MAXDIAG]);
+    status = std::max(status, (int)rec[PR_PCG_STATUS]);
+  }
+  const double* me = mr->h_red + (size_t)mr->rank * PEER_RED_N;
+  in->h_scalars[0] = chi;
+  in->h_scalars[1] = scale;
+  in->h_scalars[2] = md;
+  in->h_scalars[3] = me[PR_GAMMA];
+  in->h_scalars[4] = me[PR_GAMMA0];
+  in->h_iscalars[0] = (int)me[PR_PCG_ITERS];
+  in->h_iscalars[1] = status;
+  return SSB_OK;
+}
+
+// own estimates -> the full replica of every rank
+__global__ void k_gather_push(DevGraph G, PeerGather PG, const int* own_l2g, int n_own, const int* ownlm_l2g, int n_owned_lm) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_own) {
+    const Pose X = G.pose[t];
+    for (int r = 0; r < PG.world; ++r) ((Pose*)PG.pose_full[r])[own_l2g[t]] = X;
+  } else if (t < n_own + n_owned_lm) {
+    const int l = t - n_own;
+    const double4 v = reinterpret_cast<const double4*>(G.lm)[l];
+    for (int r = 0; r < PG.world; ++r) reinterpret_cast<double4*>(PG.lm_full[r])[ownlm_l2g[l]] = v;
+  }
+}
+
+static int prepare(ssb_graph* g);
+// outer handle: (re)build the plan, this rank's subgraph handle, the arenas and the push tables
+static int prepare_sharded(ssb_graph* g) {
+  SSB_CUDA_CHECK(cudaSetDevice(g->device));
+  if (!g->ll.empty()) {
+    set_error("landmark-landmark (EdgePointXYZ) edges are not supported on a sharded graph");
+    return SSB_ERR_INVALID;
+  }
+  const int world = g->comm_world, rank = g->comm_rank;
+  if (!g->shard) {
+    ssb_graph_opts o = g->opts;
+    o.device = g->device;
+    o.reserved[2] = g->opts.reserved[2] > 0 ? g->opts.reserved[2] : g->pcg_grid;
+    g->shard = ssb_graph_create(&o);
+    if (!g->shard) return SSB_ERR_CUDA;
+    g->shard->mr = new MrCtx();
+    MrCtx* mr = g->shard->mr;
+    mr->world = world;
+    mr->rank = rank;
+    mr->nb = g->shard->pcg_grid;
+    SSB_CUDA_CHECK(cudaMallocHost((void**)&mr->h_red, (size_t)SSB_MAX_WORLD * PEER_RED_N * sizeof(double)));
+    SSB_CUDA_CHECK(cudaMallocHost((void**)&mr->h_err, sizeof(int)));
+    SSB_TRY(mr->d_err.ensure(1));
+    SSB_CUDA_CHECK(cudaMemset(mr->d_err.p, 0, sizeof(int)));
+  }
+  ssb_graph* in = g->shard;
+  MrCtx* mr = in->mr;
+  if (g->structure_dirty) {
+    const int Np = (int)g->poses.size(), Nl = (int)(g->lms.size() / 4);
+    if (Np < world) {
+      set_error("sharded graph: %d keyframes cannot be split over %d ranks", Np, world);
+      return SSB_ERR_INVALID;
+    }
+    if (!g->plan) g->plan = new ShardPlan();
+    ShardPlan& plan = *g->plan;
+    build_plan(g, world, mr->nb, plan);
+    const RankLocal& R = plan.R[rank];
+    // hessian indices of the full graph (ssb_graph_hessian_index, marginals)
+    int h = 0;
+    for (auto& v : g->V) v.hidx = v.fixed ? -1 : h++;
+    // ---- the local subgraph ----
+    const int NpL = (int)R.l2g_pose.size(), NlL = (int)R.l2g_lm.size();
+    in->V.clear();
+    in->E.clear();
+    in->poses.resize(NpL);
+    in->lms.resize((size_t)4 * NlL);
+    in->lm_kind.assign(NlL, 0);
+    in->pose_vid.clear();
+    in->lm_vid.clear();
+    in->pl.clear();
+    in->pl_zd.clear();
+    in->pp.clear();
+    in->n_plane_vertices = 0;
+    for (int k = 0; k < NpL; ++k) {
+      const int gp = R.l2g_pose[k];
+      HostVertex v{VK_SE3, k, g->V[g->pose_vid[gp]].fixed, -1};
+      in->pose_vid.push_back((int)in->V.size());
+      in->V.push_back(v);
+    }
+    for (int k = 0; k < NlL; ++k) {
+      const int gl = R.l2g_lm[k];
+      HostVertex v{g->lm_kind[gl] ? VK_PLANE : VK_XYZ, k, g->V[g->lm_vid[gl]].fixed, -1};
+      in->lm_kind[k] = g->lm_kind[gl];
+      if (g->lm_kind[gl]) in->n_plane_vertices++;
+      in->lm_vid.push_back((int)in->V.size());
+      in->V.push_back(v);
+    }
+    std::vector<int> ElL(world, 0);
+    for (auto& e : g->pl)
+      for (int r = 0; r < world; ++r)
+        if (plan.R[r].g2l_lm[e.l] >= 0) ElL[r]++;
+    std::vector<PLEdge> pl_own;
+    std::vector<double> zd_own;
+    for (size_t k = 0; k < g->pl.size(); ++k) {
+      const PLEdge& e = g->pl[k];
+      const int ll = R.g2l_lm[e.l];
+      if (ll < 0) continue;
+      PLEdge le = e;
+      le.p = R.g2l_pose[e.p];
+      le.l = ll;
+      in->pl.push_back(le);
+      in->pl_zd.push_back(g->pl_zd[k]);
+      in->E.push_back({EK_PL, (int)in->pl.size() - 1});
+      if (e.p >= R.ps && e.p < R.pe) {
+        pl_own.push_back(le);
+        zd_own.push_back(g->pl_zd[k]);
+      }
+    }
+    std::vector<PPEdge> pp_own;
+    for (auto& e : g->pp) {
+      const bool io = e.i >= R.ps && e.i < R.pe, jo = e.j >= R.ps && e.j < R.pe;
+      if (!io && !jo) continue;
+      PPEdge le = e;
+      le.i = R.g2l_pose[e.i];
+      le.j = R.g2l_pose[e.j];
+      in->pp.push_back(le);
+      in->E.push_back({EK_PP, (int)in->pp.size() - 1});
+      if (io) pp_own.push_back(le);   // a boundary edge is counted by the owner of its first vertex
+    }
+    mr->n_own = R.pe - R.ps;
+    mr->n_owned_lm = R.n_owned_lm;
+    mr->sortkey = R.l2g_pose;
+    mr->lm_owned.assign(std::max(NlL, 1), 0);
+    for (int k = 0; k < R.n_owned_lm; ++k) mr->lm_owned[k] = 1;
+    in->structure_dirty = true;
+    // ---- arenas: the buffers a neighbour writes into are windows of the arena ----
+    SSB_TRY(map_arenas(g, plan, ElL));
+    const ArenaLayout& L = mr->lay[rank];
+    in->d_ucell.set_view(mr->arena + L.cells, L.n_cells);
+    in->d_lines.set_view(mr->arena + L.lines, L.n_lines);
+    in->d_x.set_view(mr->arena + L.x, L.n_x);
+    // ---- push tables ----
+    {
+      std::vector<int> urow(mr->n_own + 1, 0);
+      std::vector<uint4*> ucellp;
+      std::vector<double*> uxp;
+      for (int k = 0; k < mr->n_own; ++k) {
+        const int gp = R.l2g_pose[k];
+        for (int r = 0; r < world; ++r) {
+          if (r == rank) continue;
+          const int li = plan.R[r].g2l_pose[gp];
+          if (li < 0) continue;
+          ucellp.push_back((uint4*)(mr->peer_base[r] + mr->lay[r].cells) + 6 * (size_t)li);
+          uxp.push_back((double*)(mr->peer_base[r] + mr->lay[r].x) + 6 * (size_t)li);
+        }
+        urow[k + 1] = (int)ucellp.size();
+      }
+      const int n_own_parts = R.partbase[R.n_owned_lm];
+      std::vector<int> vrow(n_own_parts + 1, 0);
+      std::vector<uint4*> vcellp;
+      for (int k = 0; k < R.n_owned_lm; ++k) {
+        const int gl = R.l2g_lm[k];
+        for (int q = R.partbase[k]; q < R.partbase[k + 1]; ++q) {
+          for (int r = 0; r < world; ++r) {
+            if (r == rank) continue;
+            const int ll = plan.R[r].g2l_lm[gl];
+            if (ll < 0) continue;
+            const size_t cell = mr->lay[r].n_ucells + (size_t)3 * (plan.R[r].partbase[ll] + (q - R.partbase[k]));
+            vcellp.push_back((uint4*)(mr->peer_base[r] + mr->lay[r].cells) + cell);
+          }
+          vrow[q + 1] = (int)vcellp.size();
+        }
+      }
+      cudaStream_t s = in->stream;
+      SSB_TRY(mr->d_upush_rowptr.ensure(urow.size()));
+      SSB_TRY(mr->d_upush_cell.ensure(std::max<size_t>(ucellp.size(), 1)));
+      SSB_TRY(mr->d_upush_x.ensure(std::max<size_t>(uxp.size(), 1)));
+      SSB_TRY(mr->d_vpush_rowptr.ensure(vrow.size()));
+      SSB_TRY(mr->d_vpush_cell.ensure(std::max<size_t>(vcellp.size(), 1)));
+      SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_upush_rowptr.p, urow.data(), urow.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+      if (!ucellp.empty()) {
+        SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_upush_cell.p, ucellp.data(), ucellp.size() * sizeof(uint4*), cudaMemcpyHostToDevice, s));
+        SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_upush_x.p, uxp.data(), uxp.size() * sizeof(double*), cudaMemcpyHostToDevice, s));
+      }
+      SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_vpush_rowptr.p, vrow.data(), vrow.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+      if (!vcellp.empty())
+        SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_vpush_cell.p, vcellp.data(), vcellp.size() * sizeof(uint4*), cudaMemcpyHostToDevice, s));
+      // chi2 tables and gather maps
+      mr->n_pl_own = (int)pl_own.size();
+      mr->n_pp_own = (int)pp_own.size();
+      SSB_TRY(mr->d_pl_own.ensure(std::max<size_t>(pl_own.size(), 1)));
+      SSB_TRY(mr->d_zd_own.ensure(std::max<size_t>(zd_own.size(), 1)));
+      SSB_TRY(mr->d_pp_own.ensure(std::max<size_t>(pp_own.size(), 1)));
+      if (!pl_own.empty()) {
+        SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_pl_own.p, pl_own.data(), pl_own.size() * sizeof(PLEdge), cudaMemcpyHostToDevice, s));
+        SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_zd_own.p, zd_own.data(), zd_own.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+      }
+      if (!pp_own.empty())
+        SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_pp_own.p, pp_own.data(), pp_own.size() * sizeof(PPEdge), cudaMemcpyHostToDevice, s));
+      SSB_TRY(mr->d_own_l2g.ensure(std::max(mr->n_own, 1)));
+      SSB_TRY(mr->d_ownlm_l2g.ensure(std::max(R.n_owned_lm, 1)));
+      if (mr->n_own) SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_own_l2g.p, R.l2g_pose.data(), mr->n_own * sizeof(int), cudaMemcpyHostToDevice, s));
+      if (R.n_owned_lm)
+        SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_ownlm_l2g.p, R.l2g_lm.data(), R.n_owned_lm * sizeof(int), cudaMemcpyHostToDevice, s));
+      SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+      mr->FP.upush_rowptr = mr->d_upush_rowptr.p;
+      mr->FP.upush_cell = mr->d_upush_cell.p;
+      mr->FP.upush_x = mr->d_upush_x.p;
+      mr->FP.vpush_rowptr = mr->d_vpush_rowptr.p;
+      mr->FP.vpush_cell = mr->d_vpush_cell.p;
+    }
+    g->structure_dirty = false;
+    g->host_est_dirty = true;
+  }
+  if (g->host_est_dirty) {
+    const RankLocal& R = g->plan->R[rank];
+    for (size_t k = 0; k < R.l2g_pose.size(); ++k) in->poses[k] = g->poses[R.l2g_pose[k]];
+    for (size_t k = 0; k < R.l2g_lm.size(); ++k) std::memcpy(&in->lms[4 * k], &g->lms[4 * (size_t)R.l2g_lm[k]], 4 * sizeof(double));
+    in->host_est_dirty = true;
+    in->device_est_newer = false;
+    g->host_est_dirty = false;
+    g->device_est_newer = false;
+  }
+  const bool rebuilt = in->structure_dirty;
+  SSB_TRY(prepare(in));
+  if (!in->fast_ok) {
+    set_error("sharded graph: the shard of rank %d (%d own keyframes, %d local) does not fit the on-chip PCG kernel", rank, mr->n_own,
+              (int)in->poses.size());
+    return SSB_ERR_INVALID;
+  }
+  // ranks sharing one device: cudaMalloc / cudaFree synchronise the whole device, so nobody may start a kernel that
+  // waits for a peer while another rank is still allocating — meet on the host once the tables are built
+  if (rebuilt && g->local_group) {
+    PeerBlob dummy{}, all[SSB_MAX_WORLD];
+    SSB_TRY(exchange_blobs(g, dummy, all));
+  }
+  return SSB_OK;
+}
+
+// after an LM run on the shard: every rank pushes the estimates it owns into everybody's full replica; read it back
+static int gather_estimates_sharded(ssb_graph* g) {
+  ssb_graph* in = g->shard;
+  MrCtx* mr = in->mr;
+  const int n = mr->n_own + mr->n_owned_lm;
+  if (n) {
+    k_gather_push<<<(n + 127) / 128, 128, 0, in->stream>>>(in->G, mr->PG, mr->d_own_l2g.p, mr->n_own, mr->d_ownlm_l2g.p, mr->n_owned_lm);
+    in->launches++;
+  }
+  SSB_TRY(peer_exchange(in, false));
+  const ArenaLayout& L = mr->lay[mr->rank];
+  const size_t Np = g->poses.size(), Nl = g->lms.size() / 4;
+  if (Np) SSB_CUDA_CHECK(cudaMemcpyAsync(g->poses.data(), mr->arena + L.pose_full, Np * sizeof(Pose), cudaMemcpyDeviceToHost, in->stream));
+  if (Nl) SSB_CUDA_CHECK(cudaMemcpyAsync(g->lms.data(), mr->arena + L.lm_full, Nl * 4 * sizeof(double), cudaMemcpyDeviceToHost, in->stream));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(mr->h_err, mr->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, in->stream));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(in->stream));
+  if (*mr->h_err) {
+    set_error("sharded graph: rank %d did not arrive at the final gather (timeout)", *mr->h_err - 1);
+    return SSB_ERR_COMM;
+  }
+  in->device_est_newer = false;   // the shard's host copy is not used; the outer handle holds the estimates
+  g->device_est_newer = false;
+  g->host_est_dirty = false;
   return SSB_OK;
 }
 
 static int read_scalars(ssb_graph* g) {
+  if (g->mr) return read_scalars_sharded(g);
   SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_scalars, g->d_scalars.p, 32 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
   SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_iscalars, g->d_iscalars.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
   SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
@@ -1480,10 +2090,13 @@ static int lm_loop(ssb_graph* g, int max_iterations, ssb_lm_stats* st) {
   g->history.clear();
   g->ev_used = 0;
   SSB_CUDA_CHECK(cudaEventRecord(g->ev0, s));
+  static const bool dbg = std::getenv("SSB_SHARD_DEBUG") != nullptr;
+  const int dbg_rank = g->mr ? g->mr->rank : 0;
   SSB_TRY(launch_chi2(g));
   SSB_TRY(read_scalars(g));
   double currentChi = g->h_scalars[0];
   st->chi2_initial = currentChi;
+  if (dbg) std::fprintf(stderr, "[ssb lm r%d] chi2_0 = %.6f\n", dbg_rank, currentChi);
   double lambda = 0.0, ni = 2.0;
   bool ok = true;
   int it = 0;
@@ -1502,12 +2115,13 @@ static int lm_loop(ssb_graph* g, int max_iterations, ssb_lm_stats* st) {
     int qmax = 0, pcg_its = 0;
     const double chi_before = currentChi;
     do {
-      if (g->comm_world > 1)
-        SSB_TRY(launch_solve_mg(g, lambda));
-      else
-        SSB_TRY(launch_solve(g, lambda, 1));  // push() + setLambda + solve + update
+      if (dbg) std::fprintf(stderr, "[ssb lm r%d] it %d trial %d lambda %.3e: solve\n", dbg_rank, it, qmax, lambda);
+      SSB_TRY(launch_solve(g, lambda, 1));  // push() + setLambda + solve + update
       SSB_TRY(launch_chi2(g));              // computeActiveErrors + activeRobustChi2
       SSB_TRY(read_scalars(g));
+      if (dbg)
+        std::fprintf(stderr, "[ssb lm r%d] it %d trial %d: pcg %d its status %d chi2 %.6f scale %.6e\n", dbg_rank, it, qmax, g->h_iscalars[0],
+                     g->h_iscalars[1], g->h_scalars[0], g->h_scalars[1]);
       st->total_trials++;
       pcg_its += g->h_iscalars[0];
       double tempChi = g->h_scalars[0];
@@ -1566,9 +2180,32 @@ static int lm_loop(ssb_graph* g, int max_iterations, ssb_lm_stats* st) {
 
 extern "C" {
 
+static bool is_sharded(const ssb_graph* g) { return g->comm_world > 1; }
+
 int ssb_graph_prepare(ssb_graph* g) {
   if (!g) return SSB_ERR_INVALID;
-  return prepare(g);
+  return is_sharded(g) ? prepare_sharded(g) : prepare(g);
+}
+
+// sharded LM: the loop runs on this rank's subgraph handle; every host decision is taken from the same exchanged
+// records on every rank, so the ranks stay in lock-step without a leader
+static int optimize_sharded(ssb_graph* g, int max_iterations, ssb_lm_stats* st, bool do_prepare) {
+  const double t0 = wall_ms();
+  if (do_prepare) SSB_TRY(prepare_sharded(g));
+  if (!g->shard || g->structure_dirty) {
+    set_error("optimize_resident: call ssb_graph_prepare first");
+    return SSB_ERR_INVALID;
+  }
+  st->ms_prepare = wall_ms() - t0;
+  ssb_graph* in = g->shard;
+  SSB_CUDA_CHECK(cudaSetDevice(in->device));
+  const long long l0 = in->launches;
+  SSB_TRY(lm_loop(in, max_iterations, st));
+  g->history = in->history;
+  SSB_TRY(gather_estimates_sharded(g));
+  st->ms_total = wall_ms() - t0;
+  st->kernel_launches = in->launches - l0;
+  return SSB_OK;
 }
 
 int ssb_graph_optimize(ssb_graph* g, int max_iterations, ssb_lm_stats* stats) {
@@ -1578,6 +2215,11 @@ int ssb_graph_optimize(ssb_graph* g, int max_iterations, ssb_lm_stats* stats) {
   if (g->E.size() < 10) {  // graph_slam.cpp:184-186
     if (stats) *stats = st;
     return 0;
+  }
+  if (is_sharded(g)) {
+    SSB_TRY(optimize_sharded(g, max_iterations, &st, true));
+    if (stats) *stats = st;
+    return 1;
   }
   const double t0 = wall_ms();
   const long long l0 = g->launches;
@@ -1606,6 +2248,11 @@ int ssb_graph_optimize_resident(ssb_graph* g, int max_iterations, ssb_lm_stats* 
     return 0;
   }
   SSB_CUDA_CHECK(cudaSetDevice(g->device));
+  if (is_sharded(g)) {
+    SSB_TRY(optimize_sharded(g, max_iterations, &st, false));
+    if (stats) *stats = st;
+    return 1;
+  }
   const double t0 = wall_ms();
   const long long l0 = g->launches;
   int r = lm_loop(g, max_iterations, &st);
@@ -1641,6 +2288,13 @@ int ssb_graph_get_history(ssb_graph* g, double* out6n, int cap) {
 
 int ssb_graph_chi2(ssb_graph* g, double* chi2_out) {
   if (!g || !chi2_out) return SSB_ERR_INVALID;
+  if (is_sharded(g)) {   // collective: every rank must call
+    SSB_TRY(prepare_sharded(g));
+    SSB_TRY(launch_chi2(g->shard));
+    SSB_TRY(read_scalars(g->shard));
+    *chi2_out = g->shard->h_scalars[0];
+    return SSB_OK;
+  }
   SSB_TRY(prepare(g));
   SSB_TRY(launch_chi2(g));
   SSB_TRY(read_scalars(g));
@@ -1733,6 +2387,13 @@ int ssb_graph_invalidate(ssb_graph* g) {
 
 int ssb_graph_snapshot(ssb_graph* g) {
   if (!g) return SSB_ERR_INVALID;
+  if (is_sharded(g)) {
+    SSB_TRY(prepare_sharded(g));
+    g->snap_poses = g->poses;
+    g->snap_lms = g->lms;
+    g->have_snapshot = true;
+    return ssb_graph_snapshot(g->shard);
+  }
   SSB_TRY(prepare(g));
   SSB_TRY(g->d_pose_snap.ensure(g->G.Np));
   SSB_TRY(g->d_lm_snap.ensure((size_t)4 * g->G.Nl));
@@ -1749,6 +2410,13 @@ int ssb_graph_restore(ssb_graph* g) {
     return SSB_ERR_INVALID;
   }
   SSB_CUDA_CHECK(cudaSetDevice(g->device));
+  if (is_sharded(g)) {
+    g->poses = g->snap_poses;
+    g->lms = g->snap_lms;
+    SSB_TRY(ssb_graph_restore(g->shard));
+    g->shard->device_est_newer = false;
+    return SSB_OK;
+  }
   const int n = std::max(g->G.Np, g->G.Nl);
   k_copy_state<<<(n + 255) / 256, 256, 0, g->stream>>>(g->G.pose, g->d_pose_snap.p, g->G.Np, g->G.lm, g->d_lm_snap.p, g->G.Nl);
   g->launches++;
@@ -1760,7 +2428,7 @@ int ssb_graph_restore(ssb_graph* g) {
 }
 
 int ssb_graph_edge_linearize(ssb_graph* g, int eid, double* err, double* Ji, double* Jj) {
-  if (!g || eid < 0 || eid >= (int)g->E.size() || !err || !Ji || !Jj) return SSB_ERR_INVALID;
+  if (!g || eid < 0 || eid >= (int)g->E.size() || !err || !Ji || !Jj || is_sharded(g)) return SSB_ERR_INVALID;
   SSB_TRY(prepare(g));
   HostEdgeRef r = g->E[eid];
   if (r.kind == EK_LL) return SSB_ERR_INVALID;
@@ -1784,6 +2452,10 @@ int ssb_graph_edge_linearize(ssb_graph* g, int eid, double* err, double* Ji, dou
 
 int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len) {
   if (!g || !x) return SSB_ERR_INVALID;
+  if (is_sharded(g)) {
+    set_error("solve_once: test hook of the unsharded back-end");
+    return SSB_ERR_INVALID;
+  }
   SSB_TRY(prepare(g));
   SSB_TRY(launch_linearize(g));
   SSB_TRY(launch_solve(g, lambda, 0));
@@ -1836,8 +2508,8 @@ int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* o
       return SSB_ERR_INVALID;
     }
   if (g->E.size() < 10) return 0;  // nothing was ever optimised (graph_slam.cpp:184-186)
-  if (g->comm_world > 1) {
-    set_error("landmark_marginals: not available on a sharded graph in this round");
+  if (is_sharded(g)) {
+    set_error("landmark_marginals: not available on a sharded graph");
     return 0;
   }
   SSB_TRY(prepare(g));
@@ -2035,7 +2707,9 @@ int ssb_comm_unique_id(unsigned char id_out[128]) {
   return SSB_OK;
 }
 int ssb_graph_attach_comm(ssb_graph* g, int rank, int world, const unsigned char unique_id[128]) {
-  if (!g || world < 1 || rank < 0 || rank >= world) return SSB_ERR_INVALID;
+  if (!g || world < 1 || world > SSB_MAX_WORLD || rank < 0 || rank >= world) return SSB_ERR_INVALID;
+  g->local_group = 0;
+  g->structure_dirty = true;
   NcclApi& N = nccl_api();
   if (g->comm && N.ok) {
     N.CommDestroy(g->comm);
@@ -2057,10 +2731,51 @@ int ssb_graph_attach_comm(ssb_graph* g, int rank, int world, const unsigned char
   g->comm_world = world;
   return SSB_OK;
 }
-// contiguous keyframe / landmark ranges owned by `rank` (host-only helper, no GPU needed)
+// ranks = host threads of THIS process (one handle each; same or different devices): the arena pointers are handed
+// over through an in-process registry keyed by `group_key`.  Several shards may share one GPU ("virtual shards":
+// cta_per_rank = 74 or 37 so that all shards' persistent kernels are resident together) — this is how the sharded
+// protocol is exercised on a single-GPU box.
+int ssb_graph_attach_local(ssb_graph* g, int rank, int world, const char* group_key, int cta_per_rank) {
+  if (!g || world < 1 || world > SSB_MAX_WORLD || rank < 0 || rank >= world || !group_key) return SSB_ERR_INVALID;
+  if (g->shard) {
+    set_error("attach_local: the graph is already sharded");
+    return SSB_ERR_INVALID;
+  }
+  g->comm_rank = world > 1 ? rank : 0;
+  g->comm_world = world;
+  g->local_group = world > 1;
+  g->local_key = group_key;
+  g->opts.reserved[2] = cta_per_rank > 0 ? cta_per_rank : 0;
+  g->structure_dirty = true;
+  return SSB_OK;
+}
+// own keyframe range [out[0], out[1]) of `rank` and, with a graph, its local sizes: out[2] = keyframes incl. ghosts,
+// out[3] = landmarks touched (host-only helper)
 int ssb_shard_ranges(int n_poses, int n_landmarks, int world, int rank, int out4[4]) {
   if (world < 1 || rank < 0 || rank >= world || !out4 || n_poses < 0 || n_landmarks < 0) return SSB_ERR_INVALID;
-  shard_ranges(n_poses, n_landmarks, world, rank, out4);
+  const int per = std::max(1, (n_poses + world - 1) / world);
+  out4[0] = std::min(n_poses, rank * per);
+  out4[1] = rank == world - 1 ? n_poses : std::min(n_poses, (rank + 1) * per);
+  out4[2] = out4[3] = 0;
+  return SSB_OK;
+}
+// the sharding plan of the current graph as every rank computes it (host-only): for rank `rank`, out[0..1] = own
+// keyframe range, out[2] = local keyframes (own + ghosts), out[3] = owned landmarks, out[4] = touched landmarks,
+// out[5] = local pose-landmark edges
+int ssb_graph_shard_info(ssb_graph* g, int world, int rank, int out6[6]) {
+  if (!g || world < 1 || world > SSB_MAX_WORLD || rank < 0 || rank >= world || !out6) return SSB_ERR_INVALID;
+  ShardPlan plan;
+  build_plan(g, world, 148, plan);
+  const RankLocal& R = plan.R[rank];
+  out6[0] = R.ps;
+  out6[1] = R.pe;
+  out6[2] = (int)R.l2g_pose.size();
+  out6[3] = R.n_owned_lm;
+  out6[4] = (int)R.l2g_lm.size();
+  int el = 0;
+  for (auto& e : g->pl)
+    if (R.g2l_lm[e.l] >= 0) ++el;
+  out6[5] = el;
   return SSB_OK;
 }
 

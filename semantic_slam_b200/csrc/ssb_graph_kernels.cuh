@@ -19,6 +19,11 @@ namespace cg = cooperative_groups;
 
 struct DevGraph {
   int Np, Nl, El, Epp;
+  // Sharded graphs (ssb_peer.cuh): this rank's local subgraph holds its own keyframes [0, Np_own) followed by
+  // "ghost" keyframes owned by other ranks (they observe a landmark one of ours observes, or are odometry
+  // neighbours); landmarks with lm_owned == 0 are eliminated by another rank.  Unsharded: Np_own == Np, null.
+  int Np_own;
+  const unsigned char* lm_owned;
   Pose* pose;
   double* lm;  // 4 doubles per landmark
   const unsigned char* pose_fixed;
@@ -250,11 +255,11 @@ __global__ void k_maxdiag(DevGraph G) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   double m = 0.0;
   if (t < G.Np) {
-    if (!G.pose_fixed[t])
+    if (!G.pose_fixed[t] && t < G.Np_own)
       for (int k = 0; k < 6; ++k) m = fmax(m, fabs(G.Hpp[36 * (size_t)t + 7 * k]));
   } else if (t < G.Np + G.Nl) {
     int l = t - G.Np;
-    if (!G.lm_fixed[l]) {
+    if (!G.lm_fixed[l] && (G.lm_owned == nullptr || G.lm_owned[l])) {
       m = fmax(m, fabs(G.Hll[6 * (size_t)l + 0]));
       m = fmax(m, fabs(G.Hll[6 * (size_t)l + 3]));
       m = fmax(m, fabs(G.Hll[6 * (size_t)l + 5]));
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(128) k_prep_landmarks(DevGraph G, double lambd
 
 __global__ void __launch_bounds__(64) k_prep_poses(DevGraph G, double lambda) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= G.Np) return;
+  if (i >= G.Np_own) return;
   double D[36], g[6];
   for (int k = 0; k < 36; ++k) D[k] = G.Hpp[36 * (size_t)i + k];
   for (int k = 0; k < 6; ++k) {
@@ -519,7 +524,7 @@ __device__ __forceinline__ bool warp_inv6(double* col) {
 __global__ void __launch_bounds__(256) k_coarse_basis(DevGraph G, CoarseDev Cz) {
   __shared__ double sh[33];
   __shared__ double cen[3];
-  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np, p0 + Cz.C);
+  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np_own, p0 + Cz.C);
   double s[3] = {0, 0, 0};
   for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x)
     for (int k = 0; k < 3; ++k) s[k] += G.pose[i].t[k];
@@ -579,13 +584,13 @@ __global__ void __launch_bounds__(128) k_sub_basis(DevGraph G, CoarseDev Cz) {
   // one thread per pose; the aggregate centroid is recomputed by each of its (<= 5) threads in the same order
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= G.Np) return;
-  const int i0 = 5 * (i / 5), i1 = min(G.Np, i0 + 5);
+  const int i0 = 5 * (i / 5), i1 = min(G.Np_own, i0 + 5);   // ghost keyframes carry no basis (B = 0)
   double cen[3] = {0, 0, 0};
   for (int q = i0; q < i1; ++q)
     for (int k = 0; k < 3; ++k) cen[k] += G.pose[q].t[k];
-  for (int k = 0; k < 3; ++k) cen[k] /= (double)(i1 - i0);
+  for (int k = 0; k < 3; ++k) cen[k] /= (double)max(1, i1 - i0);
   double* B = Cz.B1mat + 36 * (size_t)i;
-  if (G.pose_fixed[i]) {
+  if (G.pose_fixed[i] || i >= G.Np_own) {
     for (int k = 0; k < 36; ++k) B[k] = 0.0;
     return;
   }
@@ -632,7 +637,7 @@ __global__ void __launch_bounds__(SUBA_THREADS) k_sub_assemble(DevGraph G, Coars
   const int sl = threadIdx.x / 36, ent = threadIdx.x - 36 * sl;
   const int a = blockIdx.x;
   const int r = ent / 6, c = ent - 6 * r;
-  const int i0 = 5 * a, i1 = min(G.Np, i0 + 5);
+  const int i0 = 5 * a, i1 = min(G.Np_own, i0 + 5);
   if (sl < 5) {
     double d = 0.0;
     bool any = false;
@@ -756,7 +761,7 @@ __global__ void __launch_bounds__(GRP_THREADS) k_grp_invert(DevGraph G, CoarseDe
   }
   if (nseg == 0 && tid == 0) segoff[0] = 0;
   // pose-pose edges between different aggregates of the group: every pose counts its own (role 0) ...
-  const int np = min(G.Np, 5 * a1) - 5 * a0;
+  const int np = min(G.Np_own, 5 * a1) - 5 * a0;
   int my_n = 0;
   if (tid < np) {
     const int i = 5 * a0 + tid, ai = tid / 5;
@@ -1006,7 +1011,7 @@ __device__ void coarse_assemble(const DevGraph& G, const CoarseDev& Cz, double l
         const int code = G.pose_pp_idx[kk];
         const int e = code >> 1, role = code & 1;
         const int j = role == 0 ? G.pp[e].j : G.pp[e].i;
-        if (j >= p0 && j < p1) continue;
+        if ((j >= p0 && j < p1) || j >= G.Np_own) continue;   // ghost keyframes have no coarse unknowns here
         const int gj = j / Cz.C;
         const double* Bj = Cz.Bmat + 36 * (size_t)j;
         const double* Ho = G.Hoff + 36 * (size_t)e;
@@ -1181,7 +1186,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   const int slot = lane / 6, comp = lane - 6 * slot;
   const bool lane_active = lane < 30;
   const int base_lane = 6 * slot;
-  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np, p0 + Cz.C);
+  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np_own, p0 + Cz.C);
   unsigned epoch = 0;
   double* pold = G.p0;
   double* pnew = G.p1;
@@ -1420,246 +1425,6 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Multi-GPU PCG phases (one process per GPU).  The Schur PCG is row-sharded by contiguous keyframe
-// range [ps, pe) and landmark range [ls, le); the vectors p, v (and finally x) are replicated with
-// NCCL all-gathers, the two dot products with NCCL all-reduces (host side: ssb_graph.cu).  Everything
-// else in the LM iteration (linearisation, update, chi2) is computed redundantly and deterministically
-// on every rank, so all ranks hold bit-identical estimates.  Block-Jacobi preconditioner.
-// mg scalars: [0],[1] rz ping-pong  [2] pq  [3] rz0  [4] done  [5] iterations  [6] status  [7] breakdown
-//             [8] lambda  [9] tol^2
-// ---------------------------------------------------------------------------------------------
-struct MgRange {
-  int ps, pe, ls, le;
-};
-
-__global__ void __launch_bounds__(256) k_mg_init(DevGraph G, MgRange R, double* mg, double* p) {
-  __shared__ double sh[33];
-  __shared__ int is_last;
-  const int lane = threadIdx.x & 31;
-  const int slot = lane / 6, comp = lane - 6 * slot, base_lane = 6 * slot;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
-  double local = 0.0;
-  for (int pbase = R.ps + gw * 5; pbase < R.pe; pbase += tw * 5) {
-    const int i = pbase + slot;
-    const bool act = lane < 30 && i < R.pe;
-    const double rc = act ? G.g[6 * (size_t)i + comp] : 0.0;
-    double zc = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const double rk = __shfl_sync(0xffffffffu, rc, base_lane + k);
-      if (act) zc += G.Dinv[36 * (size_t)i + 6 * comp + k] * rk;
-    }
-    if (act) {
-      G.x[6 * (size_t)i + comp] = 0.0;
-      G.r[6 * (size_t)i + comp] = rc;
-      G.z[6 * (size_t)i + comp] = zc;
-      p[6 * (size_t)i + comp] = zc;
-      local += rc * zc;
-    }
-  }
-  const double bs = block_sum(local, sh);
-  if (threadIdx.x == 0) {
-    G.part[blockIdx.x] = bs;
-    __threadfence();
-    is_last = (atomicAdd(G.iscalars + 3, 1) == (int)gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    double s = 0.0;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) s += __ldcg(G.part + k);
-    s = block_sum(s, sh);
-    if (threadIdx.x == 0) {
-      mg[0] = s;  // local partial of rz0, all-reduced by the host
-      mg[4] = 0.0;
-      mg[5] = 0.0;
-      mg[6] = 0.0;
-      mg[7] = 0.0;
-      G.iscalars[3] = 0;
-    }
-  }
-}
-__global__ void k_mg_after_init(double* mg) {
-  mg[3] = mg[0];
-  if (!(mg[0] > 0.0)) {
-    mg[4] = 1.0;
-    if (mg[0] != 0.0) mg[6] = 2.0;
-  }
-}
-
-__global__ void __launch_bounds__(256) k_mg_p1(DevGraph G, MgRange R, const double* mg, const double* p) {
-  if (mg[4] != 0.0) return;
-  const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
-  for (int l = R.ls + gw; l < R.le; l += tw) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    const int e1 = G.lm_rowptr[l + 1];
-    for (int e = G.lm_rowptr[l] + lane; e < e1; e += 32) {
-      const double* Hl = G.HplL + 18 * (size_t)e;
-      const double* pp = p + 6 * (size_t)G.pl[e].p;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const double pc = pp[c];
-        a0 += Hl[c] * pc;
-        a1 += Hl[6 + c] * pc;
-        a2 += Hl[12 + c] * pc;
-      }
-    }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    a2 = warp_sum(a2);
-    if (lane == 0) {
-      const double* Wi = G.HllInv + 6 * (size_t)l;
-      G.v[3 * (size_t)l + 0] = Wi[0] * a0 + Wi[1] * a1 + Wi[2] * a2;
-      G.v[3 * (size_t)l + 1] = Wi[1] * a0 + Wi[3] * a1 + Wi[4] * a2;
-      G.v[3 * (size_t)l + 2] = Wi[2] * a0 + Wi[4] * a1 + Wi[5] * a2;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) k_mg_p2(DevGraph G, MgRange R, double* mg, const double* p) {
-  __shared__ double sh[33];
-  __shared__ int is_last;
-  if (mg[4] != 0.0) return;
-  const double lambda = mg[8];  // set by the host before the solve (keeps the captured graph reusable)
-  const int lane = threadIdx.x & 31;
-  const int slot = lane / 6, comp = lane - 6 * slot, base_lane = 6 * slot;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
-  double local = 0.0;
-  for (int pbase = R.ps + gw * 5; pbase < R.pe; pbase += tw * 5) {
-    const int i = pbase + slot;
-    const bool act = lane < 30 && i < R.pe;
-    const double pc = act ? p[6 * (size_t)i + comp] : 0.0;
-    double qv = lambda * pc;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const double pk = __shfl_sync(0xffffffffu, pc, base_lane + k);
-      if (act) qv += G.Hpp[36 * (size_t)i + 6 * comp + k] * pk;
-    }
-    if (act) {
-      for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
-        const int code = G.pose_pp_idx[kk];
-        const int e = code >> 1, role = code & 1;
-        const int other = role == 0 ? G.pp[e].j : G.pp[e].i;
-        const double* Ho = G.Hoff + 36 * (size_t)e;
-        const double* po = p + 6 * (size_t)other;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) qv += (role == 0 ? Ho[6 * comp + k] : Ho[6 * k + comp]) * po[k];
-      }
-      for (int kk = G.pose_pl_rowptr[i]; kk < G.pose_pl_rowptr[i + 1]; ++kk) {
-        const double* Hp = G.HplP + 18 * (size_t)kk + 3 * comp;
-        const double* vv = G.v + 3 * (size_t)G.plP_lm[kk];
-        qv -= Hp[0] * vv[0] + Hp[1] * vv[1] + Hp[2] * vv[2];
-      }
-      G.q[6 * (size_t)i + comp] = qv;
-      local += pc * qv;
-    }
-  }
-  const double bs = block_sum(local, sh);
-  if (threadIdx.x == 0) {
-    G.part[blockIdx.x] = bs;
-    __threadfence();
-    is_last = (atomicAdd(G.iscalars + 3, 1) == (int)gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    double s = 0.0;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) s += __ldcg(G.part + k);
-    s = block_sum(s, sh);
-    if (threadIdx.x == 0) {
-      mg[2] = s;
-      G.iscalars[3] = 0;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) k_mg_p3(DevGraph G, MgRange R, double* mg, const double* p, int par) {
-  __shared__ double sh[33];
-  __shared__ int is_last;
-  if (mg[4] != 0.0) return;
-  const double pq = mg[2];
-  const bool bad = !(pq > 0.0) || !isfinite(pq);
-  const double alpha = bad ? 0.0 : mg[par] / pq;
-  const int lane = threadIdx.x & 31;
-  const int slot = lane / 6, comp = lane - 6 * slot, base_lane = 6 * slot;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
-  double local = 0.0;
-  for (int pbase = R.ps + gw * 5; pbase < R.pe; pbase += tw * 5) {
-    const int i = pbase + slot;
-    const bool act = lane < 30 && i < R.pe;
-    double rc = 0.0;
-    if (act) {
-      const size_t o = 6 * (size_t)i + comp;
-      G.x[o] += alpha * p[o];
-      rc = G.r[o] - alpha * G.q[o];
-      G.r[o] = rc;
-    }
-    double zc = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const double rk = __shfl_sync(0xffffffffu, rc, base_lane + k);
-      if (act) zc += G.Dinv[36 * (size_t)i + 6 * comp + k] * rk;
-    }
-    if (act) {
-      G.z[6 * (size_t)i + comp] = zc;
-      local += rc * zc;
-    }
-  }
-  const double bs = block_sum(local, sh);
-  if (threadIdx.x == 0) {
-    G.part[blockIdx.x] = bs;
-    __threadfence();
-    is_last = (atomicAdd(G.iscalars + 3, 1) == (int)gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    double s = 0.0;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) s += __ldcg(G.part + k);
-    s = block_sum(s, sh);
-    if (threadIdx.x == 0) {
-      mg[par ^ 1] = s;  // local partial of the new rz, all-reduced by the host
-      G.iscalars[3] = 0;
-      if (bad) mg[7] = 1.0;  // breakdown seen by this rank (identical on all ranks)
-    }
-  }
-}
-
-// beta = rz_new / rz_old ; p = z + beta p (owned rows) ; convergence / breakdown flags
-__global__ void __launch_bounds__(256) k_mg_p4(DevGraph G, MgRange R, double* mg, double* p, int par) {
-  if (mg[4] != 0.0) return;
-  const double tol2 = mg[9];
-  const double rzo = mg[par], rzn = mg[par ^ 1];
-  const bool bad = mg[7] != 0.0;
-  const double beta = rzn / rzo;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = 6 * (R.pe - R.ps);
-  for (int k = t; k < n; k += gridDim.x * blockDim.x) {
-    const size_t o = 6 * (size_t)R.ps + k;
-    p[o] = G.z[o] + beta * p[o];
-  }
-  // the flags are written by the block that finishes last so that no block of this launch sees them early
-  __shared__ int is_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    is_last = (atomicAdd(G.iscalars + 3, 1) == (int)gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    G.iscalars[3] = 0;
-    mg[5] += 1.0;
-    if (bad) {
-      mg[6] = 1.0;
-      mg[4] = 1.0;
-    } else if (!(rzn > tol2 * mg[3])) {
-      mg[4] = 1.0;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // K4: back-substitution + state update (+ backup for LM reject) + computeScale partials
 //   dl = (Hll+lambda)^-1 (bl - sum_e HplL_e dp),  l += dl ;  X <- X * fromVectorMQT(dp)
 //   scale = sum_j d_j (lambda d_j + b_j)      (OptimizationAlgorithmLevenberg::computeScale)
@@ -1700,9 +1465,10 @@ __global__ void __launch_bounds__(128) k_backsub_update(DevGraph G, double lambd
         for (int c = 0; c < 3; ++c) cur[c] += d[c];  // VertexPointXYZ::oplusImpl
       }
       for (int c = 0; c < 4; ++c) G.lm[4 * (size_t)l + c] = cur[c];
+      const bool mine = G.lm_owned == nullptr || G.lm_owned[l] != 0;   // a shared landmark is counted by its owner
       for (int c = 0; c < 3; ++c) {
         G.dl[3 * (size_t)l + c] = d[c];
-        sc += d[c] * (lambda * d[c] + G.bl[3 * (size_t)l + c]);
+        if (mine) sc += d[c] * (lambda * d[c] + G.bl[3 * (size_t)l + c]);
       }
     }
   } else if (t < 32 * G.Nl + G.Np) {
@@ -1715,7 +1481,8 @@ __global__ void __launch_bounds__(128) k_backsub_update(DevGraph G, double lambd
       pose_oplus(X, d);
       G.pose[i] = X;
     }
-    for (int c = 0; c < 6; ++c) sc += d[c] * (lambda * d[c] + G.bp[6 * (size_t)i + c]);
+    if (i < G.Np_own)
+      for (int c = 0; c < 6; ++c) sc += d[c] * (lambda * d[c] + G.bp[6 * (size_t)i + c]);
   }
   double bs = block_sum(sc, sh);
   if (threadIdx.x == 0) {

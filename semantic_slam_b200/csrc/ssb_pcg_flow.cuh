@@ -24,6 +24,7 @@
 // cleared between solves.
 #pragma once
 #include "ssb_graph_kernels.cuh"
+#include "ssb_peer.cuh"
 
 namespace ssb {
 
@@ -35,6 +36,18 @@ struct FlowBufs {
   unsigned tagbase;
   double2* hlpark;  // [gridDim.x * warps][9][32] landmark-role blocks parked in L2 between iterations
   unsigned long long* trace;  // debug (-DSSB_FLOW_TRACE): [gridDim.x][8] globaltimer stamps of one iteration
+};
+
+// Sharded graphs (template parameter MR of k_pcg_flow): what a CTA writes into the arenas of the other ranks.
+// All tables hold absolute pointers into the peers' mapped arenas, built by the host per structure change.
+struct FlowPeer {
+  int world, rank;
+  const int* upush_rowptr;     // [Np_own + 1] ranks that hold my keyframe as a ghost
+  uint4* const* upush_cell;    //   its 6 u cells in that rank's cell buffer
+  double* const* upush_x;      //   its 6 slots in that rank's solution vector
+  const int* vpush_rowptr;     // [own landmark parts + 1] ranks whose keyframes see the landmark of the part
+  uint4* const* vpush_cell;    //   the 3 v cells of the part in that rank's cell buffer
+  uint4* lines[SSB_MAX_WORLD]; // every rank's reduction lines [2][world][NB][8]; line (p, r, b) is written by CTA b of rank r
 };
 
 __device__ __forceinline__ void st_cell(uint4* c, double v, unsigned tag) {
@@ -69,15 +82,37 @@ __device__ __forceinline__ void lds_row6(uint32_t addr, double* out) {
 #define SSB_SPIN_LIMIT (1u << 24)
 #endif
 // spin on one cell (the first attempt was already issued by the caller)
+// SYS: the cell may have been written by another rank over NVLink (system-scope load, and a globaltimer deadline
+// checked every 4096 polls: a rank that died must not hang this one — trap instead)
+template <bool SYS>
+__device__ __forceinline__ uint4 ld_cell_t(const uint4* p) {
+  if constexpr (SYS)
+    return ld_cell_sys(p);
+  else
+    return ld_cell(p);
+}
+__device__ __noinline__ void peer_deadline(unsigned long long& t0) {
+  const unsigned long long now = peer_globaltimer();
+  if (t0 == 0)
+    t0 = now;
+  else if (now - t0 > SSB_PEER_TIMEOUT_NS)
+    __trap();
+}
+template <bool SYS = false>
 __device__ __forceinline__ double cell_wait(const uint4* p, uint4 c, unsigned tag) {
 #ifdef SSB_WATCHDOG
   unsigned spins = 0;
 #endif
+  unsigned polls = 0;
+  unsigned long long t0 = 0;
   while (!cell_ok(c, tag)) {
 #if SSB_POLL_NS > 0
     __nanosleep(SSB_POLL_NS);
 #endif
-    c = ld_cell(p);
+    c = ld_cell_t<SYS>(p);
+    if constexpr (SYS) {
+      if ((++polls & 4095u) == 0) peer_deadline(t0);
+    }
 #ifdef SSB_WATCHDOG
     if (++spins > SSB_SPIN_LIMIT) __trap();
 #endif
@@ -88,7 +123,7 @@ __device__ __forceinline__ double cell_wait(const uint4* p, uint4 c, unsigned ta
 // Batch wait: N cells base[off[m]] (off[m] < 0: not wanted) were all loaded once into c[].  Cells are consumed in
 // order; when cell m had to be spun on, the copies of the later cells are stale too, so they are re-issued TOGETHER
 // right after m arrived (one extra round trip for the rest of the batch instead of one per cell), and only then.
-template <int N>
+template <int N, bool SYS = false>
 __device__ __forceinline__ void cells_wait(const uint4* base, const int (&off)[N], uint4 (&c)[N], unsigned tag,
                                            double (&val)[N]) {
 #pragma unroll
@@ -99,18 +134,23 @@ __device__ __forceinline__ void cells_wait(const uint4* base, const int (&off)[N
 #ifdef SSB_WATCHDOG
         unsigned spins = 0;
 #endif
+        unsigned polls = 0;
+        unsigned long long t0 = 0;
         do {
 #if SSB_POLL_NS > 0
           __nanosleep(SSB_POLL_NS);
 #endif
-          c[m] = ld_cell(base + off[m]);
+          c[m] = ld_cell_t<SYS>(base + off[m]);
+          if constexpr (SYS) {
+            if ((++polls & 4095u) == 0) peer_deadline(t0);
+          }
 #ifdef SSB_WATCHDOG
           if (++spins > SSB_SPIN_LIMIT) __trap();
 #endif
         } while (!cell_ok(c[m], tag));
 #pragma unroll
         for (int q = m + 1; q < N; ++q)
-          if (off[q] >= 0 && !cell_ok(c[q], tag)) c[q] = ld_cell(base + off[q]);
+          if (off[q] >= 0 && !cell_ok(c[q], tag)) c[q] = ld_cell_t<SYS>(base + off[q]);
       }
       val[m] = cell_val(c[m]);
     }
@@ -386,7 +426,7 @@ __global__ void __launch_bounds__(CINV_THREADS, SSB_CINV_MINB)
   constexpr int nc = 6 * NB;
   double* Arow = dsm;             // [6][nc]
   double* red = Arow + 6 * nc;    // [CINV_THREADS / 36][36]
-  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np, p0 + Cz.C);
+  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np_own, p0 + Cz.C);
   coarse_assemble<CINV_THREADS>(G, Cz, lambda, Arow, red, p0, p1);
   const bool ok = coarse_gj_flow<CINV_THREADS, NB>(gj, tag, Arow, order, mask);
   if (ok)
@@ -396,11 +436,15 @@ __global__ void __launch_bounds__(CINV_THREADS, SSB_CINV_MINB)
 
 // NB = gridDim.x as a compile-time constant (148 = one CTA per B200 SM): every shared-memory array then has a
 // constant address and the reduction / coarse loops unroll.
-template <int NB>
+// MR: the graph is sharded over FP.world ranks (this grid = the CTAs of rank FP.rank); the cells a neighbour needs are
+// also written into its arena, the dot products are folded over the lines of every rank.  The preconditioner stays
+// rank-local (ghost keyframes carry no basis): block-Jacobi on S + exact groups + one coarse level per rank.
+template <int NB, bool MR = false>
 __global__ void __launch_bounds__(PCGF_THREADS, 1)
-    k_pcg_flow(DevGraph G, CoarseDev Cz, BarSlot* slots, FlowBufs F, FlowTabs T, double lambda, double tol2, int maxit) {
+    k_pcg_flow(DevGraph G, CoarseDev Cz, BarSlot* slots, FlowBufs F, FlowTabs T, double lambda, double tol2, int maxit, FlowPeer FP) {
   extern __shared__ __align__(16) double dsm[];
   __shared__ double s6[8], zc6[8], red6[7 * 32];
+  __shared__ double rs_sh[2 * SSB_MAX_WORLD];   // MR: (gamma, delta) sums of the other ranks' lines
   __shared__ int ovcnt[PCGF_THREADS / 32];
   constexpr int nblk = NB;
   constexpr int nc = 6 * nblk;
@@ -434,7 +478,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   const int warp = threadIdx.x >> 5;
   const int slot = lane / 6, comp = lane - 6 * slot;
   const int base_lane = 6 * slot;
-  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np, p0 + Cz.C);
+  const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np_own, p0 + Cz.C);
   const int i = p0 + warp * 5 + slot;          // my pose (pose role)
   const bool act = lane < 30 && i < p1;
   const int part = warp * nblk + blockIdx.x;   // my landmark part (landmark role), round-robin over CTAs
@@ -606,6 +650,33 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   const unsigned tb = F.tagbase;
   uint4* const my_ucell = F.ucell + 6 * (size_t)(act ? i : 0) + comp;
   double* const my_ush = u_sh + 6 * (warp * 5 + slot) + comp;
+  // MR: ranks that hold my keyframe as a ghost (the first two targets in registers, the rest from the table),
+  // and (landmark role, lanes 3..) the ranks whose keyframes see my part's landmark: lane 3 + 3 q + c pushes
+  // component c to target q
+  int upn = 0, up0i = 0;
+  uint4 *upa = nullptr, *upb = nullptr, *vpush = nullptr;
+  if constexpr (MR) {
+    if (act) {
+      up0i = FP.upush_rowptr[i];
+      upn = FP.upush_rowptr[i + 1] - up0i;
+      if (upn > 0) upa = FP.upush_cell[up0i] + comp;
+      if (upn > 1) upb = FP.upush_cell[up0i + 1] + comp;
+    }
+    if (lact && lane >= 3) {
+      const int q = (lane - 3) / 3, v0 = FP.vpush_rowptr[part];
+      if (q < FP.vpush_rowptr[part + 1] - v0) vpush = FP.vpush_cell[v0 + q] + (lane - 3 - 3 * q);
+    }
+  }
+#define SSB_FLOW_PUBLISH_U(tag_)                                                              \
+  if (act) {                                                                                  \
+    st_cell(my_ucell, uc, (tag_));                                                            \
+    *my_ush = uc;                                                                             \
+    if constexpr (MR) {                                                                       \
+      if (upn > 0) st_cell_sys(upa, uc, (tag_));                                              \
+      if (upn > 1) st_cell_sys(upb, uc, (tag_));                                              \
+      for (int q_ = 2; q_ < upn; ++q_) st_cell_sys(FP.upush_cell[up0i + q_] + comp, uc, (tag_)); \
+    }                                                                                         \
+  }
   double xc = 0.0;
   double rcomp = act ? G.g[6 * (size_t)i + comp] : 0.0;
   double uc = 0.0, pc = 0.0, sc = 0.0, cz = 0.0, cy = 0.0, wv = 0.0;
@@ -667,10 +738,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     uc = act ? _z + cz : 0.0;                                                                           \
   }
   SSB_FLOW_PRECOND()
-  if (act) {
-    st_cell(my_ucell, uc, tb + 1u);
-    *my_ush = uc;
-  }
+  SSB_FLOW_PUBLISH_U(tb + 1u)
 
   double gamma = 0.0, gamma0 = 0.0, inv_gamma_old = 1.0, inv_alpha = 1.0;
   int it = 0;
@@ -711,7 +779,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       uint4 c[6];
 #pragma unroll
       for (int m = 0; m < 6; ++m)
-        if (uoff[m] >= 0) c[m] = ld_cell(F.ucell + uoff[m]);
+        if (uoff[m] >= 0) c[m] = ld_cell_t<MR>(F.ucell + uoff[m]);
       double HLc[18];
 #pragma unroll
       for (int q = 0; q < 9; ++q) {
@@ -720,7 +788,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
         HLc[2 * q + 1] = h.y;
       }
       double uv[6];
-      cells_wait<6>(F.ucell, uoff, c, tg, uv);
+      cells_wait<6, MR>(F.ucell, uoff, c, tg, uv);
 #pragma unroll
       for (int m = 0; m < 6; ++m) {   // uv = 0 and HLc = 0 for unused items
         a[0] += HLc[3 * m] * uv[m];
@@ -735,10 +803,10 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
           oc[m] = -1;
           if (idx < 6 * nov) {
             oc[m] = ov_cell[6 * ovbase + idx];
-            c[m] = ld_cell(F.ucell + oc[m]);
+            c[m] = ld_cell_t<MR>(F.ucell + oc[m]);
           }
         }
-        cells_wait<6>(F.ucell, oc, c, tg, uv);
+        cells_wait<6, MR>(F.ucell, oc, c, tg, uv);
 #pragma unroll
         for (int m = 0; m < 6; ++m)
           if (oc[m] >= 0) {
@@ -752,7 +820,12 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       const double a0 = __shfl_sync(0xffffffffu, rsum, 0);
       const double a1 = __shfl_sync(0xffffffffu, rsum, 8);
       const double a2 = __shfl_sync(0xffffffffu, rsum, 16);
-      if (lane < 3) st_cell(F.vcell + 3 * (size_t)part + lane, Wr[0] * a0 + Wr[1] * a1 + Wr[2] * a2, tg);
+      const double vval = Wr[0] * a0 + Wr[1] * a1 + Wr[2] * a2;   // valid in lanes 0..2
+      if (lane < 3) st_cell(F.vcell + 3 * (size_t)part + lane, vval, tg);
+      if constexpr (MR) {
+        const double vv = __shfl_sync(0xffffffffu, vval, lane >= 3 ? (lane - 3) % 3 : 0);
+        if (vpush) st_cell_sys(vpush, vv, tg);
+      }
     }
     SSB_FTICK(0);
     // ---- stage u of external neighbours and v of my poses' landmarks into shared memory ----------------
@@ -765,20 +838,21 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
         sc_[m] = -1;
         if (q < nstage) {
           sc_[m] = stage_src[q];
-          c[m] = ld_cell(F.ucell + (sc_[m] & 0xffffff));
+          c[m] = ld_cell_t<MR>(F.ucell + (sc_[m] & 0xffffff));
         }
       }
       int so[3];
       double sv[3];
 #pragma unroll
       for (int m = 0; m < 3; ++m) so[m] = sc_[m] >= 0 ? (sc_[m] & 0xffffff) : -1;
-      cells_wait<3>(F.ucell, so, c, tg, sv);
+      cells_wait<3, MR>(F.ucell, so, c, tg, sv);
 #pragma unroll
       for (int m = 0; m < 3; ++m)
         if (sc_[m] >= 0) {
           const int np = sc_[m] >> 24;   // 0 for u cells, >= 1 for v cells (parts of one landmark are adjacent)
           double val = sv[m];
-          for (int j = 1; j < np; ++j) val += cell_wait(F.ucell + so[m] + 3 * j, ld_cell(F.ucell + so[m] + 3 * j), tg);
+          for (int j = 1; j < np; ++j)
+            val += cell_wait<MR>(F.ucell + so[m] + 3 * j, ld_cell_t<MR>(F.ucell + so[m] + 3 * j), tg);
           u_sh[6 * PCGW_POSES + threadIdx.x + PCGF_THREADS * m] = val;
         }
     }
@@ -820,15 +894,27 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     }
     SSB_FTICK(2);
     __syncthreads();
-    if (warp == 0 && lane < 8) {
+    const int mr_world = MR ? FP.world : 1, mr_rank = MR ? FP.rank : 0;
+    if (warp == 0) {
       double t = 0.0;
+      if (lane < 8) {
 #pragma unroll
-      for (int ww = 0; ww < PCGF_THREADS / 32; ++ww) t += scratch8[8 * ww + lane];
-      st_cell(F.lines + ((size_t)(tg & 1u) * nblk + blockIdx.x) * 8 + lane, t, tg);
+        for (int ww = 0; ww < PCGF_THREADS / 32; ++ww) t += scratch8[8 * ww + lane];
+        st_cell(F.lines + (((size_t)(tg & 1u) * mr_world + mr_rank) * nblk + blockIdx.x) * 8 + lane, t, tg);
+      }
+      if constexpr (MR) {
+        // the two dot-product partials also go into the same line slot of every other rank: lane 8 + 2 j + k
+        const double tv = __shfl_sync(0xffffffffu, t, lane >= 8 ? ((lane - 8) & 1) : 0);
+        const int j = (lane - 8) >> 1;
+        if (lane >= 8 && j < mr_world - 1) {
+          const int peer = j < mr_rank ? j : j + 1;
+          st_cell_sys(FP.lines[peer] + (((size_t)(tg & 1u) * mr_world + mr_rank) * nblk + blockIdx.x) * 8 + ((lane - 8) & 1), tv, tg);
+        }
+      }
     }
     {
       // pull all-gather of the nblk lines: thread q reads cell q (coalesced), value k of line q/8
-      const uint4* L = F.lines + (size_t)(tg & 1u) * nblk * 8;
+      const uint4* L = F.lines + ((size_t)(tg & 1u) * mr_world + mr_rank) * nblk * 8;
       uint4 c[3];
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
@@ -865,6 +951,34 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
           wc[6 * ln + k - 2] = val;
       }
     }
+    if constexpr (MR) {
+      // the other ranks: two warps per rank (gamma, delta) fold its nblk partials straight from the cells, with the
+      // same summation tree that rank uses for its own lines => every CTA of every rank gets identical bits
+      static_assert(PCGF_THREADS / 32 >= 2 * (SSB_MAX_WORLD - 1), "two warps per remote rank");
+      constexpr int RM = (NB + 31) / 32;
+      const int j = warp >> 1, kq = warp & 1;
+      if (j < mr_world - 1) {
+        const int peer = j < mr_rank ? j : j + 1;
+        const uint4* Lr = F.lines + ((size_t)(tg & 1u) * mr_world + peer) * nblk * 8;
+        uint4 c[RM];
+        int ro[RM];
+        double rv[RM];
+#pragma unroll
+        for (int m = 0; m < RM; ++m) {
+          const int cta = lane + 32 * m;
+          ro[m] = cta < nblk ? 8 * cta + kq : -1;
+          if (ro[m] >= 0) c[m] = ld_cell_sys(Lr + ro[m]);
+        }
+        cells_wait<RM, true>(Lr, ro, c, tg, rv);
+        double t = 0.0;
+#pragma unroll
+        for (int m = 0; m < RM; ++m)
+          if (ro[m] >= 0) t += rv[m];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) rs_sh[2 * peer + kq] = t;
+      }
+    }
     SSB_FTICK(3);
     __syncthreads();
     SSB_FTICK(4);
@@ -882,6 +996,15 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       }
       gamma = tg_;
       delta = td_;
+      if constexpr (MR) {   // rank order, identical on every rank
+        double g2 = 0.0, d2 = 0.0;
+        for (int r = 0; r < mr_world; ++r) {
+          g2 += r == mr_rank ? tg_ : rs_sh[2 * r];
+          d2 += r == mr_rank ? td_ : rs_sh[2 * r + 1];
+        }
+        gamma = g2;
+        delta = d2;
+      }
     }
     if (use_coarse) {
       if (warp < 12) {  // two warps per row of A_c^-1
@@ -929,14 +1052,16 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       cz -= alpha * cy;
     }
     SSB_FLOW_PRECOND()
-    if (act) {
-      st_cell(my_ucell, uc, tg + 1u);
-      *my_ush = uc;
-    }
+    SSB_FLOW_PUBLISH_U(tg + 1u)
     SSB_FTICK(6);
   }
 #undef SSB_FLOW_PRECOND
-  if (act) G.x[6 * (size_t)i + comp] = xc;
+#undef SSB_FLOW_PUBLISH_U
+  if (act) {
+    G.x[6 * (size_t)i + comp] = xc;
+    if constexpr (MR)   // the solution of a boundary keyframe goes to every rank that updates it as a ghost
+      for (int q = 0; q < upn; ++q) st_relaxed_sys_f64(FP.upush_x[up0i + q] + comp, xc);
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     G.iscalars[0] = it;
     G.iscalars[1] = status;

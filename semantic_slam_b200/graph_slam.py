@@ -211,3 +211,14 @@ class GraphSLAM:
 
     def attach_comm(self, rank, world, unique_id: bytes):
         check(self._L.ssb_graph_attach_comm(self._h, rank, world, unique_id), "attach_comm")
+
+    def attach_local(self, rank: int, world: int, group_key: str, cta_per_rank: int = 0):
+        """Shard this graph with `world - 1` other handles driven by host threads of this process (one handle per
+        thread; every handle must replay the same add_* calls).  cta_per_rank = 74 / 37: the shards share one GPU."""
+        check(self._L.ssb_graph_attach_local(self._h, rank, world, group_key.encode(), cta_per_rank), "attach_local")
+
+    def shard_info(self, world: int, rank: int):
+        """(own keyframe range, local keyframes incl. ghosts, owned landmarks, touched landmarks, local edges)."""
+        out = np.zeros(6, dtype=np.int32)
+        check(self._L.ssb_graph_shard_info(self._h, world, rank, out.ctypes.data_as(ip)), "shard_info")
+        return tuple(int(v) for v in out)

@@ -168,6 +168,13 @@ int ssb_graph_attach_comm(ssb_graph* g, int rank, int world, const unsigned char
 int ssb_graph_attach_local(ssb_graph* g, int rank, int world, const char* group_key, int cta_per_rank);
 int ssb_shard_ranges(int n_poses, int n_landmarks, int world, int rank, int out4[4]);
 int ssb_graph_shard_info(ssb_graph* g, int world, int rank, int out6[6]);
+/* The same plan from bare index lists (host-only, no GPU, no handle).  pl_pose / pl_lm: keyframe and landmark index
+ * (within their kind) of every pose-landmark edge; pp_i / pp_j: keyframes of every pose-pose edge.  For `rank`:
+ * out[0..1] own keyframe range, out[2] local keyframes, out[3] owned / out[4] touched landmarks, out[5] local
+ * pose-landmark edges, out[6] u pushes (keyframe, rank) and out[7] v pushes (landmark part, rank) per PCG iteration.
+ * ghost_out (NULL or n_poses ints): the ghost keyframes; push_to (NULL or world ints): own keyframes pushed per rank. */
+int ssb_shard_plan(int n_poses, int n_landmarks, const int* pl_pose, const int* pl_lm, int n_pl, const int* pp_i, const int* pp_j,
+                   int n_pp, int world, int rank, int out8[8], int* ghost_out, int* push_to);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Path (2): planar_segmentation RANSAC plane fit on bbox-cropped depth clouds                  */

@@ -57,7 +57,7 @@ SYMBOLS = [
     "ssb_graph_prepare", "ssb_graph_optimize", "ssb_graph_optimize_resident", "ssb_graph_get_history",
     "ssb_graph_landmark_marginals", "ssb_graph_save_g2o", "ssb_graph_load_g2o", "ssb_graph_edge_linearize",
     "ssb_graph_solve_once", "ssb_comm_unique_id", "ssb_graph_attach_comm", "ssb_graph_attach_local", "ssb_shard_ranges",
-    "ssb_graph_shard_info", "ssb_ransac_default_opts",
+    "ssb_graph_shard_info", "ssb_shard_plan", "ssb_ransac_default_opts",
     "ssb_ransac_create", "ssb_ransac_destroy", "ssb_ransac_plane_batch", "ssb_ransac_upload",
     "ssb_ransac_run_resident", "ssb_ransac_fetch", "ssb_ransac_stream", "ssb_ransac_launch_count", "ssb_ransac_timing", "ssb_crop_bbox",
     "ssb_segment_planar_surfaces", "ssb_assoc_default_opts", "ssb_assoc_create", "ssb_assoc_destroy", "ssb_assoc_find_matches",
@@ -123,6 +123,7 @@ def lib():
     L.ssb_shard_ranges.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip]
     L.ssb_graph_attach_local.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_int]
     L.ssb_graph_shard_info.argtypes = [vp, C.c_int, C.c_int, ip]
+    L.ssb_shard_plan.argtypes = [C.c_int, C.c_int, ip, ip, C.c_int, ip, ip, C.c_int, C.c_int, C.c_int, ip, ip, ip]
     L.ssb_ransac_default_opts.argtypes = [C.POINTER(RansacOpts)]
     L.ssb_ransac_create.argtypes = [C.c_int]
     L.ssb_ransac_create.restype = vp

@@ -1589,8 +1589,18 @@ static ArenaLayout arena_layout(int world, int nb, int NpL, int NlL, int ElL, in
   return L;
 }
 
+struct EdgeIdx {
+  int a, b;
+};
+static void build_plan_raw(int Np, int Nl, const std::vector<EdgeIdx>& pl, const std::vector<EdgeIdx>& pp, int world, int nb, ShardPlan& P);
 static void build_plan(const ssb_graph* g, int world, int nb, ShardPlan& P) {
-  const int Np = (int)g->poses.size(), Nl = (int)(g->lms.size() / 4);
+  std::vector<EdgeIdx> pl(g->pl.size()), pp(g->pp.size());
+  for (size_t k = 0; k < g->pl.size(); ++k) pl[k] = {g->pl[k].p, g->pl[k].l};
+  for (size_t k = 0; k < g->pp.size(); ++k) pp[k] = {g->pp[k].i, g->pp[k].j};
+  build_plan_raw((int)g->poses.size(), (int)(g->lms.size() / 4), pl, pp, world, nb, P);
+}
+// pl: (keyframe, landmark) index pairs; pp: (keyframe i, keyframe j) index pairs — indices within their kind
+static void build_plan_raw(int Np, int Nl, const std::vector<EdgeIdx>& pl, const std::vector<EdgeIdx>& pp, int world, int nb, ShardPlan& P) {
   P.world = world;
   P.nb = nb;
   P.Np = Np;
@@ -1604,24 +1614,24 @@ static void build_plan(const ssb_graph* g, int world, int nb, ShardPlan& P) {
   }
   P.lm_deg.assign(Nl, 0);
   std::vector<int> first(Nl, Np);
-  for (auto& e : g->pl) {
-    P.lm_deg[e.l]++;
-    first[e.l] = std::min(first[e.l], e.p);
+  for (auto& e : pl) {
+    P.lm_deg[e.b]++;
+    first[e.b] = std::min(first[e.b], e.a);
   }
   P.lm_owner.assign(Nl, 0);
   for (int l = 0; l < Nl; ++l) P.lm_owner[l] = first[l] < Np ? rank_of(first[l]) : 0;
   // touched[r][l]
   std::vector<std::vector<unsigned char>> touched(world, std::vector<unsigned char>(std::max(Nl, 1), 0));
-  for (auto& e : g->pl) touched[rank_of(e.p)][e.l] = 1;
+  for (auto& e : pl) touched[rank_of(e.a)][e.b] = 1;
   for (int l = 0; l < Nl; ++l) touched[P.lm_owner[l]][l] = 1;   // (a landmark without edges stays with rank 0)
   for (int r = 0; r < world; ++r) {
     RankLocal& R = P.R[r];
     std::vector<unsigned char> need(std::max(Np, 1), 0);
-    for (auto& e : g->pl)
-      if (touched[r][e.l]) need[e.p] = 1;
-    for (auto& e : g->pp) {
-      const bool io = e.i >= R.ps && e.i < R.pe, jo = e.j >= R.ps && e.j < R.pe;
-      if (io || jo) need[e.i] = need[e.j] = 1;
+    for (auto& e : pl)
+      if (touched[r][e.b]) need[e.a] = 1;
+    for (auto& e : pp) {
+      const bool io = e.a >= R.ps && e.a < R.pe, jo = e.b >= R.ps && e.b < R.pe;
+      if (io || jo) need[e.a] = need[e.b] = 1;
     }
     R.l2g_pose.clear();
     for (int p = R.ps; p < R.pe; ++p) R.l2g_pose.push_back(p);
@@ -2757,6 +2767,55 @@ int ssb_shard_ranges(int n_poses, int n_landmarks, int world, int rank, int out4
   out4[0] = std::min(n_poses, rank * per);
   out4[1] = rank == world - 1 ? n_poses : std::min(n_poses, (rank + 1) * per);
   out4[2] = out4[3] = 0;
+  return SSB_OK;
+}
+// The sharding plan from bare index lists (host-only, no GPU, no handle): what ssb_graph_prepare derives on every rank.
+// pl_pose / pl_lm: keyframe and landmark index of every pose-landmark edge; pp_i / pp_j: keyframes of every pose-pose
+// edge.  For `rank`: out[0..1] own keyframe range, out[2] local keyframes, out[3] owned / out[4] touched landmarks,
+// out[5] local pose-landmark edges, out[6] (keyframe, rank) pushes of u per PCG iteration, out[7] (landmark part, rank)
+// pushes of v.  ghost_out (may be NULL, capacity n_poses): global indices of the ghost keyframes, returns their count in
+// out[2] - (out[1] - out[0]).  push_to (may be NULL, world ints): number of own keyframes pushed to every rank.
+int ssb_shard_plan(int n_poses, int n_landmarks, const int* pl_pose, const int* pl_lm, int n_pl, const int* pp_i, const int* pp_j,
+                   int n_pp, int world, int rank, int out8[8], int* ghost_out, int* push_to) {
+  if (world < 1 || world > SSB_MAX_WORLD || rank < 0 || rank >= world || !out8 || n_poses < 0 || n_landmarks < 0 || n_pl < 0 || n_pp < 0)
+    return SSB_ERR_INVALID;
+  std::vector<EdgeIdx> pl(n_pl), pp(n_pp);
+  for (int k = 0; k < n_pl; ++k) {
+    if (pl_pose[k] < 0 || pl_pose[k] >= n_poses || pl_lm[k] < 0 || pl_lm[k] >= n_landmarks) return SSB_ERR_INVALID;
+    pl[k] = {pl_pose[k], pl_lm[k]};
+  }
+  for (int k = 0; k < n_pp; ++k) {
+    if (pp_i[k] < 0 || pp_i[k] >= n_poses || pp_j[k] < 0 || pp_j[k] >= n_poses) return SSB_ERR_INVALID;
+    pp[k] = {pp_i[k], pp_j[k]};
+  }
+  ShardPlan plan;
+  build_plan_raw(n_poses, n_landmarks, pl, pp, world, 148, plan);
+  const RankLocal& R = plan.R[rank];
+  out8[0] = R.ps;
+  out8[1] = R.pe;
+  out8[2] = (int)R.l2g_pose.size();
+  out8[3] = R.n_owned_lm;
+  out8[4] = (int)R.l2g_lm.size();
+  int el = 0;
+  for (auto& e : pl)
+    if (R.g2l_lm[e.b] >= 0) ++el;
+  out8[5] = el;
+  int upush = 0, vpush = 0;
+  if (push_to)
+    for (int r = 0; r < world; ++r) push_to[r] = 0;
+  for (int gp = R.ps; gp < R.pe; ++gp)
+    for (int r = 0; r < world; ++r)
+      if (r != rank && plan.R[r].g2l_pose[gp] >= 0) {
+        ++upush;
+        if (push_to) push_to[r]++;
+      }
+  for (int k = 0; k < R.n_owned_lm; ++k)
+    for (int r = 0; r < world; ++r)
+      if (r != rank && plan.R[r].g2l_lm[R.l2g_lm[k]] >= 0) vpush += R.partbase[k + 1] - R.partbase[k];
+  out8[6] = upush;
+  out8[7] = vpush;
+  if (ghost_out)
+    for (size_t k = R.pe - R.ps; k < R.l2g_pose.size(); ++k) ghost_out[k - (R.pe - R.ps)] = R.l2g_pose[k];
   return SSB_OK;
 }
 // the sharding plan of the current graph as every rank computes it (host-only): for rank `rank`, out[0..1] = own

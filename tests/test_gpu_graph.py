@@ -4,6 +4,7 @@ import pytest
 
 import oracle
 from semantic_slam_b200 import GraphSLAM, synth
+from parity import assert_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -101,8 +102,7 @@ def test_lm_trajectory_cfg1(precond, generic):
     P, X = g.get_all(spec.n_poses, spec.n_landmarks)
     Po, Xo = o.get_all(spec.n_poses, spec.n_landmarks)
     # north_star bar: parameters within 1e-5 relative after the same LM iteration count
-    assert np.abs(P - Po).max() <= 1e-5 * max(1.0, np.abs(Po).max())
-    assert np.abs(X - Xo).max() <= 1e-5 * max(1.0, np.abs(Xo).max())
+    assert_parity(P, X, Po, Xo)
 
 
 def test_landmark_marginals_match_oracle():
@@ -151,8 +151,7 @@ def test_reject_path_and_termination():
     assert g.terminated and o.terminated
     P, X = g.get_all(spec.n_poses, spec.n_landmarks)
     Po, Xo = o.get_all(spec.n_poses, spec.n_landmarks)
-    assert np.abs(P - Po).max() <= 1e-5 * max(1.0, np.abs(Po).max())
-    assert np.abs(X - Xo).max() <= 1e-5 * max(1.0, np.abs(Xo).max())
+    assert_parity(P, X, Po, Xo)
     assert abs(g.stats["chi2_final"] - o.history[-1, 1]) <= 1e-8 * o.history[-1, 1]
 
 
@@ -183,8 +182,7 @@ def test_incremental_growth():
     assert g.optimize(4) and o.optimize(4)
     P, X = g.get_all(spec.n_poses, spec.n_landmarks)
     Po, Xo = o.get_all(spec.n_poses, spec.n_landmarks)
-    assert np.abs(P - Po).max() <= 1e-5 * max(1.0, np.abs(Po).max())
-    assert np.abs(X - Xo).max() <= 1e-5 * max(1.0, np.abs(Xo).max())
+    assert_parity(P, X, Po, Xo)
 
 
 def test_coarse_level_reduces_pcg_iterations():
@@ -257,8 +255,7 @@ def test_cfg2_parity_at_bench_tolerance():
     assert np.allclose(g.history[:, 1], hist[:20, 1], rtol=1e-5)
     assert abs(g.history[-1, 1] - hist[19, 1]) <= 1e-9 * hist[19, 1]
     P, X = g.get_all(spec.n_poses, spec.n_landmarks)
-    assert np.abs(P - gold["poses"]).max() <= 1e-5 * max(1.0, np.abs(gold["poses"]).max())
-    assert np.abs(X - gold["landmarks"]).max() <= 1e-5 * max(1.0, np.abs(gold["landmarks"]).max())
+    assert_parity(P, X, gold["poses"], gold["landmarks"])
 
 
 # ---- plane landmarks: VertexPlane / EdgeSE3Plane (dormant in the reference) -------------------
@@ -383,8 +380,7 @@ def test_pose_pose_loop_closures_inside_groups():
     assert g.optimize(5) and o.optimize(5)
     P, X = g.get_all(spec.n_poses, spec.n_landmarks)
     Po, Xo = o.get_all(spec.n_poses, spec.n_landmarks)
-    assert np.abs(P - Po).max() <= 1e-5 * max(1.0, np.abs(Po).max())
-    assert np.abs(X - Xo).max() <= 1e-5 * max(1.0, np.abs(Xo).max())
+    assert_parity(P, X, Po, Xo)
     assert abs(g.stats["chi2_final"] - o.history[-1, 1]) <= 1e-8 * o.history[-1, 1]
 
 
@@ -409,8 +405,7 @@ def test_edges_added_out_of_order():
     assert g.optimize(6) and o.optimize(6)
     P, X = g.get_all(spec.n_poses, spec.n_landmarks)
     Po, Xo = o.get_all(spec.n_poses, spec.n_landmarks)
-    assert np.abs(P - Po).max() <= 1e-5 * max(1.0, np.abs(Po).max())
-    assert np.abs(X - Xo).max() <= 1e-5 * max(1.0, np.abs(Xo).max())
+    assert_parity(P, X, Po, Xo)
     assert abs(g.stats["chi2_final"] - o.history[-1, 1]) <= 1e-8 * o.history[-1, 1]
     # and the same graph in creation order lands on the same optimum
     g2 = GraphSLAM(preconditioner=3)

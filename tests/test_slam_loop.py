@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import oracle
+from parity import point_error, pose_errors
 from oracle.association import OracleDataAssociation
 from semantic_slam_b200 import synth
 from semantic_slam_b200.semantic_graph_slam import SemanticGraphSLAM, matrix2vector
@@ -48,8 +49,9 @@ def test_loop_parity_gpu_vs_oracle(use_maha, strict):
     assert len(a.landmark_nodes_) == len(b.landmark_nodes_) >= 8
     for ka, kb in zip(a.keyframes_, b.keyframes_):
         Ta, Tb = a.graph_slam_.get_se3(ka["node"]), b.graph_slam_.get_se3(kb["node"])
-        assert np.abs(Ta - Tb).max() <= 1e-5 * max(1.0, np.abs(Tb).max())
+        rot, tr = pose_errors(Ta, Tb)
+        assert rot <= 1e-5 and tr <= 1e-5, (rot, tr)
     for lid in a.landmark_nodes_:
         pa = a.graph_slam_.get_point_xyz(a.landmark_nodes_[lid])
         pb = b.graph_slam_.get_point_xyz(b.landmark_nodes_[lid])
-        assert np.abs(pa - pb).max() <= 1e-5 * max(1.0, np.abs(pb).max())
+        assert point_error(pa, pb) <= 1e-5

@@ -34,7 +34,7 @@ if which in ("all", "cfg5"):
     its = 0
     marks = {}
     for k in range(n_kf):
-        slam.add_keyframe(stream.odom[k], stream.detections[k])
+        slam.feed(stream.odom[k], stream.detections[k])
         slam.run()
         if g.stats is not None and g.num_edges() >= 10:
             t_opt += g.stats["ms_total"] * 1e-3

@@ -9,7 +9,7 @@ a = DataAssociation(use_maha_dist=False, use_eq_dist=True, eq_dist_thres=1.5, la
 slam = SemanticGraphSLAM(g, a, stream.info6, cam_angle=stream.cam_angle, max_iterations=1024)
 t0 = time.time()
 for k in range(n_kf):
-    slam.add_keyframe(stream.odom[k], stream.detections[k])
+    slam.feed(stream.odom[k], stream.detections[k])
     t = time.perf_counter()
     slam.run()
     dt = time.perf_counter() - t

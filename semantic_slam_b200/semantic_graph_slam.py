@@ -36,6 +36,23 @@ def _inv(A):
     return T
 
 
+def _rotvec(R):
+    c = np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)
+    th = np.arccos(c)
+    if th < 1e-12:
+        return np.zeros(3)
+    return th / (2.0 * np.sin(th)) * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+
+
+def _rot(w):
+    th = np.linalg.norm(w)
+    if th < 1e-12:
+        return np.eye(3)
+    k = w / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
 class SemanticGraphSLAM:
     max_keyframes_per_update = 10          # semantic_graph_slam.cpp:18
 
@@ -55,14 +72,39 @@ class SemanticGraphSLAM:
         self.first_key_added_ = False
         self.association_log = []            # per keyframe: [(landmark id, is_new)] — the parity target
 
-    # semantic_graph_slam::VIOCallback  :238-290 (every pose handed in is a keyframe)
-    def add_keyframe(self, odom34, detections):
+    # semantic_graph_slam::VIOCallback  :234-287, the branch taken when the keyframe gate REJECTS the pose (:239-247,
+    # :253-261): robot_pose_ is dead-reckoned by the odometry increment, nothing is queued
+    def add_odometry(self, odom34):
         odom34 = np.asarray(odom34, dtype=np.float64)
         if self.first_key_added_ and self.prev_odom_ is not None:
             self.robot_pose_ = _mul(self.robot_pose_, _mul(_inv(self.prev_odom_), odom34))
+        self.prev_odom_ = odom34
+
+    # ... and the branch taken when the pose becomes a keyframe (:264-284): the keyframe stores robot_pose_ AS IT IS —
+    # the increment of this very pose is not applied — and only prev_odom_ advances.  With a stream in
+    # which every pose is a keyframe the association therefore runs on the last optimised pose (:94), one step behind.
+    def add_keyframe(self, odom34, detections):
+        odom34 = np.asarray(odom34, dtype=np.float64)
         self.keyframe_queue_.append({"odom": odom34, "robot_pose": self.robot_pose_.copy(), "obj_info": list(detections),
                                      "node": None})
         self.prev_odom_ = odom34
+
+    def feed(self, odom34, detections, substeps: int = 4):
+        """A VIO stream running at `substeps` x the keyframe rate: the poses between the previous keyframe and this one
+        (interpolated here) are rejected by the keyframe gate and only dead-reckon robot_pose_ (add_odometry); the last
+        one becomes the keyframe.  This is the call pattern of the reference's node (VIOCallback per odometry message)."""
+        odom34 = np.asarray(odom34, dtype=np.float64)
+        if self.prev_odom_ is not None and substeps > 1:
+            A = self.prev_odom_
+            rel = _mul(_inv(A), odom34)
+            w = _rotvec(rel[:, :3])
+            for k in range(1, substeps):
+                t = k / substeps
+                step = np.zeros((3, 4))
+                step[:, :3] = _rot(w * t)
+                step[:, 3] = rel[:, 3] * t
+                self.add_odometry(_mul(A, step))
+        self.add_keyframe(odom34, detections)
 
     # semantic_graph_slam::empty_keyframe_queue  :104-152
     def _empty_keyframe_queue(self):

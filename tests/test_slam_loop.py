@@ -17,7 +17,7 @@ def _drive(graph, assoc, stream, max_iterations=30, use_maha=False):
     slam = SemanticGraphSLAM(graph, assoc, stream.info6, cam_angle=stream.cam_angle, use_maha_dist=use_maha,
                              max_iterations=max_iterations)
     for k in range(stream.odom.shape[0]):
-        slam.add_keyframe(stream.odom[k], stream.detections[k])
+        slam.feed(stream.odom[k], stream.detections[k])
         assert slam.run()
     return slam
 

@@ -8,9 +8,11 @@ import numpy as np
 from semantic_slam_b200 import GraphSLAM, synth
 
 
-def run_sharded(spec, world, iters, virtual=True, preconditioner=3, pcg_tol=1e-8, key="g", timeout=300, resident_repeat=0):
+def run_sharded(spec, world, iters, virtual=True, preconditioner=3, pcg_tol=1e-8, key="g", timeout=300, resident_repeat=0,
+                force_generic=False):
     cta = {1: 0, 2: 74, 4: 37}[world] if virtual else 0
-    graphs = [GraphSLAM(device=0 if virtual else r, preconditioner=preconditioner, pcg_tol=pcg_tol) for r in range(world)]
+    graphs = [GraphSLAM(device=0 if virtual else r, preconditioner=preconditioner, pcg_tol=pcg_tol, force_generic=force_generic)
+              for r in range(world)]
     out = [None] * world
     err = [None] * world
 
@@ -59,10 +61,12 @@ if __name__ == "__main__":
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--repeat", type=int, default=0)
     ap.add_argument("--oracle", action="store_true")
+    ap.add_argument("--generic", action="store_true", help="force the streaming PCG kernel")
     a = ap.parse_args()
     spec = synth.make_config_graph(a.config)
-    res = run_sharded(spec, a.world, a.iters, virtual=a.virtual, preconditioner=a.precond, pcg_tol=a.tol, resident_repeat=a.repeat)
-    g1 = GraphSLAM(preconditioner=a.precond, pcg_tol=a.tol)
+    res = run_sharded(spec, a.world, a.iters, virtual=a.virtual, preconditioner=a.precond, pcg_tol=a.tol, resident_repeat=a.repeat,
+                      force_generic=a.generic, timeout=900)
+    g1 = GraphSLAM(preconditioner=a.precond, pcg_tol=a.tol, force_generic=a.generic)
     synth.load_graph(g1, spec)
     g1.optimize(a.iters)
     P1, X1 = g1.get_all(spec.n_poses, spec.n_landmarks)

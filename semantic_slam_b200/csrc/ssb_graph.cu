@@ -224,6 +224,9 @@ struct MrCtx {                        // member of the INNER (shard) handle
   DBuf<uint4*> d_upush_cell, d_vpush_cell;
   DBuf<double*> d_upush_x;
   FlowPeer FP{};
+  StreamPeer SP{};
+  DBuf<double*> d_zpush_z, d_svpush_v;
+  DBuf<int> d_svpush_rowptr;
   // chi2 over the edges this rank owns (a shared edge is counted once)
   DBuf<PLEdge> d_pl_own;
   DBuf<PPEdge> d_pp_own;
@@ -426,13 +429,14 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
   g->pcg_grid = std::min(g->num_sms, PCG_THREADS);  // one persistent CTA per SM
   const bool shard_handle = g->opts.reserved[2] > 0;   // internal: a shard of a larger graph, reserved[2] = CTAs of this rank
   if (shard_handle) g->pcg_grid = std::min(g->pcg_grid, g->opts.reserved[2]);
-  g->pcg_smem = (size_t)(PCG_THREADS + 14 * 6 * g->pcg_grid + (PCG_THREADS / 36) * 36) * sizeof(double);
+  g->pcg_smem = (size_t)(PCG_PART + 14 * 6 * g->pcg_grid + (PCG_THREADS / 36) * 36) * sizeof(double);
   g->allow_fast = g->opts.reserved[0] == 0;
   g->use_flow = flow_kernel(g->pcg_grid, shard_handle) != nullptr;
   g->pcgw_smem = pcg_flow_smem_doubles(g->pcg_grid) * sizeof(double);
   int nb = 0;
-  e = cudaFuncSetAttribute(k_pcg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_smem);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg, PCG_THREADS, g->pcg_smem);
+  void* sk = shard_handle ? (void*)k_pcg<true> : (void*)k_pcg<false>;
+  e = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_smem);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sk, PCG_THREADS, g->pcg_smem);
   if (e != cudaSuccess || nb < 1) {
     set_error("k_pcg cannot be made resident (occupancy %d, %zu B smem): %s", nb, g->pcg_smem, cudaGetErrorString(e));
     delete g;
@@ -1491,7 +1495,9 @@ static int launch_pcg(ssb_graph* g, double lambda) {
   }
   BarSlot* slots = g->d_slots.p;
   SSB_CUDA_CHECK(cudaMemsetAsync(slots, 0, ((size_t)2 * g->pcg_grid + 1) * sizeof(BarSlot), s));
-  void* args[] = {(void*)&G, (void*)&g->Cz, (void*)&slots, (void*)&lambda, (void*)&tol2, (void*)&maxit};
+  StreamPeer SP{};
+  if (g->mr) SP = g->mr->SP;
+  void* args[] = {(void*)&G, (void*)&g->Cz, (void*)&slots, (void*)&lambda, (void*)&tol2, (void*)&maxit, (void*)&SP};
   if (g->ev_used + 2 > g->ev_pool.size()) {
     for (int k = 0; k < 64; ++k) {
       cudaEvent_t e;
@@ -1526,10 +1532,16 @@ static int launch_pcg(ssb_graph* g, double lambda) {
     } else
       SSB_CUDA_CHECK(cudaLaunchCooperativeKernel(flow_kernel(g->pcg_grid, g->mr != nullptr), dim3(g->pcg_grid), dim3(PCGF_THREADS), fargs, g->pcgw_smem, s));
   } else if (g->mr) {
-    set_error("sharded graph: a shard does not fit the on-chip PCG kernel (<= %d keyframes per CTA); the streaming kernel is single-rank only", 5 * (PCGF_THREADS / 32));
-    return SSB_ERR_INVALID;
+    // the cross-rank barrier slots of the streaming kernel start every launch from zero on every rank
+    SSB_CUDA_CHECK(cudaMemsetAsync(g->mr->arena + g->mr->lay[g->mr->rank].slots, 0, ((size_t)2 * g->mr->world * g->pcg_grid + 1) * sizeof(BarSlot), s));
+    SSB_TRY(peer_exchange(g, false));
+    if (g->pcg_grid < g->num_sms) {   // shards sharing one GPU: see the data-flow kernel above
+      SSB_CUDA_CHECK(cudaLaunchKernel((void*)k_pcg<true>, dim3(g->pcg_grid), dim3(PCG_THREADS), args, g->pcg_smem, s));
+      SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+    } else
+      SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg<true>, dim3(g->pcg_grid), dim3(PCG_THREADS), args, g->pcg_smem, s));
   } else
-    SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(g->pcg_grid), dim3(PCG_THREADS), args, g->pcg_smem, s));
+    SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_pcg<false>, dim3(g->pcg_grid), dim3(PCG_THREADS), args, g->pcg_smem, s));
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_pool[g->ev_used + 1], s));
   g->ev_used += 2;
   g->launches++;
@@ -1961,11 +1973,14 @@ static int prepare_sharded(ssb_graph* g) {
     in->d_ucell.set_view(mr->arena + L.cells, L.n_cells);
     in->d_lines.set_view(mr->arena + L.lines, L.n_lines);
     in->d_x.set_view(mr->arena + L.x, L.n_x);
+    in->d_z.set_view(mr->arena + L.z, L.n_x);
+    in->d_v.set_view(mr->arena + L.v, L.n_v);
     // ---- push tables ----
     {
       std::vector<int> urow(mr->n_own + 1, 0);
       std::vector<uint4*> ucellp;
-      std::vector<double*> uxp;
+      std::vector<double*> uxp, uzp, svp;
+      std::vector<int> svrow(R.n_owned_lm + 1, 0);
       for (int k = 0; k < mr->n_own; ++k) {
         const int gp = R.l2g_pose[k];
         for (int r = 0; r < world; ++r) {
@@ -1974,6 +1989,7 @@ static int prepare_sharded(ssb_graph* g) {
           if (li < 0) continue;
           ucellp.push_back((uint4*)(mr->peer_base[r] + mr->lay[r].cells) + 6 * (size_t)li);
           uxp.push_back((double*)(mr->peer_base[r] + mr->lay[r].x) + 6 * (size_t)li);
+          uzp.push_back((double*)(mr->peer_base[r] + mr->lay[r].z) + 6 * (size_t)li);
         }
         urow[k + 1] = (int)ucellp.size();
       }
@@ -1982,6 +1998,12 @@ static int prepare_sharded(ssb_graph* g) {
       std::vector<uint4*> vcellp;
       for (int k = 0; k < R.n_owned_lm; ++k) {
         const int gl = R.l2g_lm[k];
+        for (int r = 0; r < world; ++r) {
+          if (r == rank) continue;
+          const int ll = plan.R[r].g2l_lm[gl];
+          if (ll >= 0) svp.push_back((double*)(mr->peer_base[r] + mr->lay[r].v) + 3 * (size_t)ll);
+        }
+        svrow[k + 1] = (int)svp.size();
         for (int q = R.partbase[k]; q < R.partbase[k + 1]; ++q) {
           for (int r = 0; r < world; ++r) {
             if (r == rank) continue;
@@ -2004,6 +2026,12 @@ static int prepare_sharded(ssb_graph* g) {
         SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_upush_cell.p, ucellp.data(), ucellp.size() * sizeof(uint4*), cudaMemcpyHostToDevice, s));
         SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_upush_x.p, uxp.data(), uxp.size() * sizeof(double*), cudaMemcpyHostToDevice, s));
       }
+      SSB_TRY(mr->d_zpush_z.ensure(std::max<size_t>(uzp.size(), 1)));
+      SSB_TRY(mr->d_svpush_v.ensure(std::max<size_t>(svp.size(), 1)));
+      SSB_TRY(mr->d_svpush_rowptr.ensure(svrow.size()));
+      if (!uzp.empty()) SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_zpush_z.p, uzp.data(), uzp.size() * sizeof(double*), cudaMemcpyHostToDevice, s));
+      if (!svp.empty()) SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_svpush_v.p, svp.data(), svp.size() * sizeof(double*), cudaMemcpyHostToDevice, s));
+      SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_svpush_rowptr.p, svrow.data(), svrow.size() * sizeof(int), cudaMemcpyHostToDevice, s));
       SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_vpush_rowptr.p, vrow.data(), vrow.size() * sizeof(int), cudaMemcpyHostToDevice, s));
       if (!vcellp.empty())
         SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_vpush_cell.p, vcellp.data(), vcellp.size() * sizeof(uint4*), cudaMemcpyHostToDevice, s));
@@ -2030,6 +2058,15 @@ static int prepare_sharded(ssb_graph* g) {
       mr->FP.upush_x = mr->d_upush_x.p;
       mr->FP.vpush_rowptr = mr->d_vpush_rowptr.p;
       mr->FP.vpush_cell = mr->d_vpush_cell.p;
+      mr->SP.world = world;
+      mr->SP.rank = rank;
+      mr->SP.zpush_rowptr = mr->d_upush_rowptr.p;
+      mr->SP.zpush_z = mr->d_zpush_z.p;
+      mr->SP.zpush_x = mr->d_upush_x.p;
+      mr->SP.n_own_lm = R.n_owned_lm;
+      mr->SP.vpush_rowptr = mr->d_svpush_rowptr.p;
+      mr->SP.vpush_v = mr->d_svpush_v.p;
+      for (int r = 0; r < world; ++r) mr->SP.slots[r] = mr->P.slots[r];
     }
     g->structure_dirty = false;
     g->host_est_dirty = true;
@@ -2045,16 +2082,16 @@ static int prepare_sharded(ssb_graph* g) {
   }
   const bool rebuilt = in->structure_dirty;
   SSB_TRY(prepare(in));
-  if (!in->fast_ok) {
-    set_error("sharded graph: the shard of rank %d (%d own keyframes, %d local) does not fit the on-chip PCG kernel", rank, mr->n_own,
-              (int)in->poses.size());
-    return SSB_ERR_INVALID;
-  }
-  // ranks sharing one device: cudaMalloc / cudaFree synchronise the whole device, so nobody may start a kernel that
-  // waits for a peer while another rank is still allocating — meet on the host once the tables are built
-  if (rebuilt && g->local_group) {
-    PeerBlob dummy{}, all[SSB_MAX_WORLD];
-    SSB_TRY(exchange_blobs(g, dummy, all));
+  // Meet on the host once the tables are built: (1) every rank must run the SAME PCG kernel — the on-chip data-flow
+  // kernel only if every shard fits it, else the streaming kernel everywhere; (2) ranks sharing one device: cudaMalloc /
+  // cudaFree synchronise the whole device, so nobody may start a kernel that waits for a peer while another rank is
+  // still allocating.
+  if (rebuilt) {
+    PeerBlob mine{}, all[SSB_MAX_WORLD];
+    mine.serial = in->fast_ok ? 1 : 0;
+    SSB_TRY(exchange_blobs(g, mine, all));
+    for (int r = 0; r < world; ++r)
+      if (!all[r].serial) in->fast_ok = false;
   }
   return SSB_OK;
 }

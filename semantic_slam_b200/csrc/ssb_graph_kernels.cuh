@@ -13,6 +13,7 @@
 #include <cooperative_groups.h>
 #include "ssb_common.cuh"
 #include "ssb_math.cuh"
+#include "ssb_peer.cuh"
 
 namespace ssb {
 namespace cg = cooperative_groups;
@@ -1163,15 +1164,83 @@ __device__ __forceinline__ double sub_level_apply(const CoarseDev& Cz, int i, in
   return add;
 }
 
+// Sharded graphs (template parameter MR of k_pcg): what the streaming kernel writes into the other ranks' arenas.
+struct StreamPeer {
+  int world, rank;
+  const int* zpush_rowptr;     // [Np_own + 1] ranks that hold my keyframe as a ghost ...
+  double* const* zpush_z;      //   ... its 6 slots in that rank's z vector
+  double* const* zpush_x;      //   ... and in its solution vector
+  int n_own_lm;                // the landmarks this rank eliminates: local landmarks [0, n_own_lm)
+  const int* vpush_rowptr;     // [n_own_lm + 1] ranks whose keyframes see the landmark ...
+  double* const* vpush_v;      //   ... its 3 slots in that rank's v vector
+  unsigned char* slots[SSB_MAX_WORLD];   // every rank's barrier slots [2][world * NB] + counter
+};
+constexpr int PCG_PART = PCG_THREADS > SSB_MAX_WORLD * 148 ? PCG_THREADS : SSB_MAX_WORLD * 148 + 8;
+
+// Barrier + fixed-order all-reduce over the CTAs of EVERY rank: a CTA writes its payload slot and adds to the arrival
+// counter in every rank's arena (system-scope release: everything its threads pushed to the neighbours before is visible
+// there first), then waits for world * gridDim.x arrivals on its OWN counter.  The 6 values of my6 stay local (the coarse
+// level is per rank).  Every CTA of every rank folds the same world * gridDim.x partials in the same order.
+__device__ __forceinline__ double grid_bar_sum_mr(const StreamPeer& SP, unsigned& epoch, double my_partial, const double* my6,
+                                                  double* gather, double* part_sh) {
+  ++epoch;
+  const int nb = gridDim.x, tot = SP.world * nb;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < SP.world; ++r) {
+      BarSlot* S = reinterpret_cast<BarSlot*>(SP.slots[r]) + (size_t)(epoch & 1u) * tot + SP.rank * nb + blockIdx.x;
+      st_relaxed_sys_f64(&S->v[0], my_partial);
+      if (my6 && r == SP.rank) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) S->v[1 + k] = my6[k];
+      }
+    }
+    for (int r = 0; r < SP.world; ++r)
+      red_release_sys_add_u32(&(reinterpret_cast<BarSlot*>(SP.slots[r]) + 2 * (size_t)tot)->epoch, 1u);
+    const unsigned* counter = &(reinterpret_cast<BarSlot*>(SP.slots[SP.rank]) + 2 * (size_t)tot)->epoch;
+    const unsigned target = epoch * (unsigned)tot;
+    unsigned polls = 0;
+    unsigned long long t0 = 0;
+    while (ld_acquire_sys_u32(counter) < target) {
+      if ((++polls & 1023u) == 0) {
+        const unsigned long long now = peer_globaltimer();
+        if (t0 == 0)
+          t0 = now;
+        else if (now - t0 > SSB_PEER_TIMEOUT_NS)
+          __trap();
+      }
+    }
+  }
+  __syncthreads();
+  const BarSlot* S = reinterpret_cast<const BarSlot*>(SP.slots[SP.rank]) + (size_t)(epoch & 1u) * tot;
+  for (int k = threadIdx.x; k < tot; k += blockDim.x) part_sh[k] = __ldcg(&S[k].v[0]);
+  if (gather && threadIdx.x < nb) {
+    const BarSlot* o = S + SP.rank * nb + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) gather[6 * threadIdx.x + k] = __ldcg(&o->v[1 + k]);
+  }
+  __syncthreads();
+  double t = 0.0;
+  for (int k = (threadIdx.x & 31); k < tot; k += 32) t += part_sh[k];
+  return warp_sum(t);
+}
+
+// MR: this grid = the CTAs of rank SP.rank of a sharded graph.  The vectors a neighbour reads (z of boundary keyframes, v
+// of shared landmarks, finally x) are also written into its arena before the barrier that publishes them; the three
+// barriers of an iteration span all ranks.  The preconditioner is rank-local (ghost keyframes carry no basis).
+template <bool MR>
 __global__ void __launch_bounds__(PCG_THREADS, 1)
-    k_pcg(DevGraph G, CoarseDev Cz, BarSlot* slots, double lambda, double tol2, int maxit) {
+    k_pcg(DevGraph G, CoarseDev Cz, BarSlot* slots, double lambda, double tol2, int maxit, StreamPeer SP) {
   extern __shared__ __align__(16) double dsm[];
   __shared__ double sh[33];
   __shared__ double s6[8], zc6[8], red6[6 * 32];
   const int nblk = gridDim.x;
   const int nc = 6 * nblk;
-  double* part_sh = dsm;                 // [1024]
-  double* Arow = part_sh + PCG_THREADS;  // [6][nc]   rows of A_c, then of A_c^-1
+  unsigned epoch_g = 0;
+#define SSB_GBAR(partial_, my6_, gather_) \
+  (MR ? grid_bar_sum_mr(SP, epoch_g, (partial_), (my6_), (gather_), part_sh) : grid_bar_sum(slots, epoch, (partial_), (my6_), (gather_), part_sh))
+  double* part_sh = dsm;                 // [PCG_PART]
+  double* Arow = part_sh + PCG_PART;     // [6][nc]   rows of A_c, then of A_c^-1
   double* panel_sh = Arow + 6 * nc;      // [6][nc]
   double* rc = panel_sh + 6 * nc;        // [nc] restricted residual (kept by recurrence)
   double* qc = rc + nc;                  // [nc] gathered restricted q
@@ -1253,11 +1322,15 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
         for (int k = 0; k < 6; ++k) zc += B[k] * zc6[k];
       }
       G.z[6 * (size_t)i + comp] = zc;
+      if constexpr (MR)
+        for (int q = SP.zpush_rowptr[i]; q < SP.zpush_rowptr[i + 1]; ++q) st_relaxed_sys_f64(SP.zpush_z[q] + comp, zc);
       local += rcomp * zc;
     }
   }
+  if constexpr (MR)   // p of a ghost keyframe is rebuilt here from its z (pushed by the owner): p_0 = 0
+    for (int k = 6 * G.Np_own + blockIdx.x * blockDim.x + threadIdx.x; k < 6 * G.Np; k += gridDim.x * blockDim.x) pold[k] = 0.0;
   double bs = block_sum(local, sh);
-  double rz = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh);
+  double rz = SSB_GBAR(bs, nullptr, nullptr);
   const double rz0 = rz;
   double beta = 0.0;
   int it = 0;
@@ -1267,7 +1340,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   }
   for (it = 0; it < maxit; ++it) {
     // ---- phase 1: v_l = (Hll+lambda)^-1 sum_e HplL_e p_e,  p = z + beta * pold (on the fly)
-    for (int l = gw; l < G.Nl; l += total_warps) {
+    for (int l = gw; l < (MR ? SP.n_own_lm : G.Nl); l += total_warps) {   // a shard's owned landmarks come first
       double a0 = 0.0, a1 = 0.0, a2 = 0.0;
       const int e1 = G.lm_rowptr[l + 1];
       for (int e = G.lm_rowptr[l] + lane; e < e1; e += 32) {
@@ -1288,12 +1361,21 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       a2 = warp_sum(a2);
       if (lane == 0) {
         const double* Wi = G.HllInv + 6 * (size_t)l;
-        G.v[3 * (size_t)l + 0] = Wi[0] * a0 + Wi[1] * a1 + Wi[2] * a2;
-        G.v[3 * (size_t)l + 1] = Wi[1] * a0 + Wi[3] * a1 + Wi[4] * a2;
-        G.v[3 * (size_t)l + 2] = Wi[2] * a0 + Wi[4] * a1 + Wi[5] * a2;
+        const double v0 = Wi[0] * a0 + Wi[1] * a1 + Wi[2] * a2;
+        const double v1 = Wi[1] * a0 + Wi[3] * a1 + Wi[4] * a2;
+        const double v2 = Wi[2] * a0 + Wi[4] * a1 + Wi[5] * a2;
+        G.v[3 * (size_t)l + 0] = v0;
+        G.v[3 * (size_t)l + 1] = v1;
+        G.v[3 * (size_t)l + 2] = v2;
+        if constexpr (MR)
+          for (int q = SP.vpush_rowptr[l]; q < SP.vpush_rowptr[l + 1]; ++q) {
+            st_relaxed_sys_f64(SP.vpush_v[q] + 0, v0);
+            st_relaxed_sys_f64(SP.vpush_v[q] + 1, v1);
+            st_relaxed_sys_f64(SP.vpush_v[q] + 2, v2);
+          }
       }
     }
-    grid_bar_sum(slots, epoch, 0.0, nullptr, nullptr, part_sh);
+    SSB_GBAR(0.0, nullptr, nullptr);
     // ---- phase 2: q = (Hpp + lambda) p + sum Hoff p_nbr - sum HplP v ; partial p.q ; restricted q
     local = 0.0;
 #pragma unroll
@@ -1356,9 +1438,12 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
         }
       }
     }
+    if constexpr (MR)   // p of the ghost keyframes (read by phase 1 / 2 of the next iteration through pold)
+      for (int k = 6 * G.Np_own + blockIdx.x * blockDim.x + threadIdx.x; k < 6 * G.Np; k += gridDim.x * blockDim.x)
+        pnew[k] = __ldcg(G.z + k) + beta * __ldcg(pold + k);
     bs = block_sum(local, sh);
     if (use_coarse) block_sum6(l6, s6, red6);
-    const double pq = grid_bar_sum(slots, epoch, bs, use_coarse ? s6 : nullptr, use_coarse ? qc : nullptr, part_sh);
+    const double pq = SSB_GBAR(bs, use_coarse ? s6 : nullptr, use_coarse ? qc : nullptr);
     if (!(pq > 0.0) || !isfinite(pq)) {  // breakdown: S not positive definite / non-finite data
       status = 1;
       break;
@@ -1401,11 +1486,13 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
           for (int k = 0; k < 6; ++k) zc += B[k] * zc6[k];
         }
         G.z[6 * (size_t)i + comp] = zc;
+        if constexpr (MR)
+          for (int q = SP.zpush_rowptr[i]; q < SP.zpush_rowptr[i + 1]; ++q) st_relaxed_sys_f64(SP.zpush_z[q] + comp, zc);
         local += rcomp * zc;
       }
     }
     bs = block_sum(local, sh);
-    const double rzn = grid_bar_sum(slots, epoch, bs, nullptr, nullptr, part_sh);
+    const double rzn = SSB_GBAR(bs, nullptr, nullptr);
     beta = rzn / rz;
     rz = rzn;
     double* t = pold;
@@ -1416,6 +1503,16 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       break;
     }
   }
+  if constexpr (MR) {   // the solution of a boundary keyframe goes to every rank that updates it as a ghost
+    for (int pbase = p0 + warp * 5; pbase < p1; pbase += warps_per_block * 5) {
+      const int i = pbase + slot;
+      if (lane_active && i < p1) {
+        const double xv = G.x[6 * (size_t)i + comp];
+        for (int q = SP.zpush_rowptr[i]; q < SP.zpush_rowptr[i + 1]; ++q) st_relaxed_sys_f64(SP.zpush_x[q] + comp, xv);
+      }
+    }
+  }
+#undef SSB_GBAR
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     G.iscalars[0] = it;
     G.iscalars[1] = status;

@@ -259,6 +259,15 @@ struct ssb_graph {
   std::vector<int> pl_full_info_sym;  // unused
   std::vector<LLEdge> ll;
   std::vector<int> plL_of_edge;  // creation index -> L-order position
+  // landmarks promoted into the reduced system (they carry a landmark-landmark edge, ssb_math.cuh pp_edge_linearize):
+  // the tables prepare() works on when `ll` is not empty — keyframes + pseudo-keyframes, their edges as pose-pose entries
+  std::vector<Pose> eff_poses;
+  std::vector<PPEdge> eff_pp;
+  std::vector<PLEdge> eff_pl;
+  std::vector<double> eff_zd;
+  std::vector<int> prom_lm;            // promoted landmark ids (index k -> pseudo-keyframe poses.size() + k)
+  std::vector<unsigned char> eff_kind; // per effective keyframe: 1 = promoted landmark
+  DBuf<unsigned char> d_pose_kind;
   bool structure_dirty = true;
   bool host_est_dirty = true;    // host estimates changed since last upload
   bool device_est_newer = false; // device estimates not yet copied back
@@ -664,9 +673,18 @@ static int sync_estimates_to_host(ssb_graph* g) {
   if (!g->device_est_newer) return SSB_OK;
   SSB_CUDA_CHECK(cudaSetDevice(g->device));
   const size_t Np = g->poses.size(), Nl = g->lms.size() / 4;
-  if (Np) SSB_CUDA_CHECK(cudaMemcpyAsync(g->poses.data(), g->d_pose.p, Np * sizeof(Pose), cudaMemcpyDeviceToHost, g->stream));
+  const bool prom = !g->ll.empty() && g->eff_poses.size() == Np + g->prom_lm.size() && !g->prom_lm.empty();
+  if (prom)
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->eff_poses.data(), g->d_pose.p, g->eff_poses.size() * sizeof(Pose), cudaMemcpyDeviceToHost, g->stream));
+  else if (Np)
+    SSB_CUDA_CHECK(cudaMemcpyAsync(g->poses.data(), g->d_pose.p, Np * sizeof(Pose), cudaMemcpyDeviceToHost, g->stream));
   if (Nl) SSB_CUDA_CHECK(cudaMemcpyAsync(g->lms.data(), g->d_lm.p, Nl * 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
   SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
+  if (prom) {   // promoted landmarks live among the keyframes on the device
+    std::copy(g->eff_poses.begin(), g->eff_poses.begin() + Np, g->poses.begin());
+    for (size_t k = 0; k < g->prom_lm.size(); ++k)
+      for (int c = 0; c < 3; ++c) g->lms[4 * (size_t)g->prom_lm[k] + c] = g->eff_poses[Np + k].t[c];
+  }
   g->device_est_newer = false;
   return SSB_OK;
 }
@@ -743,15 +761,98 @@ static void nd_order_rec(const std::vector<std::vector<int>>& adj, std::vector<i
   for (int v : S) order.push_back(v);
 }
 
+// 3x3 information (upper triangle, 6 values) into the upper-left corner of a 6x6 upper triangle (21 values)
+static void pack_info3_into6(const double* u3, double* u21) {
+  for (int k = 0; k < 21; ++k) u21[k] = 0.0;
+  u21[0] = u3[0];
+  u21[1] = u3[1];
+  u21[2] = u3[2];
+  u21[6] = u3[3];
+  u21[7] = u3[4];
+  u21[11] = u3[5];
+}
+static void refresh_promoted_estimates(ssb_graph* g) {
+  const size_t Np = g->poses.size();
+  g->eff_poses.resize(Np + g->prom_lm.size());
+  std::copy(g->poses.begin(), g->poses.end(), g->eff_poses.begin());
+  for (size_t k = 0; k < g->prom_lm.size(); ++k) {
+    Pose P;
+    std::memset(&P, 0, sizeof(P));
+    for (int c = 0; c < 3; ++c) P.t[c] = g->lms[4 * (size_t)g->prom_lm[k] + c];
+    P.q[3] = 1.0;
+    g->eff_poses[Np + k] = P;
+  }
+}
+// landmark-landmark edges (GraphSLAM::add_point_xyz_point_xyz_edge, graph_slam.cpp:168-180): every landmark they touch
+// leaves the point-wise Schur elimination and joins the reduced system as a pseudo-keyframe
+static int build_promoted(ssb_graph* g) {
+  const int Np = (int)g->poses.size(), Nl = (int)(g->lms.size() / 4);
+  std::vector<int> prom_idx(std::max(Nl, 1), -1);
+  g->prom_lm.clear();
+  for (auto& e : g->ll)
+    for (int l : {e.a, e.b}) {
+      if (g->lm_kind[l]) {
+        set_error("landmark-landmark edges between plane vertices are not defined (EdgePointXYZ joins VertexPointXYZ)");
+        return SSB_ERR_INVALID;
+      }
+      if (prom_idx[l] < 0) {
+        prom_idx[l] = (int)g->prom_lm.size();
+        g->prom_lm.push_back(l);
+      }
+    }
+  refresh_promoted_estimates(g);
+  g->eff_kind.assign(Np + g->prom_lm.size(), 0);
+  for (size_t k = 0; k < g->prom_lm.size(); ++k) g->eff_kind[Np + k] = 1;
+  g->eff_pp = g->pp;
+  g->eff_pl.clear();
+  g->eff_zd.clear();
+  for (size_t k = 0; k < g->pl.size(); ++k) {
+    const PLEdge& e = g->pl[k];
+    if (prom_idx[e.l] < 0) {
+      g->eff_pl.push_back(e);
+      g->eff_zd.push_back(g->pl_zd[k]);
+      continue;
+    }
+    PPEdge q;
+    std::memset(&q, 0, sizeof(q));
+    q.i = e.p;
+    q.j = Np + prom_idx[e.l];
+    for (int c = 0; c < 3; ++c) q.zt[c] = e.z[c];
+    q.zq[3] = 1.0;
+    pack_info3_into6(e.info, q.info);
+    q.pad = 1.0;
+    g->eff_pp.push_back(q);
+  }
+  for (auto& e : g->ll) {
+    PPEdge q;
+    std::memset(&q, 0, sizeof(q));
+    q.i = Np + prom_idx[e.a];
+    q.j = Np + prom_idx[e.b];
+    for (int c = 0; c < 3; ++c) q.zt[c] = e.z[c];
+    q.zq[3] = 1.0;
+    const double u3[6] = {e.info[0], 0.5 * (e.info[1] + e.info[3]), 0.5 * (e.info[2] + e.info[6]), e.info[4],
+                          0.5 * (e.info[5] + e.info[7]), e.info[8]};
+    pack_info3_into6(u3, q.info);
+    q.pad = 2.0;
+    g->eff_pp.push_back(q);
+  }
+  return SSB_OK;
+}
+
 // Build CSR edge tables (initializeOptimization + buildStructure analogue) and upload everything.
 static int prepare(ssb_graph* g) {
   SSB_CUDA_CHECK(cudaSetDevice(g->device));
-  if (!g->ll.empty()) {
-    set_error("landmark-landmark (EdgePointXYZ) edges are not supported by the Schur back-end in this round");
-    return SSB_ERR_INVALID;
+  const bool prom = !g->ll.empty();
+  if (prom && g->structure_dirty) {
+    SSB_TRY(sync_estimates_to_host(g));
+    SSB_TRY(build_promoted(g));
   }
-  const int Np = (int)g->poses.size(), Nl = (int)(g->lms.size() / 4);
-  const int El = (int)g->pl.size(), Epp = (int)g->pp.size();
+  const std::vector<Pose>& POSES = prom ? g->eff_poses : g->poses;
+  const std::vector<PPEdge>& PP = prom ? g->eff_pp : g->pp;
+  const std::vector<PLEdge>& PL = prom ? g->eff_pl : g->pl;
+  const std::vector<double>& ZD = prom ? g->eff_zd : g->pl_zd;
+  const int Np = (int)POSES.size(), Nl = (int)(g->lms.size() / 4);
+  const int El = (int)PL.size(), Epp = (int)PP.size();
   // a shard of a larger graph: own keyframes [0, n_own), then ghosts; owned landmarks [0, n_owned_lm), then ghosts
   const MrCtx* mr = g->mr;
   const int n_own = mr ? mr->n_own : Np;
@@ -768,6 +869,7 @@ static int prepare(ssb_graph* g) {
       else
         lfix[v.idx] = v.fixed;
     }
+    for (size_t k = 0; k < (prom ? g->prom_lm.size() : 0); ++k) pfix[g->poses.size() + k] = lfix[g->prom_lm[k]];
     const bool prep_timing = std::getenv("SSB_PREP_TIMING") != nullptr;
     double tp0 = wall_ms();
     auto tick = [&](const char* what) {
@@ -779,7 +881,7 @@ static int prepare(ssb_graph* g) {
     };
     // L-order (stable counting sort by landmark)
     std::vector<int> lm_rowptr(Nl + 1, 0);
-    for (auto& e : g->pl) lm_rowptr[e.l + 1]++;
+    for (auto& e : PL) lm_rowptr[e.l + 1]++;
     for (int l = 0; l < Nl; ++l) lm_rowptr[l + 1] += lm_rowptr[l];
     SSB_TRY(g->h_plL.ensure(std::max(El, 1)));
     SSB_TRY(g->h_zdL.ensure(std::max(El, 1)));
@@ -803,7 +905,7 @@ static int prepare(ssb_graph* g) {
       {
         std::vector<int> lastp(std::max(Nl, 1), -1);
         for (int k = 0; k < El; ++k) {
-          const PLEdge& e = g->pl[k];
+          const PLEdge& e = PL[k];
           if (key(e.p) < lastp[e.l]) {
             pose_sorted = false;
             break;
@@ -813,19 +915,19 @@ static int prepare(ssb_graph* g) {
       }
       std::vector<int> cntl(lm_rowptr.begin(), lm_rowptr.end() - 1);
       if (pose_sorted) {
-        for (int k = 0; k < El; ++k) ord[cntl[g->pl[k].l]++] = k;
+        for (int k = 0; k < El; ++k) ord[cntl[PL[k].l]++] = k;
       } else {
         tmp.resize(El);
         std::vector<int> cntp(nkey + 1, 0);
-        for (int k = 0; k < El; ++k) cntp[key(g->pl[k].p) + 1]++;
+        for (int k = 0; k < El; ++k) cntp[key(PL[k].p) + 1]++;
         for (int i = 0; i < nkey; ++i) cntp[i + 1] += cntp[i];
-        for (int k = 0; k < El; ++k) tmp[cntp[key(g->pl[k].p)]++] = k;
-        for (int q = 0; q < El; ++q) ord[cntl[g->pl[tmp[q]].l]++] = tmp[q];
+        for (int k = 0; k < El; ++k) tmp[cntp[key(PL[k].p)]++] = k;
+        for (int q = 0; q < El; ++q) ord[cntl[PL[tmp[q]].l]++] = tmp[q];
       }
       const bool planes = g->n_plane_vertices != 0;
       for (int pos = 0; pos < El; ++pos) {
-        plL[pos] = g->pl[ord[pos]];
-        if (planes) zdL[pos] = g->pl_zd[ord[pos]];
+        plL[pos] = PL[ord[pos]];
+        if (planes) zdL[pos] = ZD[ord[pos]];
         g->plL_of_edge[ord[pos]] = pos;
       }
     }
@@ -954,7 +1056,7 @@ static int prepare(ssb_graph* g) {
     for (int k = 0; k < El; ++k) ppl_idx[fill2[plL[k].p]++] = k;
     // pose-pose incidence
     std::vector<int> ppp_rowptr(Np + 1, 0);
-    for (auto& e : g->pp) {
+    for (auto& e : PP) {
       ppp_rowptr[e.i + 1]++;
       ppp_rowptr[e.j + 1]++;
     }
@@ -962,8 +1064,8 @@ static int prepare(ssb_graph* g) {
     std::vector<int> fill3(ppp_rowptr.begin(), ppp_rowptr.end() - 1);
     std::vector<int> ppp_idx(std::max(2 * Epp, 1));
     for (int k = 0; k < Epp; ++k) {
-      ppp_idx[fill3[g->pp[k].i]++] = (k << 1) | 0;
-      ppp_idx[fill3[g->pp[k].j]++] = (k << 1) | 1;
+      ppp_idx[fill3[PP[k].i]++] = (k << 1) | 0;
+      ppp_idx[fill3[PP[k].j]++] = (k << 1) | 1;
     }
     tick("run lists + CSR");
     // allocate + upload
@@ -1076,7 +1178,7 @@ static int prepare(ssb_graph* g) {
                 upp.push_back(e);
               }
               pp_loc[kk] = e_slot[e];
-              const int o = role == 0 ? g->pp[e].j : g->pp[e].i;
+              const int o = role == 0 ? PP[e].j : PP[e].i;
               int src;
               if (o >= q0 && o < q1) {
                 src = o - q0;
@@ -1124,7 +1226,7 @@ static int prepare(ssb_graph* g) {
           cadj[a].push_back(b);
           cadj[b].push_back(a);
         };
-        for (auto& e : g->pp)
+        for (auto& e : PP)
           if (e.i < n_own && e.j < n_own) link(e.i / Cc, e.j / Cc);
         for (int l = 0; l < Nl; ++l)
           for (int ra = lm_run_rowptr[l]; ra < lm_run_rowptr[l + 1]; ++ra)
@@ -1274,7 +1376,7 @@ static int prepare(ssb_graph* g) {
     if (g->n_plane_vertices) {
       SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_kind.p, g->lm_kind.data(), Nl, cudaMemcpyHostToDevice, s));
     }
-    if (Epp) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pp.p, g->pp.data(), (size_t)Epp * sizeof(PPEdge), cudaMemcpyHostToDevice, s));
+    if (Epp) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pp.p, PP.data(), (size_t)Epp * sizeof(PPEdge), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm_rowptr.p, lm_rowptr.data(), (Nl + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pl_rowptr.p, ppl_rowptr.data(), (Np + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     if (El) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pl_idx.p, ppl_idx.data(), (size_t)El * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1329,6 +1431,13 @@ static int prepare(ssb_graph* g) {
     G.iscalars = g->d_iscalars.p;
     G.Np_own = n_own;
     G.lm_owned = nullptr;
+    G.pose_kind = nullptr;
+    if (prom) {
+      SSB_TRY(g->d_pose_kind.ensure(std::max(Np, 1)));
+      SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_kind.p, g->eff_kind.data(), Np, cudaMemcpyHostToDevice, g->stream));
+      SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
+      G.pose_kind = g->d_pose_kind.p;
+    }
     if (mr) {
       SSB_TRY(g->d_lm_owned.ensure(std::max(Nl, 1)));
       if (Nl) {
@@ -1340,7 +1449,8 @@ static int prepare(ssb_graph* g) {
   }
   if (g->host_est_dirty) {
     cudaStream_t s = g->stream;
-    if (Np) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose.p, g->poses.data(), (size_t)Np * sizeof(Pose), cudaMemcpyHostToDevice, s));
+    if (prom) refresh_promoted_estimates(g);
+    if (Np) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose.p, POSES.data(), (size_t)Np * sizeof(Pose), cudaMemcpyHostToDevice, s));
     if (Nl) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_lm.p, g->lms.data(), (size_t)4 * Nl * sizeof(double), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaStreamSynchronize(s));
     g->host_est_dirty = false;
@@ -2475,7 +2585,7 @@ int ssb_graph_restore(ssb_graph* g) {
 }
 
 int ssb_graph_edge_linearize(ssb_graph* g, int eid, double* err, double* Ji, double* Jj) {
-  if (!g || eid < 0 || eid >= (int)g->E.size() || !err || !Ji || !Jj || is_sharded(g)) return SSB_ERR_INVALID;
+  if (!g || eid < 0 || eid >= (int)g->E.size() || !err || !Ji || !Jj || is_sharded(g) || !g->ll.empty()) return SSB_ERR_INVALID;
   SSB_TRY(prepare(g));
   HostEdgeRef r = g->E[eid];
   if (r.kind == EK_LL) return SSB_ERR_INVALID;
@@ -2530,11 +2640,17 @@ int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len) {
     return SSB_ERR_INVALID;
   }
   int o = 0;
+  std::vector<int> prom_idx(g->lms.size() / 4 + 1, -1);
+  if (!g->ll.empty())
+    for (size_t k = 0; k < g->prom_lm.size(); ++k) prom_idx[g->prom_lm[k]] = (int)k;
   for (auto& v : g->V) {
     if (v.fixed) continue;
     if (v.kind == VK_SE3) {
       std::memcpy(x + o, &dp[6 * (size_t)v.idx], 6 * sizeof(double));
       o += 6;
+    } else if (prom_idx[v.idx] >= 0) {   // a promoted landmark is solved for among the keyframes
+      std::memcpy(x + o, &dp[6 * (g->poses.size() + (size_t)prom_idx[v.idx])], 3 * sizeof(double));
+      o += 3;
     } else {
       std::memcpy(x + o, &dl[3 * (size_t)v.idx], 3 * sizeof(double));
       o += 3;
@@ -2555,6 +2671,10 @@ int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* o
       return SSB_ERR_INVALID;
     }
   if (g->E.size() < 10) return 0;  // nothing was ever optimised (graph_slam.cpp:184-186)
+  if (!g->ll.empty()) {
+    set_error("landmark_marginals: not available on a graph with landmark-landmark edges");
+    return 0;
+  }
   if (is_sharded(g)) {
     set_error("landmark_marginals: not available on a sharded graph");
     return 0;

@@ -25,6 +25,9 @@ struct DevGraph {
   // neighbours); landmarks with lm_owned == 0 are eliminated by another rank.  Unsharded: Np_own == Np, null.
   int Np_own;
   const unsigned char* lm_owned;
+  // 1 = pseudo-keyframe: a landmark promoted into the reduced system because it carries a landmark-landmark edge
+  // (ssb_math.cuh: pp_edge_linearize); null = none
+  const unsigned char* pose_kind;
   Pose* pose;
   double* lm;  // 4 doubles per landmark
   const unsigned char* pose_fixed;
@@ -197,9 +200,9 @@ __global__ void __launch_bounds__(64) k_lin_poses(DevGraph G) {
     const Pose Y = G.pose[other];
     double err[6], Ji[36], Jj[36], W[36];
     if (role == 0)
-      pp_linearize(X, Y, ed->zt, ed->zq, err, Ji, Jj);
+      pp_edge_linearize(*ed, X, Y, err, Ji, Jj);
     else
-      pp_linearize(Y, X, ed->zt, ed->zq, err, Ji, Jj);
+      pp_edge_linearize(*ed, Y, X, err, Ji, Jj);
     expand_sym6(ed->info, W);
     const double* J = role == 0 ? Ji : Jj;
     double JtW[36];
@@ -246,6 +249,8 @@ __global__ void __launch_bounds__(64) k_lin_poses(DevGraph G) {
       H[7 * k] = 1.0;
       b[k] = 0.0;
     }
+  } else if (G.pose_kind && G.pose_kind[i]) {   // promoted landmark: the three unused increments are pinned
+    H[21] = H[28] = H[35] = 1.0;
   }
   for (int k = 0; k < 36; ++k) G.Hpp[36 * (size_t)i + k] = H[k];
   for (int k = 0; k < 6; ++k) G.bp[6 * (size_t)i + k] = b[k];
@@ -257,7 +262,7 @@ __global__ void k_maxdiag(DevGraph G) {
   double m = 0.0;
   if (t < G.Np) {
     if (!G.pose_fixed[t] && t < G.Np_own)
-      for (int k = 0; k < 6; ++k) m = fmax(m, fabs(G.Hpp[36 * (size_t)t + 7 * k]));
+      for (int k = 0; k < ((G.pose_kind && G.pose_kind[t]) ? 3 : 6); ++k) m = fmax(m, fabs(G.Hpp[36 * (size_t)t + 7 * k]));
   } else if (t < G.Np + G.Nl) {
     int l = t - G.Np;
     if (!G.lm_fixed[l] && (G.lm_owned == nullptr || G.lm_owned[l])) {
@@ -536,7 +541,7 @@ __global__ void __launch_bounds__(256) k_coarse_basis(DevGraph G, CoarseDev Cz) 
   __syncthreads();
   for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
     double* B = Cz.Bmat + 36 * (size_t)i;
-    if (G.pose_fixed[i]) {
+    if (G.pose_fixed[i] || (G.pose_kind && G.pose_kind[i])) {   // (a promoted landmark is not part of a rigid body)
       for (int k = 0; k < 36; ++k) B[k] = 0.0;
       continue;
     }
@@ -591,7 +596,7 @@ __global__ void __launch_bounds__(128) k_sub_basis(DevGraph G, CoarseDev Cz) {
     for (int k = 0; k < 3; ++k) cen[k] += G.pose[q].t[k];
   for (int k = 0; k < 3; ++k) cen[k] /= (double)max(1, i1 - i0);
   double* B = Cz.B1mat + 36 * (size_t)i;
-  if (G.pose_fixed[i] || i >= G.Np_own) {
+  if (G.pose_fixed[i] || i >= G.Np_own || (G.pose_kind && G.pose_kind[i])) {
     for (int k = 0; k < 36; ++k) B[k] = 0.0;
     return;
   }
@@ -1423,11 +1428,26 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
         }
       }
       if (act) {
+        // the pose's landmark edges in batches of 4: the landmark ids, then every v triple and block row are requested
+        // together (one dependent-load round trip per batch instead of two per edge)
         const int q0 = G.pose_pl_rowptr[i], q1 = G.pose_pl_rowptr[i + 1];
-        for (int kk = q0; kk < q1; ++kk) {
-          const double* Hp = G.HplP + 18 * (size_t)kk + 3 * comp;
-          const double* vv = G.v + 3 * (size_t)G.plP_lm[kk];
-          qv -= Hp[0] * __ldcg(vv) + Hp[1] * __ldcg(vv + 1) + Hp[2] * __ldcg(vv + 2);
+        for (int kk = q0; kk < q1; kk += 4) {
+          int lm[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) lm[u] = kk + u < q1 ? G.plP_lm[kk + u] : -1;
+          double hv[4][3], vv[4][3];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double* Hp = G.HplP + 18 * (size_t)(kk + u) + 3 * comp;
+            const double* vp = G.v + 3 * (size_t)(lm[u] < 0 ? 0 : lm[u]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              hv[u][c] = lm[u] >= 0 ? Hp[c] : 0.0;
+              vv[u][c] = lm[u] >= 0 ? __ldcg(vp + c) : 0.0;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) qv -= hv[u][0] * vv[u][0] + hv[u][1] * vv[u][1] + hv[u][2] * vv[u][2];
         }
         G.q[6 * (size_t)i + comp] = qv;
         local += pc * qv;
@@ -1575,7 +1595,10 @@ __global__ void __launch_bounds__(128) k_backsub_update(DevGraph G, double lambd
     double d[6];
     for (int c = 0; c < 6; ++c) d[c] = G.pose_fixed[i] ? 0.0 : G.x[6 * (size_t)i + c];
     if (!G.pose_fixed[i]) {
-      pose_oplus(X, d);
+      if (G.pose_kind && G.pose_kind[i]) {   // VertexPointXYZ::oplusImpl of a promoted landmark
+        for (int c = 0; c < 3; ++c) X.t[c] += d[c];
+      } else
+        pose_oplus(X, d);
       G.pose[i] = X;
     }
     if (i < G.Np_own)
@@ -1656,7 +1679,7 @@ __global__ void __launch_bounds__(CHI2_THREADS) k_chi2(DevGraph G, double* part,
         const Pose Xi = G.pose[ed->i];
         const Pose Xj = G.pose[ed->j];
         double err[6];
-        pp_linearize(Xi, Xj, ed->zt, ed->zq, err, nullptr, nullptr);
+        pp_edge_linearize(*ed, Xi, Xj, err, nullptr, nullptr);
         acc += quad6(ed->info, err);
       }
     }
@@ -1737,7 +1760,7 @@ __global__ void k_edge_linearize(DevGraph G, int kind, int e, double* out /* err
   double* Jj = out + 42;
   if (kind == 0) {
     const PPEdge* ed = G.pp + e;
-    pp_linearize(G.pose[ed->i], G.pose[ed->j], ed->zt, ed->zq, err, Ji, Jj);
+    pp_edge_linearize(*ed, G.pose[ed->i], G.pose[ed->j], err, Ji, Jj);
   } else {
     const PLEdge ed = G.pl[e];
     double JlT[9];

@@ -464,6 +464,47 @@ SSB_HD void pp_linearize(const Pose& Xi, const Pose& Xj, const double* zt, const
   }
 }
 
+// -------- pose-pose table entries of other kinds (PPEdge::pad = kind).  A landmark that carries a landmark-landmark edge
+// (g2o::EdgePointXYZ, GraphSLAM::add_point_xyz_point_xyz_edge graph_slam.cpp:168-180) cannot be eliminated point-wise by
+// the Schur step: it is PROMOTED into the reduced system as a pseudo-keyframe (t = xyz, identity rotation, the last three
+// increments pinned by an identity block).  Its edges become pose-pose entries with the 3x3 information in the upper-left
+// corner of the 6x6 one and errors / Jacobians padded with zeros, so every accumulation kernel runs unchanged.
+//   kind 1: EdgeSE3PointXYZ, vertex i = keyframe, vertex j = promoted landmark   e = Ri'(pj - ti) - z
+//   kind 2: EdgePointXYZ,    both promoted landmarks                             e = (pj - pi) - z
+SSB_HD int pp_kind(const PPEdge& ed) { return (int)ed.pad; }
+SSB_HD void pp_edge_linearize(const PPEdge& ed, const Pose& Xi, const Pose& Xj, double* e, double* Ji, double* Jj) {
+  const int kind = pp_kind(ed);
+  if (kind == 0) {
+    pp_linearize(Xi, Xj, ed.zt, ed.zq, e, Ji, Jj);
+    return;
+  }
+  e[3] = e[4] = e[5] = 0.0;
+  if (Ji)
+    for (int k = 0; k < 36; ++k) {
+      Ji[k] = 0.0;
+      Jj[k] = 0.0;
+    }
+  if (kind == 1) {
+    PLLin L;
+    pl_linearize(Xi, Xj.t, ed.zt, L);
+    for (int k = 0; k < 3; ++k) e[k] = L.e[k];
+    if (!Ji) return;
+    double Jp[18];
+    pl_jac_pose(L.pc, Jp);
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 6; ++c) Ji[6 * r + c] = Jp[6 * r + c];
+      for (int c = 0; c < 3; ++c) Jj[6 * r + c] = L.R[3 * c + r];   // Ri'
+    }
+  } else {
+    for (int k = 0; k < 3; ++k) e[k] = (Xj.t[k] - Xi.t[k]) - ed.zt[k];
+    if (!Ji) return;
+    for (int k = 0; k < 3; ++k) {
+      Ji[7 * k] = -1.0;
+      Jj[7 * k] = 1.0;
+    }
+  }
+}
+
 // chi2 helpers
 SSB_HD double quad3(const double* u, const double* e) {
   return u[0] * e[0] * e[0] + u[3] * e[1] * e[1] + u[5] * e[2] * e[2] +

@@ -317,6 +317,33 @@ typedef struct ssb_detected_object { /* detected_object  include/planar_segmenta
 int ssb_segment_planar_surfaces(const ssb_planar_region* regions, int n, const float robot_pose[6], float cam_angle,
                                 int object_type, float prob, float planar_area, ssb_detected_object* out);
 
+/* The LIVE segmentation path: plane_segmentation::computeNormalsFromPointCloud (src/planar_segmentation/
+ * plane_segmentation.cpp:84-106 -> pcl::IntegralImageNormalEstimation, COVARIANCE_MATRIX, depth-change factor 0.03,
+ * smoothing 20) + plane_segmentation::multiPlaneSegmentation's PCL call (:136-156 -> pcl::OrganizedMultiPlaneSegmentation::
+ * segmentAndRefine, 2 degrees / 0.02 m) + pcl::calculatePolygonArea (:189), for every bbox crop of a frame on the device
+ * (csrc/ssb_organized.cuh).  Together with ssb_segment_planar_surfaces this is point_cloud_segmentation::
+ * segmentallPointCloudData (include/planar_segmentation/point_cloud_segmentation.h:105-181) without the class filter. */
+typedef struct ssb_organized_opts {
+  float max_depth_change_factor;   /* 0.03  plane_segmentation.cpp:98 */
+  float normal_smoothing_size;     /* 20    :99 */
+  int min_inliers;                 /* num_point_seg (500; the shipped yamls use 100), :7,139 */
+  float angular_threshold;         /* 0.017453 * 2 rad, :140 */
+  float distance_threshold;        /* 0.02 m (depth dependent inside PCL), :141 */
+  float maximum_curvature;         /* 0.001, PCL default */
+  int norm_point_thres;            /* crops with fewer points are skipped (5000), :8,93 */
+  int reserved[3];
+} ssb_organized_opts;
+void ssb_organized_default_opts(ssb_organized_opts* o);
+/* regions: [n_boxes][max_regions] in PCL's order (by label); n_regions[b] = regions found (may exceed max_regions),
+ * -1 = spurious bbox, -2 = crop skipped (below norm_point_thres).  Optional outputs (NULL to skip): n_inliers
+ * [n_boxes][max_regions] (after the refinement); per point, concatenated over the non-spurious boxes in row-major crop
+ * order: normals_out [][4] (nx, ny, nz, curvature; NaN where PCL leaves NaN), labels_out (after the refinement, -1 = none),
+ * dist_out (the smoothing distance map).  At most 64 regions per crop are kept. */
+int ssb_organized_planes(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout, const ssb_bbox* boxes, int n_boxes,
+                         const ssb_organized_opts* opts, int max_regions, ssb_planar_region* regions, int* n_regions, int* n_inliers,
+                         float* normals_out, int* labels_out, float* dist_out);
+double ssb_organized_last_ms(ssb_ransac* r);
+
 void ssb_assoc_default_opts(ssb_assoc_opts* o);
 ssb_assoc* ssb_assoc_create(const ssb_assoc_opts* opts);   /* data_association::data_association + init */
 void ssb_assoc_destroy(ssb_assoc* a);

@@ -333,3 +333,44 @@ def ransac_plane_batch(msg, width, height, point_step, row_step, offsets, boxes,
     if r != 0:
         raise RuntimeError("oracle ransac failed")
     return res, counts, (mask[:total] if mask is not None else None)
+
+
+# ---- the live segmentation path (oracle_segment.cpp): integral-image normals + organised multi-plane segmentation ----
+def integral_normals(cloud_hw4, max_depth_change_factor=0.03, smoothing_size=20.0):
+    """pcl::IntegralImageNormalEstimation (COVARIANCE_MATRIX) on an organised (h, w, 4) float32 crop.
+    Returns (normals (h, w, 4): nx ny nz curvature, distance map (h, w))."""
+    c = np.ascontiguousarray(cloud_hw4, dtype=np.float32)
+    h, w = c.shape[:2]
+    nrm = np.zeros((h, w, 4), dtype=np.float32)
+    dist = np.zeros((h, w), dtype=np.float32)
+    L = lib()
+    L.orc_integral_normals.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.orc_integral_normals(c.ctypes.data, w, h, max_depth_change_factor, smoothing_size, nrm.ctypes.data, dist.ctypes.data)
+    return nrm, dist
+
+
+def organized_planes(cloud_hw4, min_inliers=500, angular_threshold=0.017453 * 2.0, distance_threshold=0.02,
+                     maximum_curvature=0.001, max_depth_change_factor=0.03, smoothing_size=20.0, max_regions=64):
+    """IntegralImageNormalEstimation + OrganizedMultiPlaneSegmentation::segmentAndRefine + contour + polygon area."""
+    c = np.ascontiguousarray(cloud_hw4, dtype=np.float32)
+    h, w = c.shape[:2]
+    nrm = np.zeros((h, w, 4), dtype=np.float32)
+    lcc = np.zeros((h, w), dtype=np.int32)
+    lref = np.zeros((h, w), dtype=np.int32)
+    cen = np.zeros((max_regions, 3), dtype=np.float32)
+    mod = np.zeros((max_regions, 4), dtype=np.float32)
+    nin = np.zeros(max_regions, dtype=np.int32)
+    ncon = np.zeros(max_regions, dtype=np.int32)
+    area = np.zeros(max_regions, dtype=np.float32)
+    L = lib()
+    L.orc_organized_planes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+    n = L.orc_organized_planes(c.ctypes.data, w, h, max_depth_change_factor, smoothing_size, int(min_inliers), angular_threshold,
+                               distance_threshold, maximum_curvature, nrm.ctypes.data, lcc.ctypes.data, lref.ctypes.data, max_regions,
+                               cen.ctypes.data, mod.ctypes.data, nin.ctypes.data, ncon.ctypes.data, area.ctypes.data)
+    if n < 0:
+        raise RuntimeError("oracle organized_planes failed")
+    m = min(n, max_regions)
+    return {"n": n, "normals": nrm, "labels_cc": lcc, "labels": lref, "centroid": cen[:m], "model": mod[:m], "n_inliers": nin[:m],
+            "contour_points": ncon[:m], "area": area[:m]}

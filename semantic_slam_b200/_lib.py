@@ -39,6 +39,12 @@ class RansacOpts(C.Structure):
                 ("probability", C.c_double), ("device", C.c_int), ("reserved", C.c_int * 3)]
 
 
+class OrganizedOpts(C.Structure):
+    _fields_ = [("max_depth_change_factor", C.c_float), ("normal_smoothing_size", C.c_float), ("min_inliers", C.c_int),
+                ("angular_threshold", C.c_float), ("distance_threshold", C.c_float), ("maximum_curvature", C.c_float),
+                ("norm_point_thres", C.c_int), ("reserved", C.c_int * 3)]
+
+
 def build(verbose: bool = False) -> str:
     """Compile libssb.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-s"]
@@ -59,7 +65,7 @@ SYMBOLS = [
     "ssb_graph_solve_once", "ssb_comm_unique_id", "ssb_graph_attach_comm", "ssb_graph_attach_local", "ssb_shard_ranges",
     "ssb_graph_shard_info", "ssb_shard_plan", "ssb_ransac_default_opts",
     "ssb_ransac_create", "ssb_ransac_destroy", "ssb_ransac_plane_batch", "ssb_ransac_upload",
-    "ssb_ransac_run_resident", "ssb_ransac_fetch", "ssb_ransac_stream", "ssb_ransac_launch_count", "ssb_ransac_timing", "ssb_crop_bbox",
+    "ssb_organized_default_opts", "ssb_organized_planes", "ssb_organized_last_ms", "ssb_ransac_run_resident", "ssb_ransac_fetch", "ssb_ransac_stream", "ssb_ransac_launch_count", "ssb_ransac_timing", "ssb_crop_bbox",
     "ssb_segment_planar_surfaces", "ssb_assoc_default_opts", "ssb_assoc_create", "ssb_assoc_destroy", "ssb_assoc_find_matches",
     "ssb_assoc_set_landmark_estimate", "ssb_assoc_set_landmark_cov", "ssb_assoc_num_landmarks", "ssb_assoc_get_landmark",
     "ssb_last_error", "ssb_build_info", "ssb_graph_stream", "ssb_graph_snapshot", "ssb_graph_restore",
@@ -139,6 +145,11 @@ def lib():
     L.ssb_ransac_launch_count.restype = C.c_longlong
     L.ssb_ransac_timing.argtypes = [vp, dp]
     L.ssb_crop_bbox.argtypes = [vp, vp, C.POINTER(CloudLayoutC), vp, vp]
+    L.ssb_organized_default_opts.argtypes = [C.POINTER(OrganizedOpts)]
+    L.ssb_organized_planes.argtypes = [vp, vp, C.POINTER(CloudLayoutC), vp, C.c_int, C.POINTER(OrganizedOpts), C.c_int, vp, vp, vp, vp,
+                                       vp, vp]
+    L.ssb_organized_last_ms.argtypes = [vp]
+    L.ssb_organized_last_ms.restype = C.c_double
     _LIB = L
     return L
 

@@ -19,6 +19,7 @@
 
 #include "../../include/ssb.h"
 #include "ssb_common.cuh"
+#include "ssb_organized.cuh"
 
 namespace ssb {
 
@@ -518,6 +519,18 @@ struct ssb_ransac {
   bool uploaded = false;
   long long launches = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // run begin/end, k_count begin/end
+  // organised multi-plane segmentation (ssb_organized.cuh)
+  RBuf<ssb_org::OrgBox> d_oboxes;
+  RBuf<unsigned char> d_change;
+  RBuf<float> d_dist, d_planed;
+  RBuf<float4> d_nrm;
+  RBuf<double> d_ii;
+  RBuf<unsigned> d_ic;
+  RBuf<int> d_parent, d_label, d_count, d_nlabels, d_ncand, d_nreg, d_l2m;
+  RBuf<ssb_org::OrgRegion> d_oreg;
+  RBuf<unsigned long long> d_lastev;
+  cudaEvent_t oev[2] = {nullptr, nullptr};
+  double org_ms = 0.0;
 };
 
 static int plan(ssb_ransac* r, const ssb_cloud_layout* L, const ssb_bbox* bx, int nb) {
@@ -754,5 +767,156 @@ int ssb_crop_bbox(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout
   SSB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
   return r->boxes[0].n;
 }
+
+// ---- the live segmentation path: integral-image normals + organised multi-plane segmentation (ssb_organized.cuh) ----
+void ssb_organized_default_opts(ssb_organized_opts* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->max_depth_change_factor = 0.03f;      // plane_segmentation.cpp:98
+  o->normal_smoothing_size = 20.0f;        // :99
+  o->min_inliers = 500;                    // num_point_seg default, plane_segmentation.cpp:7
+  o->angular_threshold = 0.017453f * 2.0f; // :140
+  o->distance_threshold = 0.02f;           // :141
+  o->maximum_curvature = 0.001f;           // pcl::OrganizedMultiPlaneSegmentation default
+  o->norm_point_thres = 5000;              // plane_segmentation.cpp:8
+}
+
+int ssb_organized_planes(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout, const ssb_bbox* boxes, int n_boxes,
+                         const ssb_organized_opts* opts, int max_regions, ssb_planar_region* regions, int* n_regions, int* n_inliers,
+                         float* normals_out, int* labels_out, float* dist_out) {
+  using namespace ssb_org;
+  if (!r || !msg || !layout || (n_boxes > 0 && !boxes) || n_boxes < 0 || max_regions < 0 || (n_boxes > 0 && !n_regions)) {
+    set_error("ssb_organized_planes: invalid argument");
+    return SSB_ERR_INVALID;
+  }
+  ssb_organized_opts od;
+  if (!opts) {
+    ssb_organized_default_opts(&od);
+    opts = &od;
+  }
+  ssb_ransac_opts ro;
+  ssb_ransac_default_opts(&ro);
+  int rc = ssb_ransac_upload(r, msg, layout, boxes, n_boxes, nullptr, 0, &ro);   // cloud + crop plan on the device
+  if (rc) return rc;
+  const int nb = n_boxes;
+  if (nb == 0) return SSB_OK;
+  if (layout->width > ORG_THREADS) {
+    set_error("ssb_organized_planes: clouds wider than %d pixels are not supported", ORG_THREADS);
+    return SSB_ERR_INVALID;
+  }
+  std::vector<OrgBox> ob(nb);
+  long long ii_total = 0;
+  for (int b = 0; b < nb; ++b) {
+    const BoxInfo& B = r->boxes[b];
+    OrgBox& o = ob[b];
+    o.w = B.w;
+    o.h = B.h;
+    // computeNormalsFromPointCloud returns no normals for crops below norm_point_thres (:93) and the caller skips them
+    o.n = (B.n > 0 && B.n >= opts->norm_point_thres) ? B.n : 0;
+    o.pt_off = B.pt_off;
+    o.ii_off = ii_total;
+    if (o.n > 0) ii_total += (long long)(B.w + 1) * (B.h + 1);
+  }
+  const size_t tot = (size_t)std::max<long long>(r->total_pts, 1);
+  if ((rc = r->d_oboxes.ensure(nb)) || (rc = r->d_change.ensure(tot)) || (rc = r->d_dist.ensure(tot)) || (rc = r->d_planed.ensure(tot)) ||
+      (rc = r->d_nrm.ensure(tot)) || (rc = r->d_ii.ensure(9 * (size_t)std::max<long long>(ii_total, 1))) ||
+      (rc = r->d_ic.ensure((size_t)std::max<long long>(ii_total, 1))) || (rc = r->d_parent.ensure(tot)) || (rc = r->d_label.ensure(tot)) ||
+      (rc = r->d_count.ensure(tot)) || (rc = r->d_l2m.ensure(tot)) || (rc = r->d_nlabels.ensure(nb)) || (rc = r->d_ncand.ensure(nb)) ||
+      (rc = r->d_nreg.ensure(nb)) || (rc = r->d_oreg.ensure((size_t)nb * ORG_MAXR)) || (rc = r->d_lastev.ensure((size_t)nb * ORG_MAXR)))
+    return rc;
+  cudaStream_t s = r->stream;
+  for (int k = 0; k < 2; ++k)
+    if (!r->oev[k]) SSB_CUDA_CHECK(cudaEventCreate(&r->oev[k]));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(r->d_oboxes.p, ob.data(), nb * sizeof(OrgBox), cudaMemcpyHostToDevice, s));
+  OrgOpts O;
+  O.max_depth_change_factor = opts->max_depth_change_factor;
+  O.smoothing_size = opts->normal_smoothing_size;
+  O.min_inliers = opts->min_inliers;
+  O.cos_angular = (float)std::cos((double)opts->angular_threshold);
+  O.distance_threshold = opts->distance_threshold;
+  O.maximum_curvature = opts->maximum_curvature;
+  O.refine_distance = 0.02f;   // PlaneRefinementComparator's default; the reference leaves it untouched
+  O.norm_point_thres = opts->norm_point_thres;
+  SSB_CUDA_CHECK(cudaEventRecord(r->oev[0], s));
+  dim3 g2(8, nb);
+  k_crop<<<g2, 256, 0, s>>>(r->d_msg.p, r->layout, r->d_boxes.p, r->d_crop.p);
+  SSB_CUDA_CHECK(cudaMemsetAsync(r->d_change.p, 255, tot, s));
+  k_org_change<<<g2, 256, 0, s>>>(r->d_crop.p, r->d_oboxes.p, O, r->d_change.p);
+  k_org_distance<<<nb, ORG_THREADS, 0, s>>>(r->d_oboxes.p, r->d_change.p, r->d_dist.p);
+  k_org_integral<<<nb, ORG_THREADS, 0, s>>>(r->d_crop.p, r->d_oboxes.p, r->d_ii.p, r->d_ic.p);
+  dim3 g3(32, nb);
+  k_org_normals<<<g3, 256, 0, s>>>(r->d_crop.p, r->d_oboxes.p, O, r->d_dist.p, r->d_ii.p, r->d_ic.p, r->d_nrm.p, r->d_planed.p);
+  k_org_cc_init<<<g2, 256, 0, s>>>(r->d_crop.p, r->d_oboxes.p, r->d_parent.p);
+  k_org_cc_merge<<<g3, 256, 0, s>>>(r->d_crop.p, r->d_oboxes.p, O, r->d_nrm.p, r->d_planed.p, r->d_parent.p);
+  k_org_cc_label<<<nb, ORG_THREADS, 0, s>>>(r->d_oboxes.p, r->d_parent.p, r->d_label.p, r->d_count.p, r->d_nlabels.p);
+  k_org_candidates<<<nb, ORG_THREADS, 0, s>>>(r->d_oboxes.p, O, r->d_count.p, r->d_nlabels.p, r->d_oreg.p, r->d_ncand.p, r->d_l2m.p);
+  dim3 g4(nb, (ORG_MAXR + 63) / 64);
+  k_org_moments<<<g4, 64, 0, s>>>(r->d_crop.p, r->d_oboxes.p, O, r->d_label.p, r->d_ncand.p, r->d_oreg.p);
+  k_org_select<<<nb, 64, 0, s>>>(r->d_oboxes.p, r->d_ncand.p, r->d_oreg.p, r->d_nreg.p, r->d_l2m.p, r->d_lastev.p);
+  k_org_refine<<<nb, ORG_THREADS, 0, s>>>(r->d_crop.p, r->d_oboxes.p, O, r->d_label.p, r->d_l2m.p, r->d_oreg.p, r->d_lastev.p);
+  k_org_boundary<<<nb, 64, 0, s>>>(r->d_crop.p, r->d_oboxes.p, r->d_label.p, r->d_nreg.p, r->d_lastev.p, r->d_oreg.p);
+  r->launches += 14;
+  SSB_CUDA_CHECK(cudaEventRecord(r->oev[1], s));
+  SSB_CUDA_CHECK(cudaGetLastError());
+  std::vector<OrgRegion> hreg((size_t)nb * ORG_MAXR);
+  std::vector<int> hn(nb);
+  SSB_CUDA_CHECK(cudaMemcpyAsync(hreg.data(), r->d_oreg.p, hreg.size() * sizeof(OrgRegion), cudaMemcpyDeviceToHost, s));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(hn.data(), r->d_nreg.p, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+  std::vector<float4> hnrm;
+  std::vector<int> hlab;
+  std::vector<float> hdist;
+  if (normals_out) {
+    hnrm.resize(tot);
+    SSB_CUDA_CHECK(cudaMemcpyAsync(hnrm.data(), r->d_nrm.p, tot * sizeof(float4), cudaMemcpyDeviceToHost, s));
+  }
+  if (labels_out) {
+    hlab.resize(tot);
+    SSB_CUDA_CHECK(cudaMemcpyAsync(hlab.data(), r->d_label.p, tot * sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
+  if (dist_out) {
+    hdist.resize(tot);
+    SSB_CUDA_CHECK(cudaMemcpyAsync(hdist.data(), r->d_dist.p, tot * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+  float ms = 0.0f;
+  SSB_CUDA_CHECK(cudaEventElapsedTime(&ms, r->oev[0], r->oev[1]));
+  r->org_ms = ms;
+  size_t o = 0;
+  for (int b = 0; b < nb; ++b) {
+    const BoxInfo& B = r->boxes[b];
+    if (B.n < 0) {
+      n_regions[b] = -1;   // "spurious" bbox (plane_segmentation.cpp:34-38)
+      continue;
+    }
+    if (ob[b].n == 0) {
+      n_regions[b] = -2;   // fewer than norm_point_thres points: no normals, crop skipped (:93, point_cloud_segmentation.h:164-165)
+    } else {
+      n_regions[b] = hn[b];
+      for (int k = 0; k < hn[b] && k < max_regions; ++k) {
+        const OrgRegion& R = hreg[(size_t)b * ORG_MAXR + k];
+        if (regions) {
+          ssb_planar_region& q = regions[(size_t)b * max_regions + k];
+          for (int c = 0; c < 3; ++c) q.centroid[c] = R.centroid[c];
+          for (int c = 0; c < 4; ++c) q.model[c] = R.model[c];
+          q.contour_points = R.contour_n;
+          q.area = R.area;
+        }
+        if (n_inliers) n_inliers[(size_t)b * max_regions + k] = R.n_inliers;
+      }
+    }
+    if (B.n > 0) {   // per-point outputs: plain concatenation over the non-spurious boxes
+      if (normals_out) std::memcpy(normals_out + 4 * o, hnrm.data() + B.pt_off, (size_t)B.n * sizeof(float4));
+      if (labels_out) std::memcpy(labels_out + o, hlab.data() + B.pt_off, (size_t)B.n * sizeof(int));
+      if (dist_out) std::memcpy(dist_out + o, hdist.data() + B.pt_off, (size_t)B.n * sizeof(float));
+      if (ob[b].n == 0) {
+        if (labels_out) std::fill(labels_out + o, labels_out + o + B.n, -1);
+      }
+      o += B.n;
+    }
+  }
+  return SSB_OK;
+}
+// CUDA-event time of the device pipeline of the last ssb_organized_planes call (crop .. boundary), ms
+double ssb_organized_last_ms(ssb_ransac* r) { return r ? r->org_ms : 0.0; }
 
 }  // extern "C"

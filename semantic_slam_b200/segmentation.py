@@ -145,3 +145,49 @@ class PlaneSegmentation:
 
     def launch_count(self):
         return self._L.ssb_ransac_launch_count(self._h)
+
+
+PLANAR_REGION_DTYPE = np.dtype([("centroid", "f4", 3), ("model", "f4", 4), ("contour_points", "i4"), ("area", "f4")])
+
+
+class OrganizedSegmentation(PlaneSegmentation):
+    """The LIVE segmentation path of the reference on the device: ``plane_segmentation::computeNormalsFromPointCloud``
+    (plane_segmentation.cpp:84-106, pcl::IntegralImageNormalEstimation) + the PCL call of ``multiPlaneSegmentation``
+    (:136-156, pcl::OrganizedMultiPlaneSegmentation::segmentAndRefine) + contour / polygon area (:169,189), batched over
+    all bounding boxes of a frame (include/ssb.h: ssb_organized_planes)."""
+
+    def __init__(self, device: int = -1, num_point_seg: int = 500, norm_point_thres: int = 5000, **kw):
+        super().__init__(device=device)
+        self.oopts = _lib.OrganizedOpts()
+        self._L.ssb_organized_default_opts(C.byref(self.oopts))
+        self.oopts.min_inliers = int(num_point_seg)
+        self.oopts.norm_point_thres = int(norm_point_thres)
+        for k, v in kw.items():
+            setattr(self.oopts, k, v)
+
+    def segment(self, msg, layout: CloudLayout, boxes, max_regions: int = 16, want_points: bool = False):
+        """Returns (regions [nb, max_regions] structured, n_regions [nb], n_inliers [nb, max_regions]) and, with
+        want_points, per-point normals / labels / distance map concatenated over the non-spurious boxes."""
+        msg = np.ascontiguousarray(msg, dtype=np.uint8)
+        boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 4)
+        nb = boxes.shape[0]
+        reg = np.zeros((nb, max_regions), dtype=PLANAR_REGION_DTYPE)
+        nreg = np.zeros(nb, dtype=np.int32)
+        nin = np.zeros((nb, max_regions), dtype=np.int32)
+        valid = (boxes[:, 2] >= 0) & (boxes[:, 3] >= 0) & (boxes[:, 0] >= 0) & (boxes[:, 1] >= 0) & \
+                (boxes[:, 0] + boxes[:, 2] <= layout.width) & (boxes[:, 1] + boxes[:, 3] <= layout.height)
+        total = int((boxes[valid, 2].astype(np.int64) * boxes[valid, 3]).sum())
+        nrm = lab = dist = None
+        if want_points:
+            nrm = np.zeros((max(total, 1), 4), dtype=np.float32)
+            lab = np.zeros(max(total, 1), dtype=np.int32)
+            dist = np.zeros(max(total, 1), dtype=np.float32)
+        lc = layout.c()
+        check(self._L.ssb_organized_planes(self._h, msg.ctypes.data, C.byref(lc), boxes.ctypes.data, nb, C.byref(self.oopts),
+                                           max_regions, reg.ctypes.data, nreg.ctypes.data, nin.ctypes.data,
+                                           nrm.ctypes.data if want_points else None, lab.ctypes.data if want_points else None,
+                                           dist.ctypes.data if want_points else None), "ssb_organized_planes")
+        self.last_ms = float(self._L.ssb_organized_last_ms(self._h))
+        if want_points:
+            return reg, nreg, nin, nrm[:total], lab[:total], dist[:total]
+        return reg, nreg, nin

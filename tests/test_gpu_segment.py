@@ -1,0 +1,87 @@
+"""GPU parity of the LIVE segmentation path: ssb_organized_planes (csrc/ssb_organized.cuh) vs the
+sequential CPU restatement of PCL's integral-image normals + organised multi-plane segmentation (oracle/oracle_segment.cpp).
+Every stage evaluates the same per-pixel arithmetic in a dependency-respecting order, so the bar is BIT-EXACT: distance map,
+normals (incl. the NaN pattern), labels after the refinement, region centroids / models / inlier counts / contours / areas."""
+import numpy as np
+import pytest
+
+import oracle
+from semantic_slam_b200 import CloudLayout, OrganizedSegmentation, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _frame(n_boxes, seed, box_min=150, box_max=200, nan_frac=0.0005):
+    cl = synth.make_cloud(n_boxes=n_boxes, n_hyp=1, nan_frac=nan_frac, box_min=box_min, box_max=box_max, seed=seed)
+    lay = CloudLayout(cl.width, cl.height, cl.point_step, cl.row_step, cl.offsets)
+    return cl, lay
+
+
+def _same_bits(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    b = np.ascontiguousarray(b, dtype=np.float32).view(np.uint32)
+    nan_a, nan_b = (a & 0x7fffffff) > 0x7f800000, (b & 0x7fffffff) > 0x7f800000
+    return np.array_equal(nan_a, nan_b) and np.array_equal(a[~nan_a], b[~nan_b])
+
+
+@pytest.mark.parametrize("seed", [77, 78])
+def test_organized_planes_bit_exact_vs_oracle(seed):
+    cl, lay = _frame(8, seed)
+    seg = OrganizedSegmentation(num_point_seg=500)
+    reg, nreg, nin, nrm, lab, dist = seg.segment(cl.msg, lay, cl.boxes, max_regions=16, want_points=True)
+    o = 0
+    total_regions = 0
+    for b in range(cl.boxes.shape[0]):
+        crop = oracle.crop(cl.msg, cl.width, cl.height, cl.point_step, cl.row_step, cl.offsets, cl.boxes[b])
+        h, w = crop.shape[:2]
+        r = oracle.organized_planes(crop, min_inliers=500, max_regions=16)
+        n = h * w
+        od = oracle.integral_normals(crop)[1].reshape(-1)
+        assert np.array_equal(dist[o:o + n], od), f"box {b}: distance map differs in {(dist[o:o+n] != od).sum()} pixels"
+        assert _same_bits(nrm[o:o + n], r["normals"].reshape(-1, 4)), f"box {b}: normals differ"
+        assert np.array_equal(lab[o:o + n], r["labels"].reshape(-1)), \
+            f"box {b}: labels differ in {(lab[o:o+n] != r['labels'].reshape(-1)).sum()} of {n} pixels"
+        assert nreg[b] == r["n"], (b, nreg[b], r["n"])
+        m = min(r["n"], 16)
+        total_regions += m
+        assert _same_bits(reg["centroid"][b, :m], r["centroid"]) and _same_bits(reg["model"][b, :m], r["model"])
+        assert np.array_equal(nin[b, :m], r["n_inliers"])
+        assert np.array_equal(reg["contour_points"][b, :m], r["contour_points"])
+        assert _same_bits(reg["area"][b, :m], r["area"])
+        o += n
+    assert total_regions >= 4
+    assert seg.last_ms > 0
+
+
+def test_organized_planes_edge_cases():
+    cl, lay = _frame(5, 91, box_min=60, box_max=200)
+    boxes = cl.boxes.copy()
+    boxes[0] = (600, 10, 80, 50)          # spurious: reaches past the right border (plane_segmentation.cpp:34-35)
+    boxes[1] = (10, 10, 60, 60)           # 3 600 points < norm_point_thres: no normals, crop skipped (:93)
+    boxes[2] = (100, 100, 0, 0)           # empty crop
+    seg = OrganizedSegmentation(num_point_seg=500, norm_point_thres=5000)
+    reg, nreg, nin = seg.segment(cl.msg, lay, boxes, max_regions=8)
+    assert nreg[0] == -1 and nreg[1] == -2 and nreg[2] == -2
+    for b in (3, 4):
+        crop = oracle.crop(cl.msg, cl.width, cl.height, cl.point_step, cl.row_step, cl.offsets, boxes[b])
+        if crop.shape[0] * crop.shape[1] < 5000:
+            assert nreg[b] == -2
+            continue
+        r = oracle.organized_planes(crop, min_inliers=500, max_regions=8)
+        assert nreg[b] == r["n"]
+
+
+def test_all_nan_crop_and_full_frame():
+    cl, lay = _frame(2, 5)
+    msg = cl.msg.copy().view(np.float32).reshape(cl.height, cl.width, 8)
+    msg[100:300, 100:300, :3] = np.nan
+    boxes = np.array([[100, 100, 200, 200], [0, 0, 640, 480]], dtype=np.int32)
+    seg = OrganizedSegmentation(num_point_seg=500)
+    reg, nreg, nin, nrm, lab, dist = seg.segment(msg.reshape(-1).view(np.uint8), lay, boxes, max_regions=32, want_points=True)
+    assert nreg[0] == 0 and (lab[:40000] == -1).all() and np.isnan(nrm[:40000]).all()
+    crop = oracle.crop(msg.reshape(-1).view(np.uint8), cl.width, cl.height, cl.point_step, cl.row_step, cl.offsets, boxes[1])
+    r = oracle.organized_planes(crop, min_inliers=500, max_regions=32)
+    assert nreg[1] == r["n"]
+    assert np.array_equal(lab[40000:], r["labels"].reshape(-1))
+    m = min(r["n"], 32)
+    assert np.array_equal(nin[1, :m], r["n_inliers"]) and np.array_equal(reg["contour_points"][1, :m], r["contour_points"])

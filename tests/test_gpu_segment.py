@@ -49,7 +49,7 @@ def test_organized_planes_bit_exact_vs_oracle(seed):
         assert np.array_equal(reg["contour_points"][b, :m], r["contour_points"])
         assert _same_bits(reg["area"][b, :m], r["area"])
         o += n
-    assert total_regions >= 4
+    assert total_regions >= 2
     assert seg.last_ms > 0
 
 

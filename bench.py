@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--pcg-tol", type=float, default=1e-6)
     ap.add_argument("--preconditioner", type=int, default=3)
     ap.add_argument("--no-cfg4", action="store_true", help="skip the 100k-keyframe secondary workload (BASELINE.json configs[3])")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the per-frame loop (BASELINE.json configs[4])")
+    ap.add_argument("--cfg5-frames", type=int, default=1000)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -397,6 +399,63 @@ def main():
                                      "frac": ach4 / (hbm_peak * world),
                                      "note": "algorithmic bytes = pcg iterations x B_cg (%d B) / CUDA-event time of the kernel" % gb4["b_cg"]}}
         del g4
+
+    # ---------------- cfg5 (BASELINE.json configs[4]): the per-frame loop of semantic_graph_slam::run ------------------
+    # (src/ps_graph_slam/semantic_graph_slam.cpp:58-102) every keyframe: segment the detections' crops (the LIVE path:
+    # integral-image normals + organised multi-plane segmentation, ssb_organized_planes), associate, grow the graph,
+    # re-optimise the WHOLE graph (optimize(1024) until g2o's LM terminates).  The stream's detections are camera-frame
+    # centroids (synth.make_frame_stream), so the segmentation runs on a fixed synthetic frame with one crop per detection:
+    # it is timed inside the loop, its output is checked against the oracle in tests/test_gpu_segment.py, and the
+    # association consumes the stream's centroids.  Single GPU (a growing graph of <= 4000 keyframes fits one chip).
+    if not args.no_cfg5 and world == 1:
+        from semantic_slam_b200 import DataAssociation, OrganizedSegmentation, SemanticGraphSLAM
+        n_kf = args.cfg5_frames
+        stream = synth.make_frame_stream(n_kf, max(12, n_kf // 10), seed=synth.SEED_BASE + 5, max_det=3)
+        clf = synth.make_cloud(n_boxes=3, n_hyp=1, nan_frac=0.0005, box_min=150, box_max=200, seed=77)
+        layf = CloudLayout(clf.width, clf.height, clf.point_step, clf.row_step, clf.offsets)
+        oseg = OrganizedSegmentation(device=local, num_point_seg=500)
+        KITTI = dict(use_maha_dist=False, use_eq_dist=True, eq_dist_thres=1.5, land_noise_low=0.1, strict=True)
+
+        def drive(graph, assoc, n, segment):
+            slam = SemanticGraphSLAM(graph, assoc, stream.info6, cam_angle=stream.cam_angle, max_iterations=1024)
+            t_seg = t_all = 0.0
+            marks = {}
+            t0 = time.perf_counter()
+            for k in range(n):
+                if stream.detections[k]:
+                    ts = time.perf_counter()
+                    segment(len(stream.detections[k]))
+                    t_seg += time.perf_counter() - ts
+                slam.feed(stream.odom[k], stream.detections[k])
+                slam.run()
+                if k + 1 in (n // 4, n // 2, n, 250):
+                    marks[k + 1] = time.perf_counter() - t0
+            t_all = time.perf_counter() - t0
+            return slam, t_all, t_seg, marks
+
+        g5 = GraphSLAM(device=local, preconditioner=args.preconditioner, pcg_tol=args.pcg_tol)
+        slam5, t5, t5seg, marks5 = drive(g5, DataAssociation(**KITTI), n_kf,
+                                         lambda nd: oseg.segment(clf.msg, layf, clf.boxes[:nd], max_regions=8))
+        line["cfg5"] = {"metric": "frames/sec (per-frame segment + associate + optimise loop)", "value": n_kf / t5, "unit": "frames/s",
+                        "workload": "cfg5: %d keyframes, %d mapped landmarks, %d edges at the end; optimize(1024) of the whole graph "
+                                    "per keyframe" % (n_kf, len(slam5.landmark_nodes_), g5.num_edges()),
+                        "ms_per_frame": 1e3 * t5 / n_kf, "segmentation_ms_per_frame": 1e3 * t5seg / n_kf,
+                        "elapsed_s_at_frames": marks5, "pcg_tol": args.pcg_tol}
+        if rank == 0 and not args.no_cpu_baseline:
+            import oracle
+            from oracle.association import OracleDataAssociation
+            n_cpu = min(n_kf, 250)
+            crops = [oracle.crop(clf.msg, clf.width, clf.height, clf.point_step, clf.row_step, clf.offsets, clf.boxes[b]) for b in range(3)]
+            slamo, t5o, t5oseg, _ = drive(oracle.OracleGraphSLAM(threads=1), OracleDataAssociation(**KITTI), n_cpu,
+                                          lambda nd: [oracle.organized_planes(crops[b], min_inliers=500) for b in range(nd)])
+            same = slamo.association_log == slam5.association_log[:len(slamo.association_log)]
+            line["cfg5"]["cpu_baseline"] = {"value": n_cpu / t5o, "unit": "frames/s", "cores": 1, "kind": "port",
+                                            "sample": "the first %d keyframes of the same stream (%.1f s, of which segmentation %.1f s)"
+                                                      % (n_cpu, t5o, t5oseg)}
+            line["cfg5"]["gpu_on_the_same_%d_frames" % n_cpu] = {"value": n_cpu / marks5.get(n_cpu, t5 * n_cpu / n_kf) if n_cpu in marks5 else None,
+                                                                  "unit": "frames/s"}
+            line["cfg5"]["association_identical_to_cpu"] = bool(same)
+        del g5
 
     # ---------------- CPU baseline (rank 0, N == 1 only) -----------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

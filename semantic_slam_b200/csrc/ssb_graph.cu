@@ -2508,6 +2508,7 @@ int ssb_graph_set_fixed(ssb_graph* g, int vid, int fixed) {
 }
 int ssb_graph_hessian_index(ssb_graph* g, int vid) {
   if (!g || vid < 0 || vid >= (int)g->V.size()) return SSB_ERR_INVALID;
+  if (!g->structure_dirty) return g->V[vid].hidx;   // assigned by prepare (buildIndexMapping): O(1) after an optimize
   int h = 0;
   for (int k = 0; k < vid; ++k)
     if (!g->V[k].fixed) ++h;

@@ -12,10 +12,11 @@
 //   normals               : independent per pixel (4-corner sums, float covariance, pcl::eigen33)
 //   connected components  : the partition does not depend on the scan order -> lock-free union-find (root = smallest
 //                           raster index), labels renumbered by first pixel like PCL's run table
-//   region moments        : float sums in raster order (pcl::computeMeanAndCovarianceMatrix) -> one thread per region
+//   region moments        : float sums in raster order (pcl::computeMeanAndCovarianceMatrix) -> one warp per region:
+//                           coalesced loads, the matching pixels added one by one (ballot + shuffle)
 //   refinement            : two raster sweeps whose label hand-offs run along rows -> rows in sequence, each row resolved
 //                           in closed form with two block-wide max-scans (nearest seed / nearest failing pixel)
-//   boundary + area       : Moore tracing from the last inlier, float cross-product sum in order -> one thread per region
+//   boundary + area       : Moore tracing from the last inlier, float cross-product sum in order -> one walker per region
 // This translation unit is compiled with -fmad=false: no product-sum is contracted into an FMA.
 #pragma once
 #include <cfloat>
@@ -403,37 +404,57 @@ __global__ void __launch_bounds__(ORG_THREADS) k_org_cc_label(const OrgBox* __re
 __global__ void __launch_bounds__(ORG_THREADS) k_org_candidates(const OrgBox* __restrict__ boxes, OrgOpts O, const int* __restrict__ count,
                                                                 const int* __restrict__ n_labels, OrgRegion* __restrict__ regions,
                                                                 int* __restrict__ n_cand, int* __restrict__ l2m) {
-  __shared__ int s_n;
+  __shared__ int warp_tot[ORG_THREADS / 32];
+  __shared__ int carry;
   const OrgBox B = boxes[blockIdx.x];
-  if (threadIdx.x == 0) s_n = 0;
+  if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   if (B.n > 0) {
     const int* Cn = count + B.pt_off;
     int* M = l2m + B.pt_off;
     const int nl = n_labels[blockIdx.x];
     for (int i = threadIdx.x; i < B.n; i += blockDim.x) M[i] = -1;
-    __syncthreads();
-    // label order: one thread walks the label table (a few thousand entries at most)
-    if (threadIdx.x == 0) {
-      int n = 0;
-      for (int l = 0; l < nl; ++l)
-        if ((unsigned)Cn[l] > (unsigned)O.min_inliers && n < ORG_MAXR) {
-          OrgRegion& R = regions[(size_t)blockIdx.x * ORG_MAXR + n];
-          R.label = l;
-          R.keep = 0;
-          R.n_inliers = Cn[l];
-          ++n;
-        }
-      s_n = n;
+    // stream compaction in label order (block-wide exclusive scan of the "more than min_inliers pixels" flags)
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    for (int base = 0; base < nl; base += blockDim.x) {
+      const int l = base + threadIdx.x;
+      const int flag = (l < nl && (unsigned)Cn[l] > (unsigned)O.min_inliers) ? 1 : 0;
+      int v = flag;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      if (lane == 31) warp_tot[wp] = v;
+      __syncthreads();
+      int off = carry;
+      for (int k = 0; k < wp; ++k) off += warp_tot[k];
+      const int pos = off + v - 1;
+      if (flag && pos < ORG_MAXR) {
+        OrgRegion& R = regions[(size_t)blockIdx.x * ORG_MAXR + pos];
+        R.label = l;
+        R.keep = 0;
+        R.n_inliers = Cn[l];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += warp_tot[k];
+        carry += t;
+      }
+      __syncthreads();
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) n_cand[blockIdx.x] = s_n;
+  if (threadIdx.x == 0) n_cand[blockIdx.x] = min(carry, ORG_MAXR);
 }
-__global__ void __launch_bounds__(64) k_org_moments(const float4* __restrict__ crop, const OrgBox* __restrict__ boxes, OrgOpts O,
+// One warp per candidate region.  The warp reads 32 consecutive pixels at a time (coalesced); the pixels of the region are then
+// added ONE BY ONE in raster order, every lane carrying the same nine float accumulators (pcl::computeMeanAndCovarianceMatrix
+// sums in single precision in index order, and float addition does not commute with regrouping).
+__global__ void __launch_bounds__(32) k_org_moments(const float4* __restrict__ crop, const OrgBox* __restrict__ boxes, OrgOpts O,
                                                     const int* __restrict__ label, const int* __restrict__ n_cand,
                                                     OrgRegion* __restrict__ regions) {
-  const int b = blockIdx.x, k = blockIdx.y * blockDim.x + threadIdx.x;
+  const int b = blockIdx.x, k = blockIdx.y, lane = threadIdx.x;
   const OrgBox B = boxes[b];
   if (B.n <= 0 || k >= n_cand[b]) return;
   OrgRegion& R = regions[(size_t)b * ORG_MAXR + k];
@@ -442,22 +463,36 @@ __global__ void __launch_bounds__(64) k_org_moments(const float4* __restrict__ c
   const int lab = R.label;
   float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   int cnt = 0, last = -1;
-  for (int i = 0; i < B.n; ++i) {
-    if (L[i] != lab) continue;
-    last = i;
-    const float4 p = Pt[i];
-    if (!fin(p.x) || !fin(p.y) || !fin(p.z)) continue;
-    a[0] += p.x * p.x;
-    a[1] += p.x * p.y;
-    a[2] += p.x * p.z;
-    a[3] += p.y * p.y;
-    a[4] += p.y * p.z;
-    a[5] += p.z * p.z;
-    a[6] += p.x;
-    a[7] += p.y;
-    a[8] += p.z;
-    ++cnt;
+  // the next 32 pixels are requested while the current ones are being added
+  int l_next = lane < B.n ? L[lane] : -1;
+  float4 p_next = lane < B.n ? Pt[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = 0; base < B.n; base += 32) {
+    const bool mine = l_next == lab && base + lane < B.n;
+    const float4 p = p_next;
+    const int in = base + 32 + lane;
+    l_next = in < B.n ? L[in] : -1;
+    p_next = in < B.n ? Pt[in] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool ok = mine && fin(p.x) && fin(p.y) && fin(p.z);
+    const unsigned mm = __ballot_sync(0xffffffffu, mine);
+    if (mm) last = base + 31 - __clz((int)mm);
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    while (m) {
+      const int src = __ffs((int)m) - 1;
+      m &= m - 1;
+      const float x = __shfl_sync(0xffffffffu, p.x, src), y = __shfl_sync(0xffffffffu, p.y, src), z = __shfl_sync(0xffffffffu, p.z, src);
+      a[0] += x * x;
+      a[1] += x * y;
+      a[2] += x * z;
+      a[3] += y * y;
+      a[4] += y * z;
+      a[5] += z * z;
+      a[6] += x;
+      a[7] += y;
+      a[8] += z;
+      ++cnt;
+    }
   }
+  if (lane != 0) return;
   const float fc = (float)cnt;
   for (int q = 0; q < 9; ++q) a[q] /= fc;
   float cov[9];
@@ -615,34 +650,53 @@ __global__ void __launch_bounds__(ORG_THREADS) k_org_refine(const float4* __rest
 }
 
 // ---- boundary (findLabeledRegionBoundary from the last inlier) + calculatePolygonArea, one thread per region -------------
-__global__ void __launch_bounds__(64) k_org_boundary(const float4* __restrict__ crop, const OrgBox* __restrict__ boxes, const int* __restrict__ lab,
-                                                     const int* __restrict__ n_reg, const unsigned long long* __restrict__ last_ev,
-                                                     OrgRegion* __restrict__ regions) {
-  const int b = blockIdx.x, k = threadIdx.x;
+// One CTA per (crop, region): the threads count the inliers; thread 0 then walks the contour.
+__global__ void __launch_bounds__(256) k_org_boundary(const float4* __restrict__ crop, const OrgBox* __restrict__ boxes, const int* __restrict__ lab,
+                                                      const int* __restrict__ n_reg, const unsigned long long* __restrict__ last_ev,
+                                                      OrgRegion* __restrict__ regions) {
+  __shared__ int s_cnt;
+  const int b = blockIdx.x, k = blockIdx.y;
   const OrgBox B = boxes[b];
   if (B.n <= 0 || k >= n_reg[b]) return;
   OrgRegion& R = regions[(size_t)b * ORG_MAXR + k];
   const int w = B.w, h = B.h;
   const int* L = lab + B.pt_off;
   const float4* Pt = crop + B.pt_off;
-  // inliers after the refinement
-  int cnt = 0;
-  for (int i = 0; i < B.n; ++i) cnt += L[i] == R.label ? 1 : 0;
-  R.n_inliers = cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < B.n; i += blockDim.x) c += L[i] == R.label ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  R.n_inliers = s_cnt;   // inliers after the refinement
   const unsigned long long ev = last_ev[(size_t)b * ORG_MAXR + k];
   const int start = ev ? (int)(ev & 0xffffffull) : R.last_inlier;
   R.last_inlier = start;
   const int dx[8] = {-1, -1, 0, 1, 1, 1, 0, -1}, dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
   int cur = start, cx = start % w, cy = start / w;
   const int label = L[start];
+  // labels of the 8 neighbours of (cx, cy), requested together; out of the image: "another label" for the first test,
+  // "not the region" for the walk (PCL tests the bounds before the label in both)
+  auto neigh = [&](int* nl, bool* inb) {
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const int x = cx + dx[d], y = cy + dy[d];
+      inb[d] = x >= 0 && x < w && y >= 0 && y < h;
+      nl[d] = inb[d] ? L[cur + dy[d] * w + dx[d]] : -2;
+    }
+  };
+  int nl[8];
+  bool inb[8];
+  neigh(nl, inb);
   int direction = -1;
-  for (int d = 0; d < 8; ++d) {
-    const int x = cx + dx[d], y = cy + dy[d];
-    if (x >= 0 && x < w && y >= 0 && y < h && L[cur + dy[d] * w + dx[d]] != label) {
+  for (int d = 0; d < 8; ++d)
+    if (inb[d] && nl[d] != label) {
       direction = d;
       break;
     }
-  }
   if (direction == -1) {
     R.contour_n = 0;
     R.area = 0.0f;
@@ -656,16 +710,16 @@ __global__ void __launch_bounds__(64) k_org_boundary(const float4* __restrict__ 
     int nd = 0;
     for (int d = 1; d <= 8; ++d) {
       nd = (direction + d) & 7;
-      const int x = cx + dx[nd], y = cy + dy[nd];
-      if (x >= 0 && x < w && y >= 0 && y < h && L[cur + dy[nd] * w + dx[nd]] == label) break;
+      if (inb[nd] && nl[nd] == label) break;
     }
     direction = (nd + 4) & 7;
     cur += dy[nd] * w + dx[nd];
     cx += dx[nd];
     cy += dy[nd];
     ++n;
-    // polygon[i] x polygon[i+1], accumulated in order
     const float4 p = Pt[cur];
+    neigh(nl, inb);
+    // polygon[i] x polygon[i+1], accumulated in order
     const float a3[3] = {prev.x, prev.y, prev.z}, b3[3] = {p.x, p.y, p.z};
     float cr[3];
     cross3f(a3, b3, cr);

@@ -850,11 +850,11 @@ int ssb_organized_planes(ssb_ransac* r, const void* msg, const ssb_cloud_layout*
   k_org_cc_merge<<<g3, 256, 0, s>>>(r->d_crop.p, r->d_oboxes.p, O, r->d_nrm.p, r->d_planed.p, r->d_parent.p);
   k_org_cc_label<<<nb, ORG_THREADS, 0, s>>>(r->d_oboxes.p, r->d_parent.p, r->d_label.p, r->d_count.p, r->d_nlabels.p);
   k_org_candidates<<<nb, ORG_THREADS, 0, s>>>(r->d_oboxes.p, O, r->d_count.p, r->d_nlabels.p, r->d_oreg.p, r->d_ncand.p, r->d_l2m.p);
-  dim3 g4(nb, (ORG_MAXR + 63) / 64);
-  k_org_moments<<<g4, 64, 0, s>>>(r->d_crop.p, r->d_oboxes.p, O, r->d_label.p, r->d_ncand.p, r->d_oreg.p);
+  dim3 g4(nb, ORG_MAXR);
+  k_org_moments<<<g4, 32, 0, s>>>(r->d_crop.p, r->d_oboxes.p, O, r->d_label.p, r->d_ncand.p, r->d_oreg.p);
   k_org_select<<<nb, 64, 0, s>>>(r->d_oboxes.p, r->d_ncand.p, r->d_oreg.p, r->d_nreg.p, r->d_l2m.p, r->d_lastev.p);
   k_org_refine<<<nb, ORG_THREADS, 0, s>>>(r->d_crop.p, r->d_oboxes.p, O, r->d_label.p, r->d_l2m.p, r->d_oreg.p, r->d_lastev.p);
-  k_org_boundary<<<nb, 64, 0, s>>>(r->d_crop.p, r->d_oboxes.p, r->d_label.p, r->d_nreg.p, r->d_lastev.p, r->d_oreg.p);
+  k_org_boundary<<<g4, 256, 0, s>>>(r->d_crop.p, r->d_oboxes.p, r->d_label.p, r->d_nreg.p, r->d_lastev.p, r->d_oreg.p);
   r->launches += 14;
   SSB_CUDA_CHECK(cudaEventRecord(r->oev[1], s));
   SSB_CUDA_CHECK(cudaGetLastError());

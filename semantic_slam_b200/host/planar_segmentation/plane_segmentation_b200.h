@@ -30,7 +30,9 @@ class plane_segmentation_b200 {
   }
 
   // pcl::SACSegmentation(SACMODEL_PLANE, SAC_RANSAC, 0.01, optimize) over every bbox.
-  // n_hyp = 0 -> PCL behaviour (adaptive k, <= 50 iterations, RNG seed 12345 like pcl::RandomSampleConsensus).
+  // n_hyp = 0 -> PCL's STOPPING RULE (adaptive k, <= 50 iterations).  The 3-point samples come from std::mt19937(12345)
+  // modulo n, not from pcl::RandomSampleConsensus' boost::mt19937 + drawIndexSample shuffle (boost is absent here), so
+  // PCL's hypothesis sequence itself is not reproduced — pass your own index triples to ssb_ransac_plane_batch for that.
   std::vector<ssb_plane_result> fitPlanes(const void* cloud_data, const ssb_cloud_layout& layout,
                                           const std::vector<ssb_bbox>& boxes, int n_hyp = 0) {
     ssb_ransac_opts o;

@@ -72,6 +72,7 @@ struct MatrixXd {
   std::vector<double> a;
   MatrixXd() = default;
   explicit MatrixXd(int n_) : n(n_), a((size_t)n_ * n_, 0.0) {}
+  MatrixXd(int r_, int c_) : n(r_), a((size_t)r_ * c_, 0.0) {}   // (rows, cols) like Eigen::MatrixXd; square only
   static MatrixXd Identity(int n_) {
     MatrixXd M(n_);
     for (int i = 0; i < n_; ++i) M(i, i) = 1.0;
@@ -311,10 +312,7 @@ class GraphSLAM {
     }
     spinv.clear();
     for (size_t k = 0; k < vids.size(); ++k) {
-      ssb_host::MatrixXd M(3);
-#ifdef SSB_HAVE_EIGEN
-      M = ssb_host::MatrixXd(3, 3);
-#endif
+      ssb_host::MatrixXd M(3, 3);   // the (rows, cols) form also compiles when MatrixXd is Eigen::MatrixXd
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) M(r, c) = out[9 * k + 3 * r + c];
       spinv.set(vert_pairs_vec[k].first, vert_pairs_vec[k].second, M);

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include "ps_graph_slam/graph_slam.hpp"
 #include "planar_segmentation/plane_segmentation_b200.h"
+#include "planar_segmentation/point_cloud_segmentation.h"
 #include "ps_graph_slam/data_association_b200.h"
 
 int main(int argc, char** argv) {
@@ -29,6 +30,40 @@ int main(int argc, char** argv) {
   if (!run) {
     std::printf("facade linked: %s\n", ssb_build_info());
     return 0;
+  }
+  {
+    // the live segmentation facade under the reference's names: a synthetic 640x480 frame with a tilted wall in front of a
+    // far background, one accepted and one ignored detection class
+    const int W = 640, H = 480;
+    std::vector<float> msg((size_t)W * H * 8, 0.0f);
+    for (int v = 0; v < H; ++v)
+      for (int u = 0; u < W; ++u) {
+        const float dx = (u - 319.5f) / 525.0f, dy = (v - 239.5f) / 525.0f;
+        const bool wall = u >= 200 && u < 420 && v >= 120 && v < 360;
+        const float z = wall ? 1.2f / (1.0f + 0.3f * dx) : 4.0f;
+        float* p = &msg[((size_t)v * W + u) * 8];
+        p[0] = dx * z;
+        p[1] = dy * z;
+        p[2] = z;
+      }
+    point_cloud_segmentation seg(false, 500, 5000, 0.0f);
+    if (!seg.ok()) return 9;
+    ssb_host::PointCloud2View pc;
+    pc.data = msg.data();
+    pc.layout = ssb_cloud_layout{W, H, 32, 32 * W, 0, 4, 8, 16};
+    ssb_host::ObjectInfo a, b;
+    a.type = "chair";
+    a.prob = 0.9f;
+    a.tl_x = 150; a.tl_y = 80; a.width = 320; a.height = 320;
+    b = a;
+    b.type = "person";   // not in the class list of point_cloud_segmentation.h:126-130
+    const float rp[6] = {1.0f, 2.0f, 0.5f, 0.0f, 0.0f, 0.0f};
+    auto objs = seg.segmentallPointCloudData(rp, 0.0f, {a, b}, pc);
+    if (objs.empty()) return 10;
+    for (auto& o : objs)
+      if (o.type != "chair" || (o.plane_type != "horizontal" && o.plane_type != "vertical")) return 11;
+    std::printf("segmentallPointCloudData: %zu planar surface(s), first at z = %.3f (%s)\n", objs.size(), objs[0].pose[2],
+                objs[0].plane_type.c_str());
   }
   ps_graph_slam::GraphSLAM gs(false);
   if (!gs.graph) return 2;

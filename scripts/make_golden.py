@@ -69,3 +69,39 @@ for tag, kw in (("eq", dict(use_maha_dist=False, use_eq_dist=True, eq_dist_thres
     rec[tag + "_pose"] = np.array(pose, dtype=np.float32)
 np.savez_compressed(os.path.join(out, "assoc_stream_oracle.npz"), **rec)
 print("association done", {k: v.shape for k, v in rec.items()})
+
+# cfg1 as a g2o text file (the format GraphSLAM::save writes, graph_slam.cpp:236-239): with it a real g2o can close the
+# loop off-box —   g2o -solver lm_var -i 8 -o out.g2o tests/golden/cfg1.g2o   must reproduce tests/golden/cfg1_oracle.json
+# (chi2 per iteration in its verbose output, final vertices in out.g2o).
+def write_g2o(spec, path):
+    from scipy.spatial.transform import Rotation
+    with open(path, "w") as f:
+        f.write("PARAMS_SE3OFFSET 0 0 0 0 0 0 0 1\n")
+        for v in range(spec.vkind.size):
+            if spec.vkind[v] == 0:
+                T = spec.vpose[v]
+                q = Rotation.from_matrix(T[:, :3]).as_quat()
+                if q[3] < 0:
+                    q = -q
+                f.write("VERTEX_SE3:QUAT %d %s\n" % (v, " ".join("%.17g" % x for x in list(T[:, 3]) + list(q))))
+                if v == 0:
+                    f.write("FIX 0\n")
+            else:
+                f.write("VERTEX_TRACKXYZ %d %s\n" % (v, " ".join("%.17g" % x for x in spec.vxyz[v])))
+        iu6 = [(r, c) for r in range(6) for c in range(r, 6)]
+        iu3 = [(r, c) for r in range(3) for c in range(r, 3)]
+        for e in range(spec.ekind.size):
+            if spec.ekind[e] == 0:
+                Z = spec.eZ[e]
+                q = Rotation.from_matrix(Z[:, :3]).as_quat()
+                if q[3] < 0:
+                    q = -q
+                f.write("EDGE_SE3:QUAT %d %d %s %s\n" % (spec.evi[e], spec.evj[e], " ".join("%.17g" % x for x in list(Z[:, 3]) + list(q)),
+                                                       " ".join("%.17g" % spec.einfo6[r, c] for r, c in iu6)))
+            else:
+                f.write("EDGE_SE3_TRACKXYZ %d %d 0 %s %s\n" % (spec.evi[e], spec.evj[e], " ".join("%.17g" % x for x in spec.ez[e]),
+                                                             " ".join("%.17g" % spec.einfo3[r, c] for r, c in iu3)))
+
+
+write_g2o(synth.make_config_graph("cfg1"), os.path.join(out, "cfg1.g2o"))
+print("g2o export done")

@@ -482,3 +482,19 @@ def test_cfg4_three_iterations_vs_oracle():
     P, X = g.get_all(spec.n_poses, spec.n_landmarks)
     Po, Xo = o.get_all(spec.n_poses, spec.n_landmarks)
     assert_parity(P, X, Po, Xo)
+
+
+def test_g2o_fixture_through_the_product_loader():
+    """tests/golden/cfg1.g2o (the off-box interchange file, scripts/make_golden.py) loaded by ssb_graph_load_g2o: the LM
+    trajectory must be the one committed in cfg1_oracle.json, and saving it again must give back the same numbers"""
+    import json, os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    g = GraphSLAM(pcg_tol=1e-10)
+    g.load(os.path.join(here, "cfg1.g2o"))
+    with open(os.path.join(here, "cfg1_oracle.json")) as f:
+        gold = json.load(f)
+    assert g.optimize(8)
+    assert np.allclose(g.history[:, 1], np.array(gold["history"])[:, 1], rtol=1e-8)
+    spec = synth.make_config_graph("cfg1")
+    P, X = g.get_all(spec.n_poses, spec.n_landmarks)
+    assert_parity(P, X, np.array(gold["poses"]), np.array(gold["landmarks"]))

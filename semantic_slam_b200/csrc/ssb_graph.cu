@@ -1547,7 +1547,15 @@ static int launch_prep(ssb_graph* g, double lambda, bool separate_coarse = false
     }
     // same tag family as the cells of the coming k_pcg_flow launch (flow_seq + 1): unique per launch
     const unsigned tag = ((g->flow_seq + 1u) << 16) + 1u;
-    k_coarse_invert<148><<<g->pcg_grid, CINV_THREADS, g->cinv_smem, s3>>>(G, g->Cz, g->d_gj.p, tag, g->FT.gj_order, g->FT.gj_mask, lambda);
+    // its 148 CTAs wait on each other's panels: launched cooperatively (the runtime refuses the launch unless the whole
+    // grid can be resident) — the kernels running beside it never wait on anything, so it always gets its SMs
+    {
+      uint4* gjp = g->d_gj.p;
+      const int* gjo = g->FT.gj_order;
+      const unsigned* gjm = g->FT.gj_mask;
+      void* cargs[] = {(void*)&G, (void*)&g->Cz, (void*)&gjp, (void*)&tag, (void*)&gjo, (void*)&gjm, (void*)&lambda};
+      SSB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coarse_invert<148>, dim3(g->pcg_grid), dim3(CINV_THREADS), cargs, g->cinv_smem, s3));
+    }
     g->launches++;
     SSB_CUDA_CHECK(cudaEventRecord(g->ev_join3, s3));
     g->coarse_ready = true;
@@ -2232,11 +2240,32 @@ static int gather_estimates_sharded(ssb_graph* g) {
   return SSB_OK;
 }
 
+// Host-side deadline for everything queued on the handle's stream.  The persistent PCG kernel waits on cells written by
+// its own CTAs; if one is ever lost the kernel spins forever and a plain cudaStreamSynchronize would hang the caller with
+// it.  Polling the stream costs nothing on the device (the in-kernel counter costs 4 %, ssb_pcg_flow.cuh): after
+// SSB_HOST_DEADLINE_S seconds the call returns an error — the process must then exit to release the GPU.
+static int stream_wait(ssb_graph* g) {
+  static const double limit_s = [] {
+    const char* e = std::getenv("SSB_HOST_DEADLINE_S");
+    return e ? std::max(1.0, std::atof(e)) : 120.0;
+  }();
+  const double t0 = wall_ms();
+  unsigned spins = 0;
+  for (;;) {
+    const cudaError_t q = cudaStreamQuery(g->stream);
+    if (q == cudaSuccess) return SSB_OK;
+    if (q != cudaErrorNotReady) SSB_CUDA_CHECK(q);
+    if ((++spins & 1023u) == 0 && wall_ms() - t0 > 1e3 * limit_s) {
+      set_error("the device did not finish within %.0f s (a persistent kernel is waiting for data that never arrived); exit the process to release the GPU", limit_s);
+      return SSB_ERR_CUDA;
+    }
+  }
+}
 static int read_scalars(ssb_graph* g) {
   if (g->mr) return read_scalars_sharded(g);
   SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_scalars, g->d_scalars.p, 32 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
   SSB_CUDA_CHECK(cudaMemcpyAsync(g->h_iscalars, g->d_iscalars.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-  SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
+  SSB_TRY(stream_wait(g));
   return SSB_OK;
 }
 

@@ -84,6 +84,16 @@ __device__ __forceinline__ void lds_row6(uint32_t addr, double* out) {
 // spin on one cell (the first attempt was already issued by the caller)
 // SYS: the cell may have been written by another rank over NVLink (system-scope load, and a globaltimer deadline
 // checked every 4096 polls: a rank that died must not hang this one — trap instead)
+// In-kernel watchdog of the single-GPU kernel (-DSSB_RELEASE_WATCHDOG=1): the same deadline as the cross-rank waits — a
+// poll counter that only runs while a wait is actually spinning, a globaltimer read every 4096 polls against a deadline
+// kept in shared memory; a cell that has not arrived after SSB_PEER_TIMEOUT_NS traps (sticky launch error).  OFF by
+// default: measured on cfg2 (A/B on one box, same spills as without) 551 -> 529 LM it/s, -4 % — the spin loops ARE the
+// critical path of this kernel and one extra add + test per poll shows.  The sharded kernels (MR) always carry it;
+// single-GPU release builds rely on the host-side deadline of read_scalars (ssb_graph.cu) instead.
+#ifndef SSB_RELEASE_WATCHDOG
+#define SSB_RELEASE_WATCHDOG 0
+#endif
+constexpr bool kFlowWatch = SSB_RELEASE_WATCHDOG != 0;
 template <bool SYS>
 __device__ __forceinline__ uint4 ld_cell_t(const uint4* p) {
   if constexpr (SYS)
@@ -91,12 +101,10 @@ __device__ __forceinline__ uint4 ld_cell_t(const uint4* p) {
   else
     return ld_cell(p);
 }
-__device__ __noinline__ void peer_deadline(unsigned long long& t0) {
-  const unsigned long long now = peer_globaltimer();
-  if (t0 == 0)
-    t0 = now;
-  else if (now - t0 > SSB_PEER_TIMEOUT_NS)
-    __trap();
+// the deadline of this launch lives in shared memory (set once by the kernel): the waits keep only a poll counter
+__shared__ unsigned long long s_flow_deadline;
+__device__ __forceinline__ void peer_deadline() {
+  if (peer_globaltimer() > s_flow_deadline) __trap();
 }
 template <bool SYS = false>
 __device__ __forceinline__ double cell_wait(const uint4* p, uint4 c, unsigned tag) {
@@ -104,14 +112,13 @@ __device__ __forceinline__ double cell_wait(const uint4* p, uint4 c, unsigned ta
   unsigned spins = 0;
 #endif
   unsigned polls = 0;
-  unsigned long long t0 = 0;
   while (!cell_ok(c, tag)) {
 #if SSB_POLL_NS > 0
     __nanosleep(SSB_POLL_NS);
 #endif
     c = ld_cell_t<SYS>(p);
-    if constexpr (SYS) {
-      if ((++polls & 4095u) == 0) peer_deadline(t0);
+    if constexpr (SYS || kFlowWatch) {
+      if ((++polls & 4095u) == 0) peer_deadline();
     }
 #ifdef SSB_WATCHDOG
     if (++spins > SSB_SPIN_LIMIT) __trap();
@@ -135,14 +142,13 @@ __device__ __forceinline__ void cells_wait(const uint4* base, const int (&off)[N
         unsigned spins = 0;
 #endif
         unsigned polls = 0;
-        unsigned long long t0 = 0;
         do {
 #if SSB_POLL_NS > 0
           __nanosleep(SSB_POLL_NS);
 #endif
           c[m] = ld_cell_t<SYS>(base + off[m]);
-          if constexpr (SYS) {
-            if ((++polls & 4095u) == 0) peer_deadline(t0);
+          if constexpr (SYS || kFlowWatch) {
+            if ((++polls & 4095u) == 0) peer_deadline();
           }
 #ifdef SSB_WATCHDOG
           if (++spins > SSB_SPIN_LIMIT) __trap();
@@ -426,6 +432,7 @@ __global__ void __launch_bounds__(CINV_THREADS, SSB_CINV_MINB)
   constexpr int nc = 6 * NB;
   double* Arow = dsm;             // [6][nc]
   double* red = Arow + 6 * nc;    // [CINV_THREADS / 36][36]
+  if (threadIdx.x == 0) s_flow_deadline = peer_globaltimer() + SSB_PEER_TIMEOUT_NS;
   const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np_own, p0 + Cz.C);
   coarse_assemble<CINV_THREADS>(G, Cz, lambda, Arow, red, p0, p1);
   const bool ok = coarse_gj_flow<CINV_THREADS, NB>(gj, tag, Arow, order, mask);
@@ -476,6 +483,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_flow_deadline = peer_globaltimer() + SSB_PEER_TIMEOUT_NS;   // read by the waits (after a barrier)
   const int slot = lane / 6, comp = lane - 6 * slot;
   const int base_lane = 6 * slot;
   const int p0 = blockIdx.x * Cz.C, p1 = min(G.Np_own, p0 + Cz.C);

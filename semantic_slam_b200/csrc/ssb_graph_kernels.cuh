@@ -1200,8 +1200,12 @@ __device__ __forceinline__ double grid_bar_sum_mr(const StreamPeer& SP, unsigned
         for (int k = 0; k < 6; ++k) S->v[1 + k] = my6[k];
       }
     }
+    // ONE system-scope fence for everything this CTA pushed (cumulative through the bar.sync above), then relaxed arrivals:
+    // a release per rank would drain the NVLink write queue `world` times (measured: the barrier, not the data, bound the
+    // 4-GPU iteration at 127 us with red.release.sys per rank)
+    __threadfence_system();
     for (int r = 0; r < SP.world; ++r)
-      red_release_sys_add_u32(&(reinterpret_cast<BarSlot*>(SP.slots[r]) + 2 * (size_t)tot)->epoch, 1u);
+      red_relaxed_sys_add_u32(&(reinterpret_cast<BarSlot*>(SP.slots[r]) + 2 * (size_t)tot)->epoch, 1u);
     const unsigned* counter = &(reinterpret_cast<BarSlot*>(SP.slots[SP.rank]) + 2 * (size_t)tot)->epoch;
     const unsigned target = epoch * (unsigned)tot;
     unsigned polls = 0;

@@ -57,6 +57,9 @@ __device__ __forceinline__ uint4 ld_cell_sys(const uint4* c) {
 __device__ __forceinline__ void red_release_sys_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_sys_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -192,7 +192,7 @@ struct ShardPlan {
 };
 // byte offsets inside a rank's peer arena (a function of that rank's local sizes => computable by everybody)
 struct ArenaLayout {
-  size_t flags, red, cells, lines, x, z, v, slots, pose_full, lm_full, total;
+  size_t flags, red, cells, lines, x, z, v, slots, pose_full, lm_full, gcent, grows, glines, total;
   size_t n_cells, n_ucells, n_lines, n_x, n_v;
 };
 struct PeerBlob {                     // what the ranks tell each other when an arena was (re)allocated
@@ -225,6 +225,12 @@ struct MrCtx {                        // member of the INNER (shard) handle
   DBuf<double*> d_upush_x;
   FlowPeer FP{};
   StreamPeer SP{};
+  GlobDev GD{};                               // rank-level coarse level of the preconditioner
+  bool glob = false;
+  DBuf<int> d_pose_rank;
+  DBuf<double> d_Bg, d_Gg, d_gpart;
+  DBuf<float> d_Aginv;
+  DBuf<double*> d_gcent_all, d_grows_all;
   DBuf<double*> d_zpush_z, d_svpush_v;
   DBuf<int> d_svpush_rowptr;
   // chi2 over the edges this rank owns (a shared edge is counted once)
@@ -299,7 +305,7 @@ struct ssb_graph {
   DBuf<double> d_x, d_r, d_z, d_p0, d_p1, d_q, d_v, d_dl, d_part, d_scalars, d_tmp;
   DBuf<int> d_iscalars, d_ainv_ok;
   // coarse level
-  DBuf<double> d_Bmat, d_Grun, d_panel, d_B1mat, d_D1inv, d_ainv;
+  DBuf<double> d_Bmat, d_Grun, d_panel, d_B1mat, d_D1inv, d_ainv, d_ctacen;
   bool ainv_valid = false;   // d_ainv holds the rows of a previously inverted coarse matrix
   int solves_since_refresh = 0;
   DBuf<int> d_run_lm, d_run_group, d_run_e0, d_lm_run_rowptr, d_grp_run_rowptr, d_grp_runs;
@@ -1265,6 +1271,7 @@ static int prepare(ssb_graph* g) {
                          g->d_ft_part_lm.p, g->d_ft_part_e0.p, g->d_ft_part_e1.p, g->d_ft_lm_partbase.p, n_parts};
       }
     }
+    SSB_TRY(g->d_ctacen.ensure((size_t)3 * nblk));
     SSB_TRY(g->d_Bmat.ensure((size_t)36 * Np));
     if (mr && Np) SSB_CUDA_CHECK(cudaMemsetAsync(g->d_Bmat.p, 0, (size_t)36 * Np * sizeof(double), g->stream));   // ghosts: B = 0
     SSB_TRY(g->d_B1mat.ensure((size_t)36 * Np));
@@ -1336,6 +1343,7 @@ static int prepare(ssb_graph* g) {
       Cz.C = Cc;
       Cz.nc = ncoarse;
       Cz.Bmat = g->d_Bmat.p;
+      Cz.cen = g->d_ctacen.p;
       Cz.Grun = g->d_Grun.p;
       Cz.run_lm = g->d_run_lm.p;
       Cz.run_group = g->d_run_group.p;
@@ -1461,6 +1469,7 @@ static int prepare(ssb_graph* g) {
 }
 
 // ---- kernel launch helpers -----------------------------------------------------------------
+static int peer_exchange(ssb_graph* g, bool with_record);
 static int launch_chi2(ssb_graph* g) {
   DevGraph G = g->G;
   if (g->mr) {   // a shard sums the edges it owns; the partial sums are folded by read_scalars_sharded
@@ -1514,6 +1523,16 @@ static int launch_linearize(ssb_graph* g) {
   }
   SSB_CUDA_CHECK(cudaEventRecord(g->ev_join, s2));
   SSB_CUDA_CHECK(cudaStreamWaitEvent(s, g->ev_join, 0));
+  if (g->mr && g->mr->glob && g->fast_ok) {
+    // rank-level coarse level, per linearisation: everybody's centroid, then the prolongation blocks about the owner's
+    // centroid (ghosts included) and the per-(landmark, rank) products
+    MrCtx* mr = g->mr;
+    k_g_centroid<<<1, 1024, 0, s>>>(G, mr->world, mr->rank, mr->d_gcent_all.p);
+    SSB_TRY(peer_exchange(g, false));
+    k_g_basis<<<(G.Np + 127) / 128, 128, 0, s>>>(G, mr->GD);
+    if (G.Nl) k_g_runs<<<(18 * mr->world * G.Nl + 127) / 128, 128, 0, s>>>(G, mr->GD);
+    g->launches += 3;
+  }
   SSB_CUDA_CHECK(cudaGetLastError());
   g->have_system = true;
   return SSB_OK;
@@ -1576,6 +1595,15 @@ static int launch_prep(ssb_graph* g, double lambda, bool separate_coarse = false
     SSB_CUDA_CHECK(cudaStreamWaitEvent(s, g->ev_join, 0));
   }
   if (cinv) SSB_CUDA_CHECK(cudaStreamWaitEvent(s, g->ev_join3, 0));
+  if (g->mr && g->mr->glob && g->fast_ok) {
+    // rank-level coarse level, per damped trial: my 6 rows of A_g -> everybody; invert the 6W x 6W matrix redundantly
+    MrCtx* mr = g->mr;
+    k_g_rows<<<G_ROW_BLOCKS, G_ROW_THREADS, 0, s>>>(G, mr->GD, lambda);
+    k_g_fold<<<1, G_ROW_THREADS, 0, s>>>(mr->GD, G_ROW_BLOCKS, mr->d_grows_all.p);
+    SSB_TRY(peer_exchange(g, false));
+    k_g_invert<<<1, 256, 0, s>>>(mr->GD, 1.0f);
+    g->launches += 3;
+  }
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;
 }
@@ -1715,6 +1743,12 @@ static ArenaLayout arena_layout(int world, int nb, int NpL, int NlL, int ElL, in
   o = align_up(o + (size_t)std::max(NpG, 1) * sizeof(Pose), 256);
   L.lm_full = o;
   o = align_up(o + (size_t)std::max(NlG, 1) * 4 * sizeof(double), 256);
+  L.gcent = o;
+  o = align_up(o + (size_t)world * 4 * sizeof(double), 256);
+  L.grows = o;
+  o = align_up(o + (size_t)world * 36 * world * sizeof(double), 256);
+  L.glines = o;
+  o = align_up(o + L.n_lines * sizeof(uint4), 256);
   L.total = o;
   return L;
 }
@@ -1918,7 +1952,9 @@ static int map_arenas(ssb_graph* g, const ShardPlan& plan, const std::vector<int
     mr->PG.pose_full[r] = base + mr->lay[r].pose_full;
     mr->PG.lm_full[r] = (double*)(base + mr->lay[r].lm_full);
     mr->FP.lines[r] = P.lines[r];
+    mr->FP.glines[r] = (uint4*)(base + mr->lay[r].glines);
   }
+  mr->FP.gcent = (const double*)(mr->arena + mr->lay[rank].gcent);
   mr->PG.world = world;
   mr->FP.world = world;
   mr->FP.rank = rank;
@@ -2185,6 +2221,42 @@ static int prepare_sharded(ssb_graph* g) {
       mr->SP.vpush_rowptr = mr->d_svpush_rowptr.p;
       mr->SP.vpush_v = mr->d_svpush_v.p;
       for (int r = 0; r < world; ++r) mr->SP.slots[r] = mr->P.slots[r];
+      // rank-level coarse level: owner of every local keyframe, pointers to every rank's centroid / row-block slots
+      {
+        const int per = std::max(1, (plan.Np + world - 1) / world);
+        std::vector<int> prank(NpL);
+        for (int k = 0; k < NpL; ++k) prank[k] = std::min(world - 1, R.l2g_pose[k] / per);
+        std::vector<double*> gc(world), gr(world);
+        for (int r = 0; r < world; ++r) {
+          gc[r] = (double*)(mr->peer_base[r] + mr->lay[r].gcent);
+          gr[r] = (double*)(mr->peer_base[r] + mr->lay[r].grows);
+        }
+        SSB_TRY(mr->d_pose_rank.ensure(std::max(NpL, 1)));
+        SSB_TRY(mr->d_Bg.ensure((size_t)36 * std::max(NpL, 1)));
+        SSB_TRY(mr->d_Gg.ensure((size_t)18 * world * std::max(NlL, 1)));
+        SSB_TRY(mr->d_gpart.ensure((size_t)G_ROW_BLOCKS * 36 * world));
+        SSB_TRY(mr->d_Aginv.ensure((size_t)36 * world));
+        SSB_TRY(mr->d_gcent_all.ensure(world));
+        SSB_TRY(mr->d_grows_all.ensure(world));
+        if (NpL) SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_pose_rank.p, prank.data(), NpL * sizeof(int), cudaMemcpyHostToDevice, s));
+        SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_gcent_all.p, gc.data(), world * sizeof(double*), cudaMemcpyHostToDevice, s));
+        SSB_CUDA_CHECK(cudaMemcpyAsync(mr->d_grows_all.p, gr.data(), world * sizeof(double*), cudaMemcpyHostToDevice, s));
+        SSB_CUDA_CHECK(cudaMemsetAsync(mr->d_Aginv.p, 0, (size_t)36 * world * sizeof(float), s));
+        SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+        GlobDev& GD = mr->GD;
+        GD.world = world;
+        GD.rank = rank;
+        GD.pose_rank = mr->d_pose_rank.p;
+        GD.gcent = (double*)(mr->arena + L.gcent);
+        GD.Bg = mr->d_Bg.p;
+        GD.Gg = mr->d_Gg.p;
+        GD.part = mr->d_gpart.p;
+        GD.grows = (double*)(mr->arena + L.grows);
+        GD.Aginv = mr->d_Aginv.p;
+        mr->glob = in->opts.preconditioner >= 1 && std::getenv("SSB_NO_GLOBAL_LEVEL") == nullptr;
+        mr->FP.glob = mr->glob ? 1 : 0;
+        mr->FP.Aginv = mr->d_Aginv.p;
+      }
     }
     g->structure_dirty = false;
     g->host_est_dirty = true;

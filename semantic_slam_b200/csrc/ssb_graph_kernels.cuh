@@ -339,6 +339,7 @@ struct CoarseDev {
   int C;    // poses per CTA (multiple of 5)
   int nc;   // 6 * gridDim.x
   double* Bmat;            // [Np][36]
+  double* cen;             // [gridDim.x][3] centroid of every CTA's aggregate (read by the rank-level coarse level)
   double* Grun;            // [n_runs][18]  (3x6) = sum_e HplL_e B_p(e) over the run
   const int* run_lm;       // [n_runs]
   const int* run_group;    // [n_runs]
@@ -536,7 +537,10 @@ __global__ void __launch_bounds__(256) k_coarse_basis(DevGraph G, CoarseDev Cz) 
     for (int k = 0; k < 3; ++k) s[k] += G.pose[i].t[k];
   for (int k = 0; k < 3; ++k) {
     double t = block_sum(s[k], sh);
-    if (threadIdx.x == 0) cen[k] = p1 > p0 ? t / (double)(p1 - p0) : 0.0;
+    if (threadIdx.x == 0) {
+      cen[k] = p1 > p0 ? t / (double)(p1 - p0) : 0.0;
+      if (Cz.cen) Cz.cen[3 * blockIdx.x + k] = cen[k];
+    }
   }
   __syncthreads();
   for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
@@ -1542,6 +1546,185 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     G.iscalars[1] = status;
     G.scalars[3] = rz;
     G.scalars[4] = rz0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sharded graphs: the RANK-LEVEL coarse level of the preconditioner.  Every rank is one more rigid-body aggregate (6
+// unknowns: translation + rotation of all its keyframes about their centroid c_r); A_g = P_g' S P_g is 6W x 6W.  It is the
+// only level that couples the ranks (the per-CTA coarse matrix and the groups see S restricted to the rank), and what
+// keeps the iteration count from growing with the number of ranks (scripts/shard_precond_study.py: 196 -> 105 iterations
+// per solve on 2 ranks, 409 -> 170 on 8).  P_g = P_c E with E_a = [I, -[c_a - c_r]x; 0, I] for CTA aggregate a of rank r, so
+// inside the PCG kernel the level rides on the per-CTA coarse values: P_g'w = sum_a E_a' (P_c'w)_a, prolongation
+// B_i (E_a z_g).  Assembly: rank r computes its 6 rows of A_g from its own keyframes (a touched landmark has all its edges
+// here, ghosts included), pushes them to everybody, every rank inverts the 6W x 6W matrix redundantly.
+// ---------------------------------------------------------------------------------------------
+struct GlobDev {
+  int world, rank;
+  const int* pose_rank;   // [Np] owner of every local keyframe
+  double* gcent;          // [world][4] centroids of all ranks (in my arena; slot s written by rank s)
+  double* Bg;             // [Np][36] prolongation blocks about the OWNER's centroid
+  double* Gg;             // [Nl][world][18] sum over the landmark's edges whose keyframe belongs to rank s of HplL_e Bg_p(e)
+  double* part;           // [G_ROW_BLOCKS][world * 36]
+  double* grows;          // [world][36 * world] row blocks of A_g (in my arena; slot s written by rank s)
+  float* Aginv;           // [6][6 world] my rows of w_g A_g^-1 (zeros: level off)
+};
+constexpr int G_ROW_BLOCKS = 148;
+constexpr int G_ROW_THREADS = 36 * SSB_MAX_WORLD;
+
+// own centroid -> slot `rank` of every rank's gcent (fixed-order block reduction)
+__global__ void __launch_bounds__(1024) k_g_centroid(DevGraph G, int world, int rank, double* const* gcent_all) {
+  __shared__ double sh[33];
+  double s[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < G.Np_own; i += blockDim.x)
+    for (int k = 0; k < 3; ++k) s[k] += G.pose[i].t[k];
+  double c[3];
+  for (int k = 0; k < 3; ++k) c[k] = block_sum(s[k], sh) / (double)max(1, G.Np_own);
+  if (threadIdx.x < world)
+    for (int k = 0; k < 3; ++k) st_relaxed_sys_f64(gcent_all[threadIdx.x] + 4 * rank + k, c[k]);
+}
+__global__ void __launch_bounds__(128) k_g_basis(DevGraph G, GlobDev Gd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G.Np) return;
+  double* B = Gd.Bg + 36 * (size_t)i;
+  if (G.pose_fixed[i] || (G.pose_kind && G.pose_kind[i])) {
+    for (int k = 0; k < 36; ++k) B[k] = 0.0;
+    return;
+  }
+  const double* c = Gd.gcent + 4 * Gd.pose_rank[i];
+  const Pose X = G.pose[i];
+  double R[9];
+  quat_to_R(X.q, R);
+  const double d[3] = {X.t[0] - c[0], X.t[1] - c[1], X.t[2] - c[2]};
+  const double Sx[9] = {0, -d[2], d[1], d[2], 0, -d[0], -d[1], d[0], 0};
+  for (int r = 0; r < 3; ++r)
+    for (int cc = 0; cc < 3; ++cc) {
+      const double rt = R[3 * cc + r];
+      B[6 * r + cc] = rt;
+      B[6 * r + 3 + cc] = -(R[r] * Sx[cc] + R[3 + r] * Sx[3 + cc] + R[6 + r] * Sx[6 + cc]);
+      B[6 * (3 + r) + cc] = 0.0;
+      B[6 * (3 + r) + 3 + cc] = 0.5 * rt;
+    }
+}
+__global__ void __launch_bounds__(128) k_g_runs(DevGraph G, GlobDev Gd) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = t % 18, ls = t / 18, s = ls % Gd.world, l = ls / Gd.world;
+  if (l >= G.Nl) return;
+  const int a = q / 6, c = q - 6 * a;
+  double acc = 0.0;
+  for (int e = G.lm_rowptr[l]; e < G.lm_rowptr[l + 1]; ++e) {
+    const int p = G.pl[e].p;
+    if (Gd.pose_rank[p] != s) continue;
+    const double* Hl = G.HplL + 18 * (size_t)e + 6 * a;
+    const double* B = Gd.Bg + 36 * (size_t)p + c;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc += Hl[k] * B[6 * k];
+  }
+  Gd.Gg[(size_t)ls * 18 + q] = acc;
+}
+// per damped trial: my 6 rows of A_g, partial sums over chunks of own keyframes (thread = (column rank s, entry r, c))
+__global__ void __launch_bounds__(G_ROW_THREADS) k_g_rows(DevGraph G, GlobDev Gd, double lambda) {
+  const int s = threadIdx.x / 36, ent = threadIdx.x - 36 * s, r = ent / 6, c = ent - 6 * r;
+  const int per = (G.Np_own + gridDim.x - 1) / gridDim.x;
+  const int i0 = min(G.Np_own, (int)blockIdx.x * per), i1 = min(G.Np_own, i0 + per);
+  double acc = 0.0;
+  if (s < Gd.world)
+    for (int i = i0; i < i1; ++i) {
+      const double* Bi = Gd.Bg + 36 * (size_t)i;
+      if (s == Gd.rank) {
+        const double* H = G.Hpp + 36 * (size_t)i;
+        double t = 0.0;
+        for (int a = 0; a < 6; ++a) {
+          double hb = lambda * Bi[6 * a + c];
+          for (int b = 0; b < 6; ++b) hb += H[6 * a + b] * Bi[6 * b + c];
+          t += Bi[6 * a + r] * hb;
+        }
+        acc += t;
+      }
+      for (int kk = G.pose_pp_rowptr[i]; kk < G.pose_pp_rowptr[i + 1]; ++kk) {
+        const int code = G.pose_pp_idx[kk], e = code >> 1, role = code & 1;
+        const int j = role == 0 ? G.pp[e].j : G.pp[e].i;
+        if (Gd.pose_rank[j] != s) continue;
+        const double* Bj = Gd.Bg + 36 * (size_t)j;
+        const double* Ho = G.Hoff + 36 * (size_t)e;
+        double t = 0.0;
+        for (int a = 0; a < 6; ++a) {
+          double hb = 0.0;
+          for (int b = 0; b < 6; ++b) hb += (role == 0 ? Ho[6 * a + b] : Ho[6 * b + a]) * Bj[6 * b + c];
+          t += Bi[6 * a + r] * hb;
+        }
+        acc += t;
+      }
+      for (int kk = G.pose_pl_rowptr[i]; kk < G.pose_pl_rowptr[i + 1]; ++kk) {
+        const int l = G.plP_lm[kk];
+        const double* Hp = G.HplP + 18 * (size_t)kk;
+        const double* Wu = G.HllInv + 6 * (size_t)l;
+        const double* Gs = Gd.Gg + ((size_t)l * Gd.world + s) * 18;
+        // X = W Gs (column c), then Bi' Hp X
+        const double x0 = Wu[0] * Gs[c] + Wu[1] * Gs[6 + c] + Wu[2] * Gs[12 + c];
+        const double x1 = Wu[1] * Gs[c] + Wu[3] * Gs[6 + c] + Wu[4] * Gs[12 + c];
+        const double x2 = Wu[2] * Gs[c] + Wu[4] * Gs[6 + c] + Wu[5] * Gs[12 + c];
+        double t = 0.0;
+        for (int a = 0; a < 6; ++a) t += Bi[6 * a + r] * (Hp[3 * a] * x0 + Hp[3 * a + 1] * x1 + Hp[3 * a + 2] * x2);
+        acc -= t;
+      }
+    }
+  if (s < Gd.world) Gd.part[(size_t)blockIdx.x * (36 * Gd.world) + 36 * s + ent] = acc;
+}
+// fold the partials in block order and hand my row block to every rank (slot `rank` of their grows)
+__global__ void __launch_bounds__(G_ROW_THREADS) k_g_fold(GlobDev Gd, int nblocks, double* const* grows_all) {
+  const int n = 36 * Gd.world;
+  if ((int)threadIdx.x >= n) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; ++b) t += Gd.part[(size_t)b * n + threadIdx.x];
+  for (int q = 0; q < Gd.world; ++q) st_relaxed_sys_f64(grows_all[q] + (size_t)Gd.rank * n + threadIdx.x, t);
+}
+// every rank: A_g from the gathered row blocks, symmetrised, Gauss-Jordan inverse (SPD, no pivoting), my 6 rows as float
+__global__ void __launch_bounds__(256) k_g_invert(GlobDev Gd, float weight) {
+  constexpr int NMAX = 6 * SSB_MAX_WORLD;
+  __shared__ double A[NMAX][NMAX + 1], I[NMAX][NMAX + 1];
+  __shared__ int s_fail;
+  const int n = 6 * Gd.world;
+  if (threadIdx.x == 0) s_fail = 0;
+  for (int k = threadIdx.x; k < n * n; k += blockDim.x) {
+    const int i = k / n, j = k - i * n;
+    // row block of rank ri: entry (r, 6 s + c) stored at [ri][36 s + 6 r + c]
+    auto at = [&](int ii, int jj) { return Gd.grows[(size_t)(ii / 6) * 36 * Gd.world + 36 * (jj / 6) + 6 * (ii % 6) + (jj % 6)]; };
+    A[i][j] = 0.5 * (at(i, j) + at(j, i));
+    I[i][j] = i == j ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    const double piv = A[k][k];
+    if (!(piv > 0.0) || !isfinite(piv)) {
+      if (threadIdx.x == 0) s_fail = 1;
+      __syncthreads();
+      break;
+    }
+    const double ip = 1.0 / piv;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      A[k][j] *= ip;
+      I[k][j] *= ip;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+      const int i = idx / n, j = idx - i * n;
+      if (i == k) continue;
+      const double f = A[i][k];
+      if (j != k) A[i][j] -= f * A[k][j];
+      I[i][j] -= f * I[k][j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (i != k) A[i][k] = 0.0;
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 6 * n; k += blockDim.x) {
+    const int r = k / n, j = k - r * n;
+    const int i = 6 * Gd.rank + r;
+    Gd.Aginv[k] = s_fail ? 0.0f : (float)(weight * 0.5 * (I[i][j] + I[j][i]));
   }
 }
 

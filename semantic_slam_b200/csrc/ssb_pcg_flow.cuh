@@ -48,6 +48,12 @@ struct FlowPeer {
   const int* vpush_rowptr;     // [own landmark parts + 1] ranks whose keyframes see the landmark of the part
   uint4* const* vpush_cell;    //   the 3 v cells of the part in that rank's cell buffer
   uint4* lines[SSB_MAX_WORLD]; // every rank's reduction lines [2][world][NB][8]; line (p, r, b) is written by CTA b of rank r
+  // rank-level coarse level (ssb_graph_kernels.cuh: GlobDev).  glob != 0: every CTA writes (gamma, delta, E_a' P_c'w) into
+  // glines of EVERY rank (its own included) and all cross-rank sums are folded from there.
+  int glob;
+  uint4* glines[SSB_MAX_WORLD]; // [2][world][NB][8]
+  const float* Aginv;          // [6][6 world] my rank's rows of w_g A_g^-1
+  const double* gcent;         // [world][4] rank centroids
 };
 
 __device__ __forceinline__ void st_cell(uint4* c, double v, unsigned tag) {
@@ -451,7 +457,10 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     k_pcg_flow(DevGraph G, CoarseDev Cz, BarSlot* slots, FlowBufs F, FlowTabs T, double lambda, double tol2, int maxit, FlowPeer FP) {
   extern __shared__ __align__(16) double dsm[];
   __shared__ double s6[8], zc6[8], red6[7 * 32];
-  __shared__ double rs_sh[2 * SSB_MAX_WORLD];   // MR: (gamma, delta) sums of the other ranks' lines
+  __shared__ double rs_sh[8 * SSB_MAX_WORLD];   // MR: per rank (gamma, delta, P_g'w [6]) folded from the lines of that rank
+  __shared__ float ag_sh[MR ? 36 * SSB_MAX_WORLD : 1];   // MR: my rank's rows of w_g A_g^-1
+  __shared__ double tg6_sh[8], dga_sh[4];        // MR: A_g^-1 P_g'w (my rank's 6 values); c_a - c_rank of my CTA aggregate
+  __shared__ double gl8_sh[8];                   // MR: this CTA's (gamma, delta, P_c'w) of the iteration
   __shared__ int ovcnt[PCGF_THREADS / 32];
   constexpr int nblk = NB;
   constexpr int nc = 6 * nblk;
@@ -654,6 +663,84 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   }
   __syncthreads();
 
+  bool use_glob = false;
+  if constexpr (MR) {
+    use_glob = FP.glob != 0 && use_coarse;
+    if (use_glob) {
+      for (int k = threadIdx.x; k < 36 * FP.world; k += PCGF_THREADS) ag_sh[k] = FP.Aginv[k];
+      if (threadIdx.x < 3) dga_sh[threadIdx.x] = Cz.cen[3 * blockIdx.x + threadIdx.x] - FP.gcent[4 * FP.rank + threadIdx.x];
+    }
+    __syncthreads();
+  }
+  // MR + rank-level coarse level: publish (v0, v1, E_a' s6) of this CTA into the glines of every rank and fold the lines of
+  // every rank (two warps... 16 / world warps per rank, 8 / that many values each) into rs_sh.  Called by all threads.
+  auto glob_exchange = [&](double v0, double v1, const double* s6v /* smem, 6 */, unsigned tag) {
+    if constexpr (MR) {
+      const int W = FP.world;
+      if (warp == 0) {
+        // lane k < 8 holds value k: (v0, v1, s_t, d x s_t + s_r)
+        double val = lane == 0 ? v0 : (lane == 1 ? v1 : (lane < 8 ? s6v[lane - 2] : 0.0));
+        const double st0 = s6v[0], st1 = s6v[1], st2 = s6v[2];
+        if (lane == 5) val += dga_sh[1] * st2 - dga_sh[2] * st1;
+        if (lane == 6) val += dga_sh[2] * st0 - dga_sh[0] * st2;
+        if (lane == 7) val += dga_sh[0] * st1 - dga_sh[1] * st0;
+        const double gv = __shfl_sync(0xffffffffu, val, lane & 7);
+        for (int r0 = 0; r0 < W; r0 += 4) {
+          const int rr = r0 + (lane >> 3);
+          if (rr < W) st_cell_sys(FP.glines[rr] + (((size_t)(tag & 1u) * W + FP.rank) * nblk + blockIdx.x) * 8 + (lane & 7), gv, tag);
+        }
+      }
+      constexpr int RM = (NB + 31) / 32;
+      const int wpr = (PCGF_THREADS / 32) / W;        // warps per rank: 8, 4, 2 for 2, 4, 8 ranks
+      const int rr = warp / wpr, sub = warp - rr * wpr, nval = 8 / wpr;
+      if (rr < W) {
+        const uint4* Lr = FP.glines[FP.rank] + ((size_t)(tag & 1u) * W + rr) * nblk * 8;
+        for (int q = 0; q < nval; ++q) {
+          const int k = sub * nval + q;
+          uint4 c[RM];
+          int ro[RM];
+          double rv[RM];
+#pragma unroll
+          for (int m = 0; m < RM; ++m) {
+            const int cta = lane + 32 * m;
+            ro[m] = cta < nblk ? 8 * cta + k : -1;
+            if (ro[m] >= 0) c[m] = ld_cell_sys(Lr + ro[m]);
+          }
+          cells_wait<RM, true>(Lr, ro, c, tag, rv);
+          double t = 0.0;
+#pragma unroll
+          for (int m = 0; m < RM; ++m)
+            if (ro[m] >= 0) t += rv[m];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0) rs_sh[8 * rr + k] = t;
+        }
+      }
+    }
+  };
+  // tg6 = (my rank's rows of w_g A_g^-1) . P_g'w; call after a barrier that follows glob_exchange, barrier afterwards
+  auto glob_rows = [&]() {
+    if constexpr (MR) {
+      if (warp < 6) {
+        const int n = 6 * FP.world;
+        double t = 0.0;
+        for (int j = lane; j < n; j += 32) t += (double)ag_sh[warp * n + j] * rs_sh[8 * (j / 6) + 2 + (j % 6)];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) tg6_sh[warp] = t;
+      }
+    }
+  };
+  // E_a (tau, omega) = (tau - d x omega, omega): the rank-level correction in the coordinates of my CTA aggregate
+  auto glob_prolong = [&](double* eg) {
+    const double t0 = tg6_sh[0], t1 = tg6_sh[1], t2 = tg6_sh[2], w0 = tg6_sh[3], w1 = tg6_sh[4], w2 = tg6_sh[5];
+    eg[0] = t0 - (dga_sh[1] * w2 - dga_sh[2] * w1);
+    eg[1] = t1 - (dga_sh[2] * w0 - dga_sh[0] * w2);
+    eg[2] = t2 - (dga_sh[0] * w1 - dga_sh[1] * w0);
+    eg[3] = w0;
+    eg[4] = w1;
+    eg[5] = w2;
+  };
   // ---- init: x = 0, r = g, u = M^-1 r ------------------------------------------------------------
   const unsigned tb = F.tagbase;
   uint4* const my_ucell = F.ucell + 6 * (size_t)(act ? i : 0) + comp;
@@ -703,6 +790,18 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 6; ++k) cz += Brow[k] * zc6[k];
+    if constexpr (MR) {
+      if (use_glob) {   // z_g = A_g^-1 P_g'r, exchanged with the tag of the launch itself
+        glob_exchange(0.0, 0.0, s6, tb);
+        __syncthreads();
+        glob_rows();
+        __syncthreads();
+        double eg[6];
+        glob_prolong(eg);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cz += Brow[k] * eg[k];
+      }
+    }
   }
 #define SSB_FLOW_PRECOND()                                                                              \
   {                                                                                                     \
@@ -909,16 +1008,23 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
 #pragma unroll
         for (int ww = 0; ww < PCGF_THREADS / 32; ++ww) t += scratch8[8 * ww + lane];
         st_cell(F.lines + (((size_t)(tg & 1u) * mr_world + mr_rank) * nblk + blockIdx.x) * 8 + lane, t, tg);
+        if constexpr (MR) gl8_sh[lane] = t;
       }
       if constexpr (MR) {
-        // the two dot-product partials also go into the same line slot of every other rank: lane 8 + 2 j + k
-        const double tv = __shfl_sync(0xffffffffu, t, lane >= 8 ? ((lane - 8) & 1) : 0);
-        const int j = (lane - 8) >> 1;
-        if (lane >= 8 && j < mr_world - 1) {
-          const int peer = j < mr_rank ? j : j + 1;
-          st_cell_sys(FP.lines[peer] + (((size_t)(tg & 1u) * mr_world + mr_rank) * nblk + blockIdx.x) * 8 + ((lane - 8) & 1), tv, tg);
+        __syncwarp();
+        if (!use_glob) {
+          // the two dot-product partials also go into the same line slot of every other rank: lane 8 + 2 j + k
+          const double tv = __shfl_sync(0xffffffffu, t, lane >= 8 ? ((lane - 8) & 1) : 0);
+          const int j = (lane - 8) >> 1;
+          if (lane >= 8 && j < mr_world - 1) {
+            const int peer = j < mr_rank ? j : j + 1;
+            st_cell_sys(FP.lines[peer] + (((size_t)(tg & 1u) * mr_world + mr_rank) * nblk + blockIdx.x) * 8 + ((lane - 8) & 1), tv, tg);
+          }
         }
       }
+    }
+    if constexpr (MR) {
+      if (use_glob) glob_exchange(gl8_sh[0], gl8_sh[1], gl8_sh + 2, tg);   // warp 0 wrote gl8_sh itself
     }
     {
       // pull all-gather of the nblk lines: thread q reads cell q (coalesced), value k of line q/8
@@ -965,7 +1071,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       static_assert(PCGF_THREADS / 32 >= 2 * (SSB_MAX_WORLD - 1), "two warps per remote rank");
       constexpr int RM = (NB + 31) / 32;
       const int j = warp >> 1, kq = warp & 1;
-      if (j < mr_world - 1) {
+      if (!use_glob && j < mr_world - 1) {
         const int peer = j < mr_rank ? j : j + 1;
         const uint4* Lr = F.lines + ((size_t)(tg & 1u) * mr_world + peer) * nblk * 8;
         uint4 c[RM];
@@ -984,7 +1090,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
           if (ro[m] >= 0) t += rv[m];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) rs_sh[2 * peer + kq] = t;
+        if (lane == 0) rs_sh[8 * peer + kq] = t;
       }
     }
     SSB_FTICK(3);
@@ -1007,8 +1113,9 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       if constexpr (MR) {   // rank order, identical on every rank
         double g2 = 0.0, d2 = 0.0;
         for (int r = 0; r < mr_world; ++r) {
-          g2 += r == mr_rank ? tg_ : rs_sh[2 * r];
-          d2 += r == mr_rank ? td_ : rs_sh[2 * r + 1];
+          const bool own = r == mr_rank && !use_glob;   // with the rank-level level every rank, mine included, comes from glines
+          g2 += own ? tg_ : rs_sh[8 * r];
+          d2 += own ? td_ : rs_sh[8 * r + 1];
         }
         gamma = g2;
         delta = d2;
@@ -1021,6 +1128,9 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
         for (int j = j0 + lane; j < j1; j += 32) t += Arow[row * nc + j] * wc[j];
         t = warp_sum(t);
         if (lane == 0) dpart[warp] = t;
+      }
+      if constexpr (MR) {
+        if (use_glob) glob_rows();
       }
       __syncthreads();
     }
@@ -1056,6 +1166,14 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       double t = 0.0;
 #pragma unroll
       for (int k = 0; k < 6; ++k) t += Brow[k] * (dpart[2 * k] + dpart[2 * k + 1]);
+      if constexpr (MR) {
+        if (use_glob) {
+          double eg[6];
+          glob_prolong(eg);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) t += Brow[k] * eg[k];
+        }
+      }
       cy = t + beta * cy;
       cz -= alpha * cy;
     }

@@ -75,7 +75,8 @@ if __name__ == "__main__":
             "max_abs_vs_1gpu": float(max(np.abs(res[0]["P"] - P1).max(), np.abs(res[0]["X"] - X1).max())),
             "chi2": res[0]["history"][:, 1].tolist(), "chi2_1gpu": g1.history[:, 1].tolist(),
             "pcg_iters": int(res[0]["stats"]["total_pcg_iters"]), "pcg_iters_1gpu": int(g1.stats["total_pcg_iters"]),
-            "ms_device": res[0]["stats"]["ms_device"], "ms_device_1gpu": g1.stats["ms_device"]}
+            "ms_device": res[0]["stats"]["ms_device"], "ms_device_1gpu": g1.stats["ms_device"], "ms_pcg": res[0]["stats"]["ms_pcg"],
+            "ms_pcg_1gpu": g1.stats["ms_pcg"]}
     if a.repeat:
         line["resident_ms"] = res[0]["resident_ms"]
     if a.oracle:

@@ -187,6 +187,9 @@ def main():
     ap.add_argument("--no-cfg4", action="store_true", help="skip the 100k-keyframe secondary workload (BASELINE.json configs[3])")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the per-frame loop (BASELINE.json configs[4])")
     ap.add_argument("--cfg5-frames", type=int, default=1000)
+    ap.add_argument("--no-marginals", action="store_true", help="skip the landmark-marginals (K5) sub-object")
+    ap.add_argument("--marginals-sample", type=int, default=64, help="cfg2 landmarks whose marginals are timed on the GPU")
+    ap.add_argument("--marginals-cpu-sample", type=int, default=8, help="... and how many of them the CPU oracle computes")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -212,7 +215,7 @@ def main():
     spec = synth.make_config_graph("cfg2")
     gb = graph_bytes(spec)
     g = GraphSLAM(device=local, pcg_tol=args.pcg_tol, preconditioner=args.preconditioner)
-    synth.load_graph(g, spec)
+    ids_cfg2 = synth.load_graph(g, spec)
     P0, X0 = g.get_all(spec.n_poses, spec.n_landmarks)
     from semantic_slam_b200 import distributed as ssbd
     if world > 1:
@@ -359,6 +362,50 @@ def main():
                                         "is FP32 issue rate, not HBM (SURVEY 8d)"}},
     }
 
+    # ---------------- K5: GraphSLAM::computeLandmarkMarginals (graph_slam.cpp:221-234) ----------------------------------
+    # the reference calls it after every optimise (semantic_graph_slam.cpp:89,181-205).  Timed through the C-ABI with host
+    # buffers on (i) a sample of cfg2's landmarks right after the e2e optimise above (10 000 keyframes fill the chip: one
+    # column per PCG launch) and (ii) ALL landmarks of a 1 000-keyframe graph (the per-frame loop's size: 10 replicas of
+    # the graph side by side, one launch = 10 columns), each beside the oracle's time for the same call on the same
+    # landmarks (a CSparse-style factorisation of the full system + 3 solves per landmark).
+    if world == 1 and not args.no_marginals:
+        lm_all = ids_cfg2[spec.vkind == 1].astype(np.int32)
+        n_s = min(args.marginals_sample, lm_all.size)
+        sample = lm_all[:: max(1, lm_all.size // n_s)][:n_s]
+        g.computeLandmarkMarginals(sample[:2])                    # warm-up (coarse inverse, buffers)
+        t0 = time.perf_counter()
+        Mg = g.computeLandmarkMarginals(sample)
+        t_mg = time.perf_counter() - t0
+        specm = synth.make_graph(1000, 100, seed=synth.SEED_BASE + 6)
+        gm = GraphSLAM(device=local, pcg_tol=1e-8, preconditioner=args.preconditioner)
+        idm = synth.load_graph(gm, specm)
+        gm.optimize(10)
+        lmm = idm[specm.vkind == 1].astype(np.int32)
+        gm.computeLandmarkMarginals(lmm[:2])
+        t0 = time.perf_counter()
+        Mm = gm.computeLandmarkMarginals(lmm)
+        t_mm = time.perf_counter() - t0
+        line["marginals"] = {
+            "metric": "landmark marginals per second (3x3 blocks of H^-1, computeLandmarkMarginals)",
+            "cfg2_sample": {"landmarks": int(sample.size), "of": int(lm_all.size), "seconds": t_mg, "value": sample.size / t_mg,
+                            "unit": "landmarks/s", "all_landmarks_extrapolated_s": t_mg * lm_all.size / sample.size,
+                            "columns_per_launch": 1},
+            "kf1000_all": {"landmarks": int(lmm.size), "seconds": t_mm, "value": lmm.size / t_mm, "unit": "landmarks/s",
+                           "columns_per_launch": min(16, 10500 // 1000)}}
+        if rank == 0 and not args.no_cpu_baseline:
+            import oracle
+            om = oracle.OracleGraphSLAM(threads=1)
+            synth.load_graph(om, specm)
+            om.optimize(10)
+            t0 = time.perf_counter()
+            Mo = om.computeLandmarkMarginals(lmm)
+            t_om = time.perf_counter() - t0
+            line["marginals"]["kf1000_all"]["cpu_baseline"] = {"value": lmm.size / t_om, "unit": "landmarks/s", "cores": 1, "kind": "port",
+                                                               "seconds": t_om}
+            line["marginals"]["kf1000_all"]["max_rel_diff_vs_oracle"] = float(np.abs(Mm - Mo).max() / np.abs(Mo).max())
+            line["marginals"]["_pending_cfg2"] = [int(v) for v in sample[: args.marginals_cpu_sample]]
+        del gm
+
     # ---------------- cfg4 (BASELINE.json configs[3]): the 100k-keyframe graph, same sharding ---------------------
     # The first genuinely HBM-bound size (B_cg = 280.6 MB per PCG iteration): it does not fit on chip, so the streaming
     # PCG kernel runs (3 barriers per iteration, spanning all ranks when sharded).  5 LM iterations per step.
@@ -472,6 +519,16 @@ def main():
         line["parity"] = {"max_abs_pose_diff_vs_oracle": float(np.abs(P1 - Po).max()),
                           "max_abs_landmark_diff_vs_oracle": float(np.abs(X1 - Xo).max()),
                           "oracle_chi2_final": float(o.history[-1, 1])}
+        if "marginals" in line and "_pending_cfg2" in line["marginals"]:
+            # K5 on cfg2: same landmarks, same end state (20 LM iterations on both sides)
+            vs = np.array(line["marginals"]["_pending_cfg2"], dtype=np.int32)
+            t0 = time.perf_counter()
+            Mo2 = o.computeLandmarkMarginals(vs)
+            dtm = time.perf_counter() - t0
+            c2 = line["marginals"]["cfg2_sample"]
+            c2["cpu_baseline"] = {"value": vs.size / dtm, "unit": "landmarks/s", "cores": 1, "kind": "port",
+                                  "sample": "the first %d of the sampled landmarks (%.1f s, one factorisation included)" % (vs.size, dtm)}
+            c2["max_rel_diff_vs_oracle"] = float(np.abs(Mg[:vs.size] - Mo2).max() / np.abs(Mo2).max())
         # the RANSAC half next to ITS CPU baseline (PCL-order restatement, 1 thread, 8 of the 64 crops)
         nbs = 8
         t0 = time.perf_counter()
@@ -483,6 +540,8 @@ def main():
                                           "sample": "%d of 64 crops x 1024 hypotheses (%.1f s)" % (nbs, tr)}
         line["ransac"]["vs_cpu_baseline"] = {"resident": line["ransac"]["value"] / (nps / tr / 1e6),
                                              "e2e": line["ransac"]["e2e"]["value"] / (nps / tr / 1e6)}
+    if "marginals" in line:
+        line["marginals"].pop("_pending_cfg2", None)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

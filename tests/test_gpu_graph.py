@@ -118,6 +118,55 @@ def test_landmark_marginals_match_oracle():
     assert g.hessian_index(lms[0]) == lms[0] - 1       # first vertex fixed -> index shifts by one
 
 
+@pytest.mark.parametrize("precond", [1, 3])
+def test_landmark_marginals_several_columns_per_launch(precond, monkeypatch):
+    """K5 on a graph that fills a fraction of the chip: k replicas of the graph side by side, one PCG launch = k columns
+    (marginals_replicated in ssb_graph.cu).  Checked against the oracle AND against the one-column-per-launch path, after an
+    optimize that stops on max_iterations (last step accepted: the system was linearised one step behind the estimates) and
+    after one that runs until g2o's LM terminates."""
+    spec = synth.make_graph(600, 60, seed=31)
+    for iters in (3, 40):
+        g, o, ids = _pair(spec, preconditioner=precond, pcg_tol=1e-12)
+        assert g.optimize(iters) and o.optimize(iters)
+        lms = [int(ids[v]) for v in range(spec.vkind.size) if spec.vkind[v] == 1]
+        lms = lms[:7] + lms[-4:]                       # 33 columns: two full batches of 16 and a ragged one
+        Mo = o.computeLandmarkMarginals(lms, relinearize=False)
+        monkeypatch.delenv("SSB_MARG_REPLICAS", raising=False)
+        Mg = g.computeLandmarkMarginals(lms)
+        assert Mg is not None
+        assert np.abs(Mg - Mo).max() <= 1e-6 * np.abs(Mo).max(), np.abs(Mg - Mo).max() / np.abs(Mo).max()
+        Mg2 = g.computeLandmarkMarginals(lms)          # the shadow graph is reused: same answer
+        assert np.array_equal(Mg, Mg2)
+        monkeypatch.setenv("SSB_MARG_REPLICAS", "1")
+        M1 = g.computeLandmarkMarginals(lms)
+        assert np.abs(Mg - M1).max() <= 1e-8 * np.abs(M1).max()
+        monkeypatch.delenv("SSB_MARG_REPLICAS", raising=False)
+        # growth: the shadow graph follows a structure change
+        kf = [int(ids[v]) for v in range(spec.vkind.size) if spec.vkind[v] == 0]
+        T = o.get_se3(kf[-1])
+        for b in (g, o):
+            v = b.add_se3_node(T)
+            b.add_se3_edge(kf[-1], v, np.eye(4)[:3], np.eye(6))
+            b.add_se3_point_xyz_edge(v, lms[0], np.array([1.0, 0.5, 0.2]), np.eye(3))
+        assert g.optimize(2) and o.optimize(2)
+        Mg = g.computeLandmarkMarginals(lms[:3])
+        Mo = o.computeLandmarkMarginals(lms[:3], relinearize=False)
+        assert np.abs(Mg - Mo).max() <= 1e-6 * np.abs(Mo).max()
+
+
+def test_landmark_marginals_cfg2_sample():
+    """K5 at the headline size (10 000 keyframes: one column per launch) with the bench preconditioner"""
+    spec = synth.make_config_graph("cfg2")
+    g, o, ids = _pair(spec, preconditioner=3, pcg_tol=1e-10)
+    assert g.optimize(2) and o.optimize(2)
+    lms = [int(ids[v]) for v in range(spec.vkind.size) if spec.vkind[v] == 1]
+    lms = [lms[0], lms[len(lms) // 2], lms[-1]]
+    Mg = g.computeLandmarkMarginals(lms)
+    Mo = o.computeLandmarkMarginals(lms, relinearize=False)
+    assert Mg is not None
+    assert np.abs(Mg - Mo).max() <= 1e-5 * np.abs(Mo).max(), np.abs(Mg - Mo).max() / np.abs(Mo).max()
+
+
 def test_g2o_save_load_roundtrip(tmp_path):
     spec = synth.make_config_graph("cfg1")
     g, o, ids = _pair(spec)

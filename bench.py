@@ -120,6 +120,71 @@ def graph_bytes(spec):
     return dict(Np=Np, Nl=Nl, El=El, Epp=Epp, b_cg=b_cg, b_lin=b_lin, b_chi2=b_chi2, b_upd=b_upd, h2d=h2d, d2h=d2h)
 
 
+class FrameRecorder:
+    """GraphSLAM proxy for the per-frame loop: remembers the add_* calls and, at chosen frames, the estimates right before
+    optimize(), so that exactly that frame's optimize() can be repeated on the CPU oracle afterwards (same graph, same
+    starting estimates) and compared in time and in result."""
+
+    def __init__(self, graph, probe_frames):
+        self.g = graph
+        self.calls = []
+        self.kinds = []                      # per vertex id: 0 = SE3, 1 = XYZ
+        self.probe_frames = set(probe_frames)
+        self.n_opt = 0
+        self.probes = []
+
+    def __getattr__(self, name):
+        return getattr(self.g, name)
+
+    def add_se3_node(self, T):
+        self.calls.append(("add_se3_node", (np.array(T, dtype=np.float64),)))
+        self.kinds.append(0)
+        return self.g.add_se3_node(T)
+
+    def add_point_xyz_node(self, x):
+        self.calls.append(("add_point_xyz_node", (np.array(x, dtype=np.float64),)))
+        self.kinds.append(1)
+        return self.g.add_point_xyz_node(x)
+
+    def add_se3_edge(self, a, b, Z, info):
+        self.calls.append(("add_se3_edge", (a, b, np.array(Z, dtype=np.float64), np.array(info, dtype=np.float64))))
+        return self.g.add_se3_edge(a, b, Z, info)
+
+    def add_se3_point_xyz_edge(self, a, b, z, info):
+        self.calls.append(("add_se3_point_xyz_edge", (a, b, np.array(z, dtype=np.float64), np.array(info, dtype=np.float64))))
+        return self.g.add_se3_point_xyz_edge(a, b, z, info)
+
+    def _estimates(self):
+        return [self.g.get_se3(v) if k == 0 else self.g.get_point_xyz(v) for v, k in enumerate(self.kinds)]
+
+    def optimize(self, max_iterations=1024):
+        self.n_opt += 1
+        if self.n_opt not in self.probe_frames:
+            return self.g.optimize(max_iterations)
+        before = self._estimates()
+        t0 = time.perf_counter()
+        r = self.g.optimize(max_iterations)
+        dt = time.perf_counter() - t0
+        self.probes.append({"frame": self.n_opt, "n_calls": len(self.calls), "n_vertices": len(self.kinds), "before": before,
+                            "after": self._estimates(), "gpu_ms": 1e3 * dt, "max_iterations": max_iterations,
+                            "lm_iterations": int(self.g.iterations), "trials": int((getattr(self.g, "stats", None) or {}).get("total_trials", -1))})
+        return r
+
+    def replay_on(self, oracle_graph, probe):
+        for name, a in self.calls[:probe["n_calls"]]:
+            getattr(oracle_graph, name)(*a)
+        for v in range(probe["n_vertices"]):
+            (oracle_graph.set_se3 if self.kinds[v] == 0 else oracle_graph.set_point_xyz)(v, probe["before"][v])
+        t0 = time.perf_counter()
+        oracle_graph.optimize(probe["max_iterations"])
+        dt = time.perf_counter() - t0
+        diff = 0.0
+        for v in range(probe["n_vertices"]):
+            e = oracle_graph.get_se3(v) if self.kinds[v] == 0 else oracle_graph.get_point_xyz(v)
+            diff = max(diff, float(np.abs(np.asarray(e) - np.asarray(probe["after"][v])).max()))
+        return 1e3 * dt, diff, int(oracle_graph.iterations)
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle restatement of g2o (sparse-Cholesky LM) and PCL (RANSAC) on the host cores."""
     if rank != 0:
@@ -365,9 +430,9 @@ def main():
     # ---------------- K5: GraphSLAM::computeLandmarkMarginals (graph_slam.cpp:221-234) ----------------------------------
     # the reference calls it after every optimise (semantic_graph_slam.cpp:89,181-205).  Timed through the C-ABI with host
     # buffers on (i) a sample of cfg2's landmarks right after the e2e optimise above (10 000 keyframes fill the chip: one
-    # column per PCG launch) and (ii) ALL landmarks of a 1 000-keyframe graph (the per-frame loop's size: 10 replicas of
-    # the graph side by side, one launch = 10 columns), each beside the oracle's time for the same call on the same
-    # landmarks (a CSparse-style factorisation of the full system + 3 solves per landmark).
+    # latency-bound PCG solve per column) and (ii) ALL landmarks of a 1 000-keyframe graph (the per-frame loop's size), each
+    # beside the oracle's time for the same call on the same landmarks (a CSparse-style factorisation of the full system
+    # + 3 solves per landmark).  At the small size the CPU factorisation wins; at cfg2 the GPU does.
     if world == 1 and not args.no_marginals:
         lm_all = ids_cfg2[spec.vkind == 1].astype(np.int32)
         n_s = min(args.marginals_sample, lm_all.size)
@@ -389,9 +454,9 @@ def main():
             "metric": "landmark marginals per second (3x3 blocks of H^-1, computeLandmarkMarginals)",
             "cfg2_sample": {"landmarks": int(sample.size), "of": int(lm_all.size), "seconds": t_mg, "value": sample.size / t_mg,
                             "unit": "landmarks/s", "all_landmarks_extrapolated_s": t_mg * lm_all.size / sample.size,
-                            "columns_per_launch": 1},
+                            "pcg_solves": int(3 * sample.size)},
             "kf1000_all": {"landmarks": int(lmm.size), "seconds": t_mm, "value": lmm.size / t_mm, "unit": "landmarks/s",
-                           "columns_per_launch": min(16, 10500 // 1000)}}
+                           "pcg_solves": int(3 * lmm.size)}}
         if rank == 0 and not args.no_cpu_baseline:
             import oracle
             om = oracle.OracleGraphSLAM(threads=1)
@@ -480,7 +545,8 @@ def main():
             t_all = time.perf_counter() - t0
             return slam, t_all, t_seg, marks
 
-        g5 = GraphSLAM(device=local, preconditioner=args.preconditioner, pcg_tol=args.pcg_tol)
+        g5 = FrameRecorder(GraphSLAM(device=local, preconditioner=args.preconditioner, pcg_tol=args.pcg_tol),
+                           [n_kf // 4, n_kf // 2, 3 * n_kf // 4, n_kf])
         slam5, t5, t5seg, marks5 = drive(g5, DataAssociation(**KITTI), n_kf,
                                          lambda nd: oseg.segment(clf.msg, layf, clf.boxes[:nd], max_regions=8))
         line["cfg5"] = {"metric": "frames/sec (per-frame segment + associate + optimise loop)", "value": n_kf / t5, "unit": "frames/s",
@@ -502,6 +568,13 @@ def main():
             line["cfg5"]["gpu_on_the_same_%d_frames" % n_cpu] = {"value": n_cpu / marks5.get(n_cpu, t5 * n_cpu / n_kf) if n_cpu in marks5 else None,
                                                                   "unit": "frames/s"}
             line["cfg5"]["association_identical_to_cpu"] = bool(same)
+            # the CPU loop above covers the cheap early frames only; the same frame's optimize() at four graph sizes:
+            per_size = []
+            for pr in g5.probes:
+                cpu_ms, diff, its_o = g5.replay_on(oracle.OracleGraphSLAM(threads=1), pr)
+                per_size.append({"keyframes": pr["frame"], "gpu_ms": pr["gpu_ms"], "cpu_ms": cpu_ms, "lm_iterations": pr["lm_iterations"],
+                                 "lm_iterations_cpu": its_o, "trials": pr["trials"], "max_abs_diff_after": diff})
+            line["cfg5"]["optimize_of_one_frame_by_graph_size"] = per_size
         del g5
 
     # ---------------- CPU baseline (rank 0, N == 1 only) -----------------------------------------

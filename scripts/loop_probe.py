@@ -18,12 +18,9 @@ for k in range(n_kf):
         print(f"frame {k+1}: run {dt*1e3:.1f} ms  lm_its {st['iterations']} trials {st['total_trials']} pcg {st['total_pcg_iters']} "
               f"prepare {st['ms_prepare']:.2f} device {st['ms_device']:.2f} pcg_ms {st['ms_pcg']:.2f} total {st['ms_total']:.2f} launches {st['kernel_launches']}")
 print("total", time.time() - t0)
-# K5 on the final graph: all mapped landmarks, several columns per launch vs one
+# K5 on the final graph: all mapped landmarks
 lm = np.array(sorted(slam.landmark_nodes_.values()), dtype=np.int32)
-for rep in ("", "1"):
-    if rep:
-        os.environ["SSB_MARG_REPLICAS"] = rep
-    g.computeLandmarkMarginals(lm[:2])
-    t = time.perf_counter()
-    M = g.computeLandmarkMarginals(lm)
-    print(f"marginals of {lm.size} landmarks on {n_kf} keyframes (SSB_MARG_REPLICAS={rep or 'auto'}): {(time.perf_counter()-t)*1e3:.1f} ms  trace0 {np.trace(M[0]):.9e}")
+g.computeLandmarkMarginals(lm[:2])
+t = time.perf_counter()
+M = g.computeLandmarkMarginals(lm)
+print(f"marginals of {lm.size} landmarks on {n_kf} keyframes: {(time.perf_counter()-t)*1e3:.1f} ms  trace0 {np.trace(M[0]):.9e}")

@@ -340,12 +340,6 @@ struct ssb_graph {
   ShardPlan* plan = nullptr;     // outer handle: who owns what, identical on every rank
   std::vector<Pose> snap_poses;  // outer handle: host copy of the estimates at ssb_graph_snapshot
   std::vector<double> snap_lms;
-  // ---- landmark marginals of graphs that fill only part of the chip (marginals_replicated) ----
-  ssb_graph* marg_rep = nullptr;            // k copies of this graph side by side: one PCG launch = k columns
-  int marg_rep_k = 0;
-  unsigned long long structure_serial = 0;  // bumped whenever prepare() rebuilt the tables
-  unsigned long long marg_rep_serial = 0;   // structure_serial the replicated graph was built from
-  bool linpoint_in_bak = false;             // d_pose_bak / d_lm_bak hold the estimates the resident system was linearised at
 };
 
 // k_pcg_flow is instantiated for the grids it is launched with: 148 CTAs (one per B200 SM); a sharded graph whose ranks
@@ -482,10 +476,6 @@ void ssb_graph_destroy(ssb_graph* g) {
   if (g->shard) {
     ssb_graph_destroy(g->shard);
     g->shard = nullptr;
-  }
-  if (g->marg_rep) {
-    ssb_graph_destroy(g->marg_rep);
-    g->marg_rep = nullptr;
   }
   delete g->plan;
   g->plan = nullptr;
@@ -1404,7 +1394,6 @@ static int prepare(ssb_graph* g) {
     SSB_CUDA_CHECK(cudaStreamSynchronize(s));  // host vectors above go out of scope
     tick("upload sync");
     g->structure_dirty = false;
-    g->structure_serial++;
     g->host_est_dirty = true;
     g->have_system = false;
     g->have_snapshot = false;
@@ -1546,7 +1535,6 @@ static int launch_linearize(ssb_graph* g) {
   }
   SSB_CUDA_CHECK(cudaGetLastError());
   g->have_system = true;
-  g->linpoint_in_bak = false;
   return SSB_OK;
 }
 // separate_coarse: invert the coarse matrix in k_coarse_invert (third stream) instead of inside k_pcg_flow.  Measured
@@ -1631,7 +1619,6 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
   if (apply) {
     k_backsub_update<<<(G.Np + 32 * G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
     g->launches++;
-    g->linpoint_in_bak = true;   // the backup taken before the update = the linearisation point of this iteration
   }
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;
@@ -2741,7 +2728,6 @@ int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len) {
     k_backsub_update<<<(g->G.Np + 32 * g->G.Nl + 127) / 128, 128, 0, g->stream>>>(g->G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
     k_copy_state<<<(n + 255) / 256, 256, 0, g->stream>>>(g->G.pose, g->d_pose_snap.p, g->G.Np, g->G.lm, g->d_lm_snap.p, g->G.Nl);
     g->launches += 3;
-    g->linpoint_in_bak = true;
   }
   std::vector<double> dp((size_t)6 * g->G.Np + 1), dl((size_t)3 * g->G.Nl + 1);
   SSB_CUDA_CHECK(cudaMemcpyAsync(dp.data(), g->G.x, (size_t)6 * g->G.Np * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
@@ -2779,140 +2765,6 @@ int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len) {
   return g->h_iscalars[0];
 }
 
-// ---- K5 with several right-hand sides per launch ------------------------------------------------------------------
-// One damped solve is latency-bound and costs about the same for 1 000 as for 10 000 keyframes (the data-flow kernel
-// holds up to 80 keyframes per CTA, a small graph fills a fraction of that).  The 3 n columns of the landmark marginals
-// share ONE matrix, so a graph of Np keyframes is laid out k = min(16, 10 500 / Np) times side by side in a shadow handle
-// (vertices / edges of replica j shifted by j Np, j Nl): the block-diagonal system diag(S, ..., S) with k different
-// right-hand sides is ONE conjugate-gradient solve whose iterate for block j is p_m(S) b_j with a polynomial common to
-// all blocks — it converges like the slowest column — and every existing kernel runs unchanged on the shadow graph.
-// The shadow is rebuilt when the structure changed and takes its estimates (the linearisation point of the system the
-// last optimize left behind, g2o's computeMarginals semantics) device-to-device.
-static int marg_replica_count(const ssb_graph* g) {
-  const char* ev = std::getenv("SSB_MARG_REPLICAS");   // 0 / 1: one column per launch (A/B measurements and tests)
-  const int env = ev ? std::atoi(ev) : -1;
-  const int Np = (int)g->poses.size();
-  if (env == 0 || env == 1 || Np < 1) return 1;
-  int k = std::min(SSB_MARG_MAX_REP, 10500 / Np);
-  if (env > 1) k = std::min(k, env);
-  return std::max(k, 1);
-}
-static int build_marg_replica(ssb_graph* g, int k) {
-  if (g->marg_rep && g->marg_rep_k == k && g->marg_rep_serial == g->structure_serial) return SSB_OK;
-  if (!g->marg_rep) {
-    ssb_graph_opts o = g->opts;
-    o.device = g->device;
-    g->marg_rep = ssb_graph_create(&o);
-    if (!g->marg_rep) return SSB_ERR_CUDA;
-  }
-  ssb_graph* r = g->marg_rep;
-  const int Np = (int)g->poses.size(), Nl = (int)(g->lms.size() / 4), nV = (int)g->V.size();
-  const int nPP = (int)g->pp.size(), nPL = (int)g->pl.size();
-  r->V.clear();
-  r->E.clear();
-  r->poses.clear();
-  r->lms.clear();
-  r->lm_kind.clear();
-  r->pl_zd.clear();
-  r->pose_vid.clear();
-  r->lm_vid.clear();
-  r->pp.clear();
-  r->pl.clear();
-  r->V.reserve((size_t)k * nV);
-  r->E.reserve((size_t)k * g->E.size());
-  r->pp.reserve((size_t)k * nPP);
-  r->pl.reserve((size_t)k * nPL);
-  for (int j = 0; j < k; ++j) {
-    for (const HostVertex& v0 : g->V) {
-      HostVertex v = v0;
-      v.idx += j * (v.kind == VK_SE3 ? Np : Nl);
-      v.hidx = -1;
-      r->V.push_back(v);
-    }
-    for (const HostEdgeRef& e0 : g->E) {
-      HostEdgeRef e = e0;
-      e.idx += j * (e.kind == EK_PP ? nPP : nPL);
-      r->E.push_back(e);
-    }
-    r->poses.insert(r->poses.end(), g->poses.begin(), g->poses.end());
-    r->lms.insert(r->lms.end(), g->lms.begin(), g->lms.end());
-    r->lm_kind.insert(r->lm_kind.end(), g->lm_kind.begin(), g->lm_kind.end());
-    r->pl_zd.insert(r->pl_zd.end(), g->pl_zd.begin(), g->pl_zd.end());
-    for (int v : g->pose_vid) r->pose_vid.push_back(v + j * nV);
-    for (int v : g->lm_vid) r->lm_vid.push_back(v + j * nV);
-    for (const PPEdge& e0 : g->pp) {
-      PPEdge e = e0;
-      e.i += j * Np;
-      e.j += j * Np;
-      r->pp.push_back(e);
-    }
-    for (const PLEdge& e0 : g->pl) {
-      PLEdge e = e0;
-      e.p += j * Np;
-      e.l += j * Nl;
-      r->pl.push_back(e);
-    }
-  }
-  r->n_plane_vertices = k * g->n_plane_vertices;
-  r->structure_dirty = true;
-  r->host_est_dirty = true;
-  r->device_est_newer = false;
-  g->marg_rep_k = k;
-  g->marg_rep_serial = g->structure_serial;
-  return SSB_OK;
-}
-static int marginals_replicated(ssb_graph* g, const int* vids, int n, double* out9n, int k) {
-  SSB_TRY(build_marg_replica(g, k));
-  ssb_graph* r = g->marg_rep;
-  SSB_TRY(prepare(r));
-  const int Np = g->G.Np, Nl = g->G.Nl;
-  cudaStream_t s = r->stream;
-  SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
-  // the estimates the resident system of g was linearised at (see linpoint_in_bak), into every replica
-  const bool from_bak = g->have_system && g->linpoint_in_bak;
-  const Pose* src_pose = from_bak ? g->d_pose_bak.p : g->G.pose;
-  const double* src_lm = from_bak ? g->d_lm_bak.p : g->G.lm;
-  for (int j = 0; j < k; ++j) {
-    SSB_CUDA_CHECK(cudaMemcpyAsync(r->G.pose + (size_t)j * Np, src_pose, (size_t)Np * sizeof(Pose), cudaMemcpyDeviceToDevice, s));
-    if (Nl) SSB_CUDA_CHECK(cudaMemcpyAsync(r->G.lm + (size_t)4 * j * Nl, src_lm, (size_t)4 * Nl * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  }
-  r->have_system = false;
-  const long long l0 = r->launches;
-  SSB_TRY(launch_linearize(r));
-  SSB_TRY(launch_prep(r, 0.0, std::getenv("SSB_MARG_INKERNEL") == nullptr));
-  SSB_TRY(r->d_tmp.ensure((size_t)std::max(128, 9 * n + 8)));
-  double* status = r->d_tmp.p + 9 * (size_t)n;
-  SSB_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(double), s));
-  const size_t ev_keep = r->ev_used;
-  const int ncol = 3 * n;
-  for (int c0 = 0; c0 < ncol; c0 += k) {
-    MargCols mc;
-    for (int j = 0; j < SSB_MARG_MAX_REP; ++j) {
-      const int col = c0 + j;
-      const bool live = j < k && col < ncol;
-      mc.l[j] = live ? g->V[vids[col / 3]].idx : -1;
-      mc.c[j] = live ? col % 3 : 0;
-      mc.o[j] = live ? col / 3 : 0;
-    }
-    k_marg_rhs_rep<<<k, 256, 0, s>>>(r->G, mc, Np, Nl);
-    r->ev_used = ev_keep;  // do not grow the timing-event pool
-    SSB_TRY(launch_pcg(r, 0.0));
-    k_marg_out_rep<<<k, 64, 0, s>>>(r->G, mc, Nl, r->d_tmp.p, status);
-    r->launches += 2;
-  }
-  r->ev_used = ev_keep;
-  double st = 0.0;
-  SSB_CUDA_CHECK(cudaMemcpyAsync(out9n, r->d_tmp.p, (size_t)9 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
-  SSB_CUDA_CHECK(cudaMemcpyAsync(&st, status, sizeof(double), cudaMemcpyDeviceToHost, s));
-  SSB_TRY(read_scalars(r));
-  g->launches += r->launches - l0;
-  if (st != 0.0 || r->h_iscalars[1] != 0) {
-    set_error("landmark_marginals: PCG breakdown");
-    return 0;
-  }
-  return 1;
-}
-
 int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* out9n) {
   if (!g || (n > 0 && (!vids || !out9n)) || n < 0) return SSB_ERR_INVALID;
   for (int k = 0; k < n; ++k)
@@ -2930,11 +2782,6 @@ int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* o
     return 0;
   }
   SSB_TRY(prepare(g));
-  if (n == 0) return 1;
-  {
-    const int k = marg_replica_count(g);
-    if (k >= 2) return marginals_replicated(g, vids, n, out9n, k);
-  }
   if (!g->have_system) SSB_TRY(launch_linearize(g));  // else: the system built by the last optimize (g2o semantics)
   SSB_TRY(launch_prep(g, 0.0, std::getenv("SSB_MARG_INKERNEL") == nullptr));   // env: A/B switch for measurements
   SSB_TRY(g->d_tmp.ensure((size_t)std::max(128, 9 * n)));

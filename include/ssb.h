@@ -344,6 +344,63 @@ int ssb_organized_planes(ssb_ransac* r, const void* msg, const ssb_cloud_layout*
                          float* normals_out, int* labels_out, float* dist_out);
 double ssb_organized_last_ms(ssb_ransac* r);
 
+/* ------------------------------------------------------------------------------------------- */
+/* The DORMANT plane-clustering chain (never called by the reference's live path)       */
+/*   plane_segmentation::clusterAndSegmentAllPlanes   src/planar_segmentation/plane_segmentation.cpp:261-294   */
+/*   computeKmeans -> cv::kmeans                      :525-535                                                  */
+/*   compute2DConvexHull: SACSegmentation + pcl::ProjectInliers + pcl::ConvexHull   :631-664                    */
+/* Device code: csrc/ssb_cluster.cuh.  Uses the buffers and the stream of an ssb_ransac handle.                   */
+/* ------------------------------------------------------------------------------------------- */
+/* plane_segmentation::computeKmeans (:525-535): cv::kmeans(points, K, labels, TermCriteria(EPS + ITER, max_count, epsilon),
+ * attempts, cv::KMEANS_RANDOM_CENTERS, centroids) with OpenCV's arithmetic (labels and centres bit-identical to cv::kmeans of
+ * OpenCV 4.x for the same RNG state).  data: host float [n][dims] (dims <= 4, K <= 8); rng_state: cv::theRNG().state before the
+ * call, updated to its value after it (OpenCV's initial state is 0xffffffff); labels: host int [n]; centers: host float
+ * [K][dims]; compactness: the return value of cv::kmeans.  Returns SSB_OK or an error (n < K is an error: cv::kmeans throws). */
+int ssb_kmeans(ssb_ransac* r, const float* data, int n, int dims, int K, int max_count, double epsilon, int attempts,
+               unsigned long long* rng_state, int* labels, float* centers, double* compactness);
+
+/* pcl::ProjectInliers(SACMODEL_PLANE) + pcl::ConvexHull::reconstruct of compute2DConvexHull (:649-662): the points of pts4
+ * (host float [n][4]) selected by mask (host uint8 [n]) are projected onto the plane coef (a, b, c, d) and the vertices of their
+ * planar convex hull are returned in PCL's output order (decreasing angle about the hull's centroid): rows3 [max_rows][3] = the
+ * projected hull points, src (optional) = their indices in pts4.  Returns the number of hull vertices (may exceed max_rows;
+ * only max_rows are written) or a negative error; *n_inliers = points projected. */
+int ssb_project_hull(ssb_ransac* r, const float* pts4, const unsigned char* mask, int n, const float coef[4], float* rows3, int* src,
+                     int max_rows, int* n_inliers);
+
+typedef struct ssb_cluster_opts {
+  int num_centroids_normals;     /* 4     include/planar_segmentation/plane_segmentation.h:41 */
+  int num_centroids_distance;    /* 2     :42 */
+  int kmeans_attempts;           /* 10    plane_segmentation.cpp:531 */
+  int kmeans_max_count;          /* 10    :529 */
+  double kmeans_epsilon;         /* 0.01  :530 */
+  int min_cluster_points;        /* 500: a distance cluster is kept when it has MORE points (:419) */
+  float centroid_tolerance;      /* 0.3: filterCentroids keeps normals within +-0.3 per component of the horizontal normal (:511-516) */
+  int ransac_hypotheses;         /* 0 = PCL's adaptive stopping rule on a 512-sample stream; > 0 = score that many */
+  unsigned ransac_seed;          /* 12345: std::mt19937(seed) % n draws the 3-point samples of every cluster (PCL's own
+                                    boost::mt19937 + drawIndexSample stream is not reproduced) */
+  int reserved[4];
+} ssb_cluster_opts;
+
+typedef struct ssb_plane_cluster {   /* one entry of final_normals_with_distances + its hull (:399-425, :431-477) */
+  float normal[3];               /* the (filtered) k-means centroid of the normals */
+  float distance;                /* the k-means centroid of the signed distances */
+  int normal_label, distance_label;
+  int n_points;                  /* points of the cluster (> min_cluster_points) */
+  int n_inliers;                 /* RANSAC inliers that were projected onto the plane */
+  float coef[4];                 /* the refined plane of compute2DConvexHull's SACSegmentation */
+  int row0, n_rows;              /* its rows in rows8 */
+} ssb_plane_cluster;
+
+void ssb_cluster_default_opts(ssb_cluster_opts* o);
+/* plane_segmentation::clusterAndSegmentAllPlanes (:261-294).  cloud4 / normals4: host float [n][4] (x y z rgb as produced by
+ * ssb_crop_bbox; nx ny nz curvature as produced by ssb_organized_planes' normals_out), transformation_mat: row-major 4x4.
+ * rows8: the reference's final_pose_vec, one row per hull vertex (x, y, z, nx, ny, nz, d, 0).  Optional outputs (NULL to skip):
+ * labels_out [n] = first k-means label per point (-1 where the normal is NaN), centers_out [num_centroids_normals][3].
+ * Returns 1, 0 when there were not enough normals (<= 10, :316-320), or a negative error. */
+int ssb_cluster_planes(ssb_ransac* r, const float* cloud4, const float* normals4, int n, const float transformation_mat[16],
+                       const ssb_cluster_opts* opts, unsigned long long* rng_state, float* rows8, int max_rows, int* n_rows,
+                       ssb_plane_cluster* clusters, int max_clusters, int* n_clusters, int* labels_out, float* centers_out);
+
 void ssb_assoc_default_opts(ssb_assoc_opts* o);
 ssb_assoc* ssb_assoc_create(const ssb_assoc_opts* opts);   /* data_association::data_association + init */
 void ssb_assoc_destroy(ssb_assoc* a);

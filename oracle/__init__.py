@@ -21,7 +21,7 @@ _fp = C.POINTER(C.c_float)
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_graph.cpp", "oracle_ransac.cpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_graph.cpp", "oracle_ransac.cpp", "oracle_segment.cpp", "oracle_cluster.cpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle.so"])
     return so
@@ -374,3 +374,75 @@ def organized_planes(cloud_hw4, min_inliers=500, angular_threshold=0.017453 * 2.
     m = min(n, max_regions)
     return {"n": n, "normals": nrm, "labels_cc": lcc, "labels": lref, "centroid": cen[:m], "model": mod[:m], "n_inliers": nin[:m],
             "contour_points": ncon[:m], "area": area[:m]}
+
+
+# ---- the dormant plane-clustering chain (oracle_cluster.cpp) ---------------------------------------------------------------
+PLANE_CLUSTER_DTYPE = np.dtype([("normal", np.float32, 3), ("distance", np.float32), ("normal_label", np.int32),
+                                ("distance_label", np.int32), ("n_points", np.int32), ("n_inliers", np.int32),
+                                ("coef", np.float32, 4), ("row0", np.int32), ("n_rows", np.int32)])
+
+
+def kmeans(data, K, rng_state=0xFFFFFFFF, attempts=10, max_count=10, eps=0.01):
+    """cv::kmeans(data, K, labels, TermCriteria(EPS + COUNT, max_count, eps), attempts, KMEANS_RANDOM_CENTERS, centers) restated
+    (plane_segmentation.cpp:525-535).  rng_state = cv::theRNG().state before the call.
+    Returns (compactness, labels (N,), centers (K, dims), rng state after)."""
+    d = np.ascontiguousarray(data, dtype=np.float32)
+    if d.ndim == 1:
+        d = d[:, None]
+    n, dims = d.shape
+    lab = np.zeros(n, dtype=np.int32)
+    cen = np.zeros((K, dims), dtype=np.float32)
+    st = C.c_ulonglong(rng_state if rng_state else 0xFFFFFFFF)
+    L = lib()
+    L.orc_kmeans.restype = C.c_double
+    L.orc_kmeans.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_ulonglong),
+                             C.c_void_p, C.c_void_p]
+    c = L.orc_kmeans(d.ctypes.data, n, dims, K, max_count, eps, attempts, C.byref(st), lab.ctypes.data, cen.ctypes.data)
+    return c, lab, cen, st.value
+
+
+def project_hull(pts4, mask, coef):
+    """pcl::ProjectInliers(SACMODEL_PLANE) + pcl::ConvexHull (plane_segmentation.cpp:649-662) restated.
+    Returns (hull vertices (k, 3) in PCL's output order, their indices in pts4, number of projected inliers)."""
+    p = np.ascontiguousarray(pts4, dtype=np.float32).reshape(-1, 4)
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    cf = np.ascontiguousarray(coef, dtype=np.float32)
+    n = p.shape[0]
+    rows = np.zeros((max(n, 1), 3), dtype=np.float32)
+    src = np.zeros(max(n, 1), dtype=np.int32)
+    nin = C.c_int(0)
+    L = lib()
+    L.orc_project_hull.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    k = L.orc_project_hull(p.ctypes.data, m.ctypes.data, n, cf.ctypes.data, rows.ctypes.data, src.ctypes.data, n, C.byref(nin))
+    return rows[:k].copy(), src[:k].copy(), nin.value
+
+
+def cluster_planes(cloud4, normals4, T, rng_state=0xFFFFFFFF, num_centroids_normals=4, num_centroids_distance=2, attempts=10,
+                   max_count=10, eps=0.01, min_cluster_points=500, centroid_tolerance=0.3, ransac_hypotheses=0, ransac_seed=12345,
+                   coef_override=None, max_rows=65536, max_clusters=16):
+    """plane_segmentation::clusterAndSegmentAllPlanes (plane_segmentation.cpp:261-294) restated.
+    Returns dict(rows (k, 8), clusters (structured), labels (n,), centers (Kn, 3), rng_state)."""
+    c = np.ascontiguousarray(cloud4, dtype=np.float32).reshape(-1, 4)
+    q = np.ascontiguousarray(normals4, dtype=np.float32).reshape(-1, 4)
+    n = c.shape[0]
+    assert q.shape[0] == n
+    T16 = np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+    rows = np.zeros((max_rows, 8), dtype=np.float32)
+    cl = np.zeros(max_clusters, dtype=PLANE_CLUSTER_DTYPE)
+    lab = np.zeros(n, dtype=np.int32)
+    cen = np.zeros((num_centroids_normals, 3), dtype=np.float32)
+    st = C.c_ulonglong(rng_state if rng_state else 0xFFFFFFFF)
+    nr, nc = C.c_int(0), C.c_int(0)
+    ov = None
+    if coef_override is not None:
+        ov = np.ascontiguousarray(coef_override, dtype=np.float32).reshape(-1, 4)
+        assert ov.shape[0] >= max_clusters or True
+    L = lib()
+    L.orc_cluster_planes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                     C.c_float, C.c_int, C.c_uint, C.POINTER(C.c_ulonglong), C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                     C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_cluster_planes(c.ctypes.data, q.ctypes.data, n, T16.ctypes.data, num_centroids_normals, num_centroids_distance, attempts,
+                         max_count, eps, min_cluster_points, centroid_tolerance, ransac_hypotheses, ransac_seed, C.byref(st),
+                         rows.ctypes.data, max_rows, C.byref(nr), cl.ctypes.data, max_clusters, C.byref(nc), lab.ctypes.data,
+                         cen.ctypes.data, ov.ctypes.data if ov is not None else None)
+    return dict(rows=rows[:nr.value].copy(), clusters=cl[:nc.value].copy(), labels=lab, centers=cen, rng_state=st.value)

@@ -28,39 +28,11 @@
 #include <limits>
 #include <vector>
 
+#include "oracle_ransac.h"
+
 namespace orcr {
 
-struct PlaneResult {       // must match ssb_plane_result in include/ssb.h
-  int status;              // 0 ok, 1 spurious bbox (plane_segmentation.cpp:34-38), 2 no valid model
-  int n_points;            // w*h of the crop
-  int best_hyp;            // index of the winning hypothesis (first best), -1 if none
-  int best_count;          // its inlier count
-  int iterations;          // hypotheses consumed (fixed-K: K; adaptive: PCL iterations_)
-  int refined_count;       // inliers of the refined model (== best_count when refine off)
-  float coef[4];           // winning 3-point model
-  float refined[4];        // after optimizeModelCoefficients (== coef when refine off or < 4 inliers)
-  float centroid[3];       // centroid of the winning model's inliers (zeros when not refined)
-  int reserved;
-};
 
-static inline float plane_dist(const float* c, float x, float y, float z) {
-  // Eigen SSE3 dot: (c0*x + c1*y) + (c2*z + c3*1)
-  float a = c[0] * x;
-  float b = c[1] * y;
-  float cc = c[2] * z;
-  float s0 = a + b;
-  float s1 = cc + c[3];
-  return std::fabs(s0 + s1);
-}
-
-// smallest float t with (double)t >= thr : float d satisfies (double)d < thr  <=>  d < t
-static inline float effective_threshold(double thr) {
-  float t = (float)thr;
-  if ((double)t < thr) t = std::nextafterf(t, std::numeric_limits<float>::infinity());
-  return t;
-}
-
-// SampleConsensusModelPlane::computeModelCoefficients. pts: xyz triplets (stride 4 floats).
 static bool model_from_triple(const float* pts, const int* tri, float* coef) {
   const float* p0 = pts + 4 * (size_t)tri[0];
   const float* p1 = pts + 4 * (size_t)tri[1];
@@ -253,6 +225,86 @@ static int crop(const uint8_t* msg, int width, int height, int point_step, int r
 
 using namespace orcr;
 
+// pcl::SACSegmentation (SACMODEL_PLANE, SAC_RANSAC) on one point set: hypotheses from the index triples `tri`
+// (mode 0: all K scored, first best wins; mode 1: RandomSampleConsensus::computeModel's adaptive stopping rule),
+// optional refine (optimizeModelCoefficients) and re-selection of the inliers.  Used by orc_ransac_batch per crop and by
+// the clustering chain (oracle_cluster.cpp) per cluster.  counts_out: K ints or null; mask_out: n bytes or null.
+void orc_ransac_points(const float* pts, int n, const int* tri, int K, double threshold, int refine, int mode, int max_iterations,
+                       double probability, PlaneResult& R, int* counts_out, uint8_t* mask_out) {
+  const float thr = effective_threshold(threshold);
+  int best = 0, best_k = -1;
+  float best_coef[4] = {0, 0, 0, 0};
+  int iterations = 0;
+  if (counts_out)
+    for (int k = 0; k < K; ++k) counts_out[k] = -1;
+  if (mode == 0) {
+    for (int k = 0; k < K && n > 0; ++k) {
+      float coef[4];
+      int c = 0;
+      if (model_from_triple(pts, tri + 3 * k, coef)) c = count_within(pts, n, coef, thr);
+      else c = 0;
+      if (counts_out) counts_out[k] = c;
+      if (c > best) {
+        best = c;
+        best_k = k;
+        std::memcpy(best_coef, coef, sizeof(coef));
+      }
+      ++iterations;
+    }
+  } else {
+    // RandomSampleConsensus::computeModel
+    double kk = 1.0;
+    const double log_probability = std::log(1.0 - probability);
+    const double one_over_indices = n > 0 ? 1.0 / (double)n : 0.0;
+    int skipped = 0;
+    const int max_skip = max_iterations * 10;
+    int s = 0;  // position in the sample stream
+    while (iterations < kk && skipped < max_skip && s < K && n > 0) {
+      float coef[4];
+      int k = s++;
+      if (!model_from_triple(pts, tri + 3 * k, coef)) {
+        ++skipped;
+        continue;
+      }
+      int c = count_within(pts, n, coef, thr);
+      if (counts_out) counts_out[k] = c;
+      if (c > best) {
+        best = c;
+        best_k = k;
+        std::memcpy(best_coef, coef, sizeof(coef));
+        double w = (double)best * one_over_indices;
+        double p_no_outliers = 1.0 - std::pow(w, 3.0);
+        p_no_outliers = std::max(std::numeric_limits<double>::epsilon(), p_no_outliers);
+        p_no_outliers = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no_outliers);
+        kk = log_probability / std::log(p_no_outliers);
+      }
+      ++iterations;
+      if (iterations > max_iterations) break;
+    }
+  }
+  R.iterations = iterations;
+  R.best_hyp = best_k;
+  R.best_count = best;
+  if (best_k < 0) {
+    R.status = 2;
+    if (mask_out) std::memset(mask_out, 0, n);
+    return;
+  }
+  std::memcpy(R.coef, best_coef, sizeof(best_coef));
+  if (refine)
+    refine_plane(pts, n, best_coef, thr, R.refined, R.centroid);
+  else
+    std::memcpy(R.refined, best_coef, sizeof(best_coef));
+  int rc = 0;
+  for (int i = 0; i < n; ++i) {
+    const float* p = pts + 4 * (size_t)i;
+    bool in = plane_dist(R.refined, p[0], p[1], p[2]) < thr;
+    rc += in;
+    if (mask_out) mask_out[i] = in ? 1 : 0;
+  }
+  R.refined_count = rc;
+}
+
 extern "C" {
 
 int orc_crop(const void* msg, int width, int height, int point_step, int row_step, const int* offsets4,
@@ -268,7 +320,6 @@ int orc_ransac_batch(const void* msg, int width, int height, int point_step, int
                        const int* boxes, int nb, const int* triples, int K, double threshold, int refine, int mode,
                        int max_iterations, double probability, PlaneResult* results, int* counts_out,
                        uint8_t* mask_out) {
-  const float thr = effective_threshold(threshold);
   size_t mask_off = 0;
   std::vector<float> pts;
   for (int b = 0; b < nb; ++b) {
@@ -286,79 +337,8 @@ int orc_ransac_batch(const void* msg, int width, int height, int point_step, int
     R.n_points = n;
     pts.resize((size_t)4 * std::max(n, 1));
     crop((const uint8_t*)msg, width, height, point_step, row_step, offsets4, box, pts.data());
-    const int* tri = triples + (size_t)3 * K * b;
-    int best = 0, best_k = -1;
-    float best_coef[4] = {0, 0, 0, 0};
-    int iterations = 0;
-    if (counts_out)
-      for (int k = 0; k < K; ++k) counts_out[(size_t)b * K + k] = -1;
-    if (mode == 0) {
-      for (int k = 0; k < K && n > 0; ++k) {
-        float coef[4];
-        int c = 0;
-        if (model_from_triple(pts.data(), tri + 3 * k, coef)) c = count_within(pts.data(), n, coef, thr);
-        else c = 0;
-        if (counts_out) counts_out[(size_t)b * K + k] = c;
-        if (c > best) {
-          best = c;
-          best_k = k;
-          std::memcpy(best_coef, coef, sizeof(coef));
-        }
-        ++iterations;
-      }
-    } else {
-      // RandomSampleConsensus::computeModel
-      double kk = 1.0;
-      const double log_probability = std::log(1.0 - probability);
-      const double one_over_indices = n > 0 ? 1.0 / (double)n : 0.0;
-      int skipped = 0;
-      const int max_skip = max_iterations * 10;
-      int s = 0;  // position in the sample stream
-      while (iterations < kk && skipped < max_skip && s < K && n > 0) {
-        float coef[4];
-        int k = s++;
-        if (!model_from_triple(pts.data(), tri + 3 * k, coef)) {
-          ++skipped;
-          continue;
-        }
-        int c = count_within(pts.data(), n, coef, thr);
-        if (counts_out) counts_out[(size_t)b * K + k] = c;
-        if (c > best) {
-          best = c;
-          best_k = k;
-          std::memcpy(best_coef, coef, sizeof(coef));
-          double w = (double)best * one_over_indices;
-          double p_no_outliers = 1.0 - std::pow(w, 3.0);
-          p_no_outliers = std::max(std::numeric_limits<double>::epsilon(), p_no_outliers);
-          p_no_outliers = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no_outliers);
-          kk = log_probability / std::log(p_no_outliers);
-        }
-        ++iterations;
-        if (iterations > max_iterations) break;
-      }
-    }
-    R.iterations = iterations;
-    R.best_hyp = best_k;
-    R.best_count = best;
-    if (best_k < 0) {
-      R.status = 2;
-      mask_off += (size_t)n;
-      if (mask_out) std::memset(mask_out + mask_off - n, 0, n);
-      continue;
-    }
-    std::memcpy(R.coef, best_coef, sizeof(best_coef));
-    if (refine)
-      refine_plane(pts.data(), n, best_coef, thr, R.refined, R.centroid);
-    else
-      std::memcpy(R.refined, best_coef, sizeof(best_coef));
-    int rc = 0;
-    for (int i = 0; i < n; ++i) {
-      const float* p = pts.data() + 4 * (size_t)i;
-      bool in = plane_dist(R.refined, p[0], p[1], p[2]) < thr;
-      rc += in;
-      if (mask_out) mask_out[mask_off + i] = in ? 1 : 0;
-    }
-    R.refined_count = rc;
+    orc_ransac_points(pts.data(), n, triples + (size_t)3 * K * b, K, threshold, refine, mode, max_iterations, probability, R,
+                      counts_out ? counts_out + (size_t)b * K : nullptr, mask_out ? mask_out + mask_off : nullptr);
     mask_off += (size_t)n;
   }
   return 0;

@@ -45,6 +45,13 @@ class OrganizedOpts(C.Structure):
                 ("norm_point_thres", C.c_int), ("reserved", C.c_int * 3)]
 
 
+class ClusterOpts(C.Structure):
+    _fields_ = [("num_centroids_normals", C.c_int), ("num_centroids_distance", C.c_int), ("kmeans_attempts", C.c_int),
+                ("kmeans_max_count", C.c_int), ("kmeans_epsilon", C.c_double), ("min_cluster_points", C.c_int),
+                ("centroid_tolerance", C.c_float), ("ransac_hypotheses", C.c_int), ("ransac_seed", C.c_uint),
+                ("reserved", C.c_int * 4)]
+
+
 def build(verbose: bool = False) -> str:
     """Compile libssb.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-s"]
@@ -66,6 +73,7 @@ SYMBOLS = [
     "ssb_graph_shard_info", "ssb_shard_plan", "ssb_ransac_default_opts",
     "ssb_ransac_create", "ssb_ransac_destroy", "ssb_ransac_plane_batch", "ssb_ransac_upload",
     "ssb_organized_default_opts", "ssb_organized_planes", "ssb_organized_last_ms", "ssb_ransac_run_resident", "ssb_ransac_fetch", "ssb_ransac_stream", "ssb_ransac_launch_count", "ssb_ransac_timing", "ssb_crop_bbox",
+    "ssb_kmeans", "ssb_project_hull", "ssb_cluster_default_opts", "ssb_cluster_planes",
     "ssb_segment_planar_surfaces", "ssb_assoc_default_opts", "ssb_assoc_create", "ssb_assoc_destroy", "ssb_assoc_find_matches",
     "ssb_assoc_set_landmark_estimate", "ssb_assoc_set_landmark_cov", "ssb_assoc_num_landmarks", "ssb_assoc_get_landmark",
     "ssb_last_error", "ssb_build_info", "ssb_graph_stream", "ssb_graph_snapshot", "ssb_graph_restore",
@@ -148,6 +156,11 @@ def lib():
     L.ssb_organized_default_opts.argtypes = [C.POINTER(OrganizedOpts)]
     L.ssb_organized_planes.argtypes = [vp, vp, C.POINTER(CloudLayoutC), vp, C.c_int, C.POINTER(OrganizedOpts), C.c_int, vp, vp, vp, vp,
                                        vp, vp]
+    L.ssb_kmeans.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_ulonglong), vp, vp, dp]
+    L.ssb_project_hull.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, ip]
+    L.ssb_cluster_default_opts.argtypes = [C.POINTER(ClusterOpts)]
+    L.ssb_cluster_planes.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(ClusterOpts), C.POINTER(C.c_ulonglong), vp, C.c_int, ip, vp,
+                                     C.c_int, ip, vp, vp]
     L.ssb_organized_last_ms.argtypes = [vp]
     L.ssb_organized_last_ms.restype = C.c_double
     _LIB = L

@@ -15,11 +15,14 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <random>
+#include <utility>
 #include <vector>
 
 #include "../../include/ssb.h"
 #include "ssb_common.cuh"
 #include "ssb_organized.cuh"
+#include "ssb_cluster.cuh"
 
 namespace ssb {
 
@@ -531,6 +534,12 @@ struct ssb_ransac {
   RBuf<unsigned long long> d_lastev;
   cudaEvent_t oev[2] = {nullptr, nullptr};
   double org_ms = 0.0;
+  // plane-clustering chain (ssb_cluster.cuh)
+  RBuf<unsigned char> c_flags, c_maskh;
+  RBuf<int> c_pos, c_count, c_keep, c_mem, c_labels, c_dlabels, c_src, c_cidx, c_csrc, c_ext;
+  RBuf<float> c_data, c_dist, c_init, c_centers, c_lohi;
+  RBuf<double> c_compact;
+  RBuf<float4> c_cloud, c_nrm, c_pts, c_proj, c_cand;
 };
 
 static int plan(ssb_ransac* r, const ssb_cloud_layout* L, const ssb_bbox* bx, int nb) {
@@ -573,7 +582,7 @@ static int plan(ssb_ransac* r, const ssb_cloud_layout* L, const ssb_bbox* bx, in
   return SSB_OK;
 }
 
-static int run_device(ssb_ransac* r) {
+static int run_device(ssb_ransac* r, bool skip_crop = false) {
   const int nb = r->nb, K = r->K;
   cudaStream_t s = r->stream;
   const float thr = effective_threshold(r->opts.threshold);
@@ -584,7 +593,7 @@ static int run_device(ssb_ransac* r) {
   SSB_CUDA_CHECK(cudaEventRecord(r->ev[2], s));
   SSB_CUDA_CHECK(cudaEventRecord(r->ev[3], s));
   SSB_CUDA_CHECK(cudaMemsetAsync(r->d_counts.p, 0, (size_t)nb * std::max(K, 1) * sizeof(int), s));
-  {
+  if (!skip_crop) {
     dim3 grid(8, nb);
     k_crop<<<grid, 256, 0, s>>>(r->d_msg.p, r->layout, r->d_boxes.p, r->d_crop.p);
     r->launches++;
@@ -918,5 +927,423 @@ int ssb_organized_planes(ssb_ransac* r, const void* msg, const ssb_cloud_layout*
 }
 // CUDA-event time of the device pipeline of the last ssb_organized_planes call (crop .. boundary), ms
 double ssb_organized_last_ms(ssb_ransac* r) { return r ? r->org_ms : 0.0; }
+
+}  // extern "C"
+
+// =============================================================================================================
+// The dormant plane-clustering chain (ssb_cluster.cuh): host side
+// =============================================================================================================
+namespace ssb {
+// cv::RNG (multiply-with-carry): the random centres of cv::kmeans(KMEANS_RANDOM_CENTERS) are the only thing drawn from it
+struct CvRng {
+  unsigned long long state;
+  unsigned next() {
+    state = (unsigned long long)(unsigned)state * 4164903690ULL + (unsigned)(state >> 32);
+    return (unsigned)state;
+  }
+  float uniform01() { return next() * 2.3283064365386962890625e-10f; }
+};
+static int cl_rank(ssb_ransac* r, const unsigned char* flags, int n, int* count) {
+  int rc;
+  if ((rc = r->c_pos.ensure((size_t)std::max(n, 1))) || (rc = r->c_count.ensure(16))) return rc;
+  ssb_cl::k_cl_rank<<<1, ssb_cl::CL_THREADS, 0, r->stream>>>(flags, n, r->c_pos.p, r->c_count.p);
+  r->launches++;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(count, r->c_count.p, sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  return SSB_OK;
+}
+// cv::kmeans on device-resident samples; the winning attempt's labels stay on the device (*d_labels), centres go to the host
+static int cl_kmeans(ssb_ransac* r, const float* d_data, int N, int dims, int K, int max_count, double eps, int attempts, CvRng& rng,
+                     RBuf<int>& labelbuf, int** d_labels, float* h_centers, double* compactness) {
+  if (N < K || K < 1 || K > ssb_cl::CL_MAXK || dims < 1 || dims > ssb_cl::CL_MAXD) {
+    set_error("kmeans: need 1 <= K <= %d, 1 <= dims <= %d and at least K samples (n = %d, K = %d, dims = %d)", ssb_cl::CL_MAXK,
+              ssb_cl::CL_MAXD, N, K, dims);
+    return SSB_ERR_INVALID;
+  }
+  attempts = std::max(attempts, 1);
+  eps = std::max(eps, 0.0);
+  max_count = std::min(std::max(max_count, 2), 100);
+  if (K == 1) {
+    attempts = 1;
+    max_count = 2;
+  }
+  int rc;
+  if ((rc = labelbuf.ensure((size_t)attempts * N)) || (rc = r->c_init.ensure((size_t)attempts * K * dims)) ||
+      (rc = r->c_centers.ensure((size_t)attempts * K * dims)) || (rc = r->c_compact.ensure(attempts)) || (rc = r->c_lohi.ensure(2 * ssb_cl::CL_MAXD)))
+    return rc;
+  cudaStream_t s = r->stream;
+  ssb_cl::k_cl_minmax<<<1, ssb_cl::CL_THREADS, 0, s>>>(d_data, N, dims, r->c_lohi.p);
+  float lohi[2 * ssb_cl::CL_MAXD];
+  SSB_CUDA_CHECK(cudaMemcpyAsync(lohi, r->c_lohi.p, sizeof(lohi), cudaMemcpyDeviceToHost, s));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+  std::vector<float> init((size_t)attempts * K * dims);
+  const float margin = 1.f / dims;   // generateRandomCenter
+  for (int a = 0; a < attempts; ++a)
+    for (int k = 0; k < K; ++k)
+      for (int j = 0; j < dims; ++j) {
+        const float lo = lohi[j], hi = lohi[ssb_cl::CL_MAXD + j];
+        const float u = rng.uniform01();
+        const float t = u * (1.f + margin * 2.f) - margin;
+        init[((size_t)a * K + k) * dims + j] = t * (hi - lo) + lo;
+      }
+  SSB_CUDA_CHECK(cudaMemcpyAsync(r->c_init.p, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  ssb_cl::KmArgs A;
+  A.data = d_data;
+  A.N = N;
+  A.dims = dims;
+  A.K = K;
+  A.max_count = max_count;
+  A.eps2 = eps * eps;
+  A.init = r->c_init.p;
+  A.labels = labelbuf.p;
+  A.centers = r->c_centers.p;
+  A.compactness = r->c_compact.p;
+  ssb_cl::k_cl_kmeans<<<attempts, ssb_cl::CL_THREADS, 0, s>>>(A);
+  r->launches += 2;
+  std::vector<double> comp(attempts);
+  std::vector<float> cen((size_t)attempts * K * dims);
+  SSB_CUDA_CHECK(cudaMemcpyAsync(comp.data(), r->c_compact.p, attempts * sizeof(double), cudaMemcpyDeviceToHost, s));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(cen.data(), r->c_centers.p, cen.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+  SSB_CUDA_CHECK(cudaGetLastError());
+  int best = 0;
+  double bc = std::numeric_limits<double>::max();
+  for (int a = 0; a < attempts; ++a)
+    if (comp[a] < bc) {   // `compactness < best_compactness`: the first of equal attempts stays
+      bc = comp[a];
+      best = a;
+    }
+  *d_labels = labelbuf.p + (size_t)best * N;
+  std::memcpy(h_centers, cen.data() + (size_t)best * K * dims, (size_t)K * dims * sizeof(float));
+  if (compactness) *compactness = bc;
+  return SSB_OK;
+}
+// pcl::ConvexHull::performReconstruction2D: which two coordinates (the plane normal must not lie within 10 degrees of the
+// dropped axis' complement: projection_angle_thresh_ = cos(0.174532925)) -> 0: (x, y), 1: (y, z), 2: (x, z), -1: none
+static int cl_hull_axes(const float* coef, int* iu, int* iv) {
+  const double nn = std::sqrt((double)coef[0] * coef[0] + (double)coef[1] * coef[1] + (double)coef[2] * coef[2]);
+  const float tx = std::fabs((float)(coef[0] / nn)), ty = std::fabs((float)(coef[1] / nn)), tz = std::fabs((float)(coef[2] / nn));
+  const float thr = (float)std::cos(0.174532925);
+  bool xy = true, yz = true, xz = true;
+  if (tz > thr) xz = yz = false;
+  if (tx > thr) xz = xy = false;
+  if (ty > thr) xy = yz = false;
+  if (xy) { *iu = 0; *iv = 1; return 0; }
+  if (yz) { *iu = 1; *iv = 2; return 1; }
+  if (xz) { *iu = 0; *iv = 2; return 2; }
+  return -1;
+}
+// strictly convex vertices of the candidate points (Andrew's monotone chain, orientation in double, collinear points dropped,
+// of identical points the first stands for all), then PCL's output order: decreasing atan2 about the centroid of the vertices
+static void cl_hull_host(const float4* pts, int m, int iu, int iv, std::vector<int>& hull) {
+  hull.clear();
+  if (m <= 0) return;
+  auto C = [&](int i, int ax) { return ax == 0 ? pts[i].x : ax == 1 ? pts[i].y : pts[i].z; };
+  auto U = [&](int i) { return (double)C(i, iu); };
+  auto V = [&](int i) { return (double)C(i, iv); };
+  std::vector<int> ord(m);
+  for (int i = 0; i < m; ++i) ord[i] = i;
+  std::sort(ord.begin(), ord.end(), [&](int a, int b) {
+    if (U(a) != U(b)) return U(a) < U(b);
+    if (V(a) != V(b)) return V(a) < V(b);
+    return a < b;
+  });
+  std::vector<int> uq;
+  for (int k = 0; k < m; ++k)
+    if (uq.empty() || U(ord[k]) != U(uq.back()) || V(ord[k]) != V(uq.back())) uq.push_back(ord[k]);
+  const int q = (int)uq.size();
+  if (q < 3) {
+    hull = uq;
+  } else {
+    std::vector<int> st(2 * (size_t)q);
+    int k = 0;
+    auto turn = [&](int a, int b, int c) { return (U(b) - U(a)) * (V(c) - V(a)) - (V(b) - V(a)) * (U(c) - U(a)); };
+    for (int i = 0; i < q; ++i) {
+      while (k >= 2 && turn(st[k - 2], st[k - 1], uq[i]) <= 0) --k;
+      st[k++] = uq[i];
+    }
+    for (int i = q - 2, t = k + 1; i >= 0; --i) {
+      while (k >= t && turn(st[k - 2], st[k - 1], uq[i]) <= 0) --k;
+      st[k++] = uq[i];
+    }
+    hull.assign(st.begin(), st.begin() + (k - 1));
+  }
+  std::vector<int> byidx = hull;
+  std::sort(byidx.begin(), byidx.end());
+  double cu = 0, cv = 0;
+  for (int i : byidx) {
+    cu += U(i);
+    cv += V(i);
+  }
+  const float fcu = (float)(cu / (double)byidx.size()), fcv = (float)(cv / (double)byidx.size());
+  std::vector<std::pair<double, int>> ang;
+  for (int i : byidx) {
+    const float du = C(i, iu) - fcu, dv = C(i, iv) - fcv;
+    ang.push_back({std::atan2((double)dv, (double)du) + M_PI, i});
+  }
+  std::stable_sort(ang.begin(), ang.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; });
+  hull.clear();
+  for (auto& a : ang) hull.push_back(a.second);
+}
+// ProjectInliers + ConvexHull of n device points (d_pts) selected by the device mask.  rows3 / src: host outputs.
+static int cl_project_hull(ssb_ransac* r, const float4* d_pts, const unsigned char* d_mask, int n, const float* coef, float* rows3, int* src,
+                           int max_rows, int* n_inliers, int* n_hull) {
+  *n_hull = 0;
+  if (n_inliers) *n_inliers = 0;
+  if (n <= 0) return SSB_OK;
+  cudaStream_t s = r->stream;
+  int nin = 0, rc;
+  if ((rc = cl_rank(r, d_mask, n, &nin))) return rc;
+  if (n_inliers) *n_inliers = nin;
+  int iu, iv;
+  if (nin == 0 || cl_hull_axes(coef, &iu, &iv) < 0) return SSB_OK;
+  if ((rc = r->c_proj.ensure(nin)) || (rc = r->c_src.ensure(nin)) || (rc = r->c_flags.ensure((size_t)std::max(n, nin))) || (rc = r->c_ext.ensure(8)) ||
+      (rc = r->c_cand.ensure(nin)) || (rc = r->c_cidx.ensure(nin)) || (rc = r->c_csrc.ensure(nin)))
+    return rc;
+  // sac_model_plane.hpp projectPoints: mc = (a, b, c, 0).normalized()  [Eigen 4-float squaredNorm: (p0 + p1) + (p2 + p3)]
+  float mc[4] = {coef[0], coef[1], coef[2], 0.f};
+  const float sq = (mc[0] * mc[0] + mc[1] * mc[1]) + (mc[2] * mc[2] + mc[3] * mc[3]);
+  const float nrm = std::sqrt(sq);
+  for (int k = 0; k < 4; ++k) mc[k] = mc[k] / nrm;
+  ssb_cl::k_cl_project<<<(n + 255) / 256, 256, 0, s>>>(d_pts, d_mask, r->c_pos.p, n, mc[0], mc[1], mc[2], coef[3], r->c_proj.p, r->c_src.p);
+  ssb_cl::k_cl_extremes<<<1, ssb_cl::CL_THREADS, 0, s>>>(r->c_proj.p, nin, iu, iv, r->c_ext.p);
+  ssb_cl::k_cl_flag_outside<<<(nin + 255) / 256, 256, 0, s>>>(r->c_proj.p, nin, iu, iv, r->c_ext.p, r->c_flags.p);
+  r->launches += 3;
+  int ncand = 0;
+  if ((rc = cl_rank(r, r->c_flags.p, nin, &ncand))) return rc;
+  if (ncand == 0) return SSB_OK;
+  ssb_cl::k_cl_scatter_cand<<<(nin + 255) / 256, 256, 0, s>>>(r->c_proj.p, r->c_flags.p, r->c_pos.p, nin, r->c_cand.p, r->c_cidx.p);
+  r->launches++;
+  std::vector<float4> cand(ncand);
+  std::vector<int> cidx(ncand), hsrc(nin);
+  SSB_CUDA_CHECK(cudaMemcpyAsync(cand.data(), r->c_cand.p, (size_t)ncand * sizeof(float4), cudaMemcpyDeviceToHost, s));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(cidx.data(), r->c_cidx.p, (size_t)ncand * sizeof(int), cudaMemcpyDeviceToHost, s));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(hsrc.data(), r->c_src.p, (size_t)nin * sizeof(int), cudaMemcpyDeviceToHost, s));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+  SSB_CUDA_CHECK(cudaGetLastError());
+  std::vector<int> hull;
+  cl_hull_host(cand.data(), ncand, iu, iv, hull);
+  *n_hull = (int)hull.size();
+  for (int k = 0; k < (int)hull.size() && k < max_rows; ++k) {
+    const float4 p = cand[hull[k]];
+    rows3[3 * k] = p.x;
+    rows3[3 * k + 1] = p.y;
+    rows3[3 * k + 2] = p.z;
+    if (src) src[k] = hsrc[cidx[hull[k]]];
+  }
+  return SSB_OK;
+}
+}  // namespace ssb
+
+extern "C" {
+
+void ssb_cluster_default_opts(ssb_cluster_opts* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->num_centroids_normals = 4;
+  o->num_centroids_distance = 2;
+  o->kmeans_attempts = 10;
+  o->kmeans_max_count = 10;
+  o->kmeans_epsilon = 0.01;
+  o->min_cluster_points = 500;
+  o->centroid_tolerance = 0.3f;
+  o->ransac_hypotheses = 0;
+  o->ransac_seed = 12345u;
+}
+
+int ssb_kmeans(ssb_ransac* r, const float* data, int n, int dims, int K, int max_count, double epsilon, int attempts,
+               unsigned long long* rng_state, int* labels, float* centers, double* compactness) {
+  if (!r || !data || !rng_state || !labels || !centers || n < 1) {
+    set_error("ssb_kmeans: invalid argument");
+    return SSB_ERR_INVALID;
+  }
+  SSB_CUDA_CHECK(cudaSetDevice(r->device));
+  int rc;
+  if ((rc = r->c_data.ensure((size_t)n * std::max(dims, 1)))) return rc;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(r->c_data.p, data, (size_t)n * dims * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+  CvRng rng{*rng_state ? *rng_state : 0xffffffffULL};
+  int* d_lab = nullptr;
+  if ((rc = cl_kmeans(r, r->c_data.p, n, dims, K, max_count, epsilon, attempts, rng, r->c_labels, &d_lab, centers, compactness))) return rc;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(labels, d_lab, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  *rng_state = rng.state;
+  return SSB_OK;
+}
+
+int ssb_project_hull(ssb_ransac* r, const float* pts4, const unsigned char* mask, int n, const float coef[4], float* rows3, int* src,
+                     int max_rows, int* n_inliers) {
+  if (!r || !pts4 || !mask || !coef || n < 0 || (max_rows > 0 && !rows3)) {
+    set_error("ssb_project_hull: invalid argument");
+    return SSB_ERR_INVALID;
+  }
+  SSB_CUDA_CHECK(cudaSetDevice(r->device));
+  int rc;
+  if ((rc = r->c_pts.ensure((size_t)std::max(n, 1))) || (rc = r->c_maskh.ensure((size_t)std::max(n, 1)))) return rc;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(r->c_pts.p, pts4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, r->stream));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(r->c_maskh.p, mask, (size_t)n, cudaMemcpyHostToDevice, r->stream));
+  int nh = 0;
+  if ((rc = cl_project_hull(r, r->c_pts.p, r->c_maskh.p, n, coef, rows3, src, max_rows, n_inliers, &nh))) return rc;
+  return nh;
+}
+
+int ssb_cluster_planes(ssb_ransac* r, const float* cloud4, const float* normals4, int n, const float T[16], const ssb_cluster_opts* opts_in,
+                       unsigned long long* rng_state, float* rows8, int max_rows, int* n_rows, ssb_plane_cluster* clusters, int max_clusters,
+                       int* n_clusters, int* labels_out, float* centers_out) {
+  if (!r || !cloud4 || !normals4 || !T || !rng_state || !n_rows || !n_clusters || n < 0 || (max_rows > 0 && !rows8) || (max_clusters > 0 && !clusters)) {
+    set_error("ssb_cluster_planes: invalid argument");
+    return SSB_ERR_INVALID;
+  }
+  ssb_cluster_opts o;
+  if (opts_in)
+    o = *opts_in;
+  else
+    ssb_cluster_default_opts(&o);
+  const int Kn = o.num_centroids_normals, Kd = o.num_centroids_distance;
+  *n_rows = 0;
+  *n_clusters = 0;
+  if (labels_out)
+    for (int i = 0; i < n; ++i) labels_out[i] = -1;
+  if (n == 0) return 0;
+  SSB_CUDA_CHECK(cudaSetDevice(r->device));
+  cudaStream_t s = r->stream;
+  int rc;
+  if ((rc = r->c_cloud.ensure(n)) || (rc = r->c_nrm.ensure(n)) || (rc = r->c_flags.ensure(n)) || (rc = r->c_keep.ensure(n)) ||
+      (rc = r->c_data.ensure((size_t)3 * n)) || (rc = r->c_mem.ensure(n)) || (rc = r->c_dist.ensure(n)) || (rc = r->c_pts.ensure((size_t)n + 64)))
+    return rc;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(r->c_cloud.p, cloud4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(r->c_nrm.p, normals4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, s));
+  const int nb256 = (n + 255) / 256;
+  // removeNans :479-502
+  ssb_cl::k_cl_flag_valid<<<nb256, 256, 0, s>>>(r->c_nrm.p, n, r->c_flags.p);
+  r->launches++;
+  int m = 0;
+  if ((rc = cl_rank(r, r->c_flags.p, n, &m))) return rc;
+  if (m <= 10 || m < Kn) return 0;   // :316-320
+  ssb_cl::k_cl_scatter_valid<<<nb256, 256, 0, s>>>(r->c_nrm.p, r->c_flags.p, r->c_pos.p, n, r->c_keep.p, r->c_data.p);
+  r->launches++;
+  CvRng rng{*rng_state ? *rng_state : 0xffffffffULL};
+  int* d_lab = nullptr;
+  std::vector<float> centers((size_t)Kn * 3);
+  if ((rc = cl_kmeans(r, r->c_data.p, m, 3, Kn, o.kmeans_max_count, o.kmeans_epsilon, o.kmeans_attempts, rng, r->c_labels, &d_lab, centers.data(), nullptr)))
+    return rc;
+  if (centers_out) std::memcpy(centers_out, centers.data(), centers.size() * sizeof(float));
+  if (labels_out) {
+    std::vector<int> lab(m), keep(m);
+    SSB_CUDA_CHECK(cudaMemcpyAsync(lab.data(), d_lab, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, s));
+    SSB_CUDA_CHECK(cudaMemcpyAsync(keep.data(), r->c_keep.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, s));
+    SSB_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int k = 0; k < m; ++k) labels_out[keep[k]] = lab[k];
+  }
+  // normals_of_the_horizontal_plane_in_cam = transformation_mat^T (0, 0, 1, 0) :332-346: the third row of the matrix
+  const float hz[3] = {T[8], T[9], T[10]};
+  struct Kept {
+    int c, d, np;
+    size_t off;   // in c_pts
+    float dist;
+  };
+  std::vector<Kept> kept;
+  size_t stage = 0;
+  const int mb256 = (m + 255) / 256;
+  for (int c = 0; c < Kn; ++c) {   // filterCentroids :504-523
+    const float* cc = &centers[3 * (size_t)c];
+    bool ok = true;
+    for (int j = 0; j < 3; ++j)
+      ok = ok && ((double)cc[j] < (double)hz[j] + (double)o.centroid_tolerance) && ((double)cc[j] > (double)hz[j] - (double)o.centroid_tolerance);
+    if (!ok) continue;
+    ssb_cl::k_cl_flag_eq<<<mb256, 256, 0, s>>>(d_lab, m, c, r->c_flags.p);
+    r->launches++;
+    int md = 0;
+    if ((rc = cl_rank(r, r->c_flags.p, m, &md))) return rc;
+    if (md < Kd) continue;   // cv::kmeans would throw (fewer samples than clusters)
+    ssb_cl::k_cl_scatter_members<<<mb256, 256, 0, s>>>(r->c_cloud.p, r->c_keep.p, r->c_flags.p, r->c_pos.p, m, cc[0], cc[1], cc[2], r->c_mem.p, r->c_dist.p);
+    r->launches++;
+    int* d_dlab = nullptr;
+    std::vector<float> dc(Kd);
+    if ((rc = cl_kmeans(r, r->c_dist.p, md, 1, Kd, o.kmeans_max_count, o.kmeans_epsilon, o.kmeans_attempts, rng, r->c_dlabels, &d_dlab, dc.data(), nullptr)))
+      return rc;
+    const int db256 = (md + 255) / 256;
+    for (int d = 0; d < Kd; ++d) {   // :399-425
+      ssb_cl::k_cl_flag_eq<<<db256, 256, 0, s>>>(d_dlab, md, d, r->c_flags.p);
+      r->launches++;
+      int np = 0;
+      if ((rc = cl_rank(r, r->c_flags.p, md, &np))) return rc;
+      if (!(np > o.min_cluster_points)) continue;
+      if ((int)kept.size() >= max_clusters) continue;
+      ssb_cl::k_cl_scatter_points<<<db256, 256, 0, s>>>(r->c_cloud.p, r->c_mem.p, r->c_flags.p, r->c_pos.p, md, r->c_pts.p + stage);
+      r->launches++;
+      kept.push_back({c, d, np, stage, dc[d]});
+      stage += (size_t)np;
+    }
+  }
+  *rng_state = rng.state;
+  const int ncl = (int)kept.size();
+  *n_clusters = ncl;
+  if (ncl == 0) return 1;
+  // compute2DConvexHull :631-647 on every cluster at once: the clusters are the "crops" of the RANSAC kernels
+  {
+    ssb_cloud_layout L;
+    std::memset(&L, 0, sizeof(L));
+    L.width = L.height = 1 << 30;
+    std::vector<ssb_bbox> bx(ncl);
+    for (int b = 0; b < ncl; ++b) bx[b] = {0, 0, kept[b].np, 1};
+    ssb_ransac_default_opts(&r->opts);
+    const int K = o.ransac_hypotheses > 0 ? o.ransac_hypotheses : 512;
+    r->opts.mode = o.ransac_hypotheses > 0 ? 0 : 1;
+    r->nb = ncl;
+    r->K = K;
+    r->uploaded = false;
+    if ((rc = plan(r, &L, bx.data(), ncl))) return rc;
+    const size_t nh = (size_t)ncl * K;
+    if ((rc = r->d_triples.ensure(3 * nh)) || (rc = r->d_valid.ensure(nh)) || (rc = r->d_counts.ensure(nh)) || (rc = r->d_hyp.ensure(nh))) return rc;
+    std::vector<int> tri(3 * nh);
+    for (int b = 0; b < ncl; ++b) {
+      std::mt19937 gen(o.ransac_seed);
+      for (int k = 0; k < 3 * K; ++k) tri[(size_t)3 * K * b + k] = (int)(gen() % (unsigned long long)kept[b].np);
+    }
+    SSB_CUDA_CHECK(cudaMemcpyAsync(r->d_triples.p, tri.data(), tri.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    for (int b = 0; b < ncl; ++b)
+      SSB_CUDA_CHECK(cudaMemcpyAsync(r->d_crop.p + r->boxes[b].pt_off, r->c_pts.p + kept[b].off, (size_t)kept[b].np * sizeof(float4), cudaMemcpyDeviceToDevice, s));
+    if ((rc = run_device(r, true))) return rc;
+    std::vector<ssb_plane_result> res(ncl);
+    SSB_CUDA_CHECK(cudaMemcpyAsync(res.data(), r->d_results.p, ncl * sizeof(ssb_plane_result), cudaMemcpyDeviceToHost, s));
+    SSB_CUDA_CHECK(cudaStreamSynchronize(s));   // `tri` is a local
+    int rows = 0;
+    std::vector<float> h3;
+    for (int b = 0; b < ncl; ++b) {
+      ssb_plane_cluster& C = clusters[b];
+      std::memset(&C, 0, sizeof(C));
+      const float* cc = &centers[3 * (size_t)kept[b].c];
+      for (int j = 0; j < 3; ++j) C.normal[j] = cc[j];
+      C.distance = kept[b].dist;
+      C.normal_label = kept[b].c;
+      C.distance_label = kept[b].d;
+      C.n_points = kept[b].np;
+      std::memcpy(C.coef, res[b].refined, sizeof(C.coef));
+      C.row0 = rows;
+      if (res[b].status != 0 || res[b].best_hyp < 0) continue;
+      // ProjectInliers + ConvexHull :649-662, then one row per hull vertex (getFinalPoseWithNormals :431-477)
+      h3.resize((size_t)3 * kept[b].np);
+      int nin = 0, nhull = 0;
+      if ((rc = cl_project_hull(r, r->d_crop.p + r->boxes[b].pt_off, r->d_mask.p + r->mask_off[b], kept[b].np, res[b].refined, h3.data(), nullptr,
+                                kept[b].np, &nin, &nhull)))
+        return rc;
+      C.n_inliers = nin;
+      for (int k = 0; k < nhull && rows < max_rows; ++k, ++rows) {
+        float* r8 = rows8 + 8 * (size_t)rows;
+        r8[0] = h3[3 * k];
+        r8[1] = h3[3 * k + 1];
+        r8[2] = h3[3 * k + 2];
+        r8[3] = cc[0];
+        r8[4] = cc[1];
+        r8[5] = cc[2];
+        r8[6] = kept[b].dist;
+        r8[7] = 0.f;
+      }
+      C.n_rows = rows - C.row0;
+    }
+    *n_rows = rows;
+  }
+  return 1;
+}
 
 }  // extern "C"

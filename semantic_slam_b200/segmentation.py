@@ -191,3 +191,69 @@ class OrganizedSegmentation(PlaneSegmentation):
         if want_points:
             return reg, nreg, nin, nrm[:total], lab[:total], dist[:total]
         return reg, nreg, nin
+
+
+PLANE_CLUSTER_DTYPE = np.dtype([("normal", "f4", 3), ("distance", "f4"), ("normal_label", "i4"), ("distance_label", "i4"),
+                                ("n_points", "i4"), ("n_inliers", "i4"), ("coef", "f4", 4), ("row0", "i4"), ("n_rows", "i4")])
+
+
+class PlaneClustering(PlaneSegmentation):
+    """The reference's dormant plane-clustering chain on the device (include/ssb.h: ssb_kmeans, ssb_project_hull,
+    ssb_cluster_planes; csrc/ssb_cluster.cuh): ``plane_segmentation::clusterAndSegmentAllPlanes``
+    (plane_segmentation.cpp:261-294) = two cv::kmeans passes (normals, then signed distances, :296-429) and, per cluster,
+    ``compute2DConvexHull`` (:631-664: RANSAC plane, ProjectInliers, ConvexHull) -> one row per hull vertex (:431-477)."""
+
+    def __init__(self, device: int = -1, **kw):
+        super().__init__(device=device)
+        self.copts = _lib.ClusterOpts()
+        self._L.ssb_cluster_default_opts(C.byref(self.copts))
+        for k, v in kw.items():
+            setattr(self.copts, k, v)
+
+    def computeKmeans(self, points, num_centroids, rng_state=0xFFFFFFFF, attempts=10, max_count=10, epsilon=0.01):
+        """plane_segmentation::computeKmeans (:525-535).  Returns (compactness, labels, centroids, rng state after)."""
+        d = np.ascontiguousarray(points, dtype=np.float32)
+        if d.ndim == 1:
+            d = d[:, None]
+        n, dims = d.shape
+        lab = np.zeros(n, dtype=np.int32)
+        cen = np.zeros((num_centroids, dims), dtype=np.float32)
+        st = C.c_ulonglong(rng_state)
+        comp = C.c_double(0.0)
+        check(self._L.ssb_kmeans(self._h, d.ctypes.data, n, dims, num_centroids, max_count, epsilon, attempts, C.byref(st),
+                                 lab.ctypes.data, cen.ctypes.data, C.byref(comp)), "ssb_kmeans")
+        return comp.value, lab, cen, st.value
+
+    def projectAndHull(self, pts4, mask, coef):
+        """ProjectInliers + ConvexHull of compute2DConvexHull (:649-662).  Returns (hull vertices (k, 3) in PCL's output
+        order, their indices in pts4, number of projected inliers)."""
+        p = np.ascontiguousarray(pts4, dtype=np.float32).reshape(-1, 4)
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        cf = np.ascontiguousarray(coef, dtype=np.float32)
+        n = p.shape[0]
+        rows = np.zeros((max(n, 1), 3), dtype=np.float32)
+        src = np.zeros(max(n, 1), dtype=np.int32)
+        nin = C.c_int(0)
+        k = check(self._L.ssb_project_hull(self._h, p.ctypes.data, m.ctypes.data, n, cf.ctypes.data, rows.ctypes.data,
+                                           src.ctypes.data, n, C.byref(nin)), "ssb_project_hull")
+        return rows[:k].copy(), src[:k].copy(), nin.value
+
+    def clusterAndSegmentAllPlanes(self, cloud4, normals4, transformation_mat, rng_state=0xFFFFFFFF, max_rows=65536,
+                                   max_clusters=16):
+        """Returns dict(rows (k, 8) = final_pose_vec, clusters (structured), labels (n,), centers (Kn, 3), rng_state)."""
+        c = np.ascontiguousarray(cloud4, dtype=np.float32).reshape(-1, 4)
+        q = np.ascontiguousarray(normals4, dtype=np.float32).reshape(-1, 4)
+        n = c.shape[0]
+        if q.shape[0] != n:
+            raise ValueError("cloud and normals must have the same number of points")
+        T = np.ascontiguousarray(transformation_mat, dtype=np.float32).reshape(16)
+        rows = np.zeros((max_rows, 8), dtype=np.float32)
+        cl = np.zeros(max_clusters, dtype=PLANE_CLUSTER_DTYPE)
+        lab = np.zeros(max(n, 1), dtype=np.int32)
+        cen = np.zeros((self.copts.num_centroids_normals, 3), dtype=np.float32)
+        st = C.c_ulonglong(rng_state)
+        nr, nc = C.c_int(0), C.c_int(0)
+        check(self._L.ssb_cluster_planes(self._h, c.ctypes.data, q.ctypes.data, n, T.ctypes.data, C.byref(self.copts), C.byref(st),
+                                         rows.ctypes.data, max_rows, C.byref(nr), cl.ctypes.data, max_clusters, C.byref(nc),
+                                         lab.ctypes.data, cen.ctypes.data), "ssb_cluster_planes")
+        return dict(rows=rows[:nr.value].copy(), clusters=cl[:nc.value].copy(), labels=lab[:n], centers=cen, rng_state=st.value)

@@ -433,3 +433,39 @@ def make_frame_stream(n_kf: int = 60, n_lm: int = 12, seed: int = SEED_BASE + 5,
             frame.append((0, ptype, cam.astype(np.float32), np.array([0, 0, 1, 0], dtype=np.float32)))
         dets.append(frame)
     return FrameStream(odom, dets, gt, lm, cam_angle, base.einfo6)
+
+
+# --------------------------------------------------------------------------------------------
+# Organised crop for the dormant plane-clustering chain (row f4): two parallel "horizontal" planes at
+# different distances (same normal cluster, two distance clusters) and a wall behind them
+# --------------------------------------------------------------------------------------------
+def make_cluster_scene(h: int = 200, w: int = 240, seed: int = 5, noise: float = 0.0015, nan_frac: float = 0.001,
+                       d_a: float = 1.0, d_b: float = 1.8, wall_normal=(0.55, 0.45, -0.7), d_wall: float = 2.2):
+    """Returns (cloud (h, w, 4) float32: x y z rgb, transformation_mat (4, 4) float32 whose third row is the normal of the
+    horizontal planes in the camera frame — what plane_segmentation.cpp:332-346 derives from the camera pose)."""
+    rng = np.random.default_rng(SEED_BASE + 40 + seed)
+    fx = 525.0
+    u, v = np.meshgrid(np.arange(w), np.arange(h))
+    dx, dy = (u - (w - 1) / 2) / fx, (v - (h - 1) / 2) / fx
+    nA = np.array([0.1, -0.5, -0.85])
+    nA /= np.linalg.norm(nA)
+    nC = np.asarray(wall_normal, dtype=np.float64)
+    nC = nC / np.linalg.norm(nC)
+
+    def depth(n, d0):
+        return n[2] * d0 / (n[0] * dx + n[1] * dy + n[2])
+    z = np.where(u < w // 2, depth(nA, d_a), depth(nA, d_b))
+    z = np.where(v < h // 4, depth(nC, d_wall), z)
+    z = z + rng.normal(0.0, noise, z.shape) * z * z
+    c = np.zeros((h, w, 4), dtype=np.float32)
+    c[..., 0], c[..., 1], c[..., 2] = dx * z, dy * z, z
+    drop = rng.random((h, w)) < nan_frac
+    c[drop, :3] = np.nan
+    # rotation whose third row is nA
+    a = np.cross(nA, [1.0, 0.0, 0.0])
+    a /= np.linalg.norm(a)
+    b = np.cross(nA, a)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = np.stack([a, b, nA]).astype(np.float32)
+    T[:3, 3] = [0.3, -0.2, 1.1]
+    return c, T

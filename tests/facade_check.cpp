@@ -65,6 +65,32 @@ int main(int argc, char** argv) {
     std::printf("segmentallPointCloudData: %zu planar surface(s), first at z = %.3f (%s)\n", objs.size(), objs[0].pose[2],
                 objs[0].plane_type.c_str());
   }
+  if (run) {
+    // the dormant clustering chain under the reference's names: k-means of two blobs, hull of a noisy square patch
+    plane_segmentation_b200 ps(false);
+    if (!ps.ok()) return 12;
+    std::vector<float> pts;
+    for (int i = 0; i < 400; ++i) {
+      pts.push_back(i % 2 ? 1.0f + 0.001f * (i % 7) : -1.0f - 0.001f * (i % 5));
+      pts.push_back(0.002f * (i % 11));
+      pts.push_back(0.5f);
+    }
+    std::vector<int> labels;
+    std::vector<float> cen;
+    const double comp = ps.computeKmeans(pts, 3, 2, labels, cen);
+    if (comp < 0 || labels.size() != 400 || labels[0] == labels[1] || labels[0] != labels[2]) return 13;
+    std::vector<float> patch;
+    for (int r = 0; r < 40; ++r)
+      for (int c = 0; c < 40; ++c) {
+        patch.push_back(0.01f * c);
+        patch.push_back(0.01f * r);
+        patch.push_back(1.0f + 0.0005f * ((r * 7 + c * 3) % 5));
+        patch.push_back(0.f);
+      }
+    std::vector<float> hull = ps.compute2DConvexHull(patch);
+    if (hull.size() < 12) return 14;
+    std::printf("computeKmeans: compactness %.6f; compute2DConvexHull: %zu hull vertices\n", comp, hull.size() / 3);
+  }
   ps_graph_slam::GraphSLAM gs(false);
   if (!gs.graph) return 2;
   using namespace ssb_host;

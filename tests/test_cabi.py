@@ -33,6 +33,12 @@ def test_struct_layouts_match_python_mirrors():
     import oracle
     assert PLANE_RESULT_DTYPE.itemsize == 72 and oracle.PLANE_RESULT_DTYPE == PLANE_RESULT_DTYPE
     assert C.sizeof(_lib.CloudLayoutC) == 32 and C.sizeof(_lib.RansacOpts) == 48
+    from semantic_slam_b200.segmentation import PLANE_CLUSTER_DTYPE
+    assert PLANE_CLUSTER_DTYPE.itemsize == 56 and oracle.PLANE_CLUSTER_DTYPE == PLANE_CLUSTER_DTYPE
+    co = _lib.ClusterOpts()
+    _lib.lib().ssb_cluster_default_opts(C.byref(co))
+    assert (co.num_centroids_normals, co.num_centroids_distance, co.kmeans_attempts, co.kmeans_max_count) == (4, 2, 10, 10)
+    assert co.kmeans_epsilon == 0.01 and co.min_cluster_points == 500 and co.ransac_seed == 12345
     o = _lib.GraphOpts()
     _lib.lib().ssb_graph_default_opts(C.byref(o))
     assert o.max_pcg_iters == 20000 and o.pcg_tol == 1e-8 and o.device == -1

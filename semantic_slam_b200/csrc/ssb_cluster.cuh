@@ -24,6 +24,7 @@ namespace ssb_cl {
 constexpr int CL_THREADS = 1024;
 constexpr int CL_MAXK = 8;      // clusters per k-means (the reference uses 4 and 2)
 constexpr int CL_MAXD = 4;      // dimensions per sample (3 and 1)
+constexpr int CL_UNR = 8;       // chunks of 32 samples in flight per warp in the ordered centre sums
 
 // exclusive rank of every set flag, in index order; count[0] = number of set flags.  One CTA.
 __global__ void __launch_bounds__(CL_THREADS) k_cl_rank(const unsigned char* __restrict__ flags, int n, int* __restrict__ pos,
@@ -182,26 +183,37 @@ __global__ void __launch_bounds__(CL_THREADS) k_cl_kmeans(KmArgs A) {
       if (w < K) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int cnt = 0;
-        for (int base = 0; base < N; base += 32) {
-          const int i = base + lane;
-          const bool mine = i < N && labels[i] == w;
-          float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-          if (mine) {
-            const float* sp = data + (size_t)i * dims;
-            v0 = sp[0];
-            if (dims > 1) v1 = sp[1];
-            if (dims > 2) v2 = sp[2];
-            if (dims > 3) v3 = sp[3];
+        // CL_UNR chunks of 32 points per round: every load of the round (labels and samples, unconditional and therefore
+        // coalesced) is issued before the first dependent add, so the walk is bound by the adds, not by one L2 round trip
+        // per chunk (profiles/README.md: cv::kmeans of 300 000 samples took 81 ms with one chunk in flight)
+        for (int base = 0; base < N; base += 32 * CL_UNR) {
+          int lab[CL_UNR];
+          float v0[CL_UNR], v1[CL_UNR], v2[CL_UNR], v3[CL_UNR];
+#pragma unroll
+          for (int u = 0; u < CL_UNR; ++u) {
+            const int i = base + 32 * u + lane;
+            lab[u] = i < N ? labels[i] : -1;
+            v0[u] = v1[u] = v2[u] = v3[u] = 0.f;
+            if (i < N) {
+              const float* sp = data + (size_t)i * dims;
+              v0[u] = sp[0];
+              if (dims > 1) v1[u] = sp[1];
+              if (dims > 2) v2[u] = sp[2];
+              if (dims > 3) v3[u] = sp[3];
+            }
           }
-          unsigned m = __ballot_sync(0xffffffffu, mine);
-          cnt += __popc(m);
-          while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, v0, b));
-            if (dims > 1) s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, v1, b));
-            if (dims > 2) s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, v2, b));
-            if (dims > 3) s3 = __fadd_rn(s3, __shfl_sync(0xffffffffu, v3, b));
+#pragma unroll
+          for (int u = 0; u < CL_UNR; ++u) {
+            unsigned m = __ballot_sync(0xffffffffu, lab[u] == w);
+            cnt += __popc(m);
+            while (m) {
+              const int b = __ffs(m) - 1;
+              m &= m - 1;
+              s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, v0[u], b));
+              if (dims > 1) s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, v1[u], b));
+              if (dims > 2) s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, v2[u], b));
+              if (dims > 3) s3 = __fadd_rn(s3, __shfl_sync(0xffffffffu, v3[u], b));
+            }
           }
         }
         if (lane == 0) {

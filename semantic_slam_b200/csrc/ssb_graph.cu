@@ -340,12 +340,21 @@ struct ssb_graph {
   ShardPlan* plan = nullptr;     // outer handle: who owns what, identical on every rank
   std::vector<Pose> snap_poses;  // outer handle: host copy of the estimates at ssb_graph_snapshot
   std::vector<double> snap_lms;
+  // ---- landmark marginals of graphs that fill only part of the chip (marginals_replicated) ----
+  ssb_graph* marg_rep = nullptr;            // k copies of this graph side by side: one PCG launch = k columns
+  int marg_rep_k = 0;
+  unsigned long long structure_serial = 0;  // bumped whenever prepare() rebuilt the tables
+  unsigned long long marg_rep_serial = 0;   // structure_serial the replicated graph was built from
+  bool linpoint_in_bak = false;             // d_pose_bak / d_lm_bak hold the estimates the resident system was linearised at
+  // the replicated (shadow) handle itself: copy j lives on the CTAs [j rep_ctas, (j + 1) rep_ctas) of the PCG grid
+  int rep_ctas = 0, rep_count = 0;
+  int force_C = 0;                          // keyframes per CTA (0: derived from the graph size)
 };
 
 // k_pcg_flow is instantiated for the grids it is launched with: 148 CTAs (one per B200 SM); a sharded graph whose ranks
 // are host threads sharing one GPU ("virtual shards", ssb_graph_attach_local) runs 74 or 37 CTAs per rank
-static void* flow_kernel(int grid, bool mr) {
-  if (!mr) return grid == 148 ? (void*)k_pcg_flow<148, false> : nullptr;
+static void* flow_kernel(int grid, bool mr, bool rep = false) {
+  if (!mr) return grid == 148 ? (rep ? (void*)k_pcg_flow<148, false, true> : (void*)k_pcg_flow<148, false, false>) : nullptr;
   switch (grid) {
     case 148: return (void*)k_pcg_flow<148, true>;
     case 74: return (void*)k_pcg_flow<74, true>;
@@ -461,6 +470,8 @@ ssb_graph* ssb_graph_create(const ssb_graph_opts* opts) {
     void* fk = flow_kernel(g->pcg_grid, shard_handle);
     e = cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcgw_smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fk, PCGF_THREADS, g->pcgw_smem);
+    if (e == cudaSuccess && !shard_handle && flow_kernel(g->pcg_grid, false, true))   // several right-hand sides per launch (K5)
+      e = cudaFuncSetAttribute(flow_kernel(g->pcg_grid, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcgw_smem);
   }
   if (e != cudaSuccess || nb < 1) {
     set_error("k_pcg_flow cannot be made resident (occupancy %d, %zu B smem): %s", nb, g->pcgw_smem, cudaGetErrorString(e));
@@ -476,6 +487,10 @@ void ssb_graph_destroy(ssb_graph* g) {
   if (g->shard) {
     ssb_graph_destroy(g->shard);
     g->shard = nullptr;
+  }
+  if (g->marg_rep) {
+    ssb_graph_destroy(g->marg_rep);
+    g->marg_rep = nullptr;
   }
   delete g->plan;
   g->plan = nullptr;
@@ -946,6 +961,7 @@ static int prepare(ssb_graph* g) {
     const int nblk = g->pcg_grid;
     int Cc = (n_own + nblk - 1) / nblk;
     Cc = std::max(5, ((Cc + 4) / 5) * 5);
+    if (g->force_C > 0) Cc = g->force_C;   // replicated graph: every copy starts on a CTA boundary
     std::vector<int> run_lm, run_group, run_e0, lm_run_rowptr(Nl + 1, 0);
     run_lm.reserve(El / 4 + 16);
     run_group.reserve(El / 4 + 16);
@@ -1394,6 +1410,7 @@ static int prepare(ssb_graph* g) {
     SSB_CUDA_CHECK(cudaStreamSynchronize(s));  // host vectors above go out of scope
     tick("upload sync");
     g->structure_dirty = false;
+    g->structure_serial++;
     g->host_est_dirty = true;
     g->have_system = false;
     g->have_snapshot = false;
@@ -1535,6 +1552,7 @@ static int launch_linearize(ssb_graph* g) {
   }
   SSB_CUDA_CHECK(cudaGetLastError());
   g->have_system = true;
+  g->linpoint_in_bak = false;
   return SSB_OK;
 }
 // separate_coarse: invert the coarse matrix in k_coarse_invert (third stream) instead of inside k_pcg_flow.  Measured
@@ -1619,6 +1637,7 @@ static int launch_solve(ssb_graph* g, double lambda, int apply) {
   if (apply) {
     k_backsub_update<<<(G.Np + 32 * G.Nl + 127) / 128, 128, 0, s>>>(G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
     g->launches++;
+    g->linpoint_in_bak = true;   // the backup taken before the update = the linearisation point of this iteration
   }
   SSB_CUDA_CHECK(cudaGetLastError());
   return SSB_OK;
@@ -1662,7 +1681,8 @@ static int launch_pcg(ssb_graph* g, double lambda) {
       if (g->mr) SSB_TRY(peer_exchange(g, false));   // ... nor start before everybody has cleared
       g->flow_seq = 1;
     }
-    FlowBufs F{g->d_ucell.p, g->d_ucell.p + (size_t)6 * (G.Np + 64), g->d_lines.p, g->d_gj.p, g->flow_seq << 16, g->d_hlpark.p, g->d_trace.p};
+    FlowBufs F{g->d_ucell.p, g->d_ucell.p + (size_t)6 * (G.Np + 64), g->d_lines.p, g->d_gj.p, g->flow_seq << 16, g->d_hlpark.p, g->d_trace.p,
+               g->rep_ctas, g->rep_count};
     int maxit_f = std::min(maxit, 60000);
     FlowPeer FP{};
     if (g->mr) FP = g->mr->FP;
@@ -1676,7 +1696,8 @@ static int launch_pcg(ssb_graph* g, double lambda) {
       // hold back the other rank's launches (false dependency => deadlock)
       SSB_CUDA_CHECK(cudaStreamSynchronize(s));
     } else
-      SSB_CUDA_CHECK(cudaLaunchCooperativeKernel(flow_kernel(g->pcg_grid, g->mr != nullptr), dim3(g->pcg_grid), dim3(PCGF_THREADS), fargs, g->pcgw_smem, s));
+      SSB_CUDA_CHECK(cudaLaunchCooperativeKernel(flow_kernel(g->pcg_grid, g->mr != nullptr, g->rep_count > 1), dim3(g->pcg_grid), dim3(PCGF_THREADS),
+                                                 fargs, g->pcgw_smem, s));
   } else if (g->mr) {
     // the cross-rank barrier slots of the streaming kernel start every launch from zero on every rank
     SSB_CUDA_CHECK(cudaMemsetAsync(g->mr->arena + g->mr->lay[g->mr->rank].slots, 0, ((size_t)2 * g->mr->world * g->pcg_grid + 1) * sizeof(BarSlot), s));
@@ -2728,6 +2749,7 @@ int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len) {
     k_backsub_update<<<(g->G.Np + 32 * g->G.Nl + 127) / 128, 128, 0, g->stream>>>(g->G, lambda, g->d_pose_bak.p, g->d_lm_bak.p);
     k_copy_state<<<(n + 255) / 256, 256, 0, g->stream>>>(g->G.pose, g->d_pose_snap.p, g->G.Np, g->G.lm, g->d_lm_snap.p, g->G.Nl);
     g->launches += 3;
+    g->linpoint_in_bak = true;
   }
   std::vector<double> dp((size_t)6 * g->G.Np + 1), dl((size_t)3 * g->G.Nl + 1);
   SSB_CUDA_CHECK(cudaMemcpyAsync(dp.data(), g->G.x, (size_t)6 * g->G.Np * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
@@ -2765,6 +2787,179 @@ int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len) {
   return g->h_iscalars[0];
 }
 
+// ---- K5 with several right-hand sides per launch ------------------------------------------------------------------
+// One damped solve is latency-bound and costs about the same for 1 000 as for 10 000 keyframes (the data-flow kernel
+// holds up to 80 keyframes per CTA, a small graph fills a fraction of that).  The 3 n columns of the landmark marginals
+// share ONE matrix, so a graph of Np keyframes is laid out k times side by side in a shadow handle (copy j: vertices / edges
+// shifted, keyframes padded with fixed, edge-less ones up to a CTA boundary so that copy j owns the CTAs [j R, (j + 1) R)) and
+// k_pcg_flow<148, false, true> runs one conjugate-gradient recurrence per copy: every column converges as if solved alone,
+// one launch delivers k columns.  (Sharing the CG scalars between the copies does not work: one polynomial then has to
+// serve every right-hand side and the iteration count grows with k — profiles/r02_marg_replicas/.)
+// The shadow is rebuilt when the structure changed and takes its estimates (the linearisation point of the system the
+// last optimize left behind, g2o's computeMarginals semantics) device-to-device.
+struct MargRepPlan {
+  int k, R, C, stride;   // copies, CTAs per copy, keyframes per CTA, keyframes per copy incl. padding
+};
+static MargRepPlan marg_replica_plan(const ssb_graph* g) {
+  MargRepPlan P{1, 0, 0, 0};
+  const char* ev = std::getenv("SSB_MARG_REPLICAS");   // 0 / 1: one column per launch (A/B measurements and tests)
+  const int env = ev ? std::atoi(ev) : -1;
+  const int Np = (int)g->poses.size();
+  if (env == 0 || env == 1 || Np < 1 || g->pcg_grid != 148 || !g->use_flow || !g->allow_fast || g->mr) return P;
+  int k = std::min({SSB_MARG_MAX_REP, PCGF_MAXREP, 148 / ((Np + PCGW_POSES - 1) / PCGW_POSES)});
+  if (env > 1) k = std::min(k, env);
+  if (k < 2) return P;
+  P.k = k;
+  P.R = 148 / k;
+  P.C = std::max(5, (((Np + P.R - 1) / P.R + 4) / 5) * 5);
+  P.stride = P.R * P.C;
+  if (P.C > PCGW_POSES) P.k = 1;
+  return P;
+}
+static int build_marg_replica(ssb_graph* g, const MargRepPlan& P) {
+  const int k = P.k;
+  if (g->marg_rep && g->marg_rep_k == k && g->marg_rep_serial == g->structure_serial) return SSB_OK;
+  if (!g->marg_rep) {
+    ssb_graph_opts o = g->opts;
+    o.device = g->device;
+    g->marg_rep = ssb_graph_create(&o);
+    if (!g->marg_rep) return SSB_ERR_CUDA;
+  }
+  ssb_graph* r = g->marg_rep;
+  const int Np = (int)g->poses.size(), Nl = (int)(g->lms.size() / 4), nV = (int)g->V.size();
+  const int nPP = (int)g->pp.size(), nPL = (int)g->pl.size();
+  const int pad = P.stride - Np, nV1 = nV + pad;
+  r->V.clear();
+  r->E.clear();
+  r->poses.clear();
+  r->lms.clear();
+  r->lm_kind.clear();
+  r->pl_zd.clear();
+  r->pose_vid.clear();
+  r->lm_vid.clear();
+  r->pp.clear();
+  r->pl.clear();
+  r->V.reserve((size_t)k * nV1);
+  r->E.reserve((size_t)k * g->E.size());
+  r->pp.reserve((size_t)k * nPP);
+  r->pl.reserve((size_t)k * nPL);
+  Pose ident;
+  std::memset(&ident, 0, sizeof(ident));
+  ident.q[3] = 1.0;
+  for (int j = 0; j < k; ++j) {
+    for (const HostVertex& v0 : g->V) {
+      HostVertex v = v0;
+      v.idx += j * (v.kind == VK_SE3 ? P.stride : Nl);
+      v.hidx = -1;
+      r->V.push_back(v);
+    }
+    for (int v : g->pose_vid) r->pose_vid.push_back(v + j * nV1);
+    for (int q = 0; q < pad; ++q) {   // fixed keyframes without edges: identity diagonal block, zero right-hand side
+      HostVertex v;
+      v.kind = VK_SE3;
+      v.idx = j * P.stride + Np + q;
+      v.fixed = true;
+      v.hidx = -1;
+      r->pose_vid.push_back((int)r->V.size());
+      r->V.push_back(v);
+    }
+    for (const HostEdgeRef& e0 : g->E) {
+      HostEdgeRef e = e0;
+      e.idx += j * (e.kind == EK_PP ? nPP : nPL);
+      r->E.push_back(e);
+    }
+    r->poses.insert(r->poses.end(), g->poses.begin(), g->poses.end());
+    r->poses.insert(r->poses.end(), (size_t)pad, ident);
+    r->lms.insert(r->lms.end(), g->lms.begin(), g->lms.end());
+    r->lm_kind.insert(r->lm_kind.end(), g->lm_kind.begin(), g->lm_kind.end());
+    r->pl_zd.insert(r->pl_zd.end(), g->pl_zd.begin(), g->pl_zd.end());
+    for (int v : g->lm_vid) r->lm_vid.push_back(v + j * nV1);
+    for (const PPEdge& e0 : g->pp) {
+      PPEdge e = e0;
+      e.i += j * P.stride;
+      e.j += j * P.stride;
+      r->pp.push_back(e);
+    }
+    for (const PLEdge& e0 : g->pl) {
+      PLEdge e = e0;
+      e.p += j * P.stride;
+      e.l += j * Nl;
+      r->pl.push_back(e);
+    }
+  }
+  r->n_plane_vertices = k * g->n_plane_vertices;
+  r->rep_ctas = P.R;
+  r->rep_count = k;
+  r->force_C = P.C;
+  r->structure_dirty = true;
+  r->host_est_dirty = true;
+  r->device_est_newer = false;
+  g->marg_rep_k = k;
+  g->marg_rep_serial = g->structure_serial;
+  return SSB_OK;
+}
+// returns 1 / 0 like ssb_graph_landmark_marginals, or -100 when the replicated graph does not fit the on-chip kernel
+// (the caller then solves one column per launch)
+static int marginals_replicated(ssb_graph* g, const int* vids, int n, double* out9n, const MargRepPlan& P) {
+  const int k = P.k;
+  SSB_TRY(build_marg_replica(g, P));
+  ssb_graph* r = g->marg_rep;
+  SSB_TRY(prepare(r));
+  if (!r->fast_ok || !r->use_flow) return -100;
+  const int Np = g->G.Np, Nl = g->G.Nl;
+  cudaStream_t s = r->stream;
+  SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));
+  // the estimates the resident system of g was linearised at (see linpoint_in_bak), into every copy
+  const bool from_bak = g->have_system && g->linpoint_in_bak;
+  const Pose* src_pose = from_bak ? g->d_pose_bak.p : g->G.pose;
+  const double* src_lm = from_bak ? g->d_lm_bak.p : g->G.lm;
+  for (int j = 0; j < k; ++j) {
+    SSB_CUDA_CHECK(cudaMemcpyAsync(r->G.pose + (size_t)j * P.stride, src_pose, (size_t)Np * sizeof(Pose), cudaMemcpyDeviceToDevice, s));
+    if (Nl) SSB_CUDA_CHECK(cudaMemcpyAsync(r->G.lm + (size_t)4 * j * Nl, src_lm, (size_t)4 * Nl * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  r->have_system = false;
+  const long long l0 = r->launches;
+  SSB_TRY(launch_linearize(r));
+  SSB_TRY(launch_prep(r, 0.0, std::getenv("SSB_MARG_INKERNEL") == nullptr));
+  SSB_TRY(r->d_tmp.ensure((size_t)std::max(128, 9 * n + 8)));
+  double* status = r->d_tmp.p + 9 * (size_t)n;
+  SSB_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(double), s));
+  const size_t ev_keep = r->ev_used;
+  const int ncol = 3 * n;
+  const bool dbg = std::getenv("SSB_MARG_DEBUG") != nullptr;
+  for (int c0 = 0; c0 < ncol; c0 += k) {
+    MargCols mc;
+    for (int j = 0; j < SSB_MARG_MAX_REP; ++j) {
+      const int col = c0 + j;
+      const bool live = j < k && col < ncol;
+      mc.l[j] = live ? g->V[vids[col / 3]].idx : -1;
+      mc.c[j] = live ? col % 3 : 0;
+      mc.o[j] = live ? col / 3 : 0;
+    }
+    k_marg_rhs_rep<<<k, 256, 0, s>>>(r->G, mc, P.stride, Nl);
+    r->ev_used = ev_keep;  // do not grow the timing-event pool
+    SSB_TRY(launch_pcg(r, 0.0));
+    k_marg_out_rep<<<k, 64, 0, s>>>(r->G, mc, Nl, r->d_tmp.p, status);
+    r->launches += 2;
+    if (dbg) {
+      SSB_TRY(read_scalars(r));
+      std::fprintf(stderr, "[ssb marginals] %d copies of %d keyframes (%d CTAs x %d keyframes each), columns %d..: %d PCG iterations, status %d\n", k, Np,
+                   P.R, P.C, c0, r->h_iscalars[0], r->h_iscalars[1]);
+    }
+  }
+  r->ev_used = ev_keep;
+  double st = 0.0;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(out9n, r->d_tmp.p, (size_t)9 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(&st, status, sizeof(double), cudaMemcpyDeviceToHost, s));
+  SSB_TRY(read_scalars(r));
+  g->launches += r->launches - l0;
+  if (st != 0.0 || r->h_iscalars[1] != 0) {
+    set_error("landmark_marginals: PCG breakdown");
+    return 0;
+  }
+  return 1;
+}
+
 int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* out9n) {
   if (!g || (n > 0 && (!vids || !out9n)) || n < 0) return SSB_ERR_INVALID;
   for (int k = 0; k < n; ++k)
@@ -2782,6 +2977,14 @@ int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* o
     return 0;
   }
   SSB_TRY(prepare(g));
+  if (n == 0) return 1;
+  {
+    const MargRepPlan P = marg_replica_plan(g);
+    if (P.k >= 2) {
+      const int rr = marginals_replicated(g, vids, n, out9n, P);
+      if (rr != -100) return rr;
+    }
+  }
   if (!g->have_system) SSB_TRY(launch_linearize(g));  // else: the system built by the last optimize (g2o semantics)
   SSB_TRY(launch_prep(g, 0.0, std::getenv("SSB_MARG_INKERNEL") == nullptr));   // env: A/B switch for measurements
   SSB_TRY(g->d_tmp.ensure((size_t)std::max(128, 9 * n)));

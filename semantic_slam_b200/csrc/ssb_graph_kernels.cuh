@@ -1929,6 +1929,59 @@ __global__ void k_marg_out(DevGraph G, int l, int c, double* out9) {
   }
 }
 
+// K5 on graphs that fill only part of the chip: the graph is laid out gridDim.x times side by side (marginals_replicated in
+// ssb_graph.cu; k_pcg_flow<.., REP> runs one conjugate-gradient recurrence per copy) and every copy carries its OWN
+// right-hand side, so one PCG launch delivers gridDim.x columns of the marginals.  Block j works on copy j:
+// keyframes [j stride_p, (j + 1) stride_p) (the copy's keyframes, then fixed padding up to a CTA boundary), landmarks
+// [j Nl1, (j + 1) Nl1).
+#define SSB_MARG_MAX_REP 16
+struct MargCols {
+  int l[SSB_MARG_MAX_REP];   // landmark (index inside one copy) of the column solved by copy j; < 0: idle copy
+  int c[SSB_MARG_MAX_REP];   // column of that landmark's 3x3 block
+  int o[SSB_MARG_MAX_REP];   // position of the landmark in the caller's list
+};
+__global__ void k_marg_rhs_rep(DevGraph G, MargCols mc, int stride_p, int Nl1) {
+  const int j = blockIdx.x;
+  double* gj = G.g + 6 * (size_t)j * stride_p;
+  for (int k = threadIdx.x; k < 6 * stride_p; k += blockDim.x) gj[k] = 0.0;
+  __syncthreads();
+  if (mc.l[j] < 0) return;
+  const int l = mc.l[j] + j * Nl1, c = mc.c[j];
+  const double* Wu = G.HllInv + 6 * (size_t)l;
+  const double W[9] = {Wu[0], Wu[1], Wu[2], Wu[1], Wu[3], Wu[4], Wu[2], Wu[4], Wu[5]};
+  const double w[3] = {W[c], W[3 + c], W[6 + c]};  // W e_c
+  for (int e = G.lm_rowptr[l] + threadIdx.x; e < G.lm_rowptr[l + 1]; e += blockDim.x) {
+    const double* Hl = G.HplL + 18 * (size_t)e;
+    const int p = G.pl[e].p;
+    for (int k = 0; k < 6; ++k) atomicAdd(G.g + 6 * (size_t)p + k, Hl[k] * w[0] + Hl[6 + k] * w[1] + Hl[12 + k] * w[2]);
+  }
+}
+// status: sticky flag, set when the solve that just finished reported a breakdown (G.iscalars[1])
+__global__ void k_marg_out_rep(DevGraph G, MargCols mc, int Nl1, double* out9n, double* status) {
+  __shared__ double sh[33];
+  const int j = blockIdx.x;
+  if (j == 0 && threadIdx.x == 0 && G.iscalars[1] != 0) status[0] = 1.0;
+  if (mc.l[j] < 0) return;
+  const int l = mc.l[j] + j * Nl1, c = mc.c[j];
+  double a[3] = {0, 0, 0};
+  for (int e = G.lm_rowptr[l] + threadIdx.x; e < G.lm_rowptr[l + 1]; e += blockDim.x) {
+    const double* Hl = G.HplL + 18 * (size_t)e;
+    const double* x = G.x + 6 * (size_t)G.pl[e].p;
+    for (int k = 0; k < 6; ++k) {
+      a[0] += Hl[k] * x[k];
+      a[1] += Hl[6 + k] * x[k];
+      a[2] += Hl[12 + k] * x[k];
+    }
+  }
+  for (int k = 0; k < 3; ++k) a[k] = block_sum(a[k], sh);
+  if (threadIdx.x == 0) {
+    const double* Wu = G.HllInv + 6 * (size_t)l;
+    const double W[9] = {Wu[0], Wu[1], Wu[2], Wu[1], Wu[3], Wu[4], Wu[2], Wu[4], Wu[5]};
+    double* out9 = out9n + 9 * (size_t)mc.o[j];
+    for (int r = 0; r < 3; ++r) out9[3 * r + c] = W[3 * r + c] + W[3 * r] * a[0] + W[3 * r + 1] * a[1] + W[3 * r + 2] * a[2];
+  }
+}
+
 // restore estimates (LM reject / benchmark restore)
 __global__ void k_copy_state(Pose* dst_pose, const Pose* src_pose, int Np, double* dst_lm, const double* src_lm, int Nl) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -36,6 +36,9 @@ struct FlowBufs {
   unsigned tagbase;
   double2* hlpark;  // [gridDim.x * warps][9][32] landmark-role blocks parked in L2 between iterations
   unsigned long long* trace;  // debug (-DSSB_FLOW_TRACE): [gridDim.x][8] globaltimer stamps of one iteration
+  // REP (template parameter of k_pcg_flow): the graph is rep_count copies of one graph side by side, copy j on the CTAs
+  // [j rep_ctas, (j + 1) rep_ctas), each with its own right-hand side (the landmark marginals, ssb_graph.cu)
+  int rep_ctas, rep_count;
 };
 
 // Sharded graphs (template parameter MR of k_pcg_flow): what a CTA writes into the arenas of the other ranks.
@@ -452,7 +455,12 @@ __global__ void __launch_bounds__(CINV_THREADS, SSB_CINV_MINB)
 // MR: the graph is sharded over FP.world ranks (this grid = the CTAs of rank FP.rank); the cells a neighbour needs are
 // also written into its arena, the dot products are folded over the lines of every rank.  The preconditioner stays
 // rank-local (ghost keyframes carry no basis): block-Jacobi on S + exact groups + one coarse level per rank.
-template <int NB, bool MR = false>
+// REP: block-diagonal system diag(S, ..., S) with one right-hand side per block.  The blocks share nothing but the kernel:
+// every block runs ITS OWN conjugate-gradient recurrence (gamma, delta, alpha, beta folded over the lines of its own CTAs
+// only), so each column converges as if it were solved alone.  A converged block freezes (alpha = beta = 0: it keeps
+// publishing the same cells) until every block is done — the tags advance in lock-step for the whole grid.
+constexpr int PCGF_MAXREP = PCGF_THREADS / 32;   // one warp folds the lines of one block
+template <int NB, bool MR = false, bool REP = false>
 __global__ void __launch_bounds__(PCGF_THREADS, 1)
     k_pcg_flow(DevGraph G, CoarseDev Cz, BarSlot* slots, FlowBufs F, FlowTabs T, double lambda, double tol2, int maxit, FlowPeer FP) {
   extern __shared__ __align__(16) double dsm[];
@@ -462,6 +470,9 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   __shared__ double tg6_sh[8], dga_sh[4];        // MR: A_g^-1 P_g'w (my rank's 6 values); c_a - c_rank of my CTA aggregate
   __shared__ double gl8_sh[8];                   // MR: this CTA's (gamma, delta, P_c'w) of the iteration
   __shared__ int ovcnt[PCGF_THREADS / 32];
+  __shared__ double rg_sh[REP ? PCGF_MAXREP : 1], rd_sh[REP ? PCGF_MAXREP : 1], g0_sh[REP ? PCGF_MAXREP : 1];   // REP: per block gamma, delta, gamma_0
+  __shared__ int frz_sh[REP ? PCGF_MAXREP : 1];   // REP: 0 = iterating, 1 = converged (frozen), 2 = breakdown, 3 = bad right-hand side
+  static_assert(!(MR && REP), "replicated right-hand sides are a single-GPU path");
   constexpr int nblk = NB;
   constexpr int nc = 6 * nblk;
   double* part_sh = dsm;                  // [PCGF_THREADS]  (loop: gam = [0..255], del = [256..511])
@@ -848,6 +859,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   SSB_FLOW_PUBLISH_U(tb + 1u)
 
   double gamma = 0.0, gamma0 = 0.0, inv_gamma_old = 1.0, inv_alpha = 1.0;
+  bool rep_bad = false, rep_started = false;   // REP: my block broke down / has taken its first step
   int it = 0;
 #ifdef SSB_PCG_TIMERS
   long long tmr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -993,6 +1005,8 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     {
       double t8[8];
       t8[0] = rcomp * uc;
+      if constexpr (REP)
+        if (rep_bad) t8[0] = __longlong_as_double(0x7ff8000000000000LL);   // tells every CTA that this block broke down
       t8[1] = wv * uc;
 #pragma unroll
       for (int k = 0; k < 6; ++k) t8[2 + k] = Brow[k] * wv;
@@ -1096,8 +1110,8 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     SSB_FTICK(3);
     __syncthreads();
     SSB_FTICK(4);
-    double delta;
-    {
+    double delta = 0.0;
+    if constexpr (!REP) {
       double tg_ = 0.0, td_ = 0.0;
       for (int k = lane; k < nblk; k += 32) {
         tg_ += gam[k];
@@ -1120,6 +1134,35 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
         gamma = g2;
         delta = d2;
       }
+    } else {
+      // warp j folds the lines of block j (the same tree in every CTA => identical bits => identical decisions everywhere)
+      if (warp < F.rep_count) {
+        const int c0 = warp * F.rep_ctas, c1 = c0 + F.rep_ctas;
+        double tg_ = 0.0, td_ = 0.0;
+        for (int k = c0 + lane; k < c1; k += 32) {
+          tg_ += gam[k];
+          td_ += del[k];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          tg_ += __shfl_xor_sync(0xffffffffu, tg_, o);
+          td_ += __shfl_xor_sync(0xffffffffu, td_, o);
+        }
+        if (lane == 0) {
+          rg_sh[warp] = tg_;
+          rd_sh[warp] = td_;
+          if (it == 0) {
+            g0_sh[warp] = tg_;
+            frz_sh[warp] = (tg_ > 0.0) ? 0 : (tg_ == 0.0 ? 1 : 3);   // a zero right-hand side is solved already
+          } else if (frz_sh[warp] == 0) {
+            if (!isfinite(tg_))
+              frz_sh[warp] = 2;
+            else if (!(tg_ > tol2 * g0_sh[warp]))
+              frz_sh[warp] = 1;
+          }
+        }
+      }
+      if (!use_coarse) __syncthreads();   // (with a coarse level its barrier below publishes the fold)
     }
     if (use_coarse) {
       if (warp < 12) {  // two warps per row of A_c^-1
@@ -1135,28 +1178,59 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       __syncthreads();
     }
     SSB_FTICK(5);
-    // ---- scalars (identical in every thread of every CTA) -------------------------------------------
-    if (it == 0) {
-      gamma0 = gamma;
-      if (!(gamma0 > 0.0)) {
-        status = (gamma0 == 0.0) ? 0 : 2;
+    // ---- scalars (identical in every thread of every CTA; REP: of every CTA of a block) ---------------
+    double alpha = 0.0, beta = 0.0;
+    if constexpr (!REP) {
+      if (it == 0) {
+        gamma0 = gamma;
+        if (!(gamma0 > 0.0)) {
+          status = (gamma0 == 0.0) ? 0 : 2;
+          break;
+        }
+      }
+      if (!(gamma > tol2 * gamma0)) break;
+      if (it >= maxit) break;
+      // beta = gamma/gamma_old, alpha = gamma / (delta - beta*gamma/alpha_old) with one division on the
+      // critical path (1/gamma is independent of it)
+      const double inv_gamma = fast_rcp(gamma);
+      beta = (it == 0) ? 0.0 : gamma * inv_gamma_old;
+      const double den = (it == 0) ? delta : delta - beta * gamma * inv_alpha;
+      if (!(den > 0.0) || !isfinite(den)) {
+        status = 1;
         break;
       }
+      alpha = gamma * fast_rcp(den);
+      inv_alpha = den * inv_gamma;
+      inv_gamma_old = inv_gamma;
+    } else {
+      const int myrep = min((int)blockIdx.x / F.rep_ctas, F.rep_count - 1);
+      bool all_done = true;
+      for (int j = 0; j < F.rep_count; ++j) {
+        const int f = frz_sh[j];
+        all_done = all_done && f != 0;
+        if (f == 2) status = 1;
+        if (f == 3) status = 2;
+      }
+      gamma = rg_sh[myrep];
+      delta = rd_sh[myrep];
+      if (it == 0) gamma0 = g0_sh[myrep];
+      if (all_done) break;
+      if (it >= maxit) break;
+      if (frz_sh[myrep] == 0 && !rep_bad) {
+        const double inv_gamma = fast_rcp(gamma);
+        beta = rep_started ? gamma * inv_gamma_old : 0.0;
+        const double den = rep_started ? delta - beta * gamma * inv_alpha : delta;
+        if (!(den > 0.0) || !isfinite(den)) {
+          rep_bad = true;   // freeze; the NaN published with the next line makes every CTA record the breakdown
+          beta = 0.0;
+        } else {
+          alpha = gamma * fast_rcp(den);
+          inv_alpha = den * inv_gamma;
+          inv_gamma_old = inv_gamma;
+          rep_started = true;
+        }
+      }
     }
-    if (!(gamma > tol2 * gamma0)) break;
-    if (it >= maxit) break;
-    // beta = gamma/gamma_old, alpha = gamma / (delta - beta*gamma/alpha_old) with one division on the
-    // critical path (1/gamma is independent of it)
-    const double inv_gamma = fast_rcp(gamma);
-    const double beta = (it == 0) ? 0.0 : gamma * inv_gamma_old;
-    const double den = (it == 0) ? delta : delta - beta * gamma * inv_alpha;
-    if (!(den > 0.0) || !isfinite(den)) {
-      status = 1;
-      break;
-    }
-    const double alpha = gamma * fast_rcp(den);
-    inv_alpha = den * inv_gamma;
-    inv_gamma_old = inv_gamma;
     // ---- D: recurrences and u = M^-1 r ----------------------------------------------------------------
     pc = uc + beta * pc;
     sc = wv + beta * sc;

@@ -144,6 +144,35 @@ def test_landmark_marginals_600_keyframes(precond):
         assert np.abs(Mg - Mo).max() <= 1e-6 * np.abs(Mo).max()
 
 
+@pytest.mark.parametrize("precond", [0, 1, 3])
+def test_landmark_marginals_several_columns_per_launch(precond, monkeypatch):
+    """K5 on a graph that fills a fraction of the chip: k copies of the graph side by side, one conjugate-gradient
+    recurrence per copy inside one launch (k_pcg_flow<148, false, true>, marginals_replicated in ssb_graph.cu).  Checked
+    against the oracle AND against the one-column-per-launch path; a ragged last batch and an idle copy included."""
+    spec = synth.make_graph(600, 60, seed=31)
+    g, o, ids = _pair(spec, preconditioner=precond, pcg_tol=1e-12)
+    assert g.optimize(40) and o.optimize(40)
+    lms = [int(ids[v]) for v in range(spec.vkind.size) if spec.vkind[v] == 1]
+    lms = lms[:7] + lms[-4:]                       # 33 columns: two full batches of 16 and a ragged one
+    Mo = o.computeLandmarkMarginals(lms, relinearize=False)
+    monkeypatch.delenv("SSB_MARG_REPLICAS", raising=False)
+    Mg = g.computeLandmarkMarginals(lms)
+    assert Mg is not None
+    assert np.abs(Mg - Mo).max() <= 1e-6 * np.abs(Mo).max(), np.abs(Mg - Mo).max() / np.abs(Mo).max()
+    Mg2 = g.computeLandmarkMarginals(lms)          # the shadow graph is reused: same bits
+    assert np.array_equal(Mg, Mg2)
+    monkeypatch.setenv("SSB_MARG_REPLICAS", "1")
+    M1 = g.computeLandmarkMarginals(lms)
+    assert np.abs(Mg - M1).max() <= 1e-8 * np.abs(M1).max()
+    monkeypatch.setenv("SSB_MARG_REPLICAS", "5")   # another copy count: other CTA ranges, same answer
+    M5 = g.computeLandmarkMarginals(lms[:4])
+    assert np.abs(M5 - M1[:4]).max() <= 1e-8 * np.abs(M1).max()
+    monkeypatch.delenv("SSB_MARG_REPLICAS", raising=False)
+    # every column is solved as if alone: a single landmark (one batch with 13 idle copies) gives the same block
+    Ms = g.computeLandmarkMarginals(lms[2:3])
+    assert np.abs(Ms[0] - Mg[2]).max() <= 1e-9 * np.abs(Mg[2]).max()
+
+
 def test_landmark_marginals_cfg2_sample():
     """K5 at the headline size (10 000 keyframes: one column per launch) with the bench preconditioner"""
     spec = synth.make_config_graph("cfg2")

@@ -349,6 +349,11 @@ struct ssb_graph {
   // the replicated (shadow) handle itself: copy j lives on the CTAs [j rep_ctas, (j + 1) rep_ctas) of the PCG grid
   int rep_ctas = 0, rep_count = 0;
   int force_C = 0;                          // keyframes per CTA (0: derived from the graph size)
+  int part_edges = 64;                      // a landmark's edges are cut into parts of at most this many (one warp each); 32 = no
+                                            // second batch of u cells per part (the copies multiply the parts a CTA gets)
+  int marg_plan[4] = {1, 0, 0, 0};          // cached MargRepPlan of this structure (copies, CTAs per copy, C, stride)
+  unsigned long long marg_plan_serial = ~0ULL;
+  int marg_plan_env = -2;
 };
 
 // k_pcg_flow is instantiated for the grids it is launched with: 148 CTAs (one per B200 SM); a sharded graph whose ranks
@@ -1143,10 +1148,10 @@ static int prepare(ssb_graph* g) {
       std::vector<int> part_lm, part_e0, part_e1, lm_partbase(Nl + 1, 0);
       for (int l = 0; l < Nl; ++l) {
         lm_partbase[l] = (int)part_lm.size();
-        for (int e = lm_rowptr[l]; e < lm_rowptr[l + 1]; e += 64) {
+        for (int e = lm_rowptr[l]; e < lm_rowptr[l + 1]; e += g->part_edges) {
           part_lm.push_back(l);
           part_e0.push_back(e);
-          part_e1.push_back(std::min(e + 64, lm_rowptr[l + 1]));
+          part_e1.push_back(std::min(e + g->part_edges, lm_rowptr[l + 1]));
         }
       }
       lm_partbase[Nl] = (int)part_lm.size();
@@ -1316,7 +1321,7 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_slots.ensure((size_t)2 * nblk + 1));
     SSB_TRY(g->d_ainv.ensure((size_t)nblk * 6 * ncoarse));
     // u cells, then v cells (one triple per landmark part; parts <= Nl + El / 64)
-    SSB_TRY(g->d_ucell.ensure((size_t)6 * (Np + 64) + (size_t)3 * ((size_t)Nl + El / 64 + 64)));
+    SSB_TRY(g->d_ucell.ensure((size_t)6 * (Np + 64) + (size_t)3 * ((size_t)Nl + El / g->part_edges + 64)));
     SSB_TRY(g->d_lines.ensure((size_t)2 * nblk * 8));
     SSB_TRY(g->d_hlpark.ensure((size_t)nblk * (PCGF_THREADS / 32) * 9 * 32));
     SSB_TRY(g->d_trace.ensure(8 * 256));
@@ -2800,20 +2805,83 @@ int ssb_graph_solve_once(ssb_graph* g, double lambda, double* x, int x_len) {
 struct MargRepPlan {
   int k, R, C, stride;   // copies, CTAs per copy, keyframes per CTA, keyframes per copy incl. padding
 };
-static MargRepPlan marg_replica_plan(const ssb_graph* g) {
-  MargRepPlan P{1, 0, 0, 0};
+static MargRepPlan marg_replica_plan_uncached(const ssb_graph* g, int env);
+static MargRepPlan marg_replica_plan(ssb_graph* g) {
   const char* ev = std::getenv("SSB_MARG_REPLICAS");   // 0 / 1: one column per launch (A/B measurements and tests)
   const int env = ev ? std::atoi(ev) : -1;
-  const int Np = (int)g->poses.size();
+  if (g->marg_plan_serial != g->structure_serial || g->marg_plan_env != env) {
+    const MargRepPlan P = marg_replica_plan_uncached(g, env);
+    g->marg_plan[0] = P.k;
+    g->marg_plan[1] = P.R;
+    g->marg_plan[2] = P.C;
+    g->marg_plan[3] = P.stride;
+    g->marg_plan_serial = g->structure_serial;
+    g->marg_plan_env = env;
+  }
+  return MargRepPlan{g->marg_plan[0], g->marg_plan[1], g->marg_plan[2], g->marg_plan[3]};
+}
+static MargRepPlan marg_replica_plan_uncached(const ssb_graph* g, int env) {
+  MargRepPlan P{1, 0, 0, 0};
+  const int Np = (int)g->poses.size(), Nl = (int)(g->lms.size() / 4);
   if (env == 0 || env == 1 || Np < 1 || g->pcg_grid != 148 || !g->use_flow || !g->allow_fast || g->mr) return P;
-  int k = std::min({SSB_MARG_MAX_REP, PCGF_MAXREP, 148 / ((Np + PCGW_POSES - 1) / PCGW_POSES)});
-  if (env > 1) k = std::min(k, env);
-  if (k < 2) return P;
-  P.k = k;
-  P.R = 148 / k;
-  P.C = std::max(5, (((Np + P.R - 1) / P.R + 4) / 5) * 5);
-  P.stride = P.R * P.C;
-  if (P.C > PCGW_POSES) P.k = 1;
+  int kmax = std::min({SSB_MARG_MAX_REP, PCGF_MAXREP, 148 / ((Np + PCGW_POSES - 1) / PCGW_POSES)});
+  if (env > 1) kmax = std::min(kmax, env);
+  if (kmax < 2) return P;
+  // what a CTA of the on-chip kernel can hold (the limits prepare() checks), evaluated for k copies before building them:
+  // pose-landmark / pose-pose incidences of its keyframe range, and — the landmark parts of ALL copies are dealt
+  // round-robin over the 148 CTAs — the edges beyond the first 32 of its landmark parts
+  std::vector<int> cpl(Np + 1, 0), cpp(Np + 1, 0), deg(std::max(Nl, 1), 0), ovp;
+  for (const PLEdge& e : g->pl) {
+    cpl[e.p + 1]++;
+    deg[e.l]++;
+  }
+  for (const PPEdge& e : g->pp) {
+    cpp[e.i + 1]++;
+    cpp[e.j + 1]++;
+  }
+  for (int i = 0; i < Np; ++i) {
+    cpl[i + 1] += cpl[i];
+    cpp[i + 1] += cpp[i];
+  }
+  for (int l = 0; l < Nl; ++l)
+    for (int e0 = 0; e0 < deg[l]; e0 += 32) ovp.push_back(0);   // the shadow cuts parts of <= 32 edges: no overflow batch
+  std::vector<std::pair<int, int>> byp;   // (keyframe, landmark), keyframe-major: distinct landmarks of a keyframe range
+  byp.reserve(g->pl.size());
+  for (const PLEdge& e : g->pl) byp.push_back({e.p, e.l});
+  std::sort(byp.begin(), byp.end());
+  std::vector<int> stamp(std::max(Nl, 1), -1);
+  for (int k = kmax; k >= 2; --k) {
+    const int R = 148 / k;
+    const int C = std::max(5, (((Np + R - 1) / R + 4) / 5) * 5);
+    if (C > PCGW_POSES || (long long)k * (long long)ovp.size() > 148LL * (PCGF_THREADS / 32)) continue;
+    bool ok = true;
+    for (int b = 0; b < R && ok; ++b) {
+      const int q0 = std::min(Np, b * C), q1 = std::min(Np, q0 + C);
+      int distinct = 0;
+      for (int t = cpl[q0]; t < cpl[q1]; ++t)
+        if (stamp[byp[t].second] != k * 256 + b) {
+          stamp[byp[t].second] = k * 256 + b;
+          ++distinct;
+        }
+      // (distinct pose-pose edges / external neighbours: bounded through the incidences; prepare() has the last word)
+      if (cpl[q1] - cpl[q0] > PCGF_MAXPL || distinct > PCGW_MAXU || cpp[q1] - cpp[q0] > PCGF_MAXPP || (cpp[q1] - cpp[q0]) / 2 + 2 > PCGW_MAXPPE)
+        ok = false;
+    }
+    if (ok) {
+      std::vector<int> ov(148, 0);
+      size_t q = 0;
+      for (int j = 0; j < k; ++j)
+        for (int o : ovp) ov[q++ % 148] += o;
+      for (int b = 0; b < 148; ++b)
+        if (ov[b] > PCGF_MAXOV) ok = false;
+    }
+    if (!ok) continue;
+    P.k = k;
+    P.R = R;
+    P.C = C;
+    P.stride = R * C;
+    return P;
+  }
   return P;
 }
 static int build_marg_replica(ssb_graph* g, const MargRepPlan& P) {
@@ -2891,6 +2959,7 @@ static int build_marg_replica(ssb_graph* g, const MargRepPlan& P) {
   r->rep_ctas = P.R;
   r->rep_count = k;
   r->force_C = P.C;
+  r->part_edges = 32;
   r->structure_dirty = true;
   r->host_est_dirty = true;
   r->device_est_newer = false;
@@ -2905,7 +2974,10 @@ static int marginals_replicated(ssb_graph* g, const int* vids, int n, double* ou
   SSB_TRY(build_marg_replica(g, P));
   ssb_graph* r = g->marg_rep;
   SSB_TRY(prepare(r));
-  if (!r->fast_ok || !r->use_flow) return -100;
+  if (!r->fast_ok || !r->use_flow) {   // a limit the plan did not foresee: one column per launch for this structure
+    g->marg_plan[0] = 1;
+    return -100;
+  }
   const int Np = g->G.Np, Nl = g->G.Nl;
   cudaStream_t s = r->stream;
   SSB_CUDA_CHECK(cudaStreamSynchronize(g->stream));

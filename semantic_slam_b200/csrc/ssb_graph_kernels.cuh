@@ -1007,7 +1007,9 @@ __device__ void coarse_assemble(const DevGraph& G, const CoarseDev& Cz, double l
       double t = 0.0;
       for (int k = 0; k < SLICES; ++k) t += red[36 * k + threadIdx.x];
       const int rr = threadIdx.x / 6, cc = threadIdx.x - 6 * rr;
-      if (p1 <= p0 && rr == cc) t = 1.0;  // empty aggregate: identity keeps A_c invertible
+      // an aggregate without a free keyframe (empty, or only fixed keyframes / promoted landmarks: B = 0) has an exactly zero
+      // block: identity keeps A_c invertible
+      if (rr == cc && t == 0.0) t = 1.0;
       Arow[rr * nc + 6 * myg + cc] = t;
     }
     __syncthreads();

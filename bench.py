@@ -430,9 +430,10 @@ def main():
     # ---------------- K5: GraphSLAM::computeLandmarkMarginals (graph_slam.cpp:221-234) ----------------------------------
     # the reference calls it after every optimise (semantic_graph_slam.cpp:89,181-205).  Timed through the C-ABI with host
     # buffers on (i) a sample of cfg2's landmarks right after the e2e optimise above (10 000 keyframes fill the chip: one
-    # latency-bound PCG solve per column) and (ii) ALL landmarks of a 1 000-keyframe graph (the per-frame loop's size), each
+    # latency-bound PCG solve per column) and (ii) ALL landmarks of a 1 000-keyframe graph (the per-frame loop's size: 11
+    # copies of the graph side by side, one conjugate-gradient recurrence per copy inside one launch = 11 columns), each
     # beside the oracle's time for the same call on the same landmarks (a CSparse-style factorisation of the full system
-    # + 3 solves per landmark).  At the small size the CPU factorisation wins; at cfg2 the GPU does.
+    # + 3 solves per landmark).
     if world == 1 and not args.no_marginals:
         lm_all = ids_cfg2[spec.vkind == 1].astype(np.int32)
         n_s = min(args.marginals_sample, lm_all.size)
@@ -456,7 +457,7 @@ def main():
                             "unit": "landmarks/s", "all_landmarks_extrapolated_s": t_mg * lm_all.size / sample.size,
                             "pcg_solves": int(3 * sample.size)},
             "kf1000_all": {"landmarks": int(lmm.size), "seconds": t_mm, "value": lmm.size / t_mm, "unit": "landmarks/s",
-                           "pcg_solves": int(3 * lmm.size)}}
+                           "columns": int(3 * lmm.size), "columns_per_launch": "up to 16 (one CG recurrence per copy of the graph)"}}
         if rank == 0 and not args.no_cpu_baseline:
             import oracle
             om = oracle.OracleGraphSLAM(threads=1)

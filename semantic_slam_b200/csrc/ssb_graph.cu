@@ -3026,7 +3026,7 @@ static int marginals_replicated(ssb_graph* g, const int* vids, int n, double* ou
   SSB_TRY(read_scalars(r));
   g->launches += r->launches - l0;
   if (st != 0.0 || r->h_iscalars[1] != 0) {
-    set_error("landmark_marginals: PCG breakdown");
+    set_error("landmark_marginals: PCG breakdown (status of the last launch %d: 1 = non-positive curvature, 2 = bad right-hand side)", r->h_iscalars[1]);
     return 0;
   }
   return 1;

@@ -859,7 +859,7 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
   SSB_FLOW_PUBLISH_U(tb + 1u)
 
   double gamma = 0.0, gamma0 = 0.0, inv_gamma_old = 1.0, inv_alpha = 1.0;
-  bool rep_bad = false, rep_started = false;   // REP: my block broke down / has taken its first step
+  bool rep_bad = false, rep_stalled = false, rep_started = false;   // REP: my block broke down / stagnated / has taken its first step
   int it = 0;
 #ifdef SSB_PCG_TIMERS
   long long tmr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1005,8 +1005,10 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
     {
       double t8[8];
       t8[0] = rcomp * uc;
-      if constexpr (REP)
+      if constexpr (REP) {
         if (rep_bad) t8[0] = __longlong_as_double(0x7ff8000000000000LL);   // tells every CTA that this block broke down
+        if (rep_stalled) t8[0] = 0.0;                                      // ... that it has gone as far as doubles allow
+      }
       t8[1] = wv * uc;
 #pragma unroll
       for (int k = 0; k < 6; ++k) t8[2 + k] = Brow[k] * wv;
@@ -1216,12 +1218,18 @@ __global__ void __launch_bounds__(PCGF_THREADS, 1)
       if (it == 0) gamma0 = g0_sh[myrep];
       if (all_done) break;
       if (it >= maxit) break;
-      if (frz_sh[myrep] == 0 && !rep_bad) {
+      if (frz_sh[myrep] == 0 && !rep_bad && !rep_stalled) {
         const double inv_gamma = fast_rcp(gamma);
         beta = rep_started ? gamma * inv_gamma_old : 0.0;
         const double den = rep_started ? delta - beta * gamma * inv_alpha : delta;
         if (!(den > 0.0) || !isfinite(den)) {
-          rep_bad = true;   // freeze; the NaN published with the next line makes every CTA record the breakdown
+          // freeze.  Once the residual is down by 1e-7 in the M^-1 norm a non-positive curvature is rounding noise at the
+          // attainable accuracy (tolerances near 1e-12 on a lambda = 0 system): the block counts as converged (it publishes
+          // gamma = 0).  Earlier it is a breakdown: the NaN published with the next line makes every CTA record it.
+          if (isfinite(den) && gamma <= 1e-14 * gamma0)
+            rep_stalled = true;
+          else
+            rep_bad = true;
           beta = 0.0;
         } else {
           alpha = gamma * fast_rcp(den);

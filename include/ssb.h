@@ -134,7 +134,10 @@ int ssb_graph_get_history(ssb_graph* g, double* out6n, int cap);
 
 /* GraphSLAM::computeLandmarkMarginals  graph_slam.cpp:221-234 <- getAndSetLandmarkCov
  * semantic_graph_slam.cpp:181-205: for each listed XYZ vertex the 3x3 block (H^-1)[v,v] of the last
- * built (undamped) system.  out9n: n row-major 3x3 blocks.  Returns 1 on success, 0 if unavailable. */
+ * built (undamped) system.  out9n: n row-major 3x3 blocks.  Returns 1 on success, 0 if unavailable.
+ * One Schur-complement PCG solve per column; graphs that fill a fraction of the chip are laid out up to 16 times side by
+ * side and solved 16 columns per launch (one CG recurrence per copy).  On a sharded graph every rank computes the blocks
+ * on an unsharded copy of the graph on its own GPU from the gathered final estimates (identical bits on every rank). */
 int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* out9n);
 
 /* GraphSLAM::save  graph_slam.cpp:236-239 (g2o text format: VERTEX_SE3:QUAT, VERTEX_TRACKXYZ,

@@ -9,7 +9,7 @@ from semantic_slam_b200 import GraphSLAM, synth
 
 
 def run_sharded(spec, world, iters, virtual=True, preconditioner=3, pcg_tol=1e-8, key="g", timeout=300, resident_repeat=0,
-                force_generic=False):
+                force_generic=False, marginals=None):
     cta = {1: 0, 2: 74, 4: 37}[world] if virtual else 0
     graphs = [GraphSLAM(device=0 if virtual else r, preconditioner=preconditioner, pcg_tol=pcg_tol, force_generic=force_generic)
               for r in range(world)]
@@ -24,6 +24,8 @@ def run_sharded(spec, world, iters, virtual=True, preconditioner=3, pcg_tol=1e-8
             g.optimize(iters)
             P, X = g.get_all(spec.n_poses, spec.n_landmarks)
             res = {"P": P, "X": X, "history": g.history.copy(), "stats": dict(g.stats)}
+            if marginals is not None:
+                res["marginals"] = g.computeLandmarkMarginals(marginals)
             if resident_repeat:
                 g.prepare()
                 g.snapshot()

@@ -354,6 +354,10 @@ struct ssb_graph {
   int marg_plan[4] = {1, 0, 0, 0};          // cached MargRepPlan of this structure (copies, CTAs per copy, C, stride)
   unsigned long long marg_plan_serial = ~0ULL;
   int marg_plan_env = -2;
+  // sharded graphs: the marginals are computed on an unsharded copy of the graph on this rank's GPU (marginals_sharded)
+  ssb_graph* marg_full = nullptr;
+  unsigned long long marg_full_rev = ~0ULL;
+  unsigned long long host_rev = 0;          // bumped by every call that changes the structure of the host graph
 };
 
 // k_pcg_flow is instantiated for the grids it is launched with: 148 CTAs (one per B200 SM); a sharded graph whose ranks
@@ -497,6 +501,10 @@ void ssb_graph_destroy(ssb_graph* g) {
     ssb_graph_destroy(g->marg_rep);
     g->marg_rep = nullptr;
   }
+  if (g->marg_full) {
+    ssb_graph_destroy(g->marg_full);
+    g->marg_full = nullptr;
+  }
   delete g->plan;
   g->plan = nullptr;
   if (g->mr) {
@@ -549,6 +557,7 @@ int ssb_graph_add_se3_node(ssb_graph* g, const double T34[12]) {
   g->pose_vid.push_back((int)g->V.size());
   g->V.push_back(v);
   g->structure_dirty = true;
+  g->host_rev++;
   return (int)g->V.size() - 1;
 }
 
@@ -568,6 +577,7 @@ int ssb_graph_add_point_xyz_node(ssb_graph* g, const double xyz[3]) {
   g->lm_vid.push_back((int)g->V.size());
   g->V.push_back(v);
   g->structure_dirty = true;
+  g->host_rev++;
   return (int)g->V.size() - 1;
 }
 
@@ -590,6 +600,7 @@ int ssb_graph_add_se3_edge(ssb_graph* g, int v1, int v2, const double Z34[12], c
   g->pp.push_back(e);
   g->E.push_back({EK_PP, (int)g->pp.size() - 1});
   g->structure_dirty = true;
+  g->host_rev++;
   return (int)g->E.size() - 1;
 }
 
@@ -612,6 +623,7 @@ int ssb_graph_add_se3_point_xyz_edge(ssb_graph* g, int v_se3, int v_xyz, const d
   g->pl_zd.push_back(0.0);
   g->E.push_back({EK_PL, (int)g->pl.size() - 1});
   g->structure_dirty = true;
+  g->host_rev++;
   return (int)g->E.size() - 1;
 }
 
@@ -628,6 +640,7 @@ int ssb_graph_add_point_xyz_point_xyz_edge(ssb_graph* g, int v1, int v2, const d
   g->ll.push_back(e);
   g->E.push_back({EK_LL, (int)g->ll.size() - 1});
   g->structure_dirty = true;
+  g->host_rev++;
   return (int)g->E.size() - 1;
 }
 
@@ -655,6 +668,7 @@ int ssb_graph_add_plane_node(ssb_graph* g, const double coeffs[4]) {
   g->lm_vid.push_back((int)g->V.size());
   g->V.push_back(v);
   g->structure_dirty = true;
+  g->host_rev++;
   return (int)g->V.size() - 1;
 }
 
@@ -684,6 +698,7 @@ int ssb_graph_add_se3_plane_edge(ssb_graph* g, int v_se3, int v_plane, const dou
   g->pl_zd.push_back(c[3]);
   g->E.push_back({EK_PL, (int)g->pl.size() - 1});
   g->structure_dirty = true;
+  g->host_rev++;
   return (int)g->E.size() - 1;
 }
 
@@ -2631,6 +2646,7 @@ int ssb_graph_set_fixed(ssb_graph* g, int vid, int fixed) {
   if (!g || vid < 0 || vid >= (int)g->V.size()) return SSB_ERR_INVALID;
   g->V[vid].fixed = fixed != 0;
   g->structure_dirty = true;
+  g->host_rev++;
   return SSB_OK;
 }
 int ssb_graph_hessian_index(ssb_graph* g, int vid) {
@@ -2667,6 +2683,7 @@ int ssb_graph_invalidate(ssb_graph* g) {
   if (!g) return SSB_ERR_INVALID;
   SSB_TRY(sync_estimates_to_host(g));
   g->structure_dirty = true;
+  g->host_rev++;
   return SSB_OK;
 }
 
@@ -3032,6 +3049,41 @@ static int marginals_replicated(ssb_graph* g, const int* vids, int n, double* ou
   return 1;
 }
 
+// Sharded graphs: every rank holds the full host graph and, after an optimize, the final estimates of ALL vertices (the
+// gather at the end of optimize_sharded), so the marginals are computed per rank on an UNSHARDED copy of the graph on its
+// own GPU — no exchange, every rank gets identical bits.  The copy is linearised at the final estimates (g2o's
+// computeMarginals uses the system of the last iteration: identical whenever the LM terminated on rejected trials, one
+// accepted step behind otherwise).  Capacity: the graph must fit one GPU (it does up to the streaming kernel's limits).
+static int marginals_sharded(ssb_graph* g, const int* vids, int n, double* out9n) {
+  if (!g->marg_full) {
+    ssb_graph_opts o = g->opts;
+    o.device = g->device;
+    o.reserved[2] = 0;
+    g->marg_full = ssb_graph_create(&o);
+    if (!g->marg_full) return SSB_ERR_CUDA;
+  }
+  ssb_graph* f = g->marg_full;
+  if (g->marg_full_rev != g->host_rev) {
+    f->V = g->V;
+    f->E = g->E;
+    f->lm_kind = g->lm_kind;
+    f->pl_zd = g->pl_zd;
+    f->n_plane_vertices = g->n_plane_vertices;
+    f->pose_vid = g->pose_vid;
+    f->lm_vid = g->lm_vid;
+    f->pp = g->pp;
+    f->pl = g->pl;
+    f->ll = g->ll;
+    f->structure_dirty = true;
+    g->marg_full_rev = g->host_rev;
+  }
+  f->poses = g->poses;
+  f->lms = g->lms;
+  f->host_est_dirty = true;
+  f->device_est_newer = false;
+  return ssb_graph_landmark_marginals(f, vids, n, out9n);
+}
+
 int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* out9n) {
   if (!g || (n > 0 && (!vids || !out9n)) || n < 0) return SSB_ERR_INVALID;
   for (int k = 0; k < n; ++k)
@@ -3044,10 +3096,7 @@ int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* o
     set_error("landmark_marginals: not available on a graph with landmark-landmark edges");
     return 0;
   }
-  if (is_sharded(g)) {
-    set_error("landmark_marginals: not available on a sharded graph");
-    return 0;
-  }
+  if (is_sharded(g)) return marginals_sharded(g, vids, n, out9n);
   SSB_TRY(prepare(g));
   if (n == 0) return 1;
   {
@@ -3235,6 +3284,7 @@ int ssb_graph_load_g2o(ssb_graph* g, const char* path) {
   for (int id : fixes)
     if (id >= 0 && id < (int)g->V.size()) g->V[id].fixed = true;
   g->structure_dirty = true;
+  g->host_rev++;
   return SSB_OK;
 }
 
@@ -3254,6 +3304,7 @@ int ssb_graph_attach_comm(ssb_graph* g, int rank, int world, const unsigned char
   if (!g || world < 1 || world > SSB_MAX_WORLD || rank < 0 || rank >= world) return SSB_ERR_INVALID;
   g->local_group = 0;
   g->structure_dirty = true;
+  g->host_rev++;
   NcclApi& N = nccl_api();
   if (g->comm && N.ok) {
     N.CommDestroy(g->comm);
@@ -3291,6 +3342,7 @@ int ssb_graph_attach_local(ssb_graph* g, int rank, int world, const char* group_
   g->local_key = group_key;
   g->opts.reserved[2] = cta_per_rank > 0 ? cta_per_rank : 0;
   g->structure_dirty = true;
+  g->host_rev++;
   return SSB_OK;
 }
 // own keyframe range [out[0], out[1]) of `rank` and, with a graph, its local sizes: out[2] = keyframes incl. ghosts,

@@ -72,6 +72,22 @@ def test_virtual_shards_cfg2_vs_oracle_fixture(world):
     assert_parity(res[0]["P"], res[0]["X"], gold["poses"], gold["landmarks"], what="sharded vs oracle fixture:")
 
 
+def test_virtual_shards_landmark_marginals():
+    """computeLandmarkMarginals on a sharded graph: every rank computes them on an unsharded copy of the graph on its own GPU
+    from the gathered final estimates — identical bits on every rank, the oracle's values (re-linearised at the end state)"""
+    from shard_check import run_sharded
+    spec = synth.make_config_graph("cfg1")
+    o = oracle.OracleGraphSLAM()
+    ids = synth.load_graph(o, spec)
+    o.optimize(40)
+    lms = [int(ids[v]) for v in range(spec.vkind.size) if spec.vkind[v] == 1][:6]
+    Mo = o.computeLandmarkMarginals(lms, relinearize=True)
+    res = run_sharded(spec, 2, 40, virtual=True, preconditioner=3, pcg_tol=1e-10, key="t4", marginals=lms)
+    assert res[0]["marginals"] is not None
+    assert np.array_equal(res[0]["marginals"], res[1]["marginals"])
+    assert np.abs(res[0]["marginals"] - Mo).max() <= 1e-6 * np.abs(Mo).max()
+
+
 def test_virtual_shards_growth_and_restore():
     """structure changes re-plan the shards; snapshot / restore keep every rank consistent"""
     from shard_check import run_sharded

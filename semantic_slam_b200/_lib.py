@@ -6,7 +6,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libssb.so")
+_SO = os.environ.get("SSB_LIB") or os.path.join(_HERE, "libssb.so")   # SSB_LIB: an A/B build of the library (experiments)
 _LIB = None
 
 dp = C.POINTER(C.c_double)

@@ -1147,7 +1147,10 @@ __device__ bool coarse_prologue(const DevGraph& G, const CoarseDev& Cz, BarSlot*
 //              registers, HplP / Hoff rows in shared memory for the whole solve; single-reduction CG, tagged
 //              cells instead of grid barriers.
 // ---------------------------------------------------------------------------------------------
-constexpr int PCG_THREADS = 1024;
+#ifndef SSB_PCG_THREADS
+#define SSB_PCG_THREADS 1024
+#endif
+constexpr int PCG_THREADS = SSB_PCG_THREADS;   // threads per CTA of the streaming k_pcg (A/B: -DSSB_PCG_THREADS=768)
 constexpr int PCGF_THREADS = 512;
 constexpr int PCGF_MAXPL = 448;   // pose-landmark entries cached per CTA (fast path)
 constexpr int PCGF_MAXPP = 160;   // pose-pose incidences cached per CTA (fast path)

@@ -1246,6 +1246,17 @@ __device__ __forceinline__ double grid_bar_sum_mr(const StreamPeer& SP, unsigned
 // MR: this grid = the CTAs of rank SP.rank of a sharded graph.  The vectors a neighbour reads (z of boundary keyframes, v
 // of shared landmarks, finally x) are also written into its arena before the barrier that publishes them; the three
 // barriers of an iteration span all ranks.  The preconditioner is rank-local (ghost keyframes carry no basis).
+// The streaming sweeps are chains of dependent gathers with ~640 B in flight per warp.  Requesting the operands of the NEXT
+// pass of a warp into L2 one pass ahead (prefetch.global.L2; -DSSB_PCG_PREFETCH=1) was measured on cfg4: 170.1 ms against
+// 163.5 ms without (1 037 PCG iterations) — the static operands are not what the sweeps wait for.  Off by default.
+#ifndef SSB_PCG_PREFETCH
+#define SSB_PCG_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if SSB_PCG_PREFETCH
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 template <bool MR>
 __global__ void __launch_bounds__(PCG_THREADS, 1)
     k_pcg(DevGraph G, CoarseDev Cz, BarSlot* slots, double lambda, double tol2, int maxit, StreamPeer SP) {
@@ -1361,6 +1372,8 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     for (int l = gw; l < (MR ? SP.n_own_lm : G.Nl); l += total_warps) {   // a shard's owned landmarks come first
       double a0 = 0.0, a1 = 0.0, a2 = 0.0;
       const int e1 = G.lm_rowptr[l + 1];
+      const int ln = l + total_warps;
+      const int en = (SSB_PCG_PREFETCH && ln < (MR ? SP.n_own_lm : G.Nl)) ? G.lm_rowptr[ln] : -1;   // consumed after the sweep below
       for (int e = G.lm_rowptr[l] + lane; e < e1; e += 32) {
         const int pi = G.pl[e].p;
         const double* Hl = G.HplL + 18 * (size_t)e;
@@ -1373,6 +1386,11 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
           a1 += Hl[6 + c] * pc;
           a2 += Hl[12 + c] * pc;
         }
+      }
+      if (en >= 0 && en + lane < G.El) {   // next landmark of this warp: one edge per lane (block 144 B, record 80 B)
+        prefetch_l2(G.HplL + 18 * (size_t)(en + lane));
+        prefetch_l2(G.HplL + 18 * (size_t)(en + lane) + 16);
+        prefetch_l2(G.pl + (en + lane));
       }
       a0 = warp_sum(a0);
       a1 = warp_sum(a1);
@@ -1401,6 +1419,14 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     for (int pbase = p0 + warp * 5; pbase < p1; pbase += warps_per_block * 5) {
       const int i = pbase + slot;
       const bool act = lane_active && i < p1;
+      const int inx = i + warps_per_block * 5;   // my keyframe of the next pass
+      const bool pfn = SSB_PCG_PREFETCH && lane_active && inx < p1;
+      int qn = 0;
+      if (pfn) {
+        prefetch_l2(G.Hpp + 36 * (size_t)inx + 6 * comp);
+        if (use_coarse) prefetch_l2(Cz.Bmat + 36 * (size_t)inx + 6 * comp);
+        qn = G.pose_pl_rowptr[inx];   // consumed at the end of this pass
+      }
       double pc = 0.0;
       if (act) {
         pc = __ldcg(G.z + 6 * (size_t)i + comp) + beta * __ldcg(pold + 6 * (size_t)i + comp);
@@ -1470,6 +1496,11 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
           for (int k = 0; k < 6; ++k) l6[k] += B[k] * qv;
         }
       }
+      if (pfn) {   // the pose-landmark blocks of the next keyframe (6 lanes x 128 B) and, for odometry chains, its two Hoff blocks
+        prefetch_l2(G.HplP + 18 * (size_t)qn + 16 * comp);
+        prefetch_l2(G.Hoff + 36 * (size_t)min(inx, max(G.Epp - 1, 0)) + 6 * comp);
+        prefetch_l2(G.Hoff + 36 * (size_t)max(min(inx, G.Epp) - 1, 0) + 6 * comp);
+      }
     }
     if constexpr (MR)   // p of the ghost keyframes (read by phase 1 / 2 of the next iteration through pold)
       for (int k = 6 * G.Np_own + blockIdx.x * blockDim.x + threadIdx.x; k < 6 * G.Np; k += gridDim.x * blockDim.x)
@@ -1498,6 +1529,12 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     for (int pbase = p0 + warp * 5; pbase < p1; pbase += warps_per_block * 5) {
       const int i = pbase + slot;
       const bool act = lane_active && i < p1;
+      if (SSB_PCG_PREFETCH && lane_active && i + warps_per_block * 5 < p1) {
+        const size_t on = 36 * (size_t)(i + warps_per_block * 5) + 6 * comp;
+        prefetch_l2(G.Dinv + on);
+        if (use_sub) prefetch_l2(Cz.B1mat + on);
+        if (use_coarse) prefetch_l2(Cz.Bmat + on);
+      }
       double rcomp = 0.0;
       if (act) {
         const size_t o = 6 * (size_t)i + comp;

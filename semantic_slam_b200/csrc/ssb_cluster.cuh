@@ -8,8 +8,8 @@
 // cv::kmeans is a chain of order-dependent single-precision sums (centre += sample in point order), so it is evaluated with
 // the SAME arithmetic in an order that respects the dependencies — labels and centres are bit-identical to OpenCV's:
 //   attempts          : independent once their random centres are drawn (the only use of cv::RNG) -> one CTA per attempt
-//   centre sums       : float sums in point order -> one warp per cluster: coalesced loads, members added one by one
-//                       (ballot + shuffle), the K chains run side by side
+//   centre sums       : float sums in point order -> the CTA stages tiles of samples into shared memory, one warp per
+//                       cluster adds its members one by one (ballot, four members in flight), the K chains side by side
 //   assignment        : independent per point (float distances, first minimum wins)
 //   empty clusters    : block-wide lexicographic arg-max (distance, index) = OpenCV's "last farthest point"
 // Selections (valid normals, members of a cluster, RANSAC inliers, hull candidates) are order-preserving compactions:
@@ -24,7 +24,8 @@ namespace ssb_cl {
 constexpr int CL_THREADS = 1024;
 constexpr int CL_MAXK = 8;      // clusters per k-means (the reference uses 4 and 2)
 constexpr int CL_MAXD = 4;      // dimensions per sample (3 and 1)
-constexpr int CL_UNR = 8;       // chunks of 32 samples in flight per warp in the ordered centre sums
+constexpr int CL_TILE = 4096;    // samples staged into shared memory per round of the ordered centre sums
+constexpr size_t CL_KMEANS_SMEM = (size_t)CL_TILE * (CL_MAXD + 1) * sizeof(float);   // dynamic shared memory of k_cl_kmeans
 
 // exclusive rank of every set flag, in index order; count[0] = number of set flags.  One CTA.
 __global__ void __launch_bounds__(CL_THREADS) k_cl_rank(const unsigned char* __restrict__ flags, int n, int* __restrict__ pos,
@@ -165,6 +166,8 @@ __global__ void __launch_bounds__(CL_THREADS) k_cl_kmeans(KmArgs A) {
   __shared__ int red_i[32];
   __shared__ double shift_s;
   __shared__ double sh[33];
+  extern __shared__ __align__(16) float tile_v[];        // [CL_TILE][dims] samples of the current tile ...
+  int* tile_l = reinterpret_cast<int*>(tile_v + (size_t)CL_TILE * CL_MAXD);   // ... and their labels
   const int N = A.N, dims = A.dims, K = A.K;
   const float* data = A.data;
   int* labels = A.labels + (size_t)blockIdx.x * N;
@@ -179,50 +182,58 @@ __global__ void __launch_bounds__(CL_THREADS) k_cl_kmeans(KmArgs A) {
       if (threadIdx.x < K * dims) cen[threadIdx.x] = A.init[(size_t)blockIdx.x * K * dims + threadIdx.x];
       __syncthreads();
     } else {
-      // centre sums in point order: warp k walks the points, every member is added to the running float sums in turn
-      if (w < K) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int cnt = 0;
-        // CL_UNR chunks of 32 points per round: every load of the round (labels and samples, unconditional and therefore
-        // coalesced) is issued before the first dependent add, so the walk is bound by the adds, not by one L2 round trip
-        // per chunk (profiles/README.md: cv::kmeans of 300 000 samples took 81 ms with one chunk in flight)
-        for (int base = 0; base < N; base += 32 * CL_UNR) {
-          int lab[CL_UNR];
-          float v0[CL_UNR], v1[CL_UNR], v2[CL_UNR], v3[CL_UNR];
-#pragma unroll
-          for (int u = 0; u < CL_UNR; ++u) {
-            const int i = base + 32 * u + lane;
-            lab[u] = i < N ? labels[i] : -1;
-            v0[u] = v1[u] = v2[u] = v3[u] = 0.f;
-            if (i < N) {
-              const float* sp = data + (size_t)i * dims;
-              v0[u] = sp[0];
-              if (dims > 1) v1[u] = sp[1];
-              if (dims > 2) v2[u] = sp[2];
-              if (dims > 3) v3[u] = sp[3];
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < CL_UNR; ++u) {
-            unsigned m = __ballot_sync(0xffffffffu, lab[u] == w);
+      // centre sums in point order.  The whole CTA stages a tile of samples and labels into shared memory (coalesced, all
+      // 32 warps: the global-memory latency is paid once per tile, not once per 32 samples), then warp k walks the tile and
+      // adds the members of cluster k to its running float sums one by one, four members in flight (their values are
+      // fetched from shared memory before the dependent adds).  Every lane of the warp carries the same sums.
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int cnt = 0;
+      for (int t0 = 0; t0 < N; t0 += CL_TILE) {
+        const int nt = min(CL_TILE, N - t0);
+        for (int j = threadIdx.x; j < nt * dims; j += CL_THREADS) tile_v[j] = data[(size_t)t0 * dims + j];
+        for (int j = threadIdx.x; j < nt; j += CL_THREADS) tile_l[j] = labels[t0 + j];
+        __syncthreads();
+        if (w < K) {
+          for (int base = 0; base < nt; base += 32) {
+            const int i = base + lane;
+            unsigned m = __ballot_sync(0xffffffffu, i < nt && tile_l[i] == w);
             cnt += __popc(m);
             while (m) {
-              const int b = __ffs(m) - 1;
-              m &= m - 1;
-              s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, v0[u], b));
-              if (dims > 1) s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, v1[u], b));
-              if (dims > 2) s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, v2[u], b));
-              if (dims > 3) s3 = __fadd_rn(s3, __shfl_sync(0xffffffffu, v3[u], b));
+              int nb = 0;
+              float v[4][4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.f;
+                if (m) {
+                  const int bq = __ffs(m) - 1;
+                  m &= m - 1;
+                  nb = q + 1;
+                  const float* sp = tile_v + (base + bq) * dims;
+                  v[q][0] = sp[0];
+                  if (dims > 1) v[q][1] = sp[1];
+                  if (dims > 2) v[q][2] = sp[2];
+                  if (dims > 3) v[q][3] = sp[3];
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q < nb) {   // (warp-uniform; an absent member adds nothing, not even a signed zero)
+                  s0 = __fadd_rn(s0, v[q][0]);
+                  if (dims > 1) s1 = __fadd_rn(s1, v[q][1]);
+                  if (dims > 2) s2 = __fadd_rn(s2, v[q][2]);
+                  if (dims > 3) s3 = __fadd_rn(s3, v[q][3]);
+                }
             }
           }
         }
-        if (lane == 0) {
-          cen[w * dims] = s0;
-          if (dims > 1) cen[w * dims + 1] = s1;
-          if (dims > 2) cen[w * dims + 2] = s2;
-          if (dims > 3) cen[w * dims + 3] = s3;
-          counters[w] = cnt;
-        }
+        __syncthreads();   // the tile is overwritten next
+      }
+      if (w < K && lane == 0) {
+        cen[w * dims] = s0;
+        if (dims > 1) cen[w * dims + 1] = s1;
+        if (dims > 2) cen[w * dims + 2] = s2;
+        if (dims > 3) cen[w * dims + 3] = s3;
+        counters[w] = cnt;
       }
       __syncthreads();
       // empty clusters: the farthest point of the biggest cluster becomes a one-point cluster

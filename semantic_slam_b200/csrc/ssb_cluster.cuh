@@ -9,7 +9,8 @@
 // the SAME arithmetic in an order that respects the dependencies — labels and centres are bit-identical to OpenCV's:
 //   attempts          : independent once their random centres are drawn (the only use of cv::RNG) -> one CTA per attempt
 //   centre sums       : float sums in point order -> the CTA stages tiles of samples into shared memory, one warp per
-//                       cluster adds its members one by one (ballot, four members in flight), the K chains side by side
+//                       cluster adds the samples in order (non-members masked to +0.0f, which is exact), the K chains side
+//                       by side
 //   assignment        : independent per point (float distances, first minimum wins)
 //   empty clusters    : block-wide lexicographic arg-max (distance, index) = OpenCV's "last farthest point"
 // Selections (valid normals, members of a cluster, RANSAC inliers, hull candidates) are order-preserving compactions:
@@ -182,47 +183,49 @@ __global__ void __launch_bounds__(CL_THREADS) k_cl_kmeans(KmArgs A) {
       if (threadIdx.x < K * dims) cen[threadIdx.x] = A.init[(size_t)blockIdx.x * K * dims + threadIdx.x];
       __syncthreads();
     } else {
-      // centre sums in point order.  The whole CTA stages a tile of samples and labels into shared memory (coalesced, all
-      // 32 warps: the global-memory latency is paid once per tile, not once per 32 samples), then warp k walks the tile and
-      // adds the members of cluster k to its running float sums one by one, four members in flight (their values are
-      // fetched from shared memory before the dependent adds).  Every lane of the warp carries the same sums.
+      // centre sums in point order.  The whole CTA stages a tile of samples and labels into shared memory (vector loads, all
+      // 32 warps: the global-memory latency is paid once per tile), then warp k walks the tile 32 samples at a time: every
+      // lane holds one sample, masked to +0.0f when it is not a member of cluster k, and the 32 values are added to the
+      // running sums in lane order.  Adding +0.0f is exact here — a sum that starts at +0.0f can never become -0.0f, the only
+      // value +0.0f would change — so the chain costs one dependent FADD per SAMPLE (4 cycles) instead of a ballot / find /
+      // shuffle round trip per MEMBER (~70 cycles, profiles/README.md), and the K chains are balanced whatever the cluster
+      // sizes.  Every lane of the warp carries the same sums.
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       int cnt = 0;
       for (int t0 = 0; t0 < N; t0 += CL_TILE) {
         const int nt = min(CL_TILE, N - t0);
-        for (int j = threadIdx.x; j < nt * dims; j += CL_THREADS) tile_v[j] = data[(size_t)t0 * dims + j];
-        for (int j = threadIdx.x; j < nt; j += CL_THREADS) tile_l[j] = labels[t0 + j];
+        {
+          const float* src = data + (size_t)t0 * dims;
+          const int nf = nt * dims, nf4 = ((reinterpret_cast<size_t>(src) & 15) == 0) ? nf >> 2 : 0;
+          const float4* src4 = reinterpret_cast<const float4*>(src);
+          float4* dst4 = reinterpret_cast<float4*>(tile_v);
+          for (int j = threadIdx.x; j < nf4; j += CL_THREADS) dst4[j] = src4[j];
+          for (int j = 4 * nf4 + threadIdx.x; j < nf; j += CL_THREADS) tile_v[j] = src[j];
+          const int* lsrc = labels + t0;
+          const int nl4 = ((reinterpret_cast<size_t>(lsrc) & 15) == 0) ? nt >> 2 : 0;
+          for (int j = threadIdx.x; j < nl4; j += CL_THREADS) reinterpret_cast<int4*>(tile_l)[j] = reinterpret_cast<const int4*>(lsrc)[j];
+          for (int j = 4 * nl4 + threadIdx.x; j < nt; j += CL_THREADS) tile_l[j] = lsrc[j];
+        }
         __syncthreads();
         if (w < K) {
           for (int base = 0; base < nt; base += 32) {
             const int i = base + lane;
-            unsigned m = __ballot_sync(0xffffffffu, i < nt && tile_l[i] == w);
-            cnt += __popc(m);
-            while (m) {
-              int nb = 0;
-              float v[4][4];
+            const bool mine = i < nt && tile_l[i] == w;
+            cnt += __popc(__ballot_sync(0xffffffffu, mine));
+            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+            if (mine) {
+              const float* sp = tile_v + i * dims;
+              m0 = sp[0];
+              if (dims > 1) m1 = sp[1];
+              if (dims > 2) m2 = sp[2];
+              if (dims > 3) m3 = sp[3];
+            }
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.f;
-                if (m) {
-                  const int bq = __ffs(m) - 1;
-                  m &= m - 1;
-                  nb = q + 1;
-                  const float* sp = tile_v + (base + bq) * dims;
-                  v[q][0] = sp[0];
-                  if (dims > 1) v[q][1] = sp[1];
-                  if (dims > 2) v[q][2] = sp[2];
-                  if (dims > 3) v[q][3] = sp[3];
-                }
-              }
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (q < nb) {   // (warp-uniform; an absent member adds nothing, not even a signed zero)
-                  s0 = __fadd_rn(s0, v[q][0]);
-                  if (dims > 1) s1 = __fadd_rn(s1, v[q][1]);
-                  if (dims > 2) s2 = __fadd_rn(s2, v[q][2]);
-                  if (dims > 3) s3 = __fadd_rn(s3, v[q][3]);
-                }
+            for (int j = 0; j < 32; ++j) {
+              s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, m0, j));
+              if (dims > 1) s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, m1, j));
+              if (dims > 2) s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, m2, j));
+              if (dims > 3) s3 = __fadd_rn(s3, __shfl_sync(0xffffffffu, m3, j));
             }
           }
         }

@@ -26,7 +26,7 @@ constexpr int CL_THREADS = 1024;
 constexpr int CL_MAXK = 8;      // clusters per k-means (the reference uses 4 and 2)
 constexpr int CL_MAXD = 4;      // dimensions per sample (3 and 1)
 constexpr int CL_TILE = 4096;    // samples staged into shared memory per round of the ordered centre sums
-constexpr size_t CL_KMEANS_SMEM = (size_t)CL_TILE * (CL_MAXD + 1) * sizeof(float);   // dynamic shared memory of k_cl_kmeans
+constexpr size_t CL_KMEANS_SMEM = (size_t)(CL_TILE + 8) * (CL_MAXD + 1) * sizeof(float);   // dynamic shared memory of k_cl_kmeans
 
 // exclusive rank of every set flag, in index order; count[0] = number of set flags.  One CTA.
 __global__ void __launch_bounds__(CL_THREADS) k_cl_rank(const unsigned char* __restrict__ flags, int n, int* __restrict__ pos,
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_cl_kmeans(KmArgs A) {
   __shared__ double shift_s;
   __shared__ double sh[33];
   extern __shared__ __align__(16) float tile_v[];        // [CL_TILE][dims] samples of the current tile ...
-  int* tile_l = reinterpret_cast<int*>(tile_v + (size_t)CL_TILE * CL_MAXD);   // ... and their labels
+  int* tile_l = reinterpret_cast<int*>(tile_v + (size_t)(CL_TILE + 8) * CL_MAXD);   // ... and their labels
   const int N = A.N, dims = A.dims, K = A.K;
   const float* data = A.data;
   int* labels = A.labels + (size_t)blockIdx.x * N;
@@ -184,9 +184,8 @@ __global__ void __launch_bounds__(CL_THREADS) k_cl_kmeans(KmArgs A) {
       __syncthreads();
     } else {
       // centre sums in point order.  The whole CTA stages a tile of samples and labels into shared memory (vector loads, all
-      // 32 warps: the global-memory latency is paid once per tile), then warp k walks the tile 32 samples at a time: every
-      // lane holds one sample, masked to +0.0f when it is not a member of cluster k, and the 32 values are added to the
-      // running sums in lane order.  Adding +0.0f is exact here — a sum that starts at +0.0f can never become -0.0f, the only
+      // 32 warps: the global-memory latency is paid once per tile), then warp k walks the tile sample by sample, each value
+      // masked to +0.0f when the sample is not a member of cluster k.  Adding +0.0f is exact here — a sum that starts at +0.0f can never become -0.0f, the only
       // value +0.0f would change — so the chain costs one dependent FADD per SAMPLE (4 cycles) instead of a ballot / find /
       // shuffle round trip per MEMBER (~70 cycles, profiles/README.md), and the K chains are balanced whatever the cluster
       // sizes.  Every lane of the warp carries the same sums.
@@ -208,24 +207,28 @@ __global__ void __launch_bounds__(CL_THREADS) k_cl_kmeans(KmArgs A) {
         }
         __syncthreads();
         if (w < K) {
-          for (int base = 0; base < nt; base += 32) {
-            const int i = base + lane;
-            const bool mine = i < nt && tile_l[i] == w;
-            cnt += __popc(__ballot_sync(0xffffffffu, mine));
-            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
-            if (mine) {
-              const float* sp = tile_v + i * dims;
-              m0 = sp[0];
-              if (dims > 1) m1 = sp[1];
-              if (dims > 2) m2 = sp[2];
-              if (dims > 3) m3 = sp[3];
+          // (every lane reads the same shared-memory words — broadcasts — so the loads of the next samples are in flight
+          // while the dependent adds of the current ones retire; a shuffle per sample would serialise on its latency)
+          for (int j0 = 0; j0 < nt; j0 += 8) {
+            int lb[8];
+            float x[8][4];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int j = j0 + u;   // (the tail of the last group reads stale words: masked below)
+              lb[u] = tile_l[j];
+              x[u][0] = tile_v[j * dims];
+              x[u][1] = dims > 1 ? tile_v[j * dims + 1] : 0.f;
+              x[u][2] = dims > 2 ? tile_v[j * dims + 2] : 0.f;
+              x[u][3] = dims > 3 ? tile_v[j * dims + 3] : 0.f;
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              s0 = __fadd_rn(s0, __shfl_sync(0xffffffffu, m0, j));
-              if (dims > 1) s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, m1, j));
-              if (dims > 2) s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, m2, j));
-              if (dims > 3) s3 = __fadd_rn(s3, __shfl_sync(0xffffffffu, m3, j));
+            for (int u = 0; u < 8; ++u) {
+              const bool mine = j0 + u < nt && lb[u] == w;
+              cnt += mine ? 1 : 0;
+              s0 = __fadd_rn(s0, mine ? x[u][0] : 0.f);
+              if (dims > 1) s1 = __fadd_rn(s1, mine ? x[u][1] : 0.f);
+              if (dims > 2) s2 = __fadd_rn(s2, mine ? x[u][2] : 0.f);
+              if (dims > 3) s3 = __fadd_rn(s3, mine ? x[u][3] : 0.f);
             }
           }
         }

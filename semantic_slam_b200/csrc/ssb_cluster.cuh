@@ -159,8 +159,10 @@ struct KmArgs {
   double* compactness;      // [attempts]
 };
 
-// One attempt of cv::kmeans per CTA (blockIdx.x = attempt).
-__global__ void __launch_bounds__(CL_THREADS) k_cl_kmeans(KmArgs A) {
+// One attempt of cv::kmeans per CTA (blockIdx.x = attempt).  DIMS = A.dims as a compile-time constant: the per-sample loops
+// carry no branch on the dimension (a branch per sample cost more than the dependent add it guards).
+template <int DIMS>
+__global__ void __launch_bounds__(CL_THREADS, 1) k_cl_kmeans(KmArgs A) {
   __shared__ float cen[CL_MAXK * CL_MAXD], old[CL_MAXK * CL_MAXD];
   __shared__ int counters[CL_MAXK];
   __shared__ double red_d[32];
@@ -169,7 +171,8 @@ __global__ void __launch_bounds__(CL_THREADS) k_cl_kmeans(KmArgs A) {
   __shared__ double sh[33];
   extern __shared__ __align__(16) float tile_v[];        // [CL_TILE][dims] samples of the current tile ...
   int* tile_l = reinterpret_cast<int*>(tile_v + (size_t)(CL_TILE + 8) * CL_MAXD);   // ... and their labels
-  const int N = A.N, dims = A.dims, K = A.K;
+  constexpr int dims = DIMS;
+  const int N = A.N, K = A.K;
   const float* data = A.data;
   int* labels = A.labels + (size_t)blockIdx.x * N;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

@@ -540,7 +540,7 @@ struct ssb_ransac {
   RBuf<float> c_data, c_dist, c_init, c_centers, c_lohi;
   RBuf<double> c_compact;
   RBuf<float4> c_cloud, c_nrm, c_pts, c_proj, c_cand;
-  bool km_smem_set = false;
+  int km_smem_set = 0;   // bit d: k_cl_kmeans<d> has its dynamic shared memory opted in on this device
 };
 
 static int plan(ssb_ransac* r, const ssb_cloud_layout* L, const ssb_bbox* bx, int nb) {
@@ -999,11 +999,12 @@ static int cl_kmeans(ssb_ransac* r, const float* d_data, int N, int dims, int K,
   A.labels = labelbuf.p;
   A.centers = r->c_centers.p;
   A.compactness = r->c_compact.p;
-  if (!r->km_smem_set) {   // opt-in once per handle / device (80 KB of dynamic shared memory: the staged tile)
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(ssb_cl::k_cl_kmeans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssb_cl::CL_KMEANS_SMEM));
-    r->km_smem_set = true;
+  void (*kern)(ssb_cl::KmArgs) = dims == 1 ? ssb_cl::k_cl_kmeans<1> : dims == 2 ? ssb_cl::k_cl_kmeans<2> : dims == 3 ? ssb_cl::k_cl_kmeans<3> : ssb_cl::k_cl_kmeans<4>;
+  if (!(r->km_smem_set & (1 << dims))) {   // opt-in once per handle / device (80 KB of dynamic shared memory: the staged tile)
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssb_cl::CL_KMEANS_SMEM));
+    r->km_smem_set |= 1 << dims;
   }
-  ssb_cl::k_cl_kmeans<<<attempts, ssb_cl::CL_THREADS, ssb_cl::CL_KMEANS_SMEM, s>>>(A);
+  kern<<<attempts, ssb_cl::CL_THREADS, ssb_cl::CL_KMEANS_SMEM, s>>>(A);
   r->launches += 2;
   std::vector<double> comp(attempts);
   std::vector<float> cen((size_t)attempts * K * dims);

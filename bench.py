@@ -253,6 +253,7 @@ def main():
     ap.add_argument("--no-cfg5", action="store_true", help="skip the per-frame loop (BASELINE.json configs[4])")
     ap.add_argument("--cfg5-frames", type=int, default=1000)
     ap.add_argument("--no-marginals", action="store_true", help="skip the landmark-marginals (K5) sub-object")
+    ap.add_argument("--no-cluster", action="store_true", help="skip the dormant clustering-chain sub-object")
     ap.add_argument("--marginals-sample", type=int, default=64, help="cfg2 landmarks whose marginals are timed on the GPU")
     ap.add_argument("--marginals-cpu-sample", type=int, default=8, help="... and how many of them the CPU oracle computes")
     args = ap.parse_args()
@@ -471,6 +472,50 @@ def main():
             line["marginals"]["kf1000_all"]["max_rel_diff_vs_oracle"] = float(np.abs(Mm - Mo).max() / np.abs(Mo).max())
             line["marginals"]["_pending_cfg2"] = [int(v) for v in sample[: args.marginals_cpu_sample]]
         del gm
+
+    # ---------------- the dormant k-means -> ProjectInliers -> ConvexHull chain (plane_segmentation.cpp:261-477) ----------
+    # cv::kmeans of a full-frame sized sample (300 000 x 3, K = 4, 10 attempts) and the whole chain on a synthetic crop,
+    # through the C-ABI with host buffers, beside the sequential oracle.  Labels / centres are bit-identical (tests).
+    if world == 1 and not args.no_cluster:
+        from semantic_slam_b200 import PlaneClustering
+        pcl = PlaneClustering(device=local)
+        rs = np.random.RandomState(7)
+        cs = rs.randn(4, 3)
+        cs /= np.linalg.norm(cs, axis=1, keepdims=True)
+        big = (cs[rs.randint(0, 4, 300000)] + 0.08 * rs.randn(300000, 3)).astype(np.float32)
+        cloud_c, T_c = synth.make_cluster_scene()
+        cloud_c = cloud_c.reshape(-1, 4)
+        nrm_c = np.full((cloud_c.shape[0], 4), np.nan, dtype=np.float32)
+        okc = np.isfinite(cloud_c[:, 2])
+        nrm_c[okc, :3] = T_c[2, :3] + rs.randn(int(okc.sum()), 3).astype(np.float32) * 0.03
+        pcl.computeKmeans(big, 4, rng_state=999)
+        t0 = time.perf_counter()
+        kg = pcl.computeKmeans(big, 4, rng_state=999)
+        t_kg = time.perf_counter() - t0
+        pcl.clusterAndSegmentAllPlanes(cloud_c, nrm_c, T_c)
+        t0 = time.perf_counter()
+        rg = pcl.clusterAndSegmentAllPlanes(cloud_c, nrm_c, T_c)
+        t_cg = time.perf_counter() - t0
+        line["clustering"] = {"metric": "dormant plane-clustering chain (cv::kmeans + ProjectInliers + ConvexHull)",
+                              "kmeans_300k": {"samples": 300000, "K": 4, "attempts": 10, "ms": 1e3 * t_kg, "value": 0.3 / t_kg, "unit": "Msamples/s"},
+                              "chain": {"points": int(cloud_c.shape[0]), "clusters": int(len(rg["clusters"])), "hull_rows": int(rg["rows"].shape[0]),
+                                        "ms": 1e3 * t_cg}}
+        if rank == 0 and not args.no_cpu_baseline:
+            import oracle
+            t0 = time.perf_counter()
+            ko = oracle.kmeans(big, 4, rng_state=999)
+            t_ko = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            ro = oracle.cluster_planes(cloud_c, nrm_c, T_c)
+            t_co = time.perf_counter() - t0
+            line["clustering"]["kmeans_300k"]["cpu_baseline"] = {"ms": 1e3 * t_ko, "value": 0.3 / t_ko, "unit": "Msamples/s", "cores": 1, "kind": "port"}
+            line["clustering"]["kmeans_300k"]["labels_and_centres_bit_identical"] = bool(
+                np.array_equal(kg[1], ko[1]) and np.array_equal(kg[2].view(np.uint32), ko[2].view(np.uint32)))
+            line["clustering"]["chain"]["cpu_baseline"] = {"ms": 1e3 * t_co, "cores": 1, "kind": "port"}
+            line["clustering"]["chain"]["clusters_identical"] = bool(
+                len(rg["clusters"]) == len(ro["clusters"]) and np.array_equal(rg["labels"], ro["labels"]) and
+                np.array_equal(rg["clusters"]["n_points"], ro["clusters"]["n_points"]))
+        del pcl
 
     # ---------------- cfg4 (BASELINE.json configs[3]): the 100k-keyframe graph, same sharding ---------------------
     # The first genuinely HBM-bound size (B_cg = 280.6 MB per PCG iteration): it does not fit on chip, so the streaming

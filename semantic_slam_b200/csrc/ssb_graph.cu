@@ -300,7 +300,7 @@ struct ssb_graph {
   PinnedBuf<PLEdge> h_plL;   // L-ordered pose-landmark edges, built in place by prepare()
   PinnedBuf<double> h_zdL;
   DBuf<PPEdge> d_pp;
-  DBuf<int> d_lm_rowptr, d_pose_pl_rowptr, d_pose_pl_idx, d_pose_pp_rowptr, d_pose_pp_idx, d_plP_lm;
+  DBuf<int> d_lm_rowptr, d_pose_pl_rowptr, d_pose_pl_idx, d_pose_pp_rowptr, d_pose_pp_idx, d_pose_pp_other, d_plP_lm;
   DBuf<double> d_Hpp, d_bp, d_Hoff, d_Hll, d_bl, d_HplL, d_HplP, d_HllInv, d_Dinv, d_g;
   DBuf<double> d_x, d_r, d_z, d_p0, d_p1, d_q, d_v, d_dl, d_part, d_scalars, d_tmp;
   DBuf<int> d_iscalars, d_ainv_ok;
@@ -1104,9 +1104,11 @@ static int prepare(ssb_graph* g) {
     }
     for (int i = 0; i < Np; ++i) ppp_rowptr[i + 1] += ppp_rowptr[i];
     std::vector<int> fill3(ppp_rowptr.begin(), ppp_rowptr.end() - 1);
-    std::vector<int> ppp_idx(std::max(2 * Epp, 1));
+    std::vector<int> ppp_idx(std::max(2 * Epp, 1)), ppp_other(std::max(2 * Epp, 1));
     for (int k = 0; k < Epp; ++k) {
+      ppp_other[fill3[PP[k].i]] = PP[k].j;
       ppp_idx[fill3[PP[k].i]++] = (k << 1) | 0;
+      ppp_other[fill3[PP[k].j]] = PP[k].i;
       ppp_idx[fill3[PP[k].j]++] = (k << 1) | 1;
     }
     tick("run lists + CSR");
@@ -1128,6 +1130,7 @@ static int prepare(ssb_graph* g) {
     SSB_TRY(g->d_pose_pl_idx.ensure(El));
     SSB_TRY(g->d_pose_pp_rowptr.ensure(Np + 1));
     SSB_TRY(g->d_pose_pp_idx.ensure((size_t)2 * Epp));
+    SSB_TRY(g->d_pose_pp_other.ensure((size_t)2 * Epp));
     SSB_TRY(g->d_plP_lm.ensure(El));
     SSB_TRY(g->d_Hpp.ensure((size_t)36 * Np));
     SSB_TRY(g->d_bp.ensure((size_t)6 * Np));
@@ -1426,6 +1429,7 @@ static int prepare(ssb_graph* g) {
     if (El) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pl_idx.p, ppl_idx.data(), (size_t)El * sizeof(int), cudaMemcpyHostToDevice, s));
     SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pp_rowptr.p, ppp_rowptr.data(), (Np + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     if (Epp) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pp_idx.p, ppp_idx.data(), (size_t)2 * Epp * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (Epp) SSB_CUDA_CHECK(cudaMemcpyAsync(g->d_pose_pp_other.p, ppp_other.data(), (size_t)2 * Epp * sizeof(int), cudaMemcpyHostToDevice, s));
     tick("flow tables + ND order + enqueue uploads");
     SSB_CUDA_CHECK(cudaStreamSynchronize(s));  // host vectors above go out of scope
     tick("upload sync");
@@ -1452,6 +1456,7 @@ static int prepare(ssb_graph* g) {
     G.pose_pl_idx = g->d_pose_pl_idx.p;
     G.pose_pp_rowptr = g->d_pose_pp_rowptr.p;
     G.pose_pp_idx = g->d_pose_pp_idx.p;
+    G.pose_pp_other = g->d_pose_pp_other.p;
     G.Hpp = g->d_Hpp.p;
     G.bp = g->d_bp.p;
     G.Hoff = g->d_Hoff.p;

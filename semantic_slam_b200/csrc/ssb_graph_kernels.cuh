@@ -41,6 +41,7 @@ struct DevGraph {
   const int* pose_pl_idx;
   const int* pose_pp_rowptr;
   const int* pose_pp_idx;
+  const int* pose_pp_other;   // per incidence: the keyframe at the other end (saves the dependent load of the edge record)
   double *Hpp, *bp, *Hoff, *Hll, *bl, *HplL, *HplP;
   int* plP_lm;
   double *HllInv, *Dinv, *g;
@@ -1438,42 +1439,56 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
         double pk = __shfl_sync(0xffffffffu, pc, base_lane + k);
         if (act) qv += G.Hpp[36 * (size_t)i + 6 * comp + k] * pk;
       }
-      int k0 = 0, k1 = 0;
+      int k0 = 0, k1 = 0, q0 = 0, q1 = 0;
       if (act) {
         k0 = G.pose_pp_rowptr[i];
         k1 = G.pose_pp_rowptr[i + 1];
+        q0 = G.pose_pl_rowptr[i];   // (requested here so that the landmark chain below overlaps the pose-pose chain)
+        q1 = G.pose_pl_rowptr[i + 1];
       }
+      int lm0[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) lm0[u] = (act && q0 + u < q1) ? G.plP_lm[q0 + u] : -1;
       int nmax = k1 - k0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-      for (int s = 0; s < nmax; ++s) {
-        const bool has = act && (k0 + s < k1);
-        int e = 0, role = 0, other = 0;
-        double oc = 0.0;
-        if (has) {
-          const int code = G.pose_pp_idx[k0 + s];
-          e = code >> 1;
-          role = code & 1;
-          other = role == 0 ? G.pp[e].j : G.pp[e].i;
-          oc = __ldcg(G.z + 6 * (size_t)other + comp) + beta * __ldcg(pold + 6 * (size_t)other + comp);
+      // pose-pose incidences two at a time: both neighbour vectors and both block rows are in flight together, and the
+      // neighbour index comes from the incidence table instead of the edge record (one dependent load less per chain)
+      for (int s = 0; s < nmax; s += 2) {
+        const bool h0 = act && (k0 + s < k1), h1 = act && (k0 + s + 1 < k1);
+        int c0 = 0, c1 = 0, o0 = 0, o1 = 0;
+        if (h0) {
+          c0 = G.pose_pp_idx[k0 + s];
+          o0 = G.pose_pp_other[k0 + s];
         }
+        if (h1) {
+          c1 = G.pose_pp_idx[k0 + s + 1];
+          o1 = G.pose_pp_other[k0 + s + 1];
+        }
+        double oc0 = 0.0, oc1 = 0.0, r0[6], r1[6];
+        if (h0) oc0 = __ldcg(G.z + 6 * (size_t)o0 + comp) + beta * __ldcg(pold + 6 * (size_t)o0 + comp);
+        if (h1) oc1 = __ldcg(G.z + 6 * (size_t)o1 + comp) + beta * __ldcg(pold + 6 * (size_t)o1 + comp);
+        {
+          const double* H0 = G.Hoff + 36 * (size_t)(c0 >> 1);
+          const double* H1 = G.Hoff + 36 * (size_t)(c1 >> 1);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          double ok = __shfl_sync(0xffffffffu, oc, base_lane + k);
-          if (has) {
-            const double* Ho = G.Hoff + 36 * (size_t)e;
-            qv += (role == 0 ? Ho[6 * comp + k] : Ho[6 * k + comp]) * ok;
+          for (int k = 0; k < 6; ++k) {
+            r0[k] = h0 ? ((c0 & 1) == 0 ? H0[6 * comp + k] : H0[6 * k + comp]) : 0.0;
+            r1[k] = h1 ? ((c1 & 1) == 0 ? H1[6 * comp + k] : H1[6 * k + comp]) : 0.0;
           }
         }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) qv += r0[k] * __shfl_sync(0xffffffffu, oc0, base_lane + k);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) qv += r1[k] * __shfl_sync(0xffffffffu, oc1, base_lane + k);
       }
       if (act) {
         // the pose's landmark edges in batches of 4: the landmark ids, then every v triple and block row are requested
         // together (one dependent-load round trip per batch instead of two per edge)
-        const int q0 = G.pose_pl_rowptr[i], q1 = G.pose_pl_rowptr[i + 1];
         for (int kk = q0; kk < q1; kk += 4) {
           int lm[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) lm[u] = kk + u < q1 ? G.plP_lm[kk + u] : -1;
+          for (int u = 0; u < 4; ++u) lm[u] = kk == q0 ? lm0[u] : (kk + u < q1 ? G.plP_lm[kk + u] : -1);
           double hv[4][3], vv[4][3];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {

@@ -32,6 +32,8 @@ if ROOT not in sys.path:
 import numpy as np
 
 LM_ITERS = 20
+_MARG_CPU_NOTE = ("oracle, one sparse Cholesky of the full system + g2o's MarginalCovarianceCholesky recursion (memoised "
+                  "elements of the inverse; what computeMarginals runs in the reference), 1 thread")
 
 
 def load_peaks():
@@ -255,7 +257,6 @@ def main():
     ap.add_argument("--no-marginals", action="store_true", help="skip the landmark-marginals (K5) sub-object")
     ap.add_argument("--no-cluster", action="store_true", help="skip the dormant clustering-chain sub-object")
     ap.add_argument("--marginals-sample", type=int, default=64, help="cfg2 landmarks whose marginals are timed on the GPU")
-    ap.add_argument("--marginals-cpu-sample", type=int, default=8, help="... and how many of them the CPU oracle computes")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -433,8 +434,9 @@ def main():
     # buffers on (i) a sample of cfg2's landmarks right after the e2e optimise above (10 000 keyframes fill the chip: one
     # latency-bound PCG solve per column) and (ii) ALL landmarks of a 1 000-keyframe graph (the per-frame loop's size: 11
     # copies of the graph side by side, one conjugate-gradient recurrence per copy inside one launch = 11 columns), each
-    # beside the oracle's time for the same call on the same landmarks (a CSparse-style factorisation of the full system
-    # + 3 solves per landmark).
+    # beside the oracle's time for the same call (a CSparse-style factorisation of the full system + g2o's
+    # MarginalCovarianceCholesky recursion, `method="g2o"`: the algorithm the reference's computeMarginals runs — not the
+    # three triangular solves per landmark the GPU tests use as their checker, which would flatter the GPU).
     if world == 1 and not args.no_marginals:
         lm_all = ids_cfg2[spec.vkind == 1].astype(np.int32)
         n_s = min(args.marginals_sample, lm_all.size)
@@ -465,12 +467,13 @@ def main():
             synth.load_graph(om, specm)
             om.optimize(10)
             t0 = time.perf_counter()
-            Mo = om.computeLandmarkMarginals(lmm)
+            Mo = om.computeLandmarkMarginals(lmm, method="g2o")
             t_om = time.perf_counter() - t0
             line["marginals"]["kf1000_all"]["cpu_baseline"] = {"value": lmm.size / t_om, "unit": "landmarks/s", "cores": 1, "kind": "port",
-                                                               "seconds": t_om}
+                                                               "seconds": t_om, "sample": _MARG_CPU_NOTE}
             line["marginals"]["kf1000_all"]["max_rel_diff_vs_oracle"] = float(np.abs(Mm - Mo).max() / np.abs(Mo).max())
-            line["marginals"]["_pending_cfg2"] = [int(v) for v in sample[: args.marginals_cpu_sample]]
+            line["marginals"]["_pending_cfg2"] = [int(v) for v in sample]
+            line["marginals"]["_pending_cfg2_all"] = [int(v) for v in lm_all]
         del gm
 
     # ---------------- the dormant k-means -> ProjectInliers -> ConvexHull chain (plane_segmentation.cpp:261-477) ----------
@@ -640,14 +643,21 @@ def main():
                           "oracle_chi2_final": float(o.history[-1, 1])}
         if "marginals" in line and "_pending_cfg2" in line["marginals"]:
             # K5 on cfg2: same landmarks, same end state (20 LM iterations on both sides)
+            # g2o's recursion shares the elements it memoises between landmarks, so the CPU cost is not linear in the number
+            # of landmarks: the oracle computes ALL of them (what the reference asks for after every optimise,
+            # semantic_graph_slam.cpp:181-205), the GPU figure beside it is the linear extrapolation of the timed sample
+            # (independent columns: one PCG solve each).
             vs = np.array(line["marginals"]["_pending_cfg2"], dtype=np.int32)
+            va = np.array(line["marginals"]["_pending_cfg2_all"], dtype=np.int32)
             t0 = time.perf_counter()
-            Mo2 = o.computeLandmarkMarginals(vs)
+            Mo2 = o.computeLandmarkMarginals(va, method="g2o")
             dtm = time.perf_counter() - t0
             c2 = line["marginals"]["cfg2_sample"]
-            c2["cpu_baseline"] = {"value": vs.size / dtm, "unit": "landmarks/s", "cores": 1, "kind": "port",
-                                  "sample": "the first %d of the sampled landmarks (%.1f s, one factorisation included)" % (vs.size, dtm)}
-            c2["max_rel_diff_vs_oracle"] = float(np.abs(Mg[:vs.size] - Mo2).max() / np.abs(Mo2).max())
+            c2["cpu_baseline"] = {"value": va.size / dtm, "unit": "landmarks/s", "cores": 1, "kind": "port", "seconds": dtm,
+                                  "sample": "ALL %d landmarks of cfg2; %s" % (va.size, _MARG_CPU_NOTE)}
+            pos = {int(v): k for k, v in enumerate(va)}
+            sel = np.array([pos[int(v)] for v in vs])
+            c2["max_rel_diff_vs_oracle"] = float(np.abs(Mg - Mo2[sel]).max() / np.abs(Mo2[sel]).max())
         # the RANSAC half next to ITS CPU baseline (PCL-order restatement, 1 thread, 8 of the 64 crops)
         nbs = 8
         t0 = time.perf_counter()
@@ -661,6 +671,7 @@ def main():
                                              "e2e": line["ransac"]["e2e"]["value"] / (nps / tr / 1e6)}
     if "marginals" in line:
         line["marginals"].pop("_pending_cfg2", None)
+        line["marginals"].pop("_pending_cfg2_all", None)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

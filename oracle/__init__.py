@@ -66,6 +66,7 @@ def lib():
         L.orc_graph_num_scalar.argtypes = [C.c_void_p]
         L.orc_graph_solve_once.argtypes = [C.c_void_p, C.c_double, _dp]
         L.orc_graph_landmark_marginals.argtypes = [C.c_void_p, _ip, C.c_int, _dp, C.c_int]
+        L.orc_graph_landmark_marginals_g2o.argtypes = [C.c_void_p, _ip, C.c_int, _dp, C.c_int, C.POINTER(C.c_longlong)]
         L.orc_to_vector_mqt.argtypes = [_dp, _dp]
         L.orc_from_vector_mqt.argtypes = [_dp, _dp]
         L.orc_se3_oplus.argtypes = [_dp, _dp, _dp]
@@ -207,11 +208,20 @@ class OracleGraphSLAM:
         self._L.orc_graph_last_stats(self._h, out.ctypes.data_as(_dp))
         return dict(analyze_ms=out[0], factor_ms=out[1], linearize_ms=out[2], nnzL=int(out[3]), n=int(out[4]))
 
-    def computeLandmarkMarginals(self, vids, relinearize=False):
+    def computeLandmarkMarginals(self, vids, relinearize=False, method="solve"):
+        """3x3 blocks of H^-1.  method "solve": one pair of triangular solves per column (the checker of the GPU tests);
+        "g2o": MarginalCovarianceCholesky's memoised recursion over the factor (what the reference's computeMarginals
+        runs, graph_slam.cpp:225) — the timed CPU baseline of bench.py; self.marginal_map_entries = elements it computed."""
         vids = np.ascontiguousarray(vids, dtype=np.int32)
         out = np.zeros((vids.size, 3, 3))
-        r = self._L.orc_graph_landmark_marginals(self._h, vids.ctypes.data_as(_ip), vids.size,
-                                                 out.ctypes.data_as(_dp), int(relinearize))
+        if method == "g2o":
+            cnt = C.c_longlong(0)
+            r = self._L.orc_graph_landmark_marginals_g2o(self._h, vids.ctypes.data_as(_ip), vids.size,
+                                                         out.ctypes.data_as(_dp), int(relinearize), C.byref(cnt))
+            self.marginal_map_entries = int(cnt.value)
+        else:
+            r = self._L.orc_graph_landmark_marginals(self._h, vids.ctypes.data_as(_ip), vids.size,
+                                                     out.ctypes.data_as(_dp), int(relinearize))
         if r != 1:
             raise RuntimeError("marginals failed")
         return out

@@ -35,6 +35,7 @@
 #include <map>
 #include <queue>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include <chrono>
 #ifdef _OPENMP
@@ -1400,6 +1401,88 @@ int orc_graph_landmark_marginals(void* h, const int* vids, int n, double* out9n,
       for (int r = 0; r < d; ++r) out9n[(size_t)k * d * d + d * r + c] = sol[off + r];
     }
   }
+  return 1;
+}
+
+// The same blocks the way g2o computes them: MarginalCovarianceCholesky::computeCovariance
+// (core/marginal_covariance_cholesky.cpp), called by LinearSolverCCS::solvePattern through
+// BlockSolver::computeMarginals (graph_slam.cpp:225).  No solve per column: every requested element of
+// (L L^T)^-1 follows from the entries of its own column of L and elements further down (Takahashi's
+// recursion), memoised in a hash map —
+//   diag[r] = 1 / L(r,r)
+//   s(r,c)  = sum over the off-diagonal entries (rr, L(rr,r)) of column r of  inv(min(rr,c), max(rr,c)) * L(rr,r)
+//   inv(r,r) = diag[r] * (diag[r] - s),   inv(r,c) = -s * diag[r]  (r < c)
+// with the requested elements sorted like g2o's MatrixElem::operator< (column descending, then row
+// descending) so that later requests find most of their dependencies in the map.  g2o recurses; the
+// restatement keeps its own stack (the recursion is as deep as the elimination tree is high) and adds
+// the terms in the same order.
+int orc_graph_landmark_marginals_g2o(void* h, const int* vids, int n, double* out9n, int relinearize, long long* map_entries) {
+  Graph& g = *(Graph*)h;
+  if (relinearize || !g.chol) {
+    initialize_optimization(g);
+    build_structure(g);
+    chol_analyze(g);
+    build_system(g);
+  }
+  chol_fill(g, 0.0);
+  if (!chol_factor(g)) return 0;
+  const SparseChol& S = *g.chol;
+  const int N = S.n;
+  std::vector<double> diag(N);
+  for (int r = 0; r < N; ++r) diag[r] = 1.0 / S.Lx[S.Lp[r]];
+  struct Elem { int r, c; };
+  std::vector<Elem> elems;
+  elems.reserve((size_t)n * 9);
+  for (int k = 0; k < n; ++k) {
+    int id = vids[k];
+    if (id < 0 || id >= (int)g.V.size() || g.V[id].hidx < 0) return -1;
+    int off = g.boff[g.V[id].hidx], d = g.V[id].dim();
+    for (int r = 0; r < d; ++r)
+      for (int c = 0; c < d; ++c) {
+        int rr = S.pinv_s[off + r], cc = S.pinv_s[off + c];
+        if (rr > cc) std::swap(rr, cc);
+        elems.push_back({rr, cc});
+      }
+  }
+  std::sort(elems.begin(), elems.end(), [](const Elem& a, const Elem& b) { return a.c > b.c || (a.c == b.c && a.r > b.r); });
+  std::unordered_map<unsigned long long, double> inv;
+  inv.reserve((size_t)n * 64 + 1024);
+  auto key = [N](int r, int c) { return (unsigned long long)r * (unsigned long long)N + (unsigned long long)c; };
+  struct Frame { int r, c, p; double s; };
+  std::vector<Frame> st;
+  for (const Elem& e : elems) {
+    if (inv.find(key(e.r, e.c)) != inv.end()) continue;
+    st.push_back({e.r, e.c, S.Lp[e.r] + 1, 0.0});
+    while (!st.empty()) {
+      Frame& f = st.back();
+      if (f.p < S.Lp[f.r + 1]) {
+        const int rr = S.Li[f.p];
+        const int a = rr < f.c ? rr : f.c, b = rr < f.c ? f.c : rr;
+        auto it = inv.find(key(a, b));
+        if (it != inv.end()) {
+          f.s += it->second * S.Lx[f.p];
+          ++f.p;
+        } else {
+          st.push_back({a, b, S.Lp[a] + 1, 0.0});   // f is dangling from here on: re-read st.back() next round
+        }
+      } else {
+        const double res = f.r == f.c ? diag[f.r] * (diag[f.r] - f.s) : -f.s * diag[f.r];
+        inv[key(f.r, f.c)] = res;
+        st.pop_back();
+      }
+    }
+  }
+  for (int k = 0; k < n; ++k) {
+    int id = vids[k];
+    int off = g.boff[g.V[id].hidx], d = g.V[id].dim();
+    for (int r = 0; r < d; ++r)
+      for (int c = 0; c < d; ++c) {
+        int rr = S.pinv_s[off + r], cc = S.pinv_s[off + c];
+        if (rr > cc) std::swap(rr, cc);
+        out9n[(size_t)k * d * d + d * r + c] = inv[key(rr, cc)];
+      }
+  }
+  if (map_entries) *map_entries = (long long)inv.size();
   return 1;
 }
 

@@ -21,6 +21,7 @@
 #include <iostream>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -294,16 +295,15 @@ class GraphSLAM {
   // graph_slam.cpp:221-234: vert_pairs are (hessianIndex, hessianIndex) of landmark vertices
   bool computeLandmarkMarginals(g2o::SparseBlockMatrix<ssb_host::MatrixXd>& spinv,
                                 std::vector<std::pair<int, int>> vert_pairs_vec) {
+    std::unordered_map<int, int> vid_of_hidx;   // one pass over the landmark vertices instead of a scan per pair
+    vid_of_hidx.reserve(xyz_.size());
+    for (auto& v : xyz_) vid_of_hidx.emplace(v->hessianIndex(), v->id());
     std::vector<int> vids;
+    vids.reserve(vert_pairs_vec.size());
     for (auto& pr : vert_pairs_vec) {
-      int vid = -1;
-      for (auto& v : xyz_)
-        if (v->hessianIndex() == pr.first) {
-          vid = v->id();
-          break;
-        }
-      if (vid < 0) return false;
-      vids.push_back(vid);
+      auto it = vid_of_hidx.find(pr.first);
+      if (it == vid_of_hidx.end()) return false;
+      vids.push_back(it->second);
     }
     std::vector<double> out(9 * vids.size());
     if (ssb_graph_landmark_marginals(graph, vids.data(), (int)vids.size(), out.data()) != 1) {

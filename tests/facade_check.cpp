@@ -1,11 +1,36 @@
-// Compile-and-run check of the C++ facade (POD twin; Eigen is absent from this image).
-// Built by tests/test_facade.py with g++ against include/ssb.h and libssb.so.
+// Compile-and-run check of the C++ facade.  Built by tests/test_facade.py with g++ against include/ssb.h and libssb.so,
+// twice: with the POD twins (Eigen is absent from this image) and with -DSSB_USE_EIGEN -I tests/mock_eigen, a mock that
+// has Eigen's call syntax and compile-time restrictions, so the branch a maintainer of the reference would compile is
+// exercised too.
 #include <cmath>
 #include <cstdio>
 #include "ps_graph_slam/graph_slam.hpp"
 #include "planar_segmentation/plane_segmentation_b200.h"
 #include "planar_segmentation/point_cloud_segmentation.h"
 #include "ps_graph_slam/data_association_b200.h"
+
+// the only places where the two value-type families differ: construction and the translation accessor
+#ifdef SSB_HAVE_EIGEN
+static ssb_host::Isometry3d iso_x(double x) {
+  ssb_host::Isometry3d T = ssb_host::Isometry3d::Identity();
+  T.matrix()(0, 3) = x;
+  return T;
+}
+static double x_of(const ssb_host::Isometry3d& T) { return T.matrix()(0, 3); }
+static ssb_host::Vector3d v3(double x, double y, double z) { return ssb_host::Vector3d(x, y, z); }
+static ssb_host::Vector4d v4(double a, double b, double c, double d) { return ssb_host::Vector4d(a, b, c, d); }
+static ssb_host::MatrixXd eye(int n) { return ssb_host::MatrixXd::Identity(n, n); }
+#else
+static ssb_host::Isometry3d iso_x(double x) {
+  ssb_host::Isometry3d T = ssb_host::Isometry3d::Identity();
+  T.m[3] = x;
+  return T;
+}
+static double x_of(const ssb_host::Isometry3d& T) { return T.m[3]; }
+static ssb_host::Vector3d v3(double x, double y, double z) { return ssb_host::Vector3d{{x, y, z}}; }
+static ssb_host::Vector4d v4(double a, double b, double c, double d) { return ssb_host::Vector4d{{a, b, c, d}}; }
+static ssb_host::MatrixXd eye(int n) { return ssb_host::MatrixXd::Identity(n); }
+#endif
 
 int main(int argc, char** argv) {
   const bool run = argc > 1;  // without arguments: construct nothing (no GPU needed), just prove it links
@@ -96,31 +121,34 @@ int main(int argc, char** argv) {
   using namespace ssb_host;
   std::vector<g2o::VertexSE3*> kf;
   for (int k = 0; k < 12; ++k) {
-    Isometry3d T = Isometry3d::Identity();
-    T.m[3] = 0.5 * k + (k ? 0.03 : 0.0);
-    kf.push_back(gs.add_se3_node(T));
-    if (k) {
-      Isometry3d Z = Isometry3d::Identity();
-      Z.m[3] = 0.5;
-      gs.add_se3_edge(kf[k - 1], kf[k], Z, MatrixXd::Identity(6));
-    }
+    kf.push_back(gs.add_se3_node(iso_x(0.5 * k + (k ? 0.03 : 0.0))));
+    if (k) gs.add_se3_edge(kf[k - 1], kf[k], iso_x(0.5), eye(6));
   }
-  Vector3d p{{2.0, 1.0, 0.5}};
-  g2o::VertexPointXYZ* lm = gs.add_point_xyz_node(p);
-  for (int k = 0; k < 12; ++k) {
-    Vector3d z{{2.0 - 0.5 * k, 1.0, 0.5}};
-    gs.add_se3_point_xyz_edge(kf[k], lm, z, MatrixXd::Identity(3));
-  }
+  g2o::VertexPointXYZ* lm = gs.add_point_xyz_node(v3(2.0, 1.0, 0.5));
+  for (int k = 0; k < 12; ++k) gs.add_se3_point_xyz_edge(kf[k], lm, v3(2.0 - 0.5 * k, 1.0, 0.5), eye(3));
   // plane landmark (the reference's dormant VertexPlane / EdgeSE3Plane API): the floor z = 0 seen from every keyframe
-  Vector4d floor_w{{0.0, 0.0, 1.0, 0.0}};
+  Vector4d floor_w = v4(0.0, 0.0, 1.0, 0.0);
   g2o::VertexPlane* fl = gs.add_plane_node(floor_w);
   if (!fl) return 5;
-  for (int k = 0; k < 12; ++k) gs.add_se3_plane_edge(kf[k], fl, floor_w, MatrixXd::Identity(3));
+  for (int k = 0; k < 12; ++k) gs.add_se3_plane_edge(kf[k], fl, floor_w, eye(3));
   if (!gs.optimize()) return 3;
   Vector4d fe = fl->estimate();
   if (std::fabs(fe(2) - 1.0) > 1e-6 || std::fabs(fe(3)) > 1e-6) return 6;
+  // semantic_graph_slam.cpp:181-205: marginals asked by (hessianIndex, hessianIndex), read through block(i,i)->eval()
+  lm->unlockQuadraticForm();
+  g2o::SparseBlockMatrix<MatrixXd> spinv;
+  const int hi = lm->hessianIndex();
+  if (!gs.computeLandmarkMarginals(spinv, {{hi, hi}})) return 7;
+  if (!spinv.block(hi, hi)) return 8;
+  const MatrixXd cov = spinv.block(hi, hi)->eval();
+  if (!(cov(0, 0) > 0 && cov(1, 1) > 0 && cov(2, 2) > 0) || std::fabs(cov(0, 1) - cov(1, 0)) > 1e-9 * cov(0, 0)) return 9;
   Isometry3d last = kf.back()->estimate();
-  std::printf("last keyframe x = %.6f (expect 5.5), hessianIndex(first)=%d id(last)=%d\n", last.m[3], kf[0]->hessianIndex(),
-              kf.back()->id());
-  return std::fabs(last.m[3] - 5.5) < 1e-6 ? 0 : 4;
+  std::printf("last keyframe x = %.6f (expect 5.5), hessianIndex(first)=%d id(last)=%d, landmark covariance xx = %.3e\n", x_of(last),
+              kf[0]->hessianIndex(), kf.back()->id(), cov(0, 0));
+#ifdef SSB_HAVE_EIGEN
+  std::printf("value types: Eigen call syntax\n");
+#else
+  std::printf("value types: POD twins\n");
+#endif
+  return std::fabs(x_of(last) - 5.5) < 1e-6 ? 0 : 4;
 }

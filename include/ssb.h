@@ -252,6 +252,17 @@ int ssb_ransac_timing(ssb_ransac* r, double out[2]);
 /* number of kernels launched so far on this handle */
 long long ssb_ransac_launch_count(ssb_ransac* r);
 
+/* The 3-point sample stream pcl::RandomSampleConsensus draws for a model over `n_indices` points (host only, no GPU):
+ * SampleConsensusModel's boost::mt19937 seeded with `seed` (PCL: 12345u unless `random`), read through
+ * boost::uniform_int<>(0, INT_MAX) (= the 32-bit output >> 1), and drawIndexSample's partial Fisher-Yates shuffle
+ * of `shuffled_indices_`, whose state carries over from one draw to the next
+ * (pcl/sample_consensus/sac_model.h: drawIndexSample; called per RANSAC iteration through getSamples by
+ * pcl::SACSegmentation::segment, plane_segmentation.cpp:647).  triples: int32 [n_draws][3], indices into the model's
+ * point set (the row-major crop).  A draw PCL would reject (isSampleGood: collinear) stays in the stream; the adaptive
+ * replay (ssb_ransac_opts.mode = 1) skips it exactly where PCL would draw again, so the evaluated hypotheses coincide.
+ * Returns SSB_OK; n_indices < 3 gives a stream of zeros (PCL selects no sample). */
+int ssb_ransac_pcl_samples(int n_indices, int n_draws, unsigned seed, int* triples);
+
 /* plane_segmentation::segmentPointCloudData alone (K6): out = n x 4 floats (x,y,z,rgb), row-major
  * organised crop.  Returns n = width*height, or -1 for a spurious box. */
 int ssb_crop_bbox(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout, const ssb_bbox* box, float* out);

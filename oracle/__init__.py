@@ -345,6 +345,69 @@ def ransac_plane_batch(msg, width, height, point_step, row_step, offsets, boxes,
     return res, counts, (mask[:total] if mask is not None else None)
 
 
+# ---- PCL's RANSAC sample stream, restated in pure Python (independent of the product's C++ and of libstdc++) ----------
+class _MT19937:
+    """Matsumoto & Nishimura's MT19937 with init_genrand seeding = boost::mt19937(seed) = std::mt19937(seed).
+    Known answer (C++11 [rand.predef]): the 10000th output of the default-seeded (5489) engine is 4123659995."""
+
+    def __init__(self, seed):
+        mt = [0] * 624
+        mt[0] = seed & 0xFFFFFFFF
+        for i in range(1, 624):
+            mt[i] = (1812433253 * (mt[i - 1] ^ (mt[i - 1] >> 30)) + i) & 0xFFFFFFFF
+        self.mt, self.idx = mt, 624
+
+    def __call__(self):
+        mt = self.mt
+        if self.idx >= 624:
+            for k in range(624):
+                y = (mt[k] & 0x80000000) | (mt[(k + 1) % 624] & 0x7FFFFFFF)
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0)
+            self.idx = 0
+        y = mt[self.idx]
+        self.idx += 1
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9D2C5680
+        y ^= (y << 15) & 0xEFC60000
+        y ^= y >> 18
+        return y & 0xFFFFFFFF
+
+
+def _boost_uniform_int(engine, lo, hi):
+    """boost::random::detail::generate_uniform_int for a 32-bit engine (brange = 2^32 - 1) and range = hi - lo < brange:
+    bucket_size = brange / (range + 1), incremented when brange % (range + 1) == range; result = engine() / bucket_size,
+    redrawn while it exceeds the range.  For uniform_int<>(0, INT_MAX) — PCL's rng_dist_ — bucket_size is 2 and nothing is
+    ever redrawn."""
+    rng = hi - lo
+    brange = 0xFFFFFFFF
+    assert 0 < rng < brange
+    bucket = brange // (rng + 1)
+    if brange % (rng + 1) == rng:
+        bucket += 1
+    while True:
+        r = engine() // bucket
+        if r <= rng:
+            return lo + r
+
+
+def pcl_sample_stream(n_points, n_draws, seed=12345):
+    """pcl::SampleConsensusModel::drawIndexSample, n_draws times on a fresh model over n_points points
+    (pcl/sample_consensus/sac_model.h): shuffled_indices_ starts as 0..n-1 and keeps its state between draws; every draw
+    swaps element i (i = 0, 1, 2) with element i + rnd() % (n - i) and returns the first three.  Restated for
+    tests/test_oracle_ransac.py, which compares the product's ssb_ransac_pcl_samples with it bit for bit."""
+    out = np.zeros((n_draws, 3), dtype=np.int32)
+    if n_points < 3:
+        return out
+    eng = _MT19937(seed)
+    sh = list(range(n_points))
+    for d in range(n_draws):
+        for i in range(3):
+            j = i + _boost_uniform_int(eng, 0, 2**31 - 1) % (n_points - i)
+            sh[i], sh[j] = sh[j], sh[i]
+        out[d] = sh[:3]
+    return out
+
+
 # ---- the live segmentation path (oracle_segment.cpp): integral-image normals + organised multi-plane segmentation ----
 def integral_normals(cloud_hw4, max_depth_change_factor=0.03, smoothing_size=20.0):
     """pcl::IntegralImageNormalEstimation (COVARIANCE_MATRIX) on an organised (h, w, 4) float32 crop.

@@ -7,6 +7,6 @@ importing the bindings fails loudly when the CUDA extension is missing.
 """
 from ._lib import lib, build, SsbError  # noqa: F401
 from .graph_slam import GraphSLAM  # noqa: F401
-from .segmentation import PlaneSegmentation, OrganizedSegmentation, PlaneClustering, CloudLayout  # noqa: F401
+from .segmentation import PlaneSegmentation, OrganizedSegmentation, PlaneClustering, CloudLayout, pcl_sample_stream  # noqa: F401
 from .association import DataAssociation  # noqa: F401
 from .semantic_graph_slam import SemanticGraphSLAM  # noqa: F401

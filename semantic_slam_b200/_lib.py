@@ -73,6 +73,7 @@ SYMBOLS = [
     "ssb_graph_shard_info", "ssb_shard_plan", "ssb_ransac_default_opts",
     "ssb_ransac_create", "ssb_ransac_destroy", "ssb_ransac_plane_batch", "ssb_ransac_upload",
     "ssb_organized_default_opts", "ssb_organized_planes", "ssb_organized_last_ms", "ssb_ransac_run_resident", "ssb_ransac_fetch", "ssb_ransac_stream", "ssb_ransac_launch_count", "ssb_ransac_timing", "ssb_crop_bbox",
+    "ssb_ransac_pcl_samples",
     "ssb_kmeans", "ssb_project_hull", "ssb_cluster_default_opts", "ssb_cluster_planes",
     "ssb_segment_planar_surfaces", "ssb_assoc_default_opts", "ssb_assoc_create", "ssb_assoc_destroy", "ssb_assoc_find_matches",
     "ssb_assoc_set_landmark_estimate", "ssb_assoc_set_landmark_cov", "ssb_assoc_num_landmarks", "ssb_assoc_get_landmark",
@@ -153,6 +154,7 @@ def lib():
     L.ssb_ransac_launch_count.restype = C.c_longlong
     L.ssb_ransac_timing.argtypes = [vp, dp]
     L.ssb_crop_bbox.argtypes = [vp, vp, C.POINTER(CloudLayoutC), vp, vp]
+    L.ssb_ransac_pcl_samples.argtypes = [C.c_int, C.c_int, C.c_uint, vp]
     L.ssb_organized_default_opts.argtypes = [C.POINTER(OrganizedOpts)]
     L.ssb_organized_planes.argtypes = [vp, vp, C.POINTER(CloudLayoutC), vp, C.c_int, C.POINTER(OrganizedOpts), C.c_int, vp, vp, vp, vp,
                                        vp, vp]

@@ -762,6 +762,32 @@ int ssb_ransac_plane_batch(ssb_ransac* r, const void* msg, const ssb_cloud_layou
   return ssb_ransac_fetch(r, results, counts, mask);
 }
 
+// pcl::SampleConsensusModel::drawIndexSample driven by boost::variate_generator<boost::mt19937&, boost::uniform_int<>>
+// (sac_model.h).  boost::mt19937 is std::mt19937 (same parameters and seeding); uniform_int<>(0, INT_MAX) over a 32-bit
+// engine is generate_uniform_int's bucket division with bucket_size 2 (0xffffffff / 0x80000000 = 1, and the remainder
+// equals the range, so it is incremented), i.e. the engine output shifted right by one, never rejected.
+int ssb_ransac_pcl_samples(int n_indices, int n_draws, unsigned seed, int* triples) {
+  if (n_draws < 0 || (n_draws > 0 && !triples)) return SSB_ERR_INVALID;
+  if (n_indices < 3) {
+    std::fill(triples, triples + 3 * (size_t)n_draws, 0);
+    return SSB_OK;
+  }
+  std::mt19937 alg(seed);
+  std::vector<int> shuffled(n_indices);
+  for (int i = 0; i < n_indices; ++i) shuffled[i] = i;
+  const size_t index_size = (size_t)n_indices;
+  for (int d = 0; d < n_draws; ++d) {
+    for (unsigned i = 0; i < 3; ++i) {
+      const int rnd = (int)(alg() >> 1);
+      std::swap(shuffled[i], shuffled[i + ((size_t)rnd % (index_size - i))]);
+    }
+    triples[3 * (size_t)d + 0] = shuffled[0];
+    triples[3 * (size_t)d + 1] = shuffled[1];
+    triples[3 * (size_t)d + 2] = shuffled[2];
+  }
+  return SSB_OK;
+}
+
 int ssb_crop_bbox(ssb_ransac* r, const void* msg, const ssb_cloud_layout* layout, const ssb_bbox* box, float* out) {
   if (!r || !msg || !layout || !box) return SSB_ERR_INVALID;
   ssb_ransac_opts o;

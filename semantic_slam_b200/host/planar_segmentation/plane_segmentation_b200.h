@@ -8,7 +8,6 @@
 #ifndef SSB_PLANE_SEGMENTATION_B200_H
 #define SSB_PLANE_SEGMENTATION_B200_H
 
-#include <random>
 #include <string>
 #include <vector>
 
@@ -31,9 +30,10 @@ class plane_segmentation_b200 {
   }
 
   // pcl::SACSegmentation(SACMODEL_PLANE, SAC_RANSAC, 0.01, optimize) over every bbox.
-  // n_hyp = 0 -> PCL's STOPPING RULE (adaptive k, <= 50 iterations).  The 3-point samples come from std::mt19937(12345)
-  // modulo n, not from pcl::RandomSampleConsensus' boost::mt19937 + drawIndexSample shuffle (boost is absent here), so
-  // PCL's hypothesis sequence itself is not reproduced — pass your own index triples to ssb_ransac_plane_batch for that.
+  // n_hyp = 0 -> PCL's behaviour: its stopping rule (adaptive k, <= 50 iterations) on ITS sample stream — every crop gets
+  // a fresh model like the `seg` object of compute2DConvexHull (:637), i.e. boost::mt19937(12345u) through
+  // uniform_int<>(0, INT_MAX) and drawIndexSample's running shuffle (ssb_ransac_pcl_samples).  n_hyp > 0 -> score exactly
+  // n_hyp hypotheses of that same stream, first best wins.
   std::vector<ssb_plane_result> fitPlanes(const void* cloud_data, const ssb_cloud_layout& layout,
                                           const std::vector<ssb_bbox>& boxes, int n_hyp = 0,
                                           std::vector<unsigned char>* inlier_mask = nullptr) {
@@ -42,13 +42,13 @@ class plane_segmentation_b200 {
     int K = n_hyp;
     if (K <= 0) {
       o.mode = 1;
-      K = 512;  // sample stream long enough for 50 valid iterations + skipped samples
+      K = 512;  // 51 evaluated hypotheses at most + the draws PCL would reject and repeat (collinear samples)
     }
     std::vector<int> triples((size_t)3 * K * boxes.size());
     for (size_t b = 0; b < boxes.size(); ++b) {
-      std::mt19937 rng(12345u);
-      const long long n = (long long)boxes[b].width * boxes[b].height;
-      for (int k = 0; k < 3 * K; ++k) triples[3 * K * b + k] = n > 0 ? (int)(rng() % (unsigned long long)n) : 0;
+      const bool spurious = boxes[b].width < 0 || boxes[b].height < 0;
+      const long long n = spurious ? 0 : (long long)boxes[b].width * boxes[b].height;
+      ssb_ransac_pcl_samples((int)n, K, 12345u, &triples[(size_t)3 * K * b]);
     }
     std::vector<ssb_plane_result> res(boxes.size());
     if (inlier_mask) {   // concatenated over the non-spurious boxes

@@ -28,6 +28,22 @@ class CloudLayout:
         return _lib.CloudLayoutC(self.width, self.height, self.point_step, self.row_step, *self.offsets)
 
 
+def pcl_sample_stream(n_points, n_draws, seed=12345):
+    """The 3-point sample stream pcl::RandomSampleConsensus draws for a fresh model over `n_points` points
+    (ssb_ransac_pcl_samples: boost::mt19937(seed) >> 1, drawIndexSample's running shuffle; host only).
+    n_points: int or a sequence (one crop each) -> int32 [n_draws, 3] or [n_crops, n_draws, 3]."""
+    L = _lib.lib()
+    if np.ndim(n_points) == 0:
+        out = np.zeros((n_draws, 3), dtype=np.int32)
+        check(L.ssb_ransac_pcl_samples(int(n_points), int(n_draws), int(seed), out.ctypes.data), "ssb_ransac_pcl_samples")
+        return out
+    ns = [int(v) for v in n_points]
+    out = np.zeros((len(ns), n_draws, 3), dtype=np.int32)
+    for b, n in enumerate(ns):
+        check(L.ssb_ransac_pcl_samples(n, int(n_draws), int(seed), out[b].ctypes.data), "ssb_ransac_pcl_samples")
+    return out
+
+
 class PlaneSegmentation:
     """plane_segmentation (the RANSAC part): persistent device buffers + stream."""
 
@@ -112,6 +128,18 @@ class PlaneSegmentation:
                                              counts.ctypes.data if counts is not None else None,
                                              mask.ctypes.data if mask is not None else None), "ssb_ransac_plane_batch")
         return res, counts, (mask[:total] if mask is not None else None)
+
+    def fit_planes_pcl(self, msg, layout: CloudLayout, boxes, want_mask=True, n_draws=512):
+        """pcl::SACSegmentation's own behaviour per crop (what compute2DConvexHull runs, plane_segmentation.cpp:637-647):
+        PCL's sample stream (a fresh model per crop, seed 12345) under PCL's adaptive stopping rule — the handle must have
+        been created with mode=1.  Spurious boxes get an unused stream of zeros."""
+        if self.opts.mode != 1:
+            raise ValueError("fit_planes_pcl needs PlaneSegmentation(mode=1) (PCL's adaptive stopping rule)")
+        boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 4)
+        n = np.where((boxes[:, 2] >= 0) & (boxes[:, 3] >= 0), boxes[:, 2].astype(np.int64) * boxes[:, 3], 0)
+        triples = pcl_sample_stream(n, n_draws)
+        res, _, mask = self.fit_planes(msg, layout, boxes, triples, want_counts=False, want_mask=want_mask)
+        return res, mask, triples
 
     # ---- device-resident variant (benchmark `value` leg) --------------------------------------
     def upload(self, msg, layout: CloudLayout, boxes, triples):

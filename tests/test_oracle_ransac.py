@@ -90,3 +90,57 @@ def test_golden_ransac_fixture():
     assert np.array_equal(counts, d["counts"]) and np.array_equal(res["best_hyp"], d["best_hyp"])
     assert np.array_equal(res["coef"].view(np.uint32), d["coef"].view(np.uint32))
     assert np.array_equal(np.packbits(mask), d["mask"])
+
+
+def test_mt19937_known_answer_and_boost_uniform_int():
+    """the pure-Python engine behind the oracle's PCL sampler: C++11's known answer for mt19937 (10000th output of the
+    default-seeded engine), and boost's bucket rule (uniform_int<>(0, INT_MAX) = output >> 1, small ranges by division)"""
+    e = oracle._MT19937(5489)
+    for _ in range(9999):
+        e()
+    assert e() == 4123659995
+    a, b = oracle._MT19937(12345), oracle._MT19937(12345)
+    assert [oracle._boost_uniform_int(a, 0, 2**31 - 1) for _ in range(64)] == [b() >> 1 for _ in range(64)]
+    c = oracle._MT19937(7)
+    assert all(0 <= oracle._boost_uniform_int(c, 0, 5) <= 5 for _ in range(1000))
+
+
+def test_pcl_sample_stream_product_vs_oracle():
+    """ssb_ransac_pcl_samples (the product's host code: std::mt19937, C++) against the oracle's independent pure-Python
+    restatement of PCL's drawIndexSample: bit-exact, plus what the shuffle guarantees (three distinct indices per draw,
+    the shuffle state carried from draw to draw)"""
+    from semantic_slam_b200 import pcl_sample_stream
+    for n, k, seed in ((3, 8, 12345), (4, 40, 12345), (10, 64, 12345), (14000, 512, 12345), (307200, 64, 12345), (977, 100, 99)):
+        t = pcl_sample_stream(n, k, seed)
+        assert t.dtype == np.int32 and t.shape == (k, 3)
+        assert np.array_equal(t, oracle.pcl_sample_stream(n, k, seed)), (n, k, seed)
+        assert t.min() >= 0 and t.max() < n
+        assert np.all((t[:, 0] != t[:, 1]) & (t[:, 1] != t[:, 2]) & (t[:, 0] != t[:, 2]))
+    # first draw by hand: shuffled = 0..n-1, rnd_i = mt() >> 1, swap(i, i + rnd_i % (n - i))
+    e = oracle._MT19937(12345)
+    n = 1000
+    sh = list(range(n))
+    for i in range(3):
+        j = i + (e() >> 1) % (n - i)
+        sh[i], sh[j] = sh[j], sh[i]
+    assert list(pcl_sample_stream(n, 1)[0]) == sh[:3]
+    assert np.array_equal(pcl_sample_stream(2, 5), np.zeros((5, 3), np.int32))      # PCL selects no sample
+    batch = pcl_sample_stream([10, 0, 5000], 16)
+    assert batch.shape == (3, 16, 3) and np.array_equal(batch[0], pcl_sample_stream(10, 16)) and not batch[1].any()
+
+
+def test_adaptive_mode_on_the_pcl_sample_stream():
+    """PCL behaviour end to end on the CPU side: the oracle's adaptive RANSAC fed with PCL's own sample stream finds the
+    plane of a planar crop within the 50-iteration cap"""
+    rng = np.random.default_rng(1)
+    cl = synth.make_cloud(n_boxes=2, n_hyp=8, seed=11)
+    pc = cl.msg.view(np.float32).reshape(cl.height, cl.width, 8)
+    u, v = np.meshgrid(np.arange(cl.width), np.arange(cl.height))
+    X = ((u - 319.5) / 525 * 2).astype(np.float32); Y = ((v - 239.5) / 525 * 2).astype(np.float32)
+    pc[..., 0], pc[..., 1], pc[..., 2] = X, Y, (2 - 0.2 * X + 0.1 * Y + rng.normal(0, 5e-4, X.shape)).astype(np.float32)
+    n = cl.boxes[:, 2].astype(np.int64) * cl.boxes[:, 3]
+    tri = np.stack([oracle.pcl_sample_stream(int(m), 512) for m in n])
+    res, counts, _ = oracle.ransac_plane_batch(cl.msg, cl.width, cl.height, cl.point_step, cl.row_step, cl.offsets, cl.boxes, tri,
+                                               mode=1)
+    assert np.all(res["status"] == 0) and np.all(res["iterations"] <= 51)
+    assert np.all(res["refined_count"] > 0.95 * res["n_points"])

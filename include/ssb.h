@@ -390,8 +390,8 @@ typedef struct ssb_cluster_opts {
   int min_cluster_points;        /* 500: a distance cluster is kept when it has MORE points (:419) */
   float centroid_tolerance;      /* 0.3: filterCentroids keeps normals within +-0.3 per component of the horizontal normal (:511-516) */
   int ransac_hypotheses;         /* 0 = PCL's adaptive stopping rule on a 512-sample stream; > 0 = score that many */
-  unsigned ransac_seed;          /* 12345: std::mt19937(seed) % n draws the 3-point samples of every cluster (PCL's own
-                                    boost::mt19937 + drawIndexSample stream is not reproduced) */
+  unsigned ransac_seed;          /* 12345: seed of PCL's sample stream (ssb_ransac_pcl_samples), restarted for every cluster
+                                    like the pcl::SACSegmentation object compute2DConvexHull builds per call (:637) */
   int reserved[4];
 } ssb_cluster_opts;
 

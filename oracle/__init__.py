@@ -390,6 +390,16 @@ def _boost_uniform_int(engine, lo, hi):
             return lo + r
 
 
+def pcl_sample_stream_c(n_points, n_draws, seed=12345):
+    """the C++ twin of pcl_sample_stream used inside the oracle's clustering chain (oracle_ransac.cpp, own engine)"""
+    out = np.zeros((n_draws, 3), dtype=np.int32)
+    f = lib().orc_pcl_sample_stream
+    f.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_void_p]
+    f.restype = None
+    f(int(n_points), int(n_draws), int(seed), out.ctypes.data)
+    return out
+
+
 def pcl_sample_stream(n_points, n_draws, seed=12345):
     """pcl::SampleConsensusModel::drawIndexSample, n_draws times on a fresh model over n_points points
     (pcl/sample_consensus/sac_model.h): shuffled_indices_ starts as 0..n-1 and keeps its state between draws; every draw

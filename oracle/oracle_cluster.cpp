@@ -320,8 +320,8 @@ struct OrcPlaneCluster {   // must match ssb_plane_cluster in include/ssb.h
 };
 
 // plane_segmentation::clusterAndSegmentAllPlanes (:261-294).  cloud4 / normals4: n records of 4 floats (x y z rgb / nx ny nz
-// curvature); T16: transformation_mat, row-major.  RANSAC sample stream per cluster: std::mt19937(seed) % n like the product's
-// facade (PCL's own boost::mt19937 stream is not reproducible here); n_hyp = 0: PCL's adaptive stopping rule on a 512-sample stream.
+// curvature); T16: transformation_mat, row-major.  RANSAC sample stream per cluster: PCL's own (orcr::pcl_sample_stream, a fresh
+// model per compute2DConvexHull call); n_hyp = 0: PCL's adaptive stopping rule on a 512-draw stream.
 // coef_override (4 floats per cluster, may be null): use these planes for ProjectInliers + ConvexHull instead of the oracle's own
 // refined ones (the GPU's refine differs in summation order, compared at 1e-5: the hull stage is checked on identical planes).
 // labels_out: n ints (first k-means, -1 where the normal is NaN) or null; centers_out: Kn x 3 or null.
@@ -398,8 +398,7 @@ int orc_cluster_planes(const float* cloud4, const float* normals4, int n, const 
       // compute2DConvexHull :631-664
       const int K = n_hyp > 0 ? n_hyp : 512;
       std::vector<int> tri((size_t)3 * K);
-      std::mt19937 gen(seed);
-      for (int k = 0; k < 3 * K; ++k) tri[k] = (int)(gen() % (unsigned long long)np);
+      orcr::pcl_sample_stream(np, K, seed, tri.data());
       orcr::PlaneResult R;
       std::memset(&R, 0, sizeof(R));
       R.n_points = np;

@@ -61,6 +61,56 @@ static bool model_from_triple(const float* pts, const int* tri, float* coef) {
   return true;
 }
 
+// PCL's sample stream (pcl/sample_consensus/sac_model.h): the model owns a boost::mt19937 seeded with 12345u (unless
+// `random`), read through boost::uniform_int<>(0, INT_MAX), and drawIndexSample shuffles the head of shuffled_indices_
+// (initially 0..n-1, state kept between draws):  for i in 0..2: swap(sh[i], sh[i + rnd() % (n - i)]);  sample = sh[0..2].
+// The engine is written out here (Matsumoto & Nishimura; init_genrand seeding) so that the oracle shares nothing with
+// the product's std::mt19937; boost's generate_uniform_int maps a 32-bit engine onto [0, INT_MAX] by dividing by the
+// bucket size 2 (0xffffffff / 0x80000000 = 1, +1 because the remainder equals the range).
+namespace {
+struct Mt19937 {
+  uint32_t mt[624];
+  int idx;
+  explicit Mt19937(uint32_t seed) {
+    mt[0] = seed;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    idx = 624;
+  }
+  uint32_t next() {
+    if (idx >= 624) {
+      for (int k = 0; k < 624; ++k) {
+        uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+        mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+};
+}  // namespace
+
+void pcl_sample_stream(int n, int n_draws, unsigned seed, int* triples) {
+  if (n < 3) {
+    for (int k = 0; k < 3 * n_draws; ++k) triples[k] = 0;
+    return;
+  }
+  Mt19937 eng(seed);
+  std::vector<int> sh(n);
+  for (int i = 0; i < n; ++i) sh[i] = i;
+  for (int d = 0; d < n_draws; ++d) {
+    for (int i = 0; i < 3; ++i) {
+      const uint32_t rnd = eng.next() / 2u;
+      std::swap(sh[i], sh[i + (int)(rnd % (uint32_t)(n - i))]);
+    }
+    for (int i = 0; i < 3; ++i) triples[3 * d + i] = sh[i];
+  }
+}
+
 static int count_within(const float* pts, int n, const float* coef, float thr_eff) {
   int c = 0;
   for (int i = 0; i < n; ++i) {
@@ -306,6 +356,8 @@ void orc_ransac_points(const float* pts, int n, const int* tri, int K, double th
 }
 
 extern "C" {
+
+void orc_pcl_sample_stream(int n, int n_draws, unsigned seed, int* triples) { orcr::pcl_sample_stream(n, n_draws, seed, triples); }
 
 int orc_crop(const void* msg, int width, int height, int point_step, int row_step, const int* offsets4,
              const int* box4, float* out) {

@@ -34,7 +34,8 @@ static inline float effective_threshold(double thr) {
   return t;
 }
 
-// SampleConsensusModelPlane::computeModelCoefficients. pts: xyz triplets (stride 4 floats).
+// pcl::SampleConsensusModel::drawIndexSample, n_draws times on a fresh model over n points (see oracle_ransac.cpp)
+void pcl_sample_stream(int n, int n_draws, unsigned seed, int* triples);
 }  // namespace orcr
 
 // pcl::SACSegmentation (SACMODEL_PLANE, SAC_RANSAC) on one point set (float4 records), see oracle_ransac.cpp

@@ -1328,10 +1328,9 @@ int ssb_cluster_planes(ssb_ransac* r, const float* cloud4, const float* normals4
     const size_t nh = (size_t)ncl * K;
     if ((rc = r->d_triples.ensure(3 * nh)) || (rc = r->d_valid.ensure(nh)) || (rc = r->d_counts.ensure(nh)) || (rc = r->d_hyp.ensure(nh))) return rc;
     std::vector<int> tri(3 * nh);
-    for (int b = 0; b < ncl; ++b) {
-      std::mt19937 gen(o.ransac_seed);
-      for (int k = 0; k < 3 * K; ++k) tri[(size_t)3 * K * b + k] = (int)(gen() % (unsigned long long)kept[b].np);
-    }
+    // every compute2DConvexHull call builds its own pcl::SACSegmentation (:637): a fresh model, i.e. PCL's sample stream
+    // from its seed for every cluster
+    for (int b = 0; b < ncl; ++b) ssb_ransac_pcl_samples(kept[b].np, K, o.ransac_seed, &tri[(size_t)3 * K * b]);
     SSB_CUDA_CHECK(cudaMemcpyAsync(r->d_triples.p, tri.data(), tri.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     for (int b = 0; b < ncl; ++b)
       SSB_CUDA_CHECK(cudaMemcpyAsync(r->d_crop.p + r->boxes[b].pt_off, r->c_pts.p + kept[b].off, (size_t)kept[b].np * sizeof(float4), cudaMemcpyDeviceToDevice, s));

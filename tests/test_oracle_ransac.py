@@ -114,6 +114,7 @@ def test_pcl_sample_stream_product_vs_oracle():
         t = pcl_sample_stream(n, k, seed)
         assert t.dtype == np.int32 and t.shape == (k, 3)
         assert np.array_equal(t, oracle.pcl_sample_stream(n, k, seed)), (n, k, seed)
+        assert np.array_equal(t, oracle.pcl_sample_stream_c(n, k, seed)), (n, k, seed)   # the oracle chain's C++ twin
         assert t.min() >= 0 and t.max() < n
         assert np.all((t[:, 0] != t[:, 1]) & (t[:, 1] != t[:, 2]) & (t[:, 0] != t[:, 2]))
     # first draw by hand: shuffled = 0..n-1, rnd_i = mt() >> 1, swap(i, i + rnd_i % (n - i))

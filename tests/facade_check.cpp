@@ -141,7 +141,13 @@ int main(int argc, char** argv) {
   if (!gs.computeLandmarkMarginals(spinv, {{hi, hi}})) return 7;
   if (!spinv.block(hi, hi)) return 8;
   const MatrixXd cov = spinv.block(hi, hi)->eval();
-  if (!(cov(0, 0) > 0 && cov(1, 1) > 0 && cov(2, 2) > 0) || std::fabs(cov(0, 1) - cov(1, 0)) > 1e-9 * cov(0, 0)) return 9;
+  // every column is its own PCG solve (pcg_tol 1e-8): symmetric up to that tolerance, not bit for bit
+  const double dmax = std::fmax(cov(0, 0), std::fmax(cov(1, 1), cov(2, 2)));
+  if (!(cov(0, 0) > 0 && cov(1, 1) > 0 && cov(2, 2) > 0) || std::fabs(cov(0, 1) - cov(1, 0)) > 1e-5 * dmax) {
+    std::printf("landmark covariance: [%g %g %g; %g %g %g; %g %g %g]\n", cov(0, 0), cov(0, 1), cov(0, 2), cov(1, 0), cov(1, 1), cov(1, 2),
+                cov(2, 0), cov(2, 1), cov(2, 2));
+    return 9;
+  }
   Isometry3d last = kf.back()->estimate();
   std::printf("last keyframe x = %.6f (expect 5.5), hessianIndex(first)=%d id(last)=%d, landmark covariance xx = %.3e\n", x_of(last),
               kf[0]->hessianIndex(), kf.back()->id(), cov(0, 0));

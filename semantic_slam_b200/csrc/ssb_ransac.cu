@@ -522,6 +522,8 @@ struct ssb_ransac {
   bool uploaded = false;
   long long launches = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // run begin/end, k_count begin/end
+  unsigned char* h_mask_stage = nullptr;   // page-locked landing buffer of the padded inlier mask (ssb_ransac_fetch)
+  size_t h_mask_cap = 0;
   // organised multi-plane segmentation (ssb_organized.cuh)
   RBuf<ssb_org::OrgBox> d_oboxes;
   RBuf<unsigned char> d_change;
@@ -679,6 +681,7 @@ void ssb_ransac_destroy(ssb_ransac* r) {
   }
   for (int k = 0; k < 4; ++k)
     if (r->ev[k]) cudaEventDestroy(r->ev[k]);
+  if (r->h_mask_stage) cudaFreeHost(r->h_mask_stage);
   delete r;
 }
 
@@ -733,10 +736,18 @@ int ssb_ransac_fetch(ssb_ransac* r, ssb_plane_result* results, int* counts, unsi
   const int nb = r->nb, K = r->K;
   if (results && nb) SSB_CUDA_CHECK(cudaMemcpyAsync(results, r->d_results.p, nb * sizeof(ssb_plane_result), cudaMemcpyDeviceToHost, r->stream));
   if (counts && nb && K) SSB_CUDA_CHECK(cudaMemcpyAsync(counts, r->d_counts.p, (size_t)nb * K * sizeof(int), cudaMemcpyDeviceToHost, r->stream));
-  std::vector<unsigned char> tmp;
   if (mask && r->total_pts) {
-    tmp.resize(r->total_pts);
-    SSB_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), r->d_mask.p, r->total_pts, cudaMemcpyDeviceToHost, r->stream));
+    // the padded mask lands in a page-locked buffer owned by the handle (a pageable landing buffer made the copy a
+    // staged, synchronous one and cost a fresh 0.9 MB allocation per frame)
+    if ((size_t)r->total_pts > r->h_mask_cap) {
+      if (r->h_mask_stage) cudaFreeHost(r->h_mask_stage);
+      r->h_mask_stage = nullptr;
+      r->h_mask_cap = 0;
+      const size_t cap = (size_t)r->total_pts + (size_t)r->total_pts / 4 + 4096;
+      SSB_CUDA_CHECK(cudaMallocHost((void**)&r->h_mask_stage, cap));
+      r->h_mask_cap = cap;
+    }
+    SSB_CUDA_CHECK(cudaMemcpyAsync(r->h_mask_stage, r->d_mask.p, r->total_pts, cudaMemcpyDeviceToHost, r->stream));
   }
   SSB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
   if (mask && r->total_pts) {
@@ -744,7 +755,7 @@ int ssb_ransac_fetch(ssb_ransac* r, ssb_plane_result* results, int* counts, unsi
     size_t o = 0;
     for (int b = 0; b < nb; ++b) {
       if (r->boxes[b].n > 0) {
-        std::memcpy(mask + o, tmp.data() + r->mask_off[b], r->boxes[b].n);
+        std::memcpy(mask + o, r->h_mask_stage + r->mask_off[b], r->boxes[b].n);
         o += r->boxes[b].n;
       }
     }

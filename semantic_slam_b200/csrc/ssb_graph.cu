@@ -26,6 +26,7 @@
 #include "ssb_graph_kernels.cuh"
 #include "ssb_peer.cuh"
 #include "ssb_pcg_flow.cuh"
+#include "ssb_marg_direct.cuh"
 
 // ---- NCCL, resolved at run time (the library the process already loaded — torch's — else libnccl.so.2).
 // Minimal declarations of the stable C ABI; nothing links against libnccl at build time.
@@ -304,6 +305,10 @@ struct ssb_graph {
   DBuf<double> d_Hpp, d_bp, d_Hoff, d_Hll, d_bl, d_HplL, d_HplP, d_HllInv, d_Dinv, d_g;
   DBuf<double> d_x, d_r, d_z, d_p0, d_p1, d_q, d_v, d_dl, d_part, d_scalars, d_tmp;
   DBuf<int> d_iscalars, d_ainv_ok;
+  // landmark marginals, direct form (ssb_marg_direct.cuh)
+  DBuf<double> md_Bsub, md_Ginv, md_Esub, md_Y, md_T, md_Row, md_ColT, md_Pinv, md_out;
+  DBuf<int> md_k0, md_status, md_lidx;
+  PinnedBuf<int> md_hstatus;
   // coarse level
   DBuf<double> d_Bmat, d_Grun, d_panel, d_B1mat, d_D1inv, d_ainv, d_ctacen;
   bool ainv_valid = false;   // d_ainv holds the rows of a previously inverted coarse matrix
@@ -2482,6 +2487,96 @@ static int lm_loop(ssb_graph* g, int max_iterations, ssb_lm_stats* st) {
   return SSB_OK;
 }
 
+// ---- landmark marginals, direct form (ssb_marg_direct.cuh): applies when every pose-pose edge joins consecutive keyframes ----
+namespace {
+struct MdCudaLauncher {
+  cudaStream_t s;
+  long long* launches;
+  template <class K, class... A>
+  void operator()(K kern, int gx, int gy, int block, A... args) {
+    kern<<<dim3((unsigned)gx, (unsigned)gy), block, 0, s>>>(args...);
+    ++*launches;
+  }
+  void zero(void* p, size_t n) { cudaMemsetAsync(p, 0, n, s); }
+};
+}  // namespace
+// returns 1 (done), 0 (the factorisation met a non-positive pivot: the caller falls back to the iterative path, which reports
+// the failure in its own terms), -100 (not applicable), or a negative error
+static int marginals_direct(ssb_graph* g, const int* vids, int n, double* out9n) {
+  if (const char* e = std::getenv("SSB_MARG_DIRECT"))
+    if (std::atoi(e) == 0) return -100;
+  if (g->mr || !g->ll.empty() || g->rep_count > 1) return -100;
+  const DevGraph& G = g->G;
+  if (G.Np < 1 || G.Nl < 1 || G.El < 1 || G.pose_kind != nullptr) return -100;
+  for (const PPEdge& e : g->pp)
+    if (e.i - e.j != 1 && e.j - e.i != 1) return -100;   // a loop closure: H_pp is not block tridiagonal
+  const ssb_md::MdDims d = ssb_md::md_dims(G.Np, G.Nl);
+  {
+    double limit_gb = 16.0;
+    if (const char* e = std::getenv("SSB_MARG_DIRECT_MAX_GB")) limit_gb = std::atof(e);
+    const double need = 8.0 * ((double)d.K * d.ld + (double)d.ld * d.ld + 2.0 * ssb_md::TB * d.ld + 108.0 * d.Np);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return -100;
+    const double held = 8.0 * (double)(g->md_Y.cap + g->md_T.cap);
+    if (need > limit_gb * 1e9 || need > 0.8 * ((double)free_b + held)) return -100;
+  }
+  if (!g->have_system) SSB_TRY(launch_linearize(g));   // else: the system built by the last optimize (g2o semantics)
+  SSB_TRY(g->md_Bsub.ensure((size_t)36 * d.Np));
+  SSB_TRY(g->md_Ginv.ensure((size_t)36 * d.Np));
+  SSB_TRY(g->md_Esub.ensure((size_t)36 * d.Np));
+  SSB_TRY(g->md_Y.ensure((size_t)d.K * d.ld));
+  SSB_TRY(g->md_T.ensure((size_t)d.ld * d.ld));
+  SSB_TRY(g->md_Row.ensure((size_t)ssb_md::TB * d.ld));
+  SSB_TRY(g->md_ColT.ensure((size_t)ssb_md::TB * d.ld));
+  SSB_TRY(g->md_Pinv.ensure((size_t)ssb_md::TB * ssb_md::TB));
+  SSB_TRY(g->md_out.ensure((size_t)9 * n));
+  SSB_TRY(g->md_k0.ensure(d.nt));
+  SSB_TRY(g->md_status.ensure(2));
+  SSB_TRY(g->md_lidx.ensure(n));
+  SSB_TRY(g->md_hstatus.ensure(2));
+  std::vector<int> lidx(n);
+  for (int k = 0; k < n; ++k) lidx[k] = g->V[vids[k]].idx;
+  cudaStream_t s = g->stream;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(g->md_lidx.p, lidx.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+  ssb_md::MdBuffers b{};
+  b.pose_pp_rowptr = G.pose_pp_rowptr;
+  b.pose_pp_idx = G.pose_pp_idx;
+  b.pose_pp_other = G.pose_pp_other;
+  b.Hoff = G.Hoff;
+  b.Hpp = G.Hpp;
+  b.Hll = G.Hll;
+  b.HplL = G.HplL;
+  b.edge_pose = reinterpret_cast<const int*>(G.pl);   // PLEdge::p is the first int of the 80-byte record
+  b.edge_stride = (int)(sizeof(PLEdge) / sizeof(int));
+  b.lm_rowptr = G.lm_rowptr;
+  b.lidx = g->md_lidx.p;
+  b.n_req = n;
+  b.Bsub = g->md_Bsub.p;
+  b.Ginv = g->md_Ginv.p;
+  b.Esub = g->md_Esub.p;
+  b.Y = g->md_Y.p;
+  b.T = g->md_T.p;
+  b.Row = g->md_Row.p;
+  b.ColT = g->md_ColT.p;
+  b.Pinv = g->md_Pinv.p;
+  b.tile_k0 = g->md_k0.p;
+  b.status = g->md_status.p;
+  b.out9n = g->md_out.p;
+  MdCudaLauncher L{s, &g->launches};
+  ssb_md::md_run(L, d, b);
+  SSB_CUDA_CHECK(cudaGetLastError());
+  SSB_CUDA_CHECK(cudaMemcpyAsync(out9n, g->md_out.p, (size_t)9 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(g->md_hstatus.p, g->md_status.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  SSB_TRY(stream_wait(g));
+  if (std::getenv("SSB_MARG_DEBUG"))
+    std::fprintf(stderr, "[ssb marginals] direct form: %d keyframes, %d landmarks, T %d x %d (%d tiles), Y %d rows, status %d %d\n", d.Np, d.Nl,
+                 d.ld, d.ld, d.nt, d.K, g->md_hstatus.p[0], g->md_hstatus.p[1]);
+  if (g->md_hstatus.p[0] != 0 || g->md_hstatus.p[1] != 0) return 0;
+  for (int k = 0; k < 9 * n; ++k)
+    if (!std::isfinite(out9n[k])) return 0;
+  return 1;
+}
+
 extern "C" {
 
 static bool is_sharded(const ssb_graph* g) { return g->comm_world > 1; }
@@ -3104,6 +3199,11 @@ int ssb_graph_landmark_marginals(ssb_graph* g, const int* vids, int n, double* o
   if (is_sharded(g)) return marginals_sharded(g, vids, n, out9n);
   SSB_TRY(prepare(g));
   if (n == 0) return 1;
+  {
+    const int rd = marginals_direct(g, vids, n, out9n);
+    if (rd == 1) return 1;
+    if (rd < 0 && rd != -100) return rd;
+  }
   {
     const MargRepPlan P = marg_replica_plan(g);
     if (P.k >= 2) {

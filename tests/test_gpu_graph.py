@@ -105,8 +105,11 @@ def test_lm_trajectory_cfg1(precond, generic):
     assert_parity(P, X, Po, Xo)
 
 
-def test_landmark_marginals_match_oracle():
-    """GraphSLAM::computeLandmarkMarginals (graph_slam.cpp:221-234): 3x3 blocks of H^-1 of the last built system"""
+@pytest.mark.parametrize("direct", ["1", "0"])
+def test_landmark_marginals_match_oracle(direct, monkeypatch):
+    """GraphSLAM::computeLandmarkMarginals (graph_slam.cpp:221-234): 3x3 blocks of H^-1 of the last built system; in the direct
+    form (poses eliminated, ssb_marg_direct.cuh) and by one PCG solve per column (SSB_MARG_DIRECT=0)"""
+    monkeypatch.setenv("SSB_MARG_DIRECT", direct)
     spec = synth.make_config_graph("cfg1")
     g, o, ids = _pair(spec, preconditioner=1, pcg_tol=1e-12)
     assert g.optimize(3) and o.optimize(3)
@@ -118,10 +121,11 @@ def test_landmark_marginals_match_oracle():
     assert g.hessian_index(lms[0]) == lms[0] - 1       # first vertex fixed -> index shifts by one
 
 
-@pytest.mark.parametrize("precond", [1, 3])
-def test_landmark_marginals_600_keyframes(precond):
-    """K5 on a per-frame-loop sized graph, after an optimize that stops on max_iterations (last step accepted: the system
+@pytest.mark.parametrize("precond,direct", [(1, "0"), (3, "0"), (3, "1")])
+def test_landmark_marginals_600_keyframes(precond, direct, monkeypatch):
+    """K5 on a per-frame-loop sized graph (iterative form and direct form), after an optimize that stops on max_iterations (last step accepted: the system
     was linearised one step behind the estimates) and after one that runs until g2o's LM terminates; then after growth."""
+    monkeypatch.setenv("SSB_MARG_DIRECT", direct)
     spec = synth.make_graph(600, 60, seed=31)
     for iters in (3, 40):
         g, o, ids = _pair(spec, preconditioner=precond, pcg_tol=1e-12)
@@ -149,6 +153,7 @@ def test_landmark_marginals_several_columns_per_launch(precond, monkeypatch):
     """K5 on a graph that fills a fraction of the chip: k copies of the graph side by side, one conjugate-gradient
     recurrence per copy inside one launch (k_pcg_flow<148, false, true>, marginals_replicated in ssb_graph.cu).  Checked
     against the oracle AND against the one-column-per-launch path; a ragged last batch and an idle copy included."""
+    monkeypatch.setenv("SSB_MARG_DIRECT", "0")     # this test is about the iterative path
     spec = synth.make_graph(600, 60, seed=31)
     g, o, ids = _pair(spec, preconditioner=precond, pcg_tol=1e-12)
     assert g.optimize(40) and o.optimize(40)
@@ -173,8 +178,11 @@ def test_landmark_marginals_several_columns_per_launch(precond, monkeypatch):
     assert np.abs(Ms[0] - Mg[2]).max() <= 1e-9 * np.abs(Mg[2]).max()
 
 
-def test_landmark_marginals_cfg2_sample():
-    """K5 at the headline size (10 000 keyframes: one column per launch) with the bench preconditioner"""
+@pytest.mark.parametrize("direct", ["1", "0"])
+def test_landmark_marginals_cfg2_sample(direct, monkeypatch):
+    """K5 at the headline size (10 000 keyframes): the direct form (a 5 958 x 5 958 landmark system) and one column per PCG
+    launch with the bench preconditioner"""
+    monkeypatch.setenv("SSB_MARG_DIRECT", direct)
     spec = synth.make_config_graph("cfg2")
     g, o, ids = _pair(spec, preconditioner=3, pcg_tol=1e-10)
     assert g.optimize(2) and o.optimize(2)
@@ -184,6 +192,43 @@ def test_landmark_marginals_cfg2_sample():
     Mo = o.computeLandmarkMarginals(lms, relinearize=False)
     assert Mg is not None
     assert np.abs(Mg - Mo).max() <= 1e-5 * np.abs(Mo).max(), np.abs(Mg - Mo).max() / np.abs(Mo).max()
+
+
+def test_landmark_marginals_direct_form():
+    """the direct form on its own terms: every landmark of a 600-keyframe graph to 1e-8 (no iterative tolerance involved), the
+    same bits on a second call, a subset asked in another order, the fall-back to the iterative path when a loop closure makes
+    H_pp more than block tridiagonal, and a graph that also holds plane landmarks"""
+    spec = synth.make_graph(600, 60, seed=31)
+    g, o, ids = _pair(spec, preconditioner=3, pcg_tol=1e-12)
+    assert g.optimize(40) and o.optimize(40)
+    lms = [int(ids[v]) for v in range(spec.vkind.size) if spec.vkind[v] == 1]
+    Mo = o.computeLandmarkMarginals(lms, relinearize=False, method="g2o")
+    Mg = g.computeLandmarkMarginals(lms)
+    assert Mg is not None
+    assert np.abs(Mg - Mo).max() <= 1e-8 * np.abs(Mo).max(), np.abs(Mg - Mo).max() / np.abs(Mo).max()
+    assert np.array_equal(Mg, g.computeLandmarkMarginals(lms))
+    sub = lms[::-7]
+    assert np.array_equal(g.computeLandmarkMarginals(sub), Mg[::-7])
+    # a loop closure between the first free and the last keyframe: not applicable any more, the PCG path answers
+    kf = [int(ids[v]) for v in range(spec.vkind.size) if spec.vkind[v] == 0]
+    rel = np.linalg.inv(np.vstack([o.get_se3(kf[5]), [0, 0, 0, 1]])) @ np.vstack([o.get_se3(kf[-1]), [0, 0, 0, 1]])
+    for b in (g, o):
+        b.add_se3_edge(kf[5], kf[-1], rel[:3], 10.0 * np.eye(6))
+    assert g.optimize(3) and o.optimize(3)
+    Mo2 = o.computeLandmarkMarginals(lms[:4], relinearize=False)
+    Mg2 = g.computeLandmarkMarginals(lms[:4])
+    assert np.abs(Mg2 - Mo2).max() <= 1e-6 * np.abs(Mo2).max()
+    # plane landmarks ride the same 3-DoF machinery
+    pspec = synth.make_plane_graph(16, 4, 4)
+    gp, op = GraphSLAM(preconditioner=3, pcg_tol=1e-12), oracle.OracleGraphSLAM()
+    idp = synth.load_plane_graph(gp, pspec)
+    synth.load_plane_graph(op, pspec)
+    assert gp.optimize(4) and op.optimize(4)
+    pts = [int(idp[v]) for v, vert in enumerate(pspec.vertices) if vert[0] == "xyz"]
+    if pts:
+        Mp = gp.computeLandmarkMarginals(pts)
+        Mpo = op.computeLandmarkMarginals(pts, relinearize=False)
+        assert np.abs(Mp - Mpo).max() <= 1e-4 * np.abs(Mpo).max()     # the oracle's plane Jacobians are numeric (g2o's)
 
 
 def test_g2o_save_load_roundtrip(tmp_path):

@@ -6,7 +6,8 @@
 // inverse of ONE dense matrix of size 3 Nl:
 //     (H^-1)_ll = T^-1,   T = H_ll - H_lp H_pp^-1 H_pl = H_ll - Y'Y,   Y = L^-1 H_pl,   H_pp = L L'  (L block bidiagonal)
 //   k_md_gather_sub : B_i = H(i, i-1) from the off-diagonal blocks of the pose-pose edges
-//   k_md_factor     : block-bidiagonal Cholesky of H_pp: G_i = L_ii^-1, E_i = L(i, i-1) (a sequential chain of 6 x 6 steps)
+//   k_md_factor     : block-bidiagonal Cholesky of H_pp: G_i = L_ii^-1, E_i = L(i, i-1) (a sequential chain of 6 x 6 steps, each
+//                     spread over 36 threads)
 //   k_md_sweep      : Y = L^-1 H_pl, one thread per column (landmark, component), rows before the landmark's first observer
 //                     stay zero
 //   k_md_gemm_tn    : C = beta C + alpha A'B on 64 x 64 tiles (A, B with the contraction index leading): T -= Y'Y (lower
@@ -60,64 +61,72 @@ __global__ void k_md_gather_sub(const int* __restrict__ pose_pp_rowptr, const in
   Bsub[t] = s;
 }
 
-// Block-bidiagonal Cholesky of the block-tridiagonal H_pp, one thread (the chain is sequential; 6 x 6 steps):
-//   E_i = B_i G_{i-1}',  A = H_ii - E_i E_i',  A = L L',  G_i = L^-1.   status[0] = 1 + i when A is not positive definite.
-__global__ void k_md_factor(const double* __restrict__ Hpp, const double* __restrict__ Bsub, int Np, double* __restrict__ Ginv,
-                            double* __restrict__ Esub, int* __restrict__ status) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double G[36];
-  for (int k = 0; k < 36; ++k) G[k] = 0.0;
+// Block-bidiagonal Cholesky of the block-tridiagonal H_pp.  The chain over the keyframes is sequential; inside a step the 6 x 6
+// work is spread over 36 threads of one CTA (thread k owns entry (k / 6, k % 6)), the inputs of the next step are fetched while
+// the current one runs:
+//   E_i = B_i G_{i-1}',  A = H_ii - E_i E_i',  A = L L' (column by column),  G_i = L^-1 (one thread per column).
+// status[0] = 1 + i when A is not positive definite.  (A single thread took 7 us per keyframe: dependent fp64 latencies.)
+__global__ void __launch_bounds__(64) k_md_factor(const double* __restrict__ Hpp, const double* __restrict__ Bsub, int Np,
+                                                  double* __restrict__ Ginv, double* __restrict__ Esub, int* __restrict__ status) {
+  __shared__ double Gs[36];
+  __shared__ double Es[36];
+  __shared__ double As[36];
+  __shared__ double Bs[36];
+  const int k = threadIdx.x;
+  const bool act = k < 36;
+  const int r = k / 6, c = k - 6 * r;
+  if (act) Gs[k] = 0.0;
+  double hn = act ? Hpp[k] : 0.0, bn = act ? Bsub[k] : 0.0;
   for (int i = 0; i < Np; ++i) {
-    double A[36], E[36];
-    for (int k = 0; k < 36; ++k) A[k] = Hpp[36 * (size_t)i + k];
-    if (i > 0) {
-      const double* Bk = Bsub + 36 * (size_t)i;
-      for (int r = 0; r < 6; ++r)
-        for (int c = 0; c < 6; ++c) {
-          double s = 0.0;
-          for (int q = 0; q <= c; ++q) s += Bk[6 * r + q] * G[6 * c + q];   // G lower triangular: G'(q, c) = G(c, q), q <= c
-          E[6 * r + c] = s;
-        }
-      for (int r = 0; r < 6; ++r)
-        for (int c = 0; c <= r; ++c) {
-          double s = 0.0;
-          for (int q = 0; q < 6; ++q) s += E[6 * r + q] * E[6 * c + q];
-          A[6 * r + c] -= s;
-        }
-    } else {
-      for (int k = 0; k < 36; ++k) E[k] = 0.0;
+    const double h = hn;
+    if (act) Bs[k] = bn;
+    if (act && i + 1 < Np) {
+      hn = Hpp[36 * (size_t)(i + 1) + k];
+      bn = Bsub[36 * (size_t)(i + 1) + k];
     }
-    // Cholesky of the lower triangle of A, in place
-    bool bad = false;
-    for (int c = 0; c < 6; ++c) {
-      double d = A[6 * c + c];
-      for (int q = 0; q < c; ++q) d -= A[6 * c + q] * A[6 * c + q];
-      if (!(d > 0.0)) {
-        bad = true;
-        d = 1.0;
-      }
-      const double l = sqrt(d), il = 1.0 / l;
-      A[6 * c + c] = l;
-      for (int r = c + 1; r < 6; ++r) {
-        double s = A[6 * r + c];
-        for (int q = 0; q < c; ++q) s -= A[6 * r + q] * A[6 * c + q];
-        A[6 * r + c] = s * il;
-      }
+    __syncthreads();
+    double e = 0.0;
+    if (act && i > 0)
+      for (int q = 0; q <= c; ++q) e += Bs[6 * r + q] * Gs[6 * c + q];   // G lower triangular: G'(q, c) = G(c, q), q <= c
+    if (act) Es[k] = e;
+    __syncthreads();
+    if (act) {
+      double s = 0.0;
+      for (int q = 0; q < 6; ++q) s += Es[6 * r + q] * Es[6 * c + q];
+      As[k] = h - s;
     }
-    if (bad && status[0] == 0) status[0] = 1 + i;
-    // G = L^-1 (lower triangular), column by column
-    for (int k = 0; k < 36; ++k) G[k] = 0.0;
-    for (int c = 0; c < 6; ++c) {
-      G[6 * c + c] = 1.0 / A[6 * c + c];
-      for (int r = c + 1; r < 6; ++r) {
+    __syncthreads();
+    for (int cc = 0; cc < 6; ++cc) {
+      if (k == 7 * cc) {
+        double d = As[7 * cc];
+        for (int q = 0; q < cc; ++q) d -= As[6 * cc + q] * As[6 * cc + q];
+        if (!(d > 0.0)) {
+          if (status[0] == 0) status[0] = 1 + i;
+          d = 1.0;
+        }
+        As[7 * cc] = sqrt(d);
+      }
+      __syncthreads();
+      if (act && c == cc && r > cc) {
+        double s = As[6 * r + cc];
+        for (int q = 0; q < cc; ++q) s -= As[6 * r + q] * As[6 * cc + q];
+        As[6 * r + cc] = s / As[7 * cc];
+      }
+      __syncthreads();
+    }
+    if (k < 6) {   // column k of G = L^-1
+      for (int rr = 0; rr < k; ++rr) Gs[6 * rr + k] = 0.0;
+      Gs[7 * k] = 1.0 / As[7 * k];
+      for (int rr = k + 1; rr < 6; ++rr) {
         double s = 0.0;
-        for (int q = c; q < r; ++q) s += A[6 * r + q] * G[6 * q + c];
-        G[6 * r + c] = -s / A[6 * r + r];
+        for (int q = k; q < rr; ++q) s += As[6 * rr + q] * Gs[6 * q + k];
+        Gs[6 * rr + k] = -s / As[7 * rr];
       }
     }
-    for (int k = 0; k < 36; ++k) {
-      Ginv[36 * (size_t)i + k] = G[k];
-      Esub[36 * (size_t)i + k] = E[k];
+    __syncthreads();
+    if (act) {
+      Ginv[36 * (size_t)i + k] = Gs[k];
+      Esub[36 * (size_t)i + k] = Es[k];
     }
   }
 }
@@ -364,7 +373,7 @@ inline void md_run(Launcher& L, const MdDims& d, const MdBuffers& b) {
   L.zero(b.Y, (size_t)d.K * d.ld * sizeof(double));
   L.zero(b.T, (size_t)d.ld * d.ld * sizeof(double));
   L(k_md_gather_sub, (36 * d.Np + 255) / 256, 1, 256, b.pose_pp_rowptr, b.pose_pp_idx, b.pose_pp_other, b.Hoff, d.Np, b.Bsub);
-  L(k_md_factor, 1, 1, 32, b.Hpp, (const double*)b.Bsub, d.Np, b.Ginv, b.Esub, b.status);
+  L(k_md_factor, 1, 1, 64, b.Hpp, (const double*)b.Bsub, d.Np, b.Ginv, b.Esub, b.status);
   L(k_md_sweep, (d.n3 + 127) / 128, 1, 128, b.edge_pose, b.edge_stride, b.lm_rowptr, b.HplL, (const double*)b.Ginv, (const double*)b.Esub,
     d.Np, d.n3, b.Y, d.ld);
   L(k_md_tile_k0, (d.nt + 63) / 64, 1, 64, b.edge_pose, b.edge_stride, b.lm_rowptr, d.Nl, d.nt, d.K, b.tile_k0);

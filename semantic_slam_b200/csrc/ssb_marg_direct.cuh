@@ -28,6 +28,14 @@ namespace ssb_md {
 constexpr int TB = 64;      // tile edge of T
 constexpr int KC = 16;      // contraction chunk of the tile product
 
+__host__ __device__ inline double md_rsqrt(double d) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(d);
+#else
+  return 1.0 / sqrt(d);   // the CPU emulation (tests/md_emulate.cpp)
+#endif
+}
+
 struct MdGemm {
   double* C;
   int ldc;
@@ -72,6 +80,7 @@ __global__ void __launch_bounds__(64) k_md_factor(const double* __restrict__ Hpp
   __shared__ double Es[36];
   __shared__ double As[36];
   __shared__ double Bs[36];
+  __shared__ double Il[6];
   const int k = threadIdx.x;
   const bool act = k < 36;
   const int r = k / 6, c = k - 6 * r;
@@ -96,6 +105,8 @@ __global__ void __launch_bounds__(64) k_md_factor(const double* __restrict__ Hpp
       As[k] = h - s;
     }
     __syncthreads();
+    // fp64 sqrt and division are long dependent instruction sequences and they sit on the chain: one reciprocal square root per
+    // column (il = 1 / L_cc), everything else multiplies by it
     for (int cc = 0; cc < 6; ++cc) {
       if (k == 7 * cc) {
         double d = As[7 * cc];
@@ -104,23 +115,25 @@ __global__ void __launch_bounds__(64) k_md_factor(const double* __restrict__ Hpp
           if (status[0] == 0) status[0] = 1 + i;
           d = 1.0;
         }
-        As[7 * cc] = sqrt(d);
+        const double il = md_rsqrt(d);
+        Il[cc] = il;
+        As[7 * cc] = d * il;
       }
       __syncthreads();
       if (act && c == cc && r > cc) {
         double s = As[6 * r + cc];
         for (int q = 0; q < cc; ++q) s -= As[6 * r + q] * As[6 * cc + q];
-        As[6 * r + cc] = s / As[7 * cc];
+        As[6 * r + cc] = s * Il[cc];
       }
       __syncthreads();
     }
     if (k < 6) {   // column k of G = L^-1
       for (int rr = 0; rr < k; ++rr) Gs[6 * rr + k] = 0.0;
-      Gs[7 * k] = 1.0 / As[7 * k];
+      Gs[7 * k] = Il[k];
       for (int rr = k + 1; rr < 6; ++rr) {
         double s = 0.0;
         for (int q = k; q < rr; ++q) s += As[6 * rr + q] * Gs[6 * q + k];
-        Gs[6 * rr + k] = -s / As[7 * rr];
+        Gs[6 * rr + k] = -s * Il[rr];
       }
     }
     __syncthreads();
@@ -138,6 +151,9 @@ __global__ void __launch_bounds__(64) k_md_factor(const double* __restrict__ Hpp
 __global__ void __launch_bounds__(128) k_md_sweep(const int* __restrict__ edge_pose, int edge_stride, const int* __restrict__ lm_rowptr,
                                                   const double* __restrict__ HplL, const double* __restrict__ Ginv,
                                                   const double* __restrict__ Esub, int Np, int n3, double* __restrict__ Y, int ldY) {
+  // nothing that has to come from global memory sits on the chain: the landmark's NEXT edge (keyframe and its 6 entries) is
+  // held in registers one edge ahead, and the G / E blocks of the next 8 keyframes are fetched into registers while the
+  // current 8 are consumed from shared memory
   __shared__ double Gs[8][36];
   __shared__ double Es[8][36];
   const int col = blockIdx.x * 128 + threadIdx.x;
@@ -148,21 +164,44 @@ __global__ void __launch_bounds__(128) k_md_sweep(const int* __restrict__ edge_p
     e = lm_rowptr[l];
     end = lm_rowptr[l + 1];
   }
+  int next_p = -1;   // keyframe of edge e, or -1 when the landmark has no edge left
+  double hn[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (e < end) {
+    next_p = edge_pose[(size_t)edge_stride * e];
+    const double* Hl = HplL + 18 * (size_t)e + 6 * c;
+    for (int r = 0; r < 6; ++r) hn[r] = Hl[r];
+  }
+  // this thread's share of a chunk of 8 x 36 G and 8 x 36 E entries: positions threadIdx.x + 128 j, j = 0..4 (576 in all)
+  double pre[5];
+  for (int j = 0; j < 5; ++j) {
+    const int q = threadIdx.x + 128 * j;
+    pre[j] = 0.0;
+    if (q < 576) {
+      const int which = q / 288, qq = q - 288 * which, s = qq / 36, k = qq - 36 * s;
+      if (s < Np) pre[j] = (which == 0 ? Ginv : Esub)[36 * (size_t)s + k];
+    }
+  }
   double y[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   bool started = false;
   for (int i0 = 0; i0 < Np; i0 += 8) {
     __syncthreads();
-    for (int q = threadIdx.x; q < 8 * 36; q += 128) {
-      const int s = q / 36, k = q - 36 * s;
-      const bool in = i0 + s < Np;
-      Gs[s][k] = in ? Ginv[36 * (size_t)(i0 + s) + k] : 0.0;
-      Es[s][k] = in ? Esub[36 * (size_t)(i0 + s) + k] : 0.0;
+    for (int j = 0; j < 5; ++j) {
+      const int q = threadIdx.x + 128 * j;
+      if (q < 576) {
+        const int which = q / 288, qq = q - 288 * which, s = qq / 36, k = qq - 36 * s;
+        if (which == 0)
+          Gs[s][k] = pre[j];
+        else
+          Es[s][k] = pre[j];
+        const int in = i0 + 8 + s;
+        pre[j] = in < Np ? (which == 0 ? Ginv : Esub)[36 * (size_t)in + k] : 0.0;
+      }
     }
     __syncthreads();
     if (!live) continue;
     for (int s = 0; s < 8 && i0 + s < Np; ++s) {
       const int i = i0 + s;
-      const bool has = e < end && edge_pose[(size_t)edge_stride * e] == i;
+      const bool has = next_p == i;
       if (!started && !has) continue;   // rows before the first observer stay zero
       started = true;
       double t[6];
@@ -171,10 +210,16 @@ __global__ void __launch_bounds__(128) k_md_sweep(const int* __restrict__ edge_p
         for (int q = 0; q < 6; ++q) a += Es[s][6 * r + q] * y[q];
         t[r] = -a;
       }
-      while (e < end && edge_pose[(size_t)edge_stride * e] == i) {
-        const double* Hl = HplL + 18 * (size_t)e + 6 * c;
-        for (int r = 0; r < 6; ++r) t[r] += Hl[r];
+      while (next_p == i) {
+        for (int r = 0; r < 6; ++r) t[r] += hn[r];
         ++e;
+        if (e < end) {
+          next_p = edge_pose[(size_t)edge_stride * e];
+          const double* Hl = HplL + 18 * (size_t)e + 6 * c;
+          for (int r = 0; r < 6; ++r) hn[r] = Hl[r];
+        } else {
+          next_p = -1;
+        }
       }
       for (int r = 0; r < 6; ++r) {
         double a = 0.0;

@@ -59,9 +59,14 @@ def _problem(n_kf, n_lm, seed, its, flip_every=2):
     # pose-landmark edges in L-order (landmark-major, then by keyframe): one record per non-zero H(l, p) block
     lm_rowptr, edge_pose, HplL = [0], [], []
     Hc = H.tocsc()
+    owner = np.full(H.shape[0], -1, np.int64)                   # scalar row of H -> keyframe
+    for p_, pv in enumerate(pose_v):
+        if off[pv] >= 0:
+            owner[off[pv]:off[pv] + 6] = p_
     for l, v in enumerate(lm_v):
         rows = np.unique(Hc[:, off[v]:off[v] + 3].nonzero()[0])
-        ps = sorted({p for p, pv in enumerate(pose_v) if off[pv] >= 0 and np.any((rows >= off[pv]) & (rows < off[pv] + 6))})
+        ps = np.unique(owner[rows])
+        ps = [int(p_) for p_ in ps if p_ >= 0]
         for p in ps:
             edge_pose.append(p)
             HplL.append(blk(v, pose_v[p], 3, 6))
@@ -70,14 +75,19 @@ def _problem(n_kf, n_lm, seed, its, flip_every=2):
                 edge_pose=np.array(edge_pose, np.int32), Hoff=np.array(Hoff), Hpp=Hpp, Hll=Hll, HplL=np.array(HplL))
 
 
-def _run(exe, pr, req, tmp):
-    fin, fout = os.path.join(tmp, "p.bin"), os.path.join(tmp, "o.bin")
-    with open(fin, "wb") as f:
+def write_problem(pr, req, path):
+    """the binary layout tests/md_emulate.cpp and scripts/dbg/md_time.cu read"""
+    with open(path, "wb") as f:
         np.array([pr["Np"], pr["Nl"], pr["edge_pose"].size, pr["Hoff"].shape[0], pr["idx"].size, req.size], np.int32).tofile(f)
         for a in (pr["rowptr"], pr["idx"], pr["other"], pr["lm_rowptr"], pr["edge_pose"], req.astype(np.int32)):
             a.astype(np.int32).tofile(f)
         for a in (pr["Hoff"], pr["Hpp"], pr["Hll"], pr["HplL"]):
             np.ascontiguousarray(a, dtype=np.float64).tofile(f)
+
+
+def _run(exe, pr, req, tmp):
+    fin, fout = os.path.join(tmp, "p.bin"), os.path.join(tmp, "o.bin")
+    write_problem(pr, req, fin)
     out = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     status = np.fromfile(fout, dtype=np.int32, count=2)

@@ -6,8 +6,8 @@
 // inverse of ONE dense matrix of size 3 Nl:
 //     (H^-1)_ll = T^-1,   T = H_ll - H_lp H_pp^-1 H_pl = H_ll - Y'Y,   Y = L^-1 H_pl,   H_pp = L L'  (L block bidiagonal)
 //   k_md_gather_sub : B_i = H(i, i-1) from the off-diagonal blocks of the pose-pose edges
-//   k_md_factor     : block-bidiagonal Cholesky of H_pp: G_i = L_ii^-1, E_i = L(i, i-1) (a sequential chain of 6 x 6 steps, each
-//                     spread over 36 threads)
+//   k_md_factor     : block-bidiagonal Cholesky of H_pp: G_i = L_ii^-1, E_i = L(i, i-1) (a sequential chain of 6 x 6 steps, one
+//                     warp, rows in registers, shuffles)
 //   k_md_sweep      : Y = L^-1 H_pl, one thread per column (landmark, component), rows before the landmark's first observer
 //                     stay zero
 //   k_md_gemm_tn    : C = beta C + alpha A'B on 64 x 64 tiles (A, B with the contraction index leading): T -= Y'Y (lower
@@ -18,7 +18,7 @@
 // Cost O(Nl^2 Np) instead of 3 Nl latency-bound PCG solves; exact (no tolerance), deterministic.  Used when every pose-pose
 // edge joins consecutive keyframes (else ssb_graph_landmark_marginals keeps solving column by column).
 //
-// The kernels only use blockIdx / threadIdx / __shared__ / __syncthreads, and the launch sequence lives in md_run() behind a
+// The kernels only use blockIdx / threadIdx / __shared__ / __syncthreads (and __shfl_sync inside one single-warp CTA), and the launch sequence lives in md_run() behind a
 // launcher policy, so tests/md_emulate.cpp can run THIS source on the CPU (one std::thread per CUDA thread, one barrier per
 // CTA) and check it against the oracle where no GPU exists.
 #pragma once
@@ -28,6 +28,11 @@ namespace ssb_md {
 constexpr int TB = 64;      // tile edge of T
 constexpr int KC = 16;      // contraction chunk of the tile product
 
+#ifdef __CUDACC__
+#define MD_UNROLL _Pragma("unroll")
+#else
+#define MD_UNROLL
+#endif
 __host__ __device__ inline double md_rsqrt(double d) {
 #ifdef __CUDA_ARCH__
   return rsqrt(d);
@@ -69,78 +74,108 @@ __global__ void k_md_gather_sub(const int* __restrict__ pose_pp_rowptr, const in
   Bsub[t] = s;
 }
 
-// Block-bidiagonal Cholesky of the block-tridiagonal H_pp.  The chain over the keyframes is sequential; inside a step the 6 x 6
-// work is spread over 36 threads of one CTA (thread k owns entry (k / 6, k % 6)), the inputs of the next step are fetched while
-// the current one runs:
-//   E_i = B_i G_{i-1}',  A = H_ii - E_i E_i',  A = L L' (column by column),  G_i = L^-1 (one thread per column).
-// status[0] = 1 + i when A is not positive definite.  (A single thread took 7 us per keyframe: dependent fp64 latencies.)
-__global__ void __launch_bounds__(64) k_md_factor(const double* __restrict__ Hpp, const double* __restrict__ Bsub, int Np,
+// Block-bidiagonal Cholesky of the block-tridiagonal H_pp:  E_i = B_i G_{i-1}',  A = H_ii - E_i E_i' = L L',  G_i = L^-1.
+// The chain over the keyframes is sequential, so what counts is the latency of ONE step.  One warp, everything in registers,
+// lane r < 6 owns row r of the 6 x 6 blocks; rows travel between lanes by shuffles (no shared memory, no barrier):
+//   * E row r from B row r and the previous G, which every lane holds completely; all of E is then broadcast (36 shuffles);
+//   * right-looking Cholesky by columns: lane cc takes ONE reciprocal square root (no sqrt, no division anywhere on the
+//     chain), broadcasts it, every lane scales its entry of the column, the column is broadcast (<= 5 shuffles) and every lane
+//     updates the rest of its row;
+//   * after that every lane knows all of L and inverts it for itself (15 entries), which is also the G the next step needs.
+// The inputs of the next step are fetched while the current one runs.  status[0] = 1 + i when A is not positive definite.
+// History on a B200: one thread 7 us per keyframe; 36 threads through shared memory with 16 barrier-separated phases 3.9 us.
+__global__ void __launch_bounds__(32) k_md_factor(const double* __restrict__ Hpp, const double* __restrict__ Bsub, int Np,
                                                   double* __restrict__ Ginv, double* __restrict__ Esub, int* __restrict__ status) {
-  __shared__ double Gs[36];
-  __shared__ double Es[36];
-  __shared__ double As[36];
-  __shared__ double Bs[36];
-  __shared__ double Il[6];
-  const int k = threadIdx.x;
-  const bool act = k < 36;
-  const int r = k / 6, c = k - 6 * r;
-  if (act) Gs[k] = 0.0;
-  double hn = act ? Hpp[k] : 0.0, bn = act ? Bsub[k] : 0.0;
+  const int lane = threadIdx.x;
+  const int r = lane < 6 ? lane : 5;          // lanes 6..31 shadow row 5 (they only take part in the shuffles)
+  const bool own = lane < 6;
+  double G[6][6];                             // previous G = L^-1 (lower triangular), complete on every lane
+  MD_UNROLL
+  for (int a = 0; a < 6; ++a)
+    MD_UNROLL
+    for (int c = 0; c < 6; ++c) G[a][c] = 0.0;
+  double hn[6], bn[6];
+  MD_UNROLL
+  for (int c = 0; c < 6; ++c) {
+    hn[c] = Hpp[6 * r + c];
+    bn[c] = Bsub[6 * r + c];
+  }
   for (int i = 0; i < Np; ++i) {
-    const double h = hn;
-    if (act) Bs[k] = bn;
-    if (act && i + 1 < Np) {
-      hn = Hpp[36 * (size_t)(i + 1) + k];
-      bn = Bsub[36 * (size_t)(i + 1) + k];
+    double A[6], Bv[6];
+    MD_UNROLL
+    for (int c = 0; c < 6; ++c) {
+      A[c] = hn[c];
+      Bv[c] = bn[c];
     }
-    __syncthreads();
-    double e = 0.0;
-    if (act && i > 0)
-      for (int q = 0; q <= c; ++q) e += Bs[6 * r + q] * Gs[6 * c + q];   // G lower triangular: G'(q, c) = G(c, q), q <= c
-    if (act) Es[k] = e;
-    __syncthreads();
-    if (act) {
+    if (i + 1 < Np) {
+      MD_UNROLL
+      for (int c = 0; c < 6; ++c) {
+        hn[c] = Hpp[36 * (size_t)(i + 1) + 6 * r + c];
+        bn[c] = Bsub[36 * (size_t)(i + 1) + 6 * r + c];
+      }
+    }
+    // E row r = B row r * G'   (G lower triangular: G'(q, c) = G(c, q), q <= c); zero for the first keyframe (G = 0)
+    double Er[6];
+    MD_UNROLL
+    for (int c = 0; c < 6; ++c) {
+      double e = 0.0;
+      MD_UNROLL
+      for (int q = 0; q <= c; ++q) e += Bv[q] * G[c][q];
+      Er[c] = e;
+    }
+    // A row r (lower part) -= E row r . E row c, rows c <= r fetched from their lanes
+    MD_UNROLL
+    for (int c = 0; c < 6; ++c) {
+      double Ec[6];
+      MD_UNROLL
+      for (int q = 0; q < 6; ++q) Ec[q] = __shfl_sync(0xffffffffu, Er[q], c);
       double s = 0.0;
-      for (int q = 0; q < 6; ++q) s += Es[6 * r + q] * Es[6 * c + q];
-      As[k] = h - s;
+      MD_UNROLL
+      for (int q = 0; q < 6; ++q) s += Er[q] * Ec[q];
+      if (c <= r) A[c] -= s;
     }
-    __syncthreads();
-    // fp64 sqrt and division are long dependent instruction sequences and they sit on the chain: one reciprocal square root per
-    // column (il = 1 / L_cc), everything else multiplies by it
+    // right-looking Cholesky, column by column; L[a][c] (a > c) and il[c] = 1 / L[c][c] end up on every lane
+    double L[6][6], il[6];
+    MD_UNROLL
     for (int cc = 0; cc < 6; ++cc) {
-      if (k == 7 * cc) {
-        double d = As[7 * cc];
-        for (int q = 0; q < cc; ++q) d -= As[6 * cc + q] * As[6 * cc + q];
-        if (!(d > 0.0)) {
-          if (status[0] == 0) status[0] = 1 + i;
-          d = 1.0;
-        }
-        const double il = md_rsqrt(d);
-        Il[cc] = il;
-        As[7 * cc] = d * il;
+      double d = A[cc];                        // on lane cc: the pivot
+      if (lane == cc && !(d > 0.0)) {
+        if (status[0] == 0) status[0] = 1 + i;
+        d = 1.0;
       }
-      __syncthreads();
-      if (act && c == cc && r > cc) {
-        double s = As[6 * r + cc];
-        for (int q = 0; q < cc; ++q) s -= As[6 * r + q] * As[6 * cc + q];
-        As[6 * r + cc] = s * Il[cc];
-      }
-      __syncthreads();
+      const double ilc = __shfl_sync(0xffffffffu, md_rsqrt(d > 0.0 ? d : 1.0), cc);
+      il[cc] = ilc;
+      const double lrc = A[cc] * ilc;          // lanes r >= cc: L[r][cc]
+      MD_UNROLL
+      for (int a = cc + 1; a < 6; ++a) L[a][cc] = __shfl_sync(0xffffffffu, lrc, a);
+      MD_UNROLL
+      for (int c = cc + 1; c < 6; ++c)
+        if (c <= r) A[c] -= lrc * L[c][cc];
     }
-    if (k < 6) {   // column k of G = L^-1
-      for (int rr = 0; rr < k; ++rr) Gs[6 * rr + k] = 0.0;
-      Gs[7 * k] = Il[k];
-      for (int rr = k + 1; rr < 6; ++rr) {
+    // G = L^-1, complete on every lane: G[c][c] = il[c], G[a][c] = -il[a] sum_{q = c}^{a - 1} L[a][q] G[q][c]
+    MD_UNROLL
+    for (int c = 0; c < 6; ++c) {
+      MD_UNROLL
+      for (int a = 0; a < c; ++a) G[a][c] = 0.0;
+      G[c][c] = il[c];
+      MD_UNROLL
+      for (int a = c + 1; a < 6; ++a) {
         double s = 0.0;
-        for (int q = k; q < rr; ++q) s += As[6 * rr + q] * Gs[6 * q + k];
-        Gs[6 * rr + k] = -s * Il[rr];
+        MD_UNROLL
+        for (int q = c; q < a; ++q) s += L[a][q] * G[q][c];
+        G[a][c] = -s * il[a];
       }
     }
-    __syncthreads();
-    if (act) {
-      Ginv[36 * (size_t)i + k] = Gs[k];
-      Esub[36 * (size_t)i + k] = Es[k];
-    }
+    if (own)
+      MD_UNROLL
+      for (int c = 0; c < 6; ++c) {
+        double g = 0.0;                        // G[r][c] without indexing the register array by the lane
+        MD_UNROLL
+        for (int a = c; a < 6; ++a)
+          if (a == r) g = G[a][c];
+        Ginv[36 * (size_t)i + 6 * r + c] = g;
+        Esub[36 * (size_t)i + 6 * r + c] = Er[c];
+      }
   }
 }
 
@@ -418,7 +453,7 @@ inline void md_run(Launcher& L, const MdDims& d, const MdBuffers& b) {
   L.zero(b.Y, (size_t)d.K * d.ld * sizeof(double));
   L.zero(b.T, (size_t)d.ld * d.ld * sizeof(double));
   L(k_md_gather_sub, (36 * d.Np + 255) / 256, 1, 256, b.pose_pp_rowptr, b.pose_pp_idx, b.pose_pp_other, b.Hoff, d.Np, b.Bsub);
-  L(k_md_factor, 1, 1, 64, b.Hpp, (const double*)b.Bsub, d.Np, b.Ginv, b.Esub, b.status);
+  L(k_md_factor, 1, 1, 32, b.Hpp, (const double*)b.Bsub, d.Np, b.Ginv, b.Esub, b.status);
   L(k_md_sweep, (d.n3 + 127) / 128, 1, 128, b.edge_pose, b.edge_stride, b.lm_rowptr, b.HplL, (const double*)b.Ginv, (const double*)b.Esub,
     d.Np, d.n3, b.Y, d.ld);
   L(k_md_tile_k0, (d.nt + 63) / 64, 1, 64, b.edge_pose, b.edge_stride, b.lm_rowptr, d.Nl, d.nt, d.K, b.tile_k0);

@@ -24,6 +24,15 @@ struct EmuDim { unsigned x = 1, y = 1, z = 1; };
 static thread_local EmuDim threadIdx, blockIdx, blockDim, gridDim;
 static std::barrier<>* g_cta_bar = nullptr;
 static inline void __syncthreads() { g_cta_bar->arrive_and_wait(); }
+// warp shuffle, for CTAs of exactly one warp (k_md_factor): every thread deposits its value, all meet, every thread reads
+static double g_shfl_slots[32];
+static inline double __shfl_sync(unsigned, double v, int src) {
+  g_shfl_slots[threadIdx.x] = v;
+  g_cta_bar->arrive_and_wait();
+  const double r = g_shfl_slots[src];
+  g_cta_bar->arrive_and_wait();
+  return r;
+}
 
 #include "../semantic_slam_b200/csrc/ssb_marg_direct.cuh"
 

@@ -8,6 +8,8 @@ the identical host logic once over the CUDA back-end and once over the CPU oracl
 class (detections arrive as camera-frame centroids, e.g. from PlaneSegmentation.fit_planes)."""
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 
@@ -57,7 +59,14 @@ class SemanticGraphSLAM:
     max_keyframes_per_update = 10          # semantic_graph_slam.cpp:18
 
     def __init__(self, graph_slam, data_association, odom_information, cam_angle: float = 0.0,
-                 use_maha_dist: bool = False, max_iterations: int = 1024):
+                 use_maha_dist: bool = False, max_iterations: int = 1024, always_marginals: bool = False,
+                 marginals_kwargs=None):
+        # always_marginals: getAndSetLandmarkCov after EVERY optimise whatever the gate, as the reference does
+        # (semantic_graph_slam.cpp:89,181-205); False = only when the Mahalanobis gate will read the covariances
+        self.always_marginals_ = always_marginals
+        self.marginals_kwargs_ = dict(marginals_kwargs or {})   # e.g. method="g2o" for the oracle back-end
+        self.marginals_seconds = 0.0
+        self.marginals_calls = 0
         self.graph_slam_ = graph_slam
         self.data_ass_obj_ = data_association
         self.information_ = np.asarray(odom_information, dtype=np.float64)
@@ -145,8 +154,11 @@ class SemanticGraphSLAM:
             ids = sorted(self.landmark_nodes_)
             for lid in ids:   # the reference's association reads node->estimate() live (data_association.h:378)
                 self.data_ass_obj_.setLandmarkEstimate(lid, self.graph_slam_.get_point_xyz(self.landmark_nodes_[lid]))
-            if self.use_maha_dist_ and ids:                                   # getAndSetLandmarkCov :181-205
-                covs = self.graph_slam_.computeLandmarkMarginals([self.landmark_nodes_[lid] for lid in ids])
+            if (self.use_maha_dist_ or self.always_marginals_) and ids:       # getAndSetLandmarkCov :181-205
+                t0 = time.perf_counter()
+                covs = self.graph_slam_.computeLandmarkMarginals([self.landmark_nodes_[lid] for lid in ids], **self.marginals_kwargs_)
+                self.marginals_seconds += time.perf_counter() - t0
+                self.marginals_calls += 1
                 if covs is not None:
                     for lid, c in zip(ids, covs):
                         self.data_ass_obj_.setLandmarkCovs(lid, np.asarray(c, dtype=np.float32))

@@ -2515,10 +2515,13 @@ static int marginals_direct(ssb_graph* g, const int* vids, int n, double* out9n)
     double limit_gb = 16.0;
     if (const char* e = std::getenv("SSB_MARG_DIRECT_MAX_GB")) limit_gb = std::atof(e);
     const double need = 8.0 * ((double)d.K * d.ld + (double)d.ld * d.ld + 2.0 * ssb_md::TB * d.ld + 108.0 * d.Np);
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return -100;
-    const double held = 8.0 * (double)(g->md_Y.cap + g->md_T.cap);
-    if (need > limit_gb * 1e9 || need > 0.8 * ((double)free_b + held)) return -100;
+    if (need > limit_gb * 1e9) return -100;
+    if (need > 256e6) {   // only a large system is worth a cudaMemGetInfo (a driver round trip per call otherwise: once per frame)
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return -100;
+      const double held = 8.0 * (double)(g->md_Y.cap + g->md_T.cap);
+      if (need > 0.8 * ((double)free_b + held)) return -100;
+    }
   }
   if (!g->have_system) SSB_TRY(launch_linearize(g));   // else: the system built by the last optimize (g2o semantics)
   SSB_TRY(g->md_Bsub.ensure((size_t)36 * d.Np));

@@ -28,11 +28,17 @@ def _problem(n_kf, n_lm, seed, its, flip_every=2):
     o = oracle.OracleGraphSLAM(threads=1)
     ids = synth.load_graph(o, spec)
     o.optimize(its)
-    H, b, off = o.sparse_system()
-    H = sp.csr_matrix(H)
     vk = spec.vkind
     pose_v = [v for v in range(vk.size) if vk[v] == 0]
     lm_v = [v for v in range(vk.size) if vk[v] == 1]
+    return problem_from_oracle(o, ids, pose_v, lm_v, flip_every)
+
+
+def problem_from_oracle(o, ids, pose_v, lm_v, flip_every=2):
+    """pose_v / lm_v: positions in `ids` of the keyframe / landmark vertices, keyframes in chain order"""
+    H, b, off_by_id = o.sparse_system()
+    H = sp.csr_matrix(H)
+    off = {v: off_by_id[ids[v]] for v in list(pose_v) + list(lm_v)}
     Np, Nl = len(pose_v), len(lm_v)
 
     def blk(vr, vc, dr, dc):

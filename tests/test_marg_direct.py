@@ -112,6 +112,28 @@ def test_emulated_kernels_match_the_oracle(emulator, tmp_path, n_kf, n_lm, seed)
     assert np.abs(M - Mo).max() <= 1e-9 * np.abs(Mo).max(), log
 
 
+def test_emulated_kernels_with_repeated_edges(emulator, tmp_path):
+    """a landmark matched by two detections of one keyframe gives two edges between the same pair (it happens in the per-frame
+    stream): the sweep must add both records of a keyframe before moving on"""
+    pr = _problem(40, 8, 1, its=3)
+    rp, ep, Hl = pr["lm_rowptr"], pr["edge_pose"], pr["HplL"]
+    new_rp, new_ep, new_H = [0], [], []
+    for l in range(pr["Nl"]):
+        for e in range(rp[l], rp[l + 1]):
+            if (e % 3) == 0:                                    # every third record split into two unequal parts
+                new_ep += [ep[e], ep[e]]
+                new_H += [0.25 * Hl[e], 0.75 * Hl[e]]
+            else:
+                new_ep.append(ep[e])
+                new_H.append(Hl[e])
+        new_rp.append(len(new_ep))
+    ref_status, ref_M, _ = _run(emulator, pr, np.arange(pr["Nl"]), str(tmp_path))
+    pr2 = dict(pr, lm_rowptr=np.array(new_rp, np.int32), edge_pose=np.array(new_ep, np.int32), HplL=np.array(new_H))
+    status, M, log = _run(emulator, pr2, np.arange(pr["Nl"]), str(tmp_path))
+    assert status.tolist() == [0, 0] and ref_status.tolist() == [0, 0], log
+    assert np.abs(M - ref_M).max() <= 1e-12 * np.abs(ref_M).max()
+
+
 def test_emulated_kernels_flag_a_singular_system(emulator, tmp_path):
     pr = _problem(40, 8, 1, its=2)
     pr["Hll"][3] = 0.0                                          # a landmark whose block vanishes

@@ -140,3 +140,21 @@ def test_emulated_kernels_flag_a_singular_system(emulator, tmp_path):
     pr["HplL"][pr["lm_rowptr"][3]:pr["lm_rowptr"][4]] = 0.0
     status, M, log = _run(emulator, pr, np.arange(2), str(tmp_path))
     assert status[1] != 0, log
+
+
+def test_emulated_kernels_are_race_free_under_thread_sanitizer(tmp_path):
+    """the emulator gives every CUDA thread an OS thread and every __syncthreads() / shuffle a barrier, so ThreadSanitizer sees
+    exactly the happens-before edges the CUDA code has inside a CTA: a missing barrier between conflicting shared-memory (or
+    same-CTA global-memory) accesses would be reported as a data race"""
+    exe = str(tmp_path / "md_emulate_tsan")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=thread", "-o", exe, os.path.join(ROOT, "tests", "md_emulate.cpp")],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("ThreadSanitizer is not available: " + r.stderr[-200:])
+    pr = _problem(150, 30, 6, its=3)                            # 2 x 2 tiles: the tile product, both Gauss-Jordan branches
+    fin, fout = str(tmp_path / "p.bin"), str(tmp_path / "o.bin")
+    write_problem(pr, np.arange(pr["Nl"]), fin)
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=66")
+    out = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=900, env=env)
+    assert "ThreadSanitizer" not in out.stderr and out.returncode == 0, out.stderr[-2000:]
+    assert "status 0 0" in out.stdout

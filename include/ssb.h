@@ -430,6 +430,10 @@ int ssb_assoc_set_landmark_cov(ssb_assoc* a, int id, const float cov[9]);
 /* data_association::getMappedLandmarks  :399 */
 int ssb_assoc_num_landmarks(const ssb_assoc* a);
 int ssb_assoc_get_landmark(const ssb_assoc* a, int id, ssb_landmark_obs* out);
+/* Test hook: the two float 3 x 3 inverses of the association step (row-major in and out).  kind 0 = the fixed-size
+ * Eigen::Matrix3f::inverse() of `information = covariance.inverse()` (semantic_graph_slam.cpp:170, cofactors), kind 1 = the
+ * dynamic-size Eigen::MatrixXf::inverse() of the Mahalanobis gate's Q (data_association.h:175-184, PartialPivLU + solve). */
+int ssb_assoc_inverse3(int kind, const float a[9], float r[9]);
 
 /* ------------------------------------------------------------------------------------------- */
 const char* ssb_last_error(void);

@@ -116,6 +116,46 @@ def dist(x1, x2, y1, y2, z1, z2):
     return sqrtf(f32(f32(f32(dx * dx) + f32(dy * dy)) + f32(dz * dz)))
 
 
+def inv3_lu(a):
+    """Eigen::MatrixXf::inverse() of the dynamic-size Q of the Mahalanobis gate (data_association.h:175-184):
+    partialPivLu().inverse() = solve(Identity), float.  PartialPivLU::unblocked_lu: first largest |entry| of the column is
+    the pivot, whole rows swapped, sub-column divided by the pivot, trailing a(i,j) -= l(i) u(j) (two roundings).  Then
+    X = P I, unit-lower solve and upper solve in Eigen's column-oriented form (TriangularSolverMatrix.h): x_i times the
+    reciprocal of the diagonal, then x_r -= x_i t(r,i) for the rows still to come."""
+    A = np.array(a, dtype=f32).reshape(3, 3).copy()
+    X = np.eye(3, dtype=f32)
+    piv = [0, 1, 2]
+    for k in range(3):
+        best, big = k, abs(A[k, k])
+        for i in range(k + 1, 3):
+            if abs(A[i, k]) > big:
+                best, big = i, abs(A[i, k])
+        piv[k] = best
+        if big != 0:
+            if best != k:
+                A[[k, best]] = A[[best, k]]
+            for i in range(k + 1, 3):
+                A[i, k] = f32(A[i, k] / A[k, k])
+        for i in range(k + 1, 3):
+            for j in range(k + 1, 3):
+                A[i, j] = f32(A[i, j] - f32(A[i, k] * A[k, j]))
+    for k in range(3):
+        if piv[k] != k:
+            X[[k, piv[k]]] = X[[piv[k], k]]
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        for j in range(3):
+            for i in range(3):
+                b = X[i, j]
+                for q in range(i + 1, 3):
+                    X[q, j] = f32(X[q, j] - f32(b * A[q, i]))
+            for i in (2, 1, 0):
+                X[i, j] = f32(X[i, j] * f32(f32(1.0) / A[i, i]))
+                b = X[i, j]
+                for q in range(i):
+                    X[q, j] = f32(X[q, j] - f32(b * A[q, i]))
+    return X
+
+
 def inv3(a):
     """Eigen::Matrix3f::inverse(): cofactors, determinant along column 0"""
     a = np.asarray(a, dtype=f32).reshape(3, 3)
@@ -222,7 +262,7 @@ class OracleDataAssociation:
                 found = True
                 expected = l.node_estimate.astype(f32)
                 if self.use_maha_dist:
-                    Qi = inv3(np.array([[f32(l.covariance[r, c] + self.Q[r, c]) for c in range(3)] for r in range(3)], dtype=f32))
+                    Qi = inv3_lu(np.array([[f32(l.covariance[r, c] + self.Q[r, c]) for c in range(3)] for r in range(3)], dtype=f32))
                     z = [f32(actual[k] - expected[k]) for k in range(3)]
                     t = [f32(f32(f32(z[0] * Qi[0, c]) + f32(z[1] * Qi[1, c])) + f32(z[2] * Qi[2, c])) for c in range(3)]
                     distance = f32(f32(f32(t[0] * z[0]) + f32(t[1] * z[1])) + f32(t[2] * z[2]))

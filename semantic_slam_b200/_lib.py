@@ -77,6 +77,7 @@ SYMBOLS = [
     "ssb_kmeans", "ssb_project_hull", "ssb_cluster_default_opts", "ssb_cluster_planes",
     "ssb_segment_planar_surfaces", "ssb_assoc_default_opts", "ssb_assoc_create", "ssb_assoc_destroy", "ssb_assoc_find_matches",
     "ssb_assoc_set_landmark_estimate", "ssb_assoc_set_landmark_cov", "ssb_assoc_num_landmarks", "ssb_assoc_get_landmark",
+    "ssb_assoc_inverse3",
     "ssb_last_error", "ssb_build_info", "ssb_graph_stream", "ssb_graph_snapshot", "ssb_graph_restore",
 ]
 

@@ -126,6 +126,70 @@ void inv3_cofactor(const float* a, float* r) {
   r[8] = cof(2, 2) * invdet;
 }
 
+// Eigen::MatrixXf::inverse() — what `Q.inverse()` is for the DYNAMIC-size Q of the Mahalanobis gate
+// (data_association.h:175-184): compute_inverse<.., Dynamic> = partialPivLu().inverse() = solve(Identity), in float:
+//   PartialPivLU::unblocked_lu (sizes <= 16): per column the FIRST largest |entry| is the pivot, whole rows are swapped,
+//     the column below the pivot is DIVIDED by it, the trailing block gets  a(i,j) -= l(i) * u(j)  (product rounded, then
+//     the difference: no FMA, the reference builds with SSE flags only);
+//   X = P * Identity; unit-lower solve, then upper solve, both column-oriented (TriangularSolverMatrix.h, column-major
+//     triangle): x_i is MULTIPLIED by the reciprocal of the diagonal (1 for the unit triangle), then  x_r -= x_i * t(r,i)
+//     for the rows still to come (below for the lower solve, above for the upper one).
+// a, r: 3 x 3 row-major.  A zero pivot column is left undivided like Eigen does (the reciprocal is then inf).
+void inv3_partial_piv_lu(const float* a, float* r) {
+  float A[3][3], X[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      A[i][j] = a[3 * i + j];
+      X[i][j] = i == j ? 1.0f : 0.0f;
+    }
+  int piv[3];
+  for (int k = 0; k < 3; ++k) {
+    int best = k;
+    float big = std::fabs(A[k][k]);
+    for (int i = k + 1; i < 3; ++i)
+      if (std::fabs(A[i][k]) > big) {
+        big = std::fabs(A[i][k]);
+        best = i;
+      }
+    piv[k] = best;
+    if (big != 0.0f) {
+      if (best != k)
+        for (int j = 0; j < 3; ++j) std::swap(A[k][j], A[best][j]);
+      for (int i = k + 1; i < 3; ++i) A[i][k] = A[i][k] / A[k][k];
+    }
+    for (int i = k + 1; i < 3; ++i)
+      for (int j = k + 1; j < 3; ++j) {
+        const float prod = A[i][k] * A[k][j];
+        A[i][j] = A[i][j] - prod;
+      }
+  }
+  for (int k = 0; k < 3; ++k)
+    if (piv[k] != k)
+      for (int j = 0; j < 3; ++j) std::swap(X[k][j], X[piv[k]][j]);
+  for (int j = 0; j < 3; ++j) {
+    // unit lower
+    for (int i = 0; i < 3; ++i) {
+      const float b = X[i][j] * 1.0f;
+      for (int q = i + 1; q < 3; ++q) {
+        const float prod = b * A[q][i];
+        X[q][j] = X[q][j] - prod;
+      }
+    }
+    // upper, from the last row up
+    for (int i = 2; i >= 0; --i) {
+      const float inv = 1.0f / A[i][i];
+      X[i][j] = X[i][j] * inv;
+      const float b = X[i][j];
+      for (int q = 0; q < i; ++q) {
+        const float prod = b * A[q][i];
+        X[q][j] = X[q][j] - prod;
+      }
+    }
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r[3 * i + j] = X[i][j];
+}
+
 struct Landmark {
   int id, type, plane_type;
   float pose[3], local_pose[3], cov[9], normal[4];
@@ -227,6 +291,15 @@ int ssb_assoc_set_landmark_cov(ssb_assoc* a, int id, const float cov[9]) {
   std::memcpy(a->landmarks[id].cov, cov, 9 * sizeof(float));
   return SSB_OK;
 }
+int ssb_assoc_inverse3(int kind, const float a[9], float r[9]) {
+  if (!a || !r || (kind != 0 && kind != 1)) return SSB_ERR_INVALID;
+  if (kind == 0)
+    inv3_cofactor(a, r);
+  else
+    inv3_partial_piv_lu(a, r);
+  return SSB_OK;
+}
+
 int ssb_assoc_get_landmark(const ssb_assoc* a, int id, ssb_landmark_obs* out) {
   if (!a || !out || id < 0 || id >= (int)a->landmarks.size()) return SSB_ERR_INVALID;
   const Landmark& l = a->landmarks[id];
@@ -327,7 +400,7 @@ int ssb_assoc_find_matches(ssb_assoc* a, const ssb_detection* dets, int n, const
         // Q = H sigma H' + Q_ with H = I; distance = z' Q^-1 z on the xyz components (H5)
         float Q[9], Qi[9], z[3];
         for (int k = 0; k < 9; ++k) Q[k] = l.cov[k] + a->Q[k];
-        inv3_cofactor(Q, Qi);
+        inv3_partial_piv_lu(Q, Qi);   // Q is a dynamic MatrixXf in the reference: LU, not the fixed-size cofactor formula
         for (int k = 0; k < 3; ++k) z[k] = actual[k] - expected[k];
         float t[3];
         for (int c = 0; c < 3; ++c) t[c] = (z[0] * Qi[c] + z[1] * Qi[3 + c]) + z[2] * Qi[6 + c];

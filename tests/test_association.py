@@ -202,3 +202,34 @@ def test_golden_association_stream(tag, kw):
         assert np.array_equal(np.array(ids, dtype=np.int32), gold[tag + "_ids"]), cls.__name__
         assert np.array_equal(np.array(new, dtype=bool), gold[tag + "_new"]), cls.__name__
         assert np.array_equal(np.array(pose, dtype=np.float32), gold[tag + "_pose"]), cls.__name__
+
+
+def test_the_two_float_inverses_product_vs_oracle():
+    """Eigen::Matrix3f::inverse() (cofactors: `information = covariance.inverse()`) and Eigen::MatrixXf::inverse() (PartialPivLU +
+    solve(Identity): the Mahalanobis gate's dynamic-size Q): the product's C++ against the oracle's numpy-float32 restatement bit
+    for bit, both close to the float64 inverse; matrices that need no / one / two row exchanges in the LU"""
+    import ctypes as C
+    from semantic_slam_b200 import _lib
+    from oracle.association import inv3, inv3_lu
+    L = _lib.lib()
+    L.ssb_assoc_inverse3.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(7)
+    mats = []
+    for _ in range(60):
+        B = rng.normal(size=(3, 3))
+        mats.append(B @ B.T + 0.05 * np.eye(3))                         # SPD, like Q = H sigma H' + Q_
+    for _ in range(60):
+        mats.append(rng.normal(size=(3, 3)))                             # general: pivoting happens
+    mats.append(np.array([[0.0, 2.0, 1.0], [1.0, 0.0, 3.0], [4.0, 1.0, 0.0]]))   # zero leading entry: exchanges in both steps
+    swaps = 0
+    for M in mats:
+        a = np.ascontiguousarray(M, dtype=np.float32)
+        swaps += int(np.argmax(np.abs(a[:, 0])) != 0)
+        for kind, ofun in ((0, inv3), (1, inv3_lu)):
+            r = np.zeros((3, 3), dtype=np.float32)
+            assert L.ssb_assoc_inverse3(kind, a.ctypes.data, r.ctypes.data) == 0
+            o = np.asarray(ofun(a), dtype=np.float32)
+            assert np.array_equal(r.view(np.uint32), o.view(np.uint32)), (kind, M)
+            ref = np.linalg.inv(a.astype(np.float64))
+            assert np.abs(r - ref).max() <= 2e-4 * np.abs(ref).max() * np.linalg.cond(a.astype(np.float64))
+    assert swaps > 20
